@@ -1,0 +1,82 @@
+// hc_context.h — device-side state of one CUDA layer instance (what GPUOCLLayer keeps in m_scene / m_rays / m_screen,
+// reference hydra_drv/GPUOCLLayer.h:300-470), shared by the translation units of libhydracore_b200.so.
+#pragma once
+#include "../../include/hydracore_cuda.h"
+#include "hc_layout.h"
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+void hc_set_error(const char* msg);
+int  hc_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define HC_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return hc_cuda_fail(e_, #call, __FILE__, __LINE__); } while (0)
+#define HC_REQUIRE(cond, code, msg) do { if (!(cond)) { hc_set_error(msg); return (code); } } while (0)
+
+struct HcHit;
+
+struct HcDevBuf
+{
+  void*    ptr = nullptr;
+  uint64_t bytes = 0;
+};
+
+// per-path wavefront state, structure of arrays, double buffered by the compacting shade kernel (see hc_path.cuh)
+struct HcPathBuffers
+{
+  float4* rpos[2]   = { nullptr, nullptr };   // xyz = ray origin, w = misPrev.matSamplePdf
+  float4* rdir[2]   = { nullptr, nullptr };   // xyz = ray direction, w = as_float(flags)
+  float4* thr[2]    = { nullptr, nullptr };   // xyz = path throughput, w = as_float(pixel index | specular bit 31)
+  float4* accum[2]  = { nullptr, nullptr };   // xyz = radiance gathered so far, w = unused
+  uint2*  rng[2]    = { nullptr, nullptr };   // RandomGen state (crandom.h:10-17)
+  unsigned* qpos[2] = { nullptr, nullptr };   // QMC sample index of the path (PT_QMC only)
+  HcHit*  hits      = nullptr;
+  float4* spos      = nullptr;                // shadow ray origin, w = max distance (0 = no shadow ray)
+  float4* sdir      = nullptr;                // shadow ray direction, w = unused
+  float4* sexp      = nullptr;                // xyz = throughput * unshadowed explicit light, w = as_float(slot of the path in the NEXT state buffer or ~0)
+  int64_t capacity  = 0;
+};
+
+struct hc_ctx
+{
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+  cudaDeviceProp prop{};
+  int          smCount = 0;
+
+  HcDevBuf storage[HC_STORAGE_COUNT];
+  HcDevBuf globals;                        // EngineGlobals + tables blob
+  std::vector<unsigned char> globalsHead;  // host copy of the first HC_EG_HEAD_BYTES bytes
+  HcDevBuf bvhNodes, bvhTris;              // tree 0 (opaque geometry)
+  int      nodesNum = 0, trif4Num = 0, haveInst = 1, bvhDepthBound = 0;
+  HcDevBuf instMatrices, instLightIds;
+  int      numInst = 0;
+
+  int width = 0, height = 0;
+  HcDevBuf fbSum;                          // float4 per pixel: SUM of samples
+  double   spp = 0.0;
+
+  // ray-casting scratch (hc_trace_* with HC_HOST buffers)
+  HcDevBuf scratchRays, scratchOut;
+  HcDevBuf counters;                       // device: [0] persistent-thread ray counter, [1..] compaction counters
+  float    lastTraceMs = 0.0f;
+
+  // path tracing
+  HcPathBuffers paths;
+  int      seed = 0;
+  bool     ptReady = false;
+  int      tileSize = 32, rank = 0, worldSize = 1;
+  HcDevBuf pixelRng;                       // uint2 per pixel: generator state carried across passes (trace.cl:6-13)
+  HcDevBuf qmcTable;                       // Niederreiter table, 11 x 31 uint (qmc_sobol_niederreiter.cpp:179-186)
+  unsigned passCounter = 0;
+
+  hc_stats stats{};
+  int traceGrid = 0;
+};
+
+int hc_buf_reserve(hc_ctx* ctx, HcDevBuf& b, uint64_t bytes);   // grow-only
+void hc_buf_free(HcDevBuf& b);
+
+void hc_path_free(hc_ctx* ctx);   // hc_path.cu
+int  hc_launch_trace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, HcHit* hits, unsigned char* vis);   // hc_api.cu

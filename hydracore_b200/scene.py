@@ -1,0 +1,484 @@
+"""Scene packing into the reference's blob formats and synthetic scene generators.
+
+This plays the part of RenderDriverRTE::UpdateMesh/UpdateMaterial/UpdateLight/UpdateCamera + IHWLayerDataAssembler for
+tests and benchmarks: it produces exactly what the CUDA layer (and the CPU oracle) receive through the IHWLayer boundary —
+five storages ("textures", "textures_aux", "geom", "materials", "pdfs"), the EngineGlobals + tables blob, the flat BVH4,
+inverse instance matrices and the instance -> light table.  Formats cited per function (reference file:line).
+"""
+import math
+import numpy as np
+
+from . import layout as L
+from .layer import BvhBuilder
+
+C = L.C
+INVALID_TEXTURE = -2            # 0xFFFFFFFE as int32 (cglobals.h:16)
+
+
+def _round_blocks(elems, block):            # roundBlocks, cglobals.h:628-634
+    if elems < block:
+        return block
+    return ((elems + block - 1)//block)*block
+
+
+def _as_f(i):
+    return np.array([i], np.int32).view(np.float32)[0]
+
+
+# ---------------------------------------------------------------------------------------------------------------- meshes
+class Mesh:
+    """Triangle mesh as HydraAPI hands it to UpdateMesh (HRMeshDriverInput): pos4f, norm4f, tan4f, texcoord2f, indices, matIndices."""
+
+    def __init__(self, pos, idx, norm=None, uv=None, mat=None, tan=None):
+        self.pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        self.idx = np.ascontiguousarray(idx, np.int32).reshape(-1, 3)
+        n = self.pos.shape[0]
+        self.norm = _vertex_normals(self.pos, self.idx) if norm is None else np.ascontiguousarray(norm, np.float32).reshape(n, 3)
+        self.uv = np.zeros((n, 2), np.float32) if uv is None else np.ascontiguousarray(uv, np.float32).reshape(n, 2)
+        self.mat = np.zeros(self.idx.shape[0], np.int32) if mat is None else np.ascontiguousarray(mat, np.int32).reshape(-1)
+        self.tan = np.zeros((n, 4), np.float32) if tan is None else np.ascontiguousarray(tan, np.float32).reshape(n, 4)
+
+    @property
+    def tri_count(self):
+        return self.idx.shape[0]
+
+    def vert4f(self):
+        v = np.zeros((self.pos.shape[0], 4), np.float32)
+        v[:, :3] = self.pos
+        v[:, 3] = 1.0
+        return v
+
+    def pack(self):
+        """PlainMesh blob: 64-byte header + pos4f(w=u) + norm4f(w=v) + tan4f + indices + matIndices + shadowOffsets,
+        every array padded to 16 bytes, offsets in float4 units from the header (RenderDriverRTE.cpp:1059-1159, cfetch.h:1038-1119)."""
+        nv, nt = self.pos.shape[0], self.idx.shape[0]
+        align = 16
+        header_size = _round_blocks(64, align)
+        pos_off = header_size
+        pos_size = _round_blocks(16*nv, align)
+        norm_off = pos_off + pos_size
+        norm_size = _round_blocks(16*nv, align)
+        texc_off = norm_off + norm_size
+        tang_off = texc_off
+        tang_size = _round_blocks(16*nv, align)
+        ind_off = tang_off + tang_size
+        ind_size = _round_blocks(nt*3*4, align)
+        mind_off = ind_off + ind_size
+        mind_size = _round_blocks(nt*4, align)
+        soff_off = mind_off + mind_size
+        soff_size = _round_blocks(nt*4, align)
+        total = soff_off + soff_size
+        blob = np.zeros(total, np.uint8)
+        hdr = np.zeros(16, np.int32)
+        hdr[0] = pos_off//16      # vPosOffset
+        hdr[1] = norm_off//16     # vNormOffset
+        hdr[2] = texc_off//16     # vTexCoordOffset
+        hdr[3] = ind_off//16      # vIndicesOffset
+        hdr[4] = nv               # vPosNum
+        hdr[5] = nv               # vNormNum
+        hdr[6] = nv               # vTexCoordNum
+        hdr[7] = nt*3             # tIndicesNum
+        hdr[8] = mind_off//16     # mIndicesOffset
+        hdr[9] = nt               # mIndicesNum
+        hdr[10] = tang_off//16    # vTangentOffset
+        hdr[11] = nv              # vTangentNum
+        hdr[12] = total           # totalBytesNum
+        hdr[13] = soff_off//16    # polyShadowOffset
+        blob[0:64] = hdr.view(np.uint8)
+        p4 = np.zeros((nv, 4), np.float32)
+        p4[:, :3] = self.pos
+        p4[:, 3] = self.uv[:, 0]
+        n4 = np.zeros((nv, 4), np.float32)
+        n4[:, :3] = self.norm
+        n4[:, 3] = self.uv[:, 1]
+        blob[pos_off:pos_off + 16*nv] = p4.view(np.uint8).reshape(-1)
+        blob[norm_off:norm_off + 16*nv] = n4.view(np.uint8).reshape(-1)
+        blob[tang_off:tang_off + 16*nv] = self.tan.view(np.uint8).reshape(-1)
+        blob[ind_off:ind_off + nt*12] = self.idx.view(np.uint8).reshape(-1)
+        blob[mind_off:mind_off + nt*4] = self.mat.view(np.uint8).reshape(-1)
+        blob[soff_off:soff_off + nt*4] = self.shadow_offsets().view(np.uint8).reshape(-1)
+        return blob
+
+    def shadow_offsets(self):
+        """CalcAuxShadowRaysOffsets (RenderDriverRTE.cpp:990-1056): min(0.05*sqrt(area), 0.00025*bboxMax) for smooth-shaded tris, else 0."""
+        A, B, Cc = self.pos[self.idx[:, 0]], self.pos[self.idx[:, 1]], self.pos[self.idx[:, 2]]
+        ext = (self.pos[self.idx.reshape(-1)].max(0) - self.pos[self.idx.reshape(-1)].min(0)).astype(np.float32)
+        mesh_max = np.float32(0.00025)*ext.max()
+        crpd = np.cross(A - B, A - Cc).astype(np.float32)
+        ln = np.sqrt((crpd*crpd).sum(1)).astype(np.float32)
+        fn = crpd/np.maximum(ln, np.float32(1e-30))[:, None]
+        diff = np.zeros(self.idx.shape[0], np.float32)
+        for k in range(3):
+            nk = self.norm[self.idx[:, k]]
+            d = fn - nk
+            diff += np.sqrt((d*d).sum(1)).astype(np.float32)
+        off = np.minimum(np.float32(0.05)*np.sqrt(ln*np.float32(0.5)), mesh_max).astype(np.float32)
+        return np.where(diff > np.float32(0.001), off, np.float32(0.0)).astype(np.float32)
+
+
+def _vertex_normals(pos, idx):
+    fn = np.cross(pos[idx[:, 1]] - pos[idx[:, 0]], pos[idx[:, 2]] - pos[idx[:, 0]])
+    n = np.zeros_like(pos)
+    for k in range(3):
+        np.add.at(n, idx[:, k], fn)
+    ln = np.sqrt((n*n).sum(1))
+    ln[ln == 0] = 1.0
+    return (n/ln[:, None]).astype(np.float32)
+
+
+def grid_mesh(nx, ny, size=10.0, amplitude=0.35, seed=1234, mat_blocks=None, flat=False):
+    """Displaced nx x ny-quad grid in the XZ plane (2*nx*ny triangles): the synthetic "1M-triangle mesh" is grid_mesh(708, 707)."""
+    rng = np.random.RandomState(seed)
+    xs = np.linspace(-0.5*size, 0.5*size, nx + 1, dtype=np.float32)
+    zs = np.linspace(-0.5*size, 0.5*size, ny + 1, dtype=np.float32)
+    X, Z = np.meshgrid(xs, zs)
+    k = 2.0*math.pi/size
+    Y = (amplitude*(np.sin(3.0*k*X)*np.cos(2.0*k*Z) + 0.5*np.sin(7.0*k*X + 1.3)*np.sin(5.0*k*Z + 0.7))
+         + 0.15*amplitude*rng.standard_normal(X.shape)).astype(np.float32)
+    pos = np.stack([X, Y, Z], -1).reshape(-1, 3).astype(np.float32)
+    uv = np.stack([(X/size + 0.5), (Z/size + 0.5)], -1).reshape(-1, 2).astype(np.float32)
+    i0 = (np.arange(ny)[:, None]*(nx + 1) + np.arange(nx)[None, :]).reshape(-1)
+    tri = np.empty((nx*ny, 2, 3), np.int64)
+    tri[:, 0] = np.stack([i0, i0 + nx + 1, i0 + 1], -1)
+    tri[:, 1] = np.stack([i0 + 1, i0 + nx + 1, i0 + nx + 2], -1)
+    idx = tri.reshape(-1, 3).astype(np.int32)
+    mat = None
+    if mat_blocks is not None:
+        # material id by contiguous triangle block: mat_blocks = [(fraction, matId), ...]
+        nt = idx.shape[0]
+        mat = np.zeros(nt, np.int32)
+        start = 0
+        for frac, mid in mat_blocks:
+            end = min(nt, start + int(round(frac*nt)))
+            mat[start:end] = mid
+            start = end
+        mat[start:] = mat_blocks[-1][1]
+    m = Mesh(pos, idx, uv=uv, mat=mat)
+    if flat:
+        m.norm[:] = np.array([0, 1, 0], np.float32)
+    return m
+
+
+def quad_mesh(sx, sz, y=0.0, mat_id=0, flip=False):
+    """Rectangle in the XZ plane, half sizes (sx, sz), normal +Y (or -Y when flip)."""
+    pos = np.array([[-sx, y, -sz], [sx, y, -sz], [sx, y, sz], [-sx, y, sz]], np.float32)
+    idx = np.array([[0, 2, 1], [0, 3, 2]], np.int32) if not flip else np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    nrm = np.tile(np.array([[0, -1.0 if flip else 1.0, 0]], np.float32), (4, 1))
+    uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+    return Mesh(pos, idx, norm=nrm, uv=uv, mat=np.full(2, mat_id, np.int32))
+
+
+def box_mesh(hx, hy, hz, mat_ids=(0, 0, 0, 0, 0, 0), inward=True):
+    """Axis-aligned box of half sizes (hx, hy, hz), 12 triangles, flat normals; inward=True gives a room (Cornell-box style)."""
+    faces = []
+    s = -1.0 if inward else 1.0
+    defs = [((1, 0, 0), (0, 1, 0), (0, 0, 1)), ((-1, 0, 0), (0, 0, 1), (0, 1, 0)), ((0, 1, 0), (0, 0, 1), (1, 0, 0)),
+            ((0, -1, 0), (1, 0, 0), (0, 0, 1)), ((0, 0, 1), (1, 0, 0), (0, 1, 0)), ((0, 0, -1), (0, 1, 0), (1, 0, 0))]
+    h = np.array([hx, hy, hz], np.float32)
+    pos, idx, nrm, uv, mat = [], [], [], [], []
+    for f, (n, u, v) in enumerate(defs):
+        n, u, v = np.array(n, np.float32), np.array(u, np.float32), np.array(v, np.float32)
+        c = n*h
+        corners = [c - u*h - v*h, c + u*h - v*h, c + u*h + v*h, c - u*h + v*h]
+        b = len(pos)
+        pos += corners
+        nrm += [s*n]*4
+        uv += [[0, 0], [1, 0], [1, 1], [0, 1]]
+        tri = [[b, b + 1, b + 2], [b, b + 2, b + 3]]
+        if inward:
+            tri = [[t[0], t[2], t[1]] for t in tri]
+        idx += tri
+        mat += [mat_ids[f]]*2
+        faces.append(f)
+    return Mesh(np.array(pos, np.float32), np.array(idx, np.int32), norm=np.array(nrm, np.float32), uv=np.array(uv, np.float32),
+                mat=np.array(mat, np.int32))
+
+
+def sphere_mesh(radius, nu, nv, mat_id=0):
+    """UV sphere with smooth normals, 2*nu*(nv-1) triangles."""
+    th = np.linspace(0, math.pi, nv + 1)
+    ph = np.linspace(0, 2*math.pi, nu + 1)
+    T, P = np.meshgrid(th, ph, indexing="ij")
+    n = np.stack([np.sin(T)*np.cos(P), np.cos(T), np.sin(T)*np.sin(P)], -1).reshape(-1, 3).astype(np.float32)
+    pos = (radius*n).astype(np.float32)
+    uv = np.stack([P/(2*math.pi), T/math.pi], -1).reshape(-1, 2).astype(np.float32)
+    idx = []
+    for i in range(nv):
+        for j in range(nu):
+            a = i*(nu + 1) + j
+            b = a + nu + 1
+            if i != 0:
+                idx.append([a, a + 1, b])
+            if i != nv - 1:
+                idx.append([a + 1, b + 1, b])
+    idx = np.array(idx, np.int32)
+    return Mesh(pos, idx, norm=n, uv=uv, mat=np.full(idx.shape[0], mat_id, np.int32))
+
+
+# ---------------------------------------------------------------------------------------------------------------- matrices
+def translate(x, y, z):
+    m = np.eye(4, dtype=np.float32)
+    m[:3, 3] = (x, y, z)
+    return m
+
+
+def scale(x, y, z):
+    return np.diag(np.array([x, y, z, 1.0], np.float32))
+
+
+def rotate_y(a):
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[c, 0, s, 0], [0, 1, 0, 0], [-s, 0, c, 0], [0, 0, 0, 1]], np.float32)
+
+
+def rotate_x(a):
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[1, 0, 0, 0], [0, c, -s, 0], [0, s, c, 0], [0, 0, 0, 1]], np.float32)
+
+
+def look_at(eye, center, up):                    # lookAt, cglobals.h:1006-1038 (row-major numpy; stored as columns below)
+    eye, center, up = (np.asarray(v, np.float64) for v in (eye, center, up))
+    z = eye - center
+    z /= np.linalg.norm(z)
+    x = np.cross(up, z)
+    y = np.cross(z, x)
+    x /= np.linalg.norm(x)
+    y /= np.linalg.norm(y)
+    m = np.eye(4)
+    m[0, :3], m[1, :3], m[2, :3] = x, y, z
+    m[:3, 3] = (-x.dot(eye), -y.dot(eye), -z.dot(eye))
+    return m
+
+
+def perspective(fov_deg, aspect, z_near, z_far):  # OpenGL frustum (LiteMath perspectiveMatrix)
+    ymax = z_near*math.tan(fov_deg*math.pi/360.0)
+    xmax = ymax*aspect
+    m = np.zeros((4, 4))
+    m[0, 0] = z_near/xmax
+    m[1, 1] = z_near/ymax
+    m[2, 2] = -(z_far + z_near)/(z_far - z_near)
+    m[2, 3] = -2.0*z_far*z_near/(z_far - z_near)
+    m[3, 2] = -1.0
+    return m
+
+
+def _cols(m):
+    """4x4 row-major numpy matrix -> 16 floats in column storage (float4x4::m_col, make_float4x4 cglobals.h:790-798)."""
+    return np.ascontiguousarray(np.asarray(m, np.float64).T, np.float32).reshape(16)
+
+
+# ---------------------------------------------------------------------------------------------------------------- scene
+class Camera:
+    def __init__(self, pos=(0, 0, 15), look_at=(0, 0, 0), up=(0, 1, 0), fov=45.0, near=0.1, far=1000.0, dof=False, lens_radius=0.0):
+        self.pos, self.look_at, self.up, self.fov, self.near, self.far = pos, look_at, up, fov, near, far
+        self.dof, self.lens_radius = dof, lens_radius
+
+
+class Scene:
+    """Host-side scene description -> blobs.  See materials.py for PlainMaterial / PlainLight packing."""
+
+    def __init__(self, width, height, camera=None):
+        self.width, self.height = int(width), int(height)
+        self.camera = camera or Camera()
+        self.meshes = []          # Mesh
+        self.instances = []       # (meshId, 4x4 row-major matrix, lightId or -1)
+        self.materials = []       # list of 192-float PlainMaterial nodes (a material may span several consecutive nodes)
+        self.material_ids = []    # matId -> index of its head node in self.materials
+        self.lights = []          # list of 128-float PlainLight
+        self.textures = []        # list of (w, h, rgba8 ndarray) ; texture id 0 is reserved ("no texture")
+        self.varsI = np.zeros(64, np.int32)
+        self.varsF = np.zeros(64, np.float32)
+        self.flags = 0
+        self.ms_tables = None     # (ggx u16[64*64], transp u16[64*64*64]) baked tables (bakeBrdfEnergy/MSTables*.cpp), optional
+        self.varsF[C["HRT_ABLOW_SCALE_X"]] = 1.0      # AllRenderVarialbes ctor, IHWLayer.h:25-35
+        self.varsF[C["HRT_ABLOW_SCALE_Y"]] = 1.0
+        self.varsI[C["HRT_SHADOW_MATTE_BACK"]] = INVALID_TEXTURE
+        self.varsF[C["HRT_IMAGE_GAMMA"]] = 2.2
+        self.varsF[C["HRT_TEXINPUT_GAMMA"]] = 2.2
+        self.set_trace_depth(5, 3)
+
+    def set_trace_depth(self, trace_depth, diff_trace_depth):
+        """XML trace_depth / diff_trace_depth are stored +1 (RenderDriverRTE.cpp:317-321)."""
+        self.varsI[C["HRT_TRACE_DEPTH"]] = trace_depth + 1
+        self.varsI[C["HRT_DIFFUSE_TRACE_DEPTH"]] = diff_trace_depth + 1
+
+    def add_mesh(self, mesh):
+        self.meshes.append(mesh)
+        return len(self.meshes) - 1
+
+    def add_instance(self, mesh_id, matrix=None, light_id=-1):
+        self.instances.append((mesh_id, np.eye(4, dtype=np.float32) if matrix is None else np.asarray(matrix, np.float32), light_id))
+        return len(self.instances) - 1
+
+    def add_material(self, nodes):
+        """nodes: one PlainMaterial (192 floats) or a list of consecutive nodes (blend trees reference children by relative offset)."""
+        nodes = [nodes] if isinstance(nodes, np.ndarray) and nodes.ndim == 1 else list(nodes)
+        head = len(self.materials)
+        self.materials += [np.ascontiguousarray(n, np.float32).reshape(192) for n in nodes]
+        self.material_ids.append(head)
+        return len(self.material_ids) - 1
+
+    def add_light(self, plain_light):
+        self.lights.append(np.ascontiguousarray(plain_light, np.float32).reshape(128))
+        return len(self.lights) - 1
+
+    def add_texture_rgba8(self, rgba):
+        """Texture ids start at 1; id 0 means "white" (sample2D, cfetch.h:654-655)."""
+        rgba = np.ascontiguousarray(rgba, np.uint8)
+        assert rgba.ndim == 3 and rgba.shape[2] == 4
+        self.textures.append(rgba)
+        return len(self.textures)
+
+    # ---- build everything the layer receives
+    def build(self):
+        # geometry storage + geometry table (float4 offsets)
+        geom_chunks, geom_table, off = [], [], 0
+        for m in self.meshes:
+            b = m.pack()
+            geom_table.append(off//16)
+            geom_chunks.append(b)
+            off += b.size
+        geom = np.concatenate(geom_chunks) if geom_chunks else np.zeros(16, np.uint8)
+
+        # materials storage: node k lives at float4 offset 48*k ; materialsTable[matId] -> offset of the head node
+        if not self.materials:
+            raise ValueError("scene has no materials")
+        mats = np.stack(self.materials).astype(np.float32)
+        mat_table = [48*h for h in self.material_ids]
+
+        # textures storage: slot 0 unused; each texture = int4{w,h,depth=4,bpp=4} + texels (cfetch.h:364-584)
+        tex_chunks, tex_table, off = [np.zeros(16, np.uint8)], [-1], 16
+        for t in self.textures:
+            h, w = t.shape[0], t.shape[1]
+            hdr = np.array([w, h, 4, 4], np.int32).view(np.uint8)
+            body = t.reshape(-1)
+            pad = (-body.size) % 16
+            chunk = np.concatenate([hdr, body, np.zeros(pad, np.uint8)])
+            tex_table.append(off//16)
+            tex_chunks.append(chunk)
+            off += chunk.size
+        textures = np.concatenate(tex_chunks)
+
+        # BVH
+        bb = BvhBuilder()
+        for m in self.meshes:
+            bb.add_mesh(m.vert4f(), m.idx)
+        for (mid, mat, _l) in self.instances:
+            bb.add_instance(mid, mat)
+        self.bvh = bb.commit()
+        bb.close()
+        self.inst_light_ids = np.array([l for (_m, _x, l) in self.instances], np.int32)
+
+        self.storages = dict(textures=textures, textures_aux=np.zeros(16, np.uint8), geom=geom, materials=mats.view(np.uint8).reshape(-1),
+                             pdfs=np.zeros(16, np.uint8))
+        self.globals_blob = self._pack_globals(geom_table, mat_table, tex_table)
+        return self
+
+    def _pack_globals(self, geom_table, mat_table, tex_table):
+        """EngineGlobals + tables blob (cfetch.h:21-81; CalcConstGlobDataOffsets / PrepareEngineGlobals / PrepareEngineTables /
+        SetAllPODLights / SetCamMatrices, IHWLayerDataAssembler.cpp:94-452)."""
+        W, H = self.width, self.height
+        cam = self.camera
+        nl = len(self.lights)
+        sizes = dict(materials=len(mat_table), geometry=len(geom_table), textures=len(tex_table), texturesAux=len(tex_table),
+                     pdfTable=max(nl, 1), lselRev=(nl + 1 if nl > 0 else 0), lselFwd=(nl + 1 if nl > 0 else 0), floats=0, lights=nl*128)
+        cur = _round_blocks(C["EG_sizeof"]//4, 16)
+        offs = {}
+        for k in ("materials", "geometry", "textures", "texturesAux", "pdfTable", "lselRev", "lselFwd", "floats", "lights"):
+            offs[k] = cur
+            cur += _round_blocks(sizes[k], 16)
+        blob = np.zeros(cur, np.int32)
+        b8 = blob.view(np.uint8)
+
+        def put_i(byte_off, v):
+            blob[byte_off//4] = v
+
+        def put_f(byte_off, arr):
+            a = np.ascontiguousarray(arr, np.float32).reshape(-1)
+            blob[byte_off//4:byte_off//4 + a.size] = a.view(np.int32)
+
+        aspect = float(W)/float(H)
+        proj = perspective(cam.fov, aspect, cam.near, cam.far)
+        view = look_at(cam.pos, cam.look_at, cam.up)
+        put_f(C["EG_mProj"], _cols(proj))
+        put_f(C["EG_mWorldView"], _cols(view))
+        put_f(C["EG_mProjInverse"], _cols(np.linalg.inv(proj)))
+        put_f(C["EG_mWorldViewInverse"], _cols(np.linalg.inv(view)))
+
+        varsI, varsF = self.varsI.copy(), self.varsF.copy()
+        fov_rad = np.float32(math.pi/180.0)*np.float32(cam.fov)
+        varsF[C["HRT_CAM_FOV"]] = fov_rad                              # UpdateCamera, RenderDriverRTE.cpp:1243
+        varsF[C["HRT_FOV_X"]] = fov_rad                                # SetCamMatrices, IHWLayerDataAssembler.cpp:105-109
+        varsF[C["HRT_FOV_Y"]] = fov_rad/np.float32(aspect)
+        varsF[C["HRT_WIDTH_F"]] = W
+        varsF[C["HRT_HEIGHT_F"]] = H
+        varsF[C["HRT_DOF_FOCAL_PLANE_DIST"]] = np.linalg.norm(np.asarray(cam.pos, np.float64) - np.asarray(cam.look_at, np.float64))
+        varsI[C["HRT_ENABLE_DOF"]] = 1 if cam.dof else 0
+        varsF[C["HRT_DOF_LENS_RADIUS"]] = cam.lens_radius if cam.dof else 0.0
+        blob[C["EG_varsI"]//4:C["EG_varsI"]//4 + 64] = varsI
+        put_f(C["EG_varsF"], varsF)
+
+        rm = np.full(16, -1, np.int32)                                 # SetQMCVarRemapTable, IHWLayerDataAssembler.cpp:211-323
+        variant = int(varsI[C["HRT_QMC_VARIANT"]])
+        if varsI[C["HRT_ENABLE_DOF"]] != 1 and (variant & 1):
+            variant -= 1
+        table = {0: dict(SCR_X=0, SCR_Y=1, DOF_X=2, DOF_Y=3), 1: dict(SCR_X=0, SCR_Y=1, DOF_X=2, DOF_Y=3),
+                 2: dict(SCR_X=0, SCR_Y=1, MAT_L=2, MAT_0=3, MAT_1=4),
+                 3: dict(SCR_X=0, SCR_Y=1, DOF_X=2, DOF_Y=3, MAT_L=4, MAT_0=5, MAT_1=6),
+                 4: dict(SCR_X=0, SCR_Y=1, LGT_N=2, LGT_0=3, LGT_1=4, LGT_2=5),
+                 5: dict(SCR_X=0, SCR_Y=1, DOF_X=2, DOF_Y=3, LGT_N=4, LGT_0=5, LGT_1=6, LGT_2=7),
+                 6: dict(SCR_X=0, SCR_Y=1, MAT_L=2, MAT_0=3, MAT_1=4, LGT_N=5, LGT_0=6, LGT_1=7, LGT_2=8),
+                 7: dict(SCR_X=0, SCR_Y=1, DOF_X=2, DOF_Y=3, MAT_L=4, MAT_0=5, MAT_1=6, LGT_N=7, LGT_0=8, LGT_1=9, LGT_2=10)}
+        for k, v in table.get(variant, table[0]).items():
+            rm[C["QMC_VAR_" + k]] = v
+        blob[C["EG_rmQMC"]//4:C["EG_rmQMC"]//4 + 16] = rm
+
+        fwd = np.asarray(cam.look_at, np.float64) - np.asarray(cam.pos, np.float64)
+        fwd /= np.linalg.norm(fwd)
+        put_f(C["EG_camForward"], fwd)                                 # camForward[3]
+        upv = np.linalg.inv(view)[:3, 1]
+        put_f(C["EG_camForward"] + 12, upv/np.linalg.norm(upv))        # camUpVector[3]
+        put_f(C["EG_camForward"] + 24, np.asarray(cam.look_at, np.float32))
+        put_f(C["EG_imagePlaneDist"], [W/(2.0*math.tan(0.5*float(fov_rad)))])
+
+        for key, name in (("materials", "materialsTable"), ("geometry", "geometryTable"), ("textures", "texturesTable"),
+                          ("texturesAux", "texturesAuxTable"), ("pdfTable", "pdfTableTable")):
+            put_i(C["EG_" + name + "Offset"], offs[key])
+            put_i(C["EG_" + name + "Size"], sizes[key])
+        put_i(C["EG_lightSelectorTableOffsetRev"], offs["lselRev"])
+        put_i(C["EG_lightSelectorTableSizeRev"], sizes["lselRev"])
+        put_i(C["EG_lightSelectorTableOffsetFwd"], offs["lselFwd"])
+        put_i(C["EG_lightSelectorTableSizeFwd"], sizes["lselFwd"])
+        put_i(C["EG_floatArraysOffset"], offs["floats"])
+        put_i(C["EG_floatsArraysSize"], 0)
+        put_i(C["EG_g_flags"], self.flags)
+        put_i(C["EG_skyLightId"], -1)
+        put_i(C["EG_lightsOffset"], offs["lights"])
+        put_i(C["EG_lightsSize"], nl*128)
+        put_i(C["EG_lightsNum"], nl)
+        put_i(C["EG_sunNumber"], 0)
+        put_i(C["EG_m_allTablesAreReady"], 1)
+        if self.ms_tables is not None:
+            ggx, transp = self.ms_tables
+            b8[C["EG_m_essGgx2017Table"]:C["EG_m_essGgx2017Table"] + 64*64*2] = np.ascontiguousarray(ggx, np.uint16).view(np.uint8)
+            b8[C["EG_m_essTranspTable"]:C["EG_m_essTranspTable"] + 64*64*64*2] = np.ascontiguousarray(transp, np.uint16).view(np.uint8)
+
+        blob[offs["materials"]:offs["materials"] + len(mat_table)] = mat_table
+        blob[offs["geometry"]:offs["geometry"] + len(geom_table)] = geom_table
+        blob[offs["textures"]:offs["textures"] + len(tex_table)] = tex_table
+        blob[offs["texturesAux"]:offs["texturesAux"] + len(tex_table)] = -1
+        blob[offs["pdfTable"]:offs["pdfTable"] + sizes["pdfTable"]] = -1
+        if nl > 0:
+            # light selection table = prefix sums of pick probabilities, N = lights+1 entries (RenderDriverRTE.cpp:1499-1521, clight.h:1774-1793)
+            lights = np.stack(self.lights).astype(np.float32)
+            w = np.ones(nl, np.float32)/np.float32(nl)
+            pref = np.zeros(nl + 1, np.float32)
+            acc = np.float32(0)
+            for i in range(nl):
+                pref[i] = acc
+                acc = np.float32(acc + w[i])
+            pref[nl] = acc
+            blob[offs["lselRev"]:offs["lselRev"] + nl + 1] = pref.view(np.int32)
+            blob[offs["lselFwd"]:offs["lselFwd"] + nl + 1] = pref.view(np.int32)
+            blob[offs["lights"]:offs["lights"] + nl*128] = lights.reshape(-1).view(np.int32)
+        return blob

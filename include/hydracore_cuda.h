@@ -1,0 +1,114 @@
+/* hydracore_cuda.h — the thin C ABI between the C++ CUDA layer (GPUCUDALayer : IHWLayer, MemoryStorageCUDA : IMemoryStorage)
+ * and the sm_100a kernels of libhydracore_b200.so.  POD only: plain pointers, sizes, ints.  Every entry point returns
+ * 0 on success, a positive cudaError_t value, or a negative HC_E_* code; hc_last_error() gives the text.  The C++ layer turns
+ * a non-zero status into RUN_TIME_ERROR (reference hydra_drv/globals_sys.h:56-62) or size_t(-1) where the reference does
+ * (MemoryStorageOCL.cpp:21-38).  All file:line citations are relative to the reference tree (Ray-Tracing-Systems/HydraCore).
+ *
+ * Blob formats are the reference's own: offsets in float4 (16 B) units, BVHNode 32 B in quads of 4,
+ * triangles 3 x float4 behind a one-float4 leaf header, PlainMaterial 192 floats, PlainLight 128 floats, EngineGlobals blob.
+ */
+#ifndef HYDRACORE_CUDA_H
+#define HYDRACORE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HC_ABI_VERSION 1
+
+enum { HC_OK = 0, HC_E_ARG = -1, HC_E_STATE = -2, HC_E_NOMEM = -3, HC_E_NODEVICE = -4, HC_E_RANGE = -5 };
+
+/* storage slots: the five IMemoryStorage objects RenderDriverRTE creates (RenderDriverRTE.cpp:705-709) */
+enum { HC_STORAGE_TEXTURES = 0, HC_STORAGE_TEXTURES_AUX = 1, HC_STORAGE_GEOM = 2, HC_STORAGE_MATERIALS = 3, HC_STORAGE_PDFS = 4,
+       HC_STORAGE_COUNT = 5 };
+
+/* integrators of the CPU oracle this layer reproduces (CPUExp_Integrators_PT.cpp:9, CPUExp_Integrators_PT_Loop.cpp:264,
+ * CPUExp_Integrators_PT_QMC.cpp:5) */
+enum { HC_INTEGRATOR_PT = 0, HC_INTEGRATOR_MISPT = 2, HC_INTEGRATOR_MISPT_QMC = 3 };
+
+/* memory space of a caller-supplied buffer */
+enum { HC_HOST = 0, HC_DEVICE = 1 };
+
+typedef struct hc_ctx hc_ctx;            /* one per CUDA device: what GPUOCLLayer holds in m_globals/m_scene/m_rays (GPUOCLLayer.h) */
+typedef struct hc_bvh hc_bvh;            /* host-side BVH4 builder: stands where IBVHBuilder2 stands (IBVHBuilderAPI.h:35-68)       */
+
+/* 16-byte hit record == Lite_Hit (cglobals.h:1248-1256) */
+typedef struct hc_hit { float t; int32_t primId; int32_t instId; int32_t geomId; } hc_hit;
+
+/* counters of one traversal launch / one pass (MRaysStat, cglobals.h:1764-1787, is filled from these) */
+typedef struct hc_stats
+{
+  uint64_t raysClosest;      /* closest-hit rays traced                         */
+  uint64_t raysShadow;       /* any-hit rays traced                             */
+  uint64_t paths;            /* eye paths started                               */
+  uint64_t kernelLaunches;   /* launches of OUR kernels since the last reset    */
+  float    msClosest;        /* device time (CUDA events) in closest-hit kernel */
+  float    msShadow;         /* ... any-hit kernel                              */
+  float    msShade;          /* ... surface/light/BSDF kernel                   */
+  float    msOther;          /* ray generation, compaction, accumulation        */
+} hc_stats;
+
+/* ---------------------------------------------------------------- process / device ---------------------------------------- */
+int         hc_abi_version(void);
+const char* hc_last_error(void);
+int         hc_device_count(int* outCount);                                  /* IHWLayer::ListDevices, IHWLayer.h:160          */
+int         hc_ctx_create(int device, hc_ctx** out);                          /* CreateCudaImpl beside IHWLayer.h:256-257       */
+void        hc_ctx_destroy(hc_ctx* ctx);
+int         hc_device_name(hc_ctx* ctx, char* buf, int bufSize);             /* IHWLayer::GetDeviceName, IHWLayer.h:158        */
+int         hc_mem_info(hc_ctx* ctx, size_t* freeBytes, size_t* totalBytes); /* GetAvaliableMemoryAmount, IHWLayer.h:152       */
+int         hc_sync(hc_ctx* ctx);                                            /* IHWLayer::FinishAll, IHWLayer.h:137            */
+int         hc_stream(hc_ctx* ctx, void** outCudaStream);                    /* the stream all kernels of ctx are launched on  */
+
+/* ---------------------------------------------------------------- MemoryStorageCUDA --------------------------------------- */
+int hc_storage_reserve(hc_ctx* ctx, int slot, uint64_t bytes);               /* IMemoryStorage::Reserve, MemoryStorageOCL.cpp:10 */
+int hc_storage_write(hc_ctx* ctx, int slot, uint64_t offsetBytes, const void* data, uint64_t bytes); /* MemCopyAt, :53-56     */
+int hc_storage_capacity(hc_ctx* ctx, int slot, uint64_t* outBytes);
+
+/* ---------------------------------------------------------------- scene upload -------------------------------------------- */
+int hc_set_globals(hc_ctx* ctx, const void* blob, uint64_t bytes);           /* PrepareEngineGlobals/Tables upload, GPUOCLData.cpp:289-327 */
+int hc_set_bvh(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const void* trif4, int trif4Num, int haveInst);
+                                                                              /* SetAllBVH4(ConvertionResult), GPUOCLData.cpp:88-160       */
+int hc_set_inst_matrices(hc_ctx* ctx, const float* invMatrices16, int n);    /* SetAllInstMatrices, IHWLayer.h:117                        */
+int hc_set_inst_light_ids(hc_ctx* ctx, const int32_t* lightInstId, int n);   /* SetAllInstLightInstId, IHWLayer.h:118                     */
+int hc_resize(hc_ctx* ctx, int width, int height);                           /* ResizeScreen, IHWLayer.h:147                              */
+
+/* ---------------------------------------------------------------- ray casting (kernels K1, K2, K2s) ----------------------- */
+/* rays: n x 8 floats {pos.xyz, tNear(unused, 0) | dir.xyz, tFar}.  `space` says where rays/out live (HC_HOST: copied inside). */
+int hc_make_eye_rays(hc_ctx* ctx, int width, int height, const float* offsets4OrNull, float* rays8Out, int space);
+                                                                              /* MakeEyeRaysUnifiedSampling, screen.cl:280 ; MakeRandEyeRay, cfetch.h:877 */
+int hc_trace_closest(hc_ctx* ctx, const float* rays8, int64_t n, hc_hit* hitsOut, int space);  /* BVH4TraversalInstKernel, trace.cl:50  */
+int hc_trace_shadow(hc_ctx* ctx, const float* rays8, int64_t n, uint8_t* visibleOut, int space);/* BVH4TraversalInstShadowKenrel, trace.cl:309 */
+int hc_trace_last_ms(hc_ctx* ctx, float* outMs);                             /* device time of the last hc_trace_* launch (CUDA events)   */
+
+/* ---------------------------------------------------------------- path tracing -------------------------------------------- */
+int hc_pt_init(hc_ctx* ctx, int seed);                                       /* InitPathTracing, IHWLayer.h:139 ; InitRandomGen, trace.cl:6 */
+int hc_pt_set_tiles(hc_ctx* ctx, int tileSize, int rank, int worldSize);     /* interleaved tile ownership for multi-GPU        */
+int hc_pt_pass(hc_ctx* ctx, int integrator, int passes);                     /* BeginTracingPass+EndTracingPass, IHWLayer.h:133-134         */
+int hc_fb_clear(hc_ctx* ctx);                                                /* ClearAccumulatedColor, IHWLayer.h:140                       */
+int hc_fb_device_ptr(hc_ctx* ctx, float** outSumRGBA, int64_t* outFloats);   /* per-pixel SUM buffer (for the NCCL reduce over NVLink)      */
+int hc_fb_read_hdr(hc_ctx* ctx, float* outRGBA, int width, int height);      /* GetHDRImage: sum / spp, GPUOCLLayer.cpp:1184-1215           */
+int hc_fb_read_ldr(hc_ctx* ctx, uint32_t* outRGBA8, int width, int height);  /* GetLDRImage, IHWLayer.h:149                                 */
+int hc_get_spp(hc_ctx* ctx, float* outSpp);                                  /* GetSPP, IHWLayer.h:207                                      */
+int hc_get_stats(hc_ctx* ctx, hc_stats* out);                                /* GetRaysStat, IHWLayer.h:155                                 */
+int hc_reset_stats(hc_ctx* ctx);                                             /* ResetPerfCounters, IHWLayer.h:145                           */
+
+/* ---------------------------------------------------------------- BVH4 builder (host) ------------------------------------- */
+/* Stands in for libhydrabvhbuilder (bvh_builder/bvh_access_dll2.cpp) whose Embree 2.17 back end is not available: binned-SAH
+ * BVH4 per mesh + BVH4 over instances, flattened to the SAME two-level layout ConvertMap() emits (bvh_access_dll2.cpp:388-717). */
+int  hc_bvh_create(hc_bvh** out);                                            /* CreateBuilder2, bvh_access_dll2.cpp:801        */
+void hc_bvh_destroy(hc_bvh* b);
+int  hc_bvh_add_mesh(hc_bvh* b, const float* vert4f, int numVert, const int32_t* indices, int numIndices, int* outMeshId);
+int  hc_bvh_add_instance(hc_bvh* b, int meshId, const float* matrixRowMajor16, int* outInstId);
+                                                                              /* InstanceTriangleMeshes, bvh_access_dll2.cpp:143 */
+int  hc_bvh_commit(hc_bvh* b);                                               /* CommitScene + ConvertMap                        */
+int  hc_bvh_result(hc_bvh* b, const void** nodes, int* nodesNum, const void** trif4, int* trif4Num,
+                   const float** invMatrices16, int* numInst, int* maxStackDepth);
+int  hc_bvh_bounds(hc_bvh* b, float bmin[3], float bmax[3]);                 /* IBVHBuilder2::GetBounds                         */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDRACORE_CUDA_H */

@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/hydracore_cuda.h declares; the ctypes table mirrors it.
+No compute call is made here (no GPU in the build container); without a device hc_ctx_create must fail loudly."""
+import ctypes as ct
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "hydracore_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(built):
+    from hydracore_b200 import _lib
+    names = _declared()
+    assert len(names) >= 35
+    lib = _lib.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/hydracore_cuda.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.hc_abi_version() == 1
+
+
+def test_no_device_means_loud_failure(built):
+    import hydracore_b200 as hc
+    lib = hc.load()
+    n = ct.c_int(-1)
+    rc = lib.hc_device_count(ct.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(hc.HcError):
+        hc.CudaLayer()
+
+
+def test_bvh_builder_layout(built):
+    """Host-side builder: Appendix-A invariants of the flattened tree (quad 0 root record, quad alignment, leaf headers)."""
+    import numpy as np
+    from tests import scenes
+    scn = scenes.instanced_geometry()
+    nodes, tris = scn.bvh["nodes"], scn.bvh["tris"]
+    u = nodes.view(np.uint32)
+    assert nodes.shape[0] % 4 == 0
+    assert u[0, 3] == 1 and u[0, 7] == 0                       # root record: leftOffset = 1, not a leaf
+    assert np.array_equal(nodes[1:3].reshape(16), np.eye(4, dtype=np.float32).reshape(16))   # identity matrix in nodes 1..2
+    # every triangle leaf header: {first = hdr+1, count in 1..4, -1, -1}
+    ti = tris.view(np.int32)
+    hdr = 0
+    ntri = 0
+    while hdr < tris.shape[0]:
+        assert ti[hdr, 0] == hdr + 1 and 1 <= ti[hdr, 1] <= 4 and ti[hdr, 2] == -1 and ti[hdr, 3] == -1
+        ntri += ti[hdr, 1]
+        hdr += 1 + 3*ti[hdr, 1]
+    assert hdr == tris.shape[0]
+    assert ntri == sum(m.tri_count for m in scn.meshes)       # mesh sub-trees are shared between instances
+    assert scn.bvh["inv_matrices"].shape == (8, 16)
+    assert scn.bvh["max_stack"] <= 64

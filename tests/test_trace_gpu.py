@@ -1,0 +1,121 @@
+"""GPU: K1 (eye rays), K2 (closest hit) and K2s (any hit) through the C ABI against the oracle, the golden vectors of the
+reference and — at BASELINE sizes — size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import refapi, scenes
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _same_hits(a, b, rtol=1e-5):
+    """bit-exact ids; t bit-exact except documented ties: equal-distance hits (|dt| <= 1e-5 relative) may pick another triangle."""
+    exact = (a["primId"] == b["primId"]) & (a["instId"] == b["instId"]) & (a["geomId"] == b["geomId"]) & (a["t"] == b["t"])
+    bad = ~exact
+    ties = bad & (a["primId"] >= 0) & (b["primId"] >= 0) & (np.abs(a["t"] - b["t"]) <= rtol*np.abs(b["t"]))
+    return int(bad.sum()), int((bad & ~ties).sum())
+
+
+@pytest.fixture(scope="module")
+def raycast():
+    return np.load(os.path.join(G, "raycast.npz"))
+
+
+def test_golden_hits(layer, raycast):
+    layer.SetAllBVH4(raycast["bvh_nodes"], raycast["bvh_tris"])
+    for rays, key in ((raycast["rays_primary"], "hits_primary"), (scenes.incoherent_rays(6000, 11), "hits_incoherent")):
+        h = layer.TraceClosest(rays)
+        nbad, nhard = _same_hits(h, raycast[key])
+        assert nhard == 0 and nbad <= 2, (key, nbad, nhard)
+    sh = scenes.incoherent_rays(6000, 11)
+    sh[:, 7] = raycast["shadow_tfar"]
+    v = layer.TraceShadow(sh)
+    assert (v != raycast["vis_incoherent"]).sum() <= 2
+    layer.SetAllBVH4(raycast["bvh1_nodes"], raycast["bvh1_tris"])
+    h = layer.TraceClosest(raycast["rays_single_leaf"])
+    assert _same_hits(h, raycast["hits_single_leaf"]) == (0, 0)
+
+
+@pytest.mark.parametrize("dof", [False, True])
+def test_eye_rays_bit_exact(layer, oracle, dof):
+    scn = scenes.instanced_geometry(dof=dof)
+    layer.LoadScene(scn)
+    W, H = scn.width, scn.height
+    offs = (np.random.RandomState(21).rand(W*H, 4)*2 - 1).astype(np.float32)
+    got = layer.MakeEyeRays(W, H, offs)
+    want = oracle.make_rand_eye_rays(scn.globals_blob, W, H, scenes.pixel_grid(W, H), offs)
+    assert np.array_equal(got[:, 0:3], want[:, 0:3]) and np.array_equal(got[:, 4:7], want[:, 3:6])
+    got0 = layer.MakeEyeRays(W, H, None)
+    want0 = oracle.make_rand_eye_rays(scn.globals_blob, W, H, scenes.pixel_grid(W, H), np.zeros((W*H, 4), np.float32))
+    assert np.array_equal(got0[:, 4:7], want0[:, 3:6])
+
+
+def test_closest_and_shadow_vs_oracle_200k(layer, oracle):
+    scn = scenes.instanced_geometry(320, 240)
+    layer.LoadScene(scn)
+    prim = layer.MakeEyeRays(320, 240, None)
+    rays = np.concatenate([prim, scenes.incoherent_rays(120000, 3)])
+    h = layer.TraceClosest(rays)
+    ho = oracle.trace_closest(scn.bvh["nodes"], scn.bvh["tris"], rays)
+    nbad, nhard = _same_hits(h, ho)
+    assert nhard == 0 and nbad <= 1e-4*rays.shape[0], (nbad, nhard)
+    sh = rays.copy()
+    sh[:, 7] = np.random.RandomState(8).uniform(0.1, 20.0, rays.shape[0])
+    v = layer.TraceShadow(sh)
+    vo = oracle.trace_shadow(scn.bvh["nodes"], scn.bvh["tris"], sh)
+    assert (v != vo).sum() <= 1e-4*rays.shape[0]
+
+
+def test_edge_cases(layer):
+    scn = scenes.single_triangle_leaf()
+    layer.LoadScene(scn)
+    assert layer.TraceClosest(np.zeros((0, 8), np.float32)).shape[0] == 0              # empty
+    r = np.zeros((3, 8), np.float32)
+    r[:, 0:3] = (0, 5, 0)
+    r[0, 4:7] = (0, -1, 0)          # straight down: hit at t = 5
+    r[1, 4:7] = (0, 1, 0)           # away: miss
+    r[2, 4:7] = (1, 0, 0)           # parallel to the quad: miss (division by zero inside the triangle test must not hit)
+    r[:, 7] = 3.0e38
+    h = layer.TraceClosest(r)
+    assert h["primId"][0] >= 0 and h["t"][0] == 5.0 and h["instId"][0] == 0 and h["geomId"][0] == 0
+    assert h["primId"][1] == -1 and h["primId"][2] == -1 and h["geomId"][1] == -1073741824
+    s = r.copy()
+    s[:, 7] = (4.0, 10.0, 0.0)      # occluder beyond tFar -> visible ; miss -> visible ; tFar == 0 -> visible without tracing
+    assert layer.TraceShadow(s).tolist() == [1, 1, 1]
+    s[0, 7] = 6.0
+    assert layer.TraceShadow(s).tolist() == [0, 1, 1]
+    with pytest.raises(Exception):
+        layer.SetAllBVH4(np.zeros((4, 8), np.float32), np.zeros((4, 4), np.float32))       # too small / invalid tree
+
+
+def test_million_triangles_properties(layer, oracle):
+    """BASELINE config C2 size: 1M-triangle mesh, 1080p primaries.  Checked through properties + an oracle sample."""
+    from hydracore_b200 import scene as S
+    scn = S.Scene(1920, 1080, S.Camera(pos=(0, 7, 9), look_at=(0, 0, 0), fov=45))
+    scn.add_instance(scn.add_mesh(S.grid_mesh(708, 707)))
+    scn.add_material(np.zeros(192, np.float32))
+    scn.build()
+    layer.LoadScene(scn)
+    rays = layer.MakeEyeRays(1920, 1080, None)
+    h = layer.TraceClosest(rays)
+    hit = h["primId"] >= 0
+    assert 0.3 < hit.mean() < 1.0
+    assert np.all(h["primId"][hit] < 2*708*707) and np.all(h["instId"][hit] == 0) and np.all(h["geomId"][hit] == 0)
+    assert np.all(np.isfinite(h["t"][hit])) and np.all(h["t"][hit] > 0)
+    # idempotence / determinism
+    assert np.array_equal(h.view(np.uint8), layer.TraceClosest(rays).view(np.uint8))
+    # a shadow ray stopped just short of the found hit is visible, one going past it is occluded
+    s = rays[hit][:200000].copy()
+    t = h["t"][hit][:200000]
+    s[:, 7] = t*0.999
+    assert layer.TraceShadow(s).mean() > 0.999
+    s[:, 7] = t*1.01 + 1e-3
+    assert layer.TraceShadow(s).mean() < 0.001
+    # oracle on a strided sample
+    idx = np.arange(0, rays.shape[0], 97)
+    ho = oracle.trace_closest(scn.bvh["nodes"], scn.bvh["tris"], rays[idx])
+    nbad, nhard = _same_hits(h[idx], ho)
+    assert nhard == 0 and nbad <= 3
