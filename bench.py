@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json configs[1], "C2"):
+synthetic 1,001,112-triangle mesh, 1920x1080 primary + shadow ray casting through the CUDA layer.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                   # our arm (sm_100a kernels behind the C ABI)
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # the reference's own CPU code on the host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one ray-casting pass over the whole screen: K1 eye rays -> K2 closest hit -> shadow rays to a point light ->
+K2s any hit (hc_raycast_pass).  value = (primary + shadow rays) / device time, inputs resident in HBM; e2e = the same pass
+through the reference-facing call sequence with HOST buffers: upload of the EngineGlobals blob (what RenderDriverRTE::Draw
+does before every pass, RenderDriverRTE.cpp:1723-1725) + pass + read-back of the hit and visibility buffers to pinned host
+memory.  At N > 1 every rank casts its own full frame (one process per GPU, replicated scene, no data-path collective:
+the reference's process-per-GPU mode, README.md:99-103) — weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 1920, 1080
+METRIC, UNIT = "Mrays/s", "Mrays/s"
+WORKLOAD = "C2: synthetic 1,001,112-triangle mesh, 1920x1080 primary + shadow ray casting"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.path)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def _dist():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+# ------------------------------------------------------------------------------------------------------------ reference arm
+def reference_rays(scn, ref):
+    """Primary rays of the frame (zero jitter) from the reference's own MakeRandEyeRay."""
+    from tests import refapi, scenes
+    W, H = scn.width, scn.height
+    pd = ref.make_rand_eye_rays(scn.globals_blob, W, H, scenes.pixel_grid(W, H), np.zeros((W*H, 4), np.float32))
+    return refapi.rays_from_pos_dir(pd)
+
+
+def reference_step(scn, ref, rays):
+    """One pass of the reference CPU path over `rays`: closest hit (BVH4InstTraverse via IntegratorCommon::rayTrace semantics),
+    shadow rays to the point light, shadow query (IntegratorCommon::shadowTrace semantics).  Returns rays traced."""
+    from hydracore_b200.scene import C2_LIGHT_POS
+    nodes, tris = scn.bvh["nodes"], scn.bvh["tris"]
+    hits = ref.trace_closest(nodes, tris, rays)
+    hit = hits["primId"] >= 0
+    pos = rays[:, 0:3] + rays[:, 4:7]*hits["t"][:, None]
+    L = np.array(C2_LIGHT_POS, np.float32)
+    d = L - pos[hit]
+    dist = np.sqrt((d*d).sum(1))
+    sd = d/dist[:, None]
+    eps = np.maximum(np.abs(pos[hit]).max(1), 1.0)*np.float32(1e-4)
+    sp = pos[hit] + sd*eps[:, None]
+    sh = np.zeros((sp.shape[0], 8), np.float32)
+    sh[:, 0:3] = sp
+    sh[:, 4:7] = sd
+    sh[:, 7] = np.sqrt(((sp - L)**2).sum(1))*np.float32(0.995)
+    ref.trace_shadow(nodes, tris, sh)
+    return rays.shape[0] + sh.shape[0]
+
+
+def cpu_baseline(scn, budget_s=12.0):
+    """The reference's own CPU implementation (oracle/_ref) timed on this box's host cores over a bounded sample of the workload.
+    Also returns the traversal work counters (quads / leaves / triangles per primary ray) from the oracle restatement,
+    which define the algorithmic bytes of the roofline."""
+    from tests import refapi
+    ref = refapi.Ref.try_load()
+    kind = "reference"
+    if ref is None:
+        raise RuntimeError("oracle/_ref/libhydra_ref.so is missing (built by __graft_entry__.build() where /root/reference exists)")
+    cores = len(os.sched_getaffinity(0))
+    cores = min(cores, 32) if False else cores
+    rays = reference_rays(scn, ref)
+    n = rays.shape[0]
+    # calibrate on 1/32 of the frame (strided rows keep the sample representative), then size the sample for ~budget seconds
+    probe = rays[::32]
+    t0 = time.perf_counter()
+    traced = reference_step(scn, ref, probe)
+    dt = time.perf_counter() - t0
+    rate = traced/dt
+    frac = min(1.0, budget_s*rate/(2.0*n))
+    stride = max(1, int(round(1.0/frac)))
+    sample = rays[::stride]
+    t0 = time.perf_counter()
+    traced = reference_step(scn, ref, sample)
+    dt = time.perf_counter() - t0
+    orc = refapi.Oracle()
+    sub = rays[::61]
+    _h, cnt = orc.trace_closest(scn.bvh["nodes"], scn.bvh["tris"], sub, count=True)
+    qlt = [float(c)/sub.shape[0] for c in cnt]
+    return {"value": traced/dt/1e6, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "every %d-th pixel of the 1080p frame: %d primary + shadow rays in %.2f s; closest hit = reference BVH4InstTraverse "
+                      "(Embree unavailable), OpenMP over all host threads" % (stride, traced, dt)}, qlt
+
+
+def run_reference(args):
+    world, rank, _local = _dist()
+    if rank != 0:
+        return 0
+    import __graft_entry__ as g  # noqa: F401  (libraries are prebuilt; the bvh builder lives in the product .so)
+    from hydracore_b200 import scene as S
+    from tests import refapi
+    ref = refapi.Ref.try_load()
+    if ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhydra_ref.so missing"}))
+        return 0
+    scn = S.scene_c2(WIDTH, HEIGHT)
+    rays = reference_rays(scn, ref)
+    cores = len(os.sched_getaffinity(0))
+    # bounded sample per step: calibrate so that (steps + warmup) x sample stays within ~2 minutes
+    t0 = time.perf_counter()
+    traced = reference_step(scn, ref, rays[::64])
+    rate = traced/(time.perf_counter() - t0)
+    per_step_s = min(20.0, 120.0/max(1, args.steps + args.warmup))
+    stride = max(1, int(round(2.0*rays.shape[0]/(per_step_s*rate))))
+    sample = rays[::stride]
+    for _ in range(args.warmup):
+        reference_step(scn, ref, sample)
+    t0 = time.perf_counter()
+    traced = 0
+    for _ in range(args.steps):
+        traced += reference_step(scn, ref, sample)
+    dt = time.perf_counter() - t0
+    v = traced/dt/1e6
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3*dt/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "triangles": 1001112,
+                                            "sample": "every %d-th pixel per step" % stride},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": "every %d-th pixel of the frame per step, %d rays per step" % (stride, traced//max(1, args.steps))},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import hydracore_b200 as hc
+    from hydracore_b200 import scene as S
+    from hydracore_b200._lib import HC_HOST, HC_DEVICE
+    world, rank, local = _dist()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    scn = S.scene_c2(WIDTH, HEIGHT)
+    lay = hc.CudaLayer(device=local)
+    lay.LoadScene(scn)
+    n = WIDTH*HEIGHT
+    light = S.C2_LIGHT_POS
+
+    # device-resident result buffers owned by torch (so that NCCL / torch can see them) and pinned host mirrors for e2e
+    hits_d = torch.empty(n*4, dtype=torch.int32, device=dev)
+    vis_d = torch.empty(n, dtype=torch.uint8, device=dev)
+    hits_h = torch.empty(n*4, dtype=torch.int32, pin_memory=True)
+    vis_h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    flush = torch.empty(256*1024*1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        lay.RaycastPass(light, hits_d.data_ptr(), vis_d.data_ptr(), HC_DEVICE)
+        return lay.last_trace_ms()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    lay.ResetPerfCounters()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ms = []
+    for _ in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (outside the per-step CUDA events)
+        torch.cuda.synchronize()
+        ms.append(step_device())            # device time of the 4 kernels of this step, CUDA events on the launching stream
+    barrier()
+    clocks = sampler.stop()
+    stats = lay.GetRaysStat()
+    shadow_rays = int(vis_d.numel())        # one shadow ray slot per pixel (missed pixels carry t_far = 0 and are not traced)
+    n_hit = int((hits_d.view(-1, 4)[:, 1] >= 0).sum().item())
+    rays_per_step = n + n_hit
+    t_step = float(np.sum(ms))/1e3
+    if dist is not None:
+        t = torch.tensor([t_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_step = float(t.item())
+        tot = torch.tensor([float(rays_per_step)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        rays_all = float(tot.item())
+    else:
+        rays_all = float(rays_per_step)
+    value = rays_all*args.steps/t_step/1e6
+    ms_per_step = 1e3*t_step/args.steps
+
+    # ---- e2e: globals upload + pass + read-back to pinned host memory, wall clock around synchronous API calls
+    blob = torch.from_numpy(scn.globals_blob.copy()).pin_memory()
+    blob_np = blob.numpy()
+
+    def step_e2e():
+        lay.PrepareEngineGlobals(blob_np)
+        lay.RaycastPass(light, hits_h.data_ptr(), vis_h.data_ptr(), HC_HOST)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    te = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([te], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    e2e_value = rays_all*args.steps/te/1e6
+    # parity guard: the host copy must agree with the device-resident result
+    assert torch.equal(hits_h, hits_d.cpu()) and torch.equal(vis_h, vis_d.cpu())
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel (K2 closest hit) + CPU baseline (N = 1 only)
+    peak, peak_src = _peaks()
+    qlt_path = os.path.join(ROOT, "profiles", "c2_algorithmic_bytes.json")
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu, qlt = cpu_baseline(scn)
+        try:
+            json.dump({"quads_per_ray": qlt[0], "leaves_per_ray": qlt[1], "tris_per_ray": qlt[2],
+                       "formula": "B_ray = 32 + 4 + 16 + 128*Q + 16*L + 48*T (SURVEY.md 8d)"}, open(qlt_path, "w"), indent=1)
+        except OSError:
+            pass
+    else:
+        d = json.load(open(qlt_path))
+        qlt = [d["quads_per_ray"], d["leaves_per_ray"], d["tris_per_ray"]]
+    bytes_per_ray = 52.0 + 128.0*qlt[0] + 16.0*qlt[1] + 48.0*qlt[2]
+    ms_closest = stats["msClosest"]/args.steps
+    achieved = bytes_per_ray*n/(ms_closest*1e-3)/1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "c2_ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("k_trace_closest_dram_bytes_per_launch")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "triangles": 1001112, "rays_per_step_per_gpu": rays_per_step,
+                       "l2": "flushed between steps (256 MiB memset outside the per-step CUDA events)",
+                       "parallelism": "replicated scene, one full frame per GPU, no collective" if world > 1 else "single GPU"},
+            "mrays_primary": n/(stats["msClosest"]/args.steps)/1e3, "mrays_shadow": n_hit/(stats["msShadow"]/args.steps)/1e3,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(blob_np.nbytes), "d2h_bytes_per_step": int(n*16 + n),
+                    "ms_per_step": 1e3*te/args.steps},
+            "gpu_launches": int(stats["kernelLaunches"]),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": traffic,
+                         "kernel": "k_trace<closest>", "bytes_per_ray": bytes_per_ray, "quads_leaves_tris_per_ray": qlt,
+                         "ms_per_launch": ms_closest, "peak_source": peak_src,
+                         "note": "algorithmic bytes are BVH/triangle fetches that the 126 MB L2 serves; HBM peak is the stated denominator"}}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    lay.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -48,6 +48,8 @@ SIGNATURES = {
     "hc_make_eye_rays": (_I, [_P, _I, _I, _P, _P, _I]),
     "hc_trace_closest": (_I, [_P, _P, _I64, _P, _I]),
     "hc_trace_shadow": (_I, [_P, _P, _I64, _P, _I]),
+    "hc_make_shadow_rays": (_I, [_P, _P, _P, _I64, ct.POINTER(ct.c_float), _P, _I]),
+    "hc_raycast_pass": (_I, [_P, ct.POINTER(ct.c_float), _P, _P, _I]),
     "hc_trace_last_ms": (_I, [_P, ct.POINTER(ct.c_float)]),
     "hc_pt_init": (_I, [_P, _I]),
     "hc_pt_set_tiles": (_I, [_P, _I, _I, _I]),

@@ -152,9 +152,10 @@ static void BuildRec(Tree& T, int32_t nodeIdx, int32_t first, int32_t count, int
   }
   std::sort(parts, parts + np, [](const Range& a, const Range& b) { return a.first < b.first; });
 
-  // child node indices: a sub-tree over n prims never needs more than 2n-1 nodes; carve disjoint slot ranges
+  // child node indices: every interior node has >= 2 children, so a sub-tree over c prims needs at most 2c-1 nodes;
+  // carve disjoint slot ranges (1 + sum(2c_i - 1) <= 2n - 1 slots for this sub-tree)
   int32_t slot = nodeIdx + 1;
-  for (int i = 0; i < np; i++) { N.child[i] = slot; slot += 2*parts[i].count; }
+  for (int i = 0; i < np; i++) { N.child[i] = slot; slot += 2*parts[i].count - 1; }
   for (int i = 0; i < np; i++)
   {
     const int32_t ci = N.child[i]; const Range r = parts[i];

@@ -41,9 +41,10 @@ void hc_buf_free(HcDevBuf& b) { if (b.ptr) cudaFree(b.ptr); b.ptr = nullptr; b.b
 // rpos/rdir are float4 streams with element stride `stride` (2 = interleaved {pos,dir} records, 1 = separate arrays).
 template<bool ANYHIT>
 __global__ void __launch_bounds__(HC_TRACE_BLOCK)
-k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long n,
-        HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter)
+k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long nArg,
+        const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter)
 {
+  const long long n = nDev ? (long long)(*nDev) : nArg;      // the path tracer keeps its live-path count on the device
   unsigned stkNode[HC_STACK_CAP];
   float    stkT[HC_STACK_CAP];
 
@@ -164,6 +165,26 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
   }
 }
 
+// shadow rays from closest hits toward one point light (ray-casting benchmark / debug path of the LightSample stage)
+static __global__ void k_make_shadow_rays(const float4* __restrict__ rays, const HcHit* __restrict__ hits, const long long n, const float3 L, float4* __restrict__ out)
+{
+  const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const HcHit h = hits[i];
+  float4 o = make_float4(0, 0, 0, 0), d = make_float4(0, 1, 0, 0);            // d.w = t_far = 0: "no shadow ray"
+  if (h.primId != -1)
+  {
+    const float3 ro = f3(rays[2*i]), rd = f3(rays[2*i + 1]);
+    const float3 pos = ro + rd*h.t;
+    const float3 sdir = normalize(L - pos);
+    const float eps = fmaxf(fmaxf(fabsf(pos.x), fmaxf(fabsf(pos.y), fabsf(pos.z))), 1.0f)*1e-4f;
+    const float3 spos = pos + sdir*eps;
+    o = make_float4(spos.x, spos.y, spos.z, 0.0f);
+    d = make_float4(sdir.x, sdir.y, sdir.z, length(spos - L)*0.995f);
+  }
+  out[2*i] = o; out[2*i + 1] = d;
+}
+
 // ------------------------------------------------------------------------------------------------------------------ helpers
 static int TraceGrid(hc_ctx* ctx)
 {
@@ -176,17 +197,24 @@ static int TraceGrid(hc_ctx* ctx)
 }
 
 // launch K2 (closest) or K2s (any-hit) on device-resident streams; used by hc_trace_* and by the path tracer
+static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis);
 int hc_launch_trace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, HcHit* hits, unsigned char* vis)
+{ return LaunchTrace(ctx, anyHit, rpos, rdir, stride, n, nullptr, hits, vis); }
+int hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis)
+{ return LaunchTrace(ctx, anyHit, rpos, rdir, 1, nUpper, nDev, hits, vis); }
+static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis)
 {
   if (n <= 0) return HC_OK;
   HC_REQUIRE(ctx->bvhNodes.ptr && ctx->bvhTris.ptr, HC_E_STATE, "hc_trace: no BVH uploaded (hc_set_bvh)");
   HC_REQUIRE(ctx->haveInst != 0, HC_E_STATE, "hc_trace: only the two-level (instanced) layout is supported");
   HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr;
-  unsigned long long* counter = (unsigned long long*)ctx->counters.ptr;
+  // one persistent-thread ray counter per launch in flight: rotate through the counter block so that back-to-back launches never share one
+  ctx->traceCounterSlot = (ctx->traceCounterSlot + 1) % 32;
+  unsigned long long* counter = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
   HC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
   const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
-  if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nullptr, vis, counter);
-  else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, hits, nullptr, counter);
+  if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter);
+  else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter);
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   if (anyHit) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n;
@@ -263,6 +291,7 @@ int hc_ctx_create(int device, hc_ctx** out)
   c->smCount = c->prop.multiProcessorCount;
   HC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   HC_CUDA(cudaEventCreate(&c->ev0)); HC_CUDA(cudaEventCreate(&c->ev1));
+  for (int i = 0; i < 5; i++) HC_CUDA(cudaEventCreate(&c->evStage[i]));
   int rc = hc_buf_reserve(c, c->counters, 64*sizeof(unsigned long long));
   if (rc != HC_OK) { delete c; return rc; }
   HC_CUDA(cudaMemsetAsync(c->counters.ptr, 0, c->counters.bytes, c->stream));
@@ -280,6 +309,8 @@ void hc_ctx_destroy(hc_ctx* c)
   for (int i = 0; i < HC_STORAGE_COUNT; i++) hc_buf_free(c->storage[i]);
   hc_buf_free(c->globals); hc_buf_free(c->bvhNodes); hc_buf_free(c->bvhTris); hc_buf_free(c->instMatrices); hc_buf_free(c->instLightIds);
   hc_buf_free(c->fbSum); hc_buf_free(c->scratchRays); hc_buf_free(c->scratchOut); hc_buf_free(c->counters); hc_buf_free(c->pixelRng); hc_buf_free(c->qmcTable);
+  hc_buf_free(c->rcRays); hc_buf_free(c->rcHits); hc_buf_free(c->rcSRays); hc_buf_free(c->rcVis);
+  for (int i = 0; i < 5; i++) cudaEventDestroy(c->evStage[i]);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -437,6 +468,69 @@ static int TraceEntry(hc_ctx* ctx, bool anyHit, const float* rays8, int64_t n, v
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   HC_CUDA(cudaEventElapsedTime(&ctx->lastTraceMs, ctx->ev0, ctx->ev1));
   if (anyHit) ctx->stats.msShadow += ctx->lastTraceMs; else ctx->stats.msClosest += ctx->lastTraceMs;
+  return HC_OK;
+}
+
+int hc_make_shadow_rays(hc_ctx* ctx, const float* rays8, const hc_hit* hits, int64_t n, const float lightPos[3], float* shadowRays8Out, int space)
+{
+  if (!ctx || !rays8 || !hits || !lightPos || !shadowRays8Out || n < 0) return HC_E_ARG;
+  if (n == 0) return HC_OK;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  const float4* dRays = (const float4*)rays8; const HcHit* dHits = (const HcHit*)hits; float4* dOut = (float4*)shadowRays8Out;
+  if (space == HC_HOST)
+  {
+    int rc = hc_buf_reserve(ctx, ctx->scratchRays, uint64_t(n)*64); if (rc) return rc;
+    rc = hc_buf_reserve(ctx, ctx->scratchOut, uint64_t(n)*16); if (rc) return rc;
+    HC_CUDA(cudaMemcpyAsync(ctx->scratchRays.ptr, rays8, uint64_t(n)*32, cudaMemcpyHostToDevice, ctx->stream));
+    HC_CUDA(cudaMemcpyAsync(ctx->scratchOut.ptr, hits, uint64_t(n)*16, cudaMemcpyHostToDevice, ctx->stream));
+    dRays = (const float4*)ctx->scratchRays.ptr; dHits = (const HcHit*)ctx->scratchOut.ptr; dOut = (float4*)ctx->scratchRays.ptr + 2*n;
+  }
+  const int block = 256; const int grid = int((n + block - 1)/block);
+  k_make_shadow_rays<<<grid, block, 0, ctx->stream>>>(dRays, dHits, n, make_float3(lightPos[0], lightPos[1], lightPos[2]), dOut);
+  HC_CUDA(cudaGetLastError());
+  ctx->stats.kernelLaunches++;
+  if (space == HC_HOST) HC_CUDA(cudaMemcpyAsync(shadowRays8Out, dOut, uint64_t(n)*32, cudaMemcpyDeviceToHost, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HC_OK;
+}
+
+int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull, uint8_t* visibleOutOrNull, int space)
+{
+  if (!ctx || !lightPos) return HC_E_ARG;
+  HC_REQUIRE(ctx->width > 0 && ctx->height > 0, HC_E_STATE, "hc_raycast_pass: call hc_resize first");
+  HC_REQUIRE(ctx->globals.ptr != nullptr, HC_E_STATE, "hc_raycast_pass: call hc_set_globals first");
+  HC_CUDA(cudaSetDevice(ctx->device));
+  const long long n = (long long)ctx->width*ctx->height;
+  int rc;
+  if ((rc = hc_buf_reserve(ctx, ctx->rcRays, uint64_t(n)*32))) return rc;
+  if ((rc = hc_buf_reserve(ctx, ctx->rcHits, uint64_t(n)*16))) return rc;
+  if ((rc = hc_buf_reserve(ctx, ctx->rcSRays, uint64_t(n)*32))) return rc;
+  if ((rc = hc_buf_reserve(ctx, ctx->rcVis, uint64_t(n)))) return rc;
+  float4* rays = (float4*)ctx->rcRays.ptr; HcHit* hits = (HcHit*)ctx->rcHits.ptr; float4* srays = (float4*)ctx->rcSRays.ptr;
+  unsigned char* vis = (unsigned char*)ctx->rcVis.ptr;
+  const HcCamera cam = hc_camera_from_globals(ctx->globalsHead.data());
+  const int block = 256; const int grid = int((n + block - 1)/block);
+
+  HC_CUDA(cudaEventRecord(ctx->evStage[0], ctx->stream));
+  k_make_eye_rays<<<grid, block, 0, ctx->stream>>>(cam, ctx->width, ctx->height, nullptr, rays);
+  HC_CUDA(cudaGetLastError());
+  HC_CUDA(cudaEventRecord(ctx->evStage[1], ctx->stream));
+  if ((rc = hc_launch_trace(ctx, false, rays, rays + 1, 2, n, hits, nullptr))) return rc;
+  HC_CUDA(cudaEventRecord(ctx->evStage[2], ctx->stream));
+  k_make_shadow_rays<<<grid, block, 0, ctx->stream>>>(rays, hits, n, make_float3(lightPos[0], lightPos[1], lightPos[2]), srays);
+  HC_CUDA(cudaGetLastError());
+  HC_CUDA(cudaEventRecord(ctx->evStage[3], ctx->stream));
+  if ((rc = hc_launch_trace(ctx, true, srays, srays + 1, 2, n, nullptr, vis))) return rc;
+  HC_CUDA(cudaEventRecord(ctx->evStage[4], ctx->stream));
+  ctx->stats.kernelLaunches += 2;
+  ctx->stats.paths += (uint64_t)n;
+  if (hitsOutOrNull) HC_CUDA(cudaMemcpyAsync(hitsOutOrNull, hits, uint64_t(n)*16, space == HC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+  if (visibleOutOrNull) HC_CUDA(cudaMemcpyAsync(visibleOutOrNull, vis, uint64_t(n), space == HC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms[4];
+  for (int i = 0; i < 4; i++) HC_CUDA(cudaEventElapsedTime(&ms[i], ctx->evStage[i], ctx->evStage[i + 1]));
+  ctx->stats.msOther += ms[0] + ms[2]; ctx->stats.msClosest += ms[1]; ctx->stats.msShadow += ms[3];
+  ctx->lastTraceMs = ms[0] + ms[1] + ms[2] + ms[3];
   return HC_OK;
 }
 

@@ -21,22 +21,6 @@ struct HcDevBuf
   uint64_t bytes = 0;
 };
 
-// per-path wavefront state, structure of arrays, double buffered by the compacting shade kernel (see hc_path.cuh)
-struct HcPathBuffers
-{
-  float4* rpos[2]   = { nullptr, nullptr };   // xyz = ray origin, w = misPrev.matSamplePdf
-  float4* rdir[2]   = { nullptr, nullptr };   // xyz = ray direction, w = as_float(flags)
-  float4* thr[2]    = { nullptr, nullptr };   // xyz = path throughput, w = as_float(pixel index | specular bit 31)
-  float4* accum[2]  = { nullptr, nullptr };   // xyz = radiance gathered so far, w = unused
-  uint2*  rng[2]    = { nullptr, nullptr };   // RandomGen state (crandom.h:10-17)
-  unsigned* qpos[2] = { nullptr, nullptr };   // QMC sample index of the path (PT_QMC only)
-  HcHit*  hits      = nullptr;
-  float4* spos      = nullptr;                // shadow ray origin, w = max distance (0 = no shadow ray)
-  float4* sdir      = nullptr;                // shadow ray direction, w = unused
-  float4* sexp      = nullptr;                // xyz = throughput * unshadowed explicit light, w = as_float(slot of the path in the NEXT state buffer or ~0)
-  int64_t capacity  = 0;
-};
-
 struct hc_ctx
 {
   int          device = 0;
@@ -59,11 +43,13 @@ struct hc_ctx
 
   // ray-casting scratch (hc_trace_* with HC_HOST buffers)
   HcDevBuf scratchRays, scratchOut;
+  HcDevBuf rcRays, rcHits, rcSRays, rcVis;  // hc_raycast_pass working set (device resident)
+  cudaEvent_t evStage[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
   HcDevBuf counters;                       // device: [0] persistent-thread ray counter, [1..] compaction counters
   float    lastTraceMs = 0.0f;
 
   // path tracing
-  HcPathBuffers paths;
+  void*    pathHost = nullptr;             // HcPathHost (hc_path.cu): double-buffered SoA path state, hit / visibility buffers, tile ownership
   int      seed = 0;
   bool     ptReady = false;
   int      tileSize = 32, rank = 0, worldSize = 1;
@@ -73,10 +59,12 @@ struct hc_ctx
 
   hc_stats stats{};
   int traceGrid = 0;
+  int traceCounterSlot = 0;
 };
 
 int hc_buf_reserve(hc_ctx* ctx, HcDevBuf& b, uint64_t bytes);   // grow-only
 void hc_buf_free(HcDevBuf& b);
 
 void hc_path_free(hc_ctx* ctx);   // hc_path.cu
+int  hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis);
 int  hc_launch_trace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, HcHit* hits, unsigned char* vis);   // hc_api.cu

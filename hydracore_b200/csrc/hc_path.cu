@@ -1,14 +1,610 @@
-// hc_path.cu — path tracing entry points (placeholder until the shading kernels land)
+// hc_path.cu — wavefront path tracing: K1 (eye paths), K3+K4+K5 (one fused shade kernel per bounce), K6 (warp-aggregated
+// compaction inside the shade kernel), K7 (per-pixel HDR accumulation), and the C-ABI entry points that drive them.
+//
+// What it reproduces: the CPU oracle integrators IntegratorMISPTLoop2::PathTrace (reference hydra_drv/CPUExp_Integrators_PT_Loop.cpp:
+// 264-321, the one CPUExpLayer instantiates), IntegratorStupidPT::PathTrace (CPUExp_Integrators_PT.cpp:9-38) and
+// IntegratorMISPT_QMC::DoPass (CPUExp_Integrators_PT_QMC.cpp:5-49) under IntegratorCommon::DoPass (CPUExp_Integrators_Common.cpp:278-316),
+// with the per-pixel generator rule of InitRandomGen (shaders/trace.cl:6-13): gen[p] = RandomGenInit(seed + p), carried across passes.
+//
+// How it differs from the OpenCL wavefront (GPUOCLLayerCore.cpp:9-130: 6-8 launches per bounce, ~650 B of state streamed per path per
+// bounce, no compaction): per bounce there are three launches — closest-hit traversal, any-hit traversal of the previous bounce's
+// shadow rays, and ONE shade kernel that evaluates the surface, emission/MIS, samples the light, evaluates the BSDF for it, samples the
+// next direction, updates the path and writes the survivors densely into the other half of a double-buffered SoA state (ballot/popc
+// ranks, one atomic per warp).  The unshadowed direct-light term travels with the shadow ray and is added when visibility is known.
+// Nothing is read back between bounces: every kernel takes its element count from device memory.
 #include "hc_context.h"
-void hc_path_free(hc_ctx*) {}
-extern "C" {
-int hc_resize(hc_ctx* ctx, int width, int height) { if (!ctx || width <= 0 || height <= 0) return HC_E_ARG; ctx->width = width; ctx->height = height; return HC_OK; }
-int hc_pt_init(hc_ctx*, int) { hc_set_error("not implemented"); return HC_E_STATE; }
-int hc_pt_set_tiles(hc_ctx*, int, int, int) { hc_set_error("not implemented"); return HC_E_STATE; }
-int hc_pt_pass(hc_ctx*, int, int) { hc_set_error("not implemented"); return HC_E_STATE; }
-int hc_fb_clear(hc_ctx*) { hc_set_error("not implemented"); return HC_E_STATE; }
-int hc_fb_device_ptr(hc_ctx*, float**, int64_t*) { hc_set_error("not implemented"); return HC_E_STATE; }
-int hc_fb_read_hdr(hc_ctx*, float*, int, int) { hc_set_error("not implemented"); return HC_E_STATE; }
-int hc_fb_read_ldr(hc_ctx*, uint32_t*, int, int) { hc_set_error("not implemented"); return HC_E_STATE; }
-int hc_get_spp(hc_ctx*, float*) { hc_set_error("not implemented"); return HC_E_STATE; }
+#include "hc_shade.cuh"
+#include "hc_raygen.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#define HC_SHADE_BLOCK 128
+
+struct HcPathState          // one half of the double buffer
+{
+  float4* rpos; float4* rdir; float4* thr; float4* accum; uint2* rng; unsigned* qpos;
+  float4* spos; float4* sdir; float4* sexp;
+};
+
+struct HcPassParams
+{
+  int integrator;           // HC_INTEGRATOR_*
+  int width, height;
+  int maxDepth;             // m_maxDepth of the oracle integrator
+  int depth;                // bounce index of this shade launch
+  int isLast;               // last bounce of the pass
+  unsigned qmcPass;         // passes done so far (QMC sample index = pass*W*H + i)
+  int world, rank;
+};
+
+// ------------------------------------------------------------------------------------------------------------------ K1: eye paths
+// PT/MISPT: IntegratorCommon::makeEyeRay (CPUExp_Integrators_Common.cpp:347-359): rndUniform(-1, 1) -> MakeRandEyeRay.
+// QMC     : rndLens with the Niederreiter table (crandom.h:369-391) -> MakeEyeRayFromF4Rnd, pixel = (int)fx, (int)fy.
+__global__ void __launch_bounds__(256)
+k_pt_generate(const HcCamera cam, const HcPassParams pp, const int n, const int* __restrict__ ownedPixels, uint2* __restrict__ pixelRng,
+              const int* __restrict__ rmQMC, const unsigned* __restrict__ qmcTable, HcPathState st, int* __restrict__ pathCount)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i == 0) pathCount[0] = n;
+  if (i >= n) return;
+  float3 rpos, rdir; int pixel; unsigned qpos = 0xFFFFFFFFu;
+  HcRng g;
+  if (pp.integrator == HC_INTEGRATOR_MISPT_QMC)
+  {
+    const int sample = i*pp.world + pp.rank;                      // this GPU's share of the sample indices of the pass
+    const uint2 s2 = pixelRng[sample]; g.x = s2.x; g.y = s2.y;
+    qpos = pp.qmcPass*(unsigned)(pp.width*pp.height) + (unsigned)sample;
+    float4 lens;
+    lens.y = rndQmcTab(g, rmQMC, qpos, HC_QMC_VAR_SCR_Y, qmcTable);
+    lens.z = rndQmcTab(g, rmQMC, qpos, HC_QMC_VAR_DOF_X, qmcTable);
+    lens.w = rndQmcTab(g, rmQMC, qpos, HC_QMC_VAR_DOF_Y, qmcTable);
+    lens.x = rndQmcTab(g, rmQMC, qpos, HC_QMC_VAR_SCR_X, qmcTable);
+    float fx, fy;
+    MakeEyeRayFromF4Rnd(lens, cam, rpos, rdir, fx, fy);
+    int x = (int)fx, y = (int)fy;
+    if (x >= pp.width) x = pp.width - 1;
+    if (y >= pp.height) y = pp.height - 1;
+    if (x < 0) x = 0;
+    if (y < 0) y = 0;
+    pixel = y*pp.width + x;
+    // the generator of slot `sample` is written back when the path ends; remember the slot in qpos' companion: thr.w keeps the PIXEL,
+    // the slot is recoverable from qpos (qpos - pass*W*H)
+  }
+  else
+  {
+    pixel = ownedPixels[i];
+    const uint2 s2 = pixelRng[pixel]; g.x = s2.x; g.y = s2.y;
+    const float4 r = rndFloat4_Pseudo(g);
+    const float4 offs = make_float4(-1.0f + 2.0f*r.x, -1.0f + 2.0f*r.y, -1.0f + 2.0f*r.z, -1.0f + 2.0f*r.w);   // rndUniform(gen, -1, 1), crandom.h:617-620
+    MakeRandEyeRay(pixel % pp.width, pixel / pp.width, pp.width, pp.height, offs, cam, rpos, rdir);
+  }
+  st.rpos[i]  = make_float4(rpos.x, rpos.y, rpos.z, 1.0f);                          // makeInitialMisData: matSamplePdf = 1
+  st.rdir[i]  = make_float4(rdir.x, rdir.y, rdir.z, __uint_as_float(0u));           // flags = 0
+  st.thr[i]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float((unsigned)pixel | 0x80000000u));   // isSpecular = 1
+  st.accum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  st.rng[i]   = make_uint2(g.x, g.y);
+  if (st.qpos) st.qpos[i] = qpos;
+  st.sdir[i]  = make_float4(0.0f, 1.0f, 0.0f, 0.0f);                                // no pending shadow ray
+  st.spos[i]  = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  st.sexp[i]  = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
+
+// ------------------------------------------------------------------------------------------------------------------ K3+K4+K5+K6+K7: shade
+HC_DEV void FinishPath(float4* __restrict__ fb, uint2* __restrict__ pixelRng, int rngSlot, int pixel, float3 accum, const HcRng& g)
+{
+  // K7: per-pixel HDR SUM (the GPU layer keeps sums and divides by spp on read-back, GPUOCLLayer.cpp:1184-1215)
+  float* p = reinterpret_cast<float*>(fb + pixel);
+  atomicAdd(p + 0, accum.x); atomicAdd(p + 1, accum.y); atomicAdd(p + 2, accum.z);
+  pixelRng[rngSlot] = make_uint2(g.x, g.y);
+}
+
+__global__ void __launch_bounds__(HC_SHADE_BLOCK)
+k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, int* __restrict__ nOut,
+           const HcPathState in, HcPathState out, const HcHit* __restrict__ hits, const unsigned char* __restrict__ vis,
+           const unsigned* __restrict__ qmcTable, float4* __restrict__ fb, uint2* __restrict__ pixelRng)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  const int n = *nIn;
+  bool alive = false;
+
+  // new state of a surviving path
+  float3 nPos = f3(0, 0, 0), nDir = f3(0, 0, 0), thr = f3(0, 0, 0), accum = f3(0, 0, 0);
+  float nPdf = 1.0f; unsigned nFlags = 0, pixSpec = 0, qpos = 0xFFFFFFFFu;
+  float4 sPos = make_float4(0, 0, 0, 0), sDir = make_float4(0, 1, 0, 0), sExp = make_float4(0, 0, 0, 0);
+  HcRng g; g.x = 0; g.y = 0;
+
+  if (i < n)
+  {
+    const float4 rp = in.rpos[i], rd = in.rdir[i], th = in.thr[i], ac = in.accum[i];
+    const uint2 r2 = in.rng[i]; g.x = r2.x; g.y = r2.y;
+    if (in.qpos) qpos = in.qpos[i];
+    const float3 rayPos = f3(rp), rayDir = f3(rd);
+    const unsigned flags = __float_as_uint(rd.w);
+    pixSpec = __float_as_uint(th.w);
+    const int pixel = int(pixSpec & 0x7FFFFFFFu);
+    const bool prevSpecular = (pixSpec & 0x80000000u) != 0;
+    const float prevPdf = rp.w;
+    const int rngSlot = (pp.integrator == HC_INTEGRATOR_MISPT_QMC) ? int(qpos - pp.qmcPass*(unsigned)(pp.width*pp.height)) : pixel;
+    thr = f3(th); accum = f3(ac);
+
+    // pending direct light of the previous bounce: accumColor += accumuThoroughput*explicitColor (PT_Loop.cpp:253), shadow in {0,1}
+    const float4 se = in.sexp[i];
+    if (in.sdir[i].w > 0.0f && vis[i] != 0) accum += f3(se);
+
+    const HcHit hit = hits[i];
+    const bool isPT = (pp.integrator == HC_INTEGRATOR_PT);
+    float3 curr = f3(0, 0, 0);
+    bool finished = false;
+
+    if (hit.primId == -1 || !isfinite(hit.t))                     // HitNone (cglobals.h:1270) -> environmentColor: no sky light -> black
+      finished = true;
+    else
+    {
+      const HcSurfaceHit sh = SurfaceEval(s, rayPos, rayDir, hit);
+      const float3 e = EmissionEval(s, rayPos, rayDir, sh, flags, hit.instId);
+      if (dot(e, e) > (isPT ? 1e-6f : 1e-3f))
+      {
+        if (isPT) curr = e;
+        else
+        {
+          const float* L = (s.lightsNum != 0) ? LightAt(s, s.instLightIds[hit.instId]) : nullptr;
+          if (L != nullptr)
+          {                                                       // kernel_EvalEmission (PT_Loop.cpp:86-139)
+            const float hitDist = length(rayPos - sh.pos);
+            const float lgtPdf = L[HC_PLIGHT_PICK_PROB_REV]*AreaLightEvalPDF(L, rayDir, hitDist);
+            float w = misWeightHeuristic(prevPdf, lgtPdf);
+            if (prevSpecular) w = 1.0f;
+            curr = e*w;
+          }
+          else curr = e;
+        }
+        finished = true;
+      }
+      else if (!isPT && pp.depth >= pp.maxDepth - 1)
+        finished = true;                                          // curr = 0
+      else
+      {
+        const float* mat = MaterialAt(s, sh.matId);
+        float3 explicitColor = f3(0, 0, 0);
+        if (!isPT)
+        {
+          // kernel_LightSelect / LightSample / Shade (PT_Loop.cpp:141-216); .z picks the light AND is the third sample coordinate
+          const float4 rl = rndFloat4_Pseudo(g);
+          float pick = 1.0f;
+          const int lightOffset = SelectRandomLightRev(rl.z, s, pick);
+          if (lightOffset >= 0)
+          {
+            const float* L = LightAt(s, lightOffset);
+            HcShadowSample sam;
+            AreaLightSampleRev(L, f3(rl.x, rl.y, rl.z), sh.pos, sam);
+            const float3 sdir = normalize(sam.pos - sh.pos);
+            const float3 spos = OffsShadowRayPos(sh.pos, sh.normal, sdir, sh.sRayOff);
+            const float tFar = length(spos - sam.pos)*0.995f;
+            const HcBxDF ev = MaterialEval(mat, sdir, (-1.0f)*rayDir, sh.normal, sh.texCoord, s);
+            const float c1 = fmaxf(+dot(sdir, sh.normal), 0.0f), c2 = fmaxf(-dot(sdir, sh.normal), 0.0f);
+            const float3 bx = (ev.brdf*c1 + ev.btdf*c2);
+            const float lgtPdf = sam.pdf*pick;
+            float w = misWeightHeuristic(lgtPdf, ev.pdfFwd);
+            if (sam.isPoint) w = 1.0f;
+            explicitColor = (1.0f/pick)*(sam.color*(1.0f/fmaxf(sam.pdf, HC_DEPSILON2)))*bx*w;
+            sPos = make_float4(spos.x, spos.y, spos.z, 0.0f);
+            sDir = make_float4(sdir.x, sdir.y, sdir.z, tFar);
+          }
+        }
+
+        // kernel_NextBounce (PT_Loop.cpp:218-256) / sampleAndEvalBxDF (CPUExp_Integrators_Common.cpp:528-556): RndMatAll then sample
+        const unsigned sampFlags = isPT ? 0u : flags;             // IntegratorStupidPT calls sampleAndEvalBxDF with its default flags = 0
+        const int bounceNum = int((sampFlags & 0x0000FF00u) >> 8);
+        const bool qmc = (pp.integrator == HC_INTEGRATOR_MISPT_QMC) && bounceNum == 0;
+        float rands[HC_MMLT_FLOATS_PER_BOUNCE];
+        if (qmc)
+        {
+          rands[0] = rndQmcTab(g, s.globals + HC_EG_rmQMC/4, qpos, HC_QMC_VAR_MAT_0, qmcTable);
+          rands[1] = rndQmcTab(g, s.globals + HC_EG_rmQMC/4, qpos, HC_QMC_VAR_MAT_1, qmcTable);
+          rands[2] = rndFloat1_Pseudo(g);
+          for (int k = 0; k < HC_MMLT_FLOATS_PER_MLAYER; k++) rands[3 + k] = rndQmcTab(g, s.globals + HC_EG_rmQMC/4, qpos, HC_QMC_VAR_MAT_L, qmcTable);
+        }
+        else
+        {
+          const float4 rm = rndFloat4_Pseudo(g);
+          rands[0] = rm.x; rands[1] = rm.y; rands[2] = rm.z;
+          for (int k = 0; k < HC_MMLT_FLOATS_PER_MLAYER; k++) rands[3 + k] = rndFloat1_Pseudo(g);
+        }
+        HcMatSample ms;
+        MaterialSampleAndEval(mat, rands, sh, rayDir, sampFlags, s, ms);
+        const float3 bxdfVal = ms.color*(1.0f/fmaxf(ms.pdf, isPT ? HC_DEPSILON2 : 1e-20f));
+        const float cosTheta = fabsf(dot(ms.direction, sh.normal));
+
+        sExp = make_float4(thr.x*explicitColor.x, thr.y*explicitColor.y, thr.z*explicitColor.z, 0.0f);
+        thr *= cosTheta*bxdfVal;
+        nDir = ms.direction;
+        nPos = OffsRayPos(sh.pos, sh.normal, ms.direction);
+        nPdf = ms.pdf;
+        nFlags = FlagsNextBounceLite(flags, ms, s);
+        const bool spec = (ms.flags & HC_RAY_EVENT_S) != 0 || (ms.flags & HC_RAY_EVENT_T) != 0;
+        pixSpec = (unsigned)pixel | (spec ? 0x80000000u : 0u);
+        if (pp.isLast) finished = true;                           // PT: the recursion returns 0 one level deeper; draws are already made
+        else alive = true;
+      }
+    }
+
+    if (finished)
+    {
+      accum += thr*curr;                                          // kernel_AddLastBouceContrib (PT_Loop.cpp:258-262)
+      FinishPath(fb, pixelRng, rngSlot, pixel, accum, g);
+    }
+  }
+
+  // K6: warp-aggregated compaction — survivors of a warp take consecutive slots, one atomic per warp
+  const unsigned mask = __ballot_sync(0xffffffffu, alive);
+  if (mask == 0u) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(nOut, __popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (alive)
+  {
+    const int j = base + __popc(mask & ((1u << lane) - 1u));
+    out.rpos[j]  = make_float4(nPos.x, nPos.y, nPos.z, nPdf);
+    out.rdir[j]  = make_float4(nDir.x, nDir.y, nDir.z, __uint_as_float(nFlags));
+    out.thr[j]   = make_float4(thr.x, thr.y, thr.z, __uint_as_float(pixSpec));
+    out.accum[j] = make_float4(accum.x, accum.y, accum.z, 0.0f);
+    out.rng[j]   = make_uint2(g.x, g.y);
+    if (out.qpos) out.qpos[j] = qpos;
+    out.spos[j] = sPos; out.sdir[j] = sDir; out.sexp[j] = sExp;
+  }
+}
+
+// K2 / K2s wrappers reading the ray count from device memory live in hc_api.cu (hc_launch_trace_counted)
+int hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis);
+
+// init pixel generators: InitRandomGen (shaders/trace.cl:6-13) with tid = pixel index
+__global__ void k_init_rng(uint2* __restrict__ gen, int n, int seed)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const HcRng g = RandomGenInit(seed + i);
+  gen[i] = make_uint2(g.x, g.y);
+}
+
+// GetLDRImage: clamp to 1 (ToneMapping4, cglobals.h:698), pow(x, 1/gamma) as the GPU layer does (shaders/screen.cl:457-460), RealColorToUint32 (cglobals.h:711-724)
+__global__ void k_hdr_to_ldr(const float4* __restrict__ fb, unsigned* __restrict__ out, int n, float invSpp, float invGamma)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 c = fb[i]*invSpp;
+  c.x = powf(fminf(c.x, 1.0f), invGamma); c.y = powf(fminf(c.y, 1.0f), invGamma); c.z = powf(fminf(c.z, 1.0f), invGamma); c.w = fminf(c.w, 1.0f);
+  const unsigned r = (unsigned char)(c.x*255.0f), g = (unsigned char)(c.y*255.0f), b = (unsigned char)(c.z*255.0f), a = (unsigned char)(c.w*255.0f);
+  out[i] = r | (g << 8) | (b << 16) | (a << 24);
+}
+
+// ------------------------------------------------------------------------------------------------------------------ host side
+struct HcPathHost
+{
+  HcDevBuf state[2][9];       // rpos rdir thr accum rng qpos spos sdir sexp
+  HcDevBuf hits, vis, owned, pathCount, ldr;
+  std::vector<unsigned char> materialsHost, globalsHost;
+  int64_t capacity = 0;
+  int nOwned = 0;
+};
+static HcPathHost* PH(hc_ctx* c) { return reinterpret_cast<HcPathHost*>(c->pathHost); }
+
+void hc_path_free(hc_ctx* ctx)
+{
+  HcPathHost* p = PH(ctx);
+  if (!p) return;
+  for (int b = 0; b < 2; b++) for (int k = 0; k < 9; k++) hc_buf_free(p->state[b][k]);
+  hc_buf_free(p->hits); hc_buf_free(p->vis); hc_buf_free(p->owned); hc_buf_free(p->pathCount); hc_buf_free(p->ldr);
+  delete p;
+  ctx->pathHost = nullptr;
+}
+
+static HcPathHost* EnsureHost(hc_ctx* ctx)
+{
+  if (!PH(ctx)) ctx->pathHost = new HcPathHost;
+  return PH(ctx);
+}
+
+static int ReserveState(hc_ctx* ctx, int64_t n, bool qmc)
+{
+  HcPathHost* p = EnsureHost(ctx);
+  static const int elem[9] = { 16, 16, 16, 16, 8, 4, 16, 16, 16 };
+  for (int b = 0; b < 2; b++)
+    for (int k = 0; k < 9; k++)
+    {
+      if (k == 5 && !qmc) continue;
+      int rc = hc_buf_reserve(ctx, p->state[b][k], uint64_t(n)*elem[k]); if (rc) return rc;
+    }
+  int rc;
+  if ((rc = hc_buf_reserve(ctx, p->hits, uint64_t(n)*16))) return rc;
+  if ((rc = hc_buf_reserve(ctx, p->vis, uint64_t(n)))) return rc;
+  if ((rc = hc_buf_reserve(ctx, p->pathCount, 256*sizeof(int)))) return rc;
+  p->capacity = n;
+  return HC_OK;
+}
+
+static HcPathState StateOf(HcPathHost* p, int b, bool qmc)
+{
+  HcPathState s;
+  s.rpos = (float4*)p->state[b][0].ptr; s.rdir = (float4*)p->state[b][1].ptr; s.thr = (float4*)p->state[b][2].ptr;
+  s.accum = (float4*)p->state[b][3].ptr; s.rng = (uint2*)p->state[b][4].ptr; s.qpos = qmc ? (unsigned*)p->state[b][5].ptr : nullptr;
+  s.spos = (float4*)p->state[b][6].ptr; s.sdir = (float4*)p->state[b][7].ptr; s.sexp = (float4*)p->state[b][8].ptr;
+  return s;
+}
+
+static int BuildOwnedPixels(hc_ctx* ctx)
+{
+  HcPathHost* p = EnsureHost(ctx);
+  const int W = ctx->width, H = ctx->height, T = std::max(1, ctx->tileSize);
+  const int tx = (W + T - 1)/T, ty = (H + T - 1)/T;
+  std::vector<int> owned; owned.reserve(size_t(W)*H/std::max(1, ctx->worldSize) + 1024);
+  for (int t = 0; t < tx*ty; t++)
+  {
+    if (t % ctx->worldSize != ctx->rank) continue;          // interleaved tile ownership: tile t -> GPU t mod G
+    const int x0 = (t % tx)*T, y0 = (t / tx)*T;
+    for (int y = y0; y < std::min(H, y0 + T); y++)
+      for (int x = x0; x < std::min(W, x0 + T); x++) owned.push_back(y*W + x);
+  }
+  p->nOwned = int(owned.size());
+  int rc = hc_buf_reserve(ctx, p->owned, std::max<size_t>(owned.size(), 1)*sizeof(int)); if (rc) return rc;
+  if (!owned.empty()) HC_CUDA(cudaMemcpyAsync(p->owned.ptr, owned.data(), owned.size()*sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HC_OK;
+}
+
+// reject what the kernels do not implement — loudly, at init time
+static int ValidateScene(hc_ctx* ctx, std::string& why)
+{
+  const unsigned char* g = ctx->globalsHead.data();
+  auto gi = [&](int off) { int v; memcpy(&v, g + off, 4); return v; };
+  if (gi(HC_EG_skyLightId) != -1) { why = "sky-dome lights are not supported yet"; return HC_E_ARG; }
+  if (gi(HC_EG_sunNumber) != 0) { why = "sun lights are not supported yet"; return HC_E_ARG; }
+  HcPathHost* p = PH(ctx);
+  const std::vector<unsigned char>& gl = p->globalsHost;
+  const int lightsNum = gi(HC_EG_lightsNum), lightsOffset = gi(HC_EG_lightsOffset);
+  for (int l = 0; l < lightsNum; l++)
+  {
+    const float* L = reinterpret_cast<const float*>(gl.data()) + lightsOffset + l*HC_LIGHT_DATA_SIZE;
+    int type, flags, tex, spot; memcpy(&type, L + HC_PLIGHT_TYPE, 4); memcpy(&flags, L + HC_PLIGHT_FLAGS, 4);
+    memcpy(&tex, L + HC_PLIGHT_COLOR_TEX, 4); memcpy(&spot, L + HC_AREA_LIGHT_SPOT_DISTR, 4);
+    if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "only area lights (PLAIN_LIGHT_TYPE_AREA) are supported yet"; return HC_E_ARG; }
+    if (flags & (HC_LIGHT_HAS_IES | HC_AREA_LIGHT_SKY_PORTAL | HC_LIGHT_IES_POINT_AREA)) { why = "IES / sky-portal area lights are not supported yet"; return HC_E_ARG; }
+    if (tex != HC_INVALID_TEXTURE) { why = "textured area lights are not supported yet"; return HC_E_ARG; }
+    if (spot != 0) { why = "area lights with a spot distribution are not supported yet"; return HC_E_ARG; }
+  }
+  const size_t nNodes = p->materialsHost.size()/(HC_PLAIN_MATERIAL_DATA_SIZE*4);
+  for (size_t k = 0; k < nNodes; k++)
+  {
+    const float* m = reinterpret_cast<const float*>(p->materialsHost.data()) + k*HC_PLAIN_MATERIAL_DATA_SIZE;
+    int type, flags, ntex, ptex; memcpy(&type, m + HC_PLAIN_MAT_TYPE_OFFSET, 4); memcpy(&flags, m + HC_PLAIN_MAT_FLAGS_OFFSET, 4);
+    memcpy(&ntex, m + HC_NORMAL_TEX_OFFSET, 4); memcpy(&ptex, m + HC_PROC_TEX1_F4_HEAD_OFFSET, 4);
+    const bool ok = type == HC_PLAIN_MAT_CLASS_LAMBERT || type == HC_PLAIN_MAT_CLASS_PHONG_SPECULAR || type == HC_PLAIN_MAT_CLASS_GGX ||
+                    type == HC_PLAIN_MAT_CLASS_PERFECT_MIRROR || type == HC_PLAIN_MAT_CLASS_GLASS || type == HC_PLAIN_MAT_CLASS_BLEND_MASK ||
+                    type == HC_PLAIN_MAT_CLASS_EMISSIVE;
+    if (!ok) { why = "material class " + std::to_string(type) + " is not supported yet (Lambert, Phong, GGX, mirror, glass, blend mask are)"; return HC_E_ARG; }
+    if (ntex != HC_INVALID_TEXTURE) { why = "normal maps are not supported yet (set NORMAL_TEX_OFFSET to INVALID_TEXTURE)"; return HC_E_ARG; }
+    if (ptex != HC_INVALID_TEXTURE) { why = "procedural textures are not supported yet"; return HC_E_ARG; }
+    if (type == HC_PLAIN_MAT_CLASS_GLASS && (flags & HC_PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER)) { why = "glass multiscattering table is not supported yet"; return HC_E_ARG; }
+    if (type == HC_PLAIN_MAT_CLASS_BLEND_MASK)
+    {
+      int bf; memcpy(&bf, m + HC_BLEND_MASK_FLAGS_OFFSET, 4);
+      if (bf & HC_BLEND_MASK_FALOFF) { why = "falloff blend masks are not supported yet"; return HC_E_ARG; }
+    }
+  }
+  return HC_OK;
+}
+
+static HcScene MakeScene(hc_ctx* ctx)
+{
+  const unsigned char* g = ctx->globalsHead.data();
+  auto gi = [&](int off) { int v; memcpy(&v, g + off, 4); return v; };
+  HcScene s;
+  s.globals = (const int*)ctx->globals.ptr;
+  s.geom = (const float4*)ctx->storage[HC_STORAGE_GEOM].ptr;
+  s.materials = (const float4*)ctx->storage[HC_STORAGE_MATERIALS].ptr;
+  s.textures = (const int4*)ctx->storage[HC_STORAGE_TEXTURES].ptr;
+  s.instMatrices = (const float4*)ctx->instMatrices.ptr;
+  s.instLightIds = (const int*)ctx->instLightIds.ptr;
+  s.materialsTableOffset = gi(HC_EG_materialsTableOffset); s.geometryTableOffset = gi(HC_EG_geometryTableOffset);
+  s.texturesTableOffset = gi(HC_EG_texturesTableOffset);
+  s.lightSelTableOffsetRev = gi(HC_EG_lightSelectorTableOffsetRev); s.lightSelTableSizeRev = gi(HC_EG_lightSelectorTableSizeRev);
+  s.lightsOffset = gi(HC_EG_lightsOffset); s.lightsNum = gi(HC_EG_lightsNum); s.skyLightId = gi(HC_EG_skyLightId);
+  s.gflags = gi(HC_EG_g_flags);
+  s.traceDepth = gi(HC_EG_varsI + 4*HC_HRT_TRACE_DEPTH); s.diffTraceDepth = gi(HC_EG_varsI + 4*HC_HRT_DIFFUSE_TRACE_DEPTH);
+  s.essGgxTableOffsetBytes = HC_EG_m_essGgx2017Table;
+  return s;
+}
+
+// Niederreiter base-2 table, 11 dimensions x 31 bits (Bratley-Fox-Niederreiter, TOMS 738; what initQuasirandomGenerator builds,
+// qmc_sobol_niederreiter.cpp:75-186): per dimension an irreducible polynomial p over GF(2); every deg(p) columns the running power
+// b = p^q gains one more factor p and its recurrence generates the next rows.  Only the top 31 of 63 bits are kept.
+static void BuildQmcTable(unsigned table[HC_QRNG_DIMENSIONS_K][HC_QRNG_RESOLUTION_K])
+{
+  static const unsigned long long irred[HC_QRNG_DIMENSIONS_K] = { 2, 3, 7, 11, 13, 19, 25, 31, 37, 41, 47 };
+  auto deg = [](unsigned long long p) { int d = -1; while (p) { d++; p >>= 1; } return d; };
+  auto mul = [](unsigned long long a, unsigned long long b) { unsigned long long r = 0; while (b) { if (b & 1) r ^= a; a <<= 1; b >>= 1; } return r; };
+  for (int dim = 0; dim < HC_QRNG_DIMENSIONS_K; dim++)
+  {
+    const unsigned long long p = irred[dim]; const int e = deg(p);
+    unsigned long long cj[63]; for (auto& c : cj) c = 0;
+    unsigned long long b = 1; int m = 0, u = e; int v[96];
+    for (int j = 62; j >= 32; --j, ++u)
+    {
+      if (u == e)
+      {
+        u = 0; const int m1 = m; b = mul(b, p); m += e;
+        for (int i = 0; i < m1; i++) v[i] = 0;
+        for (int i = m1; i < m; i++) v[i] = 1;
+        for (int i = m; i <= 63 + e - 2; i++) { int a = 0; for (int k = 1; k <= m; k++) a ^= v[i - k] & int((b >> (m - k)) & 1ull); v[i] = a; }
+      }
+      for (int i = 0; i < 63; i++) cj[i] |= (unsigned long long)v[i + u] << j;
+    }
+    for (int bit = 0; bit < HC_QRNG_RESOLUTION_K; bit++) table[dim][bit] = (unsigned)((cj[bit] >> 32) & 0x7FFFFFFFu);
+  }
+}
+
+extern "C"
+{
+int hc_resize(hc_ctx* ctx, int width, int height)
+{
+  if (!ctx || width <= 0 || height <= 0) return HC_E_ARG;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  ctx->width = width; ctx->height = height; ctx->ptReady = false;
+  int rc = hc_buf_reserve(ctx, ctx->fbSum, uint64_t(width)*height*16); if (rc) return rc;
+  HC_CUDA(cudaMemsetAsync(ctx->fbSum.ptr, 0, uint64_t(width)*height*16, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->spp = 0.0; ctx->passCounter = 0;
+  return HC_OK;
+}
+
+int hc_pt_set_tiles(hc_ctx* ctx, int tileSize, int rank, int worldSize)
+{
+  if (!ctx || tileSize <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) return HC_E_ARG;
+  ctx->tileSize = tileSize; ctx->rank = rank; ctx->worldSize = worldSize; ctx->ptReady = false;
+  return HC_OK;
+}
+
+int hc_pt_init(hc_ctx* ctx, int seed)
+{
+  if (!ctx) return HC_E_ARG;
+  HC_REQUIRE(ctx->width > 0 && ctx->height > 0, HC_E_STATE, "hc_pt_init: call hc_resize first");
+  HC_REQUIRE(ctx->globals.ptr && ctx->bvhNodes.ptr && ctx->instMatrices.ptr && ctx->instLightIds.ptr, HC_E_STATE,
+             "hc_pt_init: scene incomplete (globals, BVH, instance matrices and instance light ids are required)");
+  HC_REQUIRE(ctx->storage[HC_STORAGE_GEOM].ptr && ctx->storage[HC_STORAGE_MATERIALS].ptr, HC_E_STATE, "hc_pt_init: geom / materials storage missing");
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HcPathHost* p = EnsureHost(ctx);
+  // host mirrors for validation (materials are small; the globals blob carries the lights)
+  p->materialsHost.resize(ctx->storage[HC_STORAGE_MATERIALS].bytes);
+  HC_CUDA(cudaMemcpy(p->materialsHost.data(), ctx->storage[HC_STORAGE_MATERIALS].ptr, p->materialsHost.size(), cudaMemcpyDeviceToHost));
+  p->globalsHost.resize(ctx->globals.bytes);
+  HC_CUDA(cudaMemcpy(p->globalsHost.data(), ctx->globals.ptr, p->globalsHost.size(), cudaMemcpyDeviceToHost));
+  std::string why;
+  int rc = ValidateScene(ctx, why);
+  if (rc) { hc_set_error(("hc_pt_init: " + why).c_str()); return rc; }
+
+  const int n = ctx->width*ctx->height;
+  if ((rc = hc_buf_reserve(ctx, ctx->pixelRng, uint64_t(n)*8))) return rc;
+  k_init_rng<<<(n + 255)/256, 256, 0, ctx->stream>>>((uint2*)ctx->pixelRng.ptr, n, seed);
+  HC_CUDA(cudaGetLastError());
+  unsigned table[HC_QRNG_DIMENSIONS_K][HC_QRNG_RESOLUTION_K];
+  BuildQmcTable(table);
+  if ((rc = hc_buf_reserve(ctx, ctx->qmcTable, sizeof(table)))) return rc;
+  HC_CUDA(cudaMemcpyAsync(ctx->qmcTable.ptr, table, sizeof(table), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = BuildOwnedPixels(ctx))) return rc;
+  HC_CUDA(cudaMemsetAsync(ctx->fbSum.ptr, 0, uint64_t(n)*16, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->seed = seed; ctx->spp = 0.0; ctx->passCounter = 0; ctx->ptReady = true;
+  ctx->stats.kernelLaunches++;
+  return HC_OK;
+}
+
+int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
+{
+  if (!ctx || passes < 0) return HC_E_ARG;
+  HC_REQUIRE(integrator == HC_INTEGRATOR_PT || integrator == HC_INTEGRATOR_MISPT || integrator == HC_INTEGRATOR_MISPT_QMC, HC_E_ARG, "hc_pt_pass: unknown integrator");
+  HC_REQUIRE(ctx->ptReady, HC_E_STATE, "hc_pt_pass: call hc_pt_init first (after the scene, the screen size and the tiles are set)");
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HcPathHost* p = PH(ctx);
+  const bool qmc = (integrator == HC_INTEGRATOR_MISPT_QMC);
+  const int W = ctx->width, H = ctx->height;
+  const int n = qmc ? ((W*H - ctx->rank + ctx->worldSize - 1)/ctx->worldSize) : p->nOwned;
+  if (n <= 0) return HC_OK;
+  int rc = ReserveState(ctx, n, qmc); if (rc) return rc;
+  p = PH(ctx);
+  const HcScene scn = MakeScene(ctx);
+  const HcCamera cam = hc_camera_from_globals(ctx->globalsHead.data());
+  HcPassParams pp;
+  pp.integrator = integrator; pp.width = W; pp.height = H; pp.world = ctx->worldSize; pp.rank = ctx->rank;
+  pp.maxDepth = (integrator == HC_INTEGRATOR_PT) ? scn.traceDepth + 1 : scn.traceDepth;     // IntegratorStupidPT::SetMaxDepth adds one (CPUExp_Integrators.h:333)
+  HC_REQUIRE(pp.maxDepth >= 1 && pp.maxDepth < 250, HC_E_ARG, "hc_pt_pass: HRT_TRACE_DEPTH out of range");
+  int* counts = (int*)p->pathCount.ptr;
+  const int* rmQMC = (const int*)ctx->globals.ptr + HC_EG_rmQMC/4;
+  const unsigned* qtab = (const unsigned*)ctx->qmcTable.ptr;
+  const int nBounces = (integrator == HC_INTEGRATOR_PT) ? pp.maxDepth : pp.maxDepth;       // MISPT finishes every path at depth maxDepth-1
+
+  for (int pass = 0; pass < passes; pass++)
+  {
+    pp.qmcPass = ctx->passCounter;
+    HC_CUDA(cudaMemsetAsync(counts, 0, 256*sizeof(int), ctx->stream));
+    HC_CUDA(cudaEventRecord(ctx->evStage[0], ctx->stream));
+    HcPathState st0 = StateOf(p, 0, qmc);
+    k_pt_generate<<<(n + 255)/256, 256, 0, ctx->stream>>>(cam, pp, n, (const int*)p->owned.ptr, (uint2*)ctx->pixelRng.ptr, rmQMC, qtab, st0, counts);
+    HC_CUDA(cudaGetLastError());
+    ctx->stats.kernelLaunches++; ctx->stats.paths += (uint64_t)n;
+    int cur = 0;
+    for (int depth = 0; depth < nBounces; depth++)
+    {
+      HcPathState in = StateOf(p, cur, qmc), out = StateOf(p, 1 - cur, qmc);
+      pp.depth = depth; pp.isLast = (depth == nBounces - 1) ? 1 : 0;
+      if ((rc = hc_launch_trace_counted(ctx, false, in.rpos, in.rdir, n, counts + depth, (HcHit*)p->hits.ptr, nullptr))) return rc;
+      if (depth > 0 && integrator != HC_INTEGRATOR_PT)
+        if ((rc = hc_launch_trace_counted(ctx, true, in.spos, in.sdir, n, counts + depth, nullptr, (unsigned char*)p->vis.ptr))) return rc;
+      k_pt_shade<<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, ctx->stream>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
+                   (const HcHit*)p->hits.ptr, (const unsigned char*)p->vis.ptr, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr);
+      HC_CUDA(cudaGetLastError());
+      ctx->stats.kernelLaunches++;
+      cur = 1 - cur;
+    }
+    HC_CUDA(cudaEventRecord(ctx->evStage[1], ctx->stream));
+    ctx->passCounter++;
+    ctx->spp += qmc ? double(n)*ctx->worldSize/double(W*H) : 1.0;
+  }
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.0f; HC_CUDA(cudaEventElapsedTime(&ms, ctx->evStage[0], ctx->evStage[1]));
+  ctx->lastTraceMs = ms;              // device time of the LAST pass
+  return HC_OK;
+}
+
+int hc_fb_clear(hc_ctx* ctx)
+{
+  if (!ctx || !ctx->fbSum.ptr) return HC_E_STATE;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HC_CUDA(cudaMemsetAsync(ctx->fbSum.ptr, 0, uint64_t(ctx->width)*ctx->height*16, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->spp = 0.0;
+  return HC_OK;
+}
+
+int hc_fb_device_ptr(hc_ctx* ctx, float** outSumRGBA, int64_t* outFloats)
+{
+  if (!ctx || !outSumRGBA || !ctx->fbSum.ptr) return HC_E_STATE;
+  *outSumRGBA = (float*)ctx->fbSum.ptr;
+  if (outFloats) *outFloats = int64_t(ctx->width)*ctx->height*4;
+  return HC_OK;
+}
+
+int hc_fb_read_hdr(hc_ctx* ctx, float* outRGBA, int width, int height)
+{
+  if (!ctx || !outRGBA) return HC_E_ARG;
+  HC_REQUIRE(width == ctx->width && height == ctx->height && ctx->fbSum.ptr, HC_E_ARG, "hc_fb_read_hdr: bad input resolution");
+  HC_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = size_t(width)*height*4;
+  HC_CUDA(cudaMemcpyAsync(outRGBA, ctx->fbSum.ptr, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->spp > 0.0) { const float inv = float(1.0/ctx->spp); for (size_t i = 0; i < n; i++) outRGBA[i] *= inv; }   // normalisation on read-back, GPUOCLLayer.cpp:1184-1215
+  return HC_OK;
+}
+
+int hc_fb_read_ldr(hc_ctx* ctx, uint32_t* outRGBA8, int width, int height)
+{
+  if (!ctx || !outRGBA8) return HC_E_ARG;
+  HC_REQUIRE(width == ctx->width && height == ctx->height && ctx->fbSum.ptr, HC_E_ARG, "hc_fb_read_ldr: bad input resolution");
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HcPathHost* p = EnsureHost(ctx);
+  const int n = width*height;
+  int rc = hc_buf_reserve(ctx, p->ldr, uint64_t(n)*4); if (rc) return rc;
+  const float* varsF = (const float*)(ctx->globalsHead.data() + HC_EG_varsF);
+  const float gamma = varsF[HC_HRT_IMAGE_GAMMA] > 0.0f ? varsF[HC_HRT_IMAGE_GAMMA] : 2.2f;
+  k_hdr_to_ldr<<<(n + 255)/256, 256, 0, ctx->stream>>>((const float4*)ctx->fbSum.ptr, (unsigned*)p->ldr.ptr, n, ctx->spp > 0.0 ? float(1.0/ctx->spp) : 1.0f, 1.0f/gamma);
+  HC_CUDA(cudaGetLastError());
+  ctx->stats.kernelLaunches++;
+  HC_CUDA(cudaMemcpyAsync(outRGBA8, p->ldr.ptr, uint64_t(n)*4, cudaMemcpyDeviceToHost, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HC_OK;
+}
+
+int hc_get_spp(hc_ctx* ctx, float* outSpp) { if (!ctx || !outSpp) return HC_E_ARG; *outSpp = float(ctx->spp); return HC_OK; }
+} // extern "C"

@@ -1,0 +1,933 @@
+// hc_shade.cuh — device functions of the shading half of the path: surface evaluation, software
+// textures, BSDF evaluation / sampling over the blend tree, area-light sampling, emission and MIS, path-flag update.
+//
+// These restate, in our own code, the reference's device math (hydra_drv/{ctrace,cfetch,cmaterial,clight,cbidir,cglobals}.h;
+// file:line cited per function).  Formulas, operation order and — where it changes rounding — the C++ promotion of the
+// reference's unqualified math calls to double (see hc_math.cuh) are kept, so that the same random numbers give the same
+// path on the GPU and in the CPU oracle.  Supported this round: Lambert, Phong, GGX (Heitz VNDF sampling), perfect mirror,
+// GGX glass, blend masks (simple / fresnel / sigmoid), emissive materials, rectangular and disk area lights, RGBA8 textures.
+// Everything else is rejected with an error at hc_pt_init (no silent fallback).
+#pragma once
+#include "hc_math.cuh"
+#include "hc_layout.h"
+#include "hc_trace.cuh"
+
+#define HC_GEPSILON   5e-6f      // cglobals.h:68-70
+#define HC_DEPSILON   1e-20f
+#define HC_DEPSILON2  1e-30f
+#define HC_INV_PI     0.31830988618379067154f
+#define HC_INV_TWOPI  0.15915494309189533577f
+#define HC_M_TWOPI    6.28318530717958647692f
+#define HC_PI_D       3.14159265358979323846     // M_PI comes from <math.h> as a DOUBLE in the oracle build (cglobals.h:43 is skipped)
+#define HC_INVALID_TEXTURE ((int)0xFFFFFFFE)
+
+HC_DEV double D(float x) { return (double)x; }
+
+// device view of everything the shading kernels read; filled on the host from the uploaded blobs
+struct HcScene
+{
+  const int*    __restrict__ globals;       // EngineGlobals + tables blob, indexed in ints from its base (cfetch.h:135-213)
+  const float4* __restrict__ geom;          // "geom" storage
+  const float4* __restrict__ materials;     // "materials" storage
+  const int4*   __restrict__ textures;      // "textures" storage
+  const float4* __restrict__ instMatrices;  // inverse instance matrices, 4 float4 each
+  const int*    __restrict__ instLightIds;  // instance -> light index or -1
+  int materialsTableOffset, geometryTableOffset, texturesTableOffset;
+  int lightSelTableOffsetRev, lightSelTableSizeRev, lightsOffset, lightsNum, skyLightId;
+  int gflags, traceDepth, diffTraceDepth;
+  int essGgxTableOffsetBytes;
+};
+
+struct HcSurfaceHit       // SurfaceHit, cglobals.h:2514-2528
+{
+  float3 pos, normal, flatNormal, tangent, biTangent;
+  float2 texCoord;
+  int    matId;
+  float  t, sRayOff;
+  bool   hfi;
+};
+
+struct HcMatSample { float3 color, direction; float pdf; int flags; };           // MatSample, cglobals.h:388-396
+struct HcBxDF { float3 brdf, btdf; float pdfFwd, pdfRev; bool diffuse; };       // BxDFResult, cmaterial.h:2373-2384
+struct HcShadowSample { float3 pos, color; float pdf, maxDist, cosAtLight; bool isPoint; };   // ShadowSample, cglobals.h:2448-2456
+
+// ------------------------------------------------------------------------------------------------------------------ a1: RandomGen
+struct HcRng { unsigned x, y; };
+HC_DEV unsigned NextState(HcRng& g)                       // crandom.h:19-25
+{
+  const unsigned x = g.x*17u + g.y*13123u;
+  g.x = (x << 13) ^ x;
+  g.y ^= (x << 7);
+  return x;
+}
+HC_DEV HcRng RandomGenInit(int seed)                      // crandom.h:27-43
+{
+  const unsigned s = (unsigned)seed;
+  HcRng g;
+  g.x = s*(s*s*15731u + 74323u) + 871483u;
+  g.y = s*(s*s*13734u + 37828u) + 234234u;
+  const int n = seed % 7;
+  for (int i = 0; i < n; i++) NextState(g);
+  return g;
+}
+HC_DEV float4 rndFloat4_Pseudo(HcRng& g)                  // crandom.h:51-63
+{
+  const unsigned x = NextState(g);
+  const unsigned x1 = x*(x*x*15731u + 74323u) + 871483u;
+  const unsigned y1 = x*(x*x*13734u + 37828u) + 234234u;
+  const unsigned z1 = x*(x*x*11687u + 26461u) + 137589u;
+  const unsigned w1 = x*(x*x*15707u + 789221u) + 1376312589u;
+  const float scale = 1.0f/4294967296.0f;
+  return make_float4((float)x1*scale, (float)y1*scale, (float)z1*scale, (float)w1*scale);
+}
+HC_DEV float rndFloat1_Pseudo(HcRng& g)                   // crandom.h:77-83
+{
+  const unsigned x = NextState(g);
+  const unsigned t = x*(x*x*15731u + 74323u) + 871483u;
+  return (float)t*(1.0f/4294967296.0f);
+}
+HC_DEV float rndQmcSobolN(unsigned pos, int dim, const unsigned* __restrict__ table)    // crandom.h:228-236
+{
+  unsigned result = 0, data = pos;
+  for (int bit = 0; bit < HC_QRNG_RESOLUTION_K; bit++, data >>= 1)
+    if (data & 1u) result ^= table[bit + dim*HC_QRNG_RESOLUTION_K];
+  return (float)(result + 1u)*(1.0f/(float)0x80000001U);
+}
+HC_DEV float rndQmcTab(HcRng& g, const int* __restrict__ tab, unsigned pos, int var, const unsigned* __restrict__ table)   // crandom.h:250-258
+{
+  const int dim = tab[var];
+  return (dim < 0) ? rndFloat1_Pseudo(g) : rndQmcSobolN(pos, dim, table);
+}
+
+// ------------------------------------------------------------------------------------------------------------------ small helpers
+HC_DEV float epsilonOfPos(float3 p)                       // cglobals.h:737 (one double product of two floats == the float product)
+{
+  return fmaxf(fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))), 2.0f*HC_GEPSILON)*HC_GEPSILON;
+}
+HC_DEV float misHeuristicPower1(float p) { return isfinite(p) ? fabsf(p) : 0.0f; }          // cglobals.h:738
+HC_DEV float misWeightHeuristic(float a, float b)          // cglobals.h:741-745 (balance heuristic on |p|)
+{
+  const float w = misHeuristicPower1(a)/fmaxf(misHeuristicPower1(a) + misHeuristicPower1(b), HC_DEPSILON2);
+  return isfinite(w) ? w : 0.0f;
+}
+HC_DEV float3 OffsRayPos(float3 hitPos, float3 n, float3 dir)                                 // cglobals.h:764-769
+{
+  const float s = dot(dir, n) < 0.0f ? -1.0f : 1.0f;
+  const float e = epsilonOfPos(hitPos);
+  return hitPos + s*e*n;
+}
+HC_DEV float3 OffsShadowRayPos(float3 hitPos, float3 n, float3 dir, float aux)                // cglobals.h:779-784
+{
+  const float s = dot(dir, n) < 0.0f ? -1.0f : 1.0f;
+  const float e = epsilonOfPos(hitPos);
+  return hitPos + s*(e + aux)*n;
+}
+HC_DEV float3 reflect3(float3 dir, float3 n) { return normalize((n*dot(dir, n)*(-2.0f)) + dir); }   // cglobals.h:688-693
+HC_DEV float3 clamp3(float3 u, float a, float b) { return f3(clampf(u.x, a, b), clampf(u.y, a, b), clampf(u.z, a, b)); }
+
+HC_DEV void CoordinateSystem(float3 v1, float3& v2, float3& v3)                               // cglobals.h:1502-1519
+{
+  if (fabsf(v1.x) > fabsf(v1.y))
+  {
+    const float invLen = (float)(1.0/sqrt(D(v1.x*v1.x + v1.z*v1.z)));
+    v2 = f3((-1.0f)*v1.z*invLen, 0.0f, v1.x*invLen);
+  }
+  else
+  {
+    const float invLen = (float)(1.0/sqrt(D(v1.y*v1.y + v1.z*v1.z)));
+    v2 = f3(0.0f, v1.z*invLen, (-1.0f)*v1.y*invLen);
+  }
+  v3 = cross(v1, v2);
+}
+
+HC_DEV float3 MapSampleToCosineDistribution(float r1, float r2, float3 direction, float3 hitNorm, float power)   // cglobals.h:1521-1561
+{
+  if (power >= 1e6f) return direction;
+  const float sinPhi = hc_sin(2.0f*r1*3.141592654f);
+  const float cosPhi = hc_cos(2.0f*r1*3.141592654f);
+  const float cosTheta = hc_pow(1.0f - r2, 1.0f/(power + 1.0f));
+  const float sinTheta = sqrtf(1.0f - cosTheta*cosTheta);
+  const float3 dev = f3(sinTheta*cosPhi, sinTheta*sinPhi, cosTheta);
+  float3 nx, nzT;
+  CoordinateSystem(direction, nx, nzT);
+  const float3 ny = nzT, nz = direction;              // the reference swaps ny and nz after CoordinateSystem
+  float3 res = nx*dev.x + ny*dev.y + nz*dev.z;
+  const float invSign = dot(direction, hitNorm) > 0.0f ? 1.0f : -1.0f;
+  if (invSign*dot(res, hitNorm) < 0.0f)
+    res = (-1.0f)*nx*dev.x + ny*dev.y - nz*dev.z;
+  return res;
+}
+
+HC_DEV float3 MapSampleToModifiedCosineDistribution(float r1, float r2, float3 direction, float3 hitNorm, float power, bool& under)   // cglobals.h:1565-1601
+{
+  if (power >= 1e6f) return direction;        // NB: leaves `under` untouched, as the reference does
+  const float sinPhi = hc_sin(2.0f*r1*3.141592654f);
+  const float cosPhi = hc_cos(2.0f*r1*3.141592654f);
+  const float sinTheta = (float)sqrt(1.0 - pow(D(r2), D(2.0f/(power + 1.0f))));
+  float3 dev;
+  dev.x = sinTheta*cosPhi; dev.y = sinTheta*sinPhi;
+  dev.z = sqrtf(1.0f - dev.x*dev.x - dev.y*dev.y);
+  float3 nx, nzT;
+  CoordinateSystem(direction, nx, nzT);
+  const float3 ny = nzT, nz = direction;
+  float3 res = nx*dev.x + ny*dev.y + nz*dev.z;
+  under = false;
+  const float invSign = dot(direction, hitNorm) >= 0.0f ? 1.0f : -1.0f;
+  if (invSign*dot(res, hitNorm) < 0.0f)
+  {
+    res = (-1.0f)*nx*dev.x - ny*dev.y + nz*dev.z;
+    under = true;
+  }
+  return res;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ table access
+HC_DEV const float* MaterialAt(const HcScene& s, int matId)            // materialAt, cfetch.h:201-211
+{
+  const int off = s.globals[s.materialsTableOffset + matId];
+  return reinterpret_cast<const float*>(s.materials + off);
+}
+HC_DEV int   MatI(const float* m, int i) { return __float_as_int(m[i]); }
+HC_DEV const float* LightAt(const HcScene& s, int id)                  // lightAt, clight.h:1739-1749
+{
+  if (id < 0) return nullptr;
+  return reinterpret_cast<const float*>(s.globals + s.lightsOffset) + id*HC_LIGHT_DATA_SIZE;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ software textures
+HC_DEV float sRGBToLinear(float x)                                      // cglobals.h:3024-3030
+{
+  if (x <= 0.0404482362771082f) return x*0.077399381f;
+  return hc_pow((x + 0.055f)*0.947867299f, 2.4f);
+}
+HC_DEV float4 ReadUchar4(const uchar4* data, int offset)               // read_array_uchar4, cfetch.h:301-306
+{
+  const float mult = 0.003921568f;
+  const uchar4 c = data[offset];
+  return mult*make_float4((float)c.x, (float)c.y, (float)c.z, (float)c.w);
+}
+HC_DEV int4 BilinearOffsets(float ffx, float ffy, int flags, int w, int h)     // cfetch.h:315-368
+{
+  const int sx = (ffx > 0.0f) ? 1 : -1, sy = (ffy > 0.0f) ? 1 : -1;
+  const int px = (int)ffx, py = (int)ffy;
+  int px0, px1, py0, py1;
+  if (flags & HC_TEX_CLAMP_U)
+  {
+    px0 = (px >= w) ? w - 1 : px;         px1 = (px + 1 >= w) ? w - 1 : px + 1;
+    px0 = (px0 < 0) ? 0 : px0;            px1 = (px1 < 0) ? 0 : px1;
+  }
+  else
+  {
+    px0 = px % w;                         px1 = (px + sx) % w;
+    px0 = (px0 < 0) ? px0 + w : px0;      px1 = (px1 < 0) ? px1 + w : px1;
+  }
+  if (flags & HC_TEX_CLAMP_V)
+  {
+    py0 = (py >= h) ? h - 1 : py;         py1 = (py + 1 >= h) ? h - 1 : py + 1;
+    py0 = (py0 < 0) ? 0 : py0;            py1 = (py1 < 0) ? 0 : py1;
+  }
+  else
+  {
+    py0 = py % h;                         py1 = (py + sy) % h;
+    py0 = (py0 < 0) ? py0 + h : py0;      py1 = (py1 < 0) ? py1 + h : py1;
+  }
+  return make_int4(py0*w + px0, py0*w + px1, py1*w + px0, py1*w + px1);
+}
+
+// read_imagef_sw4 (cfetch.h:461-584) for RGBA8 (bpp 4) and float4 (bpp 16) images; single-channel images are rejected at init
+HC_DEV float4 ReadImageSw4(const int4* tex, float2 tc, int flags, bool srgb)
+{
+  const int4 header = *tex;
+  const int w = header.x, h = header.y, bpp = header.w;
+  float ffx = tc.x*(float)w - 0.5f, ffy = tc.y*(float)h - 0.5f;
+  if ((flags & HC_TEX_CLAMP_U) != 0 && ffx < 0) ffx = 0.0f;
+  if ((flags & HC_TEX_CLAMP_V) != 0 && ffy < 0) ffy = 0.0f;
+  float4 res = make_float4(0, 0, 0, 0);
+  if (flags & HC_TEX_POINT_SAM)
+  {
+    int px = (int)(ffx + 0.5f), py = (int)(ffy + 0.5f);
+    if (flags & HC_TEX_CLAMP_U) { px = (px >= w) ? w - 1 : px; px = (px < 0) ? 0 : px; } else { px = px % w; px = (px < 0) ? px + w : px; }
+    if (flags & HC_TEX_CLAMP_V) { py = (py >= h) ? h - 1 : py; py = (py < 0) ? 0 : py; } else { py = py % h; py = (py < 0) ? py + h : py; }
+    const int offset = py*w + px;
+    if (bpp == 4)
+    {
+      res = ReadUchar4(reinterpret_cast<const uchar4*>(tex + 1), offset);
+      if (srgb) res = make_float4(sRGBToLinear(res.x), sRGBToLinear(res.y), sRGBToLinear(res.z), sRGBToLinear(res.w));
+    }
+    else if (bpp == 16) res = reinterpret_cast<const float4*>(tex + 1)[offset];
+  }
+  else
+  {
+    const int px = (int)ffx, py = (int)ffy;
+    const float fx = fabsf(ffx - (float)px), fy = fabsf(ffy - (float)py);
+    const float fx1 = 1.0f - fx, fy1 = 1.0f - fy;
+    const float w1 = fx1*fy1, w2 = fx*fy1, w3 = fx1*fy, w4 = fx*fy;
+    const int4 o = BilinearOffsets(ffx, ffy, flags, w, h);
+    float4 f1, f2, f3v, f4;
+    if (bpp == 4)
+    {
+      const uchar4* d = reinterpret_cast<const uchar4*>(tex + 1);
+      f1 = ReadUchar4(d, o.x); f2 = ReadUchar4(d, o.y); f3v = ReadUchar4(d, o.z); f4 = ReadUchar4(d, o.w);
+      if (srgb)
+      {
+        f1 = make_float4(sRGBToLinear(f1.x), sRGBToLinear(f1.y), sRGBToLinear(f1.z), sRGBToLinear(f1.w));
+        f2 = make_float4(sRGBToLinear(f2.x), sRGBToLinear(f2.y), sRGBToLinear(f2.z), sRGBToLinear(f2.w));
+        f3v = make_float4(sRGBToLinear(f3v.x), sRGBToLinear(f3v.y), sRGBToLinear(f3v.z), sRGBToLinear(f3v.w));
+        f4 = make_float4(sRGBToLinear(f4.x), sRGBToLinear(f4.y), sRGBToLinear(f4.z), sRGBToLinear(f4.w));
+      }
+    }
+    else
+    {
+      const float4* d = reinterpret_cast<const float4*>(tex + 1);
+      f1 = d[o.x]; f2 = d[o.y]; f3v = d[o.z]; f4 = d[o.w];
+    }
+    res = make_float4(f1.x*w1 + f2.x*w2 + f3v.x*w3 + f4.x*w4, f1.y*w1 + f2.y*w2 + f3v.y*w3 + f4.y*w4,
+                      f1.z*w1 + f2.z*w2 + f3v.z*w3 + f4.z*w4, f1.w*w1 + f2.w*w2 + f3v.w*w3 + f4.w*w4);
+  }
+  return res;
+}
+
+// sample2DExt (cfetch.h:681-713) without procedural textures (none are supported: readProcTex then returns w = -1 and the image wins).
+// samplerOffset counts float4 from the start of the material node (ReadSampler, cfetch.h:588-612).
+HC_DEV float3 Sample2D(int samplerOffset, float2 tc, const float* mat, const HcScene& s)
+{
+  if (samplerOffset == HC_INVALID_TEXTURE || samplerOffset < 0) return f3(1, 1, 1);
+  const int4*   mi = reinterpret_cast<const int4*>(mat);
+  const float4* mf = reinterpret_cast<const float4*>(mat);
+  const int4 header = mi[samplerOffset];
+  const int flags = header.x; const float gamma = __int_as_float(header.y); const int texId = header.z;
+  if (texId <= 0) return f3(1, 1, 1);
+  const float4 row0 = mf[samplerOffset + 1], row1 = mf[samplerOffset + 2];
+  const float2 tct = f2(row0.x*tc.x + row0.y*tc.y + row0.w, row1.x*tc.x + row1.y*tc.y + row1.w);     // mul2x4, cfetch.h:640-646
+  const int offset = s.globals[s.texturesTableOffset + texId];
+  float4 c = (offset >= 0) ? ReadImageSw4(s.textures + offset, tct, flags, (gamma != 1.0f)) : make_float4(1, 1, 1, 1);
+  if (flags & HC_TEX_ALPHASRC_W) { c.x = c.w; c.y = c.w; c.z = c.w; }
+  return f3(c.x, c.y, c.z);
+}
+
+// ------------------------------------------------------------------------------------------------------------------ a10: surface evaluation
+// surfaceEvalLS (ctrace.h:2005-2109) + the world transform of IntegratorCommon::surfaceEval / kernel_EvalSurface
+// (CPUExp_Integrators_Common.cpp:193-242, CPUExp_Integrators_PT_Loop.cpp:35-84) and ComputeHit (shaders/trace.cl:130-227)
+HC_DEV HcSurfaceHit SurfaceEval(const HcScene& s, float3 rpos, float3 rdir, const HcHit hit)
+{
+  const HcMat4 inv = loadMat4(s.instMatrices + hit.instId*4);
+  const float3 o = mul4x3(inv, rpos), d = mul3x3(inv, rdir);
+
+  const int meshOff = s.globals[s.geometryTableOffset + hit.geomId];
+  const float4* mesh = s.geom + meshOff;
+  const int4 h0 = reinterpret_cast<const int4*>(mesh)[0];      // vPosOffset vNormOffset vTexCoordOffset vIndicesOffset
+  const int4 h2 = reinterpret_cast<const int4*>(mesh)[2];      // mIndicesOffset mIndicesNum vTangentOffset vTangentNum
+  const int4 h3 = reinterpret_cast<const int4*>(mesh)[3];      // totalBytesNum polyShadowOffset ...
+  const float4* vPos = mesh + h0.x; const float4* vNorm = mesh + h0.y; const float4* vTan = mesh + h2.z;
+  const int* vIdx = reinterpret_cast<const int*>(mesh + h0.w);
+  const int* mIdx = reinterpret_cast<const int*>(mesh + h2.x);
+  const float* sOff = reinterpret_cast<const float*>(mesh + h3.y);
+
+  HcSurfaceHit sh;
+  sh.matId = mIdx[hit.primId];
+  const int iA = vIdx[hit.primId*3 + 0], iB = vIdx[hit.primId*3 + 1], iC = vIdx[hit.primId*3 + 2];
+  const float4 A1 = vPos[iA], B1 = vPos[iB], C1 = vPos[iC];
+  const float4 A2 = vNorm[iA], B2 = vNorm[iB], C2 = vNorm[iC];
+  const float3 A = f3(A1), B = f3(B1), C = f3(C1);
+  const float3 An = f3(A2), Bn = f3(B2), Cn = f3(C2);
+  const float2 At = f2(A1.w, A2.w), Bt = f2(B1.w, B2.w), Ct = f2(C1.w, C2.w);
+
+  // triBaricentrics, ctrace.h:1986-2003
+  const float3 e1 = B - A, e2 = C - A;
+  const float3 pvec = cross(d, e2);
+  const float det = dot(e1, pvec);
+  const float invDet = 1.0f/det;
+  const float3 tvec = o - A;
+  const float v = dot(tvec, pvec)*invDet;
+  const float3 qvec = cross(tvec, e1);
+  const float u = dot(d, qvec)*invDet;
+  const float2 uv = f2(u, v);
+
+  const float w0 = 1.0f - uv.x - uv.y;
+  sh.pos      = w0*A + uv.y*B + uv.x*C;
+  sh.texCoord = w0*At + uv.y*Bt + uv.x*Ct;
+  sh.normal   = w0*An + uv.y*Bn + uv.x*Cn;
+  sh.t        = hit.t;
+  sh.sRayOff  = sOff[hit.primId];
+
+  const float4 At4 = vTan[iA], Bt4 = vTan[iB], Ct4 = vTan[iC];
+  sh.flatNormal = normalize(cross(A - B, A - C));
+  if (dot(d, sh.flatNormal) > 0.025f) sh.flatNormal = sh.flatNormal*(-1.0f);
+  const float maxEdge = fmaxf(fmaxf(length(A - B), length(A - C)), length(B - C));
+  if (sh.sRayOff > 1e-5f*maxEdge)
+  {
+    if (dot(d, sh.normal) > 0.120f)      { sh.normal = sh.normal*(-1.0f); sh.hfi = true; }
+    else if (dot(d, sh.normal) > 0.0f)   { sh.normal = sh.flatNormal; sh.hfi = false; }
+    else sh.hfi = false;
+  }
+  else
+  {
+    if (dot(d, sh.normal) > 0.0f) { sh.normal = sh.normal*(-1.0f); sh.hfi = true; }
+    else sh.hfi = false;
+  }
+  const float handedness = (At4.w < 0.0f || Bt4.w < 0.0f || Ct4.w < 0.0f) ? -1.0f : 1.0f;
+  sh.tangent   = normalize(w0*f3(At4) + uv.y*f3(Bt4) + uv.x*f3(Ct4));
+  sh.biTangent = normalize(handedness > 0.0f ? cross(sh.normal, sh.tangent) : cross(sh.tangent, sh.normal));
+  const bool badTangent = (!isfinite(sh.biTangent.x) || !isfinite(sh.biTangent.y) || !isfinite(sh.biTangent.z));
+  if (fabsf(fabsf(dot(sh.normal, sh.tangent)) - 1.0f) < 1e-4f || badTangent)
+    CoordinateSystem(sh.normal, sh.tangent, sh.biTangent);
+
+  // to world space
+  const HcMat4 m = inverse4x4(inv);
+  const float multInv = (float)(1.0/sqrt(3.0));
+  const float so = multInv*sh.sRayOff;
+  const float3 shadowStart = mul3x3(m, f3(so, so, so));
+  const HcMat4 nm = transpose(inv);
+  HcSurfaceHit ws = sh;
+  ws.pos        = mul4x3(m, sh.pos);
+  ws.normal     = normalize(mul3x3(nm, sh.normal));
+  ws.flatNormal = normalize(mul3x3(nm, sh.flatNormal));
+  ws.tangent    = normalize(mul3x3(nm, sh.tangent));
+  ws.biTangent  = normalize(mul3x3(nm, sh.biTangent));
+  ws.t          = length(ws.pos - rpos);
+  ws.sRayOff    = length(shadowStart);
+  return ws;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ a13/a14: BSDFs
+HC_DEV float3 Mat3(const float* m, int i) { return f3(m[i], m[i + 1], m[i + 2]); }
+
+// cubic spline glossiness -> Phong exponent (cosPowerFromGlosiness + its coefficient table, cmaterial.h:425-466; table = fitted data)
+__device__ static const float kGlossCoeff[10][4] = {
+  { 8.88178419700125e-14f, -1.77635683940025e-14f, 5.0f, 1.0f },        { 357.142857142857f, -35.7142857142857f, 5.0f, 1.5f },
+  { -2142.85714285714f, 428.571428571429f, 8.57142857142857f, 2.0f },   { 428.571428571431f, -42.8571428571432f, 30.0f, 5.0f },
+  { 2095.23809523810f, -152.380952380952f, 34.2857142857143f, 8.0f },   { -4761.90476190476f, 1809.52380952381f, 66.6666666666667f, 12.0f },
+  { 9914.71215351811f, 1151.38592750533f, 285.714285714286f, 32.0f },   { 45037.7068059246f, 9161.90096119855f, 813.432835820895f, 82.0f },
+  { 167903.678757035f, 183240.189801913f, 3996.94423223835f, 300.0f },  { -20281790.7444668f, 6301358.14889336f, 45682.0925553320f, 2700.0f } };
+HC_DEV float cosPowerFromGlosiness(float g)
+{
+  const float cMax = 1000000.0f;
+  const float x = g;
+  const int k = (fabsf(x - 1.0f) < 1e-5f) ? 10 : (int)(x*10.0f);
+  const float x1 = (x - (float)k*0.1f);
+  if (k == 10 || x >= 0.99f) return cMax;
+  return kGlossCoeff[k][3] + kGlossCoeff[k][2]*x1 + kGlossCoeff[k][1]*x1*x1 + kGlossCoeff[k][0]*x1*x1*x1;
+}
+
+// glossiness slot shared by Phong / GGX (phongGlosiness, ggxGlosiness: cmaterial.h:918-931, 1197-1210; same offsets 16/17/18)
+HC_DEV float Glosiness(const float* m, float2 tc, const HcScene& s)
+{
+  if (MatI(m, HC_PHONG_GLOSINESS_TEXID_OFFSET) != HC_INVALID_TEXTURE)
+  {
+    const float3 gc = Sample2D(MatI(m, HC_PHONG_GLOSINESS_TEXMATRIXID_OFFSET), tc, m, s);
+    return clampf(m[HC_PHONG_GLOSINESS_OFFSET]*maxcomp(gc), 0.0f, 0.99f);
+  }
+  return m[HC_PHONG_GLOSINESS_OFFSET];
+}
+
+// ---- Lambert (cmaterial.h:212-257)
+HC_DEV float3 LambertColor(const float* m, float2 tc, const HcScene& s)
+{
+  const float3 tex = Sample2D(MatI(m, HC_LAMBERT_TEXMATRIXID_OFFSET), tc, m, s);
+  return clamp3(tex*Mat3(m, HC_LAMBERT_COLORX_OFFSET), 0.0f, 1.0f);
+}
+HC_DEV void LambertSample(const float* m, float r1, float r2, float3 n, float2 tc, const HcScene& s, HcMatSample& out)
+{
+  const float3 color = LambertColor(m, tc, s);
+  const float3 newDir = MapSampleToCosineDistribution(r1, r2, n, n, 1.0f);
+  const float cosTheta = dot(newDir, n);
+  out.direction = newDir;
+  out.pdf = cosTheta*HC_INV_PI;
+  out.color = color*HC_INV_PI;
+  if (cosTheta <= HC_DEPSILON) out.color = f3(0, 0, 0);
+  out.flags = HC_RAY_EVENT_D;
+}
+
+// ---- perfect mirror (cmaterial.h:385-421)
+HC_DEV void MirrorSample(const float* m, float3 rayDir, float3 n, float2 tc, const HcScene& s, HcMatSample& out)
+{
+  const float3 tex = Sample2D(MatI(m, HC_MIRROR_TEXMATRIXID_OFFSET), tc, m, s);
+  float3 newDir = reflect3(rayDir, n);
+  if (dot(rayDir, n) > 0.0f) newDir = rayDir;
+  const float cosOut = dot(newDir, n);
+  out.direction = newDir;
+  out.pdf = 1.0f;
+  out.color = Mat3(m, HC_MIRROR_COLORX_OFFSET)*tex*(1.0f/fmaxf(cosOut, 1e-6f));
+  if (cosOut <= 1e-6f) out.color = f3(0, 0, 0);
+  out.flags = HC_RAY_EVENT_S;
+}
+
+// ---- modified Phong (cmaterial.h:908-1017)
+HC_DEV float PhongEnergyFix(float dotRL, float3 l, float3 n) { return dotRL/fmaxf(dot(n, l), 1e-6f); }
+HC_DEV float PhongEvalPDF(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  if (dot(n, v) < 1e-6f || dot(n, l) < 1e-6f) return 1.0f;
+  const float cosPower = cosPowerFromGlosiness(Glosiness(m, tc, s));
+  const float3 r = reflect3((-1.0f)*v, n);
+  const float cosTheta = clampf(fabsf(dot(l, r)), 0.0f, 1.0f);
+  return (float)(pow(D(cosTheta), D(cosPower))*D(cosPower + 1.0f)*D(HC_INV_TWOPI));
+}
+HC_DEV float3 PhongEvalBxDF(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  if (dot(n, v) < 1e-6f || dot(n, l) < 1e-6f) return f3(0, 0, 0);
+  const float3 tex = Sample2D(MatI(m, HC_PHONG_TEXMATRIXID_OFFSET), tc, m, s);
+  const float3 color = clamp3(Mat3(m, HC_PHONG_COLORX_OFFSET)*tex, 0.0f, 1.0f);
+  const float cosPower = cosPowerFromGlosiness(Glosiness(m, tc, s));
+  const float3 r = reflect3((-1.0f)*v, n);
+  const float cosAlpha = clampf(dot(l, r), 0.0f, 1.0f);
+  const bool fix = (MatI(m, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER) != 0;
+  const float energyFix = fix ? PhongEnergyFix(cosAlpha, l, n) : 1.0f;
+  return color*(cosPower + 2.0f)*HC_INV_TWOPI*hc_pow(cosAlpha, cosPower)*energyFix;
+}
+HC_DEV void PhongSample(const float* m, float r1, float r2, float3 rayDir, float3 n, float2 tc, const HcScene& s, HcMatSample& out)
+{
+  const float3 tex = Sample2D(MatI(m, HC_PHONG_TEXMATRIXID_OFFSET), tc, m, s);
+  const float3 color = clamp3(Mat3(m, HC_PHONG_COLORX_OFFSET)*tex, 0.0f, 1.0f);
+  const float gloss = Glosiness(m, tc, s);
+  const float cosPower = cosPowerFromGlosiness(gloss);
+  bool under = false;
+  const float3 r = reflect3(rayDir, n);
+  const float3 newDir = MapSampleToModifiedCosineDistribution(r1, r2, r, n, cosPower, under);
+  const float3 v = rayDir*(-1.0f), l = newDir;
+  if (dot(n, v) < 1e-6f || dot(n, l) < 1e-6f || under) { out.color = f3(0, 0, 0); out.pdf = 1.0f; }
+  else
+  {
+    const float cosAlpha = clampf(dot(newDir, r), 0.0f, 1.0f);
+    const float eqTemp = (float)(pow(D(cosAlpha), D(cosPower))*D(HC_INV_TWOPI));
+    const bool fix = (MatI(m, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER) != 0;
+    const float energyFix = fix ? PhongEnergyFix(cosAlpha, newDir, n) : 1.0f;
+    out.pdf = eqTemp*(cosPower + 1.0f);
+    out.color = eqTemp*(cosPower + 2.0f)*color*energyFix;
+  }
+  out.direction = newDir;
+  out.flags = (gloss >= 0.99f) ? HC_RAY_EVENT_S : HC_RAY_EVENT_G;
+}
+
+// ---- GGX (cmaterial.h:1212-1285, 1317-1381, 1454-1520)
+HC_DEV float SmithGGXMasking(float dotNV, float roughSqr)
+{
+  const float denomC = (float)(sqrt(D(roughSqr + (1.0f - roughSqr)*dotNV*dotNV)) + D(dotNV));
+  return 2.0f*dotNV/fmaxf(denomC, 1e-6f);
+}
+HC_DEV float SmithGGXMaskingShadowing(float dotNL, float dotNV, float roughSqr)
+{
+  const float denomA = (float)(D(dotNV)*sqrt(D(roughSqr + (1.0f - roughSqr)*dotNL*dotNL)));
+  const float denomB = (float)(D(dotNL)*sqrt(D(roughSqr + (1.0f - roughSqr)*dotNV*dotNV)));
+  return 2.0f*dotNL*dotNV/fmaxf(denomA + denomB, 1e-6f);
+}
+HC_DEV float GGX_Distribution(float cosNH, float alpha)
+{
+  const float alpha2 = alpha*alpha;
+  const float nh2 = clampf(cosNH*cosNH, 0.0f, 1.0f);
+  const float den = nh2*alpha2 + (1.0f - nh2);
+  return (float)(D(alpha2)/fmax(HC_PI_D*D(den)*D(den), D(1e-6f)));
+}
+HC_DEV float3 GgxVndf(float3 wo, float roughness, float u1, float u2)
+{
+  const float3 v = normalize(f3(wo.x*roughness, wo.y*roughness, wo.z));
+  const float3 XAxis = f3(1.0f, 0.0f, 0.0f), ZAxis = f3(0.0f, 0.0f, 1.0f);
+  const float3 t1 = (v.z < 0.999f) ? normalize(cross(v, ZAxis)) : XAxis;
+  const float3 t2 = cross(t1, v);
+  const float a = 1.0f/(1.0f + v.z);
+  const float r = sqrtf(u1);
+  const float phi = (u2 < a) ? (float)(D(u2/a)*HC_PI_D) : (float)(HC_PI_D + D((u2 - a)/(1.0f - a))*HC_PI_D);
+  const float p1 = (float)(D(r)*cos(D(phi)));
+  const float p2 = (float)(D(r)*sin(D(phi))*D((u2 < a) ? 1.0f : v.z));
+  const float3 n = p1*t1 + p2*t2 + sqrtf(fmaxf(0.0f, 1.0f - p1*p1 - p2*p2))*v;
+  return normalize(f3(roughness*n.x, roughness*n.y, fmaxf(0.0f, n.z)));
+}
+// GetMultiscatteringFrom2dTable + BilinearFrom2dTable (cmaterial.h:61-93, 152-159) over EngineGlobals::m_essGgx2017Table
+HC_DEV float3 GgxMultiscatter(const HcScene& s, float roughness, float dotNV, float3 color)
+{
+  const unsigned short* tab = reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(s.globals) + s.essGgxTableOffsetBytes);
+  const int W = 64, H = 64;
+  float x = clampf(dotNV*(float)W, 0.0f, W - 1.0001f), y = clampf(roughness*(float)H, 0.0f, H - 1.0001f);
+  const int fy = (int)floorf(y), fx = (int)floorf(x);
+  const int d1 = fy*W + fx, d2 = d1 + 1, d3 = (fy + 1)*W + fx, d4 = d3 + 1;
+  const float dx = x - fx, dy = y - fy;
+  const float m1 = (1.0f - dx)*(1.0f - dy), m2 = dx*(1.0f - dy), m3 = dy*(1.0f - dx), m4 = dx*dy;
+  float val = 1.0f;
+  if (fy >= 0 && fx >= 0 && fy <= H - 2 && fx <= W - 2) val = tab[d1]*m1 + tab[d2]*m2 + tab[d3]*m3 + tab[d4]*m4;
+  const float Ess = val*(1.0f/65535.0f);
+  const float3 t = color*(1.0f - Ess)/fmaxf(Ess, 1e-6f);
+  return f3(1.0f + t.x, 1.0f + t.y, 1.0f + t.z);
+}
+HC_DEV float3 GgxColor(const float* m, float2 tc, const HcScene& s)
+{
+  const float3 tex = Sample2D(MatI(m, HC_GGX_TEXMATRIXID_OFFSET), tc, m, s);
+  return clamp3(Mat3(m, HC_GGX_COLORX_OFFSET)*tex, 0.0f, 1.0f);
+}
+HC_DEV float Ggx2EvalPDF(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  const float dotNV = dot(n, v), dotNL = dot(n, l);
+  if (dotNV < 1e-6f || dotNL < 1e-6f) return 1.0f;
+  const float gloss = Glosiness(m, tc, s);
+  const float roughness = 1.0f - gloss, roughSqr = roughness*roughness;
+  const float3 h = normalize(v + l);
+  const float dotNH = dot(n, h), dotHV = dot(h, v);
+  const float G1 = SmithGGXMasking(dotNV, roughSqr);
+  const float Dd = GGX_Distribution(dotNH, roughSqr);
+  const float Dv = Dd*G1*dotHV/fmaxf(dotNV, 1e-6f);
+  const float jacob = 1.0f/fmaxf(4.0f*dotHV, 1e-6f);
+  return Dv*jacob;
+}
+HC_DEV float3 GgxEvalBxDF(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  const float dotNV = dot(n, v), dotNL = dot(n, l);
+  if (dotNV < 1e-6f || dotNL < 1e-6f) return f3(0, 0, 0);
+  const float3 color = GgxColor(m, tc, s);
+  const float gloss = Glosiness(m, tc, s);
+  const float roughness = 1.0f - gloss, roughSqr = roughness*roughness;
+  const float3 h = normalize(v + l);
+  const float dotNH = dot(n, h);
+  const float Dd = GGX_Distribution(dotNH, roughSqr);
+  const float G = SmithGGXMaskingShadowing(dotNL, dotNV, roughSqr);
+  const float Pss = Dd*G/fmaxf(4.0f*dotNV*dotNL, 1e-6f);
+  float3 Pms = f3(1, 1, 1);
+  if (MatI(m, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER) Pms = GgxMultiscatter(s, roughness, dotNV, color);
+  return color*Pss*Pms;
+}
+HC_DEV void GgxSample2(const float* m, float r1, float r2, float3 rayDir, float3 nrm, float2 tc, const HcScene& s, HcMatSample& out)
+{
+  const float3 color = GgxColor(m, tc, s);
+  const float gloss = Glosiness(m, tc, s);
+  const float roughness = 1.0f - gloss, roughSqr = roughness*roughness;
+  float3 nx, ny; const float3 nz = nrm;
+  CoordinateSystem(nz, nx, ny);
+  float Pss = 1.0f; float3 Pms = f3(1.0f, 1.0f, 1.0f);
+  const float3 wo = f3(-dot(rayDir, nx), -dot(rayDir, ny), -dot(rayDir, nz));
+  const float3 wh = GgxVndf(wo, roughSqr, r1, r2);
+  const float3 wi = 2.0f*dot(wo, wh)*wh - wo;
+  const float3 newDir = normalize(wi.x*nx + wi.y*ny + wi.z*nz);
+  const float3 v = rayDir*(-1.0f), l = newDir;
+  const float dotNV = dot(nrm, v), dotNL = dot(nrm, l);
+  if (dotNV < 1e-6f || dotNL < 1e-6f) { Pss = 0.0f; out.pdf = 1.0f; }
+  else
+  {
+    const float3 h = normalize(v + l);
+    const float dotNH = dot(nrm, h), dotHV = dot(h, v);
+    const float Dd = GGX_Distribution(dotNH, roughSqr);
+    const float G1 = SmithGGXMasking(dotNV, roughSqr);
+    const float G2 = SmithGGXMaskingShadowing(dotNL, dotNV, roughSqr);
+    Pss = Dd*G2/fmaxf(4.0f*dotNV, 1e-6f);
+    const float Dv = Dd*G1*dotHV/fmaxf(dotNV, 1e-6f);
+    const float jacob = 1.0f/fmaxf(4.0f*dotHV, 1e-6f);
+    out.pdf = Dv*jacob;
+    if (MatI(m, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER) Pms = GgxMultiscatter(s, roughness, dotNV, color);
+  }
+  out.direction = newDir;
+  out.color = color*Pss*Pms/fmaxf(dotNL, 1e-6f);
+  out.flags = (gloss >= 0.99f) ? HC_RAY_EVENT_S : HC_RAY_EVENT_G;
+}
+
+// ---- GGX glass (glassGloss cmaterial.h:610-618, myRefractGgx :674-706, GlassGGXSampleAndEvalBRDF :775-883); eval is zero (:620-629)
+HC_DEV void GlassGgxSample(const float* m, float3 rands, float3 rayDir, float3 nrm, float2 tc, bool hfi, const HcScene& s, HcMatSample& out)
+{
+  const float3 tex = Sample2D(MatI(m, HC_GLASS_TEXMATRIXID_OFFSET), tc, m, s);
+  const float3 color = clamp3(Mat3(m, HC_GLASS_COLORX_OFFSET)*tex, 0.0f, 1.0f);
+  const float3 gc = Sample2D(MatI(m, HC_GLASS_GLOSINESS_TEXMATRIXID_OFFSET), tc, m, s);
+  const float gloss = clampf(m[HC_GLASS_GLOSINESS]*maxcomp(gc), 0.0f, 1.0f);
+  const float roughness = clampf(1.0f - gloss, 0.0f, 1.0f), roughSqr = roughness*roughness;
+  const float IOR = m[HC_GLASS_IOR_OFFSET];
+  const float3 normal2 = hfi ? (-1.0f)*nrm : nrm;
+  bool spec = true; float Pss = 1.0f; const float3 Pms = f3(1.0f, 1.0f, 1.0f);
+  out.pdf = 1.0f;
+
+  // myRefractGgx(ray_dir, normal2, IOR, 1.0f, rands.z)
+  float3 rdir; bool success; float reta = 1.0f/IOR;
+  {
+    float3 nn = normal2;
+    float cosTheta = dot(nn, rayDir)*(-1.0f);
+    if (cosTheta < 0.0f) { cosTheta = cosTheta*(-1.0f); nn = nn*(-1.0f); reta = 1.0f/reta; }
+    const float dotVN = cosTheta*(-1.0f);
+    const float k = 1.0f - reta*reta*(1.0f - cosTheta*cosTheta);
+    if (k > 0.0f) { rdir = normalize(reta*rayDir + (float)(D(reta*cosTheta) - sqrt(D(k)))*nn); success = true; }
+    else          { rdir = normalize((nn*dotVN*(-2.0f)) + rayDir); success = false; reta = 1.0f; }
+  }
+
+  if (gloss < 0.999f)
+  {
+    spec = false;
+    float eta = 1.0f/IOR;
+    const float cosTheta = dot(normal2, rayDir)*(-1.0f);
+    if (cosTheta < 0.0f) eta = 1.0f/eta;
+    float3 nx, ny; const float3 nz = nrm;
+    CoordinateSystem(nz, nx, ny);
+    const float3 wo = f3(-dot(rayDir, nx), -dot(rayDir, ny), -dot(rayDir, nz));
+    const float3 wh = GgxVndf(wo, roughSqr, rands.x, rands.y);
+    const float dotWoWh = dot(wo, wh);
+    float3 newDir;
+    const float radicand = 1.0f + eta*eta*(dotWoWh*dotWoWh - 1.0f);
+    if (radicand > 0.0f) { newDir = (float)(D(eta*dotWoWh) - sqrt(D(radicand)))*wh - eta*wo; success = true; reta = eta; }
+    else                 { newDir = 2.0f*dotWoWh*wh - wo; success = false; reta = 1.0f; }
+    rdir = normalize(newDir.x*nx + newDir.y*ny + newDir.z*nz);
+    const float3 v = rayDir*(-1.0f), l = rdir;
+    const float dotNV = fabsf(dot(nrm, v)), dotNL = fabsf(dot(nrm, l));
+    const float G1 = SmithGGXMasking(dotNV, roughSqr);
+    const float G2 = SmithGGXMaskingShadowing(dotNL, dotNV, roughSqr);
+    Pss = G2/fmaxf(G1, 1e-6f);
+  }
+
+  const float cosOut = dot(rdir, nrm);
+  const float cosMult = 1.0f/fmaxf(fabsf(cosOut), 1e-6f);
+  out.direction = rdir;
+  const float adjoint = reta*reta;                      // camera paths (a_isFwdDir == false)
+  if (success) out.color = color*adjoint*Pss*Pms*cosMult;
+  else         out.color = f3(1.0f, 1.0f, 1.0f)*Pss*Pms*cosMult;
+  out.flags = spec ? (HC_RAY_EVENT_S | HC_RAY_EVENT_T) : (HC_RAY_EVENT_G | HC_RAY_EVENT_T);
+  if (success && cosOut >= -1e-6f) out.color = f3(0.0f, 0.0f, 0.0f);
+  else if (!success && cosOut < 1e-6f) out.color = f3(0.0f, 0.0f, 0.0f);
+}
+
+// ---- blend mask (fresnel helpers cglobals.h:1875-1926; blendMaskAlpha2 / blendSelectBRDF cmaterial.h:2034-2137)
+HC_DEV float fresnelDielectric(float c1, float c2, float etaExt, float etaInt)
+{
+  const float Rs = (etaExt*c1 - etaInt*c2)/(etaExt*c1 + etaInt*c2);
+  const float Rp = (etaInt*c1 - etaExt*c2)/(etaInt*c1 + etaExt*c2);
+  return (Rs*Rs + Rp*Rp)/2.0f;
+}
+HC_DEV float fresnelReflectionCoeff(float cosTheta1, float etaExt, float etaInt)
+{
+  if (cosTheta1 < 0.0f) { const float t = etaInt; etaInt = etaExt; etaExt = t; }
+  const float sinTheta2 = (float)(D(etaExt/etaInt)*sqrt(fmax(0.0, D(1.0f - cosTheta1*cosTheta1))));
+  if (sinTheta2 > 1.0f) return 1.0f;
+  const float cosTheta2 = sqrtf(fmaxf(0.0f, 1.0f - sinTheta2*sinTheta2));
+  return fresnelDielectric(fabsf(cosTheta1), cosTheta2, etaInt, etaExt);
+}
+HC_DEV float BlendMaskAlpha(const float* m, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  const float3 tex = Sample2D(MatI(m, HC_BLEND_MASK_TEXMATRIXID_OFFSET), tc, m, s);
+  const float3 lum1 = clamp3(tex*Mat3(m, HC_BLEND_MASK_COLORX_OFFSET), 0.0f, 1.0f);
+  const int bflags = MatI(m, HC_BLEND_MASK_FLAGS_OFFSET);
+  float lum;
+  if (bflags & HC_BLEND_MASK_EXTRUSION_LUMINANCE) lum = dot(f3(0.2126f, 0.7152f, 0.0722f), lum1);
+  else lum = fmaxf(lum1.x, fmaxf(lum1.y, lum1.z));
+  const float normAngle = fabsf(dot(v, n));
+  if (MatI(m, HC_BLEND_TYPE) == HC_BLEND_SIGMOID)
+  {
+    const float x2 = -5.0f + 10.0f*lum;                                                     // maxSigmoid, cmaterial.h:2026-2030
+    lum = (float)(D(1.04f)/(D(1.0f) + exp(D(-m[HC_BLEND_SIGMOID_EXP]*x2))) - D(0.02f));
+  }
+  if (bflags & HC_BLEND_MASK_FRESNEL)
+    return clampf(lum*fresnelReflectionCoeff(fabsf(normAngle), 1.0f, m[HC_BLEND_MASK_FRESNEL_IOR]), 0.0f, 1.0f);
+  return clampf(lum, 0.0f, 1.0f);
+}
+HC_DEV bool IsLeaf(const float* m) { return MatI(m, HC_PLAIN_MAT_TYPE_OFFSET) != HC_PLAIN_MAT_CLASS_BLEND_MASK; }
+
+// leaf dispatch: MaterialLeafSampleAndEvalBRDF (cmaterial.h:2245-2335) without normal maps
+HC_DEV void LeafSample(const float* m, const HcSurfaceHit& sh, float3 rayDir, float3 rands, const HcScene& s, HcMatSample& out)
+{
+  out.color = f3(0.0f, 0.0f, 0.0f); out.direction = f3(0.0f, 1.0f, 0.0f); out.pdf = 1.0f; out.flags = 0;
+  switch (MatI(m, HC_PLAIN_MAT_TYPE_OFFSET))
+  {
+    case HC_PLAIN_MAT_CLASS_PHONG_SPECULAR: PhongSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
+    case HC_PLAIN_MAT_CLASS_GGX:            GgxSample2(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
+    case HC_PLAIN_MAT_CLASS_PERFECT_MIRROR: MirrorSample(m, rayDir, sh.normal, sh.texCoord, s, out); break;
+    case HC_PLAIN_MAT_CLASS_GLASS:          GlassGgxSample(m, rands, rayDir, sh.normal, sh.texCoord, sh.hfi, s, out); break;
+    case HC_PLAIN_MAT_CLASS_LAMBERT:        LambertSample(m, rands.x, rands.y, sh.normal, sh.texCoord, s, out); break;
+    default: break;
+  }
+  if (out.pdf <= 0.0f) out.color = f3(0, 0, 0);
+}
+
+// MaterialSampleAndEvalBxDF (cmaterial.h:2345-2371) with materialRandomWalkBRDF (:2180-2207); rands[0..2] direction, rands[3..9] layers
+HC_DEV void MaterialSampleAndEval(const float* mat, const float* rands, const HcSurfaceHit& sh, float3 rayDir, unsigned rayFlags,
+                                  const HcScene& s, HcMatSample& out)
+{
+  const unsigned other = (rayFlags & 0xFFFF0000u) >> 16;
+  const bool canReflOnly = (MatI(mat, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_CAN_SAMPLE_REFL_ONLY) != 0;
+  const bool reflOnly = ((other & HC_RAY_GRAMMAR_DIRECT_LIGHT) != 0) && canReflOnly;
+  int localOffs = 0; float w = 1.0f;
+  int selOffs = 0; float selW = 1.0f;
+  const float* node = mat;
+  int i = 0;
+  while (!IsLeaf(node) && i < HC_MMLT_FLOATS_PER_MLAYER)
+  {
+    const float r3 = rands[HC_MMLT_FLOATS_PER_SAMPLE + i];
+    {                                                                                    // blendSelectBRDF
+      float alpha = BlendMaskAlpha(node, rayDir, sh.normal, sh.texCoord, s);
+      const int o1 = MatI(node, HC_BLEND_MASK_MATERIAL1_OFFSET), o2 = MatI(node, HC_BLEND_MASK_MATERIAL2_OFFSET);
+      float w1 = 1.0f; const float w2 = 1.0f;
+      const int bflags = MatI(node, HC_BLEND_MASK_FLAGS_OFFSET);
+      if ((bflags & HC_BLEND_MASK_REFLECTION_WEIGHT_IS_ONE) && IsLeaf(node + o1*HC_PLAIN_MATERIAL_DATA_SIZE)) w1 = alpha;
+      if ((bflags & HC_BLEND_MASK_FRESNEL) != 0 && (reflOnly && i == 0)) { w1 = alpha; alpha = 1.0f; }
+      if (r3 <= alpha) { selOffs = o1; selW = w1; } else { selOffs = o2; selW = w2; }
+    }
+    w = w*selW;
+    localOffs += selOffs;
+    node += selOffs*HC_PLAIN_MATERIAL_DATA_SIZE;
+    i++;
+  }
+  const float* leaf = mat + localOffs*HC_PLAIN_MATERIAL_DATA_SIZE;
+  LeafSample(leaf, sh, rayDir, f3(rands[0], rands[1], rands[2]), s, out);
+  out.color *= 1.0f/fmaxf(w, 0.015625f);
+  if ((MatI(leaf, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_SKIP_SKY_PORTAL))       // materialIsSkyPortal && isEyeRay, cmaterial.h:2366-2370
+  {
+    const bool nonSpec = (other & HC_RAY_EVENT_D) || (other & HC_RAY_EVENT_G);
+    if ((((rayFlags & 0x0000FF00u) >> 8) == 0) || !nonSpec) { out.color = f3(1, 1, 1); out.pdf = 1.0f; }
+  }
+}
+
+// materialLeafEval (cmaterial.h:2425-2551) without normal maps, camera direction
+HC_DEV HcBxDF LeafEval(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  HcBxDF r; r.brdf = f3(0, 0, 0); r.btdf = f3(0, 0, 0); r.pdfFwd = 0.0f; r.pdfRev = 0.0f; r.diffuse = false;
+  switch (MatI(m, HC_PLAIN_MAT_TYPE_OFFSET))
+  {
+    case HC_PLAIN_MAT_CLASS_PHONG_SPECULAR:
+      r.brdf = PhongEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = PhongEvalPDF(m, l, v, n, tc, s); r.pdfRev = PhongEvalPDF(m, v, l, n, tc, s); break;
+    case HC_PLAIN_MAT_CLASS_GGX:
+      r.brdf = GgxEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = Ggx2EvalPDF(m, l, v, n, tc, s); r.pdfRev = Ggx2EvalPDF(m, v, l, n, tc, s); break;
+    case HC_PLAIN_MAT_CLASS_LAMBERT:
+      r.brdf = LambertColor(m, tc, s)*HC_INV_PI*1.0f; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
+    default: break;      // mirror and glass evaluate to zero for explicit light (cmaterial.h:396-404, 620-629)
+  }
+  return r;
+}
+
+// materialEval (cmaterial.h:2554-2628): explicit-stack walk of the blend tree, same push/pop order (so sums round identically)
+HC_DEV HcBxDF MaterialEval(const float* mat, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  HcBxDF val; val.brdf = f3(0, 0, 0); val.btdf = f3(0, 0, 0); val.pdfFwd = 0.0f; val.pdfRev = 0.0f; val.diffuse = true;
+  float stackW[HC_MIX_TREE_MAX_DEEP]; int stackO[HC_MIX_TREE_MAX_DEEP];
+  int top = 0, cur = 0; float curW = 1.0f;
+  do
+  {
+    if (top > 0) { top--; cur = stackO[top]; curW = stackW[top]; }
+    const float* m = mat + cur*HC_PLAIN_MATERIAL_DATA_SIZE;
+    if (!IsLeaf(m))
+    {
+      const float alpha = BlendMaskAlpha(m, v, n, tc, s);
+      const int o1 = MatI(m, HC_BLEND_MASK_MATERIAL1_OFFSET), o2 = MatI(m, HC_BLEND_MASK_MATERIAL2_OFFSET);
+      float w1 = alpha; const float w2 = 1.0f - alpha;
+      if ((MatI(m, HC_BLEND_MASK_FLAGS_OFFSET) & HC_BLEND_MASK_REFLECTION_WEIGHT_IS_ONE) && IsLeaf(m + o1*HC_PLAIN_MATERIAL_DATA_SIZE)) w1 = 1.0f;
+      if (top < HC_MIX_TREE_MAX_DEEP) { stackW[top] = curW*w1; stackO[top] = cur + o1; top++; }
+      if (top < HC_MIX_TREE_MAX_DEEP) { stackW[top] = curW*w2; stackO[top] = cur + o2; top++; }
+    }
+    else
+    {
+      const HcBxDF b = LeafEval(m, l, v, n, tc, s);
+      val.brdf += curW*b.brdf; val.btdf += curW*b.btdf; val.pdfFwd += curW*b.pdfFwd; val.pdfRev += curW*b.pdfRev;
+      val.diffuse = val.diffuse && b.diffuse;
+    }
+  } while (top > 0);
+  return val;
+}
+
+// materialEvalEmission (cmaterial.h:2918-2978): blend nodes carry emissive headers too, so every visited node contributes
+HC_DEV float3 MaterialEvalEmission(const float* mat, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  float3 val = f3(0.0f, 0.0f, 0.0f);
+  float stackW[HC_MIX_TREE_MAX_DEEP]; int stackO[HC_MIX_TREE_MAX_DEEP];
+  int top = 0, cur = 0; float curW = 1.0f;
+  do
+  {
+    if (top > 0) { top--; cur = stackO[top]; curW = stackW[top]; }
+    const float* m = mat + cur*HC_PLAIN_MATERIAL_DATA_SIZE;
+    if (!IsLeaf(m))
+    {
+      const float alpha = BlendMaskAlpha(m, v, n, tc, s);
+      const int o1 = MatI(m, HC_BLEND_MASK_MATERIAL1_OFFSET), o2 = MatI(m, HC_BLEND_MASK_MATERIAL2_OFFSET);
+      if (top < HC_MIX_TREE_MAX_DEEP) { stackW[top] = curW*alpha; stackO[top] = cur + o1; top++; }
+      if (top < HC_MIX_TREE_MAX_DEEP) { stackW[top] = curW*(1.0f - alpha); stackO[top] = cur + o2; top++; }
+    }
+    const float3 tex = Sample2D(MatI(m, HC_EMISSIVE_TEXMATRIXID_OFFSET), tc, m, s);      // materialLeafEvalEmission, cmaterial.h:21-26
+    val += curW*(Mat3(m, HC_EMISSIVE_COLORX_OFFSET)*tex);
+  } while (top > 0);
+  return val;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ a11/a12: lights
+// SelectRandomLightRev + SelectIndexPropToOpt (clight.h:1774-1793, cglobals.h:2806-2862)
+HC_DEV int SelectRandomLightRev(float r, const HcScene& s, float& pickProb)
+{
+  const int N = s.lightSelTableSizeRev;
+  if (N == 0) { pickProb = 1.0f; return -1; }
+  if (N <= 2) { pickProb = 1.0f; return 0; }
+  const float* acc = reinterpret_cast<const float*>(s.globals + s.lightSelTableOffsetRev);
+  int left = 0, right = N - 2, counter = 0, cur = -1;
+  const float x = r*acc[N - 1];
+  while (right - left > 1 && counter < 50)
+  {
+    const int size = right + left;
+    const int p1 = (size % 2 == 0) ? (size + 1)/2 : (size + 0)/2;
+    const float a = acc[p1], b = acc[p1 + 1];
+    if (a < x && x <= b) { cur = p1; break; }
+    else if (x <= a) right = p1;
+    else if (x > b) left = p1;
+    counter++;
+  }
+  if (cur < 0)
+  {
+    const float a1 = acc[left], b1 = acc[left + 1], a2 = acc[right], b2 = acc[right + 1];
+    if (a1 < x && x <= b1) cur = left;
+    if (a2 < x && x <= b2) cur = right;
+  }
+  if (x == 0.0f) cur = 0;
+  else if (cur < 0) cur = (right + left + 1)/2;
+  pickProb = (acc[cur + 1] - acc[cur])/acc[N - 1];
+  return cur;
+}
+
+HC_DEV float AreaLightEvalPDF(const float* L, float3 rayDir, float hitDist)             // areaDiffuseLightEvalPDF, clight.h:524-530 ; PdfAtoW cglobals.h:1754
+{
+  const float3 ln = Mat3(L, HC_PLIGHT_NORM_X);
+  const float pdfA = 1.0f/fmaxf(L[HC_PLIGHT_SURFACE_AREA], HC_DEPSILON);
+  const float cosVal = fmaxf(dot(rayDir, -1.0f*ln), 0.0f);
+  return (pdfA*hitDist*hitDist)/fmaxf(cosVal, HC_DEPSILON2);
+}
+
+// AreaLightSampleRev (clight.h:1180-1229), untextured, no spot distribution / IES / sky portal (rejected at init)
+HC_DEV void AreaLightSampleRev(const float* L, float3 rands, float3 illum, HcShadowSample& out)
+{
+  const float ox = rands.x*2.0f - 1.0f, oy = rands.y*2.0f - 1.0f;
+  float3 sp = f3(ox*L[HC_AREA_LIGHT_SIZE_X], 0.0f, oy*L[HC_AREA_LIGHT_SIZE_Y]);
+  if (__float_as_int(L[HC_AREA_LIGHT_IS_DISK]) != 0)
+  {
+    // MapSamplesToDisc (cglobals.h:1609-1655)
+    const float x = ox, y = oy; float r = 0.0f, phi = 0.0f;
+    if (x > y && x > -y)  { r = x;  phi = 0.25f*3.141592654f*(y/x); }
+    if (x < y && x > -y)  { r = y;  phi = 0.25f*3.141592654f*(2.0f - x/y); }
+    if (x < y && x < -y)  { r = -x; phi = 0.25f*3.141592654f*(4.0f + y/x); }
+    if (x > y && x < -y)  { r = -y; phi = 0.25f*3.141592654f*(6 - x/y); }
+    const float2 xz = f2(r*hc_sin(phi), r*hc_cos(phi))*L[HC_AREA_LIGHT_SIZE_X];
+    sp = f3(xz.x, 0.0f, xz.y);
+  }
+  const float* M = L + HC_AREA_LIGHT_MATRIX_E00;                                         // matrix3x3f_mult_float3, cglobals.h:1091-1098
+  sp = f3(M[0]*sp.x + M[1]*sp.y + M[2]*sp.z, M[3]*sp.x + M[4]*sp.y + M[5]*sp.z, M[6]*sp.x + M[7]*sp.y + M[8]*sp.z);
+  sp = sp + Mat3(L, HC_PLIGHT_POS_X);
+  const float3 rayDir = normalize(sp - illum);
+  const float hitDist = length(sp - illum);
+  const float3 ln = Mat3(L, HC_PLIGHT_NORM_X);
+  out.isPoint = false;
+  out.pos = sp + epsilonOfPos(sp)*ln;
+  out.color = Mat3(L, HC_PLIGHT_COLOR_X);                                                // areaDiffuseLightGetIntensity, clight.h:542-611 (plain branch)
+  out.pdf = AreaLightEvalPDF(L, rayDir, hitDist);
+  out.maxDist = hitDist;
+  out.cosAtLight = -dot(rayDir, ln);
+}
+
+// emissionEval (cbidir.h:653-678) through IntegratorCommon::emissionEval (CPUExp_Integrators_Common.cpp:509-520)
+HC_DEV float3 EmissionEval(const HcScene& s, float3 rayPos, float3 rayDir, const HcSurfaceHit& sh, unsigned flags, int instId)
+{
+  const float* L = (s.lightsNum > 0) ? LightAt(s, s.instLightIds[instId]) : nullptr;
+  const float* mat = MaterialAt(s, sh.matId);
+  const float3 normal = sh.hfi ? (-1.0f)*sh.normal : sh.normal;
+  if (dot(rayDir, normal) >= 0.0f) return f3(0, 0, 0);
+  float3 outColor = MaterialEvalEmission(mat, rayDir, normal, sh.texCoord, s);
+  if ((MatI(mat, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_FORBID_EMISSIVE_GI) && (flags & 0xFFu) > 0) outColor = f3(0, 0, 0);
+  if (s.lightsNum > 0 && L != nullptr) outColor = Mat3(L, HC_PLIGHT_COLOR_X);           // lightGetIntensity -> area light base colour (clight.h:1661-1706)
+  return outColor;
+}
+
+// flagsNextBounceLite (cmaterial.h:3262-3293)
+HC_DEV unsigned FlagsNextBounceLite(unsigned flags, const HcMatSample& ms, const HcScene& s)
+{
+  const bool diffuse = (ms.flags & HC_RAY_EVENT_D) != 0;
+  const unsigned bounce = (flags & 0x0000FF00u) >> 8, diffB = flags & 0xFFu;
+  unsigned other = (flags & 0xFFFF0000u) >> 16;
+  flags = (flags & 0xFFFF00FFu) | ((bounce + 1) << 8);
+  if (diffuse) flags = (flags & 0xFFFFFF00u) | (diffB + 1);
+  const unsigned bounce2 = bounce + 1, diff2 = flags & 0xFFu;
+  if ((bounce2 >= (unsigned)s.traceDepth) || (diff2 >= (unsigned)s.diffTraceDepth + 1)) other |= HC_RAY_IS_DEAD;
+  if (ms.flags & HC_RAY_EVENT_G) other |= HC_RAY_EVENT_G;
+  if ((ms.flags & HC_RAY_EVENT_S) != 0 || (ms.flags & HC_RAY_EVENT_T) != 0) other |= HC_RAY_EVENT_S;
+  if (ms.flags & HC_RAY_EVENT_D) other |= HC_RAY_EVENT_D;
+  if (ms.flags & HC_RAY_EVENT_T) other |= HC_RAY_EVENT_T;
+  return (flags & 0x0000FFFFu) | (other << 16);
+}

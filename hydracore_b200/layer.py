@@ -164,6 +164,23 @@ class CudaLayer:
         check(self._L.hc_make_eye_rays(self._c, w, h, ct.c_void_p(offsets_ptr) if offsets_ptr else None, ct.c_void_p(rays_ptr), HC_DEVICE),
               "hc_make_eye_rays")
 
+    def MakeShadowRays(self, rays8, hits, light_pos):
+        r = np.ascontiguousarray(rays8, dtype=np.float32).reshape(-1, 8)
+        out = np.empty_like(r)
+        lp = (ct.c_float*3)(*[float(v) for v in light_pos])
+        check(self._L.hc_make_shadow_rays(self._c, _ptr(r), _ptr(np.ascontiguousarray(hits)), r.shape[0], lp, _ptr(out), HC_HOST), "hc_make_shadow_rays")
+        return out
+
+    def make_shadow_rays_device(self, rays_ptr, hits_ptr, n, light_pos, out_ptr):
+        lp = (ct.c_float*3)(*[float(v) for v in light_pos])
+        check(self._L.hc_make_shadow_rays(self._c, ct.c_void_p(rays_ptr), ct.c_void_p(hits_ptr), n, lp, ct.c_void_p(out_ptr), HC_DEVICE), "hc_make_shadow_rays")
+
+    def RaycastPass(self, light_pos, hits_ptr=None, vis_ptr=None, space=HC_HOST):
+        """K1 -> K2 -> shadow rays -> K2s over the whole screen; optional result pointers (host or device per `space`)."""
+        lp = (ct.c_float*3)(*[float(v) for v in light_pos])
+        check(self._L.hc_raycast_pass(self._c, lp, ct.c_void_p(hits_ptr) if hits_ptr else None, ct.c_void_p(vis_ptr) if vis_ptr else None, space),
+              "hc_raycast_pass")
+
     def last_trace_ms(self):
         ms = ct.c_float()
         check(self._L.hc_trace_last_ms(self._c, ct.byref(ms)), "hc_trace_last_ms")

@@ -1,0 +1,153 @@
+"""PlainMaterial (192 floats) and PlainLight (128 floats) packers for synthetic scenes.
+
+Field meaning follows the reference's converters (hydra_drv/PlainMaterialConverter.cpp, PlainLightConverter.cpp) and the slot
+maps in hydra_drv/cmaterial.h / clight.h; every offset comes from csrc/hc_layout.h (pinned against the reference in
+tests/test_layout.py).  Only what the CUDA layer supports this round is offered."""
+import math
+
+import numpy as np
+
+from .layout import C
+
+INVALID_TEXTURE = -2
+
+
+def _i2f(v):
+    return np.array([v], np.int32).view(np.float32)[0]
+
+
+def _node(mat_type, flags):
+    m = np.zeros(192, np.float32)
+    m[C["PLAIN_MAT_TYPE_OFFSET"]] = _i2f(mat_type)
+    m[C["PLAIN_MAT_FLAGS_OFFSET"]] = _i2f(flags)
+    for k in ("EMISSIVE_TEXID_OFFSET", "EMISSIVE_TEXMATRIXID_OFFSET", "OPACITY_TEX_OFFSET", "OPACITY_TEX_MATRIX", "NORMAL_TEX_OFFSET",
+              "NORMAL_TEX_MATRIX", "PROC_TEX1_F4_HEAD_OFFSET"):
+        m[C[k]] = _i2f(INVALID_TEXTURE)
+    m[C["EMISSIVE_LIGHTID_OFFSET"]] = _i2f(-1)
+    return m
+
+
+def _sampler(m, float_offset, tex_id, flags=0, gamma=2.2, row0=(1, 0, 0, 0), row1=(0, 1, 0, 0)):
+    """SWTexSampler (48 bytes: flags, gamma, texId, pad, row0, row1; cfetch.h:108-131) at `float_offset`; returns its float4 index."""
+    assert float_offset % 4 == 0
+    m[float_offset + 0] = _i2f(flags)
+    m[float_offset + 1] = gamma
+    m[float_offset + 2] = _i2f(tex_id)
+    m[float_offset + 3] = _i2f(0)
+    m[float_offset + 4:float_offset + 8] = row0
+    m[float_offset + 8:float_offset + 12] = row1
+    return float_offset//4
+
+
+def _color_slot(m, color, tex_id, texid_off, texmat_off, sampler_off, **kw):
+    m[10:13] = color
+    if tex_id and tex_id > 0:
+        m[texid_off] = _i2f(tex_id)
+        m[texmat_off] = _i2f(_sampler(m, sampler_off, tex_id, **kw))
+    else:
+        m[texid_off] = _i2f(INVALID_TEXTURE)
+        m[texmat_off] = _i2f(INVALID_TEXTURE)
+
+
+def lambert(color, tex_id=0, **kw):
+    m = _node(C["PLAIN_MAT_CLASS_LAMBERT"], C["PLAIN_MATERIAL_HAS_DIFFUSE"])
+    _color_slot(m, color, tex_id, C["LAMBERT_TEXID_OFFSET"], C["LAMBERT_TEXMATRIXID_OFFSET"], C["LAMBERT_SAMPLER0"], **kw)
+    return m
+
+
+def _glossy(mat_type, color, gloss, tex_id, flags, **kw):
+    m = _node(mat_type, flags)
+    _color_slot(m, color, tex_id, C["PHONG_TEXID_OFFSET"], C["PHONG_TEXMATRIXID_OFFSET"], C["PHONG_SAMPLER0_OFFSET"], **kw)
+    m[C["PHONG_GLOSINESS_OFFSET"]] = gloss
+    m[C["PHONG_GLOSINESS_TEXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
+    m[C["PHONG_GLOSINESS_TEXMATRIXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
+    return m
+
+
+def phong(color, gloss, tex_id=0, energy_fix=False, **kw):
+    return _glossy(C["PLAIN_MAT_CLASS_PHONG_SPECULAR"], color, gloss, tex_id,
+                   C["PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER"] if energy_fix else 0, **kw)
+
+
+def ggx(color, gloss, tex_id=0, multiscatter=False, **kw):
+    return _glossy(C["PLAIN_MAT_CLASS_GGX"], color, gloss, tex_id,
+                   C["PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER"] if multiscatter else 0, **kw)
+
+
+def mirror(color):
+    m = _node(C["PLAIN_MAT_CLASS_PERFECT_MIRROR"], 0)
+    m[10:13] = color
+    m[C["MIRROR_TEXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
+    m[C["MIRROR_TEXMATRIXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
+    return m
+
+
+def glass(color, ior=1.5, gloss=1.0):
+    m = _node(C["PLAIN_MAT_CLASS_GLASS"], C["PLAIN_MATERIAL_HAS_TRANSPARENCY"] | C["PLAIN_MATERIAL_HAVE_BTDF"])
+    m[10:13] = color
+    m[C["GLASS_TEXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
+    m[C["GLASS_TEXMATRIXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
+    m[C["GLASS_IOR_OFFSET"]] = ior
+    m[C["GLASS_FOG_COLORX_OFFSET"]:C["GLASS_FOG_COLORX_OFFSET"] + 3] = 1.0
+    m[C["GLASS_GLOSINESS"]] = gloss
+    m[C["GLASS_GLOSINESS_TEXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
+    m[C["GLASS_GLOSINESS_TEXMATRIXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
+    return m
+
+
+def emissive(color, light_id=-1):
+    """Material of a light's mesh (EmissiveMaterial, PlainMaterialConverter.cpp:31-47)."""
+    m = _node(C["PLAIN_MAT_CLASS_EMISSIVE"], C["PLAIN_MATERIAL_IS_LIGHT"])
+    m[C["EMISSIVE_COLORX_OFFSET"]:C["EMISSIVE_COLORX_OFFSET"] + 3] = color
+    m[C["EMISSIVE_LIGHTID_OFFSET"]] = _i2f(light_id)
+    return m
+
+
+def blend(mask_color, top, bottom, fresnel=True, ior=1.5, sigmoid_exp=None):
+    """BlendMask node followed by its children: `top` (material 1, chosen with probability alpha) at relative offset +1 and `bottom`
+    (material 2) right after it — the layout the converter emits for diffuse+reflect materials (PlainMaterialConverter.cpp:793-813);
+    non-fresnel blends get BLEND_MASK_REFLECTION_WEIGHT_IS_ONE (:787-788).  `top` / `bottom` are nodes or node lists."""
+    top = [top] if isinstance(top, np.ndarray) and top.ndim == 1 else list(top)
+    bottom = [bottom] if isinstance(bottom, np.ndarray) and bottom.ndim == 1 else list(bottom)
+    m = _node(C["PLAIN_MAT_CLASS_BLEND_MASK"], C["PLAIN_MATERIAL_SURFACE_BLEND"])
+    m[10:13] = mask_color
+    m[C["BLEND_MASK_TEXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
+    m[C["BLEND_MASK_TEXMATRIXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
+    flags = C["BLEND_MASK_FRESNEL"] if fresnel else C["BLEND_MASK_REFLECTION_WEIGHT_IS_ONE"]
+    m[C["BLEND_MASK_FLAGS_OFFSET"]] = _i2f(flags)
+    m[C["BLEND_MASK_MATERIAL1_OFFSET"]] = _i2f(1)
+    m[C["BLEND_MASK_MATERIAL2_OFFSET"]] = _i2f(1 + len(top))
+    m[C["BLEND_MASK_FRESNEL_IOR"]] = ior
+    btype = C["BLEND_FRESNEL"] if fresnel else C["BLEND_SIMPLE"]
+    if sigmoid_exp is not None:
+        btype = C["BLEND_SIGMOID"]
+        m[C["BLEND_SIGMOID_EXP"]] = sigmoid_exp
+    m[C["BLEND_TYPE"]] = _i2f(btype)
+    m[C["BLEND_FLAGS"]] = _i2f(0)
+    return [m] + top + bottom
+
+
+def area_light(pos, half_size, intensity, rotation=None, disk=False, pick_prob=1.0):
+    """Rectangular / disk area light (AreaDiffuseLight, PlainLightConverter.cpp:130-300): local normal (0,-1,0), sample position
+    R*(+-sx, 0, +-sy) + pos, surface area 4*sx*sy (pi*r^2 for disks); field map hydra_drv/clight.h:15-64, 493-521."""
+    L = np.zeros(128, np.float32)
+    R = np.eye(3, dtype=np.float32) if rotation is None else np.asarray(rotation, np.float32).reshape(3, 3)
+    L[C["PLIGHT_TYPE"]] = _i2f(C["PLAIN_LIGHT_TYPE_AREA"])
+    L[C["PLIGHT_FLAGS"]] = _i2f(0)
+    L[C["PLIGHT_POS_X"]:C["PLIGHT_POS_X"] + 3] = pos
+    n = R @ np.array([0, -1, 0], np.float32)
+    L[C["PLIGHT_NORM_X"]:C["PLIGHT_NORM_X"] + 3] = n/np.linalg.norm(n)
+    L[C["PLIGHT_COLOR_X"]:C["PLIGHT_COLOR_X"] + 3] = intensity
+    L[C["PLIGHT_COLOR_TEX"]] = _i2f(INVALID_TEXTURE)
+    L[C["PLIGHT_COLOR_TEX_MATRIX"]] = _i2f(INVALID_TEXTURE)
+    sx, sy = float(half_size[0]), float(half_size[1])
+    L[C["PLIGHT_SURFACE_AREA"]] = (math.pi*sx*sx) if disk else (4.0*sx*sy)
+    L[C["AREA_LIGHT_SIZE_X"]] = sx
+    L[C["AREA_LIGHT_SIZE_Y"]] = sy
+    L[C["AREA_LIGHT_MATRIX_E00"]:C["AREA_LIGHT_MATRIX_E00"] + 9] = R.reshape(9)
+    L[C["AREA_LIGHT_IS_DISK"]] = _i2f(1 if disk else 0)
+    L[C["AREA_LIGHT_SPOT_DISTR"]] = _i2f(0)
+    L[C["PLIGHT_PROB_MULT"]] = 1.0
+    L[C["PLIGHT_PICK_PROB_FWD"]] = pick_prob
+    L[C["PLIGHT_PICK_PROB_REV"]] = pick_prob
+    return L

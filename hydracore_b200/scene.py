@@ -168,7 +168,7 @@ def quad_mesh(sx, sz, y=0.0, mat_id=0, flip=False):
     return Mesh(pos, idx, norm=nrm, uv=uv, mat=np.full(2, mat_id, np.int32))
 
 
-def box_mesh(hx, hy, hz, mat_ids=(0, 0, 0, 0, 0, 0), inward=True):
+def box_mesh(hx, hy, hz, mat_ids=(0, 0, 0, 0, 0, 0), inward=True, skip_faces=()):
     """Axis-aligned box of half sizes (hx, hy, hz), 12 triangles, flat normals; inward=True gives a room (Cornell-box style)."""
     faces = []
     s = -1.0 if inward else 1.0
@@ -177,6 +177,8 @@ def box_mesh(hx, hy, hz, mat_ids=(0, 0, 0, 0, 0, 0), inward=True):
     h = np.array([hx, hy, hz], np.float32)
     pos, idx, nrm, uv, mat = [], [], [], [], []
     for f, (n, u, v) in enumerate(defs):
+        if f in skip_faces:
+            continue
         n, u, v = np.array(n, np.float32), np.array(u, np.float32), np.array(v, np.float32)
         c = n*h
         corners = [c - u*h - v*h, c + u*h - v*h, c + u*h + v*h, c - u*h + v*h]
@@ -471,6 +473,8 @@ class Scene:
         if nl > 0:
             # light selection table = prefix sums of pick probabilities, N = lights+1 entries (RenderDriverRTE.cpp:1499-1521, clight.h:1774-1793)
             lights = np.stack(self.lights).astype(np.float32)
+            lights[:, C["PLIGHT_PICK_PROB_FWD"]] = np.float32(1.0)/np.float32(nl)      # uniform pick, normalised (RenderDriverRTE.cpp:1505-1516)
+            lights[:, C["PLIGHT_PICK_PROB_REV"]] = np.float32(1.0)/np.float32(nl)
             w = np.ones(nl, np.float32)/np.float32(nl)
             pref = np.zeros(nl + 1, np.float32)
             acc = np.float32(0)
@@ -482,3 +486,16 @@ class Scene:
             blob[offs["lselFwd"]:offs["lselFwd"] + nl + 1] = pref.view(np.int32)
             blob[offs["lights"]:offs["lights"] + nl*128] = lights.reshape(-1).view(np.int32)
         return blob
+
+
+# ---------------------------------------------------------------------------------------------------------------- BASELINE configs
+C2_LIGHT_POS = (0.0, 25.0, 0.0)
+
+
+def scene_c2(width=1920, height=1080):
+    """BASELINE config C2: synthetic 1,001,112-triangle mesh (708 x 707 displaced grid, seed 1234), one instance, identity
+    matrix, 1080p pinhole camera looking down at the terrain so that ~all primary rays hit; one point light for shadow rays."""
+    scn = Scene(width, height, Camera(pos=(0.0, 9.0, 16.0), look_at=(0.0, 0.0, 1.0), fov=45.0))
+    scn.add_instance(scn.add_mesh(grid_mesh(708, 707, size=60.0, amplitude=1.6, seed=1234)))
+    scn.add_material(np.zeros(192, np.float32))
+    return scn.build()

@@ -81,6 +81,14 @@ int hc_make_eye_rays(hc_ctx* ctx, int width, int height, const float* offsets4Or
                                                                               /* MakeEyeRaysUnifiedSampling, screen.cl:280 ; MakeRandEyeRay, cfetch.h:877 */
 int hc_trace_closest(hc_ctx* ctx, const float* rays8, int64_t n, hc_hit* hitsOut, int space);  /* BVH4TraversalInstKernel, trace.cl:50  */
 int hc_trace_shadow(hc_ctx* ctx, const float* rays8, int64_t n, uint8_t* visibleOut, int space);/* BVH4TraversalInstShadowKenrel, trace.cl:309 */
+int hc_make_shadow_rays(hc_ctx* ctx, const float* rays8, const hc_hit* hits, int64_t n, const float lightPos[3], float* shadowRays8Out, int space);
+                                                                              /* shadow-ray construction of LightSample for one point light (light.cl:140, clight.h:1561;
+                                                                                 t_far = 0.995*distance, CPUExp_Integrators_PT_Loop.cpp:176); missed rays get t_far = 0 */
+int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull, uint8_t* visibleOutOrNull, int space);
+                                                                              /* one ray-casting pass over the whole screen, all on the device: K1 eye rays -> K2 closest hit ->
+                                                                                 shadow rays to lightPos -> K2s any hit.  The RT-mode pass of the OpenCL layer
+                                                                                 (GPUOCLLayer::trace1DPrimaryOnly, GPUOCLLayerCore.cpp:294) plus the shadow step of ShadePass (:1007).
+                                                                                 Results stay on the device unless out pointers are given (space says where they live). */
 int hc_trace_last_ms(hc_ctx* ctx, float* outMs);                             /* device time of the last hc_trace_* launch (CUDA events)   */
 
 /* ---------------------------------------------------------------- path tracing -------------------------------------------- */

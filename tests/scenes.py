@@ -44,3 +44,56 @@ def incoherent_rays(n, seed, radius=9.0):
     rays[:, 4:7] = d
     rays[:, 7] = 3.402823466e+38
     return rays
+
+
+def cornell(width=128, height=128, trace_depth=5, two_lights=False, dof=False, textured=True):
+    """Cornell-box style scene in the spirit of hydra_app/tests/test_42: Lambert room (one wall textured), a mirror ball, a glass
+    ball, a GGX box, a Phong-over-Lambert fresnel blend, one (or two) rectangular area lights with emissive meshes."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45, dof=dof, lens_radius=0.15))
+    scn.set_trace_depth(trace_depth, 3)
+    tex = 0
+    if textured:
+        rng = np.random.RandomState(5)
+        img = np.zeros((32, 32, 4), np.uint8)
+        yy, xx = np.mgrid[0:32, 0:32]
+        chk = (((xx//4) + (yy//4)) % 2).astype(np.uint8)
+        img[..., 0] = 60 + 180*chk
+        img[..., 1] = 200 - 120*chk
+        img[..., 2] = (rng.rand(32, 32)*255).astype(np.uint8)
+        img[..., 3] = 255
+        tex = scn.add_texture_rgba8(img)
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    floor = scn.add_material(M.lambert((0.9, 0.9, 0.9), tex_id=tex))
+    mir = scn.add_material(M.mirror((0.9, 0.9, 0.9)))
+    gls = scn.add_material(M.glass((0.95, 0.98, 0.95), ior=1.5, gloss=1.0))
+    ggxm = scn.add_material(M.ggx((0.8, 0.6, 0.2), 0.7))
+    bl = scn.add_material(M.blend((0.8, 0.8, 0.8), M.phong((0.9, 0.9, 0.9), 0.85), M.lambert((0.2, 0.3, 0.8)), fresnel=True, ior=1.5))
+    rgl = scn.add_material(M.glass((0.9, 0.9, 1.0), ior=1.33, gloss=0.8))
+    emi = scn.add_material(M.emissive((17.0, 15.0, 12.0), 0))
+    # room: faces +x, -x, +y, -y, +z, -z
+    room = scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, floor, white, white), inward=True, skip_faces=(4,)))     # open towards the camera (+z)
+    scn.add_instance(room)
+    sph = S.sphere_mesh(1.0, 32, 16)
+    for mat, mtx in ((mir, S.translate(-2.0, -2.8, -1.0) @ S.scale(1.2, 1.2, 1.2)), (gls, S.translate(1.8, -2.9, 1.2) @ S.scale(1.1, 1.1, 1.1)),
+                     (rgl, S.translate(0.0, 0.5, -2.0) @ S.scale(0.8, 1.3, 0.8))):
+        m = S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, mat, np.int32))
+        scn.add_instance(scn.add_mesh(m), mtx)
+    box = S.box_mesh(0.9, 1.6, 0.9, mat_ids=(ggxm,)*6, inward=False)
+    scn.add_instance(scn.add_mesh(box), S.translate(2.2, -2.4, -1.8) @ S.rotate_y(0.4))
+    box2 = S.box_mesh(0.8, 0.8, 0.8, mat_ids=(bl,)*6, inward=False)
+    scn.add_instance(scn.add_mesh(box2), S.translate(-0.3, -3.2, 1.8) @ S.rotate_y(-0.5))
+    from hydracore_b200 import materials as M2
+    lq = S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)
+    lmesh = scn.add_mesh(lq)
+    l0 = scn.add_light(M2.area_light((0.0, 3.95, 0.0), (1.0, 1.0), (17.0, 15.0, 12.0)))
+    scn.add_instance(lmesh, S.translate(0.0, 3.95, 0.0), light_id=l0)
+    if two_lights:
+        emi2 = scn.add_material(M.emissive((4.0, 6.0, 9.0), 1))
+        lq2 = S.quad_mesh(0.6, 0.6, y=0.0, mat_id=emi2, flip=True)
+        R = S.rotate_x(-1.2)[:3, :3]
+        l1 = scn.add_light(M2.area_light((-2.5, 1.0, 3.0), (0.6, 0.6), (4.0, 6.0, 9.0), rotation=R))
+        scn.add_instance(scn.add_mesh(lq2), S.translate(-2.5, 1.0, 3.0) @ S.rotate_x(-1.2), light_id=l1)
+    return scn.build()

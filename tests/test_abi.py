@@ -60,3 +60,34 @@ def test_bvh_builder_layout(built):
     assert ntri == sum(m.tri_count for m in scn.meshes)       # mesh sub-trees are shared between instances
     assert scn.bvh["inv_matrices"].shape == (8, 16)
     assert scn.bvh["max_stack"] <= 64
+
+
+def test_bvh_builder_against_brute_force(built, oracle):
+    """The builder must not lose triangles: reference-style traversal of its tree == brute-force Moeller-Trumbore over all triangles."""
+    import numpy as np
+    from hydracore_b200 import scene as S
+    from tests import refapi, scenes
+    scn = S.Scene(64, 36, S.Camera(pos=(0.0, 9.0, 16.0), look_at=(0.0, 0.0, 1.0), fov=45.0))
+    scn.add_instance(scn.add_mesh(S.grid_mesh(150, 149, size=60.0, amplitude=1.6)))
+    scn.add_material(np.zeros(192, np.float32))
+    scn.build()
+    rays = refapi.rays_from_pos_dir(oracle.make_rand_eye_rays(scn.globals_blob, 64, 36, scenes.pixel_grid(64, 36), np.zeros((64*36, 4), np.float32)))
+    h = oracle.trace_closest(scn.bvh["nodes"], scn.bvh["tris"], rays)
+    assert (h["primId"] >= 0).mean() > 0.8
+    m = scn.meshes[0]
+    A, B, Cc = (m.pos[m.idx[:, k]].astype(np.float64) for k in range(3))
+    e1, e2 = B - A, Cc - A
+    for i in range(0, rays.shape[0], 23):
+        o, d = rays[i, 0:3].astype(np.float64), rays[i, 4:7].astype(np.float64)
+        pv = np.cross(d, e2)
+        det = (e1*pv).sum(1)
+        tv = o - A
+        u = (tv*pv).sum(1)/det
+        qv = np.cross(tv, e1)
+        v = (qv*d).sum(1)/det
+        t = (e2*qv).sum(1)/det
+        ok = (u >= 0) & (v >= 0) & (u + v <= 1) & (t > 0)
+        if ok.any():
+            assert h["primId"][i] >= 0 and abs(t[ok].min() - h["t"][i]) <= 1e-4*t[ok].min()
+        else:
+            assert h["primId"][i] < 0
