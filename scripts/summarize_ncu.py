@@ -1,0 +1,65 @@
+"""Summarise gpurun_out/<tag>_prof.ncu-rep + <tag>_launches.csv into profiles/ (tracked):
+   python scripts/summarize_ncu.py r01a [round-label]"""
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+tag = sys.argv[1]
+label = sys.argv[2] if len(sys.argv) > 2 else tag
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+rep = os.path.join(ROOT, "gpurun_out", f"{tag}_prof.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
+out = [f"# ncu --set full summary, {label} (bench.py --steps 2 --warmup 3 --no-cpu-baseline, C2 workload, 1 x B200)\n",
+       "Per-launch values; cold-cache, serialised replay: compare shares, not absolutes.\n"]
+traffic = {}
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    name = d["Kernel Name"]
+    out.append(f"\n## {name.split('(')[0]}\n\n| metric | value | unit |\n|---|---|---|")
+    for k in KEYS:
+        if k in d:
+            out.append(f"| {k} | {d[k]} | {units[hdr.index(k)]} |")
+    if "k_trace<0>" in name or "k_trace<(bool)0>" in name:
+        traffic["k_trace_closest_dram_bytes_per_launch"] = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"]))*1e6
+        traffic["k_trace_closest_ms_under_ncu"] = float(d["gpu__time_duration.sum"])
+    if "k_trace<1>" in name or "k_trace<(bool)1>" in name:
+        traffic["k_trace_shadow_dram_bytes_per_launch"] = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"]))*1e6
+os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+open(os.path.join(ROOT, "profiles", f"{label}_ncu_full_summary.md"), "w").write("\n".join(out) + "\n")
+traffic["source"] = f"profiles/{label}_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+json.dump(traffic, open(os.path.join(ROOT, "profiles", "c2_ncu_traffic.json"), "w"), indent=1)
+
+# launch list: share of each kernel in the step
+lc = os.path.join(ROOT, "gpurun_out", f"{tag}_launches.csv")
+tot = {}
+n = {}
+for r in csv.reader(l for l in open(lc) if not l.startswith("==")):
+    if len(r) < 5 or r[0] == "ID":
+        continue
+    try:
+        t = float(r[-1])
+    except ValueError:
+        continue
+    k = r[4].split("(")[0]
+    tot[k] = tot.get(k, 0.0) + t
+    n[k] = n.get(k, 0) + 1
+s = sum(tot.values())
+lines = [f"# ncu launch list, {label}: gpu__time_duration.sum per kernel (ns), same command as above\n", "| kernel | launches | total ns | share |", "|---|---|---|---|"]
+for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
+    lines.append(f"| {k} | {n[k]} | {v:.0f} | {100*v/s:.1f} % |")
+open(os.path.join(ROOT, "profiles", f"{label}_ncu_launches.md"), "w").write("\n".join(lines) + "\n")
+import shutil
+shutil.copy(lc, os.path.join(ROOT, "profiles", f"{label}_ncu_launches.csv"))
+print("\n".join(lines))
+print(traffic)
