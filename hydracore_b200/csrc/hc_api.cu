@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <limits>
 
 // ------------------------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_lastError;
@@ -38,6 +39,8 @@ void hc_buf_free(HcDevBuf& b) { if (b.ptr) cudaFree(b.ptr); b.ptr = nullptr; b.b
 #define HC_REFILL_MIN  12      // refill a warp from the global ray counter once this many lanes are idle
 
 // K2 / K2s.  Persistent warps: lanes that finished a ray are refilled together (one atomicAdd per refill, ranks by ballot/popc).
+// Between refills a lane runs the while-while loop of hc_trace.cuh: descend through interior quads until a leaf is reached, then
+// intersect (or enter the instance); the loop is left early once so few lanes are still busy that a refill pays off.
 // rpos/rdir are float4 streams with element stride `stride` (2 = interleaved {pos,dir} records, 1 = separate arrays).
 template<bool ANYHIT>
 __global__ void __launch_bounds__(HC_TRACE_BLOCK)
@@ -45,8 +48,7 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
         const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter)
 {
   const long long n = nDev ? (long long)(*nDev) : nArg;      // the path tracer keeps its live-path count on the device
-  unsigned stkNode[HC_STACK_CAP];
-  float    stkT[HC_STACK_CAP];
+  uint2 stk[HC_STACK_CAP];                                    // {child word, entry distance}
 
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -54,11 +56,9 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
 
   bool  idle = true, exhausted = false;
   long long rayIdx = -1;
-
-  // per-ray traversal state (see Traverse<> in hc_trace.cuh for the single-ray form used by the path tracer)
-  HcHit hit; float3 o, d, inv, wo, wd; int sp = 0, instTop = 0, instId = -1; unsigned node = 1u; bool inInst = false;
-  hit.t = 0; hit.primId = -1; hit.instId = -1; hit.geomId = 0;
-  o = d = inv = wo = wd = f3(0, 0, 0);
+  HcRayTrav r;
+  TravStart(r, bvh, f3(0, 0, 0), f3(0, 0, 1), 0.0f);
+  r.node = HC_NODE_SENTINEL;
 
   for (;;)
   {
@@ -76,10 +76,9 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
         {
           const float4 p = __ldg(rpos + idx*stride), dd = __ldg(rdir + idx*stride);
           rayIdx = idx; idle = false;
-          o = f3(p); d = f3(dd); inv = SafeInverse(d);
-          hit.t = ANYHIT ? dd.w : HC_MAXFLOAT; hit.primId = -1; hit.instId = -1; hit.geomId = int(0xC0000000u);   // Make_Lite_Hit(t, -1)
-          sp = 0; node = 1u; inInst = false; instTop = 0; instId = -1;
+          TravStart(r, bvh, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
           if (ANYHIT && !(dd.w > 0.0f)) { visOut[idx] = 1; idle = true; }          // maxDist <= 0: lit (trace.cl:343-351)
+          else if (!RayIsFinite(r.o, r.d)) r.node = HC_NODE_SENTINEL;              // every comparison of the reference fails on NaN: no hit
         }
       }
       if ((long long)base + nIdle >= n) exhausted = true;
@@ -87,79 +86,24 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
     if (__all_sync(FULL, idle)) { if (exhausted) break; else continue; }
     if (idle) continue;
 
-    bool needPop = false, finished = false;
-    if (!(node & HC_LEAF_BIT))
+    while (r.node != HC_NODE_SENTINEL)
     {
-      const float4* q = bvh.nodes + size_t(node)*8;
-      const float4 a0 = __ldg(q + 0), b0 = __ldg(q + 1), a1 = __ldg(q + 2), b1 = __ldg(q + 3);
-      const float4 a2 = __ldg(q + 4), b2 = __ldg(q + 5), a3 = __ldg(q + 6), b3 = __ldg(q + 7);
-      float t0 = ChildEntry(a0, b0, o, inv, hit.t), t1 = ChildEntry(a1, b1, o, inv, hit.t);
-      float t2 = ChildEntry(a2, b2, o, inv, hit.t), t3 = ChildEntry(a3, b3, o, inv, hit.t);
-      unsigned c0 = __float_as_uint(a0.w), c1 = __float_as_uint(a1.w), c2 = __float_as_uint(a2.w), c3 = __float_as_uint(a3.w);
-      HC_CSWAP(t0, c0, t1, c1); HC_CSWAP(t2, c2, t3, c3);
-      HC_CSWAP(t0, c0, t2, c2); HC_CSWAP(t1, c1, t3, c3);
-      HC_CSWAP(t1, c1, t2, c2);
-      if (t3 < HC_MAXFLOAT && sp < HC_STACK_CAP) { stkNode[sp] = c3; stkT[sp] = t3; sp++; }
-      if (t2 < HC_MAXFLOAT && sp < HC_STACK_CAP) { stkNode[sp] = c2; stkT[sp] = t2; sp++; }
-      if (t1 < HC_MAXFLOAT && sp < HC_STACK_CAP) { stkNode[sp] = c1; stkT[sp] = t1; sp++; }
-      if (t0 < HC_MAXFLOAT) node = c0; else needPop = true;
-    }
-    else if (!inInst)
-    {
-      const float4* r = bvh.nodes + size_t(node & 0x7fffffffu)*8;
-      const unsigned next = __float_as_uint(__ldg(r + 0).w);
-      HcMat4 m; m.c0 = __ldg(r + 2); m.c1 = __ldg(r + 3); m.c2 = __ldg(r + 4); m.c3 = __ldg(r + 5);
-      instId = __float_as_int(__ldg(r + 6).x);
-      wo = o; wd = d;
-      o = mul4x3(m, o); d = mul3x3(m, d); inv = SafeInverse(d);
-      inInst = true; instTop = sp;
-      node = next;
-    }
-    else
-    {
-      const float4* tp  = bvh.tris + size_t(node & 0x7fffffffu);
-      const float4 hdr  = __ldg(tp);
-      const int first   = __float_as_int(hdr.x);
-      const int count   = __float_as_int(hdr.y);
-      const float4* tri = bvh.tris + first;
-      bool found = false;
-      for (int i = 0; i < count; i++, tri += 3)
+      while (!(r.node & HC_LEAF_BIT)) TravQuad(r, bvh, stk);
+      if (r.node == HC_NODE_SENTINEL) break;
+      if (!r.inInst) TravEnterInstance(r, bvh);
+      else
       {
-        const float4 A4 = __ldg(tri + 0), B4 = __ldg(tri + 1), C4 = __ldg(tri + 2);
-        const float3 A = f3(A4), edge1 = f3(B4) - A, edge2 = f3(C4) - A;
-        const float3 pvec = cross(d, edge2);
-        const float3 tvec = o - A;
-        const float3 qvec = cross(tvec, edge1);
-        const float invDet = 1.0f/dot(edge1, pvec);
-        const float v = dot(tvec, pvec)*invDet;
-        const float u = dot(qvec, d)*invDet;
-        const float t = dot(edge2, qvec)*invDet;
-        if (v > -HC_TRI_EPS && u > -HC_TRI_EPS && (u + v < 1.0f + HC_TRI_EPS) && t > 0.0f && t < hit.t)
-        {
-          hit.t = t; hit.primId = __float_as_int(A4.w); hit.geomId = __float_as_int(B4.w); hit.instId = instId;
-          found = true;
-        }
+        const bool found = TravLeaf(r, bvh);
+        if (ANYHIT && found) { r.node = HC_NODE_SENTINEL; break; }
+        HC_POP(r, bvh, stk)
       }
-      if (ANYHIT && found) finished = true; else needPop = true;
+      if (!exhausted && __popc(__activemask()) <= 32 - HC_REFILL_MIN) break;       // enough idle lanes for a refill
     }
 
-    if (needPop)
+    if (r.node == HC_NODE_SENTINEL)
     {
-      for (;;)
-      {
-        if (sp == 0) { finished = true; break; }
-        sp--;
-        node = stkNode[sp];
-        const float te = stkT[sp];
-        if (inInst && sp < instTop) { o = wo; d = wd; inv = SafeInverse(d); inInst = false; }
-        if (te <= hit.t) break;
-      }
-    }
-
-    if (finished)
-    {
-      if (ANYHIT) visOut[rayIdx] = (hit.primId != -1) ? 0 : 1;
-      else        hitsOut[rayIdx] = hit;
+      if (ANYHIT) visOut[rayIdx] = (r.primId != -1) ? 0 : 1;
+      else reinterpret_cast<float4*>(hitsOut)[rayIdx] = make_float4(r.t, __int_as_float(r.primId), __int_as_float(r.hitInst), __int_as_float(r.geomId));
       idle = true;
     }
   }
@@ -221,13 +165,57 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   return HC_OK;
 }
 
-// walk the uploaded tree on the host: validates offsets and bounds the traversal stack
-static int ValidateBvh(const unsigned char* nodes, int nodesNum, int trif4Num, int* outStackBound)
+// Walk the uploaded reference-layout tree (producer bvh_access_dll2.cpp:199-717) on the host: validate every
+// offset, bound the traversal stack, and re-lay it out for the device (formats in hc_trace.cuh).  Quads and instance records keep
+// their quad index, so child words of interior nodes are unchanged.
+//   interior quad q : float4[8q+0..5] = minx[4] maxx[4] miny[4] maxy[4] minz[4] maxz[4], uint4[8q+6] = child words
+//   instance record : float4[8q+0..3] = inverse matrix columns, [8q+4] = {sub-tree word, realInstId, meshId, 0}
+//   triangle leaf   : pair records of 6 float4 {Ax0 Ax1 Ay0 Ay1 | Az0 Az1 E1x0 E1x1 | E1y0 E1y1 E1z0 E1z1 | E2x0 E2x1 E2y0 E2y1 |
+//                     E2z0 E2z1 prim0 prim1 | geom0 geom1 0 0} with E1 = B - A, E2 = C - A evaluated in float exactly as
+//                     IntersectAllPrimitivesInLeaf does (ctrace.h:159-160); an odd leaf is padded with a zero triangle, whose
+//                     determinant is 0 -> v = u = t = NaN -> every acceptance test fails.
+static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const float* trif4, int trif4Num,
+                               std::vector<float>& outNodes, std::vector<float>& outPairs, int* outStackBound)
 {
   struct N { float bmin[3]; unsigned lo; float bmax[3]; unsigned esc; };
   const N* nd = (const N*)nodes;
   const int quads = nodesNum/4;
   if (quads < 2) return HC_E_ARG;
+  outNodes.assign(size_t(quads)*32, 0.0f);
+  outPairs.clear();
+  outPairs.reserve(size_t(trif4Num)*4 + 64);
+  std::vector<unsigned> leafWord(size_t(trif4Num), 0u);     // float4 offset of a leaf header -> converted child word (0 = not yet)
+  const float INF = std::numeric_limits<float>::infinity();
+
+  auto convertLeaf = [&](unsigned off, unsigned* word) -> int
+  {
+    if (off >= unsigned(trif4Num)) return HC_E_RANGE;
+    if (leafWord[off]) { *word = leafWord[off]; return HC_OK; }
+    int hdr[4]; memcpy(hdr, trif4 + size_t(off)*4, 16);
+    const int first = hdr[0], count = hdr[1];
+    if (first < 0 || count < 1 || size_t(first) + size_t(count)*3 > size_t(trif4Num)) return HC_E_RANGE;
+    const int pairs = (count + 1)/2;
+    if (pairs > HC_LEAF_PAIRS_MAX) return HC_E_RANGE;
+    const size_t index = outPairs.size()/(HC_PAIR_F4*4);
+    if (index + size_t(pairs) >= HC_LEAF_INDEX_MASK) return HC_E_RANGE;
+    outPairs.resize(outPairs.size() + size_t(pairs)*HC_PAIR_F4*4, 0.0f);
+    float* P = outPairs.data() + index*HC_PAIR_F4*4;
+    for (int k = 0; k < count; k++)
+    {
+      const float* A = trif4 + (size_t(first) + size_t(k)*3)*4; const float* B = A + 4; const float* C = A + 8;
+      float* R = P + size_t(k/2)*HC_PAIR_F4*4; const int s = k & 1;
+      const float e1[3] = { B[0] - A[0], B[1] - A[1], B[2] - A[2] }, e2[3] = { C[0] - A[0], C[1] - A[1], C[2] - A[2] };
+      R[0 + s] = A[0];  R[2 + s] = A[1];  R[4 + s] = A[2];
+      R[6 + s] = e1[0]; R[8 + s] = e1[1]; R[10 + s] = e1[2];
+      R[12 + s] = e2[0]; R[14 + s] = e2[1]; R[16 + s] = e2[2];
+      memcpy(&R[18 + s], &A[3], 4);            // primId
+      memcpy(&R[20 + s], &B[3], 4);            // geomId
+    }
+    if (count & 1) { float* R = P + size_t(count/2)*HC_PAIR_F4*4; const int m1 = -1; memcpy(&R[19], &m1, 4); memcpy(&R[21], &m1, 4); }
+    *word = leafWord[off] = HC_LEAF_BIT | (unsigned(pairs - 1) << HC_LEAF_PAIRS_SHIFT) | unsigned(index);
+    return HC_OK;
+  };
+
   struct It { unsigned quad; int depth; bool inst; };
   std::vector<It> st; st.push_back({ 1u, 1, false });
   std::vector<unsigned char> seen(size_t(quads), 0);
@@ -235,29 +223,44 @@ static int ValidateBvh(const unsigned char* nodes, int nodesNum, int trif4Num, i
   while (!st.empty())
   {
     It it = st.back(); st.pop_back();
-    if (it.quad >= unsigned(quads)) return HC_E_RANGE;
+    if (it.quad >= unsigned(quads) || it.quad == 0) return HC_E_RANGE;
     if (it.inst) maxMesh = std::max(maxMesh, it.depth); else maxTop = std::max(maxTop, it.depth);
     if (seen[it.quad]) continue;     // shared mesh sub-trees: depth of first visit is representative
     seen[it.quad] = 1;
+    float* Q = outNodes.data() + size_t(it.quad)*32;
+    unsigned words[4];
     for (int i = 0; i < 4; i++)
     {
       const N& c = nd[size_t(it.quad)*4 + i];
-      if (c.lo == 0xffffffffu && c.esc == 0xffffffffu) continue;
+      if (c.lo == 0xffffffffu && c.esc == 0xffffffffu)        // IsValidNode (cglobals.h:1321): an x slab at +inf fails for every finite ray
+      {
+        Q[0 + i] = INF; Q[4 + i] = INF; words[i] = HC_NODE_SENTINEL;
+        continue;
+      }
+      Q[0 + i] = c.bmin[0]; Q[4 + i] = c.bmax[0]; Q[8 + i] = c.bmin[1]; Q[12 + i] = c.bmax[1]; Q[16 + i] = c.bmin[2]; Q[20 + i] = c.bmax[2];
       const unsigned off = c.lo & 0x7fffffffu;
       if (c.lo & 0x80000000u)
       {
         if (!it.inst)
         {
-          if (off >= unsigned(quads)) return HC_E_RANGE;
-          const N& rec = nd[size_t(off)*4];
-          const unsigned sub = rec.lo & 0x7fffffffu;
-          if (rec.lo & 0x80000000u) { if (sub >= unsigned(trif4Num)) return HC_E_RANGE; maxMesh = std::max(maxMesh, 1); }
-          else st.push_back({ sub, 1, true });
+          if (off >= unsigned(quads) || off == 0) return HC_E_RANGE;
+          words[i] = HC_LEAF_BIT | off;
+          if (seen[off]) continue;
+          seen[off] = 1;
+          const N* rec = nd + size_t(off)*4;
+          float* R = outNodes.data() + size_t(off)*32;
+          memcpy(R, (const float*)rec + 8, 64);                // inverse matrix: float4 8Q+2 .. 8Q+5
+          unsigned sub = rec[0].lo & 0x7fffffffu, subWord;
+          if (rec[0].lo & 0x80000000u) { int rc = convertLeaf(sub, &subWord); if (rc) return rc; maxMesh = std::max(maxMesh, 1); }
+          else { subWord = sub; st.push_back({ sub, 1, true }); }
+          memcpy(R + 16, &subWord, 4);
+          memcpy(R + 17, (const float*)rec + 24, 8);           // {realInstId, meshId}: float4 8Q+6 .xy
         }
-        else if (off >= unsigned(trif4Num)) return HC_E_RANGE;
+        else { int rc = convertLeaf(off, &words[i]); if (rc) return rc; }
       }
-      else st.push_back({ off, it.depth + 1, it.inst });
+      else { words[i] = off; st.push_back({ off, it.depth + 1, it.inst }); }
     }
+    memcpy(Q + 24, words, 16);
   }
   *outStackBound = 3*(maxTop + maxMesh) + 2;
   return HC_OK;
@@ -384,14 +387,15 @@ int hc_set_bvh(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const v
   HC_REQUIRE(treeId == 0, HC_E_ARG, "hc_set_bvh: only tree 0 (opaque geometry) is supported; tree 1 holds alpha-tested meshes");
   HC_REQUIRE(haveInst != 0, HC_E_ARG, "hc_set_bvh: single-level trees (bvhType \"triangle4v\") are not supported, pass the two-level layout");
   int bound = 0;
-  int rc = ValidateBvh((const unsigned char*)nodes, nodesNum, trif4Num, &bound);
-  HC_REQUIRE(rc == HC_OK, rc, "hc_set_bvh: tree references nodes or triangles out of range");
+  std::vector<float> devNodes, devPairs;
+  int rc = ConvertBvhForDevice((const unsigned char*)nodes, nodesNum, (const float*)trif4, trif4Num, devNodes, devPairs, &bound);
+  HC_REQUIRE(rc == HC_OK, rc, "hc_set_bvh: tree references nodes or triangles out of range (or a leaf holds more than 128 triangles)");
   HC_REQUIRE(bound <= HC_STACK_CAP, HC_E_RANGE, "hc_set_bvh: tree too deep for the traversal stack");
   HC_CUDA(cudaSetDevice(ctx->device));
-  rc = hc_buf_reserve(ctx, ctx->bvhNodes, uint64_t(nodesNum)*32); if (rc) return rc;
-  rc = hc_buf_reserve(ctx, ctx->bvhTris, uint64_t(trif4Num)*16); if (rc) return rc;
-  HC_CUDA(cudaMemcpyAsync(ctx->bvhNodes.ptr, nodes, uint64_t(nodesNum)*32, cudaMemcpyHostToDevice, ctx->stream));
-  HC_CUDA(cudaMemcpyAsync(ctx->bvhTris.ptr, trif4, uint64_t(trif4Num)*16, cudaMemcpyHostToDevice, ctx->stream));
+  rc = hc_buf_reserve(ctx, ctx->bvhNodes, devNodes.size()*4); if (rc) return rc;
+  rc = hc_buf_reserve(ctx, ctx->bvhTris, std::max<size_t>(devPairs.size()*4, 16)); if (rc) return rc;
+  HC_CUDA(cudaMemcpyAsync(ctx->bvhNodes.ptr, devNodes.data(), devNodes.size()*4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!devPairs.empty()) HC_CUDA(cudaMemcpyAsync(ctx->bvhTris.ptr, devPairs.data(), devPairs.size()*4, cudaMemcpyHostToDevice, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));                // ConvertionResult pointers die at ConvertUnmap (RenderDriverRTE.cpp:1436)
   ctx->nodesNum = nodesNum; ctx->trif4Num = trif4Num; ctx->haveInst = haveInst; ctx->bvhDepthBound = bound;
   return HC_OK;

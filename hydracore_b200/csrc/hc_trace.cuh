@@ -3,26 +3,43 @@
 // Replaces BVH4TraversalInstKernel / BVH4TraversalInstShadowKenrel (reference hydra_drv/shaders/trace.cl:50, 309), i.e. the
 // device functions BVH4InstTraverse / BVH4InstTraverseShadow (hydra_drv/ctrace.h:841-1062, 1065-1294) with the triangle test
 // IntersectAllPrimitivesInLeaf (ctrace.h:124-182), the slab test RayBoxIntersectionLite2 (ctrace.h:32-53) and SafeInverse
-// (cglobals.h:726-735).  Same predicates, same float operations (no FMA contraction), same near-to-far child order, so the
-// closest hit is the same hit; what differs is HOW the tree is walked:
-//   * stack entries carry the child's entry distance, and an entry whose distance exceeds the current hit is dropped at
-//     pop time without fetching its 128-byte quad (the reference re-fetches and re-tests all four children);
-//   * one thread = one ray; the 128-byte quad is fetched with eight 128-bit loads on the read-only path;
-//   * persistent warps pull rays from a global counter with ballot/popc aggregation (one atomic per refill).
+// (cglobals.h:726-735).  Same predicates, the same IEEE float operations in the same order (no FMA contraction), the same
+// near-to-far sorting network, so the closest hit is the same hit.  What differs is HOW the tree is stored and walked:
+//
+//   * hc_set_bvh re-lays the reference blobs out for the device (ConvertBvhForDevice, hc_api.cu).  A quad stays 128 bytes and keeps its
+//     index, but becomes SoA: six float4 rows {minx[4], maxx[4], miny[4], maxy[4], minz[4], maxz[4]}, one uint4 row of child words.
+//     Two children share a 64-bit register pair, so one Blackwell packed-FP32 instruction (FADD2 / FMUL2: sub.rn.f32x2, mul.rn.f32x2,
+//     each half rounded exactly like the scalar op) slab-tests two children; the near/far row of an axis is picked by the sign of
+//     the ray direction (bit-identical to min(lo,hi) / max(lo,hi) for a finite ray) and the three axes are merged with the
+//     three-input FMNMX3.  Invalid children carry an infinite box that can never pass, so IsValidNode costs nothing.
+//   * triangles are stored two to a record with precomputed edges {A, B-A, C-A}, SoA over the pair, so the whole
+//     Moeller-Trumbore test runs in packed FP32 on two triangles at once; the leaf's triangle count lives in the child word,
+//     which removes the dependent header fetch.
+//   * stack entries carry the child's entry distance, and an entry whose distance exceeds the current hit is dropped at pop time
+//     without fetching its quad (the reference re-fetches and re-tests all four children);
+//   * "while-while" control flow (all lanes descend, then all lanes intersect) inside persistent warps that pull rays from a
+//     global counter with ballot/popc aggregation (one atomic per refill).
 #pragma once
 #include "hc_math.cuh"
 
-#define HC_LEAF_BIT   0x80000000u
-#define HC_MAXFLOAT   3.402823466e+38f // MAXFLOAT = FLT_MAX from <math.h> / OpenCL (the 1e37f fallback of ctrace.h:665-667 is never taken)
-#define HC_TRI_EPS    1e-6f            // barycentric slack, ctrace.h:111
-#define HC_STACK_CAP  64               // entries per ray; hc_set_bvh checks the tree against it
+#define HC_LEAF_BIT      0x80000000u
+#define HC_NODE_SENTINEL 0xffffffffu   // "ray finished"; also the child word of an empty slot
+#define HC_MAXFLOAT      3.402823466e+38f // MAXFLOAT = FLT_MAX from <math.h> / OpenCL (the 1e37f fallback of ctrace.h:665-667 is never taken)
+#define HC_TRI_EPS       1e-6f            // barycentric slack, ctrace.h:111
+#define HC_STACK_CAP     64               // entries per ray; hc_set_bvh checks the tree against it
+
+// triangle-leaf child word: [31] leaf | [30:25] pair records - 1 | [24:0] index of the first pair record (96 bytes each)
+#define HC_LEAF_PAIRS_SHIFT 25
+#define HC_LEAF_PAIRS_MAX   64
+#define HC_LEAF_INDEX_MASK  0x01ffffffu
+#define HC_PAIR_F4          6             // float4 per pair record
 
 struct HcHit { float t; int primId; int instId; int geomId; };   // == Lite_Hit (cglobals.h:1248-1256)
 
 struct HcBvh
 {
-  const float4* __restrict__ nodes;   // 2 float4 per node, 8 per quad
-  const float4* __restrict__ tris;    // leaf header float4 + 3 float4 per triangle
+  const float4* __restrict__ nodes;   // device layout: 8 float4 per quad (SoA boxes + child words) or per instance record
+  const float4* __restrict__ tris;    // device layout: pair records
 };
 
 HC_DEV float3 SafeInverse(float3 d)
@@ -35,19 +52,180 @@ HC_DEV float3 SafeInverse(float3 d)
   return r;
 }
 
-// one child of a quad: slab test + validity, returns entry distance or HC_MAXFLOAT when the child is not to be visited
-HC_DEV float ChildEntry(float4 lo4, float4 hi4, float3 o, float3 inv, float tHit)
+// ------------------------------------------------------------------------------------------------ packed FP32 (sm_100a)
+typedef unsigned long long hc_f2;      // two floats in one 64-bit register pair {lo, hi}
+
+HC_DEV hc_f2 pk2(float lo, float hi)          { hc_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+HC_DEV hc_f2 bc2(float v)                     { return pk2(v, v); }          // ptxas folds this into the .F32 broadcast operand form
+HC_DEV void  upk2(hc_f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+HC_DEV hc_f2 sub2(hc_f2 a, hc_f2 b)           { hc_f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+HC_DEV hc_f2 mul2(hc_f2 a, hc_f2 b)           { hc_f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+HC_DEV float max3f(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+HC_DEV float min3f(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+HC_DEV hc_f2 lo2(float4 v) { return pk2(v.x, v.y); }
+HC_DEV hc_f2 hi2(float4 v) { return pk2(v.z, v.w); }
+
+// ptxas 12.9 contracts mul.rn.f32x2 + add/sub.rn.f32x2 into FFMA2 (it never does that to the scalar .rn forms), which would round
+// once instead of twice and break bit-parity with the reference.  A difference of two PRODUCTS is therefore written as
+// fma(b, -1, a): exact, one instruction, and not contractible.  Sums of products are avoided altogether: cross products are
+// produced as (x, -y, -z) by swapping the operands of the y and z differences, so that every dot product
+// (a.x*b.x + a.y*b.y) + a.z*b.z becomes (a.x*b.x - a.y*(-b.y)) - a.z*(-b.z) — the same roundings, negation being exact.
+// tests/test_abi.py scans the SASS of the built library: an FFMA2 whose multiplier is not the immediate -1 fails the build check.
+HC_DEV hc_f2 dif2(hc_f2 a, hc_f2 b)
+{ hc_f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(b), "l"(0xbf800000bf800000ull), "l"(a)); return r; }   // a - b
+
+struct HcVec2 { hc_f2 x, y, z; };
+// cross(a, b) = (ay*bz - az*by, az*bx - ax*bz, ax*by - ay*bx), returned as (x, -y, -z)
+HC_DEV HcVec2 cross2_xnynz(const HcVec2& a, const HcVec2& b)
 {
-  const float lo  = inv.x*(lo4.x - o.x), hi  = inv.x*(hi4.x - o.x);
-  const float lo1 = inv.y*(lo4.y - o.y), hi1 = inv.y*(hi4.y - o.y);
-  const float lo2 = inv.z*(lo4.z - o.z), hi2 = inv.z*(hi4.z - o.z);
-  float tmin = fminf(lo, hi), tmax = fmaxf(lo, hi);
-  tmin = fmaxf(tmin, fminf(lo1, hi1)); tmax = fminf(tmax, fmaxf(lo1, hi1));
-  tmin = fmaxf(tmin, fminf(lo2, hi2)); tmax = fminf(tmax, fmaxf(lo2, hi2));
-  const bool valid = !((__float_as_uint(lo4.w) == 0xffffffffu) && (__float_as_uint(hi4.w) == 0xffffffffu));   // IsValidNode, cglobals.h:1321
-  const bool hit   = (tmin <= tmax) && (tmax >= 0.0f) && (tmin <= tHit) && valid;                             // t_rayMin == 0
-  return hit ? tmin : HC_MAXFLOAT;
+  HcVec2 r;
+  r.x = dif2(mul2(a.y, b.z), mul2(a.z, b.y));
+  r.y = dif2(mul2(a.x, b.z), mul2(a.z, b.x));
+  r.z = dif2(mul2(a.y, b.x), mul2(a.x, b.y));
+  return r;
 }
+// dot(a, b) with b given as (x, -y, -z): (ax*bx + ay*by) + az*bz
+HC_DEV hc_f2 dot2_xnynz(const HcVec2& a, const HcVec2& bn) { return dif2(dif2(mul2(a.x, bn.x), mul2(a.y, bn.y)), mul2(a.z, bn.z)); }
 
 #define HC_CSWAP(ta, ca, tb, cb) { const bool s_ = (tb < ta); const float tt_ = s_ ? tb : ta; const float tu_ = s_ ? ta : tb; \
                                    const unsigned ct_ = s_ ? cb : ca; const unsigned cu_ = s_ ? ca : cb; ta = tt_; tb = tu_; ca = ct_; cb = cu_; }
+
+// entry key of one child: tmin when (tmin <= tmax) && (tmax >= 0) && (tmin <= tHit), else MAXFLOAT.
+// With tHit >= 0 that condition equals max(tmin, 0) <= min(tmax, tHit).  n* / f* are the per-axis near / far plane distances.
+HC_DEV float ChildKey(float nx, float ny, float nz, float fx, float fy, float fz, float tHit)
+{
+  const float tmin = max3f(nx, ny, nz), tmax = min3f(fx, fy, fz);
+  return (fmaxf(tmin, 0.0f) <= fminf(tmax, tHit)) ? tmin : HC_MAXFLOAT;
+}
+
+// ------------------------------------------------------------------------------------------------ the traversal state of one ray
+struct HcRayTrav
+{
+  float3 o, d, inv;          // current space (world, or the instance's object space)
+  float3 wo, wd;             // world-space ray while inside an instance
+  float  t; int primId, geomId, hitInst;
+  int    instId;             // instance being traversed
+  int    sp, instTop;
+  unsigned node;
+  const char* nearX; const char* nearY; const char* nearZ;   // address of the near row of each axis in quad 0 (far row = near ^ 16)
+  bool   inInst;
+};
+
+// row order in a quad: minx 0, maxx 16, miny 32, maxy 48, minz 64, maxz 80 (bytes).  inv < 0 -> the max plane is the near one.
+// The quad array is 128-byte aligned, so `near ^ 16` addresses the far row of the same axis.
+HC_DEV void SetNearRows(HcRayTrav& r, const HcBvh& bvh)
+{
+  const char* base = reinterpret_cast<const char*>(bvh.nodes);
+  r.nearX = base + (r.inv.x < 0.0f ? 16 : 0);
+  r.nearY = base + (r.inv.y < 0.0f ? 48 : 32);
+  r.nearZ = base + (r.inv.z < 0.0f ? 80 : 64);
+}
+
+HC_DEV void TravStart(HcRayTrav& r, const HcBvh& bvh, float3 o, float3 d, float tFar)
+{
+  r.o = o; r.d = d; r.inv = SafeInverse(d); r.wo = o; r.wd = d;
+  r.t = tFar; r.primId = -1; r.hitInst = -1; r.geomId = int(0xC0000000u);      // Make_Lite_Hit(t, -1), cglobals.h:1258-1266
+  r.instId = -1; r.sp = 0; r.instTop = 0; r.node = 1u; r.inInst = false;
+  SetNearRows(r, bvh);
+}
+
+// pop until an entry that can still matter (entry distance <= current hit; t is the same quantity in world and object space because the
+// direction is not renormalised); leave the instance when the stack has dropped below its entry level
+#define HC_POP(r, bvh, stk)                                                                                \
+  {                                                                                                        \
+    for (;;)                                                                                               \
+    {                                                                                                      \
+      if (r.sp == 0) { r.node = HC_NODE_SENTINEL; break; }                                                 \
+      r.sp--;                                                                                              \
+      const uint2 e_ = stk[r.sp];                                                                          \
+      if (__uint_as_float(e_.y) <= r.t) { r.node = e_.x; break; }                                          \
+    }                                                                                                      \
+    if (r.inInst && r.sp < r.instTop)                                                                      \
+    { r.o = r.wo; r.d = r.wd; r.inv = SafeInverse(r.d); SetNearRows(r, bvh); r.inInst = false; }           \
+  }
+
+// one interior quad: slab-test four children (two per packed instruction), sort near to far, push three, descend into the nearest
+HC_DEV void TravQuad(HcRayTrav& r, const HcBvh& bvh, uint2* stk)
+{
+  const size_t qo = size_t(r.node)*128u;
+  const char* ax = r.nearX + qo; const char* ay = r.nearY + qo; const char* az = r.nearZ + qo;
+  const float4 NX = __ldg(reinterpret_cast<const float4*>(ax)), FX = __ldg(reinterpret_cast<const float4*>(size_t(ax) ^ 16u));
+  const float4 NY = __ldg(reinterpret_cast<const float4*>(ay)), FY = __ldg(reinterpret_cast<const float4*>(size_t(ay) ^ 16u));
+  const float4 NZ = __ldg(reinterpret_cast<const float4*>(az)), FZ = __ldg(reinterpret_cast<const float4*>(size_t(az) ^ 16u));
+  const uint4  ch = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(bvh.nodes) + qo + 96));
+  const hc_f2 oX = bc2(r.o.x), oY = bc2(r.o.y), oZ = bc2(r.o.z), iX = bc2(r.inv.x), iY = bc2(r.inv.y), iZ = bc2(r.inv.z);
+  // RayBoxIntersectionLite2 (ctrace.h:32-53): t = invDir*(plane - pos)
+  float nx0, nx1, nx2, nx3, ny0, ny1, ny2, ny3, nz0, nz1, nz2, nz3, fx0, fx1, fx2, fx3, fy0, fy1, fy2, fy3, fz0, fz1, fz2, fz3;
+  upk2(mul2(iX, sub2(lo2(NX), oX)), nx0, nx1); upk2(mul2(iX, sub2(hi2(NX), oX)), nx2, nx3);
+  upk2(mul2(iX, sub2(lo2(FX), oX)), fx0, fx1); upk2(mul2(iX, sub2(hi2(FX), oX)), fx2, fx3);
+  upk2(mul2(iY, sub2(lo2(NY), oY)), ny0, ny1); upk2(mul2(iY, sub2(hi2(NY), oY)), ny2, ny3);
+  upk2(mul2(iY, sub2(lo2(FY), oY)), fy0, fy1); upk2(mul2(iY, sub2(hi2(FY), oY)), fy2, fy3);
+  upk2(mul2(iZ, sub2(lo2(NZ), oZ)), nz0, nz1); upk2(mul2(iZ, sub2(hi2(NZ), oZ)), nz2, nz3);
+  upk2(mul2(iZ, sub2(lo2(FZ), oZ)), fz0, fz1); upk2(mul2(iZ, sub2(hi2(FZ), oZ)), fz2, fz3);
+  float t0 = ChildKey(nx0, ny0, nz0, fx0, fy0, fz0, r.t), t1 = ChildKey(nx1, ny1, nz1, fx1, fy1, fz1, r.t);
+  float t2 = ChildKey(nx2, ny2, nz2, fx2, fy2, fz2, r.t), t3 = ChildKey(nx3, ny3, nz3, fx3, fy3, fz3, r.t);
+  unsigned c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+  HC_CSWAP(t0, c0, t1, c1); HC_CSWAP(t2, c2, t3, c3);        // the reference's network: (0,1)(2,3) (0,2)(1,3) (1,2), ctrace.h:896-957
+  HC_CSWAP(t0, c0, t2, c2); HC_CSWAP(t1, c1, t3, c3);
+  HC_CSWAP(t1, c1, t2, c2);
+  if (t3 < HC_MAXFLOAT && r.sp < HC_STACK_CAP) { stk[r.sp] = make_uint2(c3, __float_as_uint(t3)); r.sp++; }
+  if (t2 < HC_MAXFLOAT && r.sp < HC_STACK_CAP) { stk[r.sp] = make_uint2(c2, __float_as_uint(t2)); r.sp++; }
+  if (t1 < HC_MAXFLOAT && r.sp < HC_STACK_CAP) { stk[r.sp] = make_uint2(c1, __float_as_uint(t1)); r.sp++; }
+  if (t0 < HC_MAXFLOAT) r.node = c0;
+  else HC_POP(r, bvh, stk)
+}
+
+// instance leaf of the top level: move the ray into the instance's object space (ctrace.h:1020-1046; DON'T normalise the direction)
+HC_DEV void TravEnterInstance(HcRayTrav& r, const HcBvh& bvh)
+{
+  const float4* rec = bvh.nodes + size_t(r.node & 0x7fffffffu)*8;
+  HcMat4 m; m.c0 = __ldg(rec + 0); m.c1 = __ldg(rec + 1); m.c2 = __ldg(rec + 2); m.c3 = __ldg(rec + 3);
+  const float4 w = __ldg(rec + 4);
+  r.instId = __float_as_int(w.y);
+  r.wo = r.o; r.wd = r.d;
+  r.o = mul4x3(m, r.o); r.d = mul3x3(m, r.d); r.inv = SafeInverse(r.d); SetNearRows(r, bvh);
+  r.inInst = true; r.instTop = r.sp;
+  r.node = __float_as_uint(w.x);
+}
+
+// triangle leaf: IntersectAllPrimitivesInLeaf (ctrace.h:124-182) on two triangles per step.  Returns true when a hit was accepted.
+HC_DEV bool TravLeaf(HcRayTrav& r, const HcBvh& bvh)
+{
+  const unsigned pairs = ((r.node >> HC_LEAF_PAIRS_SHIFT) & 63u) + 1u;
+  const float4* p = bvh.tris + size_t(r.node & HC_LEAF_INDEX_MASK)*HC_PAIR_F4;
+  HcVec2 O, D;
+  O.x = bc2(r.o.x); O.y = bc2(r.o.y); O.z = bc2(r.o.z);
+  D.x = bc2(r.d.x); D.y = bc2(r.d.y); D.z = bc2(r.d.z);
+  bool found = false;
+  for (unsigned k = 0; k < pairs; k++, p += HC_PAIR_F4)
+  {
+    const float4 r0 = __ldg(p + 0), r1 = __ldg(p + 1), r2 = __ldg(p + 2), r3 = __ldg(p + 3), r4 = __ldg(p + 4);
+    HcVec2 A, E1, E2;
+    A.x  = lo2(r0); A.y  = hi2(r0); A.z  = lo2(r1);
+    E1.x = hi2(r1); E1.y = lo2(r2); E1.z = hi2(r2);
+    E2.x = lo2(r3); E2.y = hi2(r3); E2.z = lo2(r4);
+    const HcVec2 pvecN = cross2_xnynz(D, E2);                                   // (p.x, -p.y, -p.z)
+    HcVec2 tvec; tvec.x = sub2(O.x, A.x); tvec.y = sub2(O.y, A.y); tvec.z = sub2(O.z, A.z);
+    const HcVec2 qvecN = cross2_xnynz(tvec, E1);                                // (q.x, -q.y, -q.z)
+    float det0, det1; upk2(dot2_xnynz(E1, pvecN), det0, det1);
+    const hc_f2 invDet = pk2(1.0f/det0, 1.0f/det1);
+    float v0, v1, u0, u1, t0, t1;
+    upk2(mul2(dot2_xnynz(tvec, pvecN), invDet), v0, v1);
+    upk2(mul2(dot2_xnynz(D, qvecN), invDet), u0, u1);                           // dot(qvec, ray_dir): products commute
+    upk2(mul2(dot2_xnynz(E2, qvecN), invDet), t0, t1);
+    if (v0 > -HC_TRI_EPS && u0 > -HC_TRI_EPS && (u0 + v0 < 1.0f + HC_TRI_EPS) && t0 > 0.0f && t0 < r.t)
+    {
+      r.t = t0; r.primId = __float_as_int(r4.z); r.geomId = __float_as_int(__ldg(p + 5).x); r.hitInst = r.instId; found = true;
+    }
+    if (v1 > -HC_TRI_EPS && u1 > -HC_TRI_EPS && (u1 + v1 < 1.0f + HC_TRI_EPS) && t1 > 0.0f && t1 < r.t)     // sequential, like the reference loop
+    {
+      r.t = t1; r.primId = __float_as_int(r4.w); r.geomId = __float_as_int(__ldg(p + 5).y); r.hitInst = r.instId; found = true;
+    }
+  }
+  return found;
+}
+
+HC_DEV bool RayIsFinite(float3 o, float3 d)
+{
+  return isfinite(o.x) && isfinite(o.y) && isfinite(o.z) && isfinite(d.x) && isfinite(d.y) && isfinite(d.z);
+}
