@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <limits>
@@ -36,16 +37,16 @@ void hc_buf_free(HcDevBuf& b) { if (b.ptr) cudaFree(b.ptr); b.ptr = nullptr; b.b
 
 // ------------------------------------------------------------------------------------------------------------------ kernels
 #define HC_TRACE_BLOCK 128
-#define HC_REFILL_MIN  12      // refill a warp from the global ray counter once this many lanes are idle
+#define HC_REFILL_MIN  24      // refill a warp from the global ray counter once this many lanes are idle (swept 4..32 on B200: 20-24 is best)
 
 // K2 / K2s.  Persistent warps: lanes that finished a ray are refilled together (one atomicAdd per refill, ranks by ballot/popc).
 // Between refills a lane runs the while-while loop of hc_trace.cuh: descend through interior quads until a leaf is reached, then
 // intersect (or enter the instance); the loop is left early once so few lanes are still busy that a refill pays off.
 // rpos/rdir are float4 streams with element stride `stride` (2 = interleaved {pos,dir} records, 1 = separate arrays).
-template<bool ANYHIT>
-__global__ void __launch_bounds__(HC_TRACE_BLOCK)
+template<bool ANYHIT, int MINB>
+__global__ void __launch_bounds__(HC_TRACE_BLOCK, MINB)
 k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long nArg,
-        const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter)
+        const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter, const int refillMin)
 {
   const long long n = nDev ? (long long)(*nDev) : nArg;      // the path tracer keeps its live-path count on the device
   uint2 stk[HC_STACK_CAP];                                    // {child word, entry distance}
@@ -63,7 +64,7 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
   for (;;)
   {
     const unsigned idleMask = __ballot_sync(FULL, idle);
-    if (idleMask != 0u && !exhausted && (__popc(idleMask) >= HC_REFILL_MIN || idleMask == FULL))
+    if (idleMask != 0u && !exhausted && (__popc(idleMask) >= refillMin || idleMask == FULL))
     {
       const int nIdle = __popc(idleMask), leader = __ffs(idleMask) - 1;
       unsigned long long base = 0;
@@ -77,30 +78,48 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
           const float4 p = __ldg(rpos + idx*stride), dd = __ldg(rdir + idx*stride);
           rayIdx = idx; idle = false;
           TravStart(r, bvh, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
-          if (ANYHIT && !(dd.w > 0.0f)) { visOut[idx] = 1; idle = true; }          // maxDist <= 0: lit (trace.cl:343-351)
+          if (ANYHIT && !(dd.w > 0.0f)) { visOut[idx] = 1; idle = true; r.node = HC_NODE_SENTINEL; }          // maxDist <= 0: lit (trace.cl:343-351)
           else if (!RayIsFinite(r.o, r.d)) r.node = HC_NODE_SENTINEL;              // every comparison of the reference fails on NaN: no hit
         }
       }
       if ((long long)base + nIdle >= n) exhausted = true;
     }
     if (__all_sync(FULL, idle)) { if (exhausted) break; else continue; }
-    if (idle) continue;
 
-    while (r.node != HC_NODE_SENTINEL)
+    // Vote scheduling: every lane is at an interior quad (Q), at a leaf (L: instance leaf or triangle-pair record) or has nothing
+    // to do.  The warp runs the step the majority is waiting for, and keeps doing so until a refill pays off.
+    for (;;)
     {
-      while (!(r.node & HC_LEAF_BIT)) TravQuad(r, bvh, stk);
-      if (r.node == HC_NODE_SENTINEL) break;
-      if (!r.inInst) TravEnterInstance(r, bvh);
-      else
+      bool wantQ = !(r.node & HC_LEAF_BIT);                                        // a finished / idle lane carries the sentinel (leaf bit set)
+      bool wantL = !wantQ && r.node != HC_NODE_SENTINEL;
+      unsigned mQ = __ballot_sync(FULL, wantQ), mL = __ballot_sync(FULL, wantL);
+      while (mQ != 0u && __popc(mQ) >= __popc(mL))
       {
-        const bool found = TravLeaf(r, bvh);
-        if (ANYHIT && found) { r.node = HC_NODE_SENTINEL; break; }
-        HC_POP(r, bvh, stk)
+        if (wantQ) TravQuad(r, bvh, stk);
+        wantQ = !(r.node & HC_LEAF_BIT); wantL = !wantQ && r.node != HC_NODE_SENTINEL;
+        mQ = __ballot_sync(FULL, wantQ); mL = __ballot_sync(FULL, wantL);
       }
-      if (!exhausted && __popc(__activemask()) <= 32 - HC_REFILL_MIN) break;       // enough idle lanes for a refill
+      while (mL != 0u && __popc(mL) > __popc(mQ))
+      {
+        if (wantL)
+        {
+          if (!r.inInst) TravEnterInstance(r, bvh);
+          else
+          {
+            bool done;
+            const bool found = TravLeafPair(r, bvh, &done);
+            if (ANYHIT && found) r.node = HC_NODE_SENTINEL;
+            else if (done) HC_POP(r, bvh, stk)
+          }
+        }
+        wantQ = !(r.node & HC_LEAF_BIT); wantL = !wantQ && r.node != HC_NODE_SENTINEL;
+        mQ = __ballot_sync(FULL, wantQ); mL = __ballot_sync(FULL, wantL);
+      }
+      const int busy = __popc(mQ | mL);
+      if (busy == 0 || (!exhausted && busy <= 32 - refillMin)) break;         // all done, or enough idle lanes for a refill
     }
 
-    if (r.node == HC_NODE_SENTINEL)
+    if (!idle && r.node == HC_NODE_SENTINEL)
     {
       if (ANYHIT) visOut[rayIdx] = (r.primId != -1) ? 0 : 1;
       else reinterpret_cast<float4*>(hitsOut)[rayIdx] = make_float4(r.t, __int_as_float(r.primId), __int_as_float(r.hitInst), __int_as_float(r.geomId));
@@ -130,11 +149,20 @@ static __global__ void k_make_shadow_rays(const float4* __restrict__ rays, const
 }
 
 // ------------------------------------------------------------------------------------------------------------------ helpers
+static int g_traceMinB = 0;
+static int TraceMinB()
+{
+  if (g_traceMinB == 0) { const char* e = getenv("HC_TRACE_MINB"); g_traceMinB = e ? atoi(e) : 6; if (g_traceMinB < 6 || g_traceMinB > 8) g_traceMinB = 6; }
+  return g_traceMinB;
+}
 static int TraceGrid(hc_ctx* ctx)
 {
   if (ctx->traceGrid > 0) return ctx->traceGrid;
   int perSM = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace<false>, HC_TRACE_BLOCK, 0);
+  const int mb = TraceMinB();
+  if (mb == 8)      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace<false, 8>, HC_TRACE_BLOCK, 0);
+  else if (mb == 7) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace<false, 7>, HC_TRACE_BLOCK, 0);
+  else              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace<false, 6>, HC_TRACE_BLOCK, 0);
   if (perSM < 1) perSM = 1;
   ctx->traceGrid = ctx->smCount*perSM;           // a whole number of waves: persistent CTAs, all resident
   return ctx->traceGrid;
@@ -157,8 +185,11 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   unsigned long long* counter = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
   HC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
   const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
-  if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter);
-  else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter);
+  const int mb = TraceMinB();
+  static int rf = 0; if (rf == 0) { const char* e = getenv("HC_TRACE_REFILL"); rf = e ? atoi(e) : HC_REFILL_MIN; if (rf < 1 || rf > 32) rf = HC_REFILL_MIN; }
+#define HC_LAUNCH_TRACE(MB) { if (anyHit) k_trace<true, MB><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf); \
+                              else        k_trace<false, MB><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf); }
+  if (mb == 8) HC_LAUNCH_TRACE(8) else if (mb == 7) HC_LAUNCH_TRACE(7) else HC_LAUNCH_TRACE(6)
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   if (anyHit) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n;

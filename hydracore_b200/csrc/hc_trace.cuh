@@ -141,10 +141,15 @@ HC_DEV void TravStart(HcRayTrav& r, const HcBvh& bvh, float3 o, float3 d, float 
       if (__uint_as_float(e_.y) <= r.t) { r.node = e_.x; break; }                                          \
     }                                                                                                      \
     if (r.inInst && r.sp < r.instTop)                                                                      \
-    { r.o = r.wo; r.d = r.wd; r.inv = SafeInverse(r.d); SetNearRows(r, bvh); r.inInst = false; }           \
+    {                                                                                                      \
+      asm volatile("" : "+f"(r.wd.x), "+f"(r.wd.y), "+f"(r.wd.z));   /* keeps SafeInverse(wd) out of the loop preheaders */ \
+      r.o = r.wo; r.d = r.wd; r.inv = SafeInverse(r.d); SetNearRows(r, bvh); r.inInst = false;             \
+    }                                                                                                      \
   }
 
-// one interior quad: slab-test four children (two per packed instruction), sort near to far, push three, descend into the nearest
+// one interior quad: slab-test four children (two per packed instruction), sort near to far, push three, descend into the nearest.
+// No capacity test on the pushes: hc_set_bvh rejects a tree whose worst-case stack exceeds HC_STACK_CAP (the reference instead
+// silently drops children once its 80-entry stack is full, ctrace.h:959-979 — a tree that deep is refused here).
 HC_DEV void TravQuad(HcRayTrav& r, const HcBvh& bvh, uint2* stk)
 {
   const size_t qo = size_t(r.node)*128u;
@@ -168,9 +173,9 @@ HC_DEV void TravQuad(HcRayTrav& r, const HcBvh& bvh, uint2* stk)
   HC_CSWAP(t0, c0, t1, c1); HC_CSWAP(t2, c2, t3, c3);        // the reference's network: (0,1)(2,3) (0,2)(1,3) (1,2), ctrace.h:896-957
   HC_CSWAP(t0, c0, t2, c2); HC_CSWAP(t1, c1, t3, c3);
   HC_CSWAP(t1, c1, t2, c2);
-  if (t3 < HC_MAXFLOAT && r.sp < HC_STACK_CAP) { stk[r.sp] = make_uint2(c3, __float_as_uint(t3)); r.sp++; }
-  if (t2 < HC_MAXFLOAT && r.sp < HC_STACK_CAP) { stk[r.sp] = make_uint2(c2, __float_as_uint(t2)); r.sp++; }
-  if (t1 < HC_MAXFLOAT && r.sp < HC_STACK_CAP) { stk[r.sp] = make_uint2(c1, __float_as_uint(t1)); r.sp++; }
+  if (t3 < HC_MAXFLOAT) { stk[r.sp] = make_uint2(c3, __float_as_uint(t3)); r.sp++; }
+  if (t2 < HC_MAXFLOAT) { stk[r.sp] = make_uint2(c2, __float_as_uint(t2)); r.sp++; }
+  if (t1 < HC_MAXFLOAT) { stk[r.sp] = make_uint2(c1, __float_as_uint(t1)); r.sp++; }
   if (t0 < HC_MAXFLOAT) r.node = c0;
   else HC_POP(r, bvh, stk)
 }
@@ -188,39 +193,38 @@ HC_DEV void TravEnterInstance(HcRayTrav& r, const HcBvh& bvh)
   r.node = __float_as_uint(w.x);
 }
 
-// triangle leaf: IntersectAllPrimitivesInLeaf (ctrace.h:124-182) on two triangles per step.  Returns true when a hit was accepted.
-HC_DEV bool TravLeaf(HcRayTrav& r, const HcBvh& bvh)
+// triangle leaf: IntersectAllPrimitivesInLeaf (ctrace.h:124-182), ONE pair record (two triangles) per call; the leaf word itself is the
+// cursor (index up, count down).  Returns true when a hit was accepted; sets *done when the leaf is exhausted.
+HC_DEV bool TravLeafPair(HcRayTrav& r, const HcBvh& bvh, bool* done)
 {
-  const unsigned pairs = ((r.node >> HC_LEAF_PAIRS_SHIFT) & 63u) + 1u;
   const float4* p = bvh.tris + size_t(r.node & HC_LEAF_INDEX_MASK)*HC_PAIR_F4;
+  *done = ((r.node >> HC_LEAF_PAIRS_SHIFT) & 63u) == 0u;
+  r.node = r.node - (1u << HC_LEAF_PAIRS_SHIFT) + 1u;
   HcVec2 O, D;
   O.x = bc2(r.o.x); O.y = bc2(r.o.y); O.z = bc2(r.o.z);
   D.x = bc2(r.d.x); D.y = bc2(r.d.y); D.z = bc2(r.d.z);
   bool found = false;
-  for (unsigned k = 0; k < pairs; k++, p += HC_PAIR_F4)
+  const float4 r0 = __ldg(p + 0), r1 = __ldg(p + 1), r2 = __ldg(p + 2), r3 = __ldg(p + 3), r4 = __ldg(p + 4);
+  HcVec2 A, E1, E2;
+  A.x  = lo2(r0); A.y  = hi2(r0); A.z  = lo2(r1);
+  E1.x = hi2(r1); E1.y = lo2(r2); E1.z = hi2(r2);
+  E2.x = lo2(r3); E2.y = hi2(r3); E2.z = lo2(r4);
+  const HcVec2 pvecN = cross2_xnynz(D, E2);                                   // (p.x, -p.y, -p.z)
+  HcVec2 tvec; tvec.x = sub2(O.x, A.x); tvec.y = sub2(O.y, A.y); tvec.z = sub2(O.z, A.z);
+  const HcVec2 qvecN = cross2_xnynz(tvec, E1);                                // (q.x, -q.y, -q.z)
+  float det0, det1; upk2(dot2_xnynz(E1, pvecN), det0, det1);
+  const hc_f2 invDet = pk2(1.0f/det0, 1.0f/det1);
+  float v0, v1, u0, u1, t0, t1;
+  upk2(mul2(dot2_xnynz(tvec, pvecN), invDet), v0, v1);
+  upk2(mul2(dot2_xnynz(D, qvecN), invDet), u0, u1);                           // dot(qvec, ray_dir): products commute
+  upk2(mul2(dot2_xnynz(E2, qvecN), invDet), t0, t1);
+  if (v0 > -HC_TRI_EPS && u0 > -HC_TRI_EPS && (u0 + v0 < 1.0f + HC_TRI_EPS) && t0 > 0.0f && t0 < r.t)
   {
-    const float4 r0 = __ldg(p + 0), r1 = __ldg(p + 1), r2 = __ldg(p + 2), r3 = __ldg(p + 3), r4 = __ldg(p + 4);
-    HcVec2 A, E1, E2;
-    A.x  = lo2(r0); A.y  = hi2(r0); A.z  = lo2(r1);
-    E1.x = hi2(r1); E1.y = lo2(r2); E1.z = hi2(r2);
-    E2.x = lo2(r3); E2.y = hi2(r3); E2.z = lo2(r4);
-    const HcVec2 pvecN = cross2_xnynz(D, E2);                                   // (p.x, -p.y, -p.z)
-    HcVec2 tvec; tvec.x = sub2(O.x, A.x); tvec.y = sub2(O.y, A.y); tvec.z = sub2(O.z, A.z);
-    const HcVec2 qvecN = cross2_xnynz(tvec, E1);                                // (q.x, -q.y, -q.z)
-    float det0, det1; upk2(dot2_xnynz(E1, pvecN), det0, det1);
-    const hc_f2 invDet = pk2(1.0f/det0, 1.0f/det1);
-    float v0, v1, u0, u1, t0, t1;
-    upk2(mul2(dot2_xnynz(tvec, pvecN), invDet), v0, v1);
-    upk2(mul2(dot2_xnynz(D, qvecN), invDet), u0, u1);                           // dot(qvec, ray_dir): products commute
-    upk2(mul2(dot2_xnynz(E2, qvecN), invDet), t0, t1);
-    if (v0 > -HC_TRI_EPS && u0 > -HC_TRI_EPS && (u0 + v0 < 1.0f + HC_TRI_EPS) && t0 > 0.0f && t0 < r.t)
-    {
-      r.t = t0; r.primId = __float_as_int(r4.z); r.geomId = __float_as_int(__ldg(p + 5).x); r.hitInst = r.instId; found = true;
-    }
-    if (v1 > -HC_TRI_EPS && u1 > -HC_TRI_EPS && (u1 + v1 < 1.0f + HC_TRI_EPS) && t1 > 0.0f && t1 < r.t)     // sequential, like the reference loop
-    {
-      r.t = t1; r.primId = __float_as_int(r4.w); r.geomId = __float_as_int(__ldg(p + 5).y); r.hitInst = r.instId; found = true;
-    }
+    r.t = t0; r.primId = __float_as_int(r4.z); r.geomId = __float_as_int(__ldg(p + 5).x); r.hitInst = r.instId; found = true;
+  }
+  if (v1 > -HC_TRI_EPS && u1 > -HC_TRI_EPS && (u1 + v1 < 1.0f + HC_TRI_EPS) && t1 > 0.0f && t1 < r.t)     // sequential, like the reference loop
+  {
+    r.t = t1; r.primId = __float_as_int(r4.w); r.geomId = __float_as_int(__ldg(p + 5).y); r.hitInst = r.instId; found = true;
   }
   return found;
 }

@@ -91,3 +91,23 @@ def test_bvh_builder_against_brute_force(built, oracle):
             assert h["primId"][i] >= 0 and abs(t[ok].min() - h["t"][i]) <= 1e-4*t[ok].min()
         else:
             assert h["primId"][i] < 0
+
+
+def test_packed_fp32_is_not_contracted(built):
+    """Bit-parity guard for the traversal kernels: ptxas contracts mul.rn.f32x2 + add/sub.rn.f32x2 into FFMA2, which rounds once
+    instead of twice.  hc_trace.cuh writes every difference of products as fma(b, -1, a); any FFMA2 in the shipped SASS whose
+    multiplier is not the immediate -1 means a packed multiply-add was fused behind our back."""
+    import shutil
+    import subprocess
+    from hydracore_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "k_trace", _lib.lib_path()], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    if "FMUL2" not in sass:       # older cuobjdump builds cannot filter by template name: dump everything
+        sass = subprocess.run([cuobjdump, "-sass", _lib.lib_path()], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    lines = [ln for ln in sass.splitlines() if " FFMA2 " in ln]
+    assert "FMUL2" in sass and "FADD2" in sass and "FMNMX3" in sass, "the traversal kernel is expected to use packed FP32 and 3-input min/max"
+    assert lines, "expected FFMA2 (a - b as fma(b, -1, a)) in the traversal kernel"
+    bad = [ln.strip() for ln in lines if ", -1, " not in ln]
+    assert not bad, "contracted packed multiply-add found:\n" + "\n".join(bad[:5])
