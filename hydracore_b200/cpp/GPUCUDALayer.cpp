@@ -1,0 +1,267 @@
+#include "GPUCUDALayer.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cwchar>
+#include <sstream>
+#include <stdexcept>
+
+static const char* const kStorageNames[HC_STORAGE_COUNT] = { "textures", "textures_aux", "geom", "materials", "pdfs" };   // RenderDriverRTE.cpp:705-709
+
+void GPUCUDALayer::Check(int rc, const char* what) const
+{
+  if (rc == HC_OK) return;
+  std::ostringstream s;
+  s << "GPUCUDALayer::" << what << ": status " << rc << ": " << hc_last_error();
+  throw std::runtime_error(s.str());                            // RUN_TIME_ERROR semantics (globals_sys.h:56-62), caught in main.cpp:331-338
+}
+
+GPUCUDALayer::GPUCUDALayer(int w, int h, int a_flags, int a_deviceId)
+  : m_ctx(nullptr), m_initFlags(a_flags), m_integratorOverride(-1), m_globalsDirty(true), m_ptInitialised(false), m_seed(0), m_spp(0.0f),
+    m_sppContributed(0.0f)
+{
+  Check(hc_ctx_create(a_deviceId, &m_ctx), "GPUCUDALayer (hc_ctx_create)");
+  memset(&m_stat, 0, sizeof(m_stat));
+  if (w > 0 && h > 0) ResizeScreen(w, h, a_flags);
+}
+
+GPUCUDALayer::~GPUCUDALayer()
+{
+  if (m_ctx) hc_ctx_destroy(m_ctx);                             // the storages belong to the driver (IHWLayerDataAssembler.cpp:66-78)
+  m_ctx = nullptr;
+}
+
+void GPUCUDALayer::Clear(CLEAR_FLAGS a_flags)
+{
+  // what GPUOCLLayer does: the storages are cleared by the driver through IMemoryStorage::Clear; here only derived state goes
+  if (a_flags & CLEAR_GEOMETRY) m_ptInitialised = false;
+  m_globalsDirty = true;
+}
+
+IMemoryStorage* GPUCUDALayer::CreateMemStorage(uint64_t a_maxSizeInBytes, const char* a_name)
+{
+  int slot = -1;
+  for (int i = 0; i < HC_STORAGE_COUNT; i++) if (std::string(a_name) == kStorageNames[i]) slot = i;
+  if (slot < 0) Check(HC_E_ARG, "CreateMemStorage (unknown storage name)");
+  IMemoryStorage* pStorage = nullptr;
+  if (slot == HC_STORAGE_GEOM || slot == HC_STORAGE_TEXTURES)   // host mirror needed by the driver (GPUOCLData.cpp:56-63)
+    pStorage = new MemoryStorageBothCPUAndCUDA(new LinearStorageCPU(), new MemoryStorageCUDA(m_ctx, slot));
+  else
+    pStorage = new MemoryStorageCUDA(m_ctx, slot);
+  if (pStorage->Reserve(a_maxSizeInBytes) == size_t(-1)) { delete pStorage; Check(HC_E_NOMEM, "CreateMemStorage (device allocation failed)"); }
+  m_allMemStorages[a_name] = pStorage;
+  return pStorage;
+}
+
+void GPUCUDALayer::PrepareEngineGlobals()
+{
+  Base::PrepareEngineGlobals();                                 // SetQMCVarRemapTable + header copy into m_cdataPrepared (IHWLayerDataAssembler.cpp:326-339)
+  m_globalsDirty = true;
+}
+
+void GPUCUDALayer::PrepareEngineTables()
+{
+  Base::PrepareEngineTables();                                  // id -> offset tables of the five storages + light selector tables (:346-388)
+  m_globalsDirty = true;
+  UploadGlobalsIfDirty();
+}
+
+void GPUCUDALayer::UploadGlobalsIfDirty()
+{
+  if (!m_globalsDirty || m_cdataPrepared.empty()) return;
+  memcpy(m_cdataPrepared.data(), &m_globsBuffHeader, sizeof(EngineGlobals));   // the header may have changed since (SetAllFlagsAndVars, SetCamMatrices)
+  Check(hc_set_globals(m_ctx, m_cdataPrepared.data(), uint64_t(m_cdataPrepared.size())*sizeof(int)), "PrepareEngineGlobals (hc_set_globals)");
+  m_globalsDirty = false;
+}
+
+void GPUCUDALayer::SetAllBVH4(const ConvertionResult& a_convertedBVH, IBVHBuilder2* a_inBuilderAPI, int a_flags)
+{
+  (void)a_inBuilderAPI; (void)a_flags;
+  if (a_convertedBVH.treesNum < 1) Check(HC_E_ARG, "SetAllBVH4 (no trees)");
+  for (int i = 1; i < a_convertedBVH.treesNum; i++)
+    if (a_convertedBVH.nodesNum[i] > 4 && a_convertedBVH.pTriangleAlpha[i] != nullptr)
+      Check(HC_E_ARG, "SetAllBVH4 (tree with an alpha-test table: opacity-mapped meshes are not supported yet)");
+  const bool haveInst = (std::string(a_convertedBVH.bvhType[0] ? a_convertedBVH.bvhType[0] : "") != "triangle4v");       // GPUOCLData.cpp:118
+  // the ConvertionResult pointers die at ConvertUnmap (RenderDriverRTE.cpp:1436): hc_set_bvh converts and uploads before it returns
+  Check(hc_set_bvh(m_ctx, 0, a_convertedBVH.pBVH[0], a_convertedBVH.nodesNum[0], a_convertedBVH.pTriangleData[0], a_convertedBVH.trif4Num[0], haveInst ? 1 : 0),
+        "SetAllBVH4 (hc_set_bvh)");
+}
+
+void GPUCUDALayer::SetAllInstMatrices(const float4x4* a_matrices, int32_t a_matrixNum)
+{
+  if (a_matrices == nullptr || a_matrixNum == 0) return;
+  Check(hc_set_inst_matrices(m_ctx, reinterpret_cast<const float*>(a_matrices), a_matrixNum), "SetAllInstMatrices");   // float4x4 = 4 column float4 (cglobals.h:206-209)
+}
+
+void GPUCUDALayer::SetAllInstLightInstId(const int32_t* a_lightInstIds, int32_t a_instNum)
+{
+  if (a_lightInstIds == nullptr || a_instNum == 0) return;
+  Check(hc_set_inst_light_ids(m_ctx, a_lightInstIds, a_instNum), "SetAllInstLightInstId");
+}
+
+void GPUCUDALayer::SetAllPODLights(PlainLight* a_lights2, size_t a_number)
+{
+  Base::SetAllPODLights(a_lights2, a_number);                   // lights + sky / sun bookkeeping into m_cdataPrepared (IHWLayerDataAssembler.cpp:390-452)
+  m_globalsDirty = true;
+}
+
+void GPUCUDALayer::SetAllFlagsAndVars(const AllRenderVarialbes& a_vars)
+{
+  Base::SetAllFlagsAndVars(a_vars);
+  m_globalsDirty = true;                                        // re-uploaded before the next pass (UpdateVarsOnGPU of the OpenCL layer, GPUOCLData.cpp:277-287)
+}
+
+void GPUCUDALayer::ResizeScreen(int w, int h, int a_flags)
+{
+  Base::ResizeScreen(w, h, a_flags);
+  Check(hc_resize(m_ctx, w, h), "ResizeScreen");
+  m_ptInitialised = false;
+  m_spp = 0.0f;
+}
+
+int GPUCUDALayer::IntegratorFromState() const
+{
+  if (m_integratorOverride >= 0) return m_integratorOverride;
+  if (m_vars.m_flags & HRT_STUPID_PT_MODE) return HC_INTEGRATOR_PT;                 // IntegratorStupidPT
+  if (m_vars.m_varsI[HRT_KMLT_OR_QMC_MAT_BOUNCES] != 0) return HC_INTEGRATOR_MISPT_QMC;   // the OpenCL layer's QMC switch (GPUOCLLayer.cpp:1436-1446)
+  return HC_INTEGRATOR_MISPT;                                                       // what CPUExpLayer instantiates (IHWLayerDataAssembler.cpp:579)
+}
+
+void GPUCUDALayer::InitPathTracing(int seed, std::vector<int32_t>* pInstRemapTable)
+{
+  (void)pInstRemapTable;
+  UploadGlobalsIfDirty();
+  m_seed = seed;
+  Check(hc_pt_init(m_ctx, seed), "InitPathTracing");
+  m_ptInitialised = true;
+  m_spp = 0.0f; m_sppContributed = 0.0f;
+}
+
+void GPUCUDALayer::BeginTracingPass()
+{
+  UploadGlobalsIfDirty();
+  if (!(m_vars.m_flags & HRT_UNIFIED_IMAGE_SAMPLING)) return;   // the OpenCL layer only draws debug normals without it (GPUOCLLayer.cpp:1455-1458)
+  if (!m_ptInitialised) InitPathTracing(m_seed);
+  Check(hc_pt_pass(m_ctx, IntegratorFromState(), 1), "BeginTracingPass");
+}
+
+void GPUCUDALayer::EndTracingPass()
+{
+  Check(hc_sync(m_ctx), "EndTracingPass");                      // clFinish of the OpenCL layer (GPUOCLLayer.cpp:1486-1491)
+  Check(hc_get_spp(m_ctx, &m_spp), "EndTracingPass (hc_get_spp)");
+  if (m_pExternalImage != nullptr) ContribToExternalImageAccumulator(m_pExternalImage);
+}
+
+void GPUCUDALayer::FinishAll() { Check(hc_sync(m_ctx), "FinishAll"); }
+
+void GPUCUDALayer::ClearAccumulatedColor()
+{
+  Check(hc_fb_clear(m_ctx), "ClearAccumulatedColor");
+  m_spp = 0.0f; m_sppContributed = 0.0f;
+}
+
+void GPUCUDALayer::ResetPerfCounters()
+{
+  memset(&m_stat, 0, sizeof(MRaysStat));
+  Check(hc_reset_stats(m_ctx), "ResetPerfCounters");
+}
+
+void GPUCUDALayer::GetLDRImage(uint32_t* data, int width, int height) const { Check(hc_fb_read_ldr(m_ctx, data, width, height), "GetLDRImage"); }
+void GPUCUDALayer::GetHDRImage(float4* data, int width, int height)   const { Check(hc_fb_read_hdr(m_ctx, reinterpret_cast<float*>(data), width, height), "GetHDRImage"); }
+
+size_t GPUCUDALayer::GetAvaliableMemoryAmount(bool allMem)
+{
+  size_t f = 0, t = 0;
+  Check(hc_mem_info(m_ctx, &f, &t), "GetAvaliableMemoryAmount");
+  return allMem ? t : f;
+}
+
+MRaysStat GPUCUDALayer::GetRaysStat()
+{
+  hc_stats s; Check(hc_get_stats(m_ctx, &s), "GetRaysStat");
+  const float total = s.msClosest + s.msShadow + s.msShade + s.msOther;
+  m_stat.traversalTimeMs  = s.msClosest;
+  m_stat.shadowTimeMs     = s.msShadow;
+  m_stat.shadeTimeMs      = s.msShade;
+  m_stat.traceTimePerCent = total > 0.0f ? int(100.0f*(s.msClosest + s.msShadow)/total) : 0;
+  m_stat.raysPerSec       = total > 0.0f ? float(double(s.raysClosest + s.raysShadow)/(1e-3*double(total))) : 0.0f;
+  m_stat.samplesPerSec    = total > 0.0f ? float(double(s.paths)/(1e-3*double(total))) : 0.0f;
+  return m_stat;
+}
+
+const char* GPUCUDALayer::GetDeviceName(int* pOCLVer) const
+{
+  if (pOCLVer) *pOCLVer = 0;
+  char buf[256]; Check(hc_device_name(m_ctx, buf, 256), "GetDeviceName");
+  m_deviceName = buf;
+  return m_deviceName.c_str();
+}
+
+const HRRenderDeviceInfoListElem* GPUCUDALayer::ListDevices() const
+{
+  int n = 0; hc_device_count(&n);
+  m_deviceList.assign(size_t(n), HRRenderDeviceInfoListElem());
+  for (int i = 0; i < n; i++)
+  {
+    HRRenderDeviceInfoListElem& e = m_deviceList[size_t(i)];
+    memset(&e, 0, sizeof(e));
+    e.id = i;
+    swprintf(e.name, 256, L"CUDA device %d", i);
+    wcsncpy(e.driver, L"CUDA (sm_100a)", 255);
+    e.isCPU = false; e.isEnabled = false;
+    e.next = (i + 1 < n) ? &m_deviceList[size_t(i) + 1] : nullptr;
+  }
+  return m_deviceList.empty() ? nullptr : m_deviceList.data();
+}
+
+void GPUCUDALayer::CallNamedFunc(const char* a_name, const char* a_args)
+{
+  const std::string name = a_name ? a_name : "", args = a_args ? a_args : "";
+  if (name == "integrator")
+  {
+    if      (args == "pt")    m_integratorOverride = HC_INTEGRATOR_PT;
+    else if (args == "mispt") m_integratorOverride = HC_INTEGRATOR_MISPT;
+    else if (args == "qmc")   m_integratorOverride = HC_INTEGRATOR_MISPT_QMC;
+    else if (args == "auto")  m_integratorOverride = -1;
+    else Check(HC_E_ARG, "CallNamedFunc(integrator): expected pt | mispt | qmc | auto");
+  }
+  else if (name == "tiles")
+  {
+    int tile = 32, rank = 0, world = 1;
+    if (sscanf(args.c_str(), "%d %d %d", &tile, &rank, &world) != 3) Check(HC_E_ARG, "CallNamedFunc(tiles): expected \"<tileSize> <rank> <worldSize>\"");
+    Check(hc_pt_set_tiles(m_ctx, tile, rank, world), "CallNamedFunc(tiles)");
+    m_ptInitialised = false;
+  }
+}
+
+// One process per GPU adds its partial sums into the shared image under the image's lock: the multi-process mode of the reference
+// (GPUOCLLayerOther.cpp:365-430; README.md:99-103).  Layer 0 of the shared image holds SUMS over spp, Header()->spp the sample count.
+void GPUCUDALayer::ContribToExternalImageAccumulator(IHRSharedAccumImage* a_pImage)
+{
+  if (a_pImage == nullptr) return;
+  const float newSpp = m_spp - m_sppContributed;
+  if (newSpp <= 0.0f) return;
+  std::vector<float> hdr(size_t(m_width)*size_t(m_height)*4);
+  Check(hc_fb_read_hdr(m_ctx, hdr.data(), m_width, m_height), "ContribToExternalImageAccumulator");
+  if (!a_pImage->Lock(100)) return;                             // try again after the next pass, like the reference
+  HRSharedBufferHeader* h = a_pImage->Header();
+  float* dst = a_pImage->ImageData(0);
+  if (h != nullptr && dst != nullptr && h->width == m_width && h->height == m_height)
+  {
+    // hdr = (sum over m_spp samples)/m_spp; the shared image wants the mean weighted by sample counts
+    const float have = h->spp, total = have + newSpp;
+    const float wOld = have/total, wNew = newSpp/total;
+    const size_t n = size_t(m_width)*size_t(m_height)*4;
+    for (size_t i = 0; i < n; i++) dst[i] = dst[i]*wOld + hdr[i]*wNew;
+    h->spp = total;
+    h->counterRcv++;
+    m_sppContributed = m_spp;
+    // the framebuffer on the device keeps accumulating; only the not-yet-contributed share is weighted in next time
+    Check(hc_fb_clear(m_ctx), "ContribToExternalImageAccumulator (hc_fb_clear)");
+    m_spp = 0.0f; m_sppContributed = 0.0f;
+  }
+  a_pImage->Unlock();
+}
+
+IHWLayer* CreateCudaImpl(int w, int h, int a_flags, int a_deviceId) { return new GPUCUDALayer(w, h, a_flags, a_deviceId); }

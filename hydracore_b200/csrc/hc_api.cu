@@ -192,7 +192,7 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   if (mb == 8) HC_LAUNCH_TRACE(8) else if (mb == 7) HC_LAUNCH_TRACE(7) else HC_LAUNCH_TRACE(6)
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
-  if (anyHit) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n;
+  if (!nDev) { if (anyHit) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n; }   // counted launches: hc_pt_pass reads the live counts back
   return HC_OK;
 }
 

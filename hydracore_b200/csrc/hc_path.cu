@@ -289,6 +289,8 @@ struct HcPathHost
   std::vector<unsigned char> materialsHost, globalsHost;
   int64_t capacity = 0;
   int nOwned = 0;
+  std::vector<cudaEvent_t> evPool;            // per-launch stage timing of the LAST pass of a hc_pt_pass call: {start, stop} pairs
+  std::vector<int> evClass;                    // 0 closest, 1 shadow, 2 shade, 3 other
 };
 static HcPathHost* PH(hc_ctx* c) { return reinterpret_cast<HcPathHost*>(c->pathHost); }
 
@@ -298,6 +300,7 @@ void hc_path_free(hc_ctx* ctx)
   if (!p) return;
   for (int b = 0; b < 2; b++) for (int k = 0; k < 9; k++) hc_buf_free(p->state[b][k]);
   hc_buf_free(p->hits); hc_buf_free(p->vis); hc_buf_free(p->owned); hc_buf_free(p->pathCount); hc_buf_free(p->ldr);
+  for (cudaEvent_t e : p->evPool) cudaEventDestroy(e);
   delete p;
   ctx->pathHost = nullptr;
 }
@@ -375,10 +378,24 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
     if (tex != HC_INVALID_TEXTURE) { why = "textured area lights are not supported yet"; return HC_E_ARG; }
     if (spot != 0) { why = "area lights with a spot distribution are not supported yet"; return HC_E_ARG; }
   }
+  // walk the material nodes REACHABLE from the materials table (the storage may hold stale or unused chunks after in-place updates)
   const size_t nNodes = p->materialsHost.size()/(HC_PLAIN_MATERIAL_DATA_SIZE*4);
-  for (size_t k = 0; k < nNodes; k++)
+  const int matTabOff = gi(HC_EG_materialsTableOffset), matTabSize = gi(HC_EG_materialsTableSize);
+  if (size_t(matTabOff) + size_t(std::max(matTabSize, 0)) > gl.size()/4) { why = "materials table lies outside the globals blob"; return HC_E_RANGE; }
+  std::vector<long long> todo;
+  for (int t = 0; t < matTabSize; t++)
   {
-    const float* m = reinterpret_cast<const float*>(p->materialsHost.data()) + k*HC_PLAIN_MATERIAL_DATA_SIZE;
+    int off4; memcpy(&off4, gl.data() + (size_t(matTabOff) + size_t(t))*4, 4);      // float4 offset of the head node, or -1
+    if (off4 < 0) continue;
+    todo.push_back((long long)off4*4);                                               // -> float index
+  }
+  size_t visited = 0;
+  while (!todo.empty())
+  {
+    const long long f0 = todo.back(); todo.pop_back();
+    if (f0 < 0 || size_t(f0) + HC_PLAIN_MATERIAL_DATA_SIZE > p->materialsHost.size()/4) { why = "material node outside the materials storage"; return HC_E_RANGE; }
+    if (++visited > 4*nNodes + 64) { why = "material blend tree does not terminate"; return HC_E_ARG; }
+    const float* m = reinterpret_cast<const float*>(p->materialsHost.data()) + f0;
     int type, flags, ntex, ptex; memcpy(&type, m + HC_PLAIN_MAT_TYPE_OFFSET, 4); memcpy(&flags, m + HC_PLAIN_MAT_FLAGS_OFFSET, 4);
     memcpy(&ntex, m + HC_NORMAL_TEX_OFFSET, 4); memcpy(&ptex, m + HC_PROC_TEX1_F4_HEAD_OFFSET, 4);
     const bool ok = type == HC_PLAIN_MAT_CLASS_LAMBERT || type == HC_PLAIN_MAT_CLASS_PHONG_SPECULAR || type == HC_PLAIN_MAT_CLASS_GGX ||
@@ -390,8 +407,12 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
     if (type == HC_PLAIN_MAT_CLASS_GLASS && (flags & HC_PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER)) { why = "glass multiscattering table is not supported yet"; return HC_E_ARG; }
     if (type == HC_PLAIN_MAT_CLASS_BLEND_MASK)
     {
-      int bf; memcpy(&bf, m + HC_BLEND_MASK_FLAGS_OFFSET, 4);
+      int bf, o1, o2; memcpy(&bf, m + HC_BLEND_MASK_FLAGS_OFFSET, 4);
+      memcpy(&o1, m + HC_BLEND_MASK_MATERIAL1_OFFSET, 4); memcpy(&o2, m + HC_BLEND_MASK_MATERIAL2_OFFSET, 4);
       if (bf & HC_BLEND_MASK_FALOFF) { why = "falloff blend masks are not supported yet"; return HC_E_ARG; }
+      if (o1 == 0 || o2 == 0) { why = "blend mask node references itself"; return HC_E_ARG; }
+      todo.push_back(f0 + (long long)o1*HC_PLAIN_MATERIAL_DATA_SIZE);               // children by RELATIVE node offset (cmaterial.h:1994-1995)
+      todo.push_back(f0 + (long long)o2*HC_PLAIN_MATERIAL_DATA_SIZE);
     }
   }
   return HC_OK;
@@ -525,13 +546,26 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   const unsigned* qtab = (const unsigned*)ctx->qmcTable.ptr;
   const int nBounces = (integrator == HC_INTEGRATOR_PT) ? pp.maxDepth : pp.maxDepth;       // MISPT finishes every path at depth maxDepth-1
 
+  // stage timing: one {start, stop} event pair per launch, summed per kernel class after the final synchronise (feeds MRaysStat /
+  // hc_stats and the roofline of bench.py).  Events on the launching stream cost ~1 us each, i.e. well below 1 % of a pass.
+  size_t evUsed = 0;
+  p->evClass.clear();
+  auto stageBegin = [&](int cls) -> int
+  {
+    if (evUsed + 2 > p->evPool.size()) { p->evPool.resize(evUsed + 2, nullptr); for (size_t k = evUsed; k < evUsed + 2; k++) if (cudaEventCreate(&p->evPool[k]) != cudaSuccess) return HC_E_NOMEM; }
+    p->evClass.push_back(cls);
+    return int(cudaEventRecord(p->evPool[evUsed], ctx->stream));
+  };
+  auto stageEnd = [&]() -> int { const int rc = int(cudaEventRecord(p->evPool[evUsed + 1], ctx->stream)); evUsed += 2; return rc; };
+#define HC_STAGE(cls, launch) { if ((rc = stageBegin(cls))) return rc; launch; if ((rc = stageEnd())) return rc; }
+
   for (int pass = 0; pass < passes; pass++)
   {
     pp.qmcPass = ctx->passCounter;
     HC_CUDA(cudaMemsetAsync(counts, 0, 256*sizeof(int), ctx->stream));
     HC_CUDA(cudaEventRecord(ctx->evStage[0], ctx->stream));
     HcPathState st0 = StateOf(p, 0, qmc);
-    k_pt_generate<<<(n + 255)/256, 256, 0, ctx->stream>>>(cam, pp, n, (const int*)p->owned.ptr, (uint2*)ctx->pixelRng.ptr, rmQMC, qtab, st0, counts);
+    HC_STAGE(3, (k_pt_generate<<<(n + 255)/256, 256, 0, ctx->stream>>>(cam, pp, n, (const int*)p->owned.ptr, (uint2*)ctx->pixelRng.ptr, rmQMC, qtab, st0, counts)));
     HC_CUDA(cudaGetLastError());
     ctx->stats.kernelLaunches++; ctx->stats.paths += (uint64_t)n;
     int cur = 0;
@@ -539,11 +573,11 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
     {
       HcPathState in = StateOf(p, cur, qmc), out = StateOf(p, 1 - cur, qmc);
       pp.depth = depth; pp.isLast = (depth == nBounces - 1) ? 1 : 0;
-      if ((rc = hc_launch_trace_counted(ctx, false, in.rpos, in.rdir, n, counts + depth, (HcHit*)p->hits.ptr, nullptr))) return rc;
+      HC_STAGE(0, if ((rc = hc_launch_trace_counted(ctx, false, in.rpos, in.rdir, n, counts + depth, (HcHit*)p->hits.ptr, nullptr))) return rc);
       if (depth > 0 && integrator != HC_INTEGRATOR_PT)
-        if ((rc = hc_launch_trace_counted(ctx, true, in.spos, in.sdir, n, counts + depth, nullptr, (unsigned char*)p->vis.ptr))) return rc;
-      k_pt_shade<<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, ctx->stream>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
-                   (const HcHit*)p->hits.ptr, (const unsigned char*)p->vis.ptr, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr);
+        HC_STAGE(1, if ((rc = hc_launch_trace_counted(ctx, true, in.spos, in.sdir, n, counts + depth, nullptr, (unsigned char*)p->vis.ptr))) return rc);
+      HC_STAGE(2, (k_pt_shade<<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, ctx->stream>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
+                   (const HcHit*)p->hits.ptr, (const unsigned char*)p->vis.ptr, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr)));
       HC_CUDA(cudaGetLastError());
       ctx->stats.kernelLaunches++;
       cur = 1 - cur;
@@ -551,10 +585,27 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
     HC_CUDA(cudaEventRecord(ctx->evStage[1], ctx->stream));
     ctx->passCounter++;
     ctx->spp += qmc ? double(n)*ctx->worldSize/double(W*H) : 1.0;
+    if (pass + 1 < passes) { evUsed = 0; p->evClass.clear(); }      // keep only the last pass's pairs (the pool is reused)
   }
+#undef HC_STAGE
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0.0f; HC_CUDA(cudaEventElapsedTime(&ms, ctx->evStage[0], ctx->evStage[1]));
   ctx->lastTraceMs = ms;              // device time of the LAST pass
+  float cls[4] = { 0, 0, 0, 0 };
+  for (size_t k = 0; k < p->evClass.size(); k++)
+  {
+    float t = 0.0f; HC_CUDA(cudaEventElapsedTime(&t, p->evPool[2*k], p->evPool[2*k + 1]));
+    cls[p->evClass[k]] += t;
+  }
+  {
+    int live[256]; HC_CUDA(cudaMemcpy(live, counts, sizeof(live), cudaMemcpyDeviceToHost));     // live paths per bounce of the last pass
+    uint64_t closest = 0, shadow = 0;
+    for (int d = 0; d < nBounces && d < 255; d++) { closest += uint64_t(live[d]); if (d > 0 && integrator != HC_INTEGRATOR_PT) shadow += uint64_t(live[d]); }
+    ctx->stats.raysClosest += closest*uint64_t(passes); ctx->stats.raysShadow += shadow*uint64_t(passes);
+  }
+  // the per-class times are those of the last pass; scale to all passes of this call
+  ctx->stats.msClosest += cls[0]*float(passes); ctx->stats.msShadow += cls[1]*float(passes);
+  ctx->stats.msShade += cls[2]*float(passes); ctx->stats.msOther += cls[3]*float(passes);
   return HC_OK;
 }
 

@@ -111,3 +111,19 @@ def test_packed_fp32_is_not_contracted(built):
     assert lines, "expected FFMA2 (a - b as fma(b, -1, a)) in the traversal kernel"
     bad = [ln.strip() for ln in lines if ", -1, " not in ln]
     assert not bad, "contracted packed multiply-add found:\n" + "\n".join(bad[:5])
+
+
+def test_cpp_layer_library_loads_and_fails_loudly_without_device(built):
+    """The C++ drop-in (GPUCUDALayer : IHWLayer) is built where the reference headers exist; without a CUDA device CreateCudaImpl throws."""
+    from tests import layerapi
+    if not layerapi.CppLayer.available():
+        pytest.skip("hydracore_b200/cpp/_build/libhydra_cuda_layer.so not present")
+    lib = ct.CDLL(layerapi.LIB)
+    for name in ("hl_create", "hl_create_storage", "hl_storage_update", "hl_set_bvh", "hl_prepare", "hl_init_path_tracing", "hl_passes", "hl_get_hdr"):
+        assert hasattr(lib, name)
+    import hydracore_b200 as hc
+    n = ct.c_int(-1)
+    if hc.load().hc_device_count(ct.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(layerapi.LayerError, match="no CUDA device"):
+        layerapi.CppLayer(16, 16)
