@@ -499,3 +499,45 @@ def scene_c2(width=1920, height=1080):
     scn.add_instance(scn.add_mesh(grid_mesh(708, 707, size=60.0, amplitude=1.6, seed=1234)))
     scn.add_material(np.zeros(192, np.float32))
     return scn.build()
+
+
+def scene_c3(width=1920, height=1080, trace_depth=8):
+    """BASELINE config C3: the C2 1M-triangle terrain with materials by triangle block {Lambert 60 %, GGX gloss 0.7 20 %, glass IOR 1.5
+    10 %, Lambert+GGX fresnel blend 10 %}, two rectangular area lights (with their emissive quads), MISPT with trace_depth 8
+    (-> HRT_TRACE_DEPTH = 9; the oracle ignores diff_trace_depth)."""
+    from . import materials as M
+    scn = Scene(width, height, Camera(pos=(0.0, 9.0, 16.0), look_at=(0.0, 0.0, 1.0), fov=45.0))
+    scn.set_trace_depth(trace_depth, 3)
+    lam = scn.add_material(M.lambert((0.62, 0.58, 0.50)))
+    ggx = scn.add_material(M.ggx((0.85, 0.70, 0.35), 0.7))
+    gls = scn.add_material(M.glass((0.95, 0.98, 0.95), ior=1.5, gloss=1.0))
+    bld = scn.add_material(M.blend((0.8, 0.8, 0.8), M.ggx((0.9, 0.9, 0.9), 0.85), M.lambert((0.2, 0.35, 0.7)), fresnel=True, ior=1.5))
+    emi0 = scn.add_material(M.emissive((60.0, 54.0, 45.0), 0))
+    emi1 = scn.add_material(M.emissive((20.0, 30.0, 45.0), 1))
+    scn.add_instance(scn.add_mesh(grid_mesh(708, 707, size=60.0, amplitude=1.6, seed=1234,
+                                            mat_blocks=[(0.6, lam), (0.2, ggx), (0.1, gls), (0.1, bld)])))
+    l0 = scn.add_light(M.area_light((0.0, 14.0, 0.0), (6.0, 6.0), (60.0, 54.0, 45.0)))
+    scn.add_instance(scn.add_mesh(quad_mesh(6.0, 6.0, y=0.0, mat_id=emi0, flip=True)), translate(0.0, 14.0, 0.0), light_id=l0)
+    l1 = scn.add_light(M.area_light((-14.0, 9.0, 10.0), (3.0, 3.0), (20.0, 30.0, 45.0)))
+    scn.add_instance(scn.add_mesh(quad_mesh(3.0, 3.0, y=0.0, mat_id=emi1, flip=True)), translate(-14.0, 9.0, 10.0), light_id=l1)
+    return scn.build()
+
+
+def scene_c4(width=1920, height=1080, instances=200, grid=(224, 224), seed=99):
+    """BASELINE config C4: 20 M instanced triangles = `instances` rigid copies (random rotation about Y + translation, seed 99) of one
+    ~100k-triangle displaced patch (224 x 224 quads = 100,352 triangles), Lambert, one large area light."""
+    from . import materials as M
+    rng = np.random.RandomState(seed)
+    scn = Scene(width, height, Camera(pos=(0.0, 55.0, 95.0), look_at=(0.0, 0.0, 5.0), fov=45.0))
+    scn.set_trace_depth(5, 3)
+    lam = scn.add_material(M.lambert((0.7, 0.7, 0.7)))
+    emi = scn.add_material(M.emissive((40.0, 40.0, 40.0), 0))
+    patch = scn.add_mesh(grid_mesh(grid[0], grid[1], size=12.0, amplitude=0.9, seed=4321, mat_blocks=[(1.0, lam)]))
+    side = int(math.ceil(math.sqrt(instances)))
+    for k in range(instances):
+        gx, gz = k % side, k//side
+        t = translate((gx - 0.5*(side - 1))*11.0 + rng.uniform(-1, 1), rng.uniform(-1.5, 1.5), (gz - 0.5*(side - 1))*11.0 + rng.uniform(-1, 1))
+        scn.add_instance(patch, t @ rotate_y(rng.uniform(0, 2*math.pi)))
+    l0 = scn.add_light(M.area_light((0.0, 60.0, 0.0), (40.0, 40.0), (40.0, 40.0, 40.0)))
+    scn.add_instance(scn.add_mesh(quad_mesh(40.0, 40.0, y=0.0, mat_id=emi, flip=True)), translate(0.0, 60.0, 0.0), light_id=l0)
+    return scn.build()
