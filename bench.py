@@ -52,7 +52,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -238,12 +238,12 @@ def run_ours(args):
         lay.RaycastPass(light, hits_d.data_ptr(), vis_d.data_ptr(), HC_DEVICE)
         return lay.last_trace_ms()
 
+    sampler = ClockSampler(local)
+    sampler.start()                         # started before the warm-up: nvidia-smi needs ~0.1 s to come up, the timed region is shorter
     for _ in range(max(args.warmup, 3)):
         step_device()
     lay.ResetPerfCounters()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     ms = []
     for _ in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (outside the per-step CUDA events)
@@ -346,7 +346,9 @@ def run_ours(args):
         cpu, qlt = cpu_baseline(scn)
         try:
             json.dump({"quads_per_ray": qlt[0], "leaves_per_ray": qlt[1], "tris_per_ray": qlt[2],
-                       "formula": "B_ray = 32 + 4 + 16 + 128*Q + 16*L + 48*T (SURVEY.md 8d)"}, open(qlt_path, "w"), indent=1)
+                       "formula": "B_ray = 32 + 4 + 16 + 128*Q + 16*L + 48*T (SURVEY.md 8d)",
+                       "source": "oracle/hydra_oracle.cpp traversal counters on every 61st primary ray of the C2 frame (bench.py, N=1)"},
+                      open(qlt_path, "w"), indent=1)
         except OSError:
             pass
     else:
