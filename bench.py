@@ -41,7 +41,7 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms; only samples inside [t_load, t_end] (GPU under our load) are kept."""
 
     def __init__(self, gpu_index):
         self.path = tempfile.mktemp(suffix=".csv")
@@ -49,7 +49,7 @@ class ClockSampler:
         self.gpu = gpu_index
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
@@ -57,8 +57,9 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    def stop(self, t_load=None, t_end=None):
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -66,25 +67,25 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [nme for k, nme in enumerate(names) if f[4 + k].lower().startswith("active")]))
             except ValueError:
                 continue
-            for k, nme in enumerate(names):
-                if f[3 + k].lower().startswith("active"):
-                    reasons.add(nme)
         os.unlink(self.path)
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-            out["sm_max_mhz"] = float(max(mx))
-        out["reasons"] = sorted(reasons)
+        inside = [r for r in rows if (t_load is None or r[0] >= t_load) and (t_end is None or r[0] <= t_end + 0.02)]
+        use = inside if inside else rows
+        if use:
+            out["sm_mhz"] = float(np.median([r[1] for r in use]))
+            out["sm_max_mhz"] = float(max(r[2] for r in use))
+            out["reasons"] = sorted({x for r in use for x in r[3]})
+            out["samples"] = len(inside)
         return out
 
 
@@ -239,8 +240,13 @@ def run_ours(args):
         return lay.last_trace_ms()
 
     sampler = ClockSampler(local)
-    sampler.start()                         # started before the warm-up: nvidia-smi needs ~0.1 s to come up, the timed region is shorter
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
+        step_device()
+    # untimed pre-roll of the same step (>= 0.4 s): nvidia-smi needs ~0.1 s to come up and a 20-step timed region lasts only tens of ms;
+    # clock samples are kept from here to the end of the timed region, i.e. only while the GPU runs this workload
+    t_load = time.time()
+    while time.time() - t_load < 0.4:
         step_device()
     lay.ResetPerfCounters()
     barrier()
@@ -250,7 +256,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms.append(step_device())            # device time of the 4 kernels of this step, CUDA events on the launching stream
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_load, time.time())
     stats = lay.GetRaysStat()
     shadow_rays = int(vis_d.numel())        # one shadow ray slot per pixel (missed pixels carry t_far = 0 and are not traced)
     n_hit = int((hits_d.view(-1, 4)[:, 1] >= 0).sum().item())

@@ -43,10 +43,10 @@ void hc_buf_free(HcDevBuf& b) { if (b.ptr) cudaFree(b.ptr); b.ptr = nullptr; b.b
 // Between refills a lane runs the while-while loop of hc_trace.cuh: descend through interior quads until a leaf is reached, then
 // intersect (or enter the instance); the loop is left early once so few lanes are still busy that a refill pays off.
 // rpos/rdir are float4 streams with element stride `stride` (2 = interleaved {pos,dir} records, 1 = separate arrays).
-template<bool ANYHIT, int MINB>
-__global__ void __launch_bounds__(HC_TRACE_BLOCK, MINB)
+template<bool ANYHIT>
+__global__ void __launch_bounds__(HC_TRACE_BLOCK, 6)   // 80 registers -> 6 CTAs (24 warps) per SM; capping at 72 / 64 registers for 7 / 8 CTAs measured slower
 k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long nArg,
-        const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter, const int refillMin)
+        const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter, const int refillMin, const int tileW)
 {
   const long long n = nDev ? (long long)(*nDev) : nArg;      // the path tracer keeps its live-path count on the device
   uint2 stk[HC_STACK_CAP];                                    // {child word, entry distance}
@@ -72,9 +72,16 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
       base = __shfl_sync(FULL, base, leader);
       if (idle)
       {
-        const long long idx = (long long)base + __popc(idleMask & ltMask);
+        long long idx = (long long)base + __popc(idleMask & ltMask);
         if (idx < n)
         {
+          if (tileW > 0)
+          {
+            // the ray stream is a W x H image in row-major order: fetch it in 8 x 4 pixel blocks, so that a warp's 32 rays cover a
+            // compact screen patch (fewer distinct BVH nodes per warp, more uniform traversal lengths) instead of a 32 x 1 strip
+            const long long blk = idx >> 5; const int w = int(idx) & 31, bpr = tileW >> 3;
+            idx = ((blk/bpr)*4 + (w >> 3))*(long long)tileW + (blk % bpr)*8 + (w & 7);
+          }
           const float4 p = __ldg(rpos + idx*stride), dd = __ldg(rdir + idx*stride);
           rayIdx = idx; idle = false;
           TravStart(r, bvh, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
@@ -149,32 +156,23 @@ static __global__ void k_make_shadow_rays(const float4* __restrict__ rays, const
 }
 
 // ------------------------------------------------------------------------------------------------------------------ helpers
-static int g_traceMinB = 0;
-static int TraceMinB()
-{
-  if (g_traceMinB == 0) { const char* e = getenv("HC_TRACE_MINB"); g_traceMinB = e ? atoi(e) : 6; if (g_traceMinB < 6 || g_traceMinB > 8) g_traceMinB = 6; }
-  return g_traceMinB;
-}
 static int TraceGrid(hc_ctx* ctx)
 {
   if (ctx->traceGrid > 0) return ctx->traceGrid;
   int perSM = 0;
-  const int mb = TraceMinB();
-  if (mb == 8)      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace<false, 8>, HC_TRACE_BLOCK, 0);
-  else if (mb == 7) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace<false, 7>, HC_TRACE_BLOCK, 0);
-  else              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace<false, 6>, HC_TRACE_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace<false>, HC_TRACE_BLOCK, 0);
   if (perSM < 1) perSM = 1;
   ctx->traceGrid = ctx->smCount*perSM;           // a whole number of waves: persistent CTAs, all resident
   return ctx->traceGrid;
 }
 
 // launch K2 (closest) or K2s (any-hit) on device-resident streams; used by hc_trace_* and by the path tracer
-static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis);
+static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW = 0);
 int hc_launch_trace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, HcHit* hits, unsigned char* vis)
 { return LaunchTrace(ctx, anyHit, rpos, rdir, stride, n, nullptr, hits, vis); }
 int hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis)
 { return LaunchTrace(ctx, anyHit, rpos, rdir, 1, nUpper, nDev, hits, vis); }
-static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis)
+static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW)
 {
   if (n <= 0) return HC_OK;
   HC_REQUIRE(ctx->bvhNodes.ptr && ctx->bvhTris.ptr, HC_E_STATE, "hc_trace: no BVH uploaded (hc_set_bvh)");
@@ -185,11 +183,9 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   unsigned long long* counter = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
   HC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
   const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
-  const int mb = TraceMinB();
   static int rf = 0; if (rf == 0) { const char* e = getenv("HC_TRACE_REFILL"); rf = e ? atoi(e) : HC_REFILL_MIN; if (rf < 1 || rf > 32) rf = HC_REFILL_MIN; }
-#define HC_LAUNCH_TRACE(MB) { if (anyHit) k_trace<true, MB><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf); \
-                              else        k_trace<false, MB><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf); }
-  if (mb == 8) HC_LAUNCH_TRACE(8) else if (mb == 7) HC_LAUNCH_TRACE(7) else HC_LAUNCH_TRACE(6)
+  if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf, tileW);
+  else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, tileW);
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   if (!nDev) { if (anyHit) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n; }   // counted launches: hc_pt_pass reads the live counts back
@@ -550,12 +546,13 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
   k_make_eye_rays<<<grid, block, 0, ctx->stream>>>(cam, ctx->width, ctx->height, nullptr, rays);
   HC_CUDA(cudaGetLastError());
   HC_CUDA(cudaEventRecord(ctx->evStage[1], ctx->stream));
-  if ((rc = hc_launch_trace(ctx, false, rays, rays + 1, 2, n, hits, nullptr))) return rc;
+  const int tileW = (ctx->width % 8 == 0 && ctx->height % 4 == 0 && !getenv("HC_TRACE_LINEAR")) ? ctx->width : 0;   // 8 x 4 pixel blocks per warp
+  if ((rc = LaunchTrace(ctx, false, rays, rays + 1, 2, n, nullptr, hits, nullptr, tileW))) return rc;
   HC_CUDA(cudaEventRecord(ctx->evStage[2], ctx->stream));
   k_make_shadow_rays<<<grid, block, 0, ctx->stream>>>(rays, hits, n, make_float3(lightPos[0], lightPos[1], lightPos[2]), srays);
   HC_CUDA(cudaGetLastError());
   HC_CUDA(cudaEventRecord(ctx->evStage[3], ctx->stream));
-  if ((rc = hc_launch_trace(ctx, true, srays, srays + 1, 2, n, nullptr, vis))) return rc;
+  if ((rc = LaunchTrace(ctx, true, srays, srays + 1, 2, n, nullptr, nullptr, vis, tileW))) return rc;
   HC_CUDA(cudaEventRecord(ctx->evStage[4], ctx->stream));
   ctx->stats.kernelLaunches += 2;
   ctx->stats.paths += (uint64_t)n;

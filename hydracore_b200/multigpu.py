@@ -23,8 +23,11 @@ def owned_pixels(width, height, tile, rank, world):
         if t % world != rank:
             continue
         x0, y0 = (t % tx)*T, (t//tx)*T
-        yy, xx = np.mgrid[y0:min(height, y0 + T), x0:min(width, x0 + T)]
-        out.append((yy*width + xx).reshape(-1))
+        x1, y1 = min(width, x0 + T), min(height, y0 + T)
+        for by in range(y0, y1, 4):                 # 8 x 4 pixel blocks inside the tile (one warp = one compact screen patch)
+            for bx in range(x0, x1, 8):
+                yy, xx = np.mgrid[by:min(y1, by + 4), bx:min(x1, bx + 8)]
+                out.append((yy*width + xx).reshape(-1))
     return np.concatenate(out) if out else np.zeros(0, np.int64)
 
 
