@@ -53,6 +53,7 @@ SIGNATURES = {
     "hc_trace_last_ms": (_I, [_P, ct.POINTER(ct.c_float)]),
     "hc_pt_init": (_I, [_P, _I]),
     "hc_pt_set_tiles": (_I, [_P, _I, _I, _I]),
+    "hc_pt_set_material_sort": (_I, [_P, _I, _I]),
     "hc_pt_pass": (_I, [_P, _I, _I]),
     "hc_fb_clear": (_I, [_P]),
     "hc_fb_device_ptr": (_I, [_P, _PP, ct.POINTER(_I64)]),

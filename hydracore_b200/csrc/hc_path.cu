@@ -104,10 +104,11 @@ HC_DEV void FinishPath(float4* __restrict__ fb, uint2* __restrict__ pixelRng, in
 __global__ void __launch_bounds__(HC_SHADE_BLOCK)
 k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, int* __restrict__ nOut,
            const HcPathState in, HcPathState out, const HcHit* __restrict__ hits, const unsigned char* __restrict__ vis,
-           const unsigned* __restrict__ qmcTable, float4* __restrict__ fb, uint2* __restrict__ pixelRng)
+           const unsigned* __restrict__ qmcTable, float4* __restrict__ fb, uint2* __restrict__ pixelRng, const int* __restrict__ perm)
 {
-  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  const int tid = blockIdx.x*blockDim.x + threadIdx.x;
   const int n = *nIn;
+  const int i = (perm != nullptr && tid < n) ? perm[tid] : tid;       // material-sorted order (k_pt_sort_*), else queue order
   bool alive = false;
 
   // new state of a surviving path
@@ -116,7 +117,7 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
   float4 sPos = make_float4(0, 0, 0, 0), sDir = make_float4(0, 1, 0, 0), sExp = make_float4(0, 0, 0, 0);
   HcRng g; g.x = 0; g.y = 0;
 
-  if (i < n)
+  if (tid < n)
   {
     const float4 rp = in.rpos[i], rd = in.rdir[i], th = in.thr[i], ac = in.accum[i];
     const uint2 r2 = in.rng[i]; g.x = r2.x; g.y = r2.y;
@@ -258,6 +259,81 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------ K6b: material sort
+// Replaces the role of bitonic_sort_gpu (reference hydra_drv/bitonic_sort_gpu.cpp:90-158, shaders/sort.cl): the live-path queue is put
+// in MATERIAL order before shading, so that the lanes of a warp run the same BSDF code and touch the same material record.  Keys are
+// small integers (material id, or one extra bucket for "missed"), so this is a counting sort in three short launches — per-CTA
+// shared-memory histogram, one-CTA scan, warp-aggregated scatter of path indices — instead of O(N log^2 N) bitonic passes.  The order
+// inside a bucket is arbitrary: every path carries its own pixel and generator, so the image does not depend on it.
+#define HC_SORT_MAX_KEYS 2048
+#define HC_SORT_BLOCK    256
+
+HC_DEV int SortKeyOf(const HcScene& s, const HcHit& h, int numKeys)
+{
+  if (h.primId == -1 || !isfinite(h.t)) return numKeys - 1;                    // HitNone -> last bucket
+  const int meshOff = s.globals[s.geometryTableOffset + h.geomId];
+  const float4* mesh = s.geom + meshOff;
+  const int mIdxOff = reinterpret_cast<const int4*>(mesh)[2].x;                // PlainMesh::mIndicesOffset (cfetch.h:1038-1059)
+  const int matId = reinterpret_cast<const int*>(mesh + mIdxOff)[h.primId];
+  return min(max(matId, 0), numKeys - 2);
+}
+
+__global__ void __launch_bounds__(HC_SORT_BLOCK)
+k_pt_sort_count(const HcScene s, const int* __restrict__ nIn, const HcHit* __restrict__ hits, unsigned short* __restrict__ keys,
+                int* __restrict__ bucketCount, const int numKeys)
+{
+  extern __shared__ int sCount[];
+  for (int k = threadIdx.x; k < numKeys; k += blockDim.x) sCount[k] = 0;
+  __syncthreads();
+  const int n = *nIn;
+  for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x)
+  {
+    const int key = SortKeyOf(s, hits[i], numKeys);
+    keys[i] = (unsigned short)key;
+    atomicAdd(&sCount[key], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < numKeys; k += blockDim.x) if (sCount[k] != 0) atomicAdd(&bucketCount[k], sCount[k]);
+}
+
+__global__ void __launch_bounds__(1024)
+k_pt_sort_scan(int* __restrict__ bucketCount, int* __restrict__ bucketCursor, const int numKeys)
+{
+  // exclusive prefix sum of <= 2048 counters by one CTA (two per thread); the counters are cleared for the next bounce
+  __shared__ int sh[HC_SORT_MAX_KEYS];
+  const int t = threadIdx.x;
+  const int a = (2*t < numKeys) ? bucketCount[2*t] : 0, b = (2*t + 1 < numKeys) ? bucketCount[2*t + 1] : 0;
+  sh[t] = a + b;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1)
+  {
+    const int v = (t >= off) ? sh[t - off] : 0;
+    __syncthreads();
+    sh[t] += v;
+    __syncthreads();
+  }
+  const int excl = sh[t] - (a + b);
+  if (2*t < numKeys)     { bucketCursor[2*t] = excl;         bucketCount[2*t] = 0; }
+  if (2*t + 1 < numKeys) { bucketCursor[2*t + 1] = excl + a; bucketCount[2*t + 1] = 0; }
+}
+
+__global__ void __launch_bounds__(HC_SORT_BLOCK)
+k_pt_sort_scatter(const int* __restrict__ nIn, const unsigned short* __restrict__ keys, int* __restrict__ bucketCursor, int* __restrict__ perm)
+{
+  const int n = *nIn;
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int key = keys[i];
+  // lanes of the warp with the same key take consecutive slots of that bucket: one atomic per (warp, key)
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, key);
+  const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&bucketCursor[key], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  perm[base + __popc(peers & ((1u << lane) - 1u))] = i;
+}
+
 // K2 / K2s wrappers reading the ray count from device memory live in hc_api.cu (hc_launch_trace_counted)
 int hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis);
 
@@ -286,6 +362,7 @@ struct HcPathHost
 {
   HcDevBuf state[2][9];       // rpos rdir thr accum rng qpos spos sdir sexp
   HcDevBuf hits, vis, owned, pathCount, ldr;
+  HcDevBuf sortKeys, sortCount, sortCursor, sortPerm;   // material sort: u16 key per path, 2 x HC_SORT_MAX_KEYS counters, int index per path
   std::vector<unsigned char> materialsHost, globalsHost;
   int64_t capacity = 0;
   int nOwned = 0;
@@ -300,6 +377,7 @@ void hc_path_free(hc_ctx* ctx)
   if (!p) return;
   for (int b = 0; b < 2; b++) for (int k = 0; k < 9; k++) hc_buf_free(p->state[b][k]);
   hc_buf_free(p->hits); hc_buf_free(p->vis); hc_buf_free(p->owned); hc_buf_free(p->pathCount); hc_buf_free(p->ldr);
+  hc_buf_free(p->sortKeys); hc_buf_free(p->sortCount); hc_buf_free(p->sortCursor); hc_buf_free(p->sortPerm);
   for (cudaEvent_t e : p->evPool) cudaEventDestroy(e);
   delete p;
   ctx->pathHost = nullptr;
@@ -325,6 +403,14 @@ static int ReserveState(hc_ctx* ctx, int64_t n, bool qmc)
   if ((rc = hc_buf_reserve(ctx, p->hits, uint64_t(n)*16))) return rc;
   if ((rc = hc_buf_reserve(ctx, p->vis, uint64_t(n)))) return rc;
   if ((rc = hc_buf_reserve(ctx, p->pathCount, 256*sizeof(int)))) return rc;
+  if ((rc = hc_buf_reserve(ctx, p->sortKeys, uint64_t(n)*2))) return rc;
+  if ((rc = hc_buf_reserve(ctx, p->sortPerm, uint64_t(n)*4))) return rc;
+  if (!p->sortCount.ptr)
+  {
+    if ((rc = hc_buf_reserve(ctx, p->sortCount, HC_SORT_MAX_KEYS*sizeof(int)))) return rc;
+    if ((rc = hc_buf_reserve(ctx, p->sortCursor, HC_SORT_MAX_KEYS*sizeof(int)))) return rc;
+    HC_CUDA(cudaMemsetAsync(p->sortCount.ptr, 0, HC_SORT_MAX_KEYS*sizeof(int), ctx->stream));
+  }
   p->capacity = n;
   return HC_OK;
 }
@@ -549,6 +635,15 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   const int* rmQMC = (const int*)ctx->globals.ptr + HC_EG_rmQMC/4;
   const unsigned* qtab = (const unsigned*)ctx->qmcTable.ptr;
   const int nBounces = (integrator == HC_INTEGRATOR_PT) ? pp.maxDepth : pp.maxDepth;       // MISPT finishes every path at depth maxDepth-1
+  // material sort: one bucket per entry of the materials table + one for rays that missed; off when the table is too large for one CTA scan
+  int sortKeys = 0;
+  if (ctx->materialSort != 0)
+  {
+    int matTab; memcpy(&matTab, ctx->globalsHead.data() + HC_EG_materialsTableSize, 4);
+    // measured on B200 (scripts/gpu_sort_ab.py): C3 (6 materials) 7.66 -> 7.26 ms per 1080p pass, shade 2.02 -> 1.41 ms, sort 0.29 ms;
+    // C4 (one surface material + the light's) 6.54 -> 6.59 ms.  Hence: only when there are at least three materials to tell apart.
+    if (matTab >= 3 && matTab + 1 <= HC_SORT_MAX_KEYS) sortKeys = matTab + 1;
+  }
 
   // stage timing: one {start, stop} event pair per launch, summed per kernel class after the final synchronise (feeds MRaysStat /
   // hc_stats and the roofline of bench.py).  Events on the launching stream cost ~1 us each, i.e. well below 1 % of a pass.
@@ -580,8 +675,24 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
       HC_STAGE(0, if ((rc = hc_launch_trace_counted(ctx, false, in.rpos, in.rdir, n, counts + depth, (HcHit*)p->hits.ptr, nullptr))) return rc);
       if (depth > 0 && integrator != HC_INTEGRATOR_PT)
         HC_STAGE(1, if ((rc = hc_launch_trace_counted(ctx, true, in.spos, in.sdir, n, counts + depth, nullptr, (unsigned char*)p->vis.ptr))) return rc);
+      const int* perm = nullptr;
+      if (sortKeys > 0 && depth >= ctx->sortFromBounce)
+      {
+        // material sort of the live-path queue (skipped while the queue is still in screen order and therefore coherent)
+        const int sortGrid = std::min((n + HC_SORT_BLOCK - 1)/HC_SORT_BLOCK, ctx->smCount*8);
+        if ((rc = stageBegin(3))) return rc;
+        k_pt_sort_count<<<sortGrid, HC_SORT_BLOCK, sortKeys*sizeof(int), ctx->stream>>>(scn, counts + depth, (const HcHit*)p->hits.ptr,
+                          (unsigned short*)p->sortKeys.ptr, (int*)p->sortCount.ptr, sortKeys);
+        k_pt_sort_scan<<<1, 1024, 0, ctx->stream>>>((int*)p->sortCount.ptr, (int*)p->sortCursor.ptr, sortKeys);
+        k_pt_sort_scatter<<<(n + HC_SORT_BLOCK - 1)/HC_SORT_BLOCK, HC_SORT_BLOCK, 0, ctx->stream>>>(counts + depth, (const unsigned short*)p->sortKeys.ptr,
+                            (int*)p->sortCursor.ptr, (int*)p->sortPerm.ptr);
+        if ((rc = stageEnd())) return rc;
+        HC_CUDA(cudaGetLastError());
+        ctx->stats.kernelLaunches += 3;
+        perm = (const int*)p->sortPerm.ptr;
+      }
       HC_STAGE(2, (k_pt_shade<<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, ctx->stream>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
-                   (const HcHit*)p->hits.ptr, (const unsigned char*)p->vis.ptr, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr)));
+                   (const HcHit*)p->hits.ptr, (const unsigned char*)p->vis.ptr, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
       HC_CUDA(cudaGetLastError());
       ctx->stats.kernelLaunches++;
       cur = 1 - cur;
@@ -658,6 +769,13 @@ int hc_fb_read_ldr(hc_ctx* ctx, uint32_t* outRGBA8, int width, int height)
   ctx->stats.kernelLaunches++;
   HC_CUDA(cudaMemcpyAsync(outRGBA8, p->ldr.ptr, uint64_t(n)*4, cudaMemcpyDeviceToHost, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HC_OK;
+}
+
+int hc_pt_set_material_sort(hc_ctx* ctx, int enable, int fromBounce)
+{
+  if (!ctx || fromBounce < 0) return HC_E_ARG;
+  ctx->materialSort = enable ? 1 : 0; ctx->sortFromBounce = fromBounce;
   return HC_OK;
 }
 

@@ -193,6 +193,9 @@ class CudaLayer:
     def SetTiles(self, tile, rank, world):
         check(self._L.hc_pt_set_tiles(self._c, int(tile), int(rank), int(world)), "hc_pt_set_tiles")
 
+    def SetMaterialSort(self, enable=True, from_bounce=1):
+        check(self._L.hc_pt_set_material_sort(self._c, 1 if enable else 0, int(from_bounce)), "hc_pt_set_material_sort")
+
     def TracingPass(self, integrator=INTEGRATOR_MISPT, passes=1):
         """BeginTracingPass + EndTracingPass, `passes` times."""
         check(self._L.hc_pt_pass(self._c, int(integrator), int(passes)), "hc_pt_pass")
