@@ -298,48 +298,56 @@ def run_ours(args):
     # parity guard: the host copy must agree with the device-resident result
     assert torch.equal(hits_h, hits_d.cpu()) and torch.equal(vis_h, vis_d.cpu())
 
-    # ---- C3 (reported next to the headline): MISPT, 8 bounces, mixed materials + 2 area lights on the same 1M-triangle terrain,
-    # image plane in interleaved 32x32 tiles across the ranks, HDR sums combined by one NCCL reduce.  Strong scaling of one frame.
-    c3 = None
+    # ---- C3 / C4 (reported next to the headline): MISPT on the 1M-triangle terrain with mixed materials + 2 area lights, and on the
+    # 20M-triangle instanced scene (fully incoherent diffuse secondary rays, compaction + material sort in the loop).  Image plane in
+    # interleaved 32x32 tiles across the ranks, HDR sums combined by one NCCL reduce: strong scaling of one frame.
+    extras = {}
     if not args.no_c3:
         from hydracore_b200 import multigpu as MG
         lay.close()
-        scn3 = S.scene_c3(WIDTH, HEIGHT)
-        lay = hc.CudaLayer(device=local)
-        lay.LoadScene(scn3)
-        lay.SetTiles(32, rank, world)
-        lay.InitPathTracing(777)
-        lay.TracingPass(2, 2)                      # warm-up passes (INTEGRATOR_MISPT = 2)
-        lay.ResetPerfCounters()
-        barrier()
-        passes = 4
-        t0 = time.perf_counter()
-        lay.TracingPass(2, passes)
-        barrier()
-        t_pass = time.perf_counter() - t0
-        st3 = lay.GetRaysStat()
-        ev_ms = st3["msClosest"] + st3["msShadow"] + st3["msShade"] + st3["msOther"]
-        t0 = time.perf_counter()
-        fb = MG.reduce_framebuffer(lay, dist, dev, dst=0)
-        t_red = time.perf_counter() - t0
-        vals = torch.tensor([t_pass, ev_ms, t_red, float(st3["paths"]), float(st3["raysClosest"]), float(st3["raysShadow"]),
-                             st3["msClosest"], st3["msShadow"], st3["msShade"]], device=dev, dtype=torch.float64)
-        mx, sm = vals.clone(), vals.clone()
-        if dist is not None:
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        mx, sm = mx.tolist(), sm.tolist()
-        mean_img = float((fb.view(-1, 4)[:, :3].sum()/(WIDTH*HEIGHT*3*(passes + 2))).item()) if rank == 0 else 0.0
-        c3 = {"workload": "C3: MISPT trace_depth 8, Lambert/GGX/glass/blend + 2 area lights, 1,001,116 triangles, 1080p, 32x32 interleaved tiles",
-              "passes": passes, "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": mx[1]/passes,
-              "paths_per_s": sm[3]/mx[0], "mrays_per_s": (sm[4] + sm[5])/mx[0]/1e6,
-              "rays_closest_per_pass": sm[4]/passes, "rays_shadow_per_pass": sm[5]/passes,
-              "stage_ms_per_pass_max": {"closest": mx[6]/passes, "shadow": mx[7]/passes, "shade": mx[8]/passes},
-              "reduce_ms": 1e3*mx[2], "reduce_bytes": WIDTH*HEIGHT*16 if world > 1 else 0, "mean_radiance": mean_img,
-              "scaling": "strong (one frame split over the ranks)"}
+        for key, label, build in (("c3", "C3: MISPT trace_depth 8, Lambert/GGX/glass/blend + 2 area lights, 1,001,116 triangles, 1080p, 32x32 interleaved tiles",
+                                   lambda: S.scene_c3(WIDTH, HEIGHT)),
+                                  ("c4", "C4: MISPT trace_depth 5 on 200 instances x 100,352 triangles = 20,070,400 instanced triangles, Lambert, 1080p, 32x32 interleaved tiles",
+                                   lambda: S.scene_c4(WIDTH, HEIGHT))):
+            scn3 = build()
+            lay = hc.CudaLayer(device=local)
+            lay.LoadScene(scn3)
+            lay.SetTiles(32, rank, world)
+            lay.InitPathTracing(777)
+            lay.TracingPass(2, 2)                      # warm-up passes (INTEGRATOR_MISPT = 2)
+            lay.ResetPerfCounters()
+            barrier()
+            passes = 4
+            t0 = time.perf_counter()
+            lay.TracingPass(2, passes)
+            barrier()
+            t_pass = time.perf_counter() - t0
+            st3 = lay.GetRaysStat()
+            ev_ms = st3["msClosest"] + st3["msShadow"] + st3["msShade"] + st3["msOther"]
+            t0 = time.perf_counter()
+            fb = MG.reduce_framebuffer(lay, dist, dev, dst=0)
+            t_red = time.perf_counter() - t0
+            vals = torch.tensor([t_pass, ev_ms, t_red, float(st3["paths"]), float(st3["raysClosest"]), float(st3["raysShadow"]),
+                                 st3["msClosest"], st3["msShadow"], st3["msShade"], st3["msOther"]], device=dev, dtype=torch.float64)
+            mx, sm = vals.clone(), vals.clone()
+            if dist is not None:
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            mx, sm = mx.tolist(), sm.tolist()
+            mean_img = float((fb.view(-1, 4)[:, :3].sum()/(WIDTH*HEIGHT*3*(passes + 2))).item()) if rank == 0 else 0.0
+            extras[key] = {"workload": label, "passes": passes, "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": mx[1]/passes,
+                           "paths_per_s": sm[3]/mx[0], "mrays_per_s": (sm[4] + sm[5])/mx[0]/1e6,
+                           "mrays_closest_kernel": sm[4]/max(mx[6], 1e-9)/1e3, "mrays_shadow_kernel": sm[5]/max(mx[7], 1e-9)/1e3,
+                           "rays_closest_per_pass": sm[4]/passes, "rays_shadow_per_pass": sm[5]/passes,
+                           "stage_ms_per_pass_max": {"closest": mx[6]/passes, "shadow": mx[7]/passes, "shade": mx[8]/passes, "raygen_sort": mx[9]/passes},
+                           "reduce_ms": 1e3*mx[2], "reduce_bytes": WIDTH*HEIGHT*16 if world > 1 else 0, "mean_radiance": mean_img,
+                           "scaling": "strong (one frame split over the ranks)"}
+            lay.close()
+        lay = None
 
     if rank != 0:
-        lay.close()
+        if lay is not None:
+            lay.close()
         if dist is not None:
             dist.destroy_process_group()
         return 0
@@ -383,10 +391,10 @@ def run_ours(args):
                          "note": "algorithmic bytes are BVH/triangle fetches that the 126 MB L2 serves; HBM peak is the stated denominator"}}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    if c3 is not None:
-        line["c3"] = c3
+    line.update(extras)
     print(json.dumps(line))
-    lay.close()
+    if lay is not None:
+        lay.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -399,7 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-c3", action="store_true", help="skip the C3 (MISPT path tracing) section")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C3 / C4 (MISPT path tracing) sections")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

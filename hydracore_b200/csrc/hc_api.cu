@@ -320,6 +320,8 @@ int hc_ctx_create(int device, hc_ctx** out)
   HC_CUDA(cudaGetDeviceProperties(&c->prop, device));
   c->smCount = c->prop.multiProcessorCount;
   HC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  HC_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+  HC_CUDA(cudaEventCreateWithFlags(&c->evCopy, cudaEventDisableTiming));
   HC_CUDA(cudaEventCreate(&c->ev0)); HC_CUDA(cudaEventCreate(&c->ev1));
   for (int i = 0; i < 5; i++) HC_CUDA(cudaEventCreate(&c->evStage[i]));
   int rc = hc_buf_reserve(c, c->counters, 64*sizeof(unsigned long long));
@@ -343,6 +345,7 @@ void hc_ctx_destroy(hc_ctx* c)
   for (int i = 0; i < 5; i++) cudaEventDestroy(c->evStage[i]);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->copyStream); cudaEventDestroy(c->evCopy);
   delete c;
 }
 
@@ -549,6 +552,13 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
   const int tileW = (ctx->width % 8 == 0 && ctx->height % 4 == 0 && !getenv("HC_TRACE_LINEAR")) ? ctx->width : 0;   // 8 x 4 pixel blocks per warp
   if ((rc = LaunchTrace(ctx, false, rays, rays + 1, 2, n, nullptr, hits, nullptr, tileW))) return rc;
   HC_CUDA(cudaEventRecord(ctx->evStage[2], ctx->stream));
+  if (hitsOutOrNull)
+  {
+    // the hit records are final once K2 is done: read them back on the copy stream while the shadow rays are built and traced
+    HC_CUDA(cudaEventRecord(ctx->evCopy, ctx->stream));
+    HC_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evCopy, 0));
+    HC_CUDA(cudaMemcpyAsync(hitsOutOrNull, hits, uint64_t(n)*16, space == HC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->copyStream));
+  }
   k_make_shadow_rays<<<grid, block, 0, ctx->stream>>>(rays, hits, n, make_float3(lightPos[0], lightPos[1], lightPos[2]), srays);
   HC_CUDA(cudaGetLastError());
   HC_CUDA(cudaEventRecord(ctx->evStage[3], ctx->stream));
@@ -556,9 +566,9 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
   HC_CUDA(cudaEventRecord(ctx->evStage[4], ctx->stream));
   ctx->stats.kernelLaunches += 2;
   ctx->stats.paths += (uint64_t)n;
-  if (hitsOutOrNull) HC_CUDA(cudaMemcpyAsync(hitsOutOrNull, hits, uint64_t(n)*16, space == HC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
   if (visibleOutOrNull) HC_CUDA(cudaMemcpyAsync(visibleOutOrNull, vis, uint64_t(n), space == HC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (hitsOutOrNull) HC_CUDA(cudaStreamSynchronize(ctx->copyStream));
   float ms[4];
   for (int i = 0; i < 4; i++) HC_CUDA(cudaEventElapsedTime(&ms[i], ctx->evStage[i], ctx->evStage[i + 1]));
   ctx->stats.msOther += ms[0] + ms[2]; ctx->stats.msClosest += ms[1]; ctx->stats.msShadow += ms[3];

@@ -25,6 +25,8 @@ struct hc_ctx
 {
   int          device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copyStream = nullptr;       // read-backs that overlap the next kernel (hc_raycast_pass)
+  cudaEvent_t  evCopy = nullptr;
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
   cudaDeviceProp prop{};
   int          smCount = 0;
