@@ -246,7 +246,7 @@ def run_ours(args):
     # untimed pre-roll of the same step (>= 0.4 s): nvidia-smi needs ~0.1 s to come up and a 20-step timed region lasts only tens of ms;
     # clock samples are kept from here to the end of the timed region, i.e. only while the GPU runs this workload
     t_load = time.time()
-    while time.time() - t_load < 0.4:
+    while time.time() - t_load < (0.0 if args.profile else 0.4):
         step_device()
     lay.ResetPerfCounters()
     barrier()
@@ -356,7 +356,7 @@ def run_ours(args):
     peak, peak_src = _peaks()
     qlt_path = os.path.join(ROOT, "profiles", "c2_algorithmic_bytes.json")
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.profile:
         cpu, qlt = cpu_baseline(scn)
         try:
             json.dump({"quads_per_ray": qlt[0], "leaves_per_ray": qlt[1], "tris_per_ray": qlt[2],
@@ -407,6 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="profiling run (ncu): no clock pre-roll, no CPU baseline")
     ap.add_argument("--no-c3", action="store_true", help="skip the C3 / C4 (MISPT path tracing) sections")
     args = ap.parse_args()
     if args.impl == "reference":

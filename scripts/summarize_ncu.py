@@ -19,8 +19,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
-out = [f"# ncu --set full summary, {label} (bench.py --steps 2 --warmup 3 --no-cpu-baseline, C2 workload, 1 x B200)\n",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "lts__t_bytes.sum.per_second"]
+out = [f"# ncu --set full summary, {label} (bench.py --steps 2 --warmup 3 --profile: C2 ray casting, then C3 / C4 MISPT passes; 1 x B200)\n",
        "Per-launch values; cold-cache, serialised replay: compare shares, not absolutes.\n"]
 traffic = {}
 for r in rows[2:]:
@@ -35,6 +37,22 @@ for r in rows[2:]:
         traffic["k_trace_closest_ms_under_ncu"] = float(d["gpu__time_duration.sum"])
     if "k_trace<1>" in name or "k_trace<(bool)1>" in name:
         traffic["k_trace_shadow_dram_bytes_per_launch"] = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"]))*1e6
+shade = os.path.join(ROOT, "gpurun_out", f"{tag}_shade.ncu-rep")
+if os.path.exists(shade):
+    raw2 = subprocess.run(["ncu", "-i", shade, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows2 = list(csv.reader(io.StringIO(raw2)))
+    h2, u2 = rows2[0], rows2[1]
+    for r in rows2[2:]:
+        d = dict(zip(h2, r))
+        out.append(f"\n## {d['Kernel Name'].split('(')[0]} (C3 pass, one bounce)\n\n| metric | value | unit |\n|---|---|---|")
+        for k in KEYS:
+            if k in d:
+                out.append(f"| {k} | {d[k]} | {u2[h2.index(k)]} |")
+for rep_name, kre in ((f"{tag}_prof.ncu-rep", "k_trace"), (f"{tag}_shade.ncu-rep", "k_pt_shade")):
+    rp = os.path.join(ROOT, "gpurun_out", rep_name)
+    if os.path.exists(rp):
+        blk = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_blocks.py"), rp, kre, "1.5"], stdout=subprocess.PIPE, text=True).stdout
+        out.append(f"\n## per-basic-block view of {kre} (scripts/ncu_blocks.py: share of issued warp-instructions, average active threads, stall samples)\n\n```\n{blk}```")
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 open(os.path.join(ROOT, "profiles", f"{label}_ncu_full_summary.md"), "w").write("\n".join(out) + "\n")
 traffic["source"] = f"profiles/{label}_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
