@@ -337,9 +337,9 @@ def run_ours(args):
             mean_img = float((fb.view(-1, 4)[:, :3].sum()/(WIDTH*HEIGHT*3*(passes + 2))).item()) if rank == 0 else 0.0
             extras[key] = {"workload": label, "passes": passes, "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": mx[1]/passes,
                            "paths_per_s": sm[3]/mx[0], "mrays_per_s": (sm[4] + sm[5])/mx[0]/1e6,
-                           "mrays_closest_kernel": sm[4]/max(mx[6], 1e-9)/1e3, "mrays_shadow_kernel": sm[5]/max(mx[7], 1e-9)/1e3,
                            "rays_closest_per_pass": sm[4]/passes, "rays_shadow_per_pass": sm[5]/passes,
-                           "stage_ms_per_pass_max": {"closest": mx[6]/passes, "shadow": mx[7]/passes, "shade": mx[8]/passes, "raygen_sort": mx[9]/passes},
+                           "stage_ms_per_pass_max": {"closest": mx[6]/passes, "shadow_added": mx[7]/passes, "shade": mx[8]/passes, "raygen_sort": mx[9]/passes},
+                           "stage_note": "closest-hit and any-hit launches of a bounce overlap on two streams: shadow_added = time from the end of the closest-hit launch to the join",
                            "reduce_ms": 1e3*mx[2], "reduce_bytes": WIDTH*HEIGHT*16 if world > 1 else 0, "mean_radiance": mean_img,
                            "scaling": "strong (one frame split over the ranks)"}
             lay.close()

@@ -167,25 +167,26 @@ static int TraceGrid(hc_ctx* ctx)
 }
 
 // launch K2 (closest) or K2s (any-hit) on device-resident streams; used by hc_trace_* and by the path tracer
-static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW = 0);
+static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW = 0, cudaStream_t stream = nullptr);
 int hc_launch_trace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, HcHit* hits, unsigned char* vis)
 { return LaunchTrace(ctx, anyHit, rpos, rdir, stride, n, nullptr, hits, vis); }
-int hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis)
-{ return LaunchTrace(ctx, anyHit, rpos, rdir, 1, nUpper, nDev, hits, vis); }
-static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW)
+int hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis, cudaStream_t stream)
+{ return LaunchTrace(ctx, anyHit, rpos, rdir, 1, nUpper, nDev, hits, vis, 0, stream); }
+static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW, cudaStream_t stream)
 {
   if (n <= 0) return HC_OK;
+  if (!stream) stream = ctx->stream;
   HC_REQUIRE(ctx->bvhNodes.ptr && ctx->bvhTris.ptr, HC_E_STATE, "hc_trace: no BVH uploaded (hc_set_bvh)");
   HC_REQUIRE(ctx->haveInst != 0, HC_E_STATE, "hc_trace: only the two-level (instanced) layout is supported");
   HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr;
   // one persistent-thread ray counter per launch in flight: rotate through the counter block so that back-to-back launches never share one
   ctx->traceCounterSlot = (ctx->traceCounterSlot + 1) % 32;
   unsigned long long* counter = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
-  HC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+  HC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
   const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
   static int rf = 0; if (rf == 0) { const char* e = getenv("HC_TRACE_REFILL"); rf = e ? atoi(e) : HC_REFILL_MIN; if (rf < 1 || rf > 32) rf = HC_REFILL_MIN; }
-  if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf, tileW);
-  else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, ctx->stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, tileW);
+  if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf, tileW);
+  else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, tileW);
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   if (!nDev) { if (anyHit) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n; }   // counted launches: hc_pt_pass reads the live counts back
@@ -322,6 +323,7 @@ int hc_ctx_create(int device, hc_ctx** out)
   HC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   HC_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
   HC_CUDA(cudaEventCreateWithFlags(&c->evCopy, cudaEventDisableTiming));
+  HC_CUDA(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming)); HC_CUDA(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
   HC_CUDA(cudaEventCreate(&c->ev0)); HC_CUDA(cudaEventCreate(&c->ev1));
   for (int i = 0; i < 5; i++) HC_CUDA(cudaEventCreate(&c->evStage[i]));
   int rc = hc_buf_reserve(c, c->counters, 64*sizeof(unsigned long long));
@@ -345,7 +347,7 @@ void hc_ctx_destroy(hc_ctx* c)
   for (int i = 0; i < 5; i++) cudaEventDestroy(c->evStage[i]);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
-  cudaStreamDestroy(c->copyStream); cudaEventDestroy(c->evCopy);
+  cudaStreamDestroy(c->copyStream); cudaEventDestroy(c->evCopy); cudaEventDestroy(c->evFork); cudaEventDestroy(c->evJoin);
   delete c;
 }
 

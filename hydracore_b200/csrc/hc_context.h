@@ -27,6 +27,7 @@ struct hc_ctx
   cudaStream_t stream = nullptr;
   cudaStream_t copyStream = nullptr;       // read-backs that overlap the next kernel (hc_raycast_pass)
   cudaEvent_t  evCopy = nullptr;
+  cudaEvent_t  evFork = nullptr, evJoin = nullptr;   // closest-hit and shadow traversal of one bounce run on two streams (hc_pt_pass)
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
   cudaDeviceProp prop{};
   int          smCount = 0;
@@ -69,5 +70,5 @@ int hc_buf_reserve(hc_ctx* ctx, HcDevBuf& b, uint64_t bytes);   // grow-only
 void hc_buf_free(HcDevBuf& b);
 
 void hc_path_free(hc_ctx* ctx);   // hc_path.cu
-int  hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis);
+int  hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis, cudaStream_t stream = nullptr);
 int  hc_launch_trace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, HcHit* hits, unsigned char* vis);   // hc_api.cu

@@ -335,7 +335,6 @@ k_pt_sort_scatter(const int* __restrict__ nIn, const unsigned short* __restrict_
 }
 
 // K2 / K2s wrappers reading the ray count from device memory live in hc_api.cu (hc_launch_trace_counted)
-int hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis);
 
 // init pixel generators: InitRandomGen (shaders/trace.cl:6-13) with tid = pixel index
 __global__ void k_init_rng(uint2* __restrict__ gen, int n, int seed)
@@ -672,9 +671,25 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
     {
       HcPathState in = StateOf(p, cur, qmc), out = StateOf(p, 1 - cur, qmc);
       pp.depth = depth; pp.isLast = (depth == nBounces - 1) ? 1 : 0;
+      // the shadow rays of the previous bounce and the closest-hit rays of this one are independent: two streams, so that the tail of
+      // one persistent launch (last warps finishing their rays) is filled by the head of the other; joined before sort / shade
+      const bool haveShadow = (depth > 0 && integrator != HC_INTEGRATOR_PT);
+      if (haveShadow)
+      {
+        HC_CUDA(cudaEventRecord(ctx->evFork, ctx->stream));
+        HC_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evFork, 0));
+      }
       HC_STAGE(0, if ((rc = hc_launch_trace_counted(ctx, false, in.rpos, in.rdir, n, counts + depth, (HcHit*)p->hits.ptr, nullptr))) return rc);
-      if (depth > 0 && integrator != HC_INTEGRATOR_PT)
-        HC_STAGE(1, if ((rc = hc_launch_trace_counted(ctx, true, in.spos, in.sdir, n, counts + depth, nullptr, (unsigned char*)p->vis.ptr))) return rc);
+      if (haveShadow)
+      {
+        // timing: the "shadow" stage is what the any-hit launch ADDS after the closest-hit launch has finished (both measured on the
+        // main stream), so that the stage times still add up to the pass
+        if ((rc = stageBegin(1))) return rc;
+        if ((rc = hc_launch_trace_counted(ctx, true, in.spos, in.sdir, n, counts + depth, nullptr, (unsigned char*)p->vis.ptr, ctx->copyStream))) return rc;
+        HC_CUDA(cudaEventRecord(ctx->evJoin, ctx->copyStream));
+        HC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+        if ((rc = stageEnd())) return rc;
+      }
       const int* perm = nullptr;
       if (sortKeys > 0 && depth >= ctx->sortFromBounce)
       {
