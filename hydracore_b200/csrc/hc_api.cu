@@ -433,6 +433,24 @@ int hc_set_bvh(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const v
   return HC_OK;
 }
 
+int hc_bvh_device_layout(const void* nodes, int nodesNum, const void* trif4, int trif4Num, float* outNodes, float* outPairs,
+                         int64_t outPairsCapacityFloats, int64_t* outPairsFloats, int* outStackBound)
+{
+  if (!nodes || !trif4 || nodesNum < 8 || trif4Num < 4) return HC_E_ARG;
+  std::vector<float> devNodes, devPairs; int bound = 0;
+  const int rc = ConvertBvhForDevice((const unsigned char*)nodes, nodesNum, (const float*)trif4, trif4Num, devNodes, devPairs, &bound);
+  HC_REQUIRE(rc == HC_OK, rc, "hc_bvh_device_layout: tree references nodes or triangles out of range (or a leaf holds more than 128 triangles)");
+  if (outStackBound) *outStackBound = bound;
+  if (outPairsFloats) *outPairsFloats = (int64_t)devPairs.size();
+  if (outNodes) memcpy(outNodes, devNodes.data(), devNodes.size()*4);
+  if (outPairs)
+  {
+    HC_REQUIRE(outPairsCapacityFloats >= (int64_t)devPairs.size(), HC_E_RANGE, "hc_bvh_device_layout: outPairs too small");
+    memcpy(outPairs, devPairs.data(), devPairs.size()*4);
+  }
+  return HC_OK;
+}
+
 int hc_set_inst_matrices(hc_ctx* ctx, const float* invMatrices16, int n)
 {
   if (!ctx || !invMatrices16 || n <= 0) return HC_E_ARG;

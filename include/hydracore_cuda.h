@@ -71,6 +71,10 @@ int hc_storage_capacity(hc_ctx* ctx, int slot, uint64_t* outBytes);
 int hc_set_globals(hc_ctx* ctx, const void* blob, uint64_t bytes);           /* PrepareEngineGlobals/Tables upload, GPUOCLData.cpp:289-327 */
 int hc_set_bvh(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const void* trif4, int trif4Num, int haveInst);
                                                                               /* SetAllBVH4(ConvertionResult), GPUOCLData.cpp:88-160       */
+int hc_bvh_device_layout(const void* nodes, int nodesNum, const void* trif4, int trif4Num, float* outNodesOrNull, float* outPairsOrNull,
+                         int64_t outPairsCapacityFloats, int64_t* outPairsFloats, int* outStackBound);
+                                                                              /* host only, no device needed: the re-layout hc_set_bvh applies before the upload (SoA quads, triangle
+                                                                                 pair records) and the worst-case traversal stack; outNodes = nodesNum*8 floats */
 int hc_set_inst_matrices(hc_ctx* ctx, const float* invMatrices16, int n);    /* SetAllInstMatrices, IHWLayer.h:117                        */
 int hc_set_inst_light_ids(hc_ctx* ctx, const int32_t* lightInstId, int n);   /* SetAllInstLightInstId, IHWLayer.h:118                     */
 int hc_resize(hc_ctx* ctx, int width, int height);                           /* ResizeScreen, IHWLayer.h:147                              */
