@@ -305,21 +305,25 @@ def run_ours(args):
     if not args.no_c3:
         from hydracore_b200 import multigpu as MG
         lay.close()
-        for key, label, build in (("c3", "C3: MISPT trace_depth 8, Lambert/GGX/glass/blend + 2 area lights, 1,001,116 triangles, 1080p, 32x32 interleaved tiles",
+        for key, label, build in (("c1", "C1: hydra_app/tests/test_42 (25,612 triangles, Lambert / Phong blend / emissive, rect area light, DOF), unidirectional PT, 512x512",
+                                   lambda: __import__("hydracore_b200.hydra_scene", fromlist=["x"]).build_scene(
+                                       __import__("hydracore_b200.hydra_scene", fromlist=["x"]).load_fixture(os.path.join(ROOT, "tests", "golden", "test_42_scene.npz")), 512, 512)),
+                                  ("c3", "C3: MISPT trace_depth 8, Lambert/GGX/glass/blend + 2 area lights, 1,001,116 triangles, 1080p, 32x32 interleaved tiles",
                                    lambda: S.scene_c3(WIDTH, HEIGHT)),
                                   ("c4", "C4: MISPT trace_depth 5 on 200 instances x 100,352 triangles = 20,070,400 instanced triangles, Lambert, 1080p, 32x32 interleaved tiles",
                                    lambda: S.scene_c4(WIDTH, HEIGHT))):
             scn3 = build()
             lay = hc.CudaLayer(device=local)
             lay.LoadScene(scn3)
+            integ = 0 if key == "c1" else 2            # C1 is quoted on unidirectional PT (INTEGRATOR_PT = 0), C3 / C4 on MISPT (= 2)
             lay.SetTiles(32, rank, world)
             lay.InitPathTracing(777)
-            lay.TracingPass(2, 2)                      # warm-up passes (INTEGRATOR_MISPT = 2)
+            lay.TracingPass(integ, 2)                  # warm-up passes
             lay.ResetPerfCounters()
             barrier()
-            passes = 4
+            passes = 64 if key == "c1" else 4
             t0 = time.perf_counter()
-            lay.TracingPass(2, passes)
+            lay.TracingPass(integ, passes)
             barrier()
             t_pass = time.perf_counter() - t0
             st3 = lay.GetRaysStat()
@@ -334,14 +338,27 @@ def run_ours(args):
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX)
                 dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             mx, sm = mx.tolist(), sm.tolist()
-            mean_img = float((fb.view(-1, 4)[:, :3].sum()/(WIDTH*HEIGHT*3*(passes + 2))).item()) if rank == 0 else 0.0
+            mean_img = float((fb.view(-1, 4)[:, :3].sum()/(scn3.width*scn3.height*3*(passes + 2))).item()) if rank == 0 else 0.0
             extras[key] = {"workload": label, "passes": passes, "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": mx[1]/passes,
                            "paths_per_s": sm[3]/mx[0], "mrays_per_s": (sm[4] + sm[5])/mx[0]/1e6,
                            "rays_closest_per_pass": sm[4]/passes, "rays_shadow_per_pass": sm[5]/passes,
                            "stage_ms_per_pass_max": {"closest": mx[6]/passes, "shadow_added": mx[7]/passes, "shade": mx[8]/passes, "raygen_sort": mx[9]/passes},
                            "stage_note": "closest-hit and any-hit launches of a bounce overlap on two streams: shadow_added = time from the end of the closest-hit launch to the join",
-                           "reduce_ms": 1e3*mx[2], "reduce_bytes": WIDTH*HEIGHT*16 if world > 1 else 0, "mean_radiance": mean_img,
+                           "reduce_ms": 1e3*mx[2], "reduce_bytes": scn3.width*scn3.height*16 if world > 1 else 0, "mean_radiance": mean_img,
                            "scaling": "strong (one frame split over the ranks)"}
+            if key == "c1" and rank == 0 and world == 1 and not args.profile and not args.no_cpu_baseline:
+                # the reference's own CPU integrator (IntegratorStupidPT compiled in place, oracle/_ref) on the same scene, host cores
+                from tests import refapi
+                rf = refapi.Ref.try_load()
+                if rf is not None:
+                    rs = rf.scene(scn3)
+                    rs.render(0, 777, 1)
+                    t0 = time.perf_counter()
+                    _img, npass = rs.render(0, 777, 2)
+                    dtc = time.perf_counter() - t0
+                    rs.close()
+                    extras[key]["cpu_reference"] = {"paths_per_s": scn3.width*scn3.height*2/dtc, "cores": len(os.sched_getaffinity(0)), "kind": "reference",
+                                                    "sample": "2 passes of 512x512 by IntegratorStupidPT (oracle/_ref, OpenMP, BVH4InstTraverse instead of Embree)"}
             lay.close()
         lay = None
 
