@@ -22,6 +22,9 @@
 #include <string>
 
 #define HC_SHADE_BLOCK 128
+#ifndef HC_SHADE_MINB
+#define HC_SHADE_MINB 4
+#endif
 
 struct HcPathState          // one half of the double buffer
 {
@@ -101,7 +104,7 @@ HC_DEV void FinishPath(float4* __restrict__ fb, uint2* __restrict__ pixelRng, in
   pixelRng[rngSlot] = make_uint2(g.x, g.y);
 }
 
-__global__ void __launch_bounds__(HC_SHADE_BLOCK)
+__global__ void __launch_bounds__(HC_SHADE_BLOCK, HC_SHADE_MINB)
 k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, int* __restrict__ nOut,
            const HcPathState in, HcPathState out, const HcHit* __restrict__ hits, const unsigned char* __restrict__ vis,
            const unsigned* __restrict__ qmcTable, float4* __restrict__ fb, uint2* __restrict__ pixelRng, const int* __restrict__ perm)

@@ -150,9 +150,11 @@ HC_DEV void TravStart(HcRayTrav& r, const HcBvh& bvh, float3 o, float3 d, float 
 // one interior quad: slab-test four children (two per packed instruction), sort near to far, push three, descend into the nearest.
 // No capacity test on the pushes: hc_set_bvh rejects a tree whose worst-case stack exceeds HC_STACK_CAP (the reference instead
 // silently drops children once its 80-entry stack is full, ctrace.h:959-979 — a tree that deep is refused here).
-HC_DEV void TravQuad(HcRayTrav& r, const HcBvh& bvh, uint2* stk)
+// slab test of the four children of quad `node` for this lane's ray: entry keys (MAXFLOAT = not to be visited) and child words
+HC_DEV void QuadKeys(const HcRayTrav& r, const HcBvh& bvh, const unsigned node, float& t0, float& t1, float& t2, float& t3,
+                     unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3)
 {
-  const size_t qo = size_t(r.node)*128u;
+  const size_t qo = size_t(node)*128u;
   const char* ax = r.nearX + qo; const char* ay = r.nearY + qo; const char* az = r.nearZ + qo;
   const float4 NX = __ldg(reinterpret_cast<const float4*>(ax)), FX = __ldg(reinterpret_cast<const float4*>(size_t(ax) ^ 16u));
   const float4 NY = __ldg(reinterpret_cast<const float4*>(ay)), FY = __ldg(reinterpret_cast<const float4*>(size_t(ay) ^ 16u));
@@ -167,9 +169,15 @@ HC_DEV void TravQuad(HcRayTrav& r, const HcBvh& bvh, uint2* stk)
   upk2(mul2(iY, sub2(lo2(FY), oY)), fy0, fy1); upk2(mul2(iY, sub2(hi2(FY), oY)), fy2, fy3);
   upk2(mul2(iZ, sub2(lo2(NZ), oZ)), nz0, nz1); upk2(mul2(iZ, sub2(hi2(NZ), oZ)), nz2, nz3);
   upk2(mul2(iZ, sub2(lo2(FZ), oZ)), fz0, fz1); upk2(mul2(iZ, sub2(hi2(FZ), oZ)), fz2, fz3);
-  float t0 = ChildKey(nx0, ny0, nz0, fx0, fy0, fz0, r.t), t1 = ChildKey(nx1, ny1, nz1, fx1, fy1, fz1, r.t);
-  float t2 = ChildKey(nx2, ny2, nz2, fx2, fy2, fz2, r.t), t3 = ChildKey(nx3, ny3, nz3, fx3, fy3, fz3, r.t);
-  unsigned c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+  t0 = ChildKey(nx0, ny0, nz0, fx0, fy0, fz0, r.t); t1 = ChildKey(nx1, ny1, nz1, fx1, fy1, fz1, r.t);
+  t2 = ChildKey(nx2, ny2, nz2, fx2, fy2, fz2, r.t); t3 = ChildKey(nx3, ny3, nz3, fx3, fy3, fz3, r.t);
+  c0 = ch.x; c1 = ch.y; c2 = ch.z; c3 = ch.w;
+}
+
+HC_DEV void TravQuad(HcRayTrav& r, const HcBvh& bvh, uint2* stk)
+{
+  float t0, t1, t2, t3; unsigned c0, c1, c2, c3;
+  QuadKeys(r, bvh, r.node, t0, t1, t2, t3, c0, c1, c2, c3);
   HC_CSWAP(t0, c0, t1, c1); HC_CSWAP(t2, c2, t3, c3);        // the reference's network: (0,1)(2,3) (0,2)(1,3) (1,2), ctrace.h:896-957
   HC_CSWAP(t0, c0, t2, c2); HC_CSWAP(t1, c1, t3, c3);
   HC_CSWAP(t1, c1, t2, c2);
@@ -195,11 +203,8 @@ HC_DEV void TravEnterInstance(HcRayTrav& r, const HcBvh& bvh)
 
 // triangle leaf: IntersectAllPrimitivesInLeaf (ctrace.h:124-182), ONE pair record (two triangles) per call; the leaf word itself is the
 // cursor (index up, count down).  Returns true when a hit was accepted; sets *done when the leaf is exhausted.
-HC_DEV bool TravLeafPair(HcRayTrav& r, const HcBvh& bvh, bool* done)
+HC_DEV bool PairTest(HcRayTrav& r, const float4* __restrict__ p)
 {
-  const float4* p = bvh.tris + size_t(r.node & HC_LEAF_INDEX_MASK)*HC_PAIR_F4;
-  *done = ((r.node >> HC_LEAF_PAIRS_SHIFT) & 63u) == 0u;
-  r.node = r.node - (1u << HC_LEAF_PAIRS_SHIFT) + 1u;
   HcVec2 O, D;
   O.x = bc2(r.o.x); O.y = bc2(r.o.y); O.z = bc2(r.o.z);
   D.x = bc2(r.d.x); D.y = bc2(r.d.y); D.z = bc2(r.d.z);
@@ -227,6 +232,14 @@ HC_DEV bool TravLeafPair(HcRayTrav& r, const HcBvh& bvh, bool* done)
     r.t = t1; r.primId = __float_as_int(r4.w); r.geomId = __float_as_int(__ldg(p + 5).y); r.hitInst = r.instId; found = true;
   }
   return found;
+}
+
+HC_DEV bool TravLeafPair(HcRayTrav& r, const HcBvh& bvh, bool* done)
+{
+  const float4* p = bvh.tris + size_t(r.node & HC_LEAF_INDEX_MASK)*HC_PAIR_F4;
+  *done = ((r.node >> HC_LEAF_PAIRS_SHIFT) & 63u) == 0u;
+  r.node = r.node - (1u << HC_LEAF_PAIRS_SHIFT) + 1u;
+  return PairTest(r, p);
 }
 
 HC_DEV bool RayIsFinite(float3 o, float3 d)

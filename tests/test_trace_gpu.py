@@ -116,3 +116,28 @@ def test_million_triangles_properties(layer, oracle):
     ho = oracle.trace_closest(scn.bvh["nodes"], scn.bvh["tris"], rays[idx])
     nbad, nhard = _same_hits(h[idx], ho)
     assert nhard == 0 and nbad <= 3
+
+
+def test_raycast_pass_vs_oracle(layer, oracle):
+    """hc_raycast_pass (K1 -> K2 -> shadow rays -> K2s, rays fetched in 8x4 pixel blocks): same hits as the oracle's BVH4InstTraverse up to
+    the documented equal-t ties, same visibility as closest-hit-then-compare."""
+    import ctypes as ct
+    from hydracore_b200 import scene as S
+    from hydracore_b200._lib import HC_HOST
+    scn = scenes.instanced_geometry(320, 240)
+    layer.LoadScene(scn)
+    n = 320*240
+    hits = np.empty(n, dtype=layer.TraceClosest(np.zeros((0, 8), np.float32)).dtype)
+    vis = np.empty(n, np.uint8)
+    light = (3.0, 12.0, 5.0)
+    layer.RaycastPass(light, hits.ctypes.data, vis.ctypes.data, HC_HOST)
+    rays = layer.MakeEyeRays(320, 240, None)
+    want = oracle.trace_closest(scn.bvh["nodes"], scn.bvh["tris"], rays)
+    nbad, nhard = _same_hits(hits, want)
+    assert nhard == 0 and nbad <= 1e-4*n, (nbad, nhard)
+    assert (hits["primId"] >= 0).mean() > 0.3
+    srays = layer.MakeShadowRays(rays, want, light)
+    vo = oracle.trace_shadow(scn.bvh["nodes"], scn.bvh["tris"], srays)
+    same = hits["primId"] == want["primId"]
+    assert ((vis != vo) & same).sum() <= 1e-4*n
+    assert 0.05 < vis[hits["primId"] >= 0].mean() < 0.999
