@@ -274,6 +274,12 @@ def run_ours(args):
     value = rays_all*args.steps/t_step/1e6
     ms_per_step = 1e3*t_step/args.steps
 
+    # ---- measured denominators beside MEASURED_PEAKS.json: L2 read bandwidth (48 MiB working set, 20 sweeps) and HBM read bandwidth (2 GiB, 1 sweep)
+    mem_peaks = None
+    if rank == 0:
+        mem_peaks = {"l2_read_gbs": lay.measure_read_bandwidth(48 << 20, 20), "hbm_read_gbs": lay.measure_read_bandwidth(2 << 30, 1),
+                     "how": "hc_measure_read_bandwidth: 128-bit ld.global.cg streaming reads, 148 x 8 CTAs, best of 5"}
+
     # ---- e2e: globals upload + pass + read-back to pinned host memory, wall clock around synchronous API calls
     blob = torch.from_numpy(scn.globals_blob.copy()).pin_memory()
     blob_np = blob.numpy()
@@ -388,10 +394,13 @@ def run_ours(args):
     bytes_per_ray = 52.0 + 128.0*qlt[0] + 16.0*qlt[1] + 48.0*qlt[2]
     ms_closest = stats["msClosest"]/args.steps
     achieved = bytes_per_ray*n/(ms_closest*1e-3)/1e9
-    traffic = None
+    traffic, ncu_extra = None, None
     tp = os.path.join(ROOT, "profiles", "c2_ncu_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("k_trace_closest_dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic = tj.get("k_trace_closest_dram_bytes_per_launch")
+        ncu_extra = {k: tj[k] for k in ("issue_active_pct", "lsu_wavefronts_pct_of_peak", "active_threads_per_warp_instruction", "l1_hit_pct", "l2_hit_pct",
+                                        "l2_to_l1_bytes_per_launch", "l1_load_bytes_per_launch", "source") if k in tj}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "triangles": 1001112, "rays_per_step_per_gpu": rays_per_step,
@@ -405,7 +414,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": traffic,
                          "kernel": "k_trace<closest>", "bytes_per_ray": bytes_per_ray, "quads_leaves_tris_per_ray": qlt,
                          "ms_per_launch": ms_closest, "peak_source": peak_src,
-                         "note": "algorithmic bytes are BVH/triangle fetches that the 126 MB L2 serves; HBM peak is the stated denominator"}}
+                         "note": "algorithmic bytes are BVH/triangle fetches that L1 (84 % hit) and the 126 MB L2 serve, so frac can exceed 1; "
+                                 "the kernel is bound by instruction issue and the L1/LSU wavefront rate (fields below, from the ncu capture in profiles/)",
+                         "measured_memory_peaks": mem_peaks, "ncu": ncu_extra}}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     line.update(extras)

@@ -52,6 +52,7 @@ SIGNATURES = {
     "hc_make_shadow_rays": (_I, [_P, _P, _P, _I64, ct.POINTER(ct.c_float), _P, _I]),
     "hc_raycast_pass": (_I, [_P, ct.POINTER(ct.c_float), _P, _P, _I]),
     "hc_trace_last_ms": (_I, [_P, ct.POINTER(ct.c_float)]),
+    "hc_measure_read_bandwidth": (_I, [_P, _U64, _I, ct.POINTER(ct.c_float)]),
     "hc_pt_init": (_I, [_P, _I]),
     "hc_pt_set_tiles": (_I, [_P, _I, _I, _I]),
     "hc_pt_set_material_sort": (_I, [_P, _I, _I]),

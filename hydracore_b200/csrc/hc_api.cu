@@ -596,6 +596,51 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
   return HC_OK;
 }
 
+// ---- memory-system microbenchmarks (denominators of the roofline that MEASURED_PEAKS.json does not hold)
+// Streaming 128-bit reads of a buffer, `repeats` sweeps per launch.  With a buffer well below the 126 MB L2 the sweeps after the first are
+// served by L2 (-> L2 read bandwidth); with a buffer far above it they come from HBM (cross-check of the driver-measured copy bandwidth).
+static __global__ void __launch_bounds__(256) k_stream_read(const uint4* __restrict__ buf, const size_t n16, const int repeats, unsigned* __restrict__ sink)
+{
+  unsigned acc = 0;
+  const size_t stride = size_t(gridDim.x)*blockDim.x;
+  for (int r = 0; r < repeats; r++)
+    for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n16; i += stride)
+    {
+      uint4 v;
+      asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(buf + i));   // .cg: bypass L1
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+  if (acc == 0x12345678u) sink[0] = acc;       // keeps the loads alive
+}
+
+int hc_measure_read_bandwidth(hc_ctx* ctx, uint64_t bytes, int repeats, float* outGBs)
+{
+  if (!ctx || !outGBs || bytes < 4096 || repeats < 1) return HC_E_ARG;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HcDevBuf b, sink;
+  int rc = hc_buf_reserve(ctx, b, bytes); if (rc) return rc;
+  rc = hc_buf_reserve(ctx, sink, 16); if (rc) { hc_buf_free(b); return rc; }
+  HC_CUDA(cudaMemsetAsync(b.ptr, 1, bytes, ctx->stream));
+  const size_t n16 = bytes/16;
+  const int grid = ctx->smCount*8;
+  k_stream_read<<<grid, 256, 0, ctx->stream>>>((const uint4*)b.ptr, n16, 2, (unsigned*)sink.ptr);         // warm-up (fills L2 when it fits)
+  float best = 0.0f;
+  for (int it = 0; it < 5; it++)
+  {
+    HC_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    k_stream_read<<<grid, 256, 0, ctx->stream>>>((const uint4*)b.ptr, n16, repeats, (unsigned*)sink.ptr);
+    HC_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    HC_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.0f; HC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    const float gbs = float(double(n16)*16.0*double(repeats)/(double(ms)*1e-3)/1e9);
+    if (gbs > best) best = gbs;
+  }
+  HC_CUDA(cudaGetLastError());
+  hc_buf_free(b); hc_buf_free(sink);
+  *outGBs = best;
+  return HC_OK;
+}
+
 int hc_trace_closest(hc_ctx* ctx, const float* rays8, int64_t n, hc_hit* hitsOut, int space) { return TraceEntry(ctx, false, rays8, n, hitsOut, space); }
 int hc_trace_shadow(hc_ctx* ctx, const float* rays8, int64_t n, uint8_t* visibleOut, int space) { return TraceEntry(ctx, true, rays8, n, visibleOut, space); }
 int hc_trace_last_ms(hc_ctx* ctx, float* outMs) { if (!ctx || !outMs) return HC_E_ARG; *outMs = ctx->lastTraceMs; return HC_OK; }

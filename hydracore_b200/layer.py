@@ -181,6 +181,11 @@ class CudaLayer:
         check(self._L.hc_raycast_pass(self._c, lp, ct.c_void_p(hits_ptr) if hits_ptr else None, ct.c_void_p(vis_ptr) if vis_ptr else None, space),
               "hc_raycast_pass")
 
+    def measure_read_bandwidth(self, nbytes, repeats):
+        g = ct.c_float()
+        check(self._L.hc_measure_read_bandwidth(self._c, int(nbytes), int(repeats), ct.byref(g)), "hc_measure_read_bandwidth")
+        return g.value
+
     def last_trace_ms(self):
         ms = ct.c_float()
         check(self._L.hc_trace_last_ms(self._c, ct.byref(ms)), "hc_trace_last_ms")

@@ -93,7 +93,10 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
                                                                                  shadow rays to lightPos -> K2s any hit.  The RT-mode pass of the OpenCL layer
                                                                                  (GPUOCLLayer::trace1DPrimaryOnly, GPUOCLLayerCore.cpp:294) plus the shadow step of ShadePass (:1007).
                                                                                  Results stay on the device unless out pointers are given (space says where they live). */
-int hc_trace_last_ms(hc_ctx* ctx, float* outMs);                             /* device time of the last hc_trace_* launch (CUDA events)   */
+int hc_trace_last_ms(hc_ctx* ctx, float* outMs);
+int hc_measure_read_bandwidth(hc_ctx* ctx, uint64_t bytes, int repeats, float* outGBs);
+                                                                              /* streaming-read microbenchmark (L1 bypassed): bytes << 126 MB and repeats > 1 gives the L2 read
+                                                                                 bandwidth, bytes >> 126 MB the HBM read bandwidth; roofline denominators measured in place */                             /* device time of the last hc_trace_* launch (CUDA events)   */
 
 /* ---------------------------------------------------------------- path tracing -------------------------------------------- */
 int hc_pt_init(hc_ctx* ctx, int seed);                                       /* InitPathTracing, IHWLayer.h:139 ; InitRandomGen, trace.cl:6 */
