@@ -210,6 +210,7 @@ def run_ours(args):
     world, rank, local = _dist()
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL writes its version / debug lines to stdout by default: keep stdout = the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
