@@ -157,8 +157,7 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
           const float* L = (s.lightsNum != 0) ? LightAt(s, s.instLightIds[hit.instId]) : nullptr;
           if (L != nullptr)
           {                                                       // kernel_EvalEmission (PT_Loop.cpp:86-139)
-            const float hitDist = length(rayPos - sh.pos);
-            const float lgtPdf = L[HC_PLIGHT_PICK_PROB_REV]*AreaLightEvalPDF(L, rayDir, hitDist);
+            const float lgtPdf = L[HC_PLIGHT_PICK_PROB_REV]*LightEvalPDF(L, rayPos, rayDir, sh.pos, sh.normal);
             float w = misWeightHeuristic(prevPdf, lgtPdf);
             if (prevSpecular) w = 1.0f;
             curr = e*w;
@@ -183,7 +182,7 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
           {
             const float* L = LightAt(s, lightOffset);
             HcShadowSample sam;
-            AreaLightSampleRev(L, f3(rl.x, rl.y, rl.z), sh.pos, sam);
+            LightSampleRev(L, f3(rl.x, rl.y, rl.z), sh.pos, sam);
             const float3 sdir = normalize(sam.pos - sh.pos);
             const float3 spos = OffsShadowRayPos(sh.pos, sh.normal, sdir, sh.sRayOff);
             const float tFar = length(spos - sam.pos)*0.995f;
@@ -465,7 +464,12 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
     const float* L = reinterpret_cast<const float*>(gl.data()) + lightsOffset + l*HC_LIGHT_DATA_SIZE;
     int type, flags, tex, spot; memcpy(&type, L + HC_PLIGHT_TYPE, 4); memcpy(&flags, L + HC_PLIGHT_FLAGS, 4);
     memcpy(&tex, L + HC_PLIGHT_COLOR_TEX, 4); memcpy(&spot, L + HC_AREA_LIGHT_SPOT_DISTR, 4);
-    if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "only area lights (PLAIN_LIGHT_TYPE_AREA) are supported yet"; return HC_E_ARG; }
+    if (type == HC_PLAIN_LIGHT_TYPE_SPHERE || type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI)
+    {
+      if (flags & HC_LIGHT_HAS_IES) { why = "IES distributions are not supported yet"; return HC_E_ARG; }
+      continue;
+    }
+    if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "only area, sphere and omni point lights are supported yet"; return HC_E_ARG; }
     if (flags & (HC_LIGHT_HAS_IES | HC_AREA_LIGHT_SKY_PORTAL | HC_LIGHT_IES_POINT_AREA)) { why = "IES / sky-portal area lights are not supported yet"; return HC_E_ARG; }
     if (tex != HC_INVALID_TEXTURE) { why = "textured area lights are not supported yet"; return HC_E_ARG; }
     if (spot != 0) { why = "area lights with a spot distribution are not supported yet"; return HC_E_ARG; }

@@ -902,6 +902,74 @@ HC_DEV void AreaLightSampleRev(const float* L, float3 rands, float3 illum, HcSha
   out.cosAtLight = -dot(rayDir, ln);
 }
 
+// ---- sphere and omni point lights (clight.h:1287-1333, 1387-1407).  The reference's host build takes M_PI from <cmath> (a double) and
+// resolves sin / cos / acos on float arguments to the double functions, so those expressions are evaluated in double and rounded once.
+#define HC_SPHERE_LIGHT_RADIUS 14
+HC_DEV float PdfAtoW(float pdfA, float dist, float cosThere) { return (pdfA*dist*dist)/fmaxf(cosThere, HC_DEPSILON2); }   // cglobals.h:1754-1757
+
+HC_DEV float SphereLightEvalPDF(const float* L, float3 illum, float3 lpos, float3 lnorm)                                   // clight.h:1287-1302
+{
+  const float lradius = L[HC_SPHERE_LIGHT_RADIUS];
+  const float3 lcenter = Mat3(L, HC_PLIGHT_POS_X);
+  const float3 diff = lcenter - illum;                                                  // DistanceSquared(a, b) = dot(b - a, b - a), cglobals.h:1152
+  if (dot(diff, diff) - lradius*lradius <= 0.0f) return 1.0f;
+  const float pdfA = 1.0f/L[HC_PLIGHT_SURFACE_AREA];
+  const float dist = length(lpos - illum);
+  const float3 dirToV = normalize(lpos - illum);
+  const float cosAtLight = fabsf(dot(dirToV, lnorm));
+  return PdfAtoW(pdfA, dist, cosAtLight);
+}
+
+HC_DEV void SphereLightSampleRev(const float* L, float3 rands, float3 illum, HcShadowSample& out)                          // clight.h:1309-1333
+{
+  const float theta = (float)(2.0*3.14159265358979323846*(double)rands.x);
+  const float phi   = (float)acos((double)(1.0f - 2.0f*rands.y));
+  const float x = (float)(sin((double)phi)*cos((double)theta));
+  const float y = (float)(sin((double)phi)*sin((double)theta));
+  const float z = (float)cos((double)phi);
+  const float3 lcenter = Mat3(L, HC_PLIGHT_POS_X);
+  const float lradius = L[HC_SPHERE_LIGHT_RADIUS];
+  const float3 samplePos = lcenter + lradius*f3(x, y, z);
+  const float3 lightNorm = normalize(samplePos - lcenter);
+  const float3 dirToV = normalize(samplePos - illum);
+  out.isPoint = false;
+  out.pos = samplePos;
+  out.color = Mat3(L, HC_PLIGHT_COLOR_X);                                                // sphereLightGetIntensity = lightBaseColor
+  out.pdf = SphereLightEvalPDF(L, illum, samplePos, lightNorm);
+  out.maxDist = length(samplePos - illum);
+  out.cosAtLight = fabsf(dot(lightNorm, dirToV));
+}
+
+HC_DEV void PointLightSampleRev(const float* L, float3 illum, HcShadowSample& out)                                         // clight.h:1394-1407, no IES
+{
+  const float3 samplePos = Mat3(L, HC_PLIGHT_POS_X);
+  const float hitDist = length(samplePos - illum);
+  out.isPoint = true;
+  out.pos = samplePos;
+  out.color = f3(1.0f, 1.0f, 1.0f)*Mat3(L, HC_PLIGHT_COLOR_X);                           // lightDistributionMask = (1,1,1) without LIGHT_HAS_IES
+  out.pdf = PdfAtoW(1.0f, hitDist, 1.0f);
+  out.maxDist = hitDist;
+  out.cosAtLight = 1.0f;
+}
+
+// LightSampleRev / lightEvalPDF dispatch (clight.h:1561-1633) over the light types hc_pt_init accepts
+HC_DEV void LightSampleRev(const float* L, float3 rands, float3 illum, HcShadowSample& out)
+{
+  const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
+  if (type == HC_PLAIN_LIGHT_TYPE_SPHERE) SphereLightSampleRev(L, rands, illum, out);
+  else if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI) PointLightSampleRev(L, illum, out);
+  else AreaLightSampleRev(L, rands, illum, out);
+}
+
+HC_DEV float LightEvalPDF(const float* L, float3 illum, float3 rayDir, float3 lpos, float3 lnorm)
+{
+  const float hitDist = length(illum - lpos);
+  const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
+  if (type == HC_PLAIN_LIGHT_TYPE_SPHERE) return SphereLightEvalPDF(L, illum, lpos, lnorm);
+  if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI) return PdfAtoW(1.0f, length(Mat3(L, HC_PLIGHT_POS_X) - illum), 1.0f);       // pointLightEvalPDF, clight.h:1387-1392
+  return AreaLightEvalPDF(L, rayDir, hitDist);
+}
+
 // emissionEval (cbidir.h:653-678) through IntegratorCommon::emissionEval (CPUExp_Integrators_Common.cpp:509-520)
 HC_DEV float3 EmissionEval(const HcScene& s, float3 rayPos, float3 rayDir, const HcSurfaceHit& sh, unsigned flags, int instId)
 {

@@ -151,3 +151,37 @@ def area_light(pos, half_size, intensity, rotation=None, disk=False, pick_prob=1
     L[C["PLIGHT_PICK_PROB_FWD"]] = pick_prob
     L[C["PLIGHT_PICK_PROB_REV"]] = pick_prob
     return L
+
+
+def sphere_light(pos, radius, intensity, pick_prob=1.0):
+    """Sphere area light (SphereLight, PlainLightConverter.cpp:445-492): centre, radius, surface area 4*pi*r^2, uniform emission."""
+    L = np.zeros(128, np.float32)
+    L[C["PLIGHT_TYPE"]] = _i2f(C["PLAIN_LIGHT_TYPE_SPHERE"])
+    L[C["PLIGHT_FLAGS"]] = _i2f(0)
+    L[C["PLIGHT_POS_X"]:C["PLIGHT_POS_X"] + 3] = pos
+    L[C["PLIGHT_COLOR_X"]:C["PLIGHT_COLOR_X"] + 3] = intensity
+    L[C["PLIGHT_COLOR_TEX"]] = _i2f(INVALID_TEXTURE)
+    L[C["PLIGHT_COLOR_TEX_MATRIX"]] = _i2f(INVALID_TEXTURE)
+    r = np.float32(radius)
+    L[14] = r                                                              # SPHERE_LIGHT_RADIUS, clight.h:33
+    L[C["PLIGHT_SURFACE_AREA"]] = np.float32(4.0)*np.float32(3.1415926535)*r*r
+    L[C["PLIGHT_PROB_MULT"]] = 1.0
+    L[C["PLIGHT_PICK_PROB_FWD"]] = pick_prob
+    L[C["PLIGHT_PICK_PROB_REV"]] = pick_prob
+    return L
+
+
+def point_light(pos, intensity, pick_prob=1.0):
+    """Omni point light without IES (PointLight, PlainLightConverter.cpp:628-690): surface area 1e-10."""
+    L = np.zeros(128, np.float32)
+    L[C["PLIGHT_TYPE"]] = _i2f(C["PLAIN_LIGHT_TYPE_POINT_OMNI"])
+    L[C["PLIGHT_FLAGS"]] = _i2f(0)
+    L[C["PLIGHT_POS_X"]:C["PLIGHT_POS_X"] + 3] = pos
+    L[C["PLIGHT_COLOR_X"]:C["PLIGHT_COLOR_X"] + 3] = intensity
+    L[C["PLIGHT_COLOR_TEX"]] = _i2f(INVALID_TEXTURE)
+    L[C["PLIGHT_COLOR_TEX_MATRIX"]] = _i2f(INVALID_TEXTURE)
+    L[C["PLIGHT_SURFACE_AREA"]] = 1e-10
+    L[C["PLIGHT_PROB_MULT"]] = 1.0
+    L[C["PLIGHT_PICK_PROB_FWD"]] = pick_prob
+    L[C["PLIGHT_PICK_PROB_REV"]] = pick_prob
+    return L

@@ -97,3 +97,25 @@ def cornell(width=128, height=128, trace_depth=5, two_lights=False, dof=False, t
         l1 = scn.add_light(M2.area_light((-2.5, 1.0, 3.0), (0.6, 0.6), (4.0, 6.0, 9.0), rotation=R))
         scn.add_instance(scn.add_mesh(lq2), S.translate(-2.5, 1.0, 3.0) @ S.rotate_x(-1.2), light_id=l1)
     return scn.build()
+
+
+def cornell_sphere_and_point_lights(width=96, height=96):
+    """The Cornell room lit by a sphere area light (with its emissive mesh, so that paths can hit it) and an omni point light."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    ggxm = scn.add_material(M.ggx((0.8, 0.6, 0.2), 0.7))
+    gls = scn.add_material(M.glass((0.95, 0.98, 0.95), ior=1.5, gloss=1.0))
+    emi = scn.add_material(M.emissive((30.0, 26.0, 20.0), 0))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, white, white, white), inward=True, skip_faces=(4,))))
+    sph = S.sphere_mesh(1.0, 32, 16)
+    for mat, mtx in ((ggxm, S.translate(-2.0, -2.8, -1.0) @ S.scale(1.2, 1.2, 1.2)), (gls, S.translate(1.8, -2.9, 1.2) @ S.scale(1.1, 1.1, 1.1))):
+        scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, mat, np.int32))), mtx)
+    l0 = scn.add_light(M.sphere_light((0.5, 2.4, 0.0), 0.6, (30.0, 26.0, 20.0)))
+    lm = S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, emi, np.int32))
+    scn.add_instance(scn.add_mesh(lm), S.translate(0.5, 2.4, 0.0) @ S.scale(0.6, 0.6, 0.6), light_id=l0)
+    scn.add_light(M.point_light((-2.5, 1.0, 3.0), (25.0, 35.0, 50.0)))
+    return scn.build()
