@@ -314,7 +314,7 @@ def run_ours(args):
         lay.close()
         for key, label, build in (("c1", "C1: hydra_app/tests/test_42 (25,612 triangles, Lambert / Phong blend / emissive, rect area light, DOF), unidirectional PT, 512x512",
                                    lambda: __import__("hydracore_b200.hydra_scene", fromlist=["x"]).build_scene(
-                                       __import__("hydracore_b200.hydra_scene", fromlist=["x"]).load_fixture(os.path.join(ROOT, "tests", "golden", "test_42_scene.npz")), 512, 512)),
+                                       __import__("hydracore_b200.hydra_scene", fromlist=["x"]).load_fixture(os.path.join(ROOT, "tests", "golden", "hydra_scenes.npz"), "test_42"), 512, 512)),
                                   ("c3", "C3: MISPT trace_depth 8, Lambert/GGX/glass/blend + 2 area lights, 1,001,116 triangles, 1080p, 32x32 interleaved tiles",
                                    lambda: S.scene_c3(WIDTH, HEIGHT)),
                                   ("c4", "C4: MISPT trace_depth 5 on 200 instances x 100,352 triangles = 20,070,400 instanced triangles, Lambert, 1080p, 32x32 interleaved tiles",

@@ -46,11 +46,21 @@ def _floats(text):
     return [float(x.rstrip("f")) for x in text.replace(",", " ").split()]
 
 
+def _val(node, default=None):
+    """Hydra XML writes scalars and colours either as element text or as a val="..." attribute."""
+    if node is None:
+        return default
+    v = node.get("val")
+    if v is None:
+        v = (node.text or "").strip()
+    return v if v != "" else default
+
+
 def parse_library(xml_path, mesh_fallback_dirs=()):
     """-> plain dict description of the scene library (no packing yet): textures, materials, lights, camera, meshes, instances, settings."""
     base = os.path.dirname(os.path.abspath(xml_path))
     root = ET.fromstring("<root>" + open(xml_path, encoding="utf-8").read().split("?>", 1)[-1] + "</root>")
-    out = dict(textures={}, materials={}, lights={}, meshes={}, instances=[], light_instances={}, settings={})
+    out = dict(textures={}, materials={}, lights={}, meshes={}, instances=[], light_instances=[], settings={})
     for t in root.find("textures_lib"):
         loc = t.get("loc")
         if loc and int(t.get("bytesize", "0")) > 16 and os.path.exists(os.path.join(base, loc)):
@@ -61,24 +71,24 @@ def parse_library(xml_path, mesh_fallback_dirs=()):
         if dif is not None:
             tex = dif.find("texture")
             tex = dif.find("color/texture") if tex is None else tex
-            d["diffuse"] = dict(color=_floats(dif.find("color").text or dif.find("color").get("val")), tex=int(tex.get("id")) if tex is not None else 0)
+            d["diffuse"] = dict(color=_floats(_val(dif.find("color"), "0 0 0")), tex=int(tex.get("id")) if tex is not None else 0)
         if ref is not None:
             col = ref.find("color")
-            d["reflect"] = dict(color=_floats(col.text or col.get("val")), gloss=float((ref.find("glossiness").text if ref.find("glossiness") is not None else "1")),
-                                brdf=ref.get("brdf_type", "phong"), fresnel=ref.find("fresnel") is not None and ref.find("fresnel").get("val", "0") == "1",
-                                ior=float(ref.find("fresnel_ior").get("val")) if ref.find("fresnel_ior") is not None else 1.5)
+            d["reflect"] = dict(color=_floats(_val(col, "0 0 0")), gloss=float(_val(ref.find("glossiness"), "1")),
+                                brdf=ref.get("brdf_type", "phong"), fresnel=_val(ref.find("fresnel"), "0") == "1", ior=float(_val(ref.find("fresnel_ior"), "1.5")))
         if emi is not None:
             col = emi.find("color")
-            d["emission"] = _floats(col.get("val") or col.text)
+            d["emission"] = _floats(_val(col, "0 0 0"))
         out["materials"][int(m.get("id"))] = d
     for l in root.find("lights_lib"):
         size, inten = l.find("size"), l.find("intensity")
-        mult = float(inten.find("multiplier").text if inten.find("multiplier").text else inten.find("multiplier").get("val"))
+        mult = float(_val(inten.find("multiplier"), "1"))
         col = inten.find("color")
-        out["lights"][int(l.get("id"))] = dict(type=l.get("type"), shape=l.get("shape"), half=(float(size.get("half_length")), float(size.get("half_width"))),
-                                                color=[c*mult for c in _floats(col.text or col.get("val"))], mat_id=int(l.get("mat_id", "-1")))
+        half = (float(size.get("half_length", "0")), float(size.get("half_width", "0"))) if size is not None else (0.0, 0.0)
+        out["lights"][int(l.get("id"))] = dict(type=l.get("type"), shape=l.get("shape", "point"), half=half, radius=float(size.get("radius", "0")) if size is not None else 0.0,
+                                                color=[c*mult for c in _floats(_val(col, "1 1 1"))], mat_id=int(l.get("mat_id", "-1")))
     cam = root.find("cam_lib")[0]
-    g = lambda n, dflt: (cam.find(n).text if cam.find(n) is not None else dflt)
+    g = lambda n, dflt: _val(cam.find(n), dflt)
     out["camera"] = dict(fov=float(g("fov", "45")), near=float(g("nearClipPlane", "0.01")), far=float(g("farClipPlane", "100")), up=_floats(g("up", "0 1 0")),
                          pos=_floats(g("position", "0 0 1")), look_at=_floats(g("look_at", "0 0 0")), dof=int(g("enable_dof", "0")) == 1,
                          lens_radius=_floats(g("dof_lens_radius", "0"))[0])
@@ -94,14 +104,15 @@ def parse_library(xml_path, mesh_fallback_dirs=()):
     rs = root.find("render_lib")[0]
     for k in ("width", "height", "trace_depth", "diff_trace_depth", "qmc_variant"):
         if rs.find(k) is not None:
-            out["settings"][k] = int(rs.find(k).text)
+            out["settings"][k] = int(_val(rs.find(k), "0"))
     scn = root.find("scenes")[0]
     for e in scn:
         mtx = np.array(_floats(e.get("matrix")), np.float32).reshape(4, 4)
         if e.tag == "instance":
-            out["instances"].append(dict(mesh_id=int(e.get("mesh_id")), matrix=mtx, light_id=int(e.get("light_id", "-1"))))
+            out["instances"].append(dict(mesh_id=int(e.get("mesh_id")), matrix=mtx, light_id=int(e.get("light_id", "-1")), linst_id=int(e.get("linst_id", "-1"))))
         elif e.tag == "instance_light":
-            out["light_instances"][int(e.get("light_id"))] = mtx
+            out["light_instances"].append(dict(id=int(e.get("id")), light_id=int(e.get("light_id")), matrix=mtx))
+    out["light_instances"].sort(key=lambda d: d["id"])
     return out
 
 
@@ -114,13 +125,21 @@ def build_scene(lib, width, height):
     tex_map = {0: 0}
     for tid in sorted(lib["textures"]):
         tex_map[tid] = scn.add_texture_rgba8(lib["textures"][tid])
-    light_map = {}
-    for lid in sorted(lib["lights"]):
-        l = lib["lights"][lid]
-        if l["type"] != "area" or l["shape"] != "rect":
-            raise ValueError("only rectangular area lights are supported yet (light %d is %s/%s)" % (lid, l["type"], l["shape"]))
-        mtx = lib["light_instances"].get(lid, np.eye(4, dtype=np.float32))
-        light_map[lid] = scn.add_light(M.area_light(tuple(mtx[:3, 3]), l["half"], tuple(l["color"]), rotation=mtx[:3, :3]))
+    # one PlainLight per <instance_light>, in instance order (the driver instantiates lights per scene instance, RenderDriverRTE.cpp:1499-1521)
+    linst_map, light_map = {}, {}
+    for li in lib["light_instances"]:
+        l, mtx = lib["lights"][li["light_id"]], li["matrix"]
+        if l["type"] == "area" and l["shape"] == "rect":
+            idx = scn.add_light(M.area_light(tuple(mtx[:3, 3]), l["half"], tuple(l["color"]), rotation=mtx[:3, :3]))
+        elif l["type"] == "area" and l["shape"] == "sphere":
+            scale = float(np.linalg.norm(mtx[:3, :3] @ (np.ones(3, np.float32)/np.float32(np.sqrt(3.0)))))       # SphereLight::Transform, PlainLightConverter.cpp:480-488
+            idx = scn.add_light(M.sphere_light(tuple(mtx[:3, 3]), l["radius"]*scale, tuple(l["color"])))
+        elif l["type"] == "point" and l["shape"] == "point":
+            idx = scn.add_light(M.point_light(tuple(mtx[:3, 3]), tuple(l["color"])))
+        else:
+            raise ValueError("light %d: type %s / shape %s is not supported yet (rect and sphere area lights, omni point lights are)" % (li["light_id"], l["type"], l["shape"]))
+        linst_map[li["id"]] = idx
+        light_map.setdefault(li["light_id"], idx)
     mat_map = {}
     for mid in range(max(lib["materials"]) + 1):
         d = lib["materials"].get(mid, dict(diffuse=dict(color=[0.5, 0.5, 0.5], tex=0)))
@@ -142,12 +161,12 @@ def build_scene(lib, width, height):
         if k not in mesh_map:
             m = lib["meshes"][k]
             mesh_map[k] = scn.add_mesh(S.Mesh(m["pos"], m["idx"], norm=m["norm"], uv=m["uv"], mat=np.array([mat_map.get(int(x), 0) for x in m["mat"]], np.int32)))
-        scn.add_instance(mesh_map[k], inst["matrix"], light_id=light_map.get(inst["light_id"], -1))
+        lidx = linst_map.get(inst.get("linst_id", -1), light_map.get(inst["light_id"], -1))
+        scn.add_instance(mesh_map[k], inst["matrix"], light_id=lidx)
     return scn.build()
 
 
-def save_fixture(lib, path):
-    """Store the parsed library as one compressed .npz (so that tests and the bench can rebuild the scene without the reference tree)."""
+def _fixture_arrays(lib):
     a = {"camera": np.array([lib["camera"][k] if not isinstance(lib["camera"][k], (list, tuple)) else 0 for k in ("fov", "near", "far", "lens_radius")], np.float64),
          "camera_vec": np.array([lib["camera"]["pos"], lib["camera"]["look_at"], lib["camera"]["up"]], np.float64), "camera_dof": np.array([int(lib["camera"]["dof"])]),
          "settings": np.array([lib["settings"].get(k, -1) for k in ("width", "height", "trace_depth", "diff_trace_depth", "qmc_variant")], np.int64)}
@@ -168,18 +187,52 @@ def save_fixture(lib, path):
                     (ref["color"] + [ref["gloss"], 1.0 if ref["brdf"] == "ggx" else 0.0, 1.0 if ref["fresnel"] else 0.0, ref["ior"]] if ref else [0, 0, 0, -1, 0, 0, 0]) +
                     (d["emission"] if "emission" in d else [-1, -1, -1]))
     a["materials"] = np.array(mats, np.float64)
-    a["lights"] = np.array([[lid] + list(l["half"]) + l["color"] + [l["mat_id"]] for lid, l in sorted(lib["lights"].items())], np.float64)
-    a["light_matrices"] = np.array([lib["light_instances"].get(lid, np.eye(4)) for lid in sorted(lib["lights"])], np.float32)
-    a["instances"] = np.array([[i["mesh_id"], i["light_id"]] for i in lib["instances"]], np.int64)
+    shapes = {"rect": 0, "sphere": 1, "point": 2}
+    a["lights"] = np.array([[lid] + list(l["half"]) + l["color"] + [l["mat_id"], shapes[l["shape"]], l["radius"]] for lid, l in sorted(lib["lights"].items())], np.float64)
+    a["light_instances"] = np.array([[li["id"], li["light_id"]] for li in lib["light_instances"]], np.int64).reshape(-1, 2)
+    a["light_matrices"] = np.array([li["matrix"] for li in lib["light_instances"]], np.float32).reshape(-1, 4, 4)
+    a["instances"] = np.array([[i["mesh_id"], i["light_id"], i.get("linst_id", -1)] for i in lib["instances"]], np.int64)
     a["instance_matrices"] = np.array([i["matrix"] for i in lib["instances"]], np.float32)
-    np.savez_compressed(path, **a)
+    return a
 
 
-def load_fixture(path):
-    z = np.load(path)
+def save_fixtures(libs, path):
+    """Store parsed libraries {name: lib} in ONE compressed .npz, so that tests and the bench can rebuild the scenes where the reference tree
+    does not exist.  Keys are "<name>::<field>"; arrays shared between scenes (the teapot, textures) are stored once and aliased."""
+    import hashlib
+    out, seen = {}, {}
+    for name, lib in libs.items():
+        for k, v in _fixture_arrays(lib).items():
+            v = np.ascontiguousarray(v)
+            key = name + "::" + k
+            h = (v.dtype.str, v.shape, hashlib.sha1(v.tobytes()).hexdigest())
+            if v.nbytes > 4096 and h in seen:
+                out[key + "@"] = np.array(seen[h])
+            else:
+                out[key] = v
+                seen[h] = key
+    np.savez_compressed(path, **out)
+
+
+class _Prefixed:
+    def __init__(self, z, prefix):
+        self.z, self.p = z, prefix
+
+    def __getitem__(self, k):
+        if self.p + k + "@" in self.z.files:
+            return self.z[str(self.z[self.p + k + "@"])]
+        return self.z[self.p + k]
+
+
+def fixture_scenes(path):
+    return sorted({k.split("::")[0] for k in np.load(path).files})
+
+
+def load_fixture(path, scene):
+    z = _Prefixed(np.load(path), scene + "::")
     cam = dict(zip(("fov", "near", "far", "lens_radius"), [float(x) for x in z["camera"]]))
     cam.update(pos=list(z["camera_vec"][0]), look_at=list(z["camera_vec"][1]), up=list(z["camera_vec"][2]), dof=bool(z["camera_dof"][0]))
-    lib = dict(camera=cam, textures={int(t): z["tex%d" % t] for t in z["tex_ids"]}, materials={}, lights={}, meshes={}, instances=[], light_instances={},
+    lib = dict(camera=cam, textures={int(t): z["tex%d" % t] for t in z["tex_ids"]}, materials={}, lights={}, meshes={}, instances=[], light_instances=[],
                settings={k: int(v) for k, v in zip(("width", "height", "trace_depth", "diff_trace_depth", "qmc_variant"), z["settings"]) if v >= 0})
     for k in z["mesh_ids"]:
         lib["meshes"][int(k)] = {f: z["mesh%d_%s" % (k, f)] for f in ("pos", "norm", "uv", "idx", "mat")}
@@ -192,9 +245,12 @@ def load_fixture(path):
         if r[13] >= 0:
             d["emission"] = list(r[13:16])
         lib["materials"][int(r[0])] = d
-    for r, mtx in zip(z["lights"], z["light_matrices"]):
-        lib["lights"][int(r[0])] = dict(type="area", shape="rect", half=(float(r[1]), float(r[2])), color=list(r[3:6]), mat_id=int(r[6]))
-        lib["light_instances"][int(r[0])] = mtx
+    shapes = {0: ("area", "rect"), 1: ("area", "sphere"), 2: ("point", "point")}
+    for r in z["lights"]:
+        ty, sh = shapes[int(r[7])]
+        lib["lights"][int(r[0])] = dict(type=ty, shape=sh, half=(float(r[1]), float(r[2])), color=list(r[3:6]), mat_id=int(r[6]), radius=float(r[8]))
+    for r, mtx in zip(z["light_instances"], z["light_matrices"]):
+        lib["light_instances"].append(dict(id=int(r[0]), light_id=int(r[1]), matrix=mtx))
     for r, mtx in zip(z["instances"], z["instance_matrices"]):
-        lib["instances"].append(dict(mesh_id=int(r[0]), light_id=int(r[1]), matrix=mtx))
+        lib["instances"].append(dict(mesh_id=int(r[0]), light_id=int(r[1]), linst_id=int(r[2]), matrix=mtx))
     return lib

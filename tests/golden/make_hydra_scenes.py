@@ -1,0 +1,46 @@
+"""Scene libraries of the reference (hydra_app/tests/*) as test fixtures.  Run where /root/reference exists:
+    python tests/golden/make_hydra_scenes.py
+writes tests/golden/hydra_scenes.npz — the PARSED libraries (meshes, textures, material / light / camera parameters; shared arrays stored
+once) so that tests and bench.py can rebuild the scenes on the GPU box, where the reference tree does not exist — and
+tests/golden/hydra_scenes_images.npz — HDR sums of 4 passes at 128x128 from the reference's CPU integrators compiled in place
+(oracle/_ref; IntegratorStupidPT = the "unidirectional PT" BASELINE config C1 names, and IntegratorMISPTLoop2; per-pixel seeding of
+SURVEY.md 8c, seed 777).
+  test_42          BASELINE config C1: teapot 25,600 triangles + box + light quad; Lambert (+texture), Phong blend, emissive; rect light; DOF
+  test_42_ggx      the same with a GGX reflection layer
+  test_224_sphere  another teapot, a rect and a SPHERE area light"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from hydracore_b200 import hydra_scene as HS  # noqa: E402
+from tests import refapi  # noqa: E402
+
+REF = os.environ.get("HYDRA_REFERENCE", "/root/reference")
+SCENES = ("test_42", "test_42_ggx", "test_224_sphere")
+
+
+def main():
+    libs = {n: HS.parse_library(os.path.join(REF, "hydra_app/tests", n, "statex_00001.xml"), mesh_fallback_dirs=[os.path.join(REF, "hydra_app/data/meshes")])
+            for n in SCENES}
+    path = os.path.join(HERE, "hydra_scenes.npz")
+    HS.save_fixtures(libs, path)
+    ref = refapi.Ref.try_load()
+    assert ref is not None, "oracle/_ref/libhydra_ref.so missing: run __graft_entry__.build() where the reference tree exists"
+    out = {}
+    for n in SCENES:
+        scn = HS.build_scene(HS.load_fixture(path, n), 128, 128)
+        rs = ref.scene(scn)
+        for kind, tag in ((0, "pt"), (2, "mispt")):
+            img, _n = rs.render(kind, 777, 4)
+            out["%s_%s_sum4" % (n, tag)] = img[..., :3].astype(np.float32)
+        rs.close()
+    np.savez_compressed(os.path.join(HERE, "hydra_scenes_images.npz"), **out)
+    print({k: float(v.mean()) for k, v in out.items()}, os.path.getsize(path))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,6 @@
-"""BASELINE config C1: hydra_app/tests/test_42 (the reference's own Cornell-box test scene), unidirectional PT.
-CPU part: the scene-library reader against the committed fixture.  GPU part: IntegratorStupidPT / MISPTLoop2 parity on the real scene
-and the full-size 512x512, 64 spp render."""
+"""BASELINE config C1: hydra_app/tests/test_42 (the reference's own Cornell-box test scene), unidirectional PT — and two more of the
+reference's scene libraries (GGX reflection layer; sphere area light).  CPU part: the scene-library reader against the committed fixture.
+GPU part: IntegratorStupidPT / MISPTLoop2 parity on the real scenes and the full-size 512x512, 64 spp render of C1."""
 import os
 
 import numpy as np
@@ -9,19 +9,20 @@ import pytest
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _scene(w, h):
+def _scene(w, h, name="test_42"):
     from hydracore_b200 import hydra_scene as HS
-    return HS.build_scene(HS.load_fixture(os.path.join(G, "test_42_scene.npz")), w, h)
+    return HS.build_scene(HS.load_fixture(os.path.join(G, "hydra_scenes.npz"), name), w, h)
 
 
 def test_fixture_describes_test_42(built):
     from hydracore_b200 import hydra_scene as HS
-    lib = HS.load_fixture(os.path.join(G, "test_42_scene.npz"))
+    assert HS.fixture_scenes(os.path.join(G, "hydra_scenes.npz")) == ["test_224_sphere", "test_42", "test_42_ggx"]
+    lib = HS.load_fixture(os.path.join(G, "hydra_scenes.npz"), "test_42")
     assert lib["meshes"][0]["idx"].shape == (25600, 3) and lib["meshes"][1]["idx"].shape == (10, 3) and lib["meshes"][5]["idx"].shape == (2, 3)
     assert len(lib["instances"]) == 3 and lib["camera"]["dof"] and abs(lib["camera"]["lens_radius"] - 0.25) < 1e-6
     assert lib["settings"]["trace_depth"] == 5 and lib["settings"]["diff_trace_depth"] == 3
     assert abs(lib["lights"][0]["color"][0] - 31.4) < 1e-4 and lib["lights"][0]["half"] == (1.0, 1.0)
-    assert abs(float(lib["light_instances"][0][1, 3]) - 3.85) < 1e-6
+    assert abs(float(lib["light_instances"][0]["matrix"][1, 3]) - 3.85) < 1e-6
     scn = _scene(64, 64)
     assert scn.bvh["inv_matrices"].shape[0] == 3 and list(scn.inst_light_ids) == [-1, -1, 0]
     ref_xml = "/root/reference/hydra_app/tests/test_42/statex_00001.xml"
@@ -32,10 +33,11 @@ def test_fixture_describes_test_42(built):
 
 
 @pytest.mark.gpu
-def test_c1_pt_and_mispt_match_reference_integrators(layer):
-    golden = np.load(os.path.join(G, "test_42_images.npz"))
-    scn = _scene(128, 128)
-    for integ, key, tol in ((0, "test_42_pt_sum4", 1e-5), (2, "test_42_mispt_sum4", 1e-4)):
+@pytest.mark.parametrize("name", ["test_42", "test_42_ggx", "test_224_sphere"])
+def test_reference_scene_libraries_match_reference_integrators(layer, name):
+    golden = np.load(os.path.join(G, "hydra_scenes_images.npz"))
+    scn = _scene(128, 128, name)
+    for integ, key, tol in ((0, name + "_pt_sum4", 1e-5), (2, name + "_mispt_sum4", 1e-4)):
         layer.LoadScene(scn)
         layer.InitPathTracing(777)
         layer.TracingPass(integ, 4)
