@@ -438,6 +438,47 @@ HC_DEV void LambertSample(const float* m, float r1, float r2, float3 n, float2 t
   out.flags = HC_RAY_EVENT_D;
 }
 
+// ---- Oren-Nayar (cmaterial.h:264-370; helpers cmatpbrt.h:17-31).  Colour / texture slots coincide with Lambert's (cmaterial.h:1912).
+#define HC_ORENNAYAR_A 16
+#define HC_ORENNAYAR_B 17
+HC_DEV float OrennayarFunc(float3 l, float3 v, float3 n, float A, float B)                 // cmaterial.h:288-334
+{
+  const float cosTheta_wi = dot(l, n), cosTheta_wo = dot(v, n);
+  const float sinTheta_wi = sqrtf(fmaxf(0.0f, 1.0f - cosTheta_wi*cosTheta_wi));
+  const float sinTheta_wo = sqrtf(fmaxf(0.0f, 1.0f - cosTheta_wo*cosTheta_wo));
+  float3 nx, ny; const float3 nz = n;
+  CoordinateSystem(nz, nx, ny);
+  const float3 wo = f3(-dot(v, nx), -dot(v, ny), -dot(v, nz));
+  const float3 wi = f3(-dot(l, nx), -dot(l, ny), -dot(l, nz));
+  float maxcos = 0.0f;
+  if ((double)sinTheta_wi > 1e-4 && (double)sinTheta_wo > 1e-4)                            // the reference compares against double literals
+  {
+    const float sinphii = (sinTheta_wi == 0.0f) ? 0.0f : clampf(wi.y/sinTheta_wi, -1.0f, 1.0f), cosphii = (sinTheta_wi == 0.0f) ? 1.0f : clampf(wi.x/sinTheta_wi, -1.0f, 1.0f);
+    const float sinphio = (sinTheta_wo == 0.0f) ? 0.0f : clampf(wo.y/sinTheta_wo, -1.0f, 1.0f), cosphio = (sinTheta_wo == 0.0f) ? 1.0f : clampf(wo.x/sinTheta_wo, -1.0f, 1.0f);
+    const float dcos = cosphii*cosphio + sinphii*sinphio;
+    maxcos = fmaxf(0.0f, dcos);
+  }
+  float sinalpha, tanbeta;
+  if (fabsf(cosTheta_wi) > fabsf(cosTheta_wo)) { sinalpha = sinTheta_wo; tanbeta = sinTheta_wi/fmaxf(fabsf(cosTheta_wi), HC_DEPSILON); }
+  else                                         { sinalpha = sinTheta_wi; tanbeta = sinTheta_wo/fmaxf(fabsf(cosTheta_wo), HC_DEPSILON); }
+  return A + B*maxcos*sinalpha*tanbeta;
+}
+HC_DEV float3 OrennayarEvalBxDF(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  return LambertColor(m, tc, s)*HC_INV_PI*OrennayarFunc(l, v, n, m[HC_ORENNAYAR_A], m[HC_ORENNAYAR_B]);
+}
+HC_DEV void OrennayarSample(const float* m, float r1, float r2, float3 rayDir, float3 n, float2 tc, const HcScene& s, HcMatSample& out)   // cmaterial.h:351-370
+{
+  const float3 color = LambertColor(m, tc, s);
+  const float3 newDir = MapSampleToCosineDistribution(r1, r2, n, n, 1.0f);
+  const float cosTheta = dot(newDir, n);
+  out.direction = newDir;
+  out.pdf = cosTheta*HC_INV_PI;
+  out.color = color*HC_INV_PI*OrennayarFunc(newDir, (-1.0f)*rayDir, n, m[HC_ORENNAYAR_A], m[HC_ORENNAYAR_B]);
+  if (cosTheta <= HC_DEPSILON) out.color = f3(0, 0, 0);
+  out.flags = HC_RAY_EVENT_D;
+}
+
 // ---- perfect mirror (cmaterial.h:385-421)
 HC_DEV void MirrorSample(const float* m, float3 rayDir, float3 n, float2 tc, const HcScene& s, HcMatSample& out)
 {
@@ -720,6 +761,7 @@ HC_DEV void LeafSample(const float* m, const HcSurfaceHit& sh, float3 rayDir, fl
     case HC_PLAIN_MAT_CLASS_PERFECT_MIRROR: MirrorSample(m, rayDir, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_GLASS:          GlassGgxSample(m, rands, rayDir, sh.normal, sh.texCoord, sh.hfi, s, out); break;
     case HC_PLAIN_MAT_CLASS_LAMBERT:        LambertSample(m, rands.x, rands.y, sh.normal, sh.texCoord, s, out); break;
+    case HC_PLAIN_MAT_CLASS_OREN_NAYAR:     OrennayarSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
     default: break;
   }
   if (out.pdf <= 0.0f) out.color = f3(0, 0, 0);
@@ -775,6 +817,8 @@ HC_DEV HcBxDF LeafEval(const float* m, float3 l, float3 v, float3 n, float2 tc, 
       r.brdf = GgxEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = Ggx2EvalPDF(m, l, v, n, tc, s); r.pdfRev = Ggx2EvalPDF(m, v, l, n, tc, s); break;
     case HC_PLAIN_MAT_CLASS_LAMBERT:
       r.brdf = LambertColor(m, tc, s)*HC_INV_PI*1.0f; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
+    case HC_PLAIN_MAT_CLASS_OREN_NAYAR:
+      r.brdf = OrennayarEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
     default: break;      // mirror and glass evaluate to zero for explicit light (cmaterial.h:396-404, 620-629)
   }
   return r;

@@ -71,7 +71,8 @@ def parse_library(xml_path, mesh_fallback_dirs=()):
         if dif is not None:
             tex = dif.find("texture")
             tex = dif.find("color/texture") if tex is None else tex
-            d["diffuse"] = dict(color=_floats(_val(dif.find("color"), "0 0 0")), tex=int(tex.get("id")) if tex is not None else 0)
+            d["diffuse"] = dict(color=_floats(_val(dif.find("color"), "0 0 0")), tex=int(tex.get("id")) if tex is not None else 0,
+                                brdf=dif.get("brdf_type", "lambert"), roughness=float(_val(dif.find("roughness"), "0")))
         if ref is not None:
             col = ref.find("color")
             d["reflect"] = dict(color=_floats(_val(col, "0 0 0")), gloss=float(_val(ref.find("glossiness"), "1")),
@@ -147,7 +148,10 @@ def build_scene(lib, width, height):
             nodes = M.emissive(tuple(d["emission"]), light_map.get(d.get("light_id", -1), -1))
         else:
             dif = d.get("diffuse", dict(color=[0, 0, 0], tex=0))
-            lam = M.lambert(tuple(dif["color"]), tex_id=tex_map.get(dif["tex"], 0))      # textures that were not shipped (dl="1") read as white
+            if dif.get("brdf", "lambert") == "orennayar":
+                lam = M.orennayar(tuple(dif["color"]), dif.get("roughness", 0.0), tex_id=tex_map.get(dif["tex"], 0))
+            else:
+                lam = M.lambert(tuple(dif["color"]), tex_id=tex_map.get(dif["tex"], 0))  # textures that were not shipped (dl="1") read as white
             if "reflect" in d and max(d["reflect"]["color"]) > 1e-5:
                 r = d["reflect"]
                 top = (M.ggx if r["brdf"] == "ggx" else M.phong)(tuple(r["color"]), r["gloss"])

@@ -55,6 +55,19 @@ def lambert(color, tex_id=0, **kw):
     return m
 
 
+def orennayar(color, roughness, tex_id=0, **kw):
+    """Oren-Nayar diffuse (OrenNayarMaterial, PlainMaterialConverter.cpp:142-170): sigma = roughness*pi/2, A and B precomputed in float."""
+    m = _node(C["PLAIN_MAT_CLASS_OREN_NAYAR"], C["PLAIN_MATERIAL_HAS_DIFFUSE"])
+    _color_slot(m, color, tex_id, C["LAMBERT_TEXID_OFFSET"], C["LAMBERT_TEXMATRIXID_OFFSET"], C["LAMBERT_SAMPLER0"], **kw)
+    f = np.float32
+    sigma = f(f(roughness)*f(np.float64(3.14159265358979323846)/2.0))        # M_PI is the <cmath> double in the reference's host build; /2.0f in double, product in float
+    sigma2 = f(sigma*sigma)
+    m[15] = f(roughness)                                                      # ORENNAYAR_ROUGHNESS
+    m[16] = f(f(1.0) - f(sigma2/f(f(2.0)*f(sigma2 + f(0.33)))))               # ORENNAYAR_A
+    m[17] = f(f(f(0.45)*sigma2)/f(sigma2 + f(0.09)))                          # ORENNAYAR_B
+    return m
+
+
 def _glossy(mat_type, color, gloss, tex_id, flags, **kw):
     m = _node(mat_type, flags)
     _color_slot(m, color, tex_id, C["PHONG_TEXID_OFFSET"], C["PHONG_TEXMATRIXID_OFFSET"], C["PHONG_SAMPLER0_OFFSET"], **kw)

@@ -99,6 +99,34 @@ def cornell(width=128, height=128, trace_depth=5, two_lights=False, dof=False, t
     return scn.build()
 
 
+def cornell_orennayar(width=96, height=96):
+    """Cornell room with Oren-Nayar walls / balls (roughness 0.3, 0.8, 1.0, one of them textured), a GGX box and one rect area light."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    img = np.zeros((16, 16, 4), np.uint8)
+    yy, xx = np.mgrid[0:16, 0:16]
+    img[..., 0] = 80 + 150*(((xx//2) + (yy//2)) % 2)
+    img[..., 1] = 200
+    img[..., 2] = 90
+    img[..., 3] = 255
+    tex = scn.add_texture_rgba8(img)
+    white = scn.add_material(M.orennayar((0.73, 0.73, 0.73), 0.8))
+    red = scn.add_material(M.orennayar((0.65, 0.05, 0.05), 0.3))
+    green = scn.add_material(M.orennayar((0.12, 0.45, 0.15), 1.0))
+    floor = scn.add_material(M.orennayar((0.9, 0.9, 0.9), 0.5, tex_id=tex))
+    ball = scn.add_material(M.orennayar((0.3, 0.4, 0.9), 0.9))
+    ggxm = scn.add_material(M.ggx((0.8, 0.6, 0.2), 0.7))
+    emi = scn.add_material(M.emissive((17.0, 15.0, 12.0), 0))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, floor, white, white), inward=True, skip_faces=(4,))))
+    sph = S.sphere_mesh(1.0, 32, 16)
+    scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, ball, np.int32))), S.translate(-1.5, -2.6, 0.5) @ S.scale(1.4, 1.4, 1.4))
+    scn.add_instance(scn.add_mesh(S.box_mesh(0.9, 1.6, 0.9, mat_ids=(ggxm,)*6, inward=False)), S.translate(2.0, -2.4, -1.5) @ S.rotate_y(0.4))
+    l0 = scn.add_light(M.area_light((0.0, 3.95, 0.0), (1.0, 1.0), (17.0, 15.0, 12.0)))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l0)
+    return scn.build()
+
+
 def cornell_sphere_and_point_lights(width=96, height=96):
     """The Cornell room lit by a sphere area light (with its emissive mesh, so that paths can hit it) and an omni point light."""
     from hydracore_b200 import materials as M
