@@ -143,8 +143,14 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
     float3 curr = f3(0, 0, 0);
     bool finished = false;
 
-    if (hit.primId == -1 || !isfinite(hit.t))                     // HitNone (cglobals.h:1270) -> environmentColor: no sky light -> black
+    if (hit.primId == -1 || !isfinite(hit.t))                     // HitNone (cglobals.h:1270) -> environmentColor (black without a sky light)
+    {
+      // IntegratorStupidPT: the initial MisData at depth 0, a value-initialised MisData() (pdf 0, not specular, material offset 0) deeper
+      // (CPUExp_Integrators_PT.cpp:9-38); the MISPT loop carries the real MisData with prevMaterialOffset = -1
+      if (isPT) curr = (pp.depth == 0) ? EnvironmentColor(s, rayDir, 1.0f, true, -1, flags) : EnvironmentColor(s, rayDir, 0.0f, false, 0, flags);
+      else      curr = EnvironmentColor(s, rayDir, prevPdf, prevSpecular, -1, flags);
       finished = true;
+    }
     else
     {
       const HcSurfaceHit sh = SurfaceEval(s, rayPos, rayDir, hit);
@@ -182,7 +188,7 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
           {
             const float* L = LightAt(s, lightOffset);
             HcShadowSample sam;
-            LightSampleRev(L, f3(rl.x, rl.y, rl.z), sh.pos, sam);
+            LightSampleRev(L, f3(rl.x, rl.y, rl.z), sh.pos, s, sam);
             const float3 sdir = normalize(sam.pos - sh.pos);
             const float3 spos = OffsShadowRayPos(sh.pos, sh.normal, sdir, sh.sRayOff);
             const float tFar = length(spos - sam.pos)*0.995f;
@@ -454,7 +460,6 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
 {
   const unsigned char* g = ctx->globalsHead.data();
   auto gi = [&](int off) { int v; memcpy(&v, g + off, 4); return v; };
-  if (gi(HC_EG_skyLightId) != -1) { why = "sky-dome lights are not supported yet"; return HC_E_ARG; }
   if (gi(HC_EG_sunNumber) != 0) { why = "sun lights are not supported yet"; return HC_E_ARG; }
   HcPathHost* p = PH(ctx);
   const std::vector<unsigned char>& gl = p->globalsHost;
@@ -464,6 +469,14 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
     const float* L = reinterpret_cast<const float*>(gl.data()) + lightsOffset + l*HC_LIGHT_DATA_SIZE;
     int type, flags, tex, spot; memcpy(&type, L + HC_PLIGHT_TYPE, 4); memcpy(&flags, L + HC_PLIGHT_FLAGS, 4);
     memcpy(&tex, L + HC_PLIGHT_COLOR_TEX, 4); memcpy(&spot, L + HC_AREA_LIGHT_SPOT_DISTR, 4);
+    if (type == HC_PLAIN_LIGHT_TYPE_SKY_DOME)
+    {
+      int tab, aux; memcpy(&tab, L + 30, 4); memcpy(&aux, L + 20, 4);                  // SKY_DOME_PDF_TABLE0, SKY_DOME_COLOR_TEX_AUX (clight.h:138, 153)
+      if (flags & 1) { why = "Perez sky model (SKY_LIGHT_USE_PEREZ_ENVIRONMENT) is not supported yet"; return HC_E_ARG; }
+      if (l != gi(HC_EG_skyLightId)) { why = "more than one sky-dome light"; return HC_E_ARG; }
+      if (!ctx->storage[HC_STORAGE_PDFS].ptr || tab < 0 || tab >= gi(HC_EG_pdfTableTableSize)) { why = "sky-dome light without a pdf table in the pdfs storage"; return HC_E_ARG; }
+      continue;
+    }
     if (type == HC_PLAIN_LIGHT_TYPE_SPHERE || type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI)
     {
       if (flags & HC_LIGHT_HAS_IES) { why = "IES distributions are not supported yet"; return HC_E_ARG; }
@@ -523,6 +536,8 @@ static HcScene MakeScene(hc_ctx* ctx)
   s.geom = (const float4*)ctx->storage[HC_STORAGE_GEOM].ptr;
   s.materials = (const float4*)ctx->storage[HC_STORAGE_MATERIALS].ptr;
   s.textures = (const int4*)ctx->storage[HC_STORAGE_TEXTURES].ptr;
+  s.pdfs = (const float4*)ctx->storage[HC_STORAGE_PDFS].ptr;
+  s.pdfTableTableOffset = gi(HC_EG_pdfTableTableOffset);
   s.instMatrices = (const float4*)ctx->instMatrices.ptr;
   s.instLightIds = (const int*)ctx->instLightIds.ptr;
   s.materialsTableOffset = gi(HC_EG_materialsTableOffset); s.geometryTableOffset = gi(HC_EG_geometryTableOffset);
@@ -631,7 +646,8 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   if (n <= 0) return HC_OK;
   int rc = ReserveState(ctx, n, qmc); if (rc) return rc;
   p = PH(ctx);
-  const HcScene scn = MakeScene(ctx);
+  HcScene scn = MakeScene(ctx);
+  if (integrator == HC_INTEGRATOR_PT) scn.gflags |= HC_HRT_STUPID_PT_MODE;          // IntegratorStupidPT::DoPass sets it in g_flags (CPUExp_Integrators.h:326-330)
   const HcCamera cam = hc_camera_from_globals(ctx->globalsHead.data());
   HcPassParams pp;
   pp.integrator = integrator; pp.width = W; pp.height = H; pp.world = ctx->worldSize; pp.rank = ctx->rank;

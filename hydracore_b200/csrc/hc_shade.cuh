@@ -30,9 +30,10 @@ struct HcScene
   const float4* __restrict__ geom;          // "geom" storage
   const float4* __restrict__ materials;     // "materials" storage
   const int4*   __restrict__ textures;      // "textures" storage
+  const float4* __restrict__ pdfs;          // "pdfs" storage (sky-dome pdf tables)
   const float4* __restrict__ instMatrices;  // inverse instance matrices, 4 float4 each
   const int*    __restrict__ instLightIds;  // instance -> light index or -1
-  int materialsTableOffset, geometryTableOffset, texturesTableOffset;
+  int materialsTableOffset, geometryTableOffset, texturesTableOffset, pdfTableTableOffset;
   int lightSelTableOffsetRev, lightSelTableSizeRev, lightsOffset, lightsNum, skyLightId;
   int gflags, traceDepth, diffTraceDepth;
   int essGgxTableOffsetBytes;
@@ -878,12 +879,8 @@ HC_DEV float3 MaterialEvalEmission(const float* mat, float3 v, float3 n, float2 
 
 // ------------------------------------------------------------------------------------------------------------------ a11/a12: lights
 // SelectRandomLightRev + SelectIndexPropToOpt (clight.h:1774-1793, cglobals.h:2806-2862)
-HC_DEV int SelectRandomLightRev(float r, const HcScene& s, float& pickProb)
+HC_DEV int SelectIndexPropToOpt(float r, const float* __restrict__ acc, int N, float& pdf)          // cglobals.h:2806-2862
 {
-  const int N = s.lightSelTableSizeRev;
-  if (N == 0) { pickProb = 1.0f; return -1; }
-  if (N <= 2) { pickProb = 1.0f; return 0; }
-  const float* acc = reinterpret_cast<const float*>(s.globals + s.lightSelTableOffsetRev);
   int left = 0, right = N - 2, counter = 0, cur = -1;
   const float x = r*acc[N - 1];
   while (right - left > 1 && counter < 50)
@@ -904,8 +901,16 @@ HC_DEV int SelectRandomLightRev(float r, const HcScene& s, float& pickProb)
   }
   if (x == 0.0f) cur = 0;
   else if (cur < 0) cur = (right + left + 1)/2;
-  pickProb = (acc[cur + 1] - acc[cur])/acc[N - 1];
+  pdf = (acc[cur + 1] - acc[cur])/acc[N - 1];
   return cur;
+}
+
+HC_DEV int SelectRandomLightRev(float r, const HcScene& s, float& pickProb)
+{
+  const int N = s.lightSelTableSizeRev;
+  if (N == 0) { pickProb = 1.0f; return -1; }
+  if (N <= 2) { pickProb = 1.0f; return 0; }
+  return SelectIndexPropToOpt(r, reinterpret_cast<const float*>(s.globals + s.lightSelTableOffsetRev), N, pickProb);
 }
 
 HC_DEV float AreaLightEvalPDF(const float* L, float3 rayDir, float hitDist)             // areaDiffuseLightEvalPDF, clight.h:524-530 ; PdfAtoW cglobals.h:1754
@@ -996,11 +1001,131 @@ HC_DEV void PointLightSampleRev(const float* L, float3 illum, HcShadowSample& ou
   out.cosAtLight = 1.0f;
 }
 
+// ---- sky dome (clight.h:286-463, cfetch.h:258-296, cbidir.h:492-533), without the Perez model and without a secondary (AUX) sky.
+// M_PI is the <cmath> double in the reference's host build; sin / cos / acos / atan2 resolve to the double functions (hc_math.cuh).
+#define HC_SKY_DOME_PDF_TABLE0  30
+#define HC_SKY_DOME_SAMPLER0    32
+#define HC_SKY_DOME_MATRIX0     36
+#define HC_SKY_DOME_INV_MATRIX0 56
+#define HC_M_PI_D 3.14159265358979323846
+HC_DEV float2 SphereMapTo2DTexCoord(float3 rayDir, float& sinTheta)                                                          // cfetch.h:258-281
+{
+  const float x = rayDir.z, y = rayDir.x, z = -rayDir.y;
+  const float theta = hc_acos(z);
+  float phi = hc_atan2(y, x);
+  if (phi < 0.0f) phi = (float)((double)phi + 2.0*HC_M_PI_D);                                // phi += 2.0f*M_PI
+  const float texX = clampf(phi*0.5f*HC_INV_PI, 0.0f, 1.0f);
+  const float texY = clampf(theta*HC_INV_PI, 0.0f, 1.0f);
+  sinTheta = sqrtf(1.0f - rayDir.y*rayDir.y);
+  return f2(texX, texY);
+}
+HC_DEV float3 TexCoord2DToSphereMap(float2 tc, float& sinThetaOut)                                                            // cfetch.h:283-296
+{
+  const float phi   = (float)((double)(tc.x*2.0f)*HC_M_PI_D);
+  const float theta = (float)((double)tc.y*HC_M_PI_D);
+  const float sinTheta = hc_sin(theta);
+  const float x = (float)((double)sinTheta*cos((double)phi));
+  const float y = (float)((double)sinTheta*sin((double)phi));
+  const float z = hc_cos(theta);
+  sinThetaOut = sinTheta;
+  return f3(y, -z, x);
+}
+HC_DEV const float* PdfTableHeader(int tableId, const HcScene& s)                                                              // cfetch.h:153-163
+{
+  const int offset = s.globals[s.pdfTableTableOffset + tableId];
+  return reinterpret_cast<const float*>(s.pdfs + offset);
+}
+HC_DEV float3 SkyLightIntensityTexturedEnv(const float* L, float3 dir, const HcScene& s)                                       // clight.h:292-307
+{
+  float sintheta = 0.0f;
+  const float2 tc = SphereMapTo2DTexCoord(dir, sintheta);
+  const float3 texColor = Sample2D(__float_as_int(L[HC_PLIGHT_COLOR_TEX_MATRIX]), tc, L + HC_SKY_DOME_SAMPLER0, s);
+  return Mat3(L, HC_PLIGHT_COLOR_X)*texColor;
+}
+HC_DEV float EvalMap2DPdf(float2 t, const float* __restrict__ intervals, int sizeX, int sizeY)                                 // clight.h:309-337 (quirks included)
+{
+  const float fw = (float)sizeX, fh = (float)sizeY;
+  if (t.x < 0.0f || t.x > 1.0f) t.x -= (float)((int)(t.x));
+  if (t.y < 0.0f || t.x > 1.0f) t.y -= (float)((int)(t.y));
+  int pixelX = (int)(fw*t.x - 0.5f), pixelY = (int)(fh*t.y - 0.5f);
+  if (pixelX >= sizeX) pixelX = sizeX - 1;
+  if (pixelY >= sizeY) pixelY = sizeY - 1;
+  if (pixelX < 0) pixelX += sizeX;
+  if (pixelY < 0) pixelY += sizeY;
+  const int pixelOffset = pixelY*sizeX + pixelX, maxSize = sizeX*sizeY;
+  const int offset0 = (pixelOffset + 0 < maxSize + 0) ? pixelOffset + 0 : maxSize - 1;
+  const int offset1 = (pixelOffset + 1 < maxSize + 1) ? pixelOffset + 1 : maxSize;
+  return (intervals[offset1] - intervals[offset0])*(fw*fh)/intervals[sizeX*sizeY];
+}
+HC_DEV float SkyLightEvalPDF(const float* L, float3 rayDir, const HcScene& s)                                                   // clight.h:339-363
+{
+  const float* hdr = PdfTableHeader(__float_as_int(L[HC_SKY_DOME_PDF_TABLE0]), s);
+  const float* intervals = hdr + 4;
+  const int sizeX = __float_as_int(hdr[0]), sizeY = __float_as_int(hdr[1]);
+  float sintheta = 0.0f;
+  const float2 tc = SphereMapTo2DTexCoord(rayDir, sintheta);
+  if (sintheta == 0.0f) return 0.0f;
+  const float4 row0 = *reinterpret_cast<const float4*>(L + HC_SKY_DOME_MATRIX0), row1 = *reinterpret_cast<const float4*>(L + HC_SKY_DOME_MATRIX0 + 4);
+  const float2 tct = f2(row0.x*tc.x + row0.y*tc.y + row0.w, row1.x*tc.x + row1.y*tc.y + row1.w);
+  const float mapPdf = EvalMap2DPdf(tct, intervals, sizeX, sizeY);
+  return (float)((double)(mapPdf*1.0f)/((double)2.0f*HC_M_PI_D*HC_M_PI_D*(double)fmaxf(fabsf(sintheta), HC_DEPSILON)));
+}
+HC_DEV void SkyLightSampleRev(const float* L, float3 rands, float3 illum, const HcScene& s, HcShadowSample& out)                // clight.h:427-463
+{
+  const float* hdr = PdfTableHeader(__float_as_int(L[HC_SKY_DOME_PDF_TABLE0]), s);
+  const float* intervals = hdr + 4;
+  const int sizeX = __float_as_int(hdr[0]), sizeY = __float_as_int(hdr[1]);
+  const float fw = (float)sizeX, fh = (float)sizeY, fN = fw*fh;
+  float pdf = 1.0f;                                                                          // sampleMap2D, clight.h:375-396
+  int pixelOffset = SelectIndexPropToOpt(rands.z, intervals, sizeX*sizeY + 1, pdf);
+  if (pixelOffset >= sizeX*sizeY) pixelOffset = sizeX*sizeY - 1;
+  const int yPos = pixelOffset/sizeX, xPos = pixelOffset - yPos*sizeX;
+  const float texX = (1.0f/fw)*(((float)(xPos) + 0.5f) + (rands.x*2.0f - 1.0f)*0.5f);
+  const float texY = (1.0f/fh)*(((float)(yPos) + 0.5f) + (rands.y*2.0f - 1.0f)*0.5f);
+  const float mapPdf = pdf*fN;
+  const HcMat4 m = loadMat4(L + HC_SKY_DOME_INV_MATRIX0);
+  const float3 tct = mul4x3(m, f3(texX, texY, 0.0f));                                        // mul(float4x4, float3) = mul4x3
+  float sintheta = 0.0f;
+  const float3 sampleDir = TexCoord2DToSphereMap(f2(tct.x, tct.y), sintheta);
+  const float radius = reinterpret_cast<const float*>(s.globals)[HC_EG_varsF/4 + 21];        // varsF[HRT_BSPHERE_RADIUS]
+  const float3 samplePos = illum + sampleDir*radius;
+  const float3 txClr = Sample2D(__float_as_int(L[HC_PLIGHT_COLOR_TEX_MATRIX]), f2(tct.x, tct.y), L + HC_SKY_DOME_SAMPLER0, s);
+  out.isPoint = false;
+  out.pos = samplePos;
+  out.color = Mat3(L, HC_PLIGHT_COLOR_X)*txClr;
+  out.pdf = (float)((double)(mapPdf*1.0f)/((double)2.0f*HC_M_PI_D*HC_M_PI_D*(double)fmaxf(fabsf(sintheta), HC_DEPSILON)));
+  out.maxDist = length(illum - samplePos);
+  out.cosAtLight = 1.0f;                                                                     // not written by the reference for sky lights; unused by the MISPT loop
+}
+// environmentColor (cbidir.h:492-533).  prevMaterialOffset: the MISPT integrators never set it (-1 from makeInitialMisData, cglobals.h:1391-1399);
+// IntegratorStupidPT recurses with a value-initialised MisData() (CPUExp_Integrators_PT.cpp:37), i.e. offset 0 = the first material node.
+HC_DEV float3 EnvironmentColor(const HcScene& s, float3 rayDir, float prevPdf, bool prevSpecular, int prevMaterialOffset, unsigned flags)
+{
+  if (s.skyLightId == -1) return f3(0, 0, 0);
+  const unsigned rayBounceNum = (flags & 0x0000FF00u) >> 8, diffBounceNum = flags & 0xFFu;
+  const float* L = LightAt(s, s.skyLightId);
+  float3 envColor = SkyLightIntensityTexturedEnv(L, rayDir, s);
+  if (rayBounceNum > 0 && !(s.gflags & HC_HRT_STUPID_PT_MODE) && !prevSpecular)
+  {
+    const float lgtPdf = L[HC_PLIGHT_PICK_PROB_REV]*SkyLightEvalPDF(L, rayDir, s);
+    envColor *= misWeightHeuristic(prevPdf, lgtPdf);
+  }
+  if (prevMaterialOffset >= 0)
+  {
+    const float* prevMat = reinterpret_cast<const float*>(s.materials + prevMaterialOffset);
+    const bool disableCaustics = (diffBounceNum > 0) && !(s.gflags & HC_HRT_ENABLE_PT_CAUSTICS) &&
+                                 ((MatI(prevMat, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_CAST_CAUSTICS) != 0);
+    if (disableCaustics) envColor = f3(0, 0, 0);
+  }
+  return envColor;
+}
+
 // LightSampleRev / lightEvalPDF dispatch (clight.h:1561-1633) over the light types hc_pt_init accepts
-HC_DEV void LightSampleRev(const float* L, float3 rands, float3 illum, HcShadowSample& out)
+HC_DEV void LightSampleRev(const float* L, float3 rands, float3 illum, const HcScene& s, HcShadowSample& out)
 {
   const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
-  if (type == HC_PLAIN_LIGHT_TYPE_SPHERE) SphereLightSampleRev(L, rands, illum, out);
+  if (type == HC_PLAIN_LIGHT_TYPE_SKY_DOME) SkyLightSampleRev(L, rands, illum, s, out);
+  else if (type == HC_PLAIN_LIGHT_TYPE_SPHERE) SphereLightSampleRev(L, rands, illum, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI) PointLightSampleRev(L, illum, out);
   else AreaLightSampleRev(L, rands, illum, out);
 }

@@ -198,3 +198,35 @@ def point_light(pos, intensity, pick_prob=1.0):
     L[C["PLIGHT_PICK_PROB_FWD"]] = pick_prob
     L[C["PLIGHT_PICK_PROB_REV"]] = pick_prob
     return L
+
+
+def sky_light(color, pdf_table_id, pick_prob=1.0):
+    """Sky-dome light without texture / Perez model (SkyDomeLight, PlainLightConverter.cpp:909-1060): identity sampler matrices, the pdf table
+    built by Scene.add_sky_pdf_table."""
+    L = np.zeros(128, np.float32)
+    Li = L.view(np.int32)
+    Li[C["PLIGHT_TYPE"]] = C["PLAIN_LIGHT_TYPE_SKY_DOME"]
+    Li[C["PLIGHT_FLAGS"]] = 0
+    L[C["PLIGHT_COLOR_X"]:C["PLIGHT_COLOR_X"] + 3] = color
+    Li[C["PLIGHT_COLOR_TEX"]] = INVALID_TEXTURE
+    Li[C["PLIGHT_COLOR_TEX_MATRIX"]] = INVALID_TEXTURE
+    L[17:20] = color                                  # SKY_DOME_COLOR_AUX_X..Z
+    Li[20] = INVALID_TEXTURE                          # SKY_DOME_COLOR_TEX_AUX
+    Li[21] = INVALID_TEXTURE                          # SKY_DOME_COLOR_TEX_MATRIX_AUX
+    Li[22] = INVALID_TEXTURE                          # SKY_DOME_AUX_TEX_MATRIX_INV
+    L[23:26] = (0.0, -1.0, 0.0)                       # SKY_DOME_SUN_DIR
+    Li[30] = pdf_table_id                             # SKY_DOME_PDF_TABLE0
+    Li[31] = pdf_table_id                             # SKY_DOME_PDF_TABLE1
+    for base in (32, 44):                             # SKY_DOME_SAMPLER0 / SAMPLER1: {flags, gamma, texId, dummy} + row0 + row1
+        Li[base + 0] = 0
+        L[base + 1] = 1.0
+        Li[base + 2] = INVALID_TEXTURE
+        L[base + 4:base + 8] = (1, 0, 0, 0)
+        L[base + 8:base + 12] = (0, 1, 0, 0)
+    for base in (56, 72):                             # SKY_DOME_INV_MATRIX0 / 1: identity float4x4 (columns)
+        L[base:base + 16] = np.eye(4, dtype=np.float32).reshape(16)
+    Li[88] = -1                                       # SKY_DOME_SUN_DIR_ID
+    L[C["PLIGHT_PROB_MULT"]] = 1.0
+    L[C["PLIGHT_PICK_PROB_FWD"]] = pick_prob
+    L[C["PLIGHT_PICK_PROB_REV"]] = pick_prob
+    return L

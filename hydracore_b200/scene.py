@@ -288,6 +288,7 @@ class Scene:
         self.material_ids = []    # matId -> index of its head node in self.materials
         self.lights = []          # list of 128-float PlainLight
         self.textures = []        # list of (w, h, rgba8 ndarray) ; texture id 0 is reserved ("no texture")
+        self.pdf_tables = []      # list of float32 arrays {as_float(w), as_float(h), as_float(1), as_float(n+1), prefix sums..., 1.0} (sky-dome lights)
         self.varsI = np.zeros(64, np.int32)
         self.varsF = np.zeros(64, np.float32)
         self.flags = 0
@@ -323,6 +324,24 @@ class Scene:
     def add_light(self, plain_light):
         self.lights.append(np.ascontiguousarray(plain_light, np.float32).reshape(128))
         return len(self.lights) - 1
+
+    def add_sky_pdf_table(self, lum=None):
+        """Pdf table of a sky-dome light as RenderDriverRTE::UpdatePdfTablesForLight builds it (RenderDriverRTE_PdfTables.cpp:520-566): prefix sums of
+        the luminance image (2x2 of 0.25 for an untextured sky); returns the table id to put into SKY_DOME_PDF_TABLE0."""
+        lum = np.full((2, 2), 0.25, np.float32) if lum is None else np.ascontiguousarray(lum, np.float32)
+        h, w = lum.shape
+        pref = np.zeros(w*h + 1, np.float32)
+        acc = np.float32(0)
+        for i, v in enumerate(lum.reshape(-1)):
+            pref[i] = acc
+            acc = np.float32(acc + v)
+        pref[w*h] = acc
+        data = np.zeros(pref.size + 5, np.float32)
+        data[0:4] = np.array([w, h, 1, pref.size + 1], np.int32).view(np.float32)
+        data[4:4 + pref.size] = pref
+        data[-1] = 1.0
+        self.pdf_tables.append(data)
+        return len(self.pdf_tables) - 1
 
     def add_texture_rgba8(self, rgba):
         """Texture ids start at 1; id 0 means "white" (sample2D, cfetch.h:654-655)."""
@@ -368,11 +387,23 @@ class Scene:
         for (mid, mat, _l) in self.instances:
             bb.add_instance(mid, mat)
         self.bvh = bb.commit()
+        lo, hi = bb.bounds()
         bb.close()
+        half = np.float32(0.5)*(hi - lo)                     # scene bounding sphere, RenderDriverRTE.cpp:1461-1467
+        self.bsphere = np.concatenate([np.float32(0.5)*(hi + lo), [np.sqrt((half*half).sum(dtype=np.float32), dtype=np.float32)]]).astype(np.float32)
         self.inst_light_ids = np.array([l for (_m, _x, l) in self.instances], np.int32)
 
+        # pdfs storage: tables padded to 16 bytes, pdfTableTable[id] -> float4 offset
+        pdf_chunks, self._pdf_table_offsets, off = [], [], 0
+        for t in self.pdf_tables:
+            b = t.view(np.uint8)
+            pad = (-b.size) % 16
+            self._pdf_table_offsets.append(off//16)
+            pdf_chunks.append(np.concatenate([b, np.zeros(pad, np.uint8)]))
+            off += b.size + pad
+        pdfs = np.concatenate(pdf_chunks) if pdf_chunks else np.zeros(16, np.uint8)
         self.storages = dict(textures=textures, textures_aux=np.zeros(16, np.uint8), geom=geom, materials=mats.view(np.uint8).reshape(-1),
-                             pdfs=np.zeros(16, np.uint8))
+                             pdfs=pdfs)
         self.globals_blob = self._pack_globals(geom_table, mat_table, tex_table)
         return self
 
@@ -383,7 +414,7 @@ class Scene:
         cam = self.camera
         nl = len(self.lights)
         sizes = dict(materials=len(mat_table), geometry=len(geom_table), textures=len(tex_table), texturesAux=len(tex_table),
-                     pdfTable=max(nl, 1), lselRev=(nl + 1 if nl > 0 else 0), lselFwd=(nl + 1 if nl > 0 else 0), floats=0, lights=nl*128)
+                     pdfTable=max(nl, 1, len(self.pdf_tables)), lselRev=(nl + 1 if nl > 0 else 0), lselFwd=(nl + 1 if nl > 0 else 0), floats=0, lights=nl*128)
         cur = _round_blocks(C["EG_sizeof"]//4, 16)
         offs = {}
         for k in ("materials", "geometry", "textures", "texturesAux", "pdfTable", "lselRev", "lselFwd", "floats", "lights"):
@@ -417,6 +448,7 @@ class Scene:
         varsF[C["HRT_DOF_FOCAL_PLANE_DIST"]] = np.linalg.norm(np.asarray(cam.pos, np.float64) - np.asarray(cam.look_at, np.float64))
         varsI[C["HRT_ENABLE_DOF"]] = 1 if cam.dof else 0
         varsF[C["HRT_DOF_LENS_RADIUS"]] = cam.lens_radius if cam.dof else 0.0
+        varsF[18:22] = self.bsphere                                     # HRT_BSPHERE_CENTER_X..Z, HRT_BSPHERE_RADIUS (RenderDriverRTE.cpp:1483-1486)
         blob[C["EG_varsI"]//4:C["EG_varsI"]//4 + 64] = varsI
         put_f(C["EG_varsF"], varsF)
 
@@ -454,7 +486,8 @@ class Scene:
         put_i(C["EG_floatArraysOffset"], offs["floats"])
         put_i(C["EG_floatsArraysSize"], 0)
         put_i(C["EG_g_flags"], self.flags)
-        put_i(C["EG_skyLightId"], -1)
+        sky = [i for i, L in enumerate(self.lights) if int(L[C["PLIGHT_TYPE"]:C["PLIGHT_TYPE"] + 1].view(np.int32)[0]) == C["PLAIN_LIGHT_TYPE_SKY_DOME"]]
+        put_i(C["EG_skyLightId"], sky[0] if sky else -1)    # SetAllPODLights, IHWLayerDataAssembler.cpp:404-416
         put_i(C["EG_lightsOffset"], offs["lights"])
         put_i(C["EG_lightsSize"], nl*128)
         put_i(C["EG_lightsNum"], nl)
@@ -470,6 +503,8 @@ class Scene:
         blob[offs["textures"]:offs["textures"] + len(tex_table)] = tex_table
         blob[offs["texturesAux"]:offs["texturesAux"] + len(tex_table)] = -1
         blob[offs["pdfTable"]:offs["pdfTable"] + sizes["pdfTable"]] = -1
+        for i, o in enumerate(getattr(self, "_pdf_table_offsets", [])):
+            blob[offs["pdfTable"] + i] = o
         if nl > 0:
             # light selection table = prefix sums of pick probabilities, N = lights+1 entries (RenderDriverRTE.cpp:1499-1521, clight.h:1774-1793)
             lights = np.stack(self.lights).astype(np.float32)

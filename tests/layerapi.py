@@ -180,6 +180,8 @@ def load_scene_like_render_driver(lay, scn, consts):
         body = t.reshape(-1)
         chunk = np.concatenate([np.array([w, h, 4, 4], np.int32).view(np.uint8), body])
         lay.StorageUpdate("textures", k + 1, chunk)
+    for k, t in enumerate(getattr(scn, "pdf_tables", [])):
+        lay.StorageUpdate("pdfs", k, t)
     lay.SetAllBVH4(scn.bvh["nodes"], scn.bvh["tris"])
     lay.SetAllInstances(scn.bvh["inv_matrices"], scn.inst_light_ids)
     cam = scn.camera
@@ -193,6 +195,7 @@ def load_scene_like_render_driver(lay, scn, consts):
     varsF[C["HRT_DOF_FOCAL_PLANE_DIST"]] = np.linalg.norm(np.asarray(cam.pos, np.float64) - np.asarray(cam.look_at, np.float64))
     varsI[C["HRT_ENABLE_DOF"]] = 1 if cam.dof else 0
     varsF[C["HRT_DOF_LENS_RADIUS"]] = cam.lens_radius if cam.dof else 0.0
+    varsF[18:22] = scn.bsphere                       # HRT_BSPHERE_* (RenderDriverRTE.cpp:1483-1486)
     lay.SetAllFlagsAndVars(varsI, varsF, scn.flags | C["HRT_UNIFIED_IMAGE_SAMPLING"])
     lay.SetCamMatrices(S._cols(np.linalg.inv(proj)), S._cols(np.linalg.inv(view)), S._cols(proj), S._cols(view), aspect, float(fov_rad), cam.look_at)
     if nl > 0:

@@ -147,3 +147,28 @@ def cornell_sphere_and_point_lights(width=96, height=96):
     scn.add_instance(scn.add_mesh(lm), S.translate(0.5, 2.4, 0.0) @ S.scale(0.6, 0.6, 0.6), light_id=l0)
     scn.add_light(M.point_light((-2.5, 1.0, 3.0), (25.0, 35.0, 50.0)))
     return scn.build()
+
+
+def open_box_under_sky(width=96, height=96, with_area_light=True):
+    """Objects on a floor under a uniform sky-dome light (plus, optionally, a rect area light): rays that leave the scene pick up the
+    environment colour with MIS, the sky is sampled through its pdf table."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 2.0, 12.0), look_at=(0, -1.0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    grey = scn.add_material(M.lambert((0.6, 0.6, 0.6)))
+    red = scn.add_material(M.lambert((0.65, 0.1, 0.1)))
+    ggxm = scn.add_material(M.ggx((0.8, 0.6, 0.2), 0.7))
+    gls = scn.add_material(M.glass((0.95, 0.98, 0.95), ior=1.5, gloss=1.0))
+    mir = scn.add_material(M.mirror((0.9, 0.9, 0.9)))
+    emi = scn.add_material(M.emissive((12.0, 11.0, 9.0), 1))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(8.0, 8.0, y=0.0, mat_id=grey)), S.translate(0.0, -4.0, 0.0))
+    sph = S.sphere_mesh(1.0, 32, 16)
+    for mat, mtx in ((ggxm, S.translate(-2.4, -2.8, 0.0) @ S.scale(1.2, 1.2, 1.2)), (gls, S.translate(0.0, -2.9, 1.5) @ S.scale(1.1, 1.1, 1.1)),
+                     (mir, S.translate(2.5, -2.7, -0.5) @ S.scale(1.3, 1.3, 1.3)), (red, S.translate(0.3, -3.2, -2.5) @ S.scale(0.8, 0.8, 0.8))):
+        scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, mat, np.int32))), mtx)
+    tab = scn.add_sky_pdf_table()
+    scn.add_light(M.sky_light((0.9, 1.0, 1.3), tab))
+    if with_area_light:
+        l1 = scn.add_light(M.area_light((0.0, 3.5, 0.0), (1.0, 1.0), (12.0, 11.0, 9.0)))
+        scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)), S.translate(0.0, 3.5, 0.0), light_id=l1)
+    return scn.build()

@@ -148,3 +148,17 @@ def test_memory_storage_cuda_contract(consts):
     with pytest.raises(layerapi.LayerError):
         lay.CreateMemStorage("no_such_storage", 64)
     lay.close()
+
+
+def test_ihwlayer_sky_dome_scene_equals_c_abi_path(consts, layer):
+    """A scene with a sky-dome light (pdf table in the "pdfs" storage, skyLightId found by the reference's SetAllPODLights) through IHWLayer."""
+    scn = scenes.open_box_under_sky(64, 64, True)
+    lay = _make(scn, consts)
+    lay.InitPathTracing(9)
+    lay.TracingPasses(2)
+    a = lay.GetHDRImage()
+    layer.LoadScene(scn)
+    layer.InitPathTracing(9)
+    layer.TracingPass(2, 2)
+    assert a[..., :3].mean() > 0.1 and np.array_equal(a, layer.GetHDRImage())
+    lay.close()
