@@ -100,7 +100,7 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
       bool wantQ = !(r.node & HC_LEAF_BIT);                                        // a finished / idle lane carries the sentinel (leaf bit set)
       bool wantL = !wantQ && r.node != HC_NODE_SENTINEL;
       unsigned mQ = __ballot_sync(FULL, wantQ), mL = __ballot_sync(FULL, wantL);
-      while (mQ != 0u && __popc(mQ) >= __popc(mL))
+      while (mQ != 0u && 2*__popc(mQ) >= __popc(mL))      // quad steps keep going until the leaf lanes outnumber them 2:1 (swept on B200: +3 %)
       {
         if (wantQ) TravQuad(r, bvh, stk);
         wantQ = !(r.node & HC_LEAF_BIT); wantL = !wantQ && r.node != HC_NODE_SENTINEL;
