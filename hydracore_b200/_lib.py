@@ -60,6 +60,7 @@ SIGNATURES = {
     "hc_fb_clear": (_I, [_P]),
     "hc_fb_device_ptr": (_I, [_P, _PP, ct.POINTER(_I64)]),
     "hc_fb_read_hdr": (_I, [_P, _P, _I, _I]),
+    "hc_fb_read_sum": (_I, [_P, _P, _I, _I]),
     "hc_fb_read_ldr": (_I, [_P, _P, _I, _I]),
     "hc_get_spp": (_I, [_P, ct.POINTER(ct.c_float)]),
     "hc_get_stats": (_I, [_P, ct.POINTER(hc_stats)]),

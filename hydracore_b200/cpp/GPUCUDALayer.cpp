@@ -158,7 +158,7 @@ void GPUCUDALayer::FinishAll() { Check(hc_sync(m_ctx), "FinishAll"); }
 void GPUCUDALayer::ClearAccumulatedColor()
 {
   Check(hc_fb_clear(m_ctx), "ClearAccumulatedColor");
-  m_spp = 0.0f; m_sppContributed = 0.0f;
+  m_spp = 0.0f;
 }
 
 void GPUCUDALayer::ResetPerfCounters()
@@ -235,33 +235,32 @@ void GPUCUDALayer::CallNamedFunc(const char* a_name, const char* a_args)
   }
 }
 
-// One process per GPU adds its partial sums into the shared image under the image's lock: the multi-process mode of the reference
-// (GPUOCLLayerOther.cpp:365-430; README.md:99-103).  Layer 0 of the shared image holds SUMS over spp, Header()->spp the sample count.
+// One process per GPU adds its SUM buffer into the shared image under the image's lock and hands over its sample count: the
+// multi-process mode of the reference (GPUOCLLayerOther.cpp:365-430; README.md:99-103).  Every process renders the FULL frame with its
+// own seed in this mode (no tile ownership), so that Header()->spp, the sum of the contributed sample counts, normalises every pixel.
 void GPUCUDALayer::ContribToExternalImageAccumulator(IHRSharedAccumImage* a_pImage)
 {
-  if (a_pImage == nullptr) return;
-  const float newSpp = m_spp - m_sppContributed;
-  if (newSpp <= 0.0f) return;
-  std::vector<float> hdr(size_t(m_width)*size_t(m_height)*4);
-  Check(hc_fb_read_hdr(m_ctx, hdr.data(), m_width, m_height), "ContribToExternalImageAccumulator");
+  if (a_pImage == nullptr || m_spp <= 0.0f) return;
+  std::vector<float> sums(size_t(m_width)*size_t(m_height)*4);
+  Check(hc_fb_read_sum(m_ctx, sums.data(), m_width, m_height), "ContribToExternalImageAccumulator");
   if (!a_pImage->Lock(100)) return;                             // try again after the next pass, like the reference
   HRSharedBufferHeader* h = a_pImage->Header();
   float* dst = a_pImage->ImageData(0);
+  bool done = false;
   if (h != nullptr && dst != nullptr && h->width == m_width && h->height == m_height)
   {
-    // hdr = (sum over m_spp samples)/m_spp; the shared image wants the mean weighted by sample counts
-    const float have = h->spp, total = have + newSpp;
-    const float wOld = have/total, wNew = newSpp/total;
     const size_t n = size_t(m_width)*size_t(m_height)*4;
-    for (size_t i = 0; i < n; i++) dst[i] = dst[i]*wOld + hdr[i]*wNew;
-    h->spp = total;
+    for (size_t i = 0; i < n; i++) dst[i] += sums[i];
     h->counterRcv++;
-    m_sppContributed = m_spp;
-    // the framebuffer on the device keeps accumulating; only the not-yet-contributed share is weighted in next time
-    Check(hc_fb_clear(m_ctx), "ContribToExternalImageAccumulator (hc_fb_clear)");
-    m_spp = 0.0f; m_sppContributed = 0.0f;
+    h->spp += m_spp;
+    done = true;
   }
   a_pImage->Unlock();
+  if (done)
+  {
+    m_sppContributed += m_spp;
+    ClearAccumulatedColor();                                   // the device buffer starts over: only not-yet-contributed samples live there
+  }
 }
 
 IHWLayer* CreateCudaImpl(int w, int h, int a_flags, int a_deviceId) { return new GPUCUDALayer(w, h, a_flags, a_deviceId); }

@@ -60,6 +60,7 @@ public:
   void ContribToExternalImageAccumulator(IHRSharedAccumImage* a_pImage) override;
 
   float GetSPP() const override { return m_spp; }
+  float GetSPPContrib() const override { return m_sppContributed; }
 
   hc_ctx* Context() const { return m_ctx; }                     // for the NCCL reduce of the caller (hc_fb_device_ptr)
 

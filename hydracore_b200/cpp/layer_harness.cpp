@@ -6,6 +6,7 @@
 // InitPathTracing, BeginTracingPass / EndTracingPass :1846-1848, GetHDRImage).
 #include "GPUCUDALayer.h"
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -28,9 +29,38 @@ namespace
   }
 }
 
+namespace
+{
+  // in-process stand-in for HydraAPI's shared-memory accumulation image (one layer of float4 sums, a header, a lock)
+  struct FakeSharedImage : public IHRSharedAccumImage
+  {
+    HRSharedBufferHeader hdr{}; std::vector<float> data; bool locked = false; int lockCalls = 0;
+    bool  Create(int w, int h, int d, const char*, char[256]) override { hdr = HRSharedBufferHeader{}; hdr.width = w; hdr.height = h; hdr.depth = d; hdr.channels = 4; data.assign(size_t(w)*h*4, 0.0f); return true; }
+    bool  Attach(const char*, char[256]) override { return true; }
+    void  Clear() override { std::fill(data.begin(), data.end(), 0.0f); hdr.spp = 0.0f; hdr.counterRcv = 0; }
+    bool  Lock(int) override { lockCalls++; if (locked) return false; locked = true; return true; }
+    void  Unlock() override { locked = false; }
+    float* ImageData(int) override { return data.data(); }
+    char*  MessageSendData() override { return nullptr; }
+    char*  MessageRcvData() override { return nullptr; }
+    HRSharedBufferHeader* Header() override { return &hdr; }
+  };
+}
+
 extern "C"
 {
 const char* hl_last_error() { return g_err.c_str(); }
+
+void* hl_shared_image_create(int w, int h) { FakeSharedImage* im = new FakeSharedImage; char err[256]; im->Create(w, h, 1, "test", err); return im; }
+void  hl_shared_image_destroy(void* im) { delete static_cast<FakeSharedImage*>(im); }
+int   hl_shared_image_read(void* im, float* out, float* spp, int* counterRcv)
+{
+  FakeSharedImage* s = static_cast<FakeSharedImage*>(im);
+  memcpy(out, s->data.data(), s->data.size()*4); *spp = s->hdr.spp; *counterRcv = s->hdr.counterRcv; return s->locked ? 1 : 0;
+}
+int hl_contribute(void* p, void* im)
+{ Session* s = static_cast<Session*>(p); return Guard([&] { s->layer->ContribToExternalImageAccumulator(static_cast<FakeSharedImage*>(im)); }); }
+float hl_get_spp_contrib(void* p) { return static_cast<Session*>(p)->layer->GetSPPContrib(); }
 
 void* hl_create(int w, int h, int flags, int deviceId)
 {

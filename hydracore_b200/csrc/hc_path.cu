@@ -792,6 +792,16 @@ int hc_fb_read_hdr(hc_ctx* ctx, float* outRGBA, int width, int height)
   return HC_OK;
 }
 
+int hc_fb_read_sum(hc_ctx* ctx, float* outRGBA, int width, int height)
+{
+  if (!ctx || !outRGBA) return HC_E_ARG;
+  HC_REQUIRE(width == ctx->width && height == ctx->height && ctx->fbSum.ptr, HC_E_ARG, "hc_fb_read_sum: bad input resolution");
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HC_CUDA(cudaMemcpyAsync(outRGBA, ctx->fbSum.ptr, size_t(width)*height*16, cudaMemcpyDeviceToHost, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HC_OK;
+}
+
 int hc_fb_read_ldr(hc_ctx* ctx, uint32_t* outRGBA8, int width, int height)
 {
   if (!ctx || !outRGBA8) return HC_E_ARG;

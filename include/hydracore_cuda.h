@@ -107,6 +107,8 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes);                     /* 
 int hc_fb_clear(hc_ctx* ctx);                                                /* ClearAccumulatedColor, IHWLayer.h:140                       */
 int hc_fb_device_ptr(hc_ctx* ctx, float** outSumRGBA, int64_t* outFloats);   /* per-pixel SUM buffer (for the NCCL reduce over NVLink)      */
 int hc_fb_read_hdr(hc_ctx* ctx, float* outRGBA, int width, int height);      /* GetHDRImage: sum / spp, GPUOCLLayer.cpp:1184-1215           */
+int hc_fb_read_sum(hc_ctx* ctx, float* outRGBA, int width, int height);      /* the raw per-pixel SUMS (what the OpenCL layer adds into the shared image,
+                                                                                 GPUOCLLayerOther.cpp:365-430)                               */
 int hc_fb_read_ldr(hc_ctx* ctx, uint32_t* outRGBA8, int width, int height);  /* GetLDRImage, IHWLayer.h:149                                 */
 int hc_get_spp(hc_ctx* ctx, float* outSpp);                                  /* GetSPP, IHWLayer.h:207                                      */
 int hc_get_stats(hc_ctx* ctx, hc_stats* out);                                /* GetRaysStat, IHWLayer.h:155                                 */

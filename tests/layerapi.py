@@ -33,6 +33,13 @@ class CppLayer:
         L.hl_create.argtypes = [ct.c_int]*4
         L.hl_get_spp.restype = ct.c_float
         L.hl_get_spp.argtypes = [ct.c_void_p]
+        L.hl_get_spp_contrib.restype = ct.c_float
+        L.hl_get_spp_contrib.argtypes = [ct.c_void_p]
+        L.hl_shared_image_create.restype = ct.c_void_p
+        L.hl_shared_image_create.argtypes = [ct.c_int, ct.c_int]
+        L.hl_shared_image_destroy.argtypes = [ct.c_void_p]
+        L.hl_shared_image_read.argtypes = [ct.c_void_p, ct.c_void_p, ct.POINTER(ct.c_float), ct.POINTER(ct.c_int)]
+        L.hl_contribute.argtypes = [ct.c_void_p, ct.c_void_p]
         L.hl_available_memory.restype = ct.c_uint64
         L.hl_available_memory.argtypes = [ct.c_void_p, ct.c_int]
         for name in ("hl_destroy", "hl_create_storage", "hl_storage_update", "hl_storage_info", "hl_resize_tables", "hl_set_bvh", "hl_set_instances",
@@ -140,6 +147,12 @@ class CppLayer:
     def GetSPP(self):
         return float(self._L.hl_get_spp(self._s))
 
+    def GetSPPContrib(self):
+        return float(self._L.hl_get_spp_contrib(self._s))
+
+    def ContribToExternalImageAccumulator(self, shared):
+        self._ck(self._L.hl_contribute(self._s, shared.h), "ContribToExternalImageAccumulator")
+
     def GetDeviceName(self):
         buf = ct.create_string_buffer(256)
         self._ck(self._L.hl_device_name(self._s, buf, 256), "GetDeviceName")
@@ -210,3 +223,27 @@ def load_scene_like_render_driver(lay, scn, consts):
         pref[nl] = acc
         lay.SetAllLights(lights, pref)
     lay.PrepareEngineGlobalsAndTables()
+
+
+class SharedImage:
+    """In-process stand-in for HydraAPI's IHRSharedAccumImage (hydracore_b200/cpp/layer_harness.cpp)."""
+
+    def __init__(self, w, h):
+        self._L = ct.CDLL(LIB)
+        self._L.hl_shared_image_create.restype = ct.c_void_p
+        self._L.hl_shared_image_create.argtypes = [ct.c_int, ct.c_int]
+        self._L.hl_shared_image_destroy.argtypes = [ct.c_void_p]
+        self._L.hl_shared_image_read.argtypes = [ct.c_void_p, ct.c_void_p, ct.POINTER(ct.c_float), ct.POINTER(ct.c_int)]
+        self.w, self.h_ = w, h
+        self.h = ct.c_void_p(self._L.hl_shared_image_create(w, h))
+
+    def read(self):
+        out = np.zeros((self.h_, self.w, 4), np.float32)
+        spp, cnt = ct.c_float(), ct.c_int()
+        locked = self._L.hl_shared_image_read(self.h, P(out), ct.byref(spp), ct.byref(cnt))
+        return out, spp.value, cnt.value, bool(locked)
+
+    def close(self):
+        if self.h:
+            self._L.hl_shared_image_destroy(self.h)
+            self.h = None

@@ -162,3 +162,25 @@ def test_ihwlayer_sky_dome_scene_equals_c_abi_path(consts, layer):
     layer.TracingPass(2, 2)
     assert a[..., :3].mean() > 0.1 and np.array_equal(a, layer.GetHDRImage())
     lay.close()
+
+
+def test_shared_image_accumulation_like_the_reference_worker_mode(consts):
+    """ContribToExternalImageAccumulator (GPUOCLLayerOther.cpp:365-430): two render processes (here: two layers with different seeds, full frame
+    each) add their SUM buffers into one shared image and hand over their sample counts; the device buffer starts over afterwards."""
+    from tests import layerapi
+    scn = scenes.cornell(48, 48)
+    shared = layerapi.SharedImage(48, 48)
+    sums = []
+    for seed, passes in ((11, 2), (12, 3)):
+        lay = _make(scn, consts)
+        lay.InitPathTracing(seed)
+        lay.TracingPasses(passes)
+        sums.append(lay.GetHDRImage()*np.float32(passes))
+        lay.ContribToExternalImageAccumulator(shared)
+        assert lay.GetSPP() == 0.0 and lay.GetSPPContrib() == float(passes) and lay.GetHDRImage().max() == 0.0
+        lay.close()
+    img, spp, cnt, locked = shared.read()
+    assert spp == 5.0 and cnt == 2 and not locked
+    want = sums[0] + sums[1]
+    assert np.abs(img[..., :3] - want[..., :3]).max() <= 1e-5*max(1.0, float(want[..., :3].max()))
+    shared.close()
