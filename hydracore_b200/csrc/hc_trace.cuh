@@ -26,7 +26,7 @@
 #define HC_NODE_SENTINEL 0xffffffffu   // "ray finished"; also the child word of an empty slot
 #define HC_MAXFLOAT      3.402823466e+38f // MAXFLOAT = FLT_MAX from <math.h> / OpenCL (the 1e37f fallback of ctrace.h:665-667 is never taken)
 #define HC_TRI_EPS       1e-6f            // barycentric slack, ctrace.h:111
-#define HC_STACK_CAP     64               // entries per ray; hc_set_bvh checks the tree against it
+#define HC_STACK_CAP     80               // entries per ray = the reference's STACK_SIZE (ctrace.h:576); hc_set_bvh checks the tree against it
 
 // triangle-leaf child word: [31] leaf | [30:25] pair records - 1 | [24:0] index of the first pair record (96 bytes each)
 #define HC_LEAF_PAIRS_SHIFT 25
