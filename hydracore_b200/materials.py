@@ -200,9 +200,9 @@ def point_light(pos, intensity, pick_prob=1.0):
     return L
 
 
-def sky_light(color, pdf_table_id, pick_prob=1.0):
-    """Sky-dome light without texture / Perez model (SkyDomeLight, PlainLightConverter.cpp:909-1060): identity sampler matrices, the pdf table
-    built by Scene.add_sky_pdf_table."""
+def sky_light(color, pdf_table_id, pick_prob=1.0, tex_id=None, gamma=1.0):
+    """Sky-dome light, optionally textured (environment map), without the Perez model (SkyDomeLight, PlainLightConverter.cpp:909-1060):
+    identity sampler matrices, the pdf table built by Scene.add_sky_pdf_table (from the map's luminance when textured)."""
     L = np.zeros(128, np.float32)
     Li = L.view(np.int32)
     Li[C["PLIGHT_TYPE"]] = C["PLAIN_LIGHT_TYPE_SKY_DOME"]
@@ -226,6 +226,13 @@ def sky_light(color, pdf_table_id, pick_prob=1.0):
     for base in (56, 72):                             # SKY_DOME_INV_MATRIX0 / 1: identity float4x4 (columns)
         L[base:base + 16] = np.eye(4, dtype=np.float32).reshape(16)
     Li[88] = -1                                       # SKY_DOME_SUN_DIR_ID
+    if tex_id is not None:                            # PlainLightConverter.cpp:969-978: texture id for the pdf table builder, sampler at offset 0
+        Li[C["PLIGHT_COLOR_TEX"]] = tex_id
+        Li[C["PLIGHT_COLOR_TEX_MATRIX"]] = 0
+        Li[20], Li[21] = tex_id, 0
+        for base in (32, 44):
+            L[base + 1] = gamma
+            Li[base + 2] = tex_id
     L[C["PLIGHT_PROB_MULT"]] = 1.0
     L[C["PLIGHT_PICK_PROB_FWD"]] = pick_prob
     L[C["PLIGHT_PICK_PROB_REV"]] = pick_prob

@@ -350,6 +350,13 @@ class Scene:
         self.textures.append(rgba)
         return len(self.textures)
 
+    def add_texture_f4(self, rgba):
+        """HDR texture: float4 texels (bpp 16, cfetch.h:364-584), e.g. an environment map."""
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        assert rgba.ndim == 3 and rgba.shape[2] == 4
+        self.textures.append(rgba)
+        return len(self.textures)
+
     # ---- build everything the layer receives
     def build(self):
         # geometry storage + geometry table (float4 offsets)
@@ -371,8 +378,8 @@ class Scene:
         tex_chunks, tex_table, off = [np.zeros(16, np.uint8)], [-1], 16
         for t in self.textures:
             h, w = t.shape[0], t.shape[1]
-            hdr = np.array([w, h, 4, 4], np.int32).view(np.uint8)
-            body = t.reshape(-1)
+            hdr = np.array([w, h, 4, 16 if t.dtype == np.float32 else 4], np.int32).view(np.uint8)
+            body = t.reshape(-1).view(np.uint8)
             pad = (-body.size) % 16
             chunk = np.concatenate([hdr, body, np.zeros(pad, np.uint8)])
             tex_table.append(off//16)

@@ -149,7 +149,7 @@ def cornell_sphere_and_point_lights(width=96, height=96):
     return scn.build()
 
 
-def open_box_under_sky(width=96, height=96, with_area_light=True):
+def open_box_under_sky(width=96, height=96, with_area_light=True, env_map=False):
     """Objects on a floor under a uniform sky-dome light (plus, optionally, a rect area light): rays that leave the scene pick up the
     environment colour with MIS, the sky is sampled through its pdf table."""
     from hydracore_b200 import materials as M
@@ -166,8 +166,22 @@ def open_box_under_sky(width=96, height=96, with_area_light=True):
     for mat, mtx in ((ggxm, S.translate(-2.4, -2.8, 0.0) @ S.scale(1.2, 1.2, 1.2)), (gls, S.translate(0.0, -2.9, 1.5) @ S.scale(1.1, 1.1, 1.1)),
                      (mir, S.translate(2.5, -2.7, -0.5) @ S.scale(1.3, 1.3, 1.3)), (red, S.translate(0.3, -3.2, -2.5) @ S.scale(0.8, 0.8, 0.8))):
         scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, mat, np.int32))), mtx)
-    tab = scn.add_sky_pdf_table()
-    scn.add_light(M.sky_light((0.9, 1.0, 1.3), tab))
+    if env_map:
+        # 16 x 8 HDR map: bright patch ("sun") + gradient; pdf table = prefix sums of its luminance (RenderDriverRTE_PdfTables.cpp:520-566)
+        yy, xx = np.mgrid[0:8, 0:16]
+        env = np.zeros((8, 16, 4), np.float32)
+        env[..., 0] = 0.4 + 0.05*xx
+        env[..., 1] = 0.5 + 0.04*yy
+        env[..., 2] = 0.9 - 0.03*yy
+        env[2, 5, 0:3] = (40.0, 36.0, 30.0)
+        env[..., 3] = 1.0
+        tex = scn.add_texture_f4(env)
+        lum = (0.2126*env[..., 0] + 0.7152*env[..., 1] + 0.0722*env[..., 2]).astype(np.float32)
+        tab = scn.add_sky_pdf_table(lum)
+        scn.add_light(M.sky_light((1.0, 1.0, 1.0), tab, tex_id=tex))
+    else:
+        tab = scn.add_sky_pdf_table()
+        scn.add_light(M.sky_light((0.9, 1.0, 1.3), tab))
     if with_area_light:
         l1 = scn.add_light(M.area_light((0.0, 3.5, 0.0), (1.0, 1.0), (12.0, 11.0, 9.0)))
         scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)), S.translate(0.0, 3.5, 0.0), light_id=l1)
