@@ -540,6 +540,78 @@ HC_DEV void PhongSample(const float* m, float r1, float r2, float3 rayDir, float
   out.flags = (gloss >= 0.99f) ? HC_RAY_EVENT_S : HC_RAY_EVENT_G;
 }
 
+// ---- Blinn distribution + Torrance-Sparrow geometry term (cmaterial.h:1020-1160, cmatpbrt.h:33-105).  Slots coincide with Phong's.
+HC_DEV float TorranceSparrowG(float NdotWh, float NdotWo, float NdotWi, float WOdotWhAbs)          // cmatpbrt.h:44-64
+{
+  const float WOdotWh = fmaxf(WOdotWhAbs, HC_DEPSILON);
+  return fminf(1.0f, fminf(2.0f*NdotWh*NdotWo/WOdotWh, 2.0f*NdotWh*NdotWi/WOdotWh));
+}
+HC_DEV float TorranceSparrowGF1(float3 wo, float3 wi)                                              // local frame, cmatpbrt.h:66-84
+{
+  const float cosThetaO = fabsf(wo.z), cosThetaI = fabsf(wi.z);
+  if (cosThetaI == 0.0f || cosThetaO == 0.0f) return 0.0f;
+  float3 wh = wi + wo;
+  if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return 0.0f;
+  wh = normalize(wh);
+  const float G = TorranceSparrowG(fabsf(wh.z), fabsf(wo.z), fabsf(wi.z), fabsf(dot(wo, wh)));
+  return fminf(G*1.0f/fmaxf(4.0f*cosThetaI*cosThetaO, HC_DEPSILON), 250.0f);
+}
+HC_DEV float TorranceSparrowGF2(float3 wo, float3 wi, float3 n)                                    // world frame, cmatpbrt.h:86-105
+{
+  const float cosThetaO = fabsf(dot(wo, n)), cosThetaI = fabsf(dot(wi, n));
+  if (cosThetaI == 0.0f || cosThetaO == 0.0f) return 0.0f;
+  float3 wh = wi + wo;
+  if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return 0.0f;
+  wh = normalize(wh);
+  const float G = TorranceSparrowG(fabsf(dot(wh, n)), fabsf(dot(wo, n)), fabsf(dot(wi, n)), fabsf(dot(wo, wh)));
+  return fminf(G*1.0f/fmaxf(4.0f*cosThetaI*cosThetaO, HC_DEPSILON), 10.0f);          // 10 here, 250 in the local-frame variant
+}
+HC_DEV float BlinnEvalPDF(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  if (dot(n, v) < 1e-6f || dot(n, l) < 1e-6f) return 1.0f;
+  const float exponent = cosPowerFromGlosiness(Glosiness(m, tc, s));
+  const float3 wh = normalize(l + v);
+  const float costheta = fabsf(dot(wh, n));
+  return (float)((D(exponent + 1.0f)*pow(D(costheta), D(exponent)))/D(HC_M_TWOPI*4.0f*dot(l, wh)));
+}
+HC_DEV float3 BlinnEvalBxDF(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  if (dot(n, v) < 1e-6f || dot(n, l) < 1e-6f) return f3(0, 0, 0);
+  const float3 tex = Sample2D(MatI(m, HC_PHONG_TEXMATRIXID_OFFSET), tc, m, s);
+  const float3 color = clamp3(Mat3(m, HC_PHONG_COLORX_OFFSET)*tex, 0.0f, 1.0f);
+  const float exponent = cosPowerFromGlosiness(Glosiness(m, tc, s));
+  const float3 wh = normalize(l + v);
+  const float cosThetaH = fabsf(dot(wh, n));
+  const float Dh = (float)(D((exponent + 2.0f)*HC_INV_TWOPI)*pow(D(cosThetaH), D(exponent)));
+  return color*Dh*TorranceSparrowGF2(l, v, n);
+}
+HC_DEV void BlinnSample(const float* m, float r1, float r2, float3 rayDir, float3 n, float2 tc, const HcScene& s, HcMatSample& out)
+{
+  const float3 tex = Sample2D(MatI(m, HC_PHONG_TEXMATRIXID_OFFSET), tc, m, s);
+  const float3 color = clamp3(Mat3(m, HC_PHONG_COLORX_OFFSET)*tex, 0.0f, 1.0f);
+  const float gloss = Glosiness(m, tc, s);
+  float3 nx, ny; const float3 nz = n;
+  CoordinateSystem(nz, nx, ny);
+  const float3 wo = f3(-dot(rayDir, nx), -dot(rayDir, ny), -dot(rayDir, nz));
+  const float exponent = cosPowerFromGlosiness(gloss);
+  const float costheta = hc_pow(r1, 1.0f/(exponent + 1.0f));
+  const float sintheta = sqrtf(fmaxf(0.0f, 1.0f - costheta*costheta));
+  const float phi = r2*HC_M_TWOPI;
+  const float3 wh = f3((float)(D(sintheta)*cos(D(phi))), (float)(D(sintheta)*sin(D(phi))), costheta);
+  const float3 wi = (2.0f*dot(wo, wh)*wh) - wo;
+  const float3 newDir = normalize(wi.x*nx + wi.y*ny + wi.z*nz);
+  const float3 v = rayDir*(-1.0f), l = newDir;
+  if (dot(n, v) < 1e-6f || dot(n, l) < 1e-6f) { out.color = f3(0, 0, 0); out.pdf = 1.0f; }
+  else
+  {
+    const float Dh = (float)(D((exponent + 2.0f)*HC_INV_TWOPI)*pow(D(costheta), D(exponent)));
+    out.color = color*Dh*TorranceSparrowGF1(wo, wi);
+    out.pdf = (float)((D(exponent + 1.0f)*pow(D(costheta), D(exponent)))/D(fmaxf(HC_M_TWOPI*4.0f*dot(wo, wh), HC_DEPSILON)));
+  }
+  out.direction = newDir;
+  out.flags = (gloss >= 0.99f) ? HC_RAY_EVENT_S : HC_RAY_EVENT_G;
+}
+
 // ---- GGX (cmaterial.h:1212-1285, 1317-1381, 1454-1520)
 HC_DEV float SmithGGXMasking(float dotNV, float roughSqr)
 {
@@ -758,6 +830,7 @@ HC_DEV void LeafSample(const float* m, const HcSurfaceHit& sh, float3 rayDir, fl
   switch (MatI(m, HC_PLAIN_MAT_TYPE_OFFSET))
   {
     case HC_PLAIN_MAT_CLASS_PHONG_SPECULAR: PhongSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
+    case HC_PLAIN_MAT_CLASS_BLINN_SPECULAR: BlinnSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_GGX:            GgxSample2(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_PERFECT_MIRROR: MirrorSample(m, rayDir, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_GLASS:          GlassGgxSample(m, rands, rayDir, sh.normal, sh.texCoord, sh.hfi, s, out); break;
@@ -814,6 +887,8 @@ HC_DEV HcBxDF LeafEval(const float* m, float3 l, float3 v, float3 n, float2 tc, 
   {
     case HC_PLAIN_MAT_CLASS_PHONG_SPECULAR:
       r.brdf = PhongEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = PhongEvalPDF(m, l, v, n, tc, s); r.pdfRev = PhongEvalPDF(m, v, l, n, tc, s); break;
+    case HC_PLAIN_MAT_CLASS_BLINN_SPECULAR:
+      r.brdf = BlinnEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = BlinnEvalPDF(m, l, v, n, tc, s); r.pdfRev = BlinnEvalPDF(m, v, l, n, tc, s); break;
     case HC_PLAIN_MAT_CLASS_GGX:
       r.brdf = GgxEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = Ggx2EvalPDF(m, l, v, n, tc, s); r.pdfRev = Ggx2EvalPDF(m, v, l, n, tc, s); break;
     case HC_PLAIN_MAT_CLASS_LAMBERT:

@@ -154,7 +154,9 @@ def build_scene(lib, width, height):
                 lam = M.lambert(tuple(dif["color"]), tex_id=tex_map.get(dif["tex"], 0))  # textures that were not shipped (dl="1") read as white
             if "reflect" in d and max(d["reflect"]["color"]) > 1e-5:
                 r = d["reflect"]
-                top = (M.ggx if r["brdf"] == "ggx" else M.phong)(tuple(r["color"]), r["gloss"])
+                if r["brdf"] not in _BRDF_CODE:
+                    raise ValueError("material %d: reflectivity brdf_type '%s' is not supported yet (phong, ggx, torranse_sparrow are)" % (mid, r["brdf"]))
+                top = {"ggx": M.ggx, "torranse_sparrow": M.blinn, "phong": M.phong}[r["brdf"]](tuple(r["color"]), r["gloss"])
                 nodes = M.blend(tuple(r["color"]), top, lam, fresnel=r["fresnel"], ior=r["ior"])
             else:
                 nodes = lam
@@ -168,6 +170,10 @@ def build_scene(lib, width, height):
         lidx = linst_map.get(inst.get("linst_id", -1), light_map.get(inst["light_id"], -1))
         scn.add_instance(mesh_map[k], inst["matrix"], light_id=lidx)
     return scn.build()
+
+
+_BRDF_CODE = {"phong": 0, "ggx": 1, "torranse_sparrow": 2}     # column 10 of the fixture's material rows
+_BRDF_NAME = {v: k for k, v in _BRDF_CODE.items()}
 
 
 def _fixture_arrays(lib):
@@ -188,7 +194,7 @@ def _fixture_arrays(lib):
         d = lib["materials"][mid]
         dif, ref = d.get("diffuse"), d.get("reflect")
         mats.append([mid, d.get("light_id", -1)] + (dif["color"] + [dif["tex"]] if dif else [0, 0, 0, -1]) +
-                    (ref["color"] + [ref["gloss"], 1.0 if ref["brdf"] == "ggx" else 0.0, 1.0 if ref["fresnel"] else 0.0, ref["ior"]] if ref else [0, 0, 0, -1, 0, 0, 0]) +
+                    (ref["color"] + [ref["gloss"], float(_BRDF_CODE[ref["brdf"]]), 1.0 if ref["fresnel"] else 0.0, ref["ior"]] if ref else [0, 0, 0, -1, 0, 0, 0]) +
                     (d["emission"] if "emission" in d else [-1, -1, -1]))
     a["materials"] = np.array(mats, np.float64)
     shapes = {"rect": 0, "sphere": 1, "point": 2}
@@ -245,7 +251,7 @@ def load_fixture(path, scene):
         if r[5] >= 0:
             d["diffuse"] = dict(color=list(r[2:5]), tex=int(r[5]))
         if r[9] >= 0:
-            d["reflect"] = dict(color=list(r[6:9]), gloss=float(r[9]), brdf="ggx" if r[10] > 0.5 else "phong", fresnel=r[11] > 0.5, ior=float(r[12]))
+            d["reflect"] = dict(color=list(r[6:9]), gloss=float(r[9]), brdf=_BRDF_NAME[int(round(r[10]))], fresnel=r[11] > 0.5, ior=float(r[12]))
         if r[13] >= 0:
             d["emission"] = list(r[13:16])
         lib["materials"][int(r[0])] = d

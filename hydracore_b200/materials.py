@@ -82,6 +82,11 @@ def phong(color, gloss, tex_id=0, energy_fix=False, **kw):
                    C["PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER"] if energy_fix else 0, **kw)
 
 
+def blinn(color, gloss, tex_id=0, **kw):
+    """BlinnTorranceSrappowMaterial (PlainMaterialConverter.cpp:462-485; XML brdf_type="torranse_sparrow"): Phong's slots, always CAST_CAUSTICS."""
+    return _glossy(C["PLAIN_MAT_CLASS_BLINN_SPECULAR"], color, gloss, tex_id, C["PLAIN_MATERIAL_CAST_CAUSTICS"], **kw)
+
+
 def ggx(color, gloss, tex_id=0, multiscatter=False, **kw):
     return _glossy(C["PLAIN_MAT_CLASS_GGX"], color, gloss, tex_id,
                    C["PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER"] if multiscatter else 0, **kw)
