@@ -83,11 +83,12 @@ def parse_library(xml_path, mesh_fallback_dirs=()):
         out["materials"][int(m.get("id"))] = d
     for l in root.find("lights_lib"):
         size, inten = l.find("size"), l.find("intensity")
-        mult = float(_val(inten.find("multiplier"), "1"))
+        mult = float(_val(inten.find("multiplier"), "1").split()[0])          # pugixml's as_float reads the leading number of "30 30 30"
         col = inten.find("color")
         half = (float(size.get("half_length", "0")), float(size.get("half_width", "0"))) if size is not None else (0.0, 0.0)
         out["lights"][int(l.get("id"))] = dict(type=l.get("type"), shape=l.get("shape", "point"), half=half, radius=float(size.get("radius", "0")) if size is not None else 0.0,
-                                                color=[c*mult for c in _floats(_val(col, "1 1 1"))], mat_id=int(l.get("mat_id", "-1")))
+                                                color=[c*mult for c in _floats(_val(col, "1 1 1"))], mat_id=int(l.get("mat_id", "-1")),
+                                                textured=col is not None and col.find("texture") is not None, perez=l.find("perez") is not None)
     cam = root.find("cam_lib")[0]
     g = lambda n, dflt: _val(cam.find(n), dflt)
     out["camera"] = dict(fov=float(g("fov", "45")), near=float(g("nearClipPlane", "0.01")), far=float(g("farClipPlane", "100")), up=_floats(g("up", "0 1 0")),
@@ -137,14 +138,17 @@ def build_scene(lib, width, height):
             idx = scn.add_light(M.sphere_light(tuple(mtx[:3, 3]), l["radius"]*scale, tuple(l["color"])))
         elif l["type"] == "point" and l["shape"] == "point":
             idx = scn.add_light(M.point_light(tuple(mtx[:3, 3]), tuple(l["color"])))
+        elif l["type"] == "sky" and not l.get("textured") and not l.get("perez"):
+            # constant-colour environment: 2x2 uniform pdf table (RenderDriverRTE_PdfTables.cpp:534-544); a black one is never picked
+            idx = scn.add_light(M.sky_light(tuple(l["color"]), scn.add_sky_pdf_table()))
         else:
-            raise ValueError("light %d: type %s / shape %s is not supported yet (rect and sphere area lights, omni point lights are)" % (li["light_id"], l["type"], l["shape"]))
+            raise ValueError("light %d: type %s / shape %s is not supported yet (rect and sphere area lights, omni point lights, untextured sky domes are)" % (li["light_id"], l["type"], l["shape"]))
         linst_map[li["id"]] = idx
         light_map.setdefault(li["light_id"], idx)
     mat_map = {}
     for mid in range(max(lib["materials"]) + 1):
         d = lib["materials"].get(mid, dict(diffuse=dict(color=[0.5, 0.5, 0.5], tex=0)))
-        if "emission" in d:
+        if "emission" in d and (max(d["emission"]) > 1e-5 or d.get("light_id", -1) >= 0 or ("diffuse" not in d and "reflect" not in d)):
             nodes = M.emissive(tuple(d["emission"]), light_map.get(d.get("light_id", -1), -1))
         else:
             dif = d.get("diffuse", dict(color=[0, 0, 0], tex=0))
@@ -156,7 +160,10 @@ def build_scene(lib, width, height):
                 r = d["reflect"]
                 if r["brdf"] not in _BRDF_CODE:
                     raise ValueError("material %d: reflectivity brdf_type '%s' is not supported yet (phong, ggx, torranse_sparrow are)" % (mid, r["brdf"]))
-                top = {"ggx": M.ggx, "torranse_sparrow": M.blinn, "phong": M.phong}[r["brdf"]](tuple(r["color"]), r["gloss"])
+                if r["gloss"] >= 0.995:                            # an untextured glossiness this high becomes a perfect mirror (PlainMaterialConverter.cpp:1128)
+                    top = M.mirror(tuple(r["color"]))
+                else:
+                    top = {"ggx": M.ggx, "torranse_sparrow": M.blinn, "phong": M.phong}[r["brdf"]](tuple(r["color"]), r["gloss"])
                 nodes = M.blend(tuple(r["color"]), top, lam, fresnel=r["fresnel"], ior=r["ior"])
             else:
                 nodes = lam
@@ -197,8 +204,8 @@ def _fixture_arrays(lib):
                     (ref["color"] + [ref["gloss"], float(_BRDF_CODE[ref["brdf"]]), 1.0 if ref["fresnel"] else 0.0, ref["ior"]] if ref else [0, 0, 0, -1, 0, 0, 0]) +
                     (d["emission"] if "emission" in d else [-1, -1, -1]))
     a["materials"] = np.array(mats, np.float64)
-    shapes = {"rect": 0, "sphere": 1, "point": 2}
-    a["lights"] = np.array([[lid] + list(l["half"]) + l["color"] + [l["mat_id"], shapes[l["shape"]], l["radius"]] for lid, l in sorted(lib["lights"].items())], np.float64)
+    shapes = {"rect": 0, "sphere": 1, "point": 2, "sky": 3}
+    a["lights"] = np.array([[lid] + list(l["half"]) + l["color"] + [l["mat_id"], shapes["sky" if l["type"] == "sky" else l["shape"]], l["radius"]] for lid, l in sorted(lib["lights"].items())], np.float64)
     a["light_instances"] = np.array([[li["id"], li["light_id"]] for li in lib["light_instances"]], np.int64).reshape(-1, 2)
     a["light_matrices"] = np.array([li["matrix"] for li in lib["light_instances"]], np.float32).reshape(-1, 4, 4)
     a["instances"] = np.array([[i["mesh_id"], i["light_id"], i.get("linst_id", -1)] for i in lib["instances"]], np.int64)
@@ -255,7 +262,7 @@ def load_fixture(path, scene):
         if r[13] >= 0:
             d["emission"] = list(r[13:16])
         lib["materials"][int(r[0])] = d
-    shapes = {0: ("area", "rect"), 1: ("area", "sphere"), 2: ("point", "point")}
+    shapes = {0: ("area", "rect"), 1: ("area", "sphere"), 2: ("point", "point"), 3: ("sky", "point")}
     for r in z["lights"]:
         ty, sh = shapes[int(r[7])]
         lib["lights"][int(r[0])] = dict(type=ty, shape=sh, half=(float(r[1]), float(r[2])), color=list(r[3:6]), mat_id=int(r[6]), radius=float(r[8]))

@@ -513,21 +513,54 @@ class Scene:
         for i, o in enumerate(getattr(self, "_pdf_table_offsets", [])):
             blob[offs["pdfTable"] + i] = o
         if nl > 0:
-            # light selection table = prefix sums of pick probabilities, N = lights+1 entries (RenderDriverRTE.cpp:1499-1521, clight.h:1774-1793)
+            # light selection tables = prefix sums of the pick probabilities, N = lights+1 entries (RenderDriverRTE.cpp:1499-1521, clight.h:1774-1793)
             lights = np.stack(self.lights).astype(np.float32)
-            lights[:, C["PLIGHT_PICK_PROB_FWD"]] = np.float32(1.0)/np.float32(nl)      # uniform pick, normalised (RenderDriverRTE.cpp:1505-1516)
-            lights[:, C["PLIGHT_PICK_PROB_REV"]] = np.float32(1.0)/np.float32(nl)
-            w = np.ones(nl, np.float32)/np.float32(nl)
-            pref = np.zeros(nl + 1, np.float32)
-            acc = np.float32(0)
-            for i in range(nl):
-                pref[i] = acc
-                acc = np.float32(acc + w[i])
-            pref[nl] = acc
-            blob[offs["lselRev"]:offs["lselRev"] + nl + 1] = pref.view(np.int32)
-            blob[offs["lselFwd"]:offs["lselFwd"] + nl + 1] = pref.view(np.int32)
+            prefs = {}
+            for fwd, slot in ((False, C["PLIGHT_PICK_PROB_REV"]), (True, C["PLIGHT_PICK_PROB_FWD"])):
+                w = light_pick_probs(lights, fwd)
+                pref = np.zeros(nl + 1, np.float32)
+                acc = np.float32(0)
+                for i in range(nl):
+                    pref[i] = acc
+                    acc = np.float32(acc + w[i])
+                pref[nl] = acc
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    lights[:, slot] = w*(np.float32(1.0)/acc)                                # stored per light, then normalised (RenderDriverRTE.cpp:1509-1516)
+                prefs[fwd] = pref
+            blob[offs["lselRev"]:offs["lselRev"] + nl + 1] = prefs[False].view(np.int32)
+            blob[offs["lselFwd"]:offs["lselFwd"] + nl + 1] = prefs[True].view(np.int32)
             blob[offs["lights"]:offs["lights"] + nl*128] = lights.reshape(-1).view(np.int32)
         return blob
+
+
+def light_pick_probs(lights, fwd):
+    """RenderDriverRTE::CalcLightPickProbTable (RenderDriverRTE_PdfTables.cpp:575-647): uniform over light groups (a light with group id -1 is
+    its own group), zero for lights flagged LIGHT_DO_NOT_SAMPLE_ME, for black lights (|colour| < 0.01), for sky domes that a sky portal
+    replaces and for sky domes in the forward (light tracing) table; times PLIGHT_PROB_MULT when that is positive.  Not normalised."""
+    li = lights.view(np.int32)
+    gid = li[:, C["PLIGHT_GROUP_ID"]]
+    members = {}
+    for g in gid:
+        if g != -1:
+            members[int(g)] = members.get(int(g), 0) + 1
+    n_groups = int((gid == -1).sum()) + len(members)
+    pick_group = np.float32(1.0)/np.float32(n_groups)
+    portal_sky = {int(li[i, C["AREA_LIGHT_SKY_SOURCE"]]) for i in range(len(lights))
+                  if li[i, C["PLIGHT_TYPE"]] == C["PLAIN_LIGHT_TYPE_AREA"] and (li[i, C["PLIGHT_FLAGS"]] & C["AREA_LIGHT_SKY_PORTAL"])}
+    out = np.zeros(len(lights), np.float32)
+    for i in range(len(lights)):
+        pp = pick_group if gid[i] == -1 else np.float32(pick_group/np.float32(members[int(gid[i])]))
+        if li[i, C["PLIGHT_FLAGS"]] & C["LIGHT_DO_NOT_SAMPLE_ME"]:
+            pp = np.float32(0)
+        if li[i, C["PLIGHT_TYPE"]] == C["PLAIN_LIGHT_TYPE_SKY_DOME"] and (fwd or i in portal_sky):
+            pp = np.float32(0)
+        col = lights[i, C["PLIGHT_COLOR_X"]:C["PLIGHT_COLOR_X"] + 3]
+        if np.sqrt(np.float32(col[0]*col[0] + col[1]*col[1] + col[2]*col[2])) < np.float32(0.01):
+            pp = np.float32(0)
+        if lights[i, C["PLIGHT_PROB_MULT"]] > 0:
+            pp = np.float32(pp*lights[i, C["PLIGHT_PROB_MULT"]])
+        out[i] = pp
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------- BASELINE configs

@@ -8,7 +8,8 @@ SURVEY.md 8c, seed 777).
   test_42          BASELINE config C1: teapot 25,600 triangles + box + light quad; Lambert (+texture), Phong blend, emissive; rect light; DOF
   test_42_ggx      the same with a GGX reflection layer
   test_224_sphere  another teapot, a rect and a SPHERE area light
-  test_42_beckmann, test_224_sphere_microfacet   the same two with brdf_type="torranse_sparrow" (Blinn distribution) reflection layers"""
+  test_42_beckmann, test_224_sphere_microfacet   the same two with brdf_type="torranse_sparrow" (Blinn distribution) reflection layers
+  test_42_with_mirror  mirror material (glossiness 1), a black sky-dome "environment" light beside the rect light, "30 30 30" multiplier"""
 import os
 import sys
 
@@ -21,7 +22,7 @@ from hydracore_b200 import hydra_scene as HS  # noqa: E402
 from tests import refapi  # noqa: E402
 
 REF = os.environ.get("HYDRA_REFERENCE", "/root/reference")
-SCENES = ("test_42", "test_42_ggx", "test_224_sphere", "test_42_beckmann", "test_224_sphere_microfacet")
+SCENES = ("test_42", "test_42_ggx", "test_224_sphere", "test_42_beckmann", "test_224_sphere_microfacet", "test_42_with_mirror")
 
 
 def main():
