@@ -318,11 +318,14 @@ def run_ours(args):
                                   ("c3", "C3: MISPT trace_depth 8, Lambert/GGX/glass/blend + 2 area lights, 1,001,116 triangles, 1080p, 32x32 interleaved tiles",
                                    lambda: S.scene_c3(WIDTH, HEIGHT)),
                                   ("c4", "C4: MISPT trace_depth 5 on 200 instances x 100,352 triangles = 20,070,400 instanced triangles, Lambert, 1080p, 32x32 interleaved tiles",
-                                   lambda: S.scene_c4(WIDTH, HEIGHT))):
+                                   lambda: S.scene_c4(WIDTH, HEIGHT)),
+                                  ("c5", "C5: MISPT-QMC (Sobol-Niederreiter screen + lens dimensions) on the C3 scene at 3840x2160; rank g takes the sample indices "
+                                         "i = g (mod G) of every pass into a full-size SUM buffer, one NCCL reduce of 8,294,400 x float4",
+                                   lambda: S.scene_c3(3840, 2160))):
             scn3 = build()
             lay = hc.CudaLayer(device=local)
             lay.LoadScene(scn3)
-            integ = 0 if key == "c1" else 2            # C1 is quoted on unidirectional PT (INTEGRATOR_PT = 0), C3 / C4 on MISPT (= 2)
+            integ = {"c1": 0, "c5": 3}.get(key, 2)     # C1: unidirectional PT (INTEGRATOR_PT = 0); C3 / C4: MISPT (= 2); C5: MISPT-QMC (= 3)
             lay.SetTiles(32, rank, world)
             lay.InitPathTracing(777)
             lay.TracingPass(integ, 2)                  # warm-up passes
@@ -353,6 +356,9 @@ def run_ours(args):
                            "stage_note": "closest-hit and any-hit launches of a bounce overlap on two streams: shadow_added = time from the end of the closest-hit launch to the join",
                            "reduce_ms": 1e3*mx[2], "reduce_bytes": scn3.width*scn3.height*16 if world > 1 else 0, "mean_radiance": mean_img,
                            "scaling": "strong (one frame split over the ranks)"}
+            if key == "c5":
+                extras[key]["spp_per_s"] = passes/mx[0]            # one pass of all ranks together = 1 sample per pixel of the 4K frame
+                extras[key]["partition"] = "Sobol sample index i = g (mod G); samples land on arbitrary pixels, so every rank keeps a full-size SUM buffer"
             if key == "c1" and rank == 0 and world == 1 and not args.profile and not args.no_cpu_baseline:
                 # the reference's own CPU integrator (IntegratorStupidPT compiled in place, oracle/_ref) on the same scene, host cores
                 from tests import refapi
