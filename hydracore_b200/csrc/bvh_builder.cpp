@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -75,11 +76,41 @@ struct Tree
 
 struct Range { int32_t first, count; Box box; };
 
-static constexpr int kBins = 16;
+// Builder parameters (defaults from the sweep in DESIGN.md section 3: 32 bins, leaves of at most 2 triangles = one device pair record, SAH leaf
+// cost counted in pair records); the HC_BVH_* environment variables exist for that sweep only.
+static constexpr int kMaxBins = 64;
+static int EnvInt(const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; }
+static int kBins  = std::min(kMaxBins, std::max(4, EnvInt("HC_BVH_BINS", 32)));
+static int kBlock = std::max(1, EnvInt("HC_BVH_BLOCK", 2));
+static int kPick  = EnvInt("HC_BVH_PICK", 0);
+static int kMaxLeafEnv = EnvInt("HC_BVH_MAXLEAF", 2);
+static int kSweep = EnvInt("HC_BVH_SWEEP", 0);
 
 // one binned-SAH split of prims[first, first+count) ; returns the size of the left part (0 < L < count)
 static int32_t SplitSAH(std::vector<Prim>& P, int32_t first, int32_t count)
 {
+  if (count <= kSweep)                                 // small range: exact sweep over the centroid order on each axis
+  {
+    float bestCost = INFINITY; int bestAxis = -1; int32_t bestL = -1;
+    std::vector<float> rA(count);
+    for (int axis = 0; axis < 3; axis++)
+    {
+      std::sort(P.begin() + first, P.begin() + first + count, [axis](const Prim& a, const Prim& b) { return (&a.c.x)[axis] < (&b.c.x)[axis]; });
+      Box acc;
+      for (int32_t i = count - 1; i > 0; i--) { acc.grow(P[first + i].box); rA[i] = acc.area(); }
+      acc = Box();
+      for (int32_t i = 0; i < count - 1; i++)
+      {
+        acc.grow(P[first + i].box);
+        const int32_t nl = i + 1, nr = count - nl;
+        const float cost = acc.area()*float((nl + kBlock - 1)/kBlock) + rA[i + 1]*float((nr + kBlock - 1)/kBlock);
+        if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestL = nl; }
+      }
+    }
+    if (bestAxis != 2)
+      std::sort(P.begin() + first, P.begin() + first + count, [bestAxis](const Prim& a, const Prim& b) { return (&a.c.x)[bestAxis] < (&b.c.x)[bestAxis]; });
+    return bestL;
+  }
   Box cb;
   for (int32_t i = first; i < first + count; i++) cb.grow(P[i].c);
   const float ext[3] = { cb.hi.x - cb.lo.x, cb.hi.y - cb.lo.y, cb.hi.z - cb.lo.z };
@@ -90,13 +121,13 @@ static int32_t SplitSAH(std::vector<Prim>& P, int32_t first, int32_t count)
     if (!(ext[axis] > 0.0f)) continue;
     const float lo = (&cb.lo.x)[axis];
     const float k  = float(kBins)*(1.0f - 1e-6f)/ext[axis];
-    Box bb[kBins]; int32_t bc[kBins] = { 0 };
+    Box bb[kMaxBins]; int32_t bc[kMaxBins] = { 0 };
     for (int32_t i = first; i < first + count; i++)
     {
       int b = int(k*((&P[i].c.x)[axis] - lo)); b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
       bb[b].grow(P[i].box); bc[b]++;
     }
-    float rArea[kBins]; int32_t rCnt[kBins];
+    float rArea[kMaxBins]; int32_t rCnt[kMaxBins];
     Box acc; int32_t n = 0;
     for (int b = kBins - 1; b > 0; b--) { acc.grow(bb[b]); n += bc[b]; rArea[b] = acc.area(); rCnt[b] = n; }
     acc = Box(); n = 0;
@@ -104,8 +135,8 @@ static int32_t SplitSAH(std::vector<Prim>& P, int32_t first, int32_t count)
     {
       acc.grow(bb[b]); n += bc[b];
       if (n == 0 || rCnt[b + 1] == 0) continue;
-      // leaves hold up to 4 triangles: cost in units of started 4-blocks, like a triangle4 leaf
-      const float cost = acc.area()*float((n + 3)/4) + rArea[b + 1]*float((rCnt[b + 1] + 3)/4);
+      // leaf cost in units of started kBlock-triangle records (the device tests triangles in pairs)
+      const float cost = acc.area()*float((n + kBlock - 1)/kBlock) + rArea[b + 1]*float((rCnt[b + 1] + kBlock - 1)/kBlock);
       if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
     }
   }
@@ -143,7 +174,7 @@ static void BuildRec(Tree& T, int32_t nodeIdx, int32_t first, int32_t count, int
   {
     int best = -1; float bestA = -1.0f;
     for (int i = 0; i < np; i++)
-      if (parts[i].count > maxLeaf) { const float a = parts[i].box.area()*float(parts[i].count); if (a > bestA) { bestA = a; best = i; } }
+      if (parts[i].count > maxLeaf) { const float a = kPick ? parts[i].box.area() : parts[i].box.area()*float(parts[i].count); if (a > bestA) { bestA = a; best = i; } }
     if (best < 0) break;
     const Range r = parts[best];
     const int32_t L = SplitSAH(T.prims, r.first, r.count);
@@ -356,7 +387,7 @@ struct Builder
         M.tree.prims.push_back(p); M.box.grow(p.box);
       }
       if (M.tree.prims.empty()) return HC_E_ARG;
-      BuildTree(M.tree, 4);
+      BuildTree(M.tree, kMaxLeafEnv);
       M.built = true;
       meshDepth = std::max(meshDepth, M.tree.depth);
     }
