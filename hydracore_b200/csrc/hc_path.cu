@@ -460,7 +460,7 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
 {
   const unsigned char* g = ctx->globalsHead.data();
   auto gi = [&](int off) { int v; memcpy(&v, g + off, 4); return v; };
-  if (gi(HC_EG_sunNumber) != 0) { why = "sun lights are not supported yet"; return HC_E_ARG; }
+  // EngineGlobals::suns (soft directional lights, IHWLayerDataAssembler.cpp:421-450) are read only by sky portals, which are rejected below
   HcPathHost* p = PH(ctx);
   const std::vector<unsigned char>& gl = p->globalsHost;
   const int lightsNum = gi(HC_EG_lightsNum), lightsOffset = gi(HC_EG_lightsOffset);
@@ -477,12 +477,13 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
       if (!ctx->storage[HC_STORAGE_PDFS].ptr || tab < 0 || tab >= gi(HC_EG_pdfTableTableSize)) { why = "sky-dome light without a pdf table in the pdfs storage"; return HC_E_ARG; }
       continue;
     }
+    if (type == HC_PLAIN_LIGHT_TYPE_POINT_SPOT || type == HC_PLAIN_LIGHT_TYPE_DIRECT) continue;
     if (type == HC_PLAIN_LIGHT_TYPE_SPHERE || type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI)
     {
       if (flags & HC_LIGHT_HAS_IES) { why = "IES distributions are not supported yet"; return HC_E_ARG; }
       continue;
     }
-    if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "only area, sphere and omni point lights are supported yet"; return HC_E_ARG; }
+    if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "cylinder and mesh lights are not supported yet (area, sphere, point, spot, directional, sky-dome lights are)"; return HC_E_ARG; }
     if (flags & (HC_LIGHT_HAS_IES | HC_AREA_LIGHT_SKY_PORTAL | HC_LIGHT_IES_POINT_AREA)) { why = "IES / sky-portal area lights are not supported yet"; return HC_E_ARG; }
     if (tex != HC_INVALID_TEXTURE) { why = "textured area lights are not supported yet"; return HC_E_ARG; }
     if (spot != 0) { why = "area lights with a spot distribution are not supported yet"; return HC_E_ARG; }
@@ -749,6 +750,16 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   {
     float t = 0.0f; HC_CUDA(cudaEventElapsedTime(&t, p->evPool[2*k], p->evPool[2*k + 1]));
     cls[p->evClass[k]] += t;
+  }
+  if (getenv("HC_PT_LOG"))                    // per-launch device times of the last pass (class 0 closest, 1 shadow added, 2 shade, 3 raygen / sort)
+  {
+    int live[256]; HC_CUDA(cudaMemcpy(live, counts, sizeof(live), cudaMemcpyDeviceToHost));
+    for (int d = 0; d < nBounces && d < 255; d++) fprintf(stderr, "[hc_pt_pass] bounce %d live %d\n", d, live[d]);
+    for (size_t k = 0; k < p->evClass.size(); k++)
+    {
+      float t = 0.0f; HC_CUDA(cudaEventElapsedTime(&t, p->evPool[2*k], p->evPool[2*k + 1]));
+      fprintf(stderr, "[hc_pt_pass] launch %zu class %d %.1f us\n", k, p->evClass[k], 1e3f*t);
+    }
   }
   {
     int live[256]; HC_CUDA(cudaMemcpy(live, counts, sizeof(live), cudaMemcpyDeviceToHost));     // live paths per bounce of the last pass

@@ -1196,12 +1196,87 @@ HC_DEV float3 EnvironmentColor(const HcScene& s, float3 rayDir, float prevPdf, b
 }
 
 // LightSampleRev / lightEvalPDF dispatch (clight.h:1561-1633) over the light types hc_pt_init accepts
+// ---- spot and directional lights (clight.h:892-912, 1416-1506; MapSamplesToCone cglobals.h:1655-1680).  Both are delta lights (isPoint).
+#define HC_POINT_LIGHT_SPOT_COS1  14
+#define HC_POINT_LIGHT_SPOT_COS2  15
+#define HC_DIRECT_LIGHT_RADIUS1   14
+#define HC_DIRECT_LIGHT_RADIUS2   15
+#define HC_DIRECT_LIGHT_SSOFTNESS 16
+#define HC_DIRECT_LIGHT_ALPHA_TAN 17
+#define HC_DIRECT_LIGHT_ALPHA_COS 18
+HC_DEV float LocalSmoothstep(float edge0, float edge1, float x)                                                             // clight.h:7-12
+{
+  const float tVal = (x - edge0)/(edge1 - edge0);
+  const float t = fminf(fmaxf(tVal, 0.0f), 1.0f);
+  return t*t*(3.0f - 2.0f*t);
+}
+HC_DEV void SpotLightSampleRev(const float* L, float3 illum, HcShadowSample& out)                                            // clight.h:1432-1450
+{
+  const float3 samplePos = Mat3(L, HC_PLIGHT_POS_X), norm = Mat3(L, HC_PLIGHT_NORM_X);
+  const float hitDist = length(samplePos - illum);
+  const float3 rayDir = normalize(samplePos - illum);
+  const float cosT = fmaxf(dot((-1.0f)*rayDir, norm), 0.0f);                                // pointSpotLightAttenuation, clight.h:1416-1423
+  const float3 color = Mat3(L, HC_PLIGHT_COLOR_X)*LocalSmoothstep(L[HC_POINT_LIGHT_SPOT_COS2], L[HC_POINT_LIGHT_SPOT_COS1], cosT);
+  out.isPoint = true;
+  out.pos = samplePos;
+  out.color = color;
+  out.pdf = PdfAtoW(1.0f, hitDist, 1.0f);
+  out.maxDist = hitDist;
+  out.cosAtLight = fmaxf(-dot(rayDir, norm), 0.0f);
+}
+HC_DEV float3 MapSamplesToCone(float cosCutoff, float sx, float sy, float3 direction)
+{
+  const float cosTheta = (1.0f - sx) + sx*cosCutoff;
+  const float sinTheta = sqrtf(1.0f - cosTheta*cosTheta);
+  const float sinPhi = (float)sin(2.0*HC_M_PI_D*(double)sy);                                 // 2.0f*M_PI*sample.y with the <cmath> double M_PI
+  const float cosPhi = (float)cos(2.0*HC_M_PI_D*(double)sy);
+  const float3 dev = f3(cosPhi*sinTheta, sinPhi*sinTheta, cosTheta);
+  float3 nx, nzT;
+  CoordinateSystem(direction, nx, nzT);
+  const float3 ny = nzT, nz = direction;
+  return nx*dev.x + ny*dev.y + nz*dev.z;
+}
+HC_DEV float DirectLightAttenuation(const float* L, float3 illum)                                                            // clight.h:892-912
+{
+  const float3 lpos = Mat3(L, HC_PLIGHT_POS_X), norm = Mat3(L, HC_PLIGHT_NORM_X);
+  const float cosAlpha = dot(normalize(illum - lpos), norm);
+  if (!(cosAlpha > 0.0f)) return 0.0f;
+  const float sinAlpha = sqrtf(1.0f - cosAlpha*cosAlpha);
+  const float d = length(illum - lpos)*sinAlpha;
+  const float r1 = L[HC_DIRECT_LIGHT_RADIUS1], r2 = L[HC_DIRECT_LIGHT_RADIUS2];
+  return LocalSmoothstep(fmaxf(r2, r1), fminf(r2, r1), d);
+}
+HC_DEV void DirectLightSampleRev(const float* L, float3 rands, float3 illum, HcShadowSample& out)                            // clight.h:1478-1506
+{
+  const float3 lpos = Mat3(L, HC_PLIGHT_POS_X);
+  float3 norm = Mat3(L, HC_PLIGHT_NORM_X);
+  const float pdfW = 1.0f;
+  if (L[HC_DIRECT_LIGHT_SSOFTNESS] > 1e-5f) norm = MapSamplesToCone(L[HC_DIRECT_LIGHT_ALPHA_COS], rands.x, rands.y, norm);
+  const float3 AC = illum - lpos;
+  const float CBLen = dot(normalize(AC), norm)*length(AC);
+  out.isPoint = true;
+  out.pos = illum - norm*CBLen;
+  out.color = Mat3(L, HC_PLIGHT_COLOR_X)*DirectLightAttenuation(L, illum)*pdfW;
+  out.pdf = pdfW;
+  out.maxDist = CBLen;
+  out.cosAtLight = 1.0f;
+}
+HC_DEV float DirectLightEvalPDF(const float* L, float3 rayDir)                                                               // clight.h:1462-1476
+{
+  if (!(L[HC_DIRECT_LIGHT_SSOFTNESS] > 1e-5f)) return 1.0f;
+  const float tanAlpha = L[HC_DIRECT_LIGHT_ALPHA_TAN];
+  const float cosTheta = -dot(rayDir, Mat3(L, HC_PLIGHT_NORM_X));
+  return (float)(HC_M_PI_D*(double)(tanAlpha*tanAlpha)*(double)(cosTheta*cosTheta*cosTheta));
+}
+
 HC_DEV void LightSampleRev(const float* L, float3 rands, float3 illum, const HcScene& s, HcShadowSample& out)
 {
   const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
   if (type == HC_PLAIN_LIGHT_TYPE_SKY_DOME) SkyLightSampleRev(L, rands, illum, s, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_SPHERE) SphereLightSampleRev(L, rands, illum, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI) PointLightSampleRev(L, illum, out);
+  else if (type == HC_PLAIN_LIGHT_TYPE_POINT_SPOT) SpotLightSampleRev(L, illum, out);
+  else if (type == HC_PLAIN_LIGHT_TYPE_DIRECT) DirectLightSampleRev(L, rands, illum, out);
   else AreaLightSampleRev(L, rands, illum, out);
 }
 
@@ -1210,7 +1285,9 @@ HC_DEV float LightEvalPDF(const float* L, float3 illum, float3 rayDir, float3 lp
   const float hitDist = length(illum - lpos);
   const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
   if (type == HC_PLAIN_LIGHT_TYPE_SPHERE) return SphereLightEvalPDF(L, illum, lpos, lnorm);
-  if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI) return PdfAtoW(1.0f, length(Mat3(L, HC_PLIGHT_POS_X) - illum), 1.0f);       // pointLightEvalPDF, clight.h:1387-1392
+  if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI || type == HC_PLAIN_LIGHT_TYPE_POINT_SPOT)                                    // pointLightEvalPDF / spotLightEvalPDF,
+    return PdfAtoW(1.0f, length(Mat3(L, HC_PLIGHT_POS_X) - illum), 1.0f);                                                  // clight.h:1387-1392, 1425-1430
+  if (type == HC_PLAIN_LIGHT_TYPE_DIRECT) return DirectLightEvalPDF(L, rayDir);
   return AreaLightEvalPDF(L, rayDir, hitDist);
 }
 

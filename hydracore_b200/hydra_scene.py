@@ -89,6 +89,14 @@ def parse_library(xml_path, mesh_fallback_dirs=()):
         out["lights"][int(l.get("id"))] = dict(type=l.get("type"), shape=l.get("shape", "point"), half=half, radius=float(size.get("radius", "0")) if size is not None else 0.0,
                                                 color=[c*mult for c in _floats(_val(col, "1 1 1"))], mat_id=int(l.get("mat_id", "-1")),
                                                 textured=col is not None and col.find("texture") is not None, perez=l.find("perez") is not None)
+        d = out["lights"][int(l.get("id"))]
+        if l.get("type") == "directional" or l.get("distribution") == "directional":        # CreateDirectLightFromXmlNode, PlainLightConverter.cpp:840-855
+            soft = float(_val(l.find("shadow_softness"), "0"))
+            d.update(type="directional", shape="point", params=[float(size.get("inner_radius", "0")) if size is not None else 0.0,
+                                                                 float(size.get("outer_radius", "0")) if size is not None else 0.0,
+                                                                 float(_val(l.find("angle_radius"), "0")) if l.find("angle_radius") is not None else 0.25*soft])
+        elif l.get("shape", "point") == "point" and l.get("distribution") == "spot":           # CreatePointSpotLightFromXmlNode, :895-906
+            d.update(type="spot", params=[float(_val(l.find("falloff_angle"), "0")), float(_val(l.find("falloff_angle2"), "0")), 0.0])
     cam = root.find("cam_lib")[0]
     g = lambda n, dflt: _val(cam.find(n), dflt)
     out["camera"] = dict(fov=float(g("fov", "45")), near=float(g("nearClipPlane", "0.01")), far=float(g("farClipPlane", "100")), up=_floats(g("up", "0 1 0")),
@@ -138,11 +146,19 @@ def build_scene(lib, width, height):
             idx = scn.add_light(M.sphere_light(tuple(mtx[:3, 3]), l["radius"]*scale, tuple(l["color"])))
         elif l["type"] == "point" and l["shape"] == "point":
             idx = scn.add_light(M.point_light(tuple(mtx[:3, 3]), tuple(l["color"])))
+        elif l["type"] == "spot":
+            L = M.spot_light(tuple(mtx[:3, 3]), (0.0, -1.0, 0.0), tuple(l["color"]), l["params"][0], l["params"][1])
+            L[5:8] = mtx[:3, :3] @ np.array([0.0, -1.0, 0.0], np.float32)            # Transform() rotates the axis without re-normalising it (:606-618)
+            idx = scn.add_light(L)
+        elif l["type"] == "directional":
+            L = M.direct_light(tuple(mtx[:3, 3]), (0.0, -1.0, 0.0), tuple(l["color"]), l["params"][0], l["params"][1], l["params"][2])
+            L[5:8] = mtx[:3, :3] @ np.array([0.0, -1.0, 0.0], np.float32)
+            idx = scn.add_light(L)
         elif l["type"] == "sky" and not l.get("textured") and not l.get("perez"):
             # constant-colour environment: 2x2 uniform pdf table (RenderDriverRTE_PdfTables.cpp:534-544); a black one is never picked
             idx = scn.add_light(M.sky_light(tuple(l["color"]), scn.add_sky_pdf_table()))
         else:
-            raise ValueError("light %d: type %s / shape %s is not supported yet (rect and sphere area lights, omni point lights, untextured sky domes are)" % (li["light_id"], l["type"], l["shape"]))
+            raise ValueError("light %d: type %s / shape %s is not supported yet (rect and sphere area lights, omni / spot point lights, directional lights, untextured sky domes are)" % (li["light_id"], l["type"], l["shape"]))
         linst_map[li["id"]] = idx
         light_map.setdefault(li["light_id"], idx)
     mat_map = {}
@@ -204,8 +220,8 @@ def _fixture_arrays(lib):
                     (ref["color"] + [ref["gloss"], float(_BRDF_CODE[ref["brdf"]]), 1.0 if ref["fresnel"] else 0.0, ref["ior"]] if ref else [0, 0, 0, -1, 0, 0, 0]) +
                     (d["emission"] if "emission" in d else [-1, -1, -1]))
     a["materials"] = np.array(mats, np.float64)
-    shapes = {"rect": 0, "sphere": 1, "point": 2, "sky": 3}
-    a["lights"] = np.array([[lid] + list(l["half"]) + l["color"] + [l["mat_id"], shapes["sky" if l["type"] == "sky" else l["shape"]], l["radius"]] for lid, l in sorted(lib["lights"].items())], np.float64)
+    shapes = {"rect": 0, "sphere": 1, "point": 2, "sky": 3, "spot": 4, "directional": 5}
+    a["lights"] = np.array([[lid] + list(l["half"]) + l["color"] + [l["mat_id"], shapes[l["type"] if l["type"] in ("sky", "spot", "directional") else l["shape"]], l["radius"]] + list(l.get("params", [0.0, 0.0, 0.0])) for lid, l in sorted(lib["lights"].items())], np.float64)
     a["light_instances"] = np.array([[li["id"], li["light_id"]] for li in lib["light_instances"]], np.int64).reshape(-1, 2)
     a["light_matrices"] = np.array([li["matrix"] for li in lib["light_instances"]], np.float32).reshape(-1, 4, 4)
     a["instances"] = np.array([[i["mesh_id"], i["light_id"], i.get("linst_id", -1)] for i in lib["instances"]], np.int64)
@@ -262,10 +278,11 @@ def load_fixture(path, scene):
         if r[13] >= 0:
             d["emission"] = list(r[13:16])
         lib["materials"][int(r[0])] = d
-    shapes = {0: ("area", "rect"), 1: ("area", "sphere"), 2: ("point", "point"), 3: ("sky", "point")}
+    shapes = {0: ("area", "rect"), 1: ("area", "sphere"), 2: ("point", "point"), 3: ("sky", "point"), 4: ("spot", "point"), 5: ("directional", "point")}
     for r in z["lights"]:
         ty, sh = shapes[int(r[7])]
-        lib["lights"][int(r[0])] = dict(type=ty, shape=sh, half=(float(r[1]), float(r[2])), color=list(r[3:6]), mat_id=int(r[6]), radius=float(r[8]))
+        lib["lights"][int(r[0])] = dict(type=ty, shape=sh, half=(float(r[1]), float(r[2])), color=list(r[3:6]), mat_id=int(r[6]), radius=float(r[8]),
+                                        params=[float(x) for x in r[9:12]] if len(r) >= 12 else [0.0, 0.0, 0.0])
     for r, mtx in zip(z["light_instances"], z["light_matrices"]):
         lib["light_instances"].append(dict(id=int(r[0]), light_id=int(r[1]), matrix=mtx))
     for r, mtx in zip(z["instances"], z["instance_matrices"]):

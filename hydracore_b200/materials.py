@@ -205,6 +205,34 @@ def point_light(pos, intensity, pick_prob=1.0):
     return L
 
 
+def spot_light(pos, direction, intensity, falloff_angle, falloff_angle2):
+    """Spot light (SpotLight + CreatePointSpotLightFromXmlNode, PlainLightConverter.cpp:568-626, 895-906): cone angles in degrees, full
+    intensity inside falloff_angle2 (cos1), smooth fall-off to zero at falloff_angle (cos2).  `direction` is the light's axis."""
+    L = point_light(pos, intensity)
+    L[C["PLIGHT_TYPE"]] = _i2f(C["PLAIN_LIGHT_TYPE_POINT_SPOT"])
+    d = np.asarray(direction, np.float32)
+    L[C["PLIGHT_NORM_X"]:C["PLIGHT_NORM_X"] + 3] = d/np.float32(np.linalg.norm(d))
+    deg = np.float32(np.pi/180.0)
+    L[14] = np.float32(np.cos(np.float32(0.5)*deg*np.float32(falloff_angle2)))       # POINT_LIGHT_SPOT_COS1
+    L[15] = np.float32(np.cos(np.float32(0.5)*deg*np.float32(falloff_angle)))        # POINT_LIGHT_SPOT_COS2
+    return L
+
+
+def direct_light(pos, direction, intensity, radius1, radius2, soft_angle_deg=0.0):
+    """Directional light (DirectLight, PlainLightConverter.cpp:500-566): parallel rays along `direction` inside a cylinder of radius1..radius2
+    (smooth fall-off between them) around the axis through `pos`; soft_angle_deg > 0 jitters the direction inside a cone (a "sun")."""
+    L = point_light(pos, intensity)
+    L[C["PLIGHT_TYPE"]] = _i2f(C["PLAIN_LIGHT_TYPE_DIRECT"])
+    d = np.asarray(direction, np.float32)
+    L[C["PLIGHT_NORM_X"]:C["PLIGHT_NORM_X"] + 3] = d/np.float32(np.linalg.norm(d))
+    alpha = np.float32(np.pi/180.0)*np.float32(soft_angle_deg)
+    L[14], L[15] = radius1, radius2                                                     # DIRECT_LIGHT_RADIUS1 / 2
+    L[16] = np.float32(soft_angle_deg)/np.float32(0.25)                                 # DIRECT_LIGHT_SSOFTNESS
+    L[17], L[18] = np.float32(np.tan(alpha)), np.float32(np.cos(alpha))                 # DIRECT_LIGHT_ALPHA_TAN / _COS
+    L[C["PLIGHT_SURFACE_AREA"]] = np.float32(np.pi)*np.float32(radius2)*np.float32(radius2)
+    return L
+
+
 def sky_light(color, pdf_table_id, pick_prob=1.0, tex_id=None, gamma=1.0):
     """Sky-dome light, optionally textured (environment map), without the Perez model (SkyDomeLight, PlainLightConverter.cpp:909-1060):
     identity sampler matrices, the pdf table built by Scene.add_sky_pdf_table (from the map's luminance when textured)."""

@@ -527,6 +527,15 @@ class Scene:
                 with np.errstate(divide="ignore", invalid="ignore"):
                     lights[:, slot] = w*(np.float32(1.0)/acc)                                # stored per light, then normalised (RenderDriverRTE.cpp:1509-1516)
                 prefs[fwd] = pref
+            # EngineGlobals::suns: SetAllPODLights copies the FIRST soft directional light into every one of the MAX_SUN_NUM = 8 slots (its search
+            # restarts from light 0 for each slot, IHWLayerDataAssembler.cpp:421-450), with the pick probabilities already normalised
+            # (RenderDriverRTE.cpp:1503-1520)
+            li = lights.view(np.int32)
+            soft = [i for i in range(nl) if li[i, C["PLIGHT_TYPE"]] == C["PLAIN_LIGHT_TYPE_DIRECT"] and lights[i, 16] > np.float32(1e-6)]   # DIRECT_LIGHT_SSOFTNESS
+            if soft:
+                for k in range(8):
+                    blob[C["EG_suns"]//4 + k*128:C["EG_suns"]//4 + (k + 1)*128] = li[soft[0]]
+                blob[C["EG_sunNumber"]//4] = 8
             blob[offs["lselRev"]:offs["lselRev"] + nl + 1] = prefs[False].view(np.int32)
             blob[offs["lselFwd"]:offs["lselFwd"] + nl + 1] = prefs[True].view(np.int32)
             blob[offs["lights"]:offs["lights"] + nl*128] = lights.reshape(-1).view(np.int32)

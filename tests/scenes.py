@@ -149,6 +149,26 @@ def cornell_sphere_and_point_lights(width=96, height=96):
     return scn.build()
 
 
+def cornell_spot_and_direct_lights(width=96, height=96, soft_sun=True):
+    """The Cornell room lit only by delta lights: a spot light from the ceiling and a directional light through the open front (a soft
+    one - a "sun" with a 2-degree cone - or a perfectly parallel one)."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    ggxm = scn.add_material(M.ggx((0.8, 0.6, 0.2), 0.7))
+    phg = scn.add_material(M.phong((0.7, 0.7, 0.8), 0.8))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, white, white, white), inward=True, skip_faces=(4,))))
+    sph = S.sphere_mesh(1.0, 32, 16)
+    for mat, mtx in ((ggxm, S.translate(-2.0, -2.8, -1.0) @ S.scale(1.2, 1.2, 1.2)), (phg, S.translate(1.8, -2.9, 1.2) @ S.scale(1.1, 1.1, 1.1))):
+        scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, mat, np.int32))), mtx)
+    scn.add_light(M.spot_light((0.5, 3.6, 0.5), (-0.2, -1.0, -0.1), (60.0, 55.0, 40.0), falloff_angle=100.0, falloff_angle2=60.0))
+    scn.add_light(M.direct_light((6.0, 5.0, 12.0), (-0.45, -0.4, -0.8), (2.0, 2.2, 2.6), radius1=3.0, radius2=5.0, soft_angle_deg=2.0 if soft_sun else 0.0))
+    return scn.build()
+
+
 def open_box_under_sky(width=96, height=96, with_area_light=True, env_map=False):
     """Objects on a floor under a uniform sky-dome light (plus, optionally, a rect area light): rays that leave the scene pick up the
     environment colour with MIS, the sky is sampled through its pdf table."""

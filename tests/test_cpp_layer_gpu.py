@@ -96,10 +96,11 @@ def test_ihwlayer_qmc_and_equivalence_with_c_abi_path(consts, golden, layer):
     lay.close()
 
 
-def test_reference_assembled_globals_equal_python_packer(consts):
+@pytest.mark.parametrize("which", ["cornell", "delta_lights_with_sun"])
+def test_reference_assembled_globals_equal_python_packer(consts, which):
     """IHWLayerDataAssembler.cpp (reference code, compiled in place) vs hydracore_b200/scene.py::_pack_globals."""
     C = consts
-    scn = scenes.cornell(64, 48, two_lights=True, dof=True)
+    scn = scenes.cornell(64, 48, two_lights=True, dof=True) if which == "cornell" else scenes.cornell_spot_and_direct_lights(64, 48, True)
     lay = _make(scn, consts)
     ref = lay.EngineGlobalsBlob()
     ours = scn.globals_blob
@@ -119,6 +120,8 @@ def test_reference_assembled_globals_equal_python_packer(consts):
     assert same(C["EG_imagePlaneDist"], 4)
     for k in ("EG_lightsNum", "EG_skyLightId", "EG_sunNumber", "EG_materialsTableSize", "EG_geometryTableSize", "EG_lightSelectorTableSizeRev"):
         assert ref[C[k]//4] == ours[C[k]//4], k
+    assert ref[C["EG_sunNumber"]//4] == (8 if which == "delta_lights_with_sun" else 0)      # the first soft directional light, MAX_SUN_NUM times
+    assert same(C["EG_suns"], 8*512)
     assert same(C["EG_m_essGgx2017Table"], 64*64*2) or scn.ms_tables is None
     nl = ref[C["EG_lightsNum"]//4]
     lr, lo = ref[C["EG_lightsOffset"]//4], ours[C["EG_lightsOffset"]//4]
