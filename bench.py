@@ -322,6 +322,8 @@ def run_ours(args):
                                   ("c5", "C5: MISPT-QMC (Sobol-Niederreiter screen + lens dimensions) on the C3 scene at 3840x2160; rank g takes the sample indices "
                                          "i = g (mod G) of every pass into a full-size SUM buffer, one NCCL reduce of 8,294,400 x float4",
                                    lambda: S.scene_c3(3840, 2160))):
+            if args.profile and key != "c3":
+                continue                               # profiler runs: the C2 steps and the C3 passes only (keeps the ncu launch list short and stable)
             scn3 = build()
             lay = hc.CudaLayer(device=local)
             lay.LoadScene(scn3)
