@@ -42,6 +42,7 @@ SIGNATURES = {
     "hc_storage_capacity": (_I, [_P, _I, ct.POINTER(_U64)]),
     "hc_set_globals": (_I, [_P, _P, _U64]),
     "hc_set_bvh": (_I, [_P, _I, _P, _I, _P, _I, _I]),
+    "hc_set_bvh_alpha": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I]),
     "hc_bvh_device_layout": (_I, [_P, _I, _P, _I, _P, _P, _I64, ct.POINTER(_I64), ct.POINTER(_I)]),
     "hc_set_inst_matrices": (_I, [_P, _P, _I]),
     "hc_set_inst_light_ids": (_I, [_P, _P, _I]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "hc_bvh_destroy": (None, [_P]),
     "hc_bvh_add_mesh": (_I, [_P, _P, _I, _P, _I, ct.POINTER(_I)]),
     "hc_bvh_add_instance": (_I, [_P, _I, _P, ct.POINTER(_I)]),
+    "hc_bvh_add_instance_id": (_I, [_P, _I, _P, _I]),
     "hc_bvh_commit": (_I, [_P]),
     "hc_bvh_result": (_I, [_P, _PP, ct.POINTER(_I), _PP, ct.POINTER(_I), _PP, ct.POINTER(_I), ct.POINTER(_I)]),
     "hc_bvh_bounds": (_I, [_P, ct.POINTER(ct.c_float), ct.POINTER(ct.c_float)]),

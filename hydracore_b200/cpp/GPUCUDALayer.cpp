@@ -79,13 +79,20 @@ void GPUCUDALayer::SetAllBVH4(const ConvertionResult& a_convertedBVH, IBVHBuilde
 {
   (void)a_inBuilderAPI; (void)a_flags;
   if (a_convertedBVH.treesNum < 1) Check(HC_E_ARG, "SetAllBVH4 (no trees)");
-  for (int i = 1; i < a_convertedBVH.treesNum; i++)
-    if (a_convertedBVH.nodesNum[i] > 4 && a_convertedBVH.pTriangleAlpha[i] != nullptr)
-      Check(HC_E_ARG, "SetAllBVH4 (tree with an alpha-test table: opacity-mapped meshes are not supported yet)");
-  const bool haveInst = (std::string(a_convertedBVH.bvhType[0] ? a_convertedBVH.bvhType[0] : "") != "triangle4v");       // GPUOCLData.cpp:118
+  if (a_convertedBVH.treesNum > 2) Check(HC_E_ARG, "SetAllBVH4 (more than two BVH trees: the driver uses tree 0 for opaque meshes and tree 1 for meshes with opacity maps)");
+  if (a_convertedBVH.pTriangleAlpha[0] != nullptr) Check(HC_E_ARG, "SetAllBVH4 (alpha-test table on tree 0 is not supported)");
   // the ConvertionResult pointers die at ConvertUnmap (RenderDriverRTE.cpp:1436): hc_set_bvh converts and uploads before it returns
-  Check(hc_set_bvh(m_ctx, 0, a_convertedBVH.pBVH[0], a_convertedBVH.nodesNum[0], a_convertedBVH.pTriangleData[0], a_convertedBVH.trif4Num[0], haveInst ? 1 : 0),
-        "SetAllBVH4 (hc_set_bvh)");
+  for (int i = 0; i < a_convertedBVH.treesNum; i++)
+  {
+    if (i > 0 && a_convertedBVH.nodesNum[i] <= 4) continue;                                                                  // empty second tree
+    const bool haveInst = (std::string(a_convertedBVH.bvhType[i] ? a_convertedBVH.bvhType[i] : "") != "triangle4v");       // GPUOCLData.cpp:118
+    if (i == 0)
+      Check(hc_set_bvh(m_ctx, 0, a_convertedBVH.pBVH[0], a_convertedBVH.nodesNum[0], a_convertedBVH.pTriangleData[0], a_convertedBVH.trif4Num[0], haveInst ? 1 : 0),
+            "SetAllBVH4 (hc_set_bvh)");
+    else                                                                                                                     // tree 1 + pTriangleAlpha (may be null), GPUOCLData.cpp:103-116
+      Check(hc_set_bvh_alpha(m_ctx, i, a_convertedBVH.pBVH[i], a_convertedBVH.nodesNum[i], a_convertedBVH.pTriangleData[i], a_convertedBVH.trif4Num[i],
+                             a_convertedBVH.pTriangleAlpha[i], a_convertedBVH.triAfNum[i], haveInst ? 1 : 0), "SetAllBVH4 (hc_set_bvh_alpha)");
+  }
 }
 
 void GPUCUDALayer::SetAllInstMatrices(const float4x4* a_matrices, int32_t a_matrixNum)

@@ -99,6 +99,20 @@ int hl_set_bvh(void* p, const void* nodes, int nodesNum, const float* trif4, int
     s->layer->SetAllBVH4(r, nullptr, 0);
   });
 }
+int hl_set_bvh2(void* p, const void* nodes, int nodesNum, const float* trif4, int trif4Num, const void* nodes1, int nodesNum1, const float* trif41, int trif4Num1,
+                const void* alpha1, int alphaNum1, const char* bvhType)
+{
+  Session* s = static_cast<Session*>(p);
+  return Guard([&]
+  {
+    ConvertionResult r;
+    r.treesNum = 2;
+    r.bvhType[0] = bvhType; r.pBVH[0] = static_cast<const BVHNode*>(nodes); r.nodesNum[0] = nodesNum; r.pTriangleData[0] = trif4; r.trif4Num[0] = trif4Num;
+    r.bvhType[1] = bvhType; r.pBVH[1] = static_cast<const BVHNode*>(nodes1); r.nodesNum[1] = nodesNum1; r.pTriangleData[1] = trif41; r.trif4Num[1] = trif4Num1;
+    r.pTriangleAlpha[1] = static_cast<const uint2*>(alpha1); r.triAfNum[1] = alphaNum1;
+    s->layer->SetAllBVH4(r, nullptr, 0);
+  });
+}
 int hl_set_instances(void* p, const float* invMatrices16, const int32_t* lightInstIds, int n)
 {
   Session* s = static_cast<Session*>(p);

@@ -223,7 +223,7 @@ struct Mesh
   int64_t subtreeRef = -1;        // leftOffsetAndLeaf of the flattened mesh root (shared by its instances)
 };
 
-struct Instance { int meshId; float m[16]; /* row-major */ float inv[16]; /* 4 columns */ Box worldBox; };
+struct Instance { int meshId; int realId = -1; /* id written into the instance record; -1 = index in this builder */ float m[16]; /* row-major */ float inv[16]; /* 4 columns */ Box worldBox; };
 
 static void Inverse4x4Columns(const float rowMajor[16], float outCols[16])
 {
@@ -338,7 +338,7 @@ struct Builder
     Node32 n0 = InvalidNode(); SetBox(n0, meshes[I.meshId].box); n0.leftOffsetAndLeaf = sub; n0.escapeIndex = 0;
     nodes[q] = n0;
     std::memcpy(&nodes[q + 1], I.inv, 64);                      // float4 idx 8Q+2 .. 8Q+5 = inverse matrix columns
-    int32_t rec[8] = { instId, I.meshId, 0, 0, 0, 0, 0, 0 };
+    int32_t rec[8] = { I.realId >= 0 ? I.realId : instId, I.meshId, 0, 0, 0, 0, 0, 0 };
     std::memcpy(&nodes[q + 3], rec, 32);                        // float4 idx 8Q+6 = int4{instId, meshId, 0, 0}
     return uint32_t(q/4);
   }
@@ -370,6 +370,9 @@ struct Builder
     {
       Mesh& M = meshes[mi];
       M.subtreeRef = -1;
+      bool used = false;
+      for (const Instance& I : insts) if (I.meshId == int(mi)) { used = true; break; }
+      if (!used) continue;                       // meshes of the other tree (one builder per tree, mesh ids shared: they are the geomId of the triangles)
       if (M.built) { meshDepth = std::max(meshDepth, M.tree.depth); continue; }
       const int32_t nt = int32_t(M.idx.size()/3);
       M.tree.prims.clear(); M.tree.prims.reserve(nt);
@@ -476,6 +479,14 @@ int hc_bvh_add_instance(hc_bvh* b, int meshId, const float* matrixRowMajor16, in
   b->b.committed = false;
   if (outInstId) *outInstId = int(b->b.insts.size()) - 1;
   return HC_OK;
+}
+
+int hc_bvh_add_instance_id(hc_bvh* b, int meshId, const float* matrixRowMajor16, int realInstId)
+{
+  if (!b || realInstId < 0) return HC_E_ARG;
+  const int rc = hc_bvh_add_instance(b, meshId, matrixRowMajor16, nullptr);
+  if (rc == HC_OK) b->b.insts.back().realId = realInstId;
+  return rc;
 }
 
 int hc_bvh_commit(hc_bvh* b) { return b ? b->b.Commit() : HC_E_ARG; }

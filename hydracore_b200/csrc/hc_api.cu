@@ -43,7 +43,10 @@ void hc_buf_free(HcDevBuf& b) { if (b.ptr) cudaFree(b.ptr); b.ptr = nullptr; b.b
 // Between refills a lane runs the while-while loop of hc_trace.cuh: descend through interior quads until a leaf is reached, then
 // intersect (or enter the instance); the loop is left early once so few lanes are still busy that a refill pays off.
 // rpos/rdir are float4 streams with element stride `stride` (2 = interleaved {pos,dir} records, 1 = separate arrays).
-template<bool ANYHIT>
+// ALPHA (closest hit only): the second, alpha-tested tree of the reference (BVH4InstTraverseAlpha after BVH4InstTraverse in
+// IntegratorCommon::rayTrace, CPUExp_Integrators_Common.cpp:122-150): starts from the hit tree 0 left in hitsOut and keeps it unless a closer
+// triangle passes the opacity lookup.
+template<bool ANYHIT, int TREE1 = 0>      // TREE1: 0 = first tree, 1 = second tree (hit carried), 2 = second tree with the alpha table
 __global__ void __launch_bounds__(HC_TRACE_BLOCK, 6)   // 80 registers -> 6 CTAs (24 warps) per SM; capping at 72 / 64 registers for 7 / 8 CTAs measured slower
 k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long nArg,
         const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter, const int refillMin, const int tileW)
@@ -85,6 +88,11 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
           const float4 p = __ldg(rpos + idx*stride), dd = __ldg(rdir + idx*stride);
           rayIdx = idx; idle = false;
           TravStart(r, bvh, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
+          if (TREE1 != 0)
+          {
+            const float4 h = reinterpret_cast<const float4*>(hitsOut)[idx];      // Lite_Hit carried from tree to tree
+            r.t = h.x; r.primId = __float_as_int(h.y); r.hitInst = __float_as_int(h.z); r.geomId = __float_as_int(h.w);
+          }
           if (ANYHIT && !(dd.w > 0.0f)) { visOut[idx] = 1; idle = true; r.node = HC_NODE_SENTINEL; }          // maxDist <= 0: lit (trace.cl:343-351)
           else if (!RayIsFinite(r.o, r.d)) r.node = HC_NODE_SENTINEL;              // every comparison of the reference fails on NaN: no hit
         }
@@ -114,7 +122,7 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
           else
           {
             bool done;
-            const bool found = TravLeafPair(r, bvh, &done);
+            const bool found = TravLeafPair<TREE1 == 2>(r, bvh, &done);
             if (ANYHIT && found) r.node = HC_NODE_SENTINEL;
             else if (done) HC_POP(r, bvh, stk)
           }
@@ -189,6 +197,28 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, tileW);
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
+  if (!anyHit && ctx->haveTree1)
+  {
+    // IntegratorCommon::rayTrace walks the trees one after another with the hit carried along (CPUExp_Integrators_Common.cpp:131-147);
+    // its shadowTrace looks at tree 0 only (:163-171), so the any-hit launch above is all a shadow ray gets - meshes with opacity maps
+    // cast no shadows in the CPU integrators, and none here
+    HcBvh b1; b1.nodes = (const float4*)ctx->bvh1Nodes.ptr; b1.tris = (const float4*)ctx->bvh1Tris.ptr;
+    ctx->traceCounterSlot = (ctx->traceCounterSlot + 1) % 32;
+    unsigned long long* counter1 = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
+    HC_CUDA(cudaMemsetAsync(counter1, 0, sizeof(unsigned long long), stream));
+    if (ctx->haveAlpha1)
+    {
+      int texTab = 0; memcpy(&texTab, ctx->globalsHead.data() + HC_EG_texturesTableOffset, 4);
+      HC_REQUIRE(ctx->globals.ptr && ctx->storage[HC_STORAGE_TEXTURES].ptr, HC_E_STATE, "hc_trace: the alpha-tested tree needs the textures storage and the globals (texture table)");
+      b1.alphaPairs = (const uint4*)ctx->bvh1AlphaPairs.ptr; b1.alphaTable = (const uint2*)ctx->bvh1AlphaTable.ptr;
+      b1.textures = (const int4*)ctx->storage[HC_STORAGE_TEXTURES].ptr; b1.texturesTable = (const int*)ctx->globals.ptr + texTab;
+      k_trace<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, tileW);
+    }
+    else
+      k_trace<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, tileW);
+    HC_CUDA(cudaGetLastError());
+    ctx->stats.kernelLaunches++;
+  }
   if (!nDev) { if (anyHit) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n; }   // counted launches: hc_pt_pass reads the live counts back
   return HC_OK;
 }
@@ -203,7 +233,8 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
 //                     IntersectAllPrimitivesInLeaf does (ctrace.h:159-160); an odd leaf is padded with a zero triangle, whose
 //                     determinant is 0 -> v = u = t = NaN -> every acceptance test fails.
 static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const float* trif4, int trif4Num,
-                               std::vector<float>& outNodes, std::vector<float>& outPairs, int* outStackBound)
+                               std::vector<float>& outNodes, std::vector<float>& outPairs, int* outStackBound,
+                               const unsigned* alphaU2 = nullptr, int alphaNum = 0, std::vector<unsigned>* outAlphaPairs = nullptr)
 {
   struct N { float bmin[3]; unsigned lo; float bmax[3]; unsigned esc; };
   const N* nd = (const N*)nodes;
@@ -228,6 +259,18 @@ static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const f
     if (index + size_t(pairs) >= HC_LEAF_INDEX_MASK) return HC_E_RANGE;
     outPairs.resize(outPairs.size() + size_t(pairs)*HC_PAIR_F4*4, 0.0f);
     float* P = outPairs.data() + index*HC_PAIR_F4*4;
+    if (outAlphaPairs)
+    {
+      // per triangle {alpha[o].x (sampler offset), alpha[o].y, alpha[o+1].y, alpha[o+2].y (packed uv)}; the empty half of an odd pair never hits
+      if (size_t(first) + size_t(count)*3 > size_t(alphaNum)) return HC_E_RANGE;
+      outAlphaPairs->resize((index + size_t(pairs))*8, 0xFFFFFFFFu);
+      for (int k = 0; k < count; k++)
+      {
+        const unsigned* a = alphaU2 + (size_t(first) + size_t(k)*3)*2;
+        unsigned* o = outAlphaPairs->data() + (index + size_t(k/2))*8 + size_t(k & 1)*4;
+        o[0] = a[0]; o[1] = a[1]; o[2] = a[3]; o[3] = a[5];
+      }
+    }
     for (int k = 0; k < count; k++)
     {
       const float* A = trif4 + (size_t(first) + size_t(k)*3)*4; const float* B = A + 4; const float* C = A + 8;
@@ -341,7 +384,7 @@ void hc_ctx_destroy(hc_ctx* c)
   cudaStreamSynchronize(c->stream);
   hc_path_free(c);
   for (int i = 0; i < HC_STORAGE_COUNT; i++) hc_buf_free(c->storage[i]);
-  hc_buf_free(c->globals); hc_buf_free(c->bvhNodes); hc_buf_free(c->bvhTris); hc_buf_free(c->instMatrices); hc_buf_free(c->instLightIds);
+  hc_buf_free(c->globals); hc_buf_free(c->bvhNodes); hc_buf_free(c->bvhTris); hc_buf_free(c->bvh1Nodes); hc_buf_free(c->bvh1Tris); hc_buf_free(c->bvh1AlphaPairs); hc_buf_free(c->bvh1AlphaTable); hc_buf_free(c->instMatrices); hc_buf_free(c->instLightIds);
   hc_buf_free(c->fbSum); hc_buf_free(c->scratchRays); hc_buf_free(c->scratchOut); hc_buf_free(c->counters); hc_buf_free(c->pixelRng); hc_buf_free(c->qmcTable);
   hc_buf_free(c->rcRays); hc_buf_free(c->rcHits); hc_buf_free(c->rcSRays); hc_buf_free(c->rcVis);
   for (int i = 0; i < 5; i++) cudaEventDestroy(c->evStage[i]);
@@ -413,25 +456,50 @@ int hc_set_globals(hc_ctx* ctx, const void* blob, uint64_t bytes)
   return HC_OK;
 }
 
-int hc_set_bvh(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const void* trif4, int trif4Num, int haveInst)
+static int SetBvhTree(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const void* trif4, int trif4Num, const void* alphaTable, int alphaNum, int haveInst)
 {
   if (!ctx || !nodes || !trif4 || nodesNum < 8 || trif4Num < 4) return HC_E_ARG;
-  HC_REQUIRE(treeId == 0, HC_E_ARG, "hc_set_bvh: only tree 0 (opaque geometry) is supported; tree 1 holds alpha-tested meshes");
+  HC_REQUIRE(treeId == 0 || treeId == 1, HC_E_ARG, "hc_set_bvh: tree 0 (opaque geometry) and tree 1 (meshes with opacity maps) are supported");
+  HC_REQUIRE(treeId == 1 || alphaTable == nullptr, HC_E_ARG, "hc_set_bvh: an alpha table on tree 0 is not supported (the driver puts opacity meshes into tree 1)");
   HC_REQUIRE(haveInst != 0, HC_E_ARG, "hc_set_bvh: single-level trees (bvhType \"triangle4v\") are not supported, pass the two-level layout");
+  HC_REQUIRE(alphaTable == nullptr || alphaNum >= trif4Num, HC_E_ARG, "hc_set_bvh_alpha: the alpha table must cover every float4 of the triangle list");
   int bound = 0;
   std::vector<float> devNodes, devPairs;
-  int rc = ConvertBvhForDevice((const unsigned char*)nodes, nodesNum, (const float*)trif4, trif4Num, devNodes, devPairs, &bound);
+  std::vector<unsigned> devAlpha;
+  int rc = ConvertBvhForDevice((const unsigned char*)nodes, nodesNum, (const float*)trif4, trif4Num, devNodes, devPairs, &bound,
+                               (const unsigned*)alphaTable, alphaNum, alphaTable ? &devAlpha : nullptr);
   HC_REQUIRE(rc == HC_OK, rc, "hc_set_bvh: tree references nodes or triangles out of range (or a leaf holds more than 128 triangles)");
   HC_REQUIRE(bound <= HC_STACK_CAP, HC_E_RANGE, "hc_set_bvh: tree too deep for the traversal stack");
   HC_CUDA(cudaSetDevice(ctx->device));
-  rc = hc_buf_reserve(ctx, ctx->bvhNodes, devNodes.size()*4); if (rc) return rc;
-  rc = hc_buf_reserve(ctx, ctx->bvhTris, std::max<size_t>(devPairs.size()*4, 16)); if (rc) return rc;
-  HC_CUDA(cudaMemcpyAsync(ctx->bvhNodes.ptr, devNodes.data(), devNodes.size()*4, cudaMemcpyHostToDevice, ctx->stream));
-  if (!devPairs.empty()) HC_CUDA(cudaMemcpyAsync(ctx->bvhTris.ptr, devPairs.data(), devPairs.size()*4, cudaMemcpyHostToDevice, ctx->stream));
+  HcDevBuf& bn = treeId ? ctx->bvh1Nodes : ctx->bvhNodes;
+  HcDevBuf& bt = treeId ? ctx->bvh1Tris : ctx->bvhTris;
+  rc = hc_buf_reserve(ctx, bn, devNodes.size()*4); if (rc) return rc;
+  rc = hc_buf_reserve(ctx, bt, std::max<size_t>(devPairs.size()*4, 16)); if (rc) return rc;
+  HC_CUDA(cudaMemcpyAsync(bn.ptr, devNodes.data(), devNodes.size()*4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!devPairs.empty()) HC_CUDA(cudaMemcpyAsync(bt.ptr, devPairs.data(), devPairs.size()*4, cudaMemcpyHostToDevice, ctx->stream));
+  if (treeId == 1)
+  {
+    ctx->haveAlpha1 = false;
+    if (alphaTable)
+    {
+      rc = hc_buf_reserve(ctx, ctx->bvh1AlphaPairs, std::max<size_t>(devAlpha.size()*4, 16)); if (rc) return rc;
+      rc = hc_buf_reserve(ctx, ctx->bvh1AlphaTable, size_t(alphaNum)*8); if (rc) return rc;
+      if (!devAlpha.empty()) HC_CUDA(cudaMemcpyAsync(ctx->bvh1AlphaPairs.ptr, devAlpha.data(), devAlpha.size()*4, cudaMemcpyHostToDevice, ctx->stream));
+      HC_CUDA(cudaMemcpyAsync(ctx->bvh1AlphaTable.ptr, alphaTable, size_t(alphaNum)*8, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->haveAlpha1 = true;
+    }
+  }
   HC_CUDA(cudaStreamSynchronize(ctx->stream));                // ConvertionResult pointers die at ConvertUnmap (RenderDriverRTE.cpp:1436)
-  ctx->nodesNum = nodesNum; ctx->trif4Num = trif4Num; ctx->haveInst = haveInst; ctx->bvhDepthBound = bound;
+  if (treeId == 0) { ctx->nodesNum = nodesNum; ctx->trif4Num = trif4Num; ctx->haveInst = haveInst; ctx->bvhDepthBound = bound; ctx->haveTree1 = false; ctx->haveAlpha1 = false; }
+  else ctx->haveTree1 = true;
   return HC_OK;
 }
+
+// SetAllBVH4 sends every tree again: tree 0 first (which forgets a previous tree 1), then - if the scene has meshes with opacity maps - tree 1
+int hc_set_bvh(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const void* trif4, int trif4Num, int haveInst)
+{ return SetBvhTree(ctx, treeId, nodes, nodesNum, trif4, trif4Num, nullptr, 0, haveInst); }
+int hc_set_bvh_alpha(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const void* trif4, int trif4Num, const void* alphaTableUint2, int alphaNum, int haveInst)
+{ return SetBvhTree(ctx, treeId, nodes, nodesNum, trif4, trif4Num, alphaTableUint2, alphaNum, haveInst); }
 
 int hc_bvh_device_layout(const void* nodes, int nodesNum, const void* trif4, int trif4Num, float* outNodes, float* outPairs,
                          int64_t outPairsCapacityFloats, int64_t* outPairsFloats, int* outStackBound)

@@ -21,6 +21,7 @@
 //     global counter with ballot/popc aggregation (one atomic per refill).
 #pragma once
 #include "hc_math.cuh"
+#include "hc_texture.cuh"
 
 #define HC_LEAF_BIT      0x80000000u
 #define HC_NODE_SENTINEL 0xffffffffu   // "ray finished"; also the child word of an empty slot
@@ -40,6 +41,12 @@ struct HcBvh
 {
   const float4* __restrict__ nodes;   // device layout: 8 float4 per quad (SoA boxes + child words) or per instance record
   const float4* __restrict__ tris;    // device layout: pair records
+  // alpha-tested tree only (BVH4InstTraverseAlpha, ctrace.h:1297-1520): per pair record two uint4 {sampler offset, packed uv of A, B, C}
+  // taken from the reference's per-triangle alpha table, the table itself (its tail holds the opacity samplers), the texture storage
+  const uint4*  __restrict__ alphaPairs    = nullptr;
+  const uint2*  __restrict__ alphaTable    = nullptr;
+  const int4*   __restrict__ textures      = nullptr;
+  const int*    __restrict__ texturesTable = nullptr;   // EngineGlobals texture table: id -> float4 offset of the image header
 };
 
 HC_DEV float3 SafeInverse(float3 d)
@@ -203,8 +210,34 @@ HC_DEV void TravEnterInstance(HcRayTrav& r, const HcBvh& bvh)
 
 // triangle leaf: IntersectAllPrimitivesInLeaf (ctrace.h:124-182), ONE pair record (two triangles) per call; the leaf word itself is the
 // cursor (index up, count down).  Returns true when a hit was accepted; sets *done when the leaf is exhausted.
-HC_DEV bool PairTest(HcRayTrav& r, const float4* __restrict__ p)
+// decompressTexCoord16 (ctrace.h:316-326) and the opacity lookup of IntersectAllPrimitivesInLeafAlpha (ctrace.h:384-398) through
+// sample2DLite (cfetch.h:738-760): a hit counts when max(rgb) of the opacity texel exceeds 0.5
+HC_DEV float2 DecompressTexCoord16(unsigned packed)
 {
+  const float fx = (1.0f/65535.0f)*(float)(packed & 0x0000FFFFu), fy = (1.0f/65535.0f)*(float)((packed & 0xFFFF0000u) >> 16);
+  return make_float2(2.0f*fx - 1.0f, 2.0f*fy - 1.0f);
+}
+HC_DEV bool AlphaPass(const HcBvh& bvh, const uint4 a, float u, float v)
+{
+  if (a.x == 0xFFFFFFFFu || (int)a.x <= 0) return true;                         // no opacity map on this triangle: sample2DLite -> (1,1,1)
+  const float2 A = DecompressTexCoord16(a.y), B = DecompressTexCoord16(a.z), C = DecompressTexCoord16(a.w);
+  const float w = 1.0f - u - v;
+  const float2 tc = make_float2(w*A.x + v*B.x + u*C.x, w*A.y + v*B.y + u*C.y);
+  const uint2* sp = bvh.alphaTable + a.x;                                       // SWTexSampler {flags, gamma, texId, dummy, row0, row1} as six uint2
+  const uint2 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2), s3 = __ldg(sp + 3), s4 = __ldg(sp + 4), s5 = __ldg(sp + 5);
+  const int flags = (int)s0.x, texId = (int)s1.x; const float gamma = __uint_as_float(s0.y);
+  if (texId == 0) return true;
+  const float2 tct = make_float2(__uint_as_float(s2.x)*tc.x + __uint_as_float(s2.y)*tc.y + __uint_as_float(s3.y),
+                                 __uint_as_float(s4.x)*tc.x + __uint_as_float(s4.y)*tc.y + __uint_as_float(s5.y));     // mul2x4, cfetch.h:640-646
+  float4 c = ReadImageSw4(bvh.textures + bvh.texturesTable[texId], tct, flags, (gamma != 1.0f));
+  if (flags & HC_TEX_ALPHASRC_W) { c.x = c.w; c.y = c.w; c.z = c.w; }
+  return fmaxf(c.x, fmaxf(c.y, c.z)) > 0.5f;
+}
+
+template<bool ALPHA>
+HC_DEV bool PairTest(HcRayTrav& r, const HcBvh& bvh, const size_t pairIndex)
+{
+  const float4* __restrict__ p = bvh.tris + pairIndex*HC_PAIR_F4;
   HcVec2 O, D;
   O.x = bc2(r.o.x); O.y = bc2(r.o.y); O.z = bc2(r.o.z);
   D.x = bc2(r.d.x); D.y = bc2(r.d.y); D.z = bc2(r.d.z);
@@ -223,23 +256,25 @@ HC_DEV bool PairTest(HcRayTrav& r, const float4* __restrict__ p)
   upk2(mul2(dot2_xnynz(tvec, pvecN), invDet), v0, v1);
   upk2(mul2(dot2_xnynz(D, qvecN), invDet), u0, u1);                           // dot(qvec, ray_dir): products commute
   upk2(mul2(dot2_xnynz(E2, qvecN), invDet), t0, t1);
-  if (v0 > -HC_TRI_EPS && u0 > -HC_TRI_EPS && (u0 + v0 < 1.0f + HC_TRI_EPS) && t0 > 0.0f && t0 < r.t)
+  if (v0 > -HC_TRI_EPS && u0 > -HC_TRI_EPS && (u0 + v0 < 1.0f + HC_TRI_EPS) && t0 > 0.0f && t0 < r.t && (!ALPHA || AlphaPass(bvh, __ldg(bvh.alphaPairs + 2*pairIndex), u0, v0)))
   {
     r.t = t0; r.primId = __float_as_int(r4.z); r.geomId = __float_as_int(__ldg(p + 5).x); r.hitInst = r.instId; found = true;
   }
-  if (v1 > -HC_TRI_EPS && u1 > -HC_TRI_EPS && (u1 + v1 < 1.0f + HC_TRI_EPS) && t1 > 0.0f && t1 < r.t)     // sequential, like the reference loop
+  if (v1 > -HC_TRI_EPS && u1 > -HC_TRI_EPS && (u1 + v1 < 1.0f + HC_TRI_EPS) && t1 > 0.0f && t1 < r.t     // sequential, like the reference loop
+      && (!ALPHA || AlphaPass(bvh, __ldg(bvh.alphaPairs + 2*pairIndex + 1), u1, v1)))
   {
     r.t = t1; r.primId = __float_as_int(r4.w); r.geomId = __float_as_int(__ldg(p + 5).y); r.hitInst = r.instId; found = true;
   }
   return found;
 }
 
+template<bool ALPHA>
 HC_DEV bool TravLeafPair(HcRayTrav& r, const HcBvh& bvh, bool* done)
 {
-  const float4* p = bvh.tris + size_t(r.node & HC_LEAF_INDEX_MASK)*HC_PAIR_F4;
+  const size_t pairIndex = size_t(r.node & HC_LEAF_INDEX_MASK);
   *done = ((r.node >> HC_LEAF_PAIRS_SHIFT) & 63u) == 0u;
   r.node = r.node - (1u << HC_LEAF_PAIRS_SHIFT) + 1u;
-  return PairTest(r, p);
+  return PairTest<ALPHA>(r, bvh, pairIndex);
 }
 
 HC_DEV bool RayIsFinite(float3 o, float3 d)

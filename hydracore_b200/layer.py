@@ -41,8 +41,12 @@ class BvhBuilder:
         check(self._L.hc_bvh_add_mesh(self._h, _ptr(v), v.shape[0], _ptr(i), i.size, ct.byref(out)), "hc_bvh_add_mesh")
         return out.value
 
-    def add_instance(self, mesh_id, matrix_row_major):
+    def add_instance(self, mesh_id, matrix_row_major, real_id=None):
+        """real_id: the scene-wide instance id written into the instance record (one builder per BVH tree); default = index in this builder."""
         m = np.ascontiguousarray(matrix_row_major, dtype=np.float32).reshape(16)
+        if real_id is not None:
+            check(self._L.hc_bvh_add_instance_id(self._h, int(mesh_id), _ptr(m), int(real_id)), "hc_bvh_add_instance_id")
+            return int(real_id)
         out = ct.c_int()
         check(self._L.hc_bvh_add_instance(self._h, int(mesh_id), _ptr(m), ct.byref(out)), "hc_bvh_add_instance")
         return out.value
@@ -118,9 +122,13 @@ class CudaLayer:
         b = np.ascontiguousarray(blob_i32).view(np.uint8).reshape(-1)
         check(self._L.hc_set_globals(self._c, _ptr(b), b.size), "hc_set_globals")
 
-    def SetAllBVH4(self, nodes, tris, have_inst=True, tree=0):
+    def SetAllBVH4(self, nodes, tris, have_inst=True, tree=0, alpha=None):
         n = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1, 8)
         t = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 4)
+        if alpha is not None:
+            a = np.ascontiguousarray(alpha, dtype=np.uint32).reshape(-1, 2)
+            check(self._L.hc_set_bvh_alpha(self._c, tree, _ptr(n), n.shape[0], _ptr(t), t.shape[0], _ptr(a), a.shape[0], 1 if have_inst else 0), "hc_set_bvh_alpha")
+            return
         check(self._L.hc_set_bvh(self._c, tree, _ptr(n), n.shape[0], _ptr(t), t.shape[0], 1 if have_inst else 0), "hc_set_bvh")
 
     def SetAllInstMatrices(self, inv_matrices):
@@ -241,6 +249,8 @@ class CudaLayer:
         for name in ("textures", "textures_aux", "geom", "materials", "pdfs"):
             self.UploadStorage(name, scn.storages[name])
         self.SetAllBVH4(scn.bvh["nodes"], scn.bvh["tris"])
+        if getattr(scn, "bvh1", None) is not None:
+            self.SetAllBVH4(scn.bvh1["nodes"], scn.bvh1["tris"], tree=1, alpha=scn.bvh1["alpha"])
         self.SetAllInstMatrices(scn.bvh["inv_matrices"])
         self.SetAllInstLightInstId(scn.inst_light_ids)
         self.ResizeScreen(scn.width, scn.height)

@@ -49,6 +49,21 @@ def _color_slot(m, color, tex_id, texid_off, texmat_off, sampler_off, **kw):
         m[texmat_off] = _i2f(INVALID_TEXTURE)
 
 
+def with_opacity(nodes, tex_id, **kw):
+    """Opacity (cut-out) map on a material: IMaterial::SetOpacitySampler puts texture id, sampler index and the sampler into the HEAD node
+    (PlainMaterialConverter.cpp:1428-1443).  Meshes that use such a material go into the alpha-tested BVH tree (RenderDriverRTE.cpp:1989);
+    the texel's max(rgb) > 0.5 keeps the hit (ctrace.h:384-398).  Sampler keywords as for colour textures (flags, gamma, row0, row1)."""
+    nodes = [nodes] if isinstance(nodes, np.ndarray) and nodes.ndim == 1 else list(nodes)
+    head = nodes[0]
+    head[C["OPACITY_TEX_OFFSET"]] = _i2f(tex_id)
+    head[C["OPACITY_TEX_MATRIX"]] = _i2f(_sampler(head, C["OPACITY_SAMPLER_OFFSET"], tex_id, **kw))
+    return nodes
+
+
+def opacity_tex_id(head_node):
+    return int(np.asarray(head_node[C["OPACITY_TEX_OFFSET"]:C["OPACITY_TEX_OFFSET"] + 1], np.float32).view(np.int32)[0])
+
+
 def lambert(color, tex_id=0, **kw):
     m = _node(C["PLAIN_MAT_CLASS_LAMBERT"], C["PLAIN_MATERIAL_HAS_DIFFUSE"])
     _color_slot(m, color, tex_id, C["LAMBERT_TEXID_OFFSET"], C["LAMBERT_TEXMATRIXID_OFFSET"], C["LAMBERT_SAMPLER0"], **kw)

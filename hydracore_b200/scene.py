@@ -387,15 +387,37 @@ class Scene:
             off += chunk.size
         textures = np.concatenate(tex_chunks)
 
-        # BVH
-        bb = BvhBuilder()
-        for m in self.meshes:
-            bb.add_mesh(m.vert4f(), m.idx)
-        for (mid, mat, _l) in self.instances:
-            bb.add_instance(mid, mat)
-        self.bvh = bb.commit()
-        lo, hi = bb.bounds()
-        bb.close()
+        # BVH: tree 0 = opaque meshes, tree 1 = meshes with at least one opacity-mapped material (MeshHaveOpacity, RenderDriverRTE.cpp:1989-1991);
+        # instance ids run over both trees in scene order, the inverse matrices are indexed by them
+        from . import materials as M
+        mat_opacity = [M.opacity_tex_id(self.materials[h]) for h in self.material_ids]
+        mesh_alpha = [bool(any(mat_opacity[int(k)] > 0 for k in np.unique(m.mat))) for m in self.meshes]   # > 0: zero-filled placeholder materials of the ray-casting scenes have no map
+        trees, lo, hi = [], None, None
+        inv_all = np.zeros((len(self.instances), 16), np.float32)
+        for tree_id in (0, 1):
+            ids = [i for i, (mid, _m, _l) in enumerate(self.instances) if mesh_alpha[mid] == bool(tree_id)]
+            if not ids:
+                trees.append(None)
+                continue
+            bb = BvhBuilder()
+            for m in self.meshes:                  # every mesh, so that builder mesh ids = scene mesh ids = geomId of the triangles; unused ones are not built
+                bb.add_mesh(m.vert4f(), m.idx)
+            for i in ids:
+                mid, mat, _l = self.instances[i]
+                bb.add_instance(mid, mat, real_id=i)
+            t = bb.commit()
+            inv_all[ids] = t["inv_matrices"]
+            blo, bhi = bb.bounds()
+            lo, hi = (blo, bhi) if lo is None else (np.minimum(lo, blo), np.maximum(hi, bhi))
+            bb.close()
+            trees.append(t)
+        if trees[0] is None:
+            raise ValueError("the scene needs at least one instance of a mesh without opacity maps (tree 0)")
+        self.bvh = trees[0]
+        self.bvh["inv_matrices"] = inv_all
+        self.bvh1 = trees[1]
+        if self.bvh1 is not None:
+            self.bvh1["alpha"] = self._alpha_table(self.bvh1["tris"], mat_opacity)
         half = np.float32(0.5)*(hi - lo)                     # scene bounding sphere, RenderDriverRTE.cpp:1461-1467
         self.bsphere = np.concatenate([np.float32(0.5)*(hi + lo), [np.sqrt((half*half).sum(dtype=np.float32), dtype=np.float32)]]).astype(np.float32)
         self.inst_light_ids = np.array([l for (_m, _x, l) in self.instances], np.int32)
@@ -413,6 +435,55 @@ class Scene:
                              pdfs=pdfs)
         self.globals_blob = self._pack_globals(geom_table, mat_table, tex_table)
         return self
+
+    def _alpha_table(self, tris, mat_opacity):
+        """RenderDriverRTE::CreateAlphaTestTable (RenderDriverRTE_AlphaTestTable.cpp:66-221): one uint2 per float4 of the triangle list -
+        {offset of the opacity sampler | smooth flag | skip-shadow flag, texture coordinate packed to 2 x 16 bits} for the three float4 of a
+        triangle, (-1, -1) for leaf headers - followed by the SWTexSampler copies (6 uint2 each), one per material with an opacity map."""
+        n = tris.shape[0]
+        ti = tris.view(np.int32)
+        with_alpha = [k for k, t in enumerate(mat_opacity) if t > 0]
+        out = np.zeros((n + 6*len(with_alpha), 2), np.uint32)
+        samplers, k = {}, 0
+
+        def wrap(v):                                   # WrapVal, cglobals.h:3014-3022
+            v = np.float32(v)
+            if v > 1.0:
+                return np.float32(v - np.float32(int(v)))
+            if v < -1.0:
+                return np.float32(np.float32(int(v)) - v)
+            return v
+
+        def pack_tc(u, v):                             # CompressTexCoord16, RenderDriverRTE_AlphaTestTable.cpp:25-38
+            tx = min(max(np.float32(np.float32(0.5)*wrap(u) + np.float32(0.5)), np.float32(0)), np.float32(1))
+            ty = min(max(np.float32(np.float32(0.5)*wrap(v) + np.float32(0.5)), np.float32(0)), np.float32(1))
+            return (int(np.float32(ty*np.float32(65535.0))) << 16) | int(np.float32(tx*np.float32(65535.0)))
+
+        while k < n:
+            if ti[k, 2] == -1 and ti[k, 3] == -1:      # object-list header
+                out[k] = (0xFFFFFFFF, 0xFFFFFFFF)
+                k += 1
+                continue
+            prim, geom = int(ti[k, 3]), int(ti[k + 1, 3])
+            mesh = self.meshes[geom]
+            mid = int(mesh.mat[prim])
+            tex = mat_opacity[mid]
+            if tex > 0:
+                if mid not in samplers:
+                    samplers[mid] = len(samplers)
+                    head = self.materials[self.material_ids[mid]]
+                    s0 = C["OPACITY_SAMPLER_OFFSET"]
+                    out[n + 6*samplers[mid]:n + 6*samplers[mid] + 6] = np.ascontiguousarray(head[s0:s0 + 12], np.float32).view(np.uint32).reshape(6, 2)
+                out[k, 0] = n + 6*samplers[mid]
+                out[k + 1, 0] = 0                      # smoothOpacity
+                out[k + 2, 0] = 0                      # skipShadow
+                for j in range(3):
+                    vi = int(mesh.idx[prim, j])
+                    out[k + j, 1] = pack_tc(mesh.uv[vi, 0], mesh.uv[vi, 1])
+            else:
+                out[k:k + 3] = (np.uint32(INVALID_TEXTURE & 0xFFFFFFFF), 0xFFFFFFFF)
+            k += 3
+        return out
 
     def _pack_globals(self, geom_table, mat_table, tex_table):
         """EngineGlobals + tables blob (cfetch.h:21-81; CalcConstGlobDataOffsets / PrepareEngineGlobals / PrepareEngineTables /

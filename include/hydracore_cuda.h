@@ -71,6 +71,13 @@ int hc_storage_capacity(hc_ctx* ctx, int slot, uint64_t* outBytes);
 int hc_set_globals(hc_ctx* ctx, const void* blob, uint64_t bytes);           /* PrepareEngineGlobals/Tables upload, GPUOCLData.cpp:289-327 */
 int hc_set_bvh(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const void* trif4, int trif4Num, int haveInst);
                                                                               /* SetAllBVH4(ConvertionResult), GPUOCLData.cpp:88-160       */
+int hc_set_bvh_alpha(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const void* trif4, int trif4Num,
+                     const void* alphaTableUint2, int alphaNum, int haveInst);
+                                                                              /* tree 1 of the ConvertionResult: meshes with opacity maps + pTriangleAlpha / triAfNum
+                                                                                 (RenderDriverRTE_AlphaTestTable.cpp:66-221; consumer BVH4InstTraverseAlpha, ctrace.h:1297).
+                                                                                 Send tree 0 first (hc_set_bvh forgets an earlier tree 1).  Closest-hit launches then walk
+                                                                                 tree 0 and tree 1 with the hit carried along; shadow rays see tree 0 only, exactly like
+                                                                                 IntegratorCommon::rayTrace / shadowTrace (CPUExp_Integrators_Common.cpp:122-171)          */
 int hc_bvh_device_layout(const void* nodes, int nodesNum, const void* trif4, int trif4Num, float* outNodesOrNull, float* outPairsOrNull,
                          int64_t outPairsCapacityFloats, int64_t* outPairsFloats, int* outStackBound);
                                                                               /* host only, no device needed: the re-layout hc_set_bvh applies before the upload (SoA quads, triangle
@@ -122,6 +129,11 @@ void hc_bvh_destroy(hc_bvh* b);
 int  hc_bvh_add_mesh(hc_bvh* b, const float* vert4f, int numVert, const int32_t* indices, int numIndices, int* outMeshId);
 int  hc_bvh_add_instance(hc_bvh* b, int meshId, const float* matrixRowMajor16, int* outInstId);
                                                                               /* InstanceTriangleMeshes, bvh_access_dll2.cpp:143 */
+int  hc_bvh_add_instance_id(hc_bvh* b, int meshId, const float* matrixRowMajor16, int realInstId);
+                                                                              /* the same with the scene-wide instance id given by the caller
+                                                                               * (a_realInstIdBase of InstanceTriangleMeshes): one builder per tree,
+                                                                               * opaque meshes in tree 0, meshes with opacity maps in tree 1
+                                                                               * (RenderDriverRTE.cpp:1989-1991)                               */
 int  hc_bvh_commit(hc_bvh* b);                                               /* CommitScene + ConvertMap                        */
 int  hc_bvh_result(hc_bvh* b, const void** nodes, int* nodesNum, const void** trif4, int* trif4Num,
                    const float** invMatrices16, int* numInst, int* maxStackDepth);

@@ -43,6 +43,9 @@ namespace
     const BVHNode*        nodes     = nullptr;
     const float4*         tris      = nullptr;
     int                   haveInst  = 1;
+    const BVHNode*        nodes1    = nullptr;   // tree 1: meshes with opacity maps (RenderDriverRTE.cpp:1989-1991)
+    const float4*         tris1     = nullptr;
+    const uint2*          alpha1    = nullptr;   // RenderDriverRTE::CreateAlphaTestTable
     std::vector<float4x4> matrices;
     std::vector<int32_t>  lightInstId;
     int w = 0, h = 0;
@@ -61,6 +64,11 @@ namespace
       p.instLightInstId = lightInstId.data();
       p.pExternalImpl   = nullptr;
       p.bvhTreesNumber  = 1;
+      if (nodes1 != nullptr)
+      {
+        p.nodesPtr[1] = nodes1; p.primsPtr[1] = tris1; p.alphaTbl[1] = alpha1; p.haveInst[1] = true;
+        p.bvhTreesNumber = 2;
+      }
       p.matrixNum       = int(matrices.size());
       return p;
     }
@@ -300,6 +308,12 @@ void* ref_scene_create(const int* globalsBlob, long long nInts,
   s->lightInstId.assign(lightInstId, lightInstId + nInst);
   s->w = w; s->h = h;
   return s;
+}
+// second tree of the ConvertionResult with its alpha table (nullptr = plain second tree); call before ref_render_create
+void ref_scene_set_tree1(void* p, const void* nodes, const void* tris, const void* alphaUint2)
+{
+  RefScene* s = (RefScene*)p;
+  s->nodes1 = (const BVHNode*)nodes; s->tris1 = (const float4*)tris; s->alpha1 = (const uint2*)alphaUint2;
 }
 void ref_scene_destroy(void* p) { delete (RefScene*)p; }
 

@@ -42,7 +42,7 @@ class CppLayer:
         L.hl_contribute.argtypes = [ct.c_void_p, ct.c_void_p]
         L.hl_available_memory.restype = ct.c_uint64
         L.hl_available_memory.argtypes = [ct.c_void_p, ct.c_int]
-        for name in ("hl_destroy", "hl_create_storage", "hl_storage_update", "hl_storage_info", "hl_resize_tables", "hl_set_bvh", "hl_set_instances",
+        for name in ("hl_destroy", "hl_create_storage", "hl_storage_update", "hl_storage_info", "hl_resize_tables", "hl_set_bvh", "hl_set_bvh2", "hl_set_instances",
                      "hl_set_lights", "hl_set_camera", "hl_get_vars", "hl_set_vars", "hl_prepare", "hl_globals_blob", "hl_call", "hl_init_path_tracing",
                      "hl_passes", "hl_clear_accumulated", "hl_get_hdr", "hl_get_ldr", "hl_device_name", "hl_device_count", "hl_rays_stat",
                      "hl_store_cpu_data"):
@@ -87,6 +87,15 @@ class CppLayer:
         t = np.ascontiguousarray(tris, np.float32).reshape(-1, 4)
         self._keep_type = ct.c_char_p(bvh_type)
         self._ck(self._L.hl_set_bvh(self._s, P(n), n.shape[0], P(t), t.shape[0], self._keep_type), "SetAllBVH4")
+
+    def SetAllBVH4TwoTrees(self, nodes, tris, nodes1, tris1, alpha1, bvh_type=b"object"):
+        """ConvertionResult with treesNum = 2: tree 1 holds the meshes with opacity maps and carries pTriangleAlpha."""
+        a = [np.ascontiguousarray(nodes, np.float32).reshape(-1, 8), np.ascontiguousarray(tris, np.float32).reshape(-1, 4),
+             np.ascontiguousarray(nodes1, np.float32).reshape(-1, 8), np.ascontiguousarray(tris1, np.float32).reshape(-1, 4),
+             np.ascontiguousarray(alpha1, np.uint32).reshape(-1, 2)]
+        self._keep_type = ct.c_char_p(bvh_type)
+        self._ck(self._L.hl_set_bvh2(self._s, P(a[0]), a[0].shape[0], P(a[1]), a[1].shape[0], P(a[2]), a[2].shape[0], P(a[3]), a[3].shape[0],
+                                     P(a[4]), a[4].shape[0], self._keep_type), "SetAllBVH4")
 
     def SetAllInstances(self, inv_matrices, light_ids):
         m = np.ascontiguousarray(inv_matrices, np.float32).reshape(-1, 16)
@@ -195,7 +204,10 @@ def load_scene_like_render_driver(lay, scn, consts):
         lay.StorageUpdate("textures", k + 1, chunk)
     for k, t in enumerate(getattr(scn, "pdf_tables", [])):
         lay.StorageUpdate("pdfs", k, t)
-    lay.SetAllBVH4(scn.bvh["nodes"], scn.bvh["tris"])
+    if getattr(scn, "bvh1", None) is not None:
+        lay.SetAllBVH4TwoTrees(scn.bvh["nodes"], scn.bvh["tris"], scn.bvh1["nodes"], scn.bvh1["tris"], scn.bvh1["alpha"])
+    else:
+        lay.SetAllBVH4(scn.bvh["nodes"], scn.bvh["tris"])
     lay.SetAllInstances(scn.bvh["inv_matrices"], scn.inst_light_ids)
     cam = scn.camera
     W, H = scn.width, scn.height

@@ -95,6 +95,8 @@ class Ref:
         L.ref_scene_create.restype = ct.c_void_p
         L.ref_scene_create.argtypes = [ct.c_void_p, ct.c_longlong] + [ct.c_void_p]*7 + [ct.c_int, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_int, ct.c_int]
         L.ref_scene_destroy.argtypes = [ct.c_void_p]
+        if hasattr(L, "ref_scene_set_tree1"):
+            L.ref_scene_set_tree1.argtypes = [ct.c_void_p]*4
         L.ref_render_create.restype = ct.c_void_p
         L.ref_render_create.argtypes = [ct.c_void_p, ct.c_int, ct.c_int]
         L.ref_render_destroy.argtypes = [ct.c_void_p]
@@ -182,6 +184,11 @@ class RefScene:
         g, geom, mats, tex, texa, pdfs, nodes, tris, inv, lids = self._keep
         self.h = ref.L.ref_scene_create(P(g), g.size, P(geom), P(mats), P(tex), P(texa), P(pdfs), P(nodes), P(tris), 1,
                                          P(inv), inv.shape[0], P(lids), scn.width, scn.height)
+        if getattr(scn, "bvh1", None) is not None:          # meshes with opacity maps: second tree + alpha table, walked by BVH4InstTraverseAlpha
+            t1 = [np.ascontiguousarray(scn.bvh1["nodes"], np.float32), np.ascontiguousarray(scn.bvh1["tris"], np.float32),
+                  np.ascontiguousarray(scn.bvh1["alpha"], np.uint32)]
+            self._keep += t1
+            ref.L.ref_scene_set_tree1(self.h, P(t1[0]), P(t1[1]), P(t1[2]))
         self._renders = []
 
     def close(self):

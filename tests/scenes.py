@@ -169,6 +169,42 @@ def cornell_spot_and_direct_lights(width=96, height=96, soft_sun=True):
     return scn.build()
 
 
+def cornell_with_cutout(width=96, height=96):
+    """The Cornell room with two instances of a quad whose material has an opacity (cut-out) map - a checker of opaque and transparent
+    cells, bilinear and point sampled - in front of the back wall and above the floor: the quads go into the alpha-tested tree 1, rays
+    pass through the transparent cells (BVH4InstTraverseAlpha), and - as in the reference's CPU integrators - they cast no shadows."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    rng = np.random.default_rng(5)
+    cells = (rng.random((8, 8)) > 0.45).astype(np.uint8)*255
+    img = np.zeros((64, 64, 4), np.uint8)
+    img[..., :3] = np.kron(cells, np.ones((8, 8), np.uint8))[..., None]
+    img[..., 3] = 255
+    tex = scn.add_texture_rgba8(img)
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    leaf = scn.add_material(M.with_opacity(M.lambert((0.2, 0.6, 0.25)), tex, gamma=1.0))
+    leaf2 = scn.add_material(M.with_opacity(M.blend((0.6, 0.6, 0.6), M.ggx((0.8, 0.8, 0.8), 0.8), M.lambert((0.7, 0.3, 0.1))), tex, gamma=1.0, flags=C_TEX_POINT_SAM()))
+    emi = scn.add_material(M.emissive((17.0, 12.0, 4.0), 0))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, white, white, white), inward=True, skip_faces=(4,))))
+    q = S.quad_mesh(2.5, 2.5)
+    q1 = scn.add_mesh(S.Mesh(q.pos, q.idx, norm=q.norm, uv=q.uv, mat=np.full(q.tri_count, leaf, np.int32)))
+    q2 = scn.add_mesh(S.Mesh(q.pos, q.idx, norm=q.norm, uv=q.uv*np.float32(1.7) - np.float32(0.3), mat=np.full(q.tri_count, leaf2, np.int32)))
+    scn.add_instance(q1, S.translate(-1.0, 0.2, -1.5) @ S.rotate_x(np.pi/2))
+    l0 = scn.add_light(M.area_light((0.0, 3.95, 0.0), (1.0, 1.0), (17.0, 12.0, 4.0)))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l0)
+    scn.add_instance(q2, S.translate(1.2, -2.0, 1.0) @ S.rotate_x(0.3))
+    scn.add_instance(q1, S.translate(1.5, 1.0, 0.5) @ S.rotate_x(np.pi/2) @ S.scale(0.5, 0.5, 0.5))
+    return scn.build()
+
+
+def C_TEX_POINT_SAM():
+    from hydracore_b200.layout import C
+    return C["TEX_POINT_SAM"]
+
+
 def open_box_under_sky(width=96, height=96, with_area_light=True, env_map=False):
     """Objects on a floor under a uniform sky-dome light (plus, optionally, a rect area light): rays that leave the scene pick up the
     environment colour with MIS, the sky is sampled through its pdf table."""
