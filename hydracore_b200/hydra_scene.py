@@ -80,6 +80,9 @@ def parse_library(xml_path, mesh_fallback_dirs=()):
         if emi is not None:
             col = emi.find("color")
             d["emission"] = _floats(_val(col, "0 0 0"))
+        opa = m.find("opacity")
+        if opa is not None and opa.find("texture") is not None:                      # cut-out map: the mesh goes into the alpha-tested BVH tree
+            d["opacity_tex"] = int(opa.find("texture").get("id"))
         out["materials"][int(m.get("id"))] = d
     for l in root.find("lights_lib"):
         size, inten = l.find("size"), l.find("intensity")
@@ -183,6 +186,8 @@ def build_scene(lib, width, height):
                 nodes = M.blend(tuple(r["color"]), top, lam, fresnel=r["fresnel"], ior=r["ior"])
             else:
                 nodes = lam
+        if d.get("opacity_tex", 0) > 0 and tex_map.get(d["opacity_tex"], 0) > 0:
+            nodes = M.with_opacity(nodes, tex_map[d["opacity_tex"]])
         mat_map[mid] = scn.add_material(nodes)
     mesh_map = {}
     for inst in lib["instances"]:
@@ -218,7 +223,7 @@ def _fixture_arrays(lib):
         dif, ref = d.get("diffuse"), d.get("reflect")
         mats.append([mid, d.get("light_id", -1)] + (dif["color"] + [dif["tex"]] if dif else [0, 0, 0, -1]) +
                     (ref["color"] + [ref["gloss"], float(_BRDF_CODE[ref["brdf"]]), 1.0 if ref["fresnel"] else 0.0, ref["ior"]] if ref else [0, 0, 0, -1, 0, 0, 0]) +
-                    (d["emission"] if "emission" in d else [-1, -1, -1]))
+                    (d["emission"] if "emission" in d else [-1, -1, -1]) + [d.get("opacity_tex", -1)])
     a["materials"] = np.array(mats, np.float64)
     shapes = {"rect": 0, "sphere": 1, "point": 2, "sky": 3, "spot": 4, "directional": 5}
     a["lights"] = np.array([[lid] + list(l["half"]) + l["color"] + [l["mat_id"], shapes[l["type"] if l["type"] in ("sky", "spot", "directional") else l["shape"]], l["radius"]] + list(l.get("params", [0.0, 0.0, 0.0])) for lid, l in sorted(lib["lights"].items())], np.float64)
@@ -277,6 +282,8 @@ def load_fixture(path, scene):
             d["reflect"] = dict(color=list(r[6:9]), gloss=float(r[9]), brdf=_BRDF_NAME[int(round(r[10]))], fresnel=r[11] > 0.5, ior=float(r[12]))
         if r[13] >= 0:
             d["emission"] = list(r[13:16])
+        if len(r) > 16 and r[16] > 0:
+            d["opacity_tex"] = int(r[16])
         lib["materials"][int(r[0])] = d
     shapes = {0: ("area", "rect"), 1: ("area", "sphere"), 2: ("point", "point"), 3: ("sky", "point"), 4: ("spot", "point"), 5: ("directional", "point")}
     for r in z["lights"]:
