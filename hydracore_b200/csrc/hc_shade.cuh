@@ -4,7 +4,7 @@
 // These restate, in our own code, the reference's device math (hydra_drv/{ctrace,cfetch,cmaterial,clight,cbidir,cglobals}.h;
 // file:line cited per function).  Formulas, operation order and — where it changes rounding — the C++ promotion of the
 // reference's unqualified math calls to double (see hc_math.cuh) are kept, so that the same random numbers give the same
-// path on the GPU and in the CPU oracle.  Supported: Lambert, Oren-Nayar, Phong, Blinn (Torrance-Sparrow), GGX (Heitz VNDF sampling +
+// path on the GPU and in the CPU oracle.  Supported: Lambert, Oren-Nayar, translucent Lambert, Phong, Blinn (Torrance-Sparrow), GGX (Heitz VNDF sampling +
 // multiscattering table), perfect mirror, GGX glass, blend masks (simple / fresnel / sigmoid), emissive materials; rectangular / disk / sphere
 // area lights, omni / spot point lights, directional lights, sky domes (constant or textured); RGBA8 and float4 textures.
 // Everything else is rejected with an error at hc_pt_init (no silent fallback).
@@ -390,6 +390,32 @@ HC_DEV void OrennayarSample(const float* m, float r1, float r2, float3 rayDir, f
   out.flags = HC_RAY_EVENT_D;
 }
 
+// ---- translucent Lambert (cmaterial.h:1850-1910): diffuse transmission through a thin sheet.  Colour / texture slots coincide with Lambert's.
+HC_DEV float TranslucentEvalPDF(float3 l, float3 v, float3 n)
+{
+  const float sign1 = dot(l, n) > 0 ? 1.0f : -1.0f, sign2 = dot(v, n) > 0 ? 1.0f : -1.0f;
+  const float coeff = (sign1*sign2 < 0.0f) ? 1.0f : 0.0f;
+  return fabsf(dot(l, n))*HC_INV_PI*coeff;
+}
+HC_DEV float3 TranslucentEvalBxDF(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+{
+  const float sign1 = dot(l, n) > 0 ? 1.0f : -1.0f, sign2 = dot(v, n) > 0 ? 1.0f : -1.0f;
+  const float coeff = (sign1*sign2 < 0.0f) ? 1.0f : 0.0f;
+  return LambertColor(m, tc, s)*coeff*HC_INV_PI;
+}
+HC_DEV void TranslucentSample(const float* m, float r1, float r2, float3 n, float2 tc, const HcScene& s, HcMatSample& out)
+{
+  const float3 kd = LambertColor(m, tc, s);
+  const float3 nn = (-1.0f)*n;
+  const float3 newDir = MapSampleToCosineDistribution(r1, r2, nn, nn, 1.0f);
+  const float cosTheta = dot(newDir, nn);
+  out.direction = newDir;
+  out.pdf = cosTheta*HC_INV_PI;
+  out.color = kd*HC_INV_PI;
+  if (cosTheta <= 1e-6f) out.color = f3(0, 0, 0);
+  out.flags = (HC_RAY_EVENT_D | HC_RAY_EVENT_T);
+}
+
 // ---- perfect mirror (cmaterial.h:385-421)
 HC_DEV void MirrorSample(const float* m, float3 rayDir, float3 n, float2 tc, const HcScene& s, HcMatSample& out)
 {
@@ -745,6 +771,7 @@ HC_DEV void LeafSample(const float* m, const HcSurfaceHit& sh, float3 rayDir, fl
     case HC_PLAIN_MAT_CLASS_PERFECT_MIRROR: MirrorSample(m, rayDir, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_GLASS:          GlassGgxSample(m, rands, rayDir, sh.normal, sh.texCoord, sh.hfi, s, out); break;
     case HC_PLAIN_MAT_CLASS_LAMBERT:        LambertSample(m, rands.x, rands.y, sh.normal, sh.texCoord, s, out); break;
+    case HC_PLAIN_MAT_CLASS_TRANSLUCENT:    TranslucentSample(m, rands.x, rands.y, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_OREN_NAYAR:     OrennayarSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
     default: break;
   }
@@ -805,6 +832,8 @@ HC_DEV HcBxDF LeafEval(const float* m, float3 l, float3 v, float3 n, float2 tc, 
       r.brdf = LambertColor(m, tc, s)*HC_INV_PI*1.0f; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
     case HC_PLAIN_MAT_CLASS_OREN_NAYAR:
       r.brdf = OrennayarEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
+    case HC_PLAIN_MAT_CLASS_TRANSLUCENT:
+      r.btdf = TranslucentEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = TranslucentEvalPDF(l, v, n); r.pdfRev = TranslucentEvalPDF(v, l, n); r.diffuse = true; break;
     default: break;      // mirror and glass evaluate to zero for explicit light (cmaterial.h:396-404, 620-629)
   }
   return r;

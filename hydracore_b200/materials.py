@@ -70,6 +70,14 @@ def lambert(color, tex_id=0, **kw):
     return m
 
 
+def translucent(color, tex_id=0, **kw):
+    """Translucent Lambert (TranslucentMaterial, PlainMaterialConverter.cpp; cmaterial.h:1850-1910): cosine-distributed transmission through
+    the surface, Lambert's colour / texture slots; flag PLAIN_MATERIAL_HAS_DIFFUSE like the converter sets."""
+    m = _node(C["PLAIN_MAT_CLASS_TRANSLUCENT"], C["PLAIN_MATERIAL_HAS_DIFFUSE"])
+    _color_slot(m, color, tex_id, C["LAMBERT_TEXID_OFFSET"], C["LAMBERT_TEXMATRIXID_OFFSET"], C["LAMBERT_SAMPLER0"], **kw)
+    return m
+
+
 def orennayar(color, roughness, tex_id=0, **kw):
     """Oren-Nayar diffuse (OrenNayarMaterial, PlainMaterialConverter.cpp:142-170): sigma = roughness*pi/2, A and B precomputed in float."""
     m = _node(C["PLAIN_MAT_CLASS_OREN_NAYAR"], C["PLAIN_MATERIAL_HAS_DIFFUSE"])
