@@ -104,6 +104,7 @@ HC_DEV void FinishPath(float4* __restrict__ fb, uint2* __restrict__ pixelRng, in
   pixelRng[rngSlot] = make_uint2(g.x, g.y);
 }
 
+template<bool NMAP>
 __global__ void __launch_bounds__(HC_SHADE_BLOCK, HC_SHADE_MINB)
 k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, int* __restrict__ nOut,
            const HcPathState in, HcPathState out, const HcHit* __restrict__ hits, const unsigned char* __restrict__ vis,
@@ -192,7 +193,7 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
             const float3 sdir = normalize(sam.pos - sh.pos);
             const float3 spos = OffsShadowRayPos(sh.pos, sh.normal, sdir, sh.sRayOff);
             const float tFar = length(spos - sam.pos)*0.995f;
-            const HcBxDF ev = MaterialEval(mat, sdir, (-1.0f)*rayDir, sh.normal, sh.texCoord, s);
+            const HcBxDF ev = MaterialEval<NMAP>(mat, sdir, (-1.0f)*rayDir, sh, s);
             const float c1 = fmaxf(+dot(sdir, sh.normal), 0.0f), c2 = fmaxf(-dot(sdir, sh.normal), 0.0f);
             const float3 bx = (ev.brdf*c1 + ev.btdf*c2);
             const float lgtPdf = sam.pdf*pick;
@@ -223,7 +224,7 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
           for (int k = 0; k < HC_MMLT_FLOATS_PER_MLAYER; k++) rands[3 + k] = rndFloat1_Pseudo(g);
         }
         HcMatSample ms;
-        MaterialSampleAndEval(mat, rands, sh, rayDir, sampFlags, s, ms);
+        MaterialSampleAndEval<NMAP>(mat, rands, sh, rayDir, sampFlags, s, ms);
         const float3 bxdfVal = ms.color*(1.0f/fmaxf(ms.pdf, isPT ? HC_DEPSILON2 : 1e-20f));
         const float cosTheta = fabsf(dot(ms.direction, sh.normal));
 
@@ -373,6 +374,7 @@ struct HcPathHost
   std::vector<unsigned char> materialsHost, globalsHost;
   int64_t capacity = 0;
   int nOwned = 0;
+  bool haveNormalMaps = false;                // set by ValidateScene: selects the k_pt_shade instantiation
   std::vector<cudaEvent_t> evPool;            // per-launch stage timing of the LAST pass of a hc_pt_pass call: {start, stop} pairs
   std::vector<int> evClass;                    // 0 closest, 1 shadow, 2 shade, 3 other
 };
@@ -462,6 +464,7 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
   auto gi = [&](int off) { int v; memcpy(&v, g + off, 4); return v; };
   // EngineGlobals::suns (soft directional lights, IHWLayerDataAssembler.cpp:421-450) are read only by sky portals, which are rejected below
   HcPathHost* p = PH(ctx);
+  p->haveNormalMaps = false;
   const std::vector<unsigned char>& gl = p->globalsHost;
   const int lightsNum = gi(HC_EG_lightsNum), lightsOffset = gi(HC_EG_lightsOffset);
   for (int l = 0; l < lightsNum; l++)
@@ -512,7 +515,13 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
                     type == HC_PLAIN_MAT_CLASS_PERFECT_MIRROR || type == HC_PLAIN_MAT_CLASS_GLASS || type == HC_PLAIN_MAT_CLASS_BLEND_MASK ||
                     type == HC_PLAIN_MAT_CLASS_EMISSIVE || type == HC_PLAIN_MAT_CLASS_OREN_NAYAR || type == HC_PLAIN_MAT_CLASS_TRANSLUCENT;
     if (!ok) { why = "material class " + std::to_string(type) + " is not supported yet (Lambert, Oren-Nayar, translucent, Phong, Blinn, GGX, mirror, glass, blend mask are)"; return HC_E_ARG; }
-    if (ntex != HC_INVALID_TEXTURE) { why = "normal maps are not supported yet (set NORMAL_TEX_OFFSET to INVALID_TEXTURE)"; return HC_E_ARG; }
+    if (ntex != HC_INVALID_TEXTURE)            // normal map: image in the "textures_aux" storage, found through the aux texture table
+    {
+      p->haveNormalMaps = true;
+      if (!ctx->storage[HC_STORAGE_TEXTURES_AUX].ptr || ntex < 0 || ntex >= gi(HC_EG_texturesAuxTableSize)) { why = "normal map without an image in the textures_aux storage"; return HC_E_ARG; }
+      int auxOff; memcpy(&auxOff, gl.data() + 4*size_t(gi(HC_EG_texturesAuxTableOffset) + ntex), 4);
+      if (auxOff < 0) { why = "normal map texture id has no entry in the aux texture table"; return HC_E_ARG; }
+    }
     if (ptex != HC_INVALID_TEXTURE) { why = "procedural textures are not supported yet"; return HC_E_ARG; }
     if (type == HC_PLAIN_MAT_CLASS_GLASS && (flags & HC_PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER)) { why = "glass multiscattering table is not supported yet"; return HC_E_ARG; }
     if (type == HC_PLAIN_MAT_CLASS_BLEND_MASK)
@@ -537,6 +546,8 @@ static HcScene MakeScene(hc_ctx* ctx)
   s.geom = (const float4*)ctx->storage[HC_STORAGE_GEOM].ptr;
   s.materials = (const float4*)ctx->storage[HC_STORAGE_MATERIALS].ptr;
   s.textures = (const int4*)ctx->storage[HC_STORAGE_TEXTURES].ptr;
+  s.texturesAux = (const int4*)ctx->storage[HC_STORAGE_TEXTURES_AUX].ptr;
+  s.texturesAuxTableOffset = gi(HC_EG_texturesAuxTableOffset);
   s.pdfs = (const float4*)ctx->storage[HC_STORAGE_PDFS].ptr;
   s.pdfTableTableOffset = gi(HC_EG_pdfTableTableOffset);
   s.instMatrices = (const float4*)ctx->instMatrices.ptr;
@@ -730,8 +741,16 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
         ctx->stats.kernelLaunches += 3;
         perm = (const int*)p->sortPerm.ptr;
       }
-      HC_STAGE(2, (k_pt_shade<<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, ctx->stream>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
-                   (const HcHit*)p->hits.ptr, (const unsigned char*)p->vis.ptr, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
+      if (p->haveNormalMaps)
+      {
+        HC_STAGE(2, (k_pt_shade<true><<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, ctx->stream>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
+                     (const HcHit*)p->hits.ptr, (const unsigned char*)p->vis.ptr, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
+      }
+      else
+      {
+        HC_STAGE(2, (k_pt_shade<false><<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, ctx->stream>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
+                     (const HcHit*)p->hits.ptr, (const unsigned char*)p->vis.ptr, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
+      }
       HC_CUDA(cudaGetLastError());
       ctx->stats.kernelLaunches++;
       cur = 1 - cur;

@@ -5,7 +5,7 @@
 // file:line cited per function).  Formulas, operation order and — where it changes rounding — the C++ promotion of the
 // reference's unqualified math calls to double (see hc_math.cuh) are kept, so that the same random numbers give the same
 // path on the GPU and in the CPU oracle.  Supported: Lambert, Oren-Nayar, translucent Lambert, Phong, Blinn (Torrance-Sparrow), GGX (Heitz VNDF sampling +
-// multiscattering table), perfect mirror, GGX glass, blend masks (simple / fresnel / sigmoid), emissive materials; rectangular / disk / sphere
+// multiscattering table), perfect mirror, GGX glass, blend masks (simple / fresnel / sigmoid), emissive materials, normal maps; rectangular / disk / sphere
 // area lights, omni / spot point lights, directional lights, sky domes (constant or textured); RGBA8 and float4 textures.
 // Everything else is rejected with an error at hc_pt_init (no silent fallback).
 #pragma once
@@ -31,10 +31,11 @@ struct HcScene
   const float4* __restrict__ geom;          // "geom" storage
   const float4* __restrict__ materials;     // "materials" storage
   const int4*   __restrict__ textures;      // "textures" storage
+  const int4*   __restrict__ texturesAux;   // "textures_aux" storage (normal maps)
   const float4* __restrict__ pdfs;          // "pdfs" storage (sky-dome pdf tables)
   const float4* __restrict__ instMatrices;  // inverse instance matrices, 4 float4 each
   const int*    __restrict__ instLightIds;  // instance -> light index or -1
-  int materialsTableOffset, geometryTableOffset, texturesTableOffset, pdfTableTableOffset;
+  int materialsTableOffset, geometryTableOffset, texturesTableOffset, texturesAuxTableOffset, pdfTableTableOffset;
   int lightSelTableOffsetRev, lightSelTableSizeRev, lightsOffset, lightsNum, skyLightId;
   int gflags, traceDepth, diffTraceDepth;
   int essGgxTableOffsetBytes;
@@ -759,10 +760,60 @@ HC_DEV float BlendMaskAlpha(const float* m, float3 v, float3 n, float2 tc, const
 }
 HC_DEV bool IsLeaf(const float* m) { return MatI(m, HC_PLAIN_MAT_TYPE_OFFSET) != HC_PLAIN_MAT_CLASS_BLEND_MASK; }
 
-// leaf dispatch: MaterialLeafSampleAndEvalBRDF (cmaterial.h:2245-2335) without normal maps
-HC_DEV void LeafSample(const float* m, const HcSurfaceHit& sh, float3 rayDir, float3 rands, const HcScene& s, HcMatSample& out)
+// ---- normal maps: sample2DAux (cfetch.h:766-789) from the "textures_aux" storage, materialNormalMapFetch / BumpMapping (cmaterial.h:2209-2243)
+HC_DEV float3 NormalMapFetch(const float* m, float2 tc, const HcScene& s)
+{
+  float3 fromTex = f3(1, 1, 1);
+  const int texId = MatI(m, HC_NORMAL_TEX_OFFSET), samplerOffset = MatI(m, HC_NORMAL_TEX_MATRIX);
+  if (samplerOffset != HC_INVALID_TEXTURE)
+  {
+    const int4 header = reinterpret_cast<const int4*>(m)[samplerOffset];
+    const float4 row0 = reinterpret_cast<const float4*>(m)[samplerOffset + 1], row1 = reinterpret_cast<const float4*>(m)[samplerOffset + 2];
+    const int flags = header.x; const float gamma = __int_as_float(header.y);
+    if (header.z != 0)
+    {
+      const float2 tct = f2(row0.x*tc.x + row0.y*tc.y + row0.w, row1.x*tc.x + row1.y*tc.y + row1.w);
+      float4 c = ReadImageSw4(s.texturesAux + s.globals[s.texturesAuxTableOffset + texId], tct, flags, (gamma != 1.0f));
+      if (flags & HC_TEX_ALPHASRC_W) { c.x = c.w; c.y = c.w; c.z = c.w; }
+      fromTex = f3(c.x, c.y, c.z);
+    }
+  }
+  float3 ts = f3(2.0f*fromTex.x - 1.0f, 2.0f*fromTex.y - 1.0f, fromTex.z);
+  const int mflags = MatI(m, HC_PLAIN_MAT_FLAGS_OFFSET);
+  if (mflags & HC_PLAIN_MATERIAL_INVERT_NMAP_Y) ts.y *= (-1.0f);
+  if (mflags & HC_PLAIN_MATERIAL_INVERT_NMAP_X) ts.x *= (-1.0f);
+  if (mflags & HC_PLAIN_MATERIAL_INVERT_SWAP_NMAP_XY) { const float t = ts.x; ts.x = ts.y; ts.y = t; }
+  return normalize(ts);
+}
+HC_DEV float3 BumpMapping(float3 tangent, float3 bitangent, float3 normal, float2 tc, const float* m, const HcScene& s)
+{
+  const float3 ts = NormalMapFetch(m, tc, s);
+  const float3 a0 = tangent, a1 = bitangent, a2 = normal;                                  // rows of the tangent transform; inverse(): cglobals.h:893-916
+  const float det = a0.x*(a1.y*a2.z - a1.z*a2.y) - a0.y*(a1.x*a2.z - a1.z*a2.x) + a0.z*(a1.x*a2.y - a1.y*a2.x);
+  float3 b0 = f3((a1.y*a2.z - a1.z*a2.y), -(a0.y*a2.z - a0.z*a2.y), (a0.y*a1.z - a0.z*a1.y));
+  float3 b1 = f3(-(a1.x*a2.z - a1.z*a2.x), (a0.x*a2.z - a0.z*a2.x), -(a0.x*a1.z - a0.z*a1.x));
+  float3 b2 = f3((a1.x*a2.y - a1.y*a2.x), -(a0.x*a2.y - a0.y*a2.x), (a0.x*a1.y - a0.y*a1.x));
+  const float sc = 1.0f/det;
+  b0 = b0*sc; b1 = b1*sc; b2 = b2*sc;
+  return normalize(f3(b0.x*ts.x + b0.y*ts.y + b0.z*ts.z, b1.x*ts.x + b1.y*ts.y + b1.z*ts.z, b2.x*ts.x + b2.y*ts.y + b2.z*ts.z));
+}
+HC_DEV bool HasNormalMap(const float* m) { return MatI(m, HC_NORMAL_TEX_OFFSET) != HC_INVALID_TEXTURE; }
+
+// leaf dispatch: MaterialLeafSampleAndEvalBRDF (cmaterial.h:2245-2335)
+// NMAP: the scene has at least one normal-mapped material (found by ValidateScene); scenes without any run the instantiation without
+// this code, which keeps the register-limited shade kernel as it was
+template<bool NMAP>
+HC_DEV void LeafSample(const float* m, const HcSurfaceHit& shIn, float3 rayDir, float3 rands, const HcScene& s, HcMatSample& out)
 {
   out.color = f3(0.0f, 0.0f, 0.0f); out.direction = f3(0.0f, 1.0f, 0.0f); out.pdf = 1.0f; out.flags = 0;
+  struct { float3 normal; float2 texCoord; bool hfi; } sh = { shIn.normal, shIn.texCoord, shIn.hfi };
+  const bool hasNormalMap = NMAP && HasNormalMap(m);
+  if (hasNormalMap)
+  {
+    const bool isGlass = (MatI(m, HC_PLAIN_MAT_TYPE_OFFSET) == HC_PLAIN_MAT_CLASS_GLASS);
+    const float3 flatNorm = (shIn.hfi && !isGlass) ? (-1.0f)*shIn.flatNormal : shIn.flatNormal;
+    sh.normal = BumpMapping(shIn.tangent, shIn.biTangent, flatNorm, shIn.texCoord, m, s);
+  }
   switch (MatI(m, HC_PLAIN_MAT_TYPE_OFFSET))
   {
     case HC_PLAIN_MAT_CLASS_PHONG_SPECULAR: PhongSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
@@ -775,10 +826,16 @@ HC_DEV void LeafSample(const float* m, const HcSurfaceHit& sh, float3 rayDir, fl
     case HC_PLAIN_MAT_CLASS_OREN_NAYAR:     OrennayarSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
     default: break;
   }
+  if (hasNormalMap)                          // the caller multiplies by the cosine to the UNBUMPED normal (cmaterial.h:2320-2330)
+  {
+    const float cosThetaOut1 = fabsf(dot(out.direction, shIn.normal)), cosThetaOut2 = fabsf(dot(out.direction, sh.normal));
+    out.color *= (cosThetaOut2/fmaxf(cosThetaOut1, HC_DEPSILON2));
+  }
   if (out.pdf <= 0.0f) out.color = f3(0, 0, 0);
 }
 
 // MaterialSampleAndEvalBxDF (cmaterial.h:2345-2371) with materialRandomWalkBRDF (:2180-2207); rands[0..2] direction, rands[3..9] layers
+template<bool NMAP>
 HC_DEV void MaterialSampleAndEval(const float* mat, const float* rands, const HcSurfaceHit& sh, float3 rayDir, unsigned rayFlags,
                                   const HcScene& s, HcMatSample& out)
 {
@@ -807,7 +864,7 @@ HC_DEV void MaterialSampleAndEval(const float* mat, const float* rands, const Hc
     i++;
   }
   const float* leaf = mat + localOffs*HC_PLAIN_MATERIAL_DATA_SIZE;
-  LeafSample(leaf, sh, rayDir, f3(rands[0], rands[1], rands[2]), s, out);
+  LeafSample<NMAP>(leaf, sh, rayDir, f3(rands[0], rands[1], rands[2]), s, out);
   out.color *= 1.0f/fmaxf(w, 0.015625f);
   if ((MatI(leaf, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_SKIP_SKY_PORTAL))       // materialIsSkyPortal && isEyeRay, cmaterial.h:2366-2370
   {
@@ -816,32 +873,48 @@ HC_DEV void MaterialSampleAndEval(const float* mat, const float* rands, const Hc
   }
 }
 
-// materialLeafEval (cmaterial.h:2425-2551) without normal maps, camera direction
-HC_DEV HcBxDF LeafEval(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+// materialLeafEval (cmaterial.h:2425-2551), camera direction (EVAL_FLAG_DEFAULT: no adjoint-BSDF fix, clamp 1e-6 in the normal-map cosine fix)
+template<bool NMAP>
+HC_DEV HcBxDF LeafEval(const float* m, float3 l, float3 v, const HcSurfaceHit& sh, const HcScene& s)
 {
   HcBxDF r; r.brdf = f3(0, 0, 0); r.btdf = f3(0, 0, 0); r.pdfFwd = 0.0f; r.pdfRev = 0.0f; r.diffuse = false;
+  float3 n = sh.normal; const float2 tc = sh.texCoord;
+  float cosMult = 1.0f, cosMult2 = 1.0f;
+  if (NMAP && HasNormalMap(m))
+  {
+    n = BumpMapping(sh.tangent, sh.biTangent, sh.flatNormal, tc, m, s);
+    const float clampVal = 1e-6f;
+    const float cosThetaOut1 = fmaxf(dot(l, sh.normal), 0.0f), cosThetaOut2 = fmaxf(dot(l, n), 0.0f);
+    cosMult = cosThetaOut2/fmaxf(cosThetaOut1, clampVal);
+    if (cosThetaOut1 <= 0.0f) cosMult = 0.0f;
+    const float cosThetaOut3 = fmaxf(-dot(l, sh.normal), 0.0f), cosThetaOut4 = fmaxf(-dot(l, n), 0.0f);
+    cosMult2 = cosThetaOut4/fmaxf(cosThetaOut3, clampVal);
+    if (cosThetaOut3 <= 0.0f) cosMult2 = 0.0f;
+  }
   switch (MatI(m, HC_PLAIN_MAT_TYPE_OFFSET))
   {
     case HC_PLAIN_MAT_CLASS_PHONG_SPECULAR:
-      r.brdf = PhongEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = PhongEvalPDF(m, l, v, n, tc, s); r.pdfRev = PhongEvalPDF(m, v, l, n, tc, s); break;
+      r.brdf = PhongEvalBxDF(m, l, v, n, tc, s)*cosMult; r.pdfFwd = PhongEvalPDF(m, l, v, n, tc, s); r.pdfRev = PhongEvalPDF(m, v, l, n, tc, s); break;
     case HC_PLAIN_MAT_CLASS_BLINN_SPECULAR:
-      r.brdf = BlinnEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = BlinnEvalPDF(m, l, v, n, tc, s); r.pdfRev = BlinnEvalPDF(m, v, l, n, tc, s); break;
+      r.brdf = BlinnEvalBxDF(m, l, v, n, tc, s)*cosMult; r.pdfFwd = BlinnEvalPDF(m, l, v, n, tc, s); r.pdfRev = BlinnEvalPDF(m, v, l, n, tc, s); break;
     case HC_PLAIN_MAT_CLASS_GGX:
-      r.brdf = GgxEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = Ggx2EvalPDF(m, l, v, n, tc, s); r.pdfRev = Ggx2EvalPDF(m, v, l, n, tc, s); break;
+      r.brdf = GgxEvalBxDF(m, l, v, n, tc, s)*cosMult; r.pdfFwd = Ggx2EvalPDF(m, l, v, n, tc, s); r.pdfRev = Ggx2EvalPDF(m, v, l, n, tc, s); break;
     case HC_PLAIN_MAT_CLASS_LAMBERT:
-      r.brdf = LambertColor(m, tc, s)*HC_INV_PI*1.0f; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
+      r.brdf = LambertColor(m, tc, s)*HC_INV_PI*cosMult; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
     case HC_PLAIN_MAT_CLASS_OREN_NAYAR:
-      r.brdf = OrennayarEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
+      r.brdf = OrennayarEvalBxDF(m, l, v, n, tc, s)*cosMult; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
     case HC_PLAIN_MAT_CLASS_TRANSLUCENT:
-      r.btdf = TranslucentEvalBxDF(m, l, v, n, tc, s)*1.0f; r.pdfFwd = TranslucentEvalPDF(l, v, n); r.pdfRev = TranslucentEvalPDF(v, l, n); r.diffuse = true; break;
+      r.btdf = TranslucentEvalBxDF(m, l, v, n, tc, s)*cosMult2; r.pdfFwd = TranslucentEvalPDF(l, v, n); r.pdfRev = TranslucentEvalPDF(v, l, n); r.diffuse = true; break;
     default: break;      // mirror and glass evaluate to zero for explicit light (cmaterial.h:396-404, 620-629)
   }
   return r;
 }
 
 // materialEval (cmaterial.h:2554-2628): explicit-stack walk of the blend tree, same push/pop order (so sums round identically)
-HC_DEV HcBxDF MaterialEval(const float* mat, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
+template<bool NMAP>
+HC_DEV HcBxDF MaterialEval(const float* mat, float3 l, float3 v, const HcSurfaceHit& sh, const HcScene& s)
 {
+  const float3 n = sh.normal; const float2 tc = sh.texCoord;
   HcBxDF val; val.brdf = f3(0, 0, 0); val.btdf = f3(0, 0, 0); val.pdfFwd = 0.0f; val.pdfRev = 0.0f; val.diffuse = true;
   float stackW[HC_MIX_TREE_MAX_DEEP]; int stackO[HC_MIX_TREE_MAX_DEEP];
   int top = 0, cur = 0; float curW = 1.0f;
@@ -860,7 +933,7 @@ HC_DEV HcBxDF MaterialEval(const float* mat, float3 l, float3 v, float3 n, float
     }
     else
     {
-      const HcBxDF b = LeafEval(m, l, v, n, tc, s);
+      const HcBxDF b = LeafEval<NMAP>(m, l, v, sh, s);
       val.brdf += curW*b.brdf; val.btdf += curW*b.btdf; val.pdfFwd += curW*b.pdfFwd; val.pdfRev += curW*b.pdfRev;
       val.diffuse = val.diffuse && b.diffuse;
     }

@@ -60,6 +60,22 @@ def with_opacity(nodes, tex_id, **kw):
     return nodes
 
 
+def with_normal_map(nodes, tex_id, invert_x=False, invert_y=False, swap_xy=False, **kw):
+    """Normal map on a material: IMaterial::SetNormalSampler + the "push down" to every node of a blend tree (PlainMaterialConverter.cpp:1395-1460):
+    NORMAL_TEX_OFFSET = texture id (looked up in the AUX texture table), NORMAL_TEX_MATRIX = float4 index of the sampler at
+    NORMAL_SAMPLER_OFFSET; flags PLAIN_MATERIAL_INVERT_NMAP_X / _Y / _SWAP_NMAP_XY.  The image comes from Scene.add_normal_map."""
+    nodes = [nodes] if isinstance(nodes, np.ndarray) and nodes.ndim == 1 else list(nodes)
+    kw.setdefault("gamma", 1.0)
+    for n in nodes:
+        n[C["NORMAL_TEX_OFFSET"]] = _i2f(tex_id)
+        n[C["NORMAL_TEX_MATRIX"]] = _i2f(_sampler(n, C["NORMAL_SAMPLER_OFFSET"], tex_id, **kw))
+        f = int(np.asarray(n[C["PLAIN_MAT_FLAGS_OFFSET"]:C["PLAIN_MAT_FLAGS_OFFSET"] + 1], np.float32).view(np.int32)[0])
+        f |= (C["PLAIN_MATERIAL_INVERT_NMAP_X"] if invert_x else 0) | (C["PLAIN_MATERIAL_INVERT_NMAP_Y"] if invert_y else 0) | \
+             (C["PLAIN_MATERIAL_INVERT_SWAP_NMAP_XY"] if swap_xy else 0)
+        n[C["PLAIN_MAT_FLAGS_OFFSET"]] = _i2f(f)
+    return nodes
+
+
 def opacity_tex_id(head_node):
     return int(np.asarray(head_node[C["OPACITY_TEX_OFFSET"]:C["OPACITY_TEX_OFFSET"] + 1], np.float32).view(np.int32)[0])
 

@@ -350,6 +350,13 @@ class Scene:
         self.textures.append(rgba)
         return len(self.textures)
 
+    def add_normal_map(self, rgba):
+        """Normal map (RGBA8): the driver keeps such images in the "textures_aux" storage under the same texture id
+        (RenderDriverRTE::UpdateImageAux; sample2DAux looks the id up in the aux texture table, cfetch.h:766-789)."""
+        tid = self.add_texture_rgba8(rgba)
+        self.aux_ids = getattr(self, "aux_ids", set()) | {tid}
+        return tid
+
     def add_texture_f4(self, rgba):
         """HDR texture: float4 texels (bpp 16, cfetch.h:364-584), e.g. an environment map."""
         rgba = np.ascontiguousarray(rgba, np.float32)
@@ -386,6 +393,15 @@ class Scene:
             tex_chunks.append(chunk)
             off += chunk.size
         textures = np.concatenate(tex_chunks)
+        aux_chunks, self._aux_table, off = [np.zeros(16, np.uint8)], [-1]*len(tex_table), 16
+        for tid in sorted(getattr(self, "aux_ids", ())):
+            t = self.textures[tid - 1]
+            body = t.reshape(-1).view(np.uint8)
+            chunk = np.concatenate([np.array([t.shape[1], t.shape[0], 4, 4], np.int32).view(np.uint8), body, np.zeros((-body.size) % 16, np.uint8)])
+            self._aux_table[tid] = off//16
+            aux_chunks.append(chunk)
+            off += chunk.size
+        textures_aux = np.concatenate(aux_chunks)
 
         # BVH: tree 0 = opaque meshes, tree 1 = meshes with at least one opacity-mapped material (MeshHaveOpacity, RenderDriverRTE.cpp:1989-1991);
         # instance ids run over both trees in scene order, the inverse matrices are indexed by them
@@ -431,7 +447,7 @@ class Scene:
             pdf_chunks.append(np.concatenate([b, np.zeros(pad, np.uint8)]))
             off += b.size + pad
         pdfs = np.concatenate(pdf_chunks) if pdf_chunks else np.zeros(16, np.uint8)
-        self.storages = dict(textures=textures, textures_aux=np.zeros(16, np.uint8), geom=geom, materials=mats.view(np.uint8).reshape(-1),
+        self.storages = dict(textures=textures, textures_aux=textures_aux, geom=geom, materials=mats.view(np.uint8).reshape(-1),
                              pdfs=pdfs)
         self.globals_blob = self._pack_globals(geom_table, mat_table, tex_table)
         return self
@@ -579,7 +595,7 @@ class Scene:
         blob[offs["materials"]:offs["materials"] + len(mat_table)] = mat_table
         blob[offs["geometry"]:offs["geometry"] + len(geom_table)] = geom_table
         blob[offs["textures"]:offs["textures"] + len(tex_table)] = tex_table
-        blob[offs["texturesAux"]:offs["texturesAux"] + len(tex_table)] = -1
+        blob[offs["texturesAux"]:offs["texturesAux"] + len(tex_table)] = getattr(self, "_aux_table", [-1]*len(tex_table))
         blob[offs["pdfTable"]:offs["pdfTable"] + sizes["pdfTable"]] = -1
         for i, o in enumerate(getattr(self, "_pdf_table_offsets", [])):
             blob[offs["pdfTable"] + i] = o

@@ -202,6 +202,9 @@ def load_scene_like_render_driver(lay, scn, consts):
         body = t.reshape(-1)
         chunk = np.concatenate([np.array([w, h, 4, 4], np.int32).view(np.uint8), body])
         lay.StorageUpdate("textures", k + 1, chunk)
+    for tid in sorted(getattr(scn, "aux_ids", ())):           # normal maps live in "textures_aux" under the same id (RenderDriverRTE::UpdateImageAux)
+        t = scn.textures[tid - 1]
+        lay.StorageUpdate("textures_aux", tid, np.concatenate([np.array([t.shape[1], t.shape[0], 4, 4], np.int32).view(np.uint8), t.reshape(-1)]))
     for k, t in enumerate(getattr(scn, "pdf_tables", [])):
         lay.StorageUpdate("pdfs", k, t)
     if getattr(scn, "bvh1", None) is not None:

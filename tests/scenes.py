@@ -190,6 +190,41 @@ def cornell_translucent(width=96, height=96):
     return scn.build()
 
 
+def cornell_normal_mapped(width=96, height=96):
+    """The Cornell room with normal-mapped surfaces: Lambert floor, a GGX sphere (map with inverted Y), a Phong-over-Lambert blend box
+    (X / Y swapped) and a glass sphere: BumpMapping in the BSDF sample and in the explicit-light evaluation, with the cosine corrections."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    yy, xx = np.meshgrid(np.arange(64), np.arange(64), indexing="ij")
+    hgt = 0.5*np.sin(xx*np.pi/8.0)*np.cos(yy*np.pi/5.0) + 0.25*np.sin((xx + 2*yy)*np.pi/11.0)
+    dx, dy = np.gradient(hgt, axis=1), np.gradient(hgt, axis=0)
+    nrm = np.stack([-dx, -dy, np.ones_like(hgt)], -1)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    img = np.zeros((64, 64, 4), np.uint8)
+    img[..., 0] = np.clip((nrm[..., 0]*0.5 + 0.5)*255.0, 0, 255).astype(np.uint8)
+    img[..., 1] = np.clip((nrm[..., 1]*0.5 + 0.5)*255.0, 0, 255).astype(np.uint8)
+    img[..., 2] = np.clip(nrm[..., 2]*255.0, 0, 255).astype(np.uint8)          # z is used as stored (materialNormalMapFetch, cmaterial.h:2216)
+    img[..., 3] = 255
+    nm = scn.add_normal_map(img)
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    floor = scn.add_material(M.with_normal_map(M.lambert((0.7, 0.7, 0.7)), nm, row0=(3, 0, 0, 0), row1=(0, 3, 0, 0)))
+    ggxm = scn.add_material(M.with_normal_map(M.ggx((0.8, 0.6, 0.2), 0.75), nm, invert_y=True))
+    bl = scn.add_material(M.with_normal_map(M.blend((0.5, 0.5, 0.5), M.phong((0.7, 0.7, 0.7), 0.7), M.lambert((0.2, 0.3, 0.7)), fresnel=True), nm, swap_xy=True))
+    gls = scn.add_material(M.with_normal_map(M.glass((0.95, 0.98, 0.95), ior=1.5, gloss=1.0), nm))
+    emi = scn.add_material(M.emissive((17.0, 15.0, 12.0), 0))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, floor, white, white), inward=True, skip_faces=(4,))))
+    sph = S.sphere_mesh(1.0, 32, 16)
+    for mat, mtx in ((ggxm, S.translate(-2.0, -2.8, -1.0) @ S.scale(1.2, 1.2, 1.2)), (gls, S.translate(1.8, -2.9, 1.2) @ S.scale(1.1, 1.1, 1.1))):
+        scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, mat, np.int32))), mtx)
+    scn.add_instance(scn.add_mesh(S.box_mesh(0.9, 1.4, 0.9, mat_ids=(bl,)*6, inward=False)), S.translate(0.3, -2.6, -1.8) @ S.rotate_y(0.5))
+    l0 = scn.add_light(M.area_light((0.0, 3.95, 0.0), (1.0, 1.0), (17.0, 15.0, 12.0)))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l0)
+    return scn.build()
+
+
 def cornell_with_cutout(width=96, height=96):
     """The Cornell room with two instances of a quad whose material has an opacity (cut-out) map - a checker of opaque and transparent
     cells, bilinear and point sampled - in front of the back wall and above the floor: the quads go into the alpha-tested tree 1, rays
