@@ -683,20 +683,25 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   // hc_stats and the roofline of bench.py).  Events on the launching stream cost ~1 us each, i.e. well below 1 % of a pass.
   size_t evUsed = 0;
   p->evClass.clear();
+  bool timed = true;                           // stage events only on the LAST pass of a call: 2 event records per launch are not free for small frames
   auto stageBegin = [&](int cls) -> int
   {
+    if (!timed) return 0;
     if (evUsed + 2 > p->evPool.size()) { p->evPool.resize(evUsed + 2, nullptr); for (size_t k = evUsed; k < evUsed + 2; k++) if (cudaEventCreate(&p->evPool[k]) != cudaSuccess) return HC_E_NOMEM; }
     p->evClass.push_back(cls);
     return int(cudaEventRecord(p->evPool[evUsed], ctx->stream));
   };
-  auto stageEnd = [&]() -> int { const int rc = int(cudaEventRecord(p->evPool[evUsed + 1], ctx->stream)); evUsed += 2; return rc; };
+  auto stageEnd = [&]() -> int { if (!timed) return 0; const int rc = int(cudaEventRecord(p->evPool[evUsed + 1], ctx->stream)); evUsed += 2; return rc; };
 #define HC_STAGE(cls, launch) { if ((rc = stageBegin(cls))) return rc; launch; if ((rc = stageEnd())) return rc; }
 
-  for (int pass = 0; pass < passes; pass++)
+  // one pass = a fixed sequence of launches (live counts stay on the device), so untimed passes of a multi-pass call are replayed from a
+  // CUDA graph captured once per call: at 512x512 (C1) the ~40 launches / memsets of a pass cost more to enqueue one by one than to run.
+  // Not for QMC (the pass index is a kernel argument).  The last pass of a call always runs directly, with the stage events.
+  auto enqueuePass = [&]() -> int
   {
-    pp.qmcPass = ctx->passCounter;
+    int rc = 0;
     HC_CUDA(cudaMemsetAsync(counts, 0, 256*sizeof(int), ctx->stream));
-    HC_CUDA(cudaEventRecord(ctx->evStage[0], ctx->stream));
+    if (timed) HC_CUDA(cudaEventRecord(ctx->evStage[0], ctx->stream));
     HcPathState st0 = StateOf(p, 0, qmc);
     HC_STAGE(3, (k_pt_generate<<<(n + 255)/256, 256, 0, ctx->stream>>>(cam, pp, n, (const int*)p->owned.ptr, (uint2*)ctx->pixelRng.ptr, rmQMC, qtab, st0, counts)));
     HC_CUDA(cudaGetLastError());
@@ -755,11 +760,49 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
       ctx->stats.kernelLaunches++;
       cur = 1 - cur;
     }
-    HC_CUDA(cudaEventRecord(ctx->evStage[1], ctx->stream));
+    if (timed) HC_CUDA(cudaEventRecord(ctx->evStage[1], ctx->stream));
+    return HC_OK;
+  };
+  // measured (scripts/gpu_graph_ab.py, ms per pass, graph / direct): C1 512x512 64 passes 0.637 / 0.681, 16 passes 0.659 / 0.690, 4 passes 0.741 / 0.729;
+  // C3 1080p 64 passes 6.73 / 6.71, 4 passes 7.07 / 6.78 (capture + instantiate cost about 1 ms): worth it only for long calls
+  const bool useGraph = !qmc && passes >= 32 && getenv("HC_PT_NO_GRAPH") == nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  uint64_t launchesPerPass = 0;
+  for (int pass = 0; pass < passes; pass++)
+  {
+    pp.qmcPass = ctx->passCounter;
+    timed = (pass == passes - 1);
+    if (useGraph && !timed)
+    {
+      if (gexec == nullptr)
+      {
+        const uint64_t l0 = ctx->stats.kernelLaunches, p0 = ctx->stats.paths;
+        HC_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueuePass();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != HC_OK || e != cudaSuccess || graph == nullptr)
+        {
+          if (graph) cudaGraphDestroy(graph);
+          cudaGetLastError();
+          hc_set_error("hc_pt_pass: capturing the pass into a CUDA graph failed");
+          return rc != HC_OK ? rc : HC_E_STATE;
+        }
+        launchesPerPass = ctx->stats.kernelLaunches - l0;
+        ctx->stats.kernelLaunches = l0; ctx->stats.paths = p0;
+        const cudaError_t e2 = cudaGraphInstantiate(&gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e2 != cudaSuccess) { cudaGetLastError(); hc_set_error("hc_pt_pass: cudaGraphInstantiate failed"); return HC_E_STATE; }
+      }
+      const cudaError_t e3 = cudaGraphLaunch(gexec, ctx->stream);
+      if (e3 != cudaSuccess) { cudaGraphExecDestroy(gexec); cudaGetLastError(); hc_set_error("hc_pt_pass: cudaGraphLaunch failed"); return HC_E_STATE; }
+      ctx->stats.kernelLaunches += launchesPerPass; ctx->stats.paths += (uint64_t)n;
+    }
+    else if ((rc = enqueuePass())) { if (gexec) cudaGraphExecDestroy(gexec); return rc; }
     ctx->passCounter++;
     ctx->spp += qmc ? double(n)*ctx->worldSize/double(W*H) : 1.0;
-    if (pass + 1 < passes) { evUsed = 0; p->evClass.clear(); }      // keep only the last pass's pairs (the pool is reused)
   }
+  if (gexec) { HC_CUDA(cudaStreamSynchronize(ctx->stream)); cudaGraphExecDestroy(gexec); }
 #undef HC_STAGE
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0.0f; HC_CUDA(cudaEventElapsedTime(&ms, ctx->evStage[0], ctx->evStage[1]));
