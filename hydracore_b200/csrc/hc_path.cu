@@ -513,8 +513,8 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
     memcpy(&ntex, m + HC_NORMAL_TEX_OFFSET, 4); memcpy(&ptex, m + HC_PROC_TEX1_F4_HEAD_OFFSET, 4);
     const bool ok = type == HC_PLAIN_MAT_CLASS_LAMBERT || type == HC_PLAIN_MAT_CLASS_PHONG_SPECULAR || type == HC_PLAIN_MAT_CLASS_BLINN_SPECULAR || type == HC_PLAIN_MAT_CLASS_GGX ||
                     type == HC_PLAIN_MAT_CLASS_PERFECT_MIRROR || type == HC_PLAIN_MAT_CLASS_GLASS || type == HC_PLAIN_MAT_CLASS_BLEND_MASK ||
-                    type == HC_PLAIN_MAT_CLASS_EMISSIVE || type == HC_PLAIN_MAT_CLASS_OREN_NAYAR || type == HC_PLAIN_MAT_CLASS_TRANSLUCENT;
-    if (!ok) { why = "material class " + std::to_string(type) + " is not supported yet (Lambert, Oren-Nayar, translucent, Phong, Blinn, GGX, mirror, glass, blend mask are)"; return HC_E_ARG; }
+                    type == HC_PLAIN_MAT_CLASS_EMISSIVE || type == HC_PLAIN_MAT_CLASS_OREN_NAYAR || type == HC_PLAIN_MAT_CLASS_TRANSLUCENT || type == HC_PLAIN_MAT_CLASS_THIN_GLASS;
+    if (!ok) { why = "material class " + std::to_string(type) + " is not supported yet (Lambert, Oren-Nayar, translucent, Phong, Blinn, GGX, mirror, glass, thin glass, blend mask are)"; return HC_E_ARG; }
     if (ntex != HC_INVALID_TEXTURE)            // normal map: image in the "textures_aux" storage, found through the aux texture table
     {
       p->haveNormalMaps = true;

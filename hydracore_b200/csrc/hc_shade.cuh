@@ -5,7 +5,7 @@
 // file:line cited per function).  Formulas, operation order and — where it changes rounding — the C++ promotion of the
 // reference's unqualified math calls to double (see hc_math.cuh) are kept, so that the same random numbers give the same
 // path on the GPU and in the CPU oracle.  Supported: Lambert, Oren-Nayar, translucent Lambert, Phong, Blinn (Torrance-Sparrow), GGX (Heitz VNDF sampling +
-// multiscattering table), perfect mirror, GGX glass, blend masks (simple / fresnel / sigmoid), emissive materials, normal maps; rectangular / disk / sphere
+// multiscattering table), perfect mirror, GGX glass, thin glass, blend masks (simple / fresnel / sigmoid), emissive materials, normal maps; rectangular / disk / sphere
 // area lights, omni / spot point lights, directional lights, sky domes (constant or textured); RGBA8 and float4 textures.
 // Everything else is rejected with an error at hc_pt_init (no silent fallback).
 #pragma once
@@ -19,6 +19,7 @@
 #define HC_INV_PI     0.31830988618379067154f
 #define HC_INV_TWOPI  0.15915494309189533577f
 #define HC_M_TWOPI    6.28318530717958647692f
+#define HC_M_PI_D     3.14159265358979323846       // M_PI of <cmath> (a double) where the reference's host build uses it
 #define HC_PI_D       3.14159265358979323846     // M_PI comes from <math.h> as a DOUBLE in the oracle build (cglobals.h:43 is skipped)
 #define HC_INVALID_TEXTURE ((int)0xFFFFFFFE)
 
@@ -415,6 +416,32 @@ HC_DEV void TranslucentSample(const float* m, float r1, float r2, float3 n, floa
   out.color = kd*HC_INV_PI;
   if (cosTheta <= 1e-6f) out.color = f3(0, 0, 0);
   out.flags = (HC_RAY_EVENT_D | HC_RAY_EVENT_T);
+}
+
+// ---- thin glass (cmaterial.h:471-555): straight-through (optionally glossy) transmission, invisible to explicit light sampling
+HC_DEV void ThinglassSample(const float* m, float r1, float r2, float3 rayDir, float3 n, float2 tc, const HcScene& s, HcMatSample& out)
+{
+  const float3 tex = Sample2D(MatI(m, HC_PHONG_TEXMATRIXID_OFFSET), tc, m, s);
+  const float3 gc = Sample2D(MatI(m, HC_PHONG_GLOSINESS_TEXMATRIXID_OFFSET), tc, m, s);           // thinglassCosPower: the slots coincide with Phong's
+  const float cosPower = cosPowerFromGlosiness(clampf(m[HC_PHONG_GLOSINESS_OFFSET]*maxcomp(gc), 0.0f, 1.0f));
+  float pdf = 1.0f, fVal = 1.0f;
+  if (cosPower < 1e6f)
+  {
+    bool under = false;
+    const float3 oldDir = rayDir;
+    rayDir = MapSampleToModifiedCosineDistribution(r1, r2, rayDir, (-1.0f)*n, cosPower, under);
+    const float cosTheta = clampf(dot(oldDir, rayDir), 0.0f, (float)(HC_M_PI_D*D(0.499995f)));
+    fVal = (float)(D((cosPower + 2.0f)*HC_INV_TWOPI)*pow(D(cosTheta), D(cosPower)));
+    if (under) fVal = 0.0f;
+    pdf = (float)(pow(D(cosTheta), D(cosPower))*D(cosPower + 1.0f)*D(0.5f*HC_INV_PI));
+  }
+  const float cosThetaOut = dot(rayDir, n);
+  const float cosMult = 1.0f/fmaxf(fabsf(cosThetaOut), 1e-6f);
+  out.direction = rayDir;
+  out.pdf = pdf;
+  out.color = fVal*Mat3(m, HC_PHONG_COLORX_OFFSET)*tex*cosMult;
+  if (cosThetaOut >= -1e-6f) out.color = f3(0, 0, 0);
+  out.flags = (HC_RAY_EVENT_S | HC_RAY_EVENT_T | HC_RAY_EVENT_TNINGLASS);
 }
 
 // ---- perfect mirror (cmaterial.h:385-421)
@@ -822,6 +849,7 @@ HC_DEV void LeafSample(const float* m, const HcSurfaceHit& shIn, float3 rayDir, 
     case HC_PLAIN_MAT_CLASS_PERFECT_MIRROR: MirrorSample(m, rayDir, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_GLASS:          GlassGgxSample(m, rands, rayDir, sh.normal, sh.texCoord, sh.hfi, s, out); break;
     case HC_PLAIN_MAT_CLASS_LAMBERT:        LambertSample(m, rands.x, rands.y, sh.normal, sh.texCoord, s, out); break;
+    case HC_PLAIN_MAT_CLASS_THIN_GLASS:     ThinglassSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_TRANSLUCENT:    TranslucentSample(m, rands.x, rands.y, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_OREN_NAYAR:     OrennayarSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
     default: break;
@@ -905,7 +933,7 @@ HC_DEV HcBxDF LeafEval(const float* m, float3 l, float3 v, const HcSurfaceHit& s
       r.brdf = OrennayarEvalBxDF(m, l, v, n, tc, s)*cosMult; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
     case HC_PLAIN_MAT_CLASS_TRANSLUCENT:
       r.btdf = TranslucentEvalBxDF(m, l, v, n, tc, s)*cosMult2; r.pdfFwd = TranslucentEvalPDF(l, v, n); r.pdfRev = TranslucentEvalPDF(v, l, n); r.diffuse = true; break;
-    default: break;      // mirror and glass evaluate to zero for explicit light (cmaterial.h:396-404, 620-629)
+    default: break;      // mirror, glass and thin glass evaluate to zero for explicit light (cmaterial.h:396-404, 620-629)
   }
   return r;
 }
@@ -1094,7 +1122,6 @@ HC_DEV void PointLightSampleRev(const float* L, float3 illum, HcShadowSample& ou
 #define HC_SKY_DOME_SAMPLER0    32
 #define HC_SKY_DOME_MATRIX0     36
 #define HC_SKY_DOME_INV_MATRIX0 56
-#define HC_M_PI_D 3.14159265358979323846
 HC_DEV float2 SphereMapTo2DTexCoord(float3 rayDir, float& sinTheta)                                                          // cfetch.h:258-281
 {
   const float x = rayDir.z, y = rayDir.x, z = -rayDir.y;

@@ -86,6 +86,12 @@ def lambert(color, tex_id=0, **kw):
     return m
 
 
+def thin_glass(color, gloss=1.0, tex_id=0, **kw):
+    """Thin glass (ThinGlassMaterial, PlainMaterialConverter.cpp:254-285; cmaterial.h:471-555): light passes straight through (a glossy lobe about
+    the ray direction when gloss < 1), tinted by `color`; Phong's slot layout."""
+    return _glossy(C["PLAIN_MAT_CLASS_THIN_GLASS"], color, gloss, tex_id, 0, **kw)
+
+
 def translucent(color, tex_id=0, **kw):
     """Translucent Lambert (TranslucentMaterial, PlainMaterialConverter.cpp; cmaterial.h:1850-1910): cosine-distributed transmission through
     the surface, Lambert's colour / texture slots; flag PLAIN_MATERIAL_HAS_DIFFUSE like the converter sets."""

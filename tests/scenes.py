@@ -171,7 +171,7 @@ def cornell_spot_and_direct_lights(width=96, height=96, soft_sun=True):
 
 def cornell_translucent(width=96, height=96):
     """The Cornell room with a translucent curtain (a quad, translucent on its own and as one side of a blend with Lambert) between the
-    light and the floor, and a translucent sphere: light reaches the floor only by diffuse transmission."""
+    light and the floor, a translucent sphere, and two thin-glass panes (clear and frosted) in front of the camera."""
     from hydracore_b200 import materials as M
     scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
     scn.set_trace_depth(5, 3)
@@ -179,12 +179,16 @@ def cornell_translucent(width=96, height=96):
     red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
     green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
     tr = scn.add_material(M.translucent((0.8, 0.75, 0.5)))
+    tg = scn.add_material(M.thin_glass((0.9, 0.7, 0.7), gloss=1.0))
+    tgg = scn.add_material(M.thin_glass((0.7, 0.9, 0.7), gloss=0.8))
     trb = scn.add_material(M.blend((0.5, 0.5, 0.5), M.translucent((0.3, 0.6, 0.9)), M.lambert((0.6, 0.6, 0.6)), fresnel=False))
     emi = scn.add_material(M.emissive((17.0, 15.0, 12.0), 0))
     scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, white, white, white), inward=True, skip_faces=(4,))))
     scn.add_instance(scn.add_mesh(S.quad_mesh(3.0, 3.0, mat_id=tr)), S.translate(-0.8, 1.5, 0.0))
     sph = S.sphere_mesh(1.0, 32, 16)
     scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, trb, np.int32))), S.translate(1.5, -2.6, 1.0) @ S.scale(1.4, 1.4, 1.4))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(1.2, 1.2, mat_id=tg)), S.translate(-2.2, -1.0, 2.0) @ S.rotate_x(np.pi/2))        # clear pane facing the camera
+    scn.add_instance(scn.add_mesh(S.quad_mesh(1.2, 1.2, mat_id=tgg)), S.translate(2.4, 0.5, 1.5) @ S.rotate_x(np.pi/2))        # frosted pane
     l0 = scn.add_light(M.area_light((0.0, 3.95, 0.0), (1.0, 1.0), (17.0, 15.0, 12.0)))
     scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l0)
     return scn.build()
