@@ -43,6 +43,8 @@ SIGNATURES = {
     "hc_set_globals": (_I, [_P, _P, _U64]),
     "hc_set_bvh": (_I, [_P, _I, _P, _I, _P, _I, _I]),
     "hc_set_bvh_alpha": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I]),
+    "hc_set_remap_lists": (_I, [_P, _P, _P, _I, _I]),
+    "hc_set_inst_remap_ids": (_I, [_P, _P, _I]),
     "hc_bvh_device_layout": (_I, [_P, _I, _P, _I, _P, _P, _I64, ct.POINTER(_I64), ct.POINTER(_I)]),
     "hc_set_inst_matrices": (_I, [_P, _P, _I]),
     "hc_set_inst_light_ids": (_I, [_P, _P, _I]),

@@ -107,6 +107,17 @@ void GPUCUDALayer::SetAllInstLightInstId(const int32_t* a_lightInstIds, int32_t 
   Check(hc_set_inst_light_ids(m_ctx, a_lightInstIds, a_instNum), "SetAllInstLightInstId");
 }
 
+void GPUCUDALayer::SetAllRemapLists(const int* a_allLists, const int2* a_table, int a_allSize, int a_tableSize)
+{
+  // per-instance material overrides (HydraAPI remap lists); empty input clears them, as GPUOCLData.cpp:203-210 does
+  Check(hc_set_remap_lists(m_ctx, a_allLists, reinterpret_cast<const int32_t*>(a_table), a_allSize, a_tableSize), "SetAllRemapLists");
+}
+
+void GPUCUDALayer::SetAllInstIdToRemapId(const int* a_allInstId, int a_instNum)
+{
+  Check(hc_set_inst_remap_ids(m_ctx, a_allInstId, a_instNum), "SetAllInstIdToRemapId");
+}
+
 void GPUCUDALayer::SetAllPODLights(PlainLight* a_lights2, size_t a_number)
 {
   Base::SetAllPODLights(a_lights2, a_number);                   // lights + sky / sun bookkeeping into m_cdataPrepared (IHWLayerDataAssembler.cpp:390-452)

@@ -28,6 +28,8 @@ public:
   void SetAllBVH4(const ConvertionResult& a_convertedBVH, IBVHBuilder2* a_inBuilderAPI, int a_flags) override;
   void SetAllInstMatrices(const float4x4* a_matrices, int32_t a_matrixNum) override;
   void SetAllInstLightInstId(const int32_t* a_lightInstIds, int32_t a_instNum) override;
+  void SetAllRemapLists(const int* a_allLists, const int2* a_table, int a_allSize, int a_tableSize) override;
+  void SetAllInstIdToRemapId(const int* a_allInstId, int a_instNum) override;
   void SetAllPODLights(PlainLight* a_lights2, size_t a_number) override;
   void SetAllFlagsAndVars(const AllRenderVarialbes& a_vars) override;
 

@@ -113,6 +113,12 @@ int hl_set_bvh2(void* p, const void* nodes, int nodesNum, const float* trif4, in
     s->layer->SetAllBVH4(r, nullptr, 0);
   });
 }
+int hl_set_remap(void* p, const int* allLists, int allSize, const int* tableOffsetAndSize, int tableSize, const int* instRemapId, int nInst)
+{
+  Session* s = static_cast<Session*>(p);
+  return Guard([&] { s->layer->SetAllRemapLists(allLists, reinterpret_cast<const int2*>(tableOffsetAndSize), allSize, tableSize);
+                     s->layer->SetAllInstIdToRemapId(instRemapId, nInst); });
+}
 int hl_set_instances(void* p, const float* invMatrices16, const int32_t* lightInstIds, int n)
 {
   Session* s = static_cast<Session*>(p);

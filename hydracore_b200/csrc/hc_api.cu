@@ -384,7 +384,7 @@ void hc_ctx_destroy(hc_ctx* c)
   cudaStreamSynchronize(c->stream);
   hc_path_free(c);
   for (int i = 0; i < HC_STORAGE_COUNT; i++) hc_buf_free(c->storage[i]);
-  hc_buf_free(c->globals); hc_buf_free(c->bvhNodes); hc_buf_free(c->bvhTris); hc_buf_free(c->bvh1Nodes); hc_buf_free(c->bvh1Tris); hc_buf_free(c->bvh1AlphaPairs); hc_buf_free(c->bvh1AlphaTable); hc_buf_free(c->instMatrices); hc_buf_free(c->instLightIds);
+  hc_buf_free(c->globals); hc_buf_free(c->bvhNodes); hc_buf_free(c->bvhTris); hc_buf_free(c->bvh1Nodes); hc_buf_free(c->bvh1Tris); hc_buf_free(c->bvh1AlphaPairs); hc_buf_free(c->bvh1AlphaTable); hc_buf_free(c->remapLists); hc_buf_free(c->remapTable); hc_buf_free(c->remapInst); hc_buf_free(c->instMatrices); hc_buf_free(c->instLightIds);
   hc_buf_free(c->fbSum); hc_buf_free(c->scratchRays); hc_buf_free(c->scratchOut); hc_buf_free(c->counters); hc_buf_free(c->pixelRng); hc_buf_free(c->qmcTable);
   hc_buf_free(c->rcRays); hc_buf_free(c->rcHits); hc_buf_free(c->rcSRays); hc_buf_free(c->rcVis);
   for (int i = 0; i < 5; i++) cudaEventDestroy(c->evStage[i]);
@@ -500,6 +500,32 @@ int hc_set_bvh(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const v
 { return SetBvhTree(ctx, treeId, nodes, nodesNum, trif4, trif4Num, nullptr, 0, haveInst); }
 int hc_set_bvh_alpha(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, const void* trif4, int trif4Num, const void* alphaTableUint2, int alphaNum, int haveInst)
 { return SetBvhTree(ctx, treeId, nodes, nodesNum, trif4, trif4Num, alphaTableUint2, alphaNum, haveInst); }
+
+// material remap lists: per-instance material overrides looked up in surface evaluation (remapMaterialId, cglobals.h:2931-2983)
+int hc_set_remap_lists(hc_ctx* ctx, const int32_t* allLists, const int32_t* tableOffsetAndSize, int allSize, int tableSize)
+{
+  if (!ctx) return HC_E_ARG;
+  if (!allLists || !tableOffsetAndSize || allSize <= 0 || tableSize <= 0) { ctx->remapListsSize = 0; ctx->remapTableSize = 0; return HC_OK; }   // GPUOCLData.cpp:203-210
+  HC_CUDA(cudaSetDevice(ctx->device));
+  int rc = hc_buf_reserve(ctx, ctx->remapLists, size_t(allSize)*4); if (rc) return rc;
+  rc = hc_buf_reserve(ctx, ctx->remapTable, size_t(tableSize)*8); if (rc) return rc;
+  HC_CUDA(cudaMemcpyAsync(ctx->remapLists.ptr, allLists, size_t(allSize)*4, cudaMemcpyHostToDevice, ctx->stream));
+  HC_CUDA(cudaMemcpyAsync(ctx->remapTable.ptr, tableOffsetAndSize, size_t(tableSize)*8, cudaMemcpyHostToDevice, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->remapListsSize = allSize; ctx->remapTableSize = tableSize;
+  return HC_OK;
+}
+int hc_set_inst_remap_ids(hc_ctx* ctx, const int32_t* instRemapListId, int n)
+{
+  if (!ctx) return HC_E_ARG;
+  if (!instRemapListId || n <= 0) { ctx->remapInstSize = 0; return HC_OK; }
+  HC_CUDA(cudaSetDevice(ctx->device));
+  int rc = hc_buf_reserve(ctx, ctx->remapInst, size_t(n)*4); if (rc) return rc;
+  HC_CUDA(cudaMemcpyAsync(ctx->remapInst.ptr, instRemapListId, size_t(n)*4, cudaMemcpyHostToDevice, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->remapInstSize = n;
+  return HC_OK;
+}
 
 int hc_bvh_device_layout(const void* nodes, int nodesNum, const void* trif4, int trif4Num, float* outNodes, float* outPairs,
                          int64_t outPairsCapacityFloats, int64_t* outPairsFloats, int* outStackBound)

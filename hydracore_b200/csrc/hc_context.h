@@ -38,6 +38,8 @@ struct hc_ctx
   HcDevBuf bvhNodes, bvhTris;              // tree 0 (opaque geometry)
   HcDevBuf bvh1Nodes, bvh1Tris, bvh1AlphaPairs, bvh1AlphaTable;   // tree 1 (meshes with opacity maps), its per-pair alpha words and the reference's alpha table
   bool     haveTree1 = false, haveAlpha1 = false;
+  HcDevBuf remapLists, remapTable, remapInst;   // material remap lists (SetAllRemapLists / SetAllInstIdToRemapId)
+  int      remapListsSize = 0, remapTableSize = 0, remapInstSize = 0;
   int      nodesNum = 0, trif4Num = 0, haveInst = 1, bvhDepthBound = 0;
   HcDevBuf instMatrices, instLightIds;
   int      numInst = 0;

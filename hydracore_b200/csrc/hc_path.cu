@@ -283,7 +283,7 @@ HC_DEV int SortKeyOf(const HcScene& s, const HcHit& h, int numKeys)
   const int meshOff = s.globals[s.geometryTableOffset + h.geomId];
   const float4* mesh = s.geom + meshOff;
   const int mIdxOff = reinterpret_cast<const int4*>(mesh)[2].x;                // PlainMesh::mIndicesOffset (cfetch.h:1038-1059)
-  const int matId = reinterpret_cast<const int*>(mesh + mIdxOff)[h.primId];
+  const int matId = RemapMaterialId(s, reinterpret_cast<const int*>(mesh + mIdxOff)[h.primId], h.instId);
   return min(max(matId, 0), numKeys - 2);
 }
 
@@ -552,6 +552,10 @@ static HcScene MakeScene(hc_ctx* ctx)
   s.pdfTableTableOffset = gi(HC_EG_pdfTableTableOffset);
   s.instMatrices = (const float4*)ctx->instMatrices.ptr;
   s.instLightIds = (const int*)ctx->instLightIds.ptr;
+  s.remapLists = ctx->remapListsSize > 0 ? (const int*)ctx->remapLists.ptr : nullptr;
+  s.remapTable = ctx->remapTableSize > 0 ? (const int2*)ctx->remapTable.ptr : nullptr;
+  s.remapInst  = ctx->remapInstSize > 0 ? (const int*)ctx->remapInst.ptr : nullptr;
+  s.remapListsSize = ctx->remapListsSize; s.remapTableSize = ctx->remapTableSize; s.remapInstSize = ctx->remapInstSize;
   s.materialsTableOffset = gi(HC_EG_materialsTableOffset); s.geometryTableOffset = gi(HC_EG_geometryTableOffset);
   s.texturesTableOffset = gi(HC_EG_texturesTableOffset);
   s.lightSelTableOffsetRev = gi(HC_EG_lightSelectorTableOffsetRev); s.lightSelTableSizeRev = gi(HC_EG_lightSelectorTableSizeRev);

@@ -36,6 +36,10 @@ struct HcScene
   const float4* __restrict__ pdfs;          // "pdfs" storage (sky-dome pdf tables)
   const float4* __restrict__ instMatrices;  // inverse instance matrices, 4 float4 each
   const int*    __restrict__ instLightIds;  // instance -> light index or -1
+  const int*    __restrict__ remapLists;    // material remap lists {from, to} pairs back to back, or nullptr (SetAllRemapLists, IHWLayer.h:122)
+  const int2*   __restrict__ remapTable;    // per list {offset into remapLists, size}
+  const int*    __restrict__ remapInst;     // instance -> remap list id or -1 (SetAllInstIdToRemapId, IHWLayer.h:123)
+  int remapListsSize, remapTableSize, remapInstSize;
   int materialsTableOffset, geometryTableOffset, texturesTableOffset, texturesAuxTableOffset, pdfTableTableOffset;
   int lightSelTableOffsetRev, lightSelTableSizeRev, lightsOffset, lightsNum, skyLightId;
   int gflags, traceDepth, diffTraceDepth;
@@ -218,6 +222,32 @@ HC_DEV float3 Sample2D(int samplerOffset, float2 tc, const float* mat, const HcS
   return f3(c.x, c.y, c.z);
 }
 
+// remapMaterialId (cglobals.h:2931-2983): per-instance material override, binary search for the first "from" id >= matId in the instance's list.
+// The reference searches offsAndSize.y PAIRS although the driver stores the number of INTS there (RenderDriverRTE.cpp:1348-1365), so the search
+// can run past the list; reads are clamped to the array here (the reference reads whatever follows).
+HC_DEV int RemapMaterialId(const HcScene& s, int mId, int instId)
+{
+  if (mId < 0 || instId < 0 || instId >= s.remapInstSize || s.remapInst == nullptr || s.remapLists == nullptr || s.remapTable == nullptr) return mId;
+  const int listId = s.remapInst[instId];
+  if (listId < 0 || listId >= s.remapTableSize) return mId;
+  const int2 os = s.remapTable[listId];
+  int low = 0, high = os.y - 1;
+  while (low <= high)
+  {
+    const int mid = low + ((high - low)/2);
+    const int at = os.x + mid*2;
+    const int from = (at >= 0 && at < s.remapListsSize) ? s.remapLists[at] : 0x7fffffff;
+    if (from >= mId) high = mid - 1; else low = mid + 1;
+  }
+  if (high + 1 < os.y)
+  {
+    const int at = os.x + (high + 1)*2;
+    if (at < 0 || at + 1 >= s.remapListsSize) return mId;
+    return (s.remapLists[at] == mId) ? s.remapLists[at + 1] : mId;
+  }
+  return mId;
+}
+
 // ------------------------------------------------------------------------------------------------------------------ a10: surface evaluation
 // surfaceEvalLS (ctrace.h:2005-2109) + the world transform of IntegratorCommon::surfaceEval / kernel_EvalSurface
 // (CPUExp_Integrators_Common.cpp:193-242, CPUExp_Integrators_PT_Loop.cpp:35-84) and ComputeHit (shaders/trace.cl:130-227)
@@ -299,6 +329,7 @@ HC_DEV HcSurfaceHit SurfaceEval(const HcScene& s, float3 rpos, float3 rdir, cons
   ws.biTangent  = normalize(mul3x3(nm, sh.biTangent));
   ws.t          = length(ws.pos - rpos);
   ws.sRayOff    = length(shadowStart);
+  ws.matId      = RemapMaterialId(s, ws.matId, hit.instId);
   return ws;
 }
 

@@ -135,6 +135,18 @@ class CudaLayer:
         m = np.ascontiguousarray(inv_matrices, dtype=np.float32).reshape(-1, 16)
         check(self._L.hc_set_inst_matrices(self._c, _ptr(m), m.shape[0]), "hc_set_inst_matrices")
 
+    def SetAllRemapLists(self, all_lists, table, inst_remap_ids):
+        """SetAllRemapLists + SetAllInstIdToRemapId (IHWLayer.h:122-123); None clears."""
+        if all_lists is None or len(all_lists) == 0:
+            check(self._L.hc_set_remap_lists(self._c, None, None, 0, 0), "hc_set_remap_lists")
+            check(self._L.hc_set_inst_remap_ids(self._c, None, 0), "hc_set_inst_remap_ids")
+            return
+        a = np.ascontiguousarray(all_lists, dtype=np.int32).reshape(-1)
+        t = np.ascontiguousarray(table, dtype=np.int32).reshape(-1, 2)
+        r = np.ascontiguousarray(inst_remap_ids, dtype=np.int32).reshape(-1)
+        check(self._L.hc_set_remap_lists(self._c, _ptr(a), _ptr(t), a.size, t.shape[0]), "hc_set_remap_lists")
+        check(self._L.hc_set_inst_remap_ids(self._c, _ptr(r), r.size), "hc_set_inst_remap_ids")
+
     def SetAllInstLightInstId(self, ids):
         a = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1)
         check(self._L.hc_set_inst_light_ids(self._c, _ptr(a), a.size), "hc_set_inst_light_ids")
@@ -253,6 +265,10 @@ class CudaLayer:
             self.SetAllBVH4(scn.bvh1["nodes"], scn.bvh1["tris"], tree=1, alpha=scn.bvh1["alpha"])
         self.SetAllInstMatrices(scn.bvh["inv_matrices"])
         self.SetAllInstLightInstId(scn.inst_light_ids)
+        if getattr(scn, "remap_lists", None):
+            self.SetAllRemapLists(*scn.remap_arrays())
+        else:
+            self.SetAllRemapLists(None, None, None)
         self.ResizeScreen(scn.width, scn.height)
         self.PrepareEngineGlobals(scn.globals_blob)
 

@@ -309,9 +309,30 @@ class Scene:
         self.meshes.append(mesh)
         return len(self.meshes) - 1
 
-    def add_instance(self, mesh_id, matrix=None, light_id=-1):
+    def add_instance(self, mesh_id, matrix=None, light_id=-1, remap_list=-1):
+        """remap_list: id from add_remap_list - this instance renders with some material ids replaced (HydraAPI remap lists)."""
         self.instances.append((mesh_id, np.eye(4, dtype=np.float32) if matrix is None else np.asarray(matrix, np.float32), light_id))
+        self.inst_remap = getattr(self, "inst_remap", [])
+        self.inst_remap += [-1]*(len(self.instances) - 1 - len(self.inst_remap)) + [int(remap_list)]
         return len(self.instances) - 1
+
+    def add_remap_list(self, pairs):
+        """pairs: [(from_material_id, to_material_id), ...]; stored sorted by `from` (remapMaterialId does a binary search, cglobals.h:2931-2983)."""
+        self.remap_lists = getattr(self, "remap_lists", [])
+        self.remap_lists.append(sorted((int(a), int(b)) for a, b in pairs))
+        return len(self.remap_lists) - 1
+
+    def remap_arrays(self):
+        """What RenderDriverRTE hands to SetAllRemapLists / SetAllInstIdToRemapId (RenderDriverRTE.cpp:1340-1376, 1478): all lists back to back,
+        {offset, size in INTS} per list, list id per instance."""
+        lists = getattr(self, "remap_lists", [])
+        flat, table = [], []
+        for l in lists:
+            table.append((len(flat), 2*len(l)))
+            for a, b in l:
+                flat += [a, b]
+        inst = list(getattr(self, "inst_remap", [])) + [-1]*(len(self.instances) - len(getattr(self, "inst_remap", [])))
+        return np.array(flat, np.int32), np.array(table, np.int32).reshape(-1, 2), np.array(inst, np.int32)
 
     def add_material(self, nodes):
         """nodes: one PlainMaterial (192 floats) or a list of consecutive nodes (blend trees reference children by relative offset)."""

@@ -84,6 +84,10 @@ int hc_bvh_device_layout(const void* nodes, int nodesNum, const void* trif4, int
                                                                                  pair records) and the worst-case traversal stack; outNodes = nodesNum*8 floats */
 int hc_set_inst_matrices(hc_ctx* ctx, const float* invMatrices16, int n);    /* SetAllInstMatrices, IHWLayer.h:117                        */
 int hc_set_inst_light_ids(hc_ctx* ctx, const int32_t* lightInstId, int n);   /* SetAllInstLightInstId, IHWLayer.h:118                     */
+int hc_set_remap_lists(hc_ctx* ctx, const int32_t* allLists, const int32_t* tableOffsetAndSize, int allSize, int tableSize);
+                                                                              /* SetAllRemapLists, IHWLayer.h:122 (GPUOCLData.cpp:200-250): {from, to} material id pairs of
+                                                                                 all lists back to back + int2 {offset, size} per list; nullptr / 0 clears                  */
+int hc_set_inst_remap_ids(hc_ctx* ctx, const int32_t* instRemapListId, int n); /* SetAllInstIdToRemapId, IHWLayer.h:123: remap list id per instance or -1                 */
 int hc_resize(hc_ctx* ctx, int width, int height);                           /* ResizeScreen, IHWLayer.h:147                              */
 
 /* ---------------------------------------------------------------- ray casting (kernels K1, K2, K2s) ----------------------- */

@@ -48,6 +48,8 @@ namespace
     const uint2*          alpha1    = nullptr;   // RenderDriverRTE::CreateAlphaTestTable
     std::vector<float4x4> matrices;
     std::vector<int32_t>  lightInstId;
+    std::vector<int>      remapLists, remapInst;   // material remap lists (SetMaterialRemapListPtrs, CPUExp_Integrators_Common.cpp:103-112)
+    std::vector<int2>     remapTable;
     int w = 0, h = 0;
 
     EngineGlobals* G() { return (EngineGlobals*)globals.data(); }
@@ -171,6 +173,9 @@ namespace
     p->SetTexturesStorageAuxPtr(s->texturesAux);
     p->SetPdfStoragePtr(s->pdfs);
     p->SetMaxDepth(maxDepth);                       // CPUExpLayer.cpp:130: m_maxDepth = HRT_TRACE_DEPTH (PT adds 1 itself)
+    if (!s->remapLists.empty() && !s->remapTable.empty() && !s->remapInst.empty())
+      p->SetMaterialRemapListPtrs(s->remapLists.data(), s->remapTable.data(), s->remapInst.data(),
+                                  int(s->remapLists.size()), int(s->remapTable.size()), int(s->remapInst.size()));
   }
 }
 
@@ -314,6 +319,15 @@ void ref_scene_set_tree1(void* p, const void* nodes, const void* tris, const voi
 {
   RefScene* s = (RefScene*)p;
   s->nodes1 = (const BVHNode*)nodes; s->tris1 = (const float4*)tris; s->alpha1 = (const uint2*)alphaUint2;
+}
+// material remap lists: what the driver hands to SetAllRemapLists / SetAllInstIdToRemapId (RenderDriverRTE.cpp:1340-1376, 1478)
+void ref_scene_set_remap(void* p, const int* allLists, int allSize, const int* tableOffsetAndSize, int tableSize, const int* instRemapId, int nInst)
+{
+  RefScene* s = (RefScene*)p;
+  s->remapLists.assign(allLists, allLists + allSize);
+  s->remapTable.resize(tableSize);
+  for (int i = 0; i < tableSize; i++) s->remapTable[i] = int2(tableOffsetAndSize[2*i], tableOffsetAndSize[2*i + 1]);
+  s->remapInst.assign(instRemapId, instRemapId + nInst);
 }
 void ref_scene_destroy(void* p) { delete (RefScene*)p; }
 

@@ -42,7 +42,7 @@ class CppLayer:
         L.hl_contribute.argtypes = [ct.c_void_p, ct.c_void_p]
         L.hl_available_memory.restype = ct.c_uint64
         L.hl_available_memory.argtypes = [ct.c_void_p, ct.c_int]
-        for name in ("hl_destroy", "hl_create_storage", "hl_storage_update", "hl_storage_info", "hl_resize_tables", "hl_set_bvh", "hl_set_bvh2", "hl_set_instances",
+        for name in ("hl_destroy", "hl_create_storage", "hl_storage_update", "hl_storage_info", "hl_resize_tables", "hl_set_bvh", "hl_set_bvh2", "hl_set_remap", "hl_set_instances",
                      "hl_set_lights", "hl_set_camera", "hl_get_vars", "hl_set_vars", "hl_prepare", "hl_globals_blob", "hl_call", "hl_init_path_tracing",
                      "hl_passes", "hl_clear_accumulated", "hl_get_hdr", "hl_get_ldr", "hl_device_name", "hl_device_count", "hl_rays_stat",
                      "hl_store_cpu_data"):
@@ -96,6 +96,11 @@ class CppLayer:
         self._keep_type = ct.c_char_p(bvh_type)
         self._ck(self._L.hl_set_bvh2(self._s, P(a[0]), a[0].shape[0], P(a[1]), a[1].shape[0], P(a[2]), a[2].shape[0], P(a[3]), a[3].shape[0],
                                      P(a[4]), a[4].shape[0], self._keep_type), "SetAllBVH4")
+
+    def SetAllRemapLists(self, all_lists, table, inst_remap_ids):
+        a = [np.ascontiguousarray(all_lists, np.int32).reshape(-1), np.ascontiguousarray(table, np.int32).reshape(-1, 2),
+             np.ascontiguousarray(inst_remap_ids, np.int32).reshape(-1)]
+        self._ck(self._L.hl_set_remap(self._s, P(a[0]), a[0].size, P(a[1]), a[1].shape[0], P(a[2]), a[2].size), "SetAllRemapLists")
 
     def SetAllInstances(self, inv_matrices, light_ids):
         m = np.ascontiguousarray(inv_matrices, np.float32).reshape(-1, 16)
@@ -211,6 +216,8 @@ def load_scene_like_render_driver(lay, scn, consts):
         lay.SetAllBVH4TwoTrees(scn.bvh["nodes"], scn.bvh["tris"], scn.bvh1["nodes"], scn.bvh1["tris"], scn.bvh1["alpha"])
     else:
         lay.SetAllBVH4(scn.bvh["nodes"], scn.bvh["tris"])
+    if getattr(scn, "remap_lists", None):            # RenderDriverRTE::BeginScene sends the lists, EndScene the per-instance ids (RenderDriverRTE.cpp:1340-1376, 1478)
+        lay.SetAllRemapLists(*scn.remap_arrays())
     lay.SetAllInstances(scn.bvh["inv_matrices"], scn.inst_light_ids)
     cam = scn.camera
     W, H = scn.width, scn.height

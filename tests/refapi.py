@@ -95,6 +95,8 @@ class Ref:
         L.ref_scene_create.restype = ct.c_void_p
         L.ref_scene_create.argtypes = [ct.c_void_p, ct.c_longlong] + [ct.c_void_p]*7 + [ct.c_int, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_int, ct.c_int]
         L.ref_scene_destroy.argtypes = [ct.c_void_p]
+        if hasattr(L, "ref_scene_set_remap"):
+            L.ref_scene_set_remap.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_int]
         if hasattr(L, "ref_scene_set_tree1"):
             L.ref_scene_set_tree1.argtypes = [ct.c_void_p]*4
         L.ref_render_create.restype = ct.c_void_p
@@ -189,6 +191,9 @@ class RefScene:
                   np.ascontiguousarray(scn.bvh1["alpha"], np.uint32)]
             self._keep += t1
             ref.L.ref_scene_set_tree1(self.h, P(t1[0]), P(t1[1]), P(t1[2]))
+        if getattr(scn, "remap_lists", None):
+            al, tb, ri = scn.remap_arrays()
+            ref.L.ref_scene_set_remap(self.h, P(al), al.size, P(tb), tb.shape[0], P(ri), ri.size)
         self._renders = []
 
     def close(self):

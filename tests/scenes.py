@@ -229,6 +229,31 @@ def cornell_normal_mapped(width=96, height=96):
     return scn.build()
 
 
+def cornell_remap_lists(width=96, height=96):
+    """Three instances of ONE two-material box mesh: as modelled, with a remap list that swaps its materials for a mirror and a GGX one, and
+    with a list whose only entry does not apply (from-id absent) - per-instance material overrides (remapMaterialId)."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    blue = scn.add_material(M.lambert((0.1, 0.2, 0.7)))
+    mir = scn.add_material(M.mirror((0.9, 0.9, 0.9)))
+    ggxm = scn.add_material(M.ggx((0.8, 0.6, 0.2), 0.7))
+    emi = scn.add_material(M.emissive((17.0, 15.0, 12.0), 0))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, white, white, white), inward=True, skip_faces=(4,))))
+    box = scn.add_mesh(S.box_mesh(0.8, 1.2, 0.8, mat_ids=(blue, blue, white, white, red, red), inward=False))
+    swap = scn.add_remap_list([(blue, mir), (red, ggxm)])
+    noop = scn.add_remap_list([(green, mir)])
+    scn.add_instance(box, S.translate(-2.3, -2.8, 0.0) @ S.rotate_y(0.4))
+    scn.add_instance(box, S.translate(0.0, -2.8, -1.0) @ S.rotate_y(-0.3), remap_list=swap)
+    scn.add_instance(box, S.translate(2.3, -2.8, 0.5) @ S.rotate_y(0.9), remap_list=noop)
+    l0 = scn.add_light(M.area_light((0.0, 3.95, 0.0), (1.0, 1.0), (17.0, 15.0, 12.0)))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l0)
+    return scn.build()
+
+
 def cornell_with_cutout(width=96, height=96):
     """The Cornell room with two instances of a quad whose material has an opacity (cut-out) map - a checker of opaque and transparent
     cells, bilinear and point sampled - in front of the back wall and above the floor: the quads go into the alpha-tested tree 1, rays

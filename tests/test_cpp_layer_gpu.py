@@ -195,6 +195,20 @@ def test_ihwlayer_normal_mapped_scene_equals_c_abi_path(consts, layer):
     lay.close()
 
 
+def test_ihwlayer_remap_lists_equal_c_abi_path(consts, layer):
+    """SetAllRemapLists / SetAllInstIdToRemapId (IHWLayer.h:122-123) through the virtual interface."""
+    scn = scenes.cornell_remap_lists(64, 64)
+    lay = _make(scn, consts)
+    lay.InitPathTracing(9)
+    lay.TracingPasses(2)
+    a = lay.GetHDRImage()
+    layer.LoadScene(scn)
+    layer.InitPathTracing(9)
+    layer.TracingPass(2, 2)
+    assert a[..., :3].mean() > 0.05 and np.array_equal(a, layer.GetHDRImage())
+    lay.close()
+
+
 def test_shared_image_accumulation_like_the_reference_worker_mode(consts):
     """ContribToExternalImageAccumulator (GPUOCLLayerOther.cpp:365-430): two render processes (here: two layers with different seeds, full frame
     each) add their SUM buffers into one shared image and hand over their sample counts; the device buffer starts over afterwards."""
