@@ -338,6 +338,7 @@ void* ref_render_create(void* scene, int kind, int seed)
   RefScene* s = (RefScene*)scene;
   RefRender* r = new RefRender; r->scn = s; r->kind = kind;
   const int depth = s->G()->varsI[HRT_TRACE_DEPTH];
+  if (kind != 0) s->G()->g_flags &= ~HRT_STUPID_PT_MODE;     // a PT render on this scene object leaves the flag behind: renders must not depend on their order
   if (kind == 0)      { r->pt.reset(new Det<IntegratorStupidPT>(s->w, s->h, s->G()));        Setup(r->pt.get(), s, depth);   r->pt->Seed(seed);
                         s->G()->g_flags |= HRT_STUPID_PT_MODE; }                              // IntegratorStupidPT::DoPass, CPUExp_Integrators.h:326-330
   else if (kind == 1) { r->mis.reset(new Det<IntegratorMISPT>(s->w, s->h, s->G(), 0));       Setup(r->mis.get(), s, depth);  r->mis->Seed(seed); }
