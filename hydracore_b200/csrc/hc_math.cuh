@@ -108,14 +108,24 @@ HC_DEV HcMat4 inverse4x4(const HcMat4& a)
 // result to float, i.e. it gets (almost always) the correctly rounded float.  B200 keeps a full-rate-ish FP64 pipe, and these
 // calls are a handful per path vertex, so we evaluate them the same way: double in, double out, round once.  sqrt and
 // division are IEEE-exact in float already (default -prec-sqrt/-prec-div), min/max/abs/floor are exact in either type.
-HC_DEV float hc_sin(float x)  { return (float)sin((double)x); }
-HC_DEV float hc_cos(float x)  { return (float)cos((double)x); }
-HC_DEV float hc_tan(float x)  { return (float)tan((double)x); }
-HC_DEV float hc_exp(float x)  { return (float)exp((double)x); }
-HC_DEV float hc_log(float x)  { return (float)log((double)x); }
-HC_DEV float hc_acos(float x) { return (float)acos((double)x); }
+// double-precision libm calls of the reference's host build, by name (kept inline: called out of line the shade kernel shrinks by another
+// 20 % but C1 / C4 get 2-4 % slower; the texture fetch, hc_shade.cuh Sample2DFetch, is what pays to keep out of line)
+HC_DEV double hc_d_sin(double x)             { return sin(x); }
+HC_DEV double hc_d_cos(double x)             { return cos(x); }
+HC_DEV double hc_d_tan(double x)             { return tan(x); }
+HC_DEV double hc_d_exp(double x)             { return exp(x); }
+HC_DEV double hc_d_log(double x)             { return log(x); }
+HC_DEV double hc_d_acos(double x)            { return acos(x); }
+HC_DEV double hc_d_atan2(double y, double x) { return atan2(y, x); }
+HC_DEV double hc_d_pow(double x, double y)   { return pow(x, y); }
+HC_DEV float hc_sin(float x)  { return (float)hc_d_sin((double)x); }
+HC_DEV float hc_cos(float x)  { return (float)hc_d_cos((double)x); }
+HC_DEV float hc_tan(float x)  { return (float)hc_d_tan((double)x); }
+HC_DEV float hc_exp(float x)  { return (float)hc_d_exp((double)x); }
+HC_DEV float hc_log(float x)  { return (float)hc_d_log((double)x); }
+HC_DEV float hc_acos(float x) { return (float)hc_d_acos((double)x); }
 HC_DEV float hc_asin(float x) { return (float)asin((double)x); }
 HC_DEV float hc_atan(float x) { return (float)atan((double)x); }
-HC_DEV float hc_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
-HC_DEV float hc_pow(float x, float y)   { return (float)pow((double)x, (double)y); }
+HC_DEV float hc_atan2(float y, float x) { return (float)hc_d_atan2((double)y, (double)x); }
+HC_DEV float hc_pow(float x, float y)   { return (float)hc_d_pow((double)x, (double)y); }
 HC_DEV float hc_sqrt(float x) { return sqrtf(x); }

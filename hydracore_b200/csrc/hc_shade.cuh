@@ -171,7 +171,7 @@ HC_DEV float3 MapSampleToModifiedCosineDistribution(float r1, float r2, float3 d
   if (power >= 1e6f) return direction;        // NB: leaves `under` untouched, as the reference does
   const float sinPhi = hc_sin(2.0f*r1*3.141592654f);
   const float cosPhi = hc_cos(2.0f*r1*3.141592654f);
-  const float sinTheta = (float)sqrt(1.0 - pow(D(r2), D(2.0f/(power + 1.0f))));
+  const float sinTheta = (float)sqrt(1.0 - hc_d_pow(D(r2), D(2.0f/(power + 1.0f))));
   float3 dev;
   dev.x = sinTheta*cosPhi; dev.y = sinTheta*sinPhi;
   dev.z = sqrtf(1.0f - dev.x*dev.x - dev.y*dev.y);
@@ -206,9 +206,9 @@ HC_DEV const float* LightAt(const HcScene& s, int id)                  // lightA
 
 // sample2DExt (cfetch.h:681-713) without procedural textures (none are supported: readProcTex then returns w = -1 and the image wins).
 // samplerOffset counts float4 from the start of the material node (ReadSampler, cfetch.h:588-612).
-HC_DEV float3 Sample2D(int samplerOffset, float2 tc, const float* mat, const HcScene& s)
+// the fetch itself is out of line: 17 call sites would otherwise each inline the bilinear / sRGB code (untextured slots return early, inline)
+static __device__ __noinline__ float3 Sample2DFetch(int samplerOffset, float2 tc, const float* mat, const int4* __restrict__ textures, const int* __restrict__ texTable)
 {
-  if (samplerOffset == HC_INVALID_TEXTURE || samplerOffset < 0) return f3(1, 1, 1);
   const int4*   mi = reinterpret_cast<const int4*>(mat);
   const float4* mf = reinterpret_cast<const float4*>(mat);
   const int4 header = mi[samplerOffset];
@@ -216,10 +216,15 @@ HC_DEV float3 Sample2D(int samplerOffset, float2 tc, const float* mat, const HcS
   if (texId <= 0) return f3(1, 1, 1);
   const float4 row0 = mf[samplerOffset + 1], row1 = mf[samplerOffset + 2];
   const float2 tct = f2(row0.x*tc.x + row0.y*tc.y + row0.w, row1.x*tc.x + row1.y*tc.y + row1.w);     // mul2x4, cfetch.h:640-646
-  const int offset = s.globals[s.texturesTableOffset + texId];
-  float4 c = (offset >= 0) ? ReadImageSw4(s.textures + offset, tct, flags, (gamma != 1.0f)) : make_float4(1, 1, 1, 1);
+  const int offset = texTable[texId];
+  float4 c = (offset >= 0) ? ReadImageSw4(textures + offset, tct, flags, (gamma != 1.0f)) : make_float4(1, 1, 1, 1);
   if (flags & HC_TEX_ALPHASRC_W) { c.x = c.w; c.y = c.w; c.z = c.w; }
   return f3(c.x, c.y, c.z);
+}
+HC_DEV float3 Sample2D(int samplerOffset, float2 tc, const float* mat, const HcScene& s)
+{
+  if (samplerOffset == HC_INVALID_TEXTURE || samplerOffset < 0) return f3(1, 1, 1);
+  return Sample2DFetch(samplerOffset, tc, mat, s.textures, s.globals + s.texturesTableOffset);
 }
 
 // remapMaterialId (cglobals.h:2931-2983): per-instance material override, binary search for the first "from" id >= matId in the instance's list.
@@ -462,9 +467,9 @@ HC_DEV void ThinglassSample(const float* m, float r1, float r2, float3 rayDir, f
     const float3 oldDir = rayDir;
     rayDir = MapSampleToModifiedCosineDistribution(r1, r2, rayDir, (-1.0f)*n, cosPower, under);
     const float cosTheta = clampf(dot(oldDir, rayDir), 0.0f, (float)(HC_M_PI_D*D(0.499995f)));
-    fVal = (float)(D((cosPower + 2.0f)*HC_INV_TWOPI)*pow(D(cosTheta), D(cosPower)));
+    fVal = (float)(D((cosPower + 2.0f)*HC_INV_TWOPI)*hc_d_pow(D(cosTheta), D(cosPower)));
     if (under) fVal = 0.0f;
-    pdf = (float)(pow(D(cosTheta), D(cosPower))*D(cosPower + 1.0f)*D(0.5f*HC_INV_PI));
+    pdf = (float)(hc_d_pow(D(cosTheta), D(cosPower))*D(cosPower + 1.0f)*D(0.5f*HC_INV_PI));
   }
   const float cosThetaOut = dot(rayDir, n);
   const float cosMult = 1.0f/fmaxf(fabsf(cosThetaOut), 1e-6f);
@@ -497,7 +502,7 @@ HC_DEV float PhongEvalPDF(const float* m, float3 l, float3 v, float3 n, float2 t
   const float cosPower = cosPowerFromGlosiness(Glosiness(m, tc, s));
   const float3 r = reflect3((-1.0f)*v, n);
   const float cosTheta = clampf(fabsf(dot(l, r)), 0.0f, 1.0f);
-  return (float)(pow(D(cosTheta), D(cosPower))*D(cosPower + 1.0f)*D(HC_INV_TWOPI));
+  return (float)(hc_d_pow(D(cosTheta), D(cosPower))*D(cosPower + 1.0f)*D(HC_INV_TWOPI));
 }
 HC_DEV float3 PhongEvalBxDF(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
 {
@@ -525,7 +530,7 @@ HC_DEV void PhongSample(const float* m, float r1, float r2, float3 rayDir, float
   else
   {
     const float cosAlpha = clampf(dot(newDir, r), 0.0f, 1.0f);
-    const float eqTemp = (float)(pow(D(cosAlpha), D(cosPower))*D(HC_INV_TWOPI));
+    const float eqTemp = (float)(hc_d_pow(D(cosAlpha), D(cosPower))*D(HC_INV_TWOPI));
     const bool fix = (MatI(m, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER) != 0;
     const float energyFix = fix ? PhongEnergyFix(cosAlpha, newDir, n) : 1.0f;
     out.pdf = eqTemp*(cosPower + 1.0f);
@@ -567,7 +572,7 @@ HC_DEV float BlinnEvalPDF(const float* m, float3 l, float3 v, float3 n, float2 t
   const float exponent = cosPowerFromGlosiness(Glosiness(m, tc, s));
   const float3 wh = normalize(l + v);
   const float costheta = fabsf(dot(wh, n));
-  return (float)((D(exponent + 1.0f)*pow(D(costheta), D(exponent)))/D(HC_M_TWOPI*4.0f*dot(l, wh)));
+  return (float)((D(exponent + 1.0f)*hc_d_pow(D(costheta), D(exponent)))/D(HC_M_TWOPI*4.0f*dot(l, wh)));
 }
 HC_DEV float3 BlinnEvalBxDF(const float* m, float3 l, float3 v, float3 n, float2 tc, const HcScene& s)
 {
@@ -577,7 +582,7 @@ HC_DEV float3 BlinnEvalBxDF(const float* m, float3 l, float3 v, float3 n, float2
   const float exponent = cosPowerFromGlosiness(Glosiness(m, tc, s));
   const float3 wh = normalize(l + v);
   const float cosThetaH = fabsf(dot(wh, n));
-  const float Dh = (float)(D((exponent + 2.0f)*HC_INV_TWOPI)*pow(D(cosThetaH), D(exponent)));
+  const float Dh = (float)(D((exponent + 2.0f)*HC_INV_TWOPI)*hc_d_pow(D(cosThetaH), D(exponent)));
   return color*Dh*TorranceSparrowGF2(l, v, n);
 }
 HC_DEV void BlinnSample(const float* m, float r1, float r2, float3 rayDir, float3 n, float2 tc, const HcScene& s, HcMatSample& out)
@@ -592,16 +597,16 @@ HC_DEV void BlinnSample(const float* m, float r1, float r2, float3 rayDir, float
   const float costheta = hc_pow(r1, 1.0f/(exponent + 1.0f));
   const float sintheta = sqrtf(fmaxf(0.0f, 1.0f - costheta*costheta));
   const float phi = r2*HC_M_TWOPI;
-  const float3 wh = f3((float)(D(sintheta)*cos(D(phi))), (float)(D(sintheta)*sin(D(phi))), costheta);
+  const float3 wh = f3((float)(D(sintheta)*hc_d_cos(D(phi))), (float)(D(sintheta)*hc_d_sin(D(phi))), costheta);
   const float3 wi = (2.0f*dot(wo, wh)*wh) - wo;
   const float3 newDir = normalize(wi.x*nx + wi.y*ny + wi.z*nz);
   const float3 v = rayDir*(-1.0f), l = newDir;
   if (dot(n, v) < 1e-6f || dot(n, l) < 1e-6f) { out.color = f3(0, 0, 0); out.pdf = 1.0f; }
   else
   {
-    const float Dh = (float)(D((exponent + 2.0f)*HC_INV_TWOPI)*pow(D(costheta), D(exponent)));
+    const float Dh = (float)(D((exponent + 2.0f)*HC_INV_TWOPI)*hc_d_pow(D(costheta), D(exponent)));
     out.color = color*Dh*TorranceSparrowGF1(wo, wi);
-    out.pdf = (float)((D(exponent + 1.0f)*pow(D(costheta), D(exponent)))/D(fmaxf(HC_M_TWOPI*4.0f*dot(wo, wh), HC_DEPSILON)));
+    out.pdf = (float)((D(exponent + 1.0f)*hc_d_pow(D(costheta), D(exponent)))/D(fmaxf(HC_M_TWOPI*4.0f*dot(wo, wh), HC_DEPSILON)));
   }
   out.direction = newDir;
   out.flags = (gloss >= 0.99f) ? HC_RAY_EVENT_S : HC_RAY_EVENT_G;
@@ -635,8 +640,8 @@ HC_DEV float3 GgxVndf(float3 wo, float roughness, float u1, float u2)
   const float a = 1.0f/(1.0f + v.z);
   const float r = sqrtf(u1);
   const float phi = (u2 < a) ? (float)(D(u2/a)*HC_PI_D) : (float)(HC_PI_D + D((u2 - a)/(1.0f - a))*HC_PI_D);
-  const float p1 = (float)(D(r)*cos(D(phi)));
-  const float p2 = (float)(D(r)*sin(D(phi))*D((u2 < a) ? 1.0f : v.z));
+  const float p1 = (float)(D(r)*hc_d_cos(D(phi)));
+  const float p2 = (float)(D(r)*hc_d_sin(D(phi))*D((u2 < a) ? 1.0f : v.z));
   const float3 n = p1*t1 + p2*t2 + sqrtf(fmaxf(0.0f, 1.0f - p1*p1 - p2*p2))*v;
   return normalize(f3(roughness*n.x, roughness*n.y, fmaxf(0.0f, n.z)));
 }
@@ -810,7 +815,7 @@ HC_DEV float BlendMaskAlpha(const float* m, float3 v, float3 n, float2 tc, const
   if (MatI(m, HC_BLEND_TYPE) == HC_BLEND_SIGMOID)
   {
     const float x2 = -5.0f + 10.0f*lum;                                                     // maxSigmoid, cmaterial.h:2026-2030
-    lum = (float)(D(1.04f)/(D(1.0f) + exp(D(-m[HC_BLEND_SIGMOID_EXP]*x2))) - D(0.02f));
+    lum = (float)(D(1.04f)/(D(1.0f) + hc_d_exp(D(-m[HC_BLEND_SIGMOID_EXP]*x2))) - D(0.02f));
   }
   if (bflags & HC_BLEND_MASK_FRESNEL)
     return clampf(lum*fresnelReflectionCoeff(fabsf(normAngle), 1.0f, m[HC_BLEND_MASK_FRESNEL_IOR]), 0.0f, 1.0f);
@@ -1118,10 +1123,10 @@ HC_DEV float SphereLightEvalPDF(const float* L, float3 illum, float3 lpos, float
 HC_DEV void SphereLightSampleRev(const float* L, float3 rands, float3 illum, HcShadowSample& out)                          // clight.h:1309-1333
 {
   const float theta = (float)(2.0*3.14159265358979323846*(double)rands.x);
-  const float phi   = (float)acos((double)(1.0f - 2.0f*rands.y));
-  const float x = (float)(sin((double)phi)*cos((double)theta));
-  const float y = (float)(sin((double)phi)*sin((double)theta));
-  const float z = (float)cos((double)phi);
+  const float phi   = (float)hc_d_acos((double)(1.0f - 2.0f*rands.y));
+  const float x = (float)(hc_d_sin((double)phi)*hc_d_cos((double)theta));
+  const float y = (float)(hc_d_sin((double)phi)*hc_d_sin((double)theta));
+  const float z = (float)hc_d_cos((double)phi);
   const float3 lcenter = Mat3(L, HC_PLIGHT_POS_X);
   const float lradius = L[HC_SPHERE_LIGHT_RADIUS];
   const float3 samplePos = lcenter + lradius*f3(x, y, z);
@@ -1169,8 +1174,8 @@ HC_DEV float3 TexCoord2DToSphereMap(float2 tc, float& sinThetaOut)              
   const float phi   = (float)((double)(tc.x*2.0f)*HC_M_PI_D);
   const float theta = (float)((double)tc.y*HC_M_PI_D);
   const float sinTheta = hc_sin(theta);
-  const float x = (float)((double)sinTheta*cos((double)phi));
-  const float y = (float)((double)sinTheta*sin((double)phi));
+  const float x = (float)((double)sinTheta*hc_d_cos((double)phi));
+  const float y = (float)((double)sinTheta*hc_d_sin((double)phi));
   const float z = hc_cos(theta);
   sinThetaOut = sinTheta;
   return f3(y, -z, x);
@@ -1298,8 +1303,8 @@ HC_DEV float3 MapSamplesToCone(float cosCutoff, float sx, float sy, float3 direc
 {
   const float cosTheta = (1.0f - sx) + sx*cosCutoff;
   const float sinTheta = sqrtf(1.0f - cosTheta*cosTheta);
-  const float sinPhi = (float)sin(2.0*HC_M_PI_D*(double)sy);                                 // 2.0f*M_PI*sample.y with the <cmath> double M_PI
-  const float cosPhi = (float)cos(2.0*HC_M_PI_D*(double)sy);
+  const float sinPhi = (float)hc_d_sin(2.0*HC_M_PI_D*(double)sy);                                 // 2.0f*M_PI*sample.y with the <cmath> double M_PI
+  const float cosPhi = (float)hc_d_cos(2.0*HC_M_PI_D*(double)sy);
   const float3 dev = f3(cosPhi*sinTheta, sinPhi*sinTheta, cosTheta);
   float3 nx, nzT;
   CoordinateSystem(direction, nx, nzT);
