@@ -480,8 +480,19 @@ static int SetBvhTree(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, 
   if (treeId == 1)
   {
     ctx->haveAlpha1 = false;
+    ctx->alphaTexIdsHost.clear();
     if (alphaTable)
     {
+      // every triangle's sampler offset must point at a whole SWTexSampler (6 uint2) inside the table; remember the texture ids for hc_pt_init
+      const unsigned* au = (const unsigned*)alphaTable;
+      for (size_t k = 0; k + 3 < devAlpha.size(); k += 4)
+      {
+        const unsigned off = devAlpha[k];
+        if (off == 0xFFFFFFFFu || (int)off <= 0) continue;
+        HC_REQUIRE((long long)off + 6 <= (long long)alphaNum, HC_E_RANGE, "hc_set_bvh_alpha: an opacity sampler offset points outside the alpha table");
+        const int texId = (int)au[2*(size_t(off) + 1)];
+        if (std::find(ctx->alphaTexIdsHost.begin(), ctx->alphaTexIdsHost.end(), texId) == ctx->alphaTexIdsHost.end()) ctx->alphaTexIdsHost.push_back(texId);
+      }
       rc = hc_buf_reserve(ctx, ctx->bvh1AlphaPairs, std::max<size_t>(devAlpha.size()*4, 16)); if (rc) return rc;
       rc = hc_buf_reserve(ctx, ctx->bvh1AlphaTable, size_t(alphaNum)*8); if (rc) return rc;
       if (!devAlpha.empty()) HC_CUDA(cudaMemcpyAsync(ctx->bvh1AlphaPairs.ptr, devAlpha.data(), devAlpha.size()*4, cudaMemcpyHostToDevice, ctx->stream));
@@ -490,6 +501,7 @@ static int SetBvhTree(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, 
     }
   }
   HC_CUDA(cudaStreamSynchronize(ctx->stream));                // ConvertionResult pointers die at ConvertUnmap (RenderDriverRTE.cpp:1436)
+  if (treeId == 0) ctx->alphaTexIdsHost.clear();
   if (treeId == 0) { ctx->nodesNum = nodesNum; ctx->trif4Num = trif4Num; ctx->haveInst = haveInst; ctx->bvhDepthBound = bound; ctx->haveTree1 = false; ctx->haveAlpha1 = false; }
   else ctx->haveTree1 = true;
   return HC_OK;
@@ -505,7 +517,10 @@ int hc_set_bvh_alpha(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, c
 int hc_set_remap_lists(hc_ctx* ctx, const int32_t* allLists, const int32_t* tableOffsetAndSize, int allSize, int tableSize)
 {
   if (!ctx) return HC_E_ARG;
-  if (!allLists || !tableOffsetAndSize || allSize <= 0 || tableSize <= 0) { ctx->remapListsSize = 0; ctx->remapTableSize = 0; return HC_OK; }   // GPUOCLData.cpp:203-210
+  if (!allLists || !tableOffsetAndSize || allSize <= 0 || tableSize <= 0) { ctx->remapListsSize = 0; ctx->remapTableSize = 0; ctx->remapListsHost.clear(); return HC_OK; }   // GPUOCLData.cpp:203-210
+  for (int i = 0; i < tableSize; i++)
+    HC_REQUIRE(tableOffsetAndSize[2*i] >= 0 && tableOffsetAndSize[2*i + 1] >= 0 && (long long)tableOffsetAndSize[2*i] + tableOffsetAndSize[2*i + 1] <= allSize, HC_E_RANGE,
+               "hc_set_remap_lists: a remap list lies outside the array of all lists");
   HC_CUDA(cudaSetDevice(ctx->device));
   int rc = hc_buf_reserve(ctx, ctx->remapLists, size_t(allSize)*4); if (rc) return rc;
   rc = hc_buf_reserve(ctx, ctx->remapTable, size_t(tableSize)*8); if (rc) return rc;
@@ -513,6 +528,7 @@ int hc_set_remap_lists(hc_ctx* ctx, const int32_t* allLists, const int32_t* tabl
   HC_CUDA(cudaMemcpyAsync(ctx->remapTable.ptr, tableOffsetAndSize, size_t(tableSize)*8, cudaMemcpyHostToDevice, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->remapListsSize = allSize; ctx->remapTableSize = tableSize;
+  ctx->remapListsHost.assign(allLists, allLists + allSize);
   return HC_OK;
 }
 int hc_set_inst_remap_ids(hc_ctx* ctx, const int32_t* instRemapListId, int n)

@@ -40,6 +40,8 @@ struct hc_ctx
   bool     haveTree1 = false, haveAlpha1 = false;
   HcDevBuf remapLists, remapTable, remapInst;   // material remap lists (SetAllRemapLists / SetAllInstIdToRemapId)
   int      remapListsSize = 0, remapTableSize = 0, remapInstSize = 0;
+  std::vector<int> remapListsHost;              // host copy for validation at hc_pt_init (every 'to' id must exist in the materials table)
+  std::vector<int> alphaTexIdsHost;             // texture ids used by the opacity samplers of tree 1, validated against the texture table
   int      nodesNum = 0, trif4Num = 0, haveInst = 1, bvhDepthBound = 0;
   HcDevBuf instMatrices, instLightIds;
   int      numInst = 0;

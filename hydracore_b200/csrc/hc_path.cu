@@ -491,6 +491,24 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
     if (tex != HC_INVALID_TEXTURE) { why = "textured area lights are not supported yet"; return HC_E_ARG; }
     if (spot != 0) { why = "area lights with a spot distribution are not supported yet"; return HC_E_ARG; }
   }
+  {
+    // remap lists: every target material id must exist; opacity samplers of the alpha-tested tree: every texture id must have an image
+    const int matTabSize0 = gi(HC_EG_materialsTableSize);
+    for (size_t k = 1; k < ctx->remapListsHost.size() && ctx->remapListsSize > 0; k += 2)
+      if (ctx->remapListsHost[k] < 0 || ctx->remapListsHost[k] >= matTabSize0) { why = "a material remap list maps to material id " + std::to_string(ctx->remapListsHost[k]) + ", which is not in the materials table"; return HC_E_RANGE; }
+    if (ctx->haveAlpha1)
+    {
+      if (!ctx->storage[HC_STORAGE_TEXTURES].ptr) { why = "opacity maps need the textures storage"; return HC_E_STATE; }
+      const int texTabOff = gi(HC_EG_texturesTableOffset), texTabSize = gi(HC_EG_texturesTableSize);
+      for (int texId : ctx->alphaTexIdsHost)
+      {
+        if (texId == 0) continue;
+        int off = -1;
+        if (texId > 0 && texId < texTabSize) memcpy(&off, gl.data() + 4*size_t(texTabOff + texId), 4);
+        if (off < 0) { why = "an opacity sampler of the alpha-tested tree uses texture id " + std::to_string(texId) + ", which has no image in the textures storage"; return HC_E_RANGE; }
+      }
+    }
+  }
   // walk the material nodes REACHABLE from the materials table (the storage may hold stale or unused chunks after in-place updates)
   const size_t nNodes = p->materialsHost.size()/(HC_PLAIN_MATERIAL_DATA_SIZE*4);
   const int matTabOff = gi(HC_EG_materialsTableOffset), matTabSize = gi(HC_EG_materialsTableSize);
