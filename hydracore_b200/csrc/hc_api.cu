@@ -46,10 +46,15 @@ void hc_buf_free(HcDevBuf& b) { if (b.ptr) cudaFree(b.ptr); b.ptr = nullptr; b.b
 // ALPHA (closest hit only): the second, alpha-tested tree of the reference (BVH4InstTraverseAlpha after BVH4InstTraverse in
 // IntegratorCommon::rayTrace, CPUExp_Integrators_Common.cpp:122-150): starts from the hit tree 0 left in hitsOut and keeps it unless a closer
 // triangle passes the opacity lookup.
-template<bool ANYHIT, int TREE1 = 0>      // TREE1: 0 = first tree, 1 = second tree (hit carried), 2 = second tree with the alpha table
+// RAYGEN (ray-casting pass only): 0 = rays come from memory; 1 = the primary eye ray of pixel idx is generated in the fetch (K1 fused into K2:
+// MakeRandEyeRay with zero offsets, the arithmetic of k_make_eye_rays); 2 = the shadow ray towards `light` is generated from the regenerated eye
+// ray and the hit record hitsIn[idx] (k_make_shadow_rays fused into K2s).  Saves two launches and 2 x 64 B per pixel of ray traffic.
+struct HcRayGen { HcCamera cam; int width, height; long long firstPixel; float3 light; const HcHit* hitsIn; };
+template<bool ANYHIT, int TREE1 = 0, int RAYGEN = 0>      // TREE1: 0 = first tree, 1 = second tree (hit carried), 2 = second tree with the alpha table
 __global__ void __launch_bounds__(HC_TRACE_BLOCK, 6)   // 80 registers -> 6 CTAs (24 warps) per SM; capping at 72 / 64 registers for 7 / 8 CTAs measured slower
 k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long nArg,
-        const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter, const int refillMin, const int tileW)
+        const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter, const int refillMin, const int tileW,
+        const HcRayGen gen = HcRayGen())
 {
   const long long n = nDev ? (long long)(*nDev) : nArg;      // the path tracer keeps its live-path count on the device
   uint2 stk[HC_STACK_CAP];                                    // {child word, entry distance}
@@ -85,7 +90,29 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
             const long long blk = idx >> 5; const int w = int(idx) & 31, bpr = tileW >> 3;
             idx = ((blk/bpr)*4 + (w >> 3))*(long long)tileW + (blk % bpr)*8 + (w & 7);
           }
-          const float4 p = __ldg(rpos + idx*stride), dd = __ldg(rdir + idx*stride);
+          float4 p, dd;
+          if (RAYGEN == 0) { p = __ldg(rpos + idx*stride); dd = __ldg(rdir + idx*stride); }
+          else
+          {
+            const long long pix = idx + gen.firstPixel;                  // launches may cover a band of the image
+            float3 eo, ed;
+            MakeRandEyeRay(int(pix % gen.width), int(pix / gen.width), gen.width, gen.height, make_float4(0.0f, 0.0f, 0.0f, 0.0f), gen.cam, eo, ed);
+            p = make_float4(eo.x, eo.y, eo.z, 0.0f); dd = make_float4(ed.x, ed.y, ed.z, HC_MAXFLOAT_RAY);
+            if (RAYGEN == 2)
+            {
+              const HcHit h = gen.hitsIn[pix];
+              p = make_float4(0, 0, 0, 0); dd = make_float4(0, 1, 0, 0);             // t_far = 0: "no shadow ray" for pixels that hit nothing
+              if (h.primId != -1)
+              {
+                const float3 pos = eo + ed*h.t;
+                const float3 sdir = normalize(gen.light - pos);
+                const float eps = fmaxf(fmaxf(fabsf(pos.x), fmaxf(fabsf(pos.y), fabsf(pos.z))), 1.0f)*1e-4f;
+                const float3 spos = pos + sdir*eps;
+                p = make_float4(spos.x, spos.y, spos.z, 0.0f);
+                dd = make_float4(sdir.x, sdir.y, sdir.z, length(spos - gen.light)*0.995f);
+              }
+            }
+          }
           rayIdx = idx; idle = false;
           TravStart(r, bvh, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
           if (TREE1 != 0)
@@ -220,6 +247,25 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
     ctx->stats.kernelLaunches++;
   }
   if (!nDev) { if (anyHit) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n; }   // counted launches: hc_pt_pass reads the live counts back
+  return HC_OK;
+}
+
+// ray-casting pass: K2 / K2s with the eye / shadow rays generated in the fetch (RAYGEN 1 / 2); first tree only (the caller falls back to rays in
+// memory when a second tree is present)
+static int LaunchTraceGen(hc_ctx* ctx, bool shadow, long long n, HcHit* hitsLocal, unsigned char* vis, int tileW, const HcRayGen& gen)
+{
+  if (n <= 0) return HC_OK;
+  cudaStream_t stream = ctx->stream;
+  HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr;
+  ctx->traceCounterSlot = (ctx->traceCounterSlot + 1) % 32;
+  unsigned long long* counter = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
+  HC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+  const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
+  if (shadow) k_trace<true, 0, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, nullptr, vis, counter, HC_REFILL_MIN, tileW, gen);
+  else        k_trace<false, 0, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, hitsLocal, nullptr, counter, HC_REFILL_MIN, tileW, gen);
+  HC_CUDA(cudaGetLastError());
+  ctx->stats.kernelLaunches++;
+  if (shadow) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n;
   return HC_OK;
 }
 
@@ -675,9 +721,18 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
   const HcCamera cam = hc_camera_from_globals(ctx->globalsHead.data());
   const int block = 256; const int grid = int((n + block - 1)/block);
 
+  // eye rays and shadow rays are generated inside the traversal kernels' ray fetch (no ray buffers, two launches fewer) unless a second BVH
+  // tree has to be walked with the same rays
+  const bool fused = !ctx->haveTree1 && ctx->bvhNodes.ptr && ctx->bvhTris.ptr && ctx->haveInst != 0 && getenv("HC_RAYCAST_UNFUSED") == nullptr;
+  HcRayGen gen; gen.cam = cam; gen.width = ctx->width; gen.height = ctx->height; gen.firstPixel = 0;
+  gen.light = make_float3(lightPos[0], lightPos[1], lightPos[2]); gen.hitsIn = hits;
   HC_CUDA(cudaEventRecord(ctx->evStage[0], ctx->stream));
-  k_make_eye_rays<<<grid, block, 0, ctx->stream>>>(cam, ctx->width, ctx->height, nullptr, rays);
-  HC_CUDA(cudaGetLastError());
+  if (!fused)
+  {
+    k_make_eye_rays<<<grid, block, 0, ctx->stream>>>(cam, ctx->width, ctx->height, nullptr, rays);
+    HC_CUDA(cudaGetLastError());
+    ctx->stats.kernelLaunches++;
+  }
   HC_CUDA(cudaEventRecord(ctx->evStage[1], ctx->stream));
   const int tileW = (ctx->width % 8 == 0 && ctx->height % 4 == 0) ? ctx->width : 0;                 // rays fetched in 8 x 4 pixel blocks per warp
   // With HOST outputs the closest-hit pass runs in two horizontal bands, so that the read-back of the first band's hit records (16 B per ray,
@@ -690,7 +745,9 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
   {
     const long long r0 = (long long)(rowGroups*b/bands)*4, r1 = std::min<long long>((long long)(rowGroups*(b + 1)/bands)*4, ctx->height);
     const long long i0 = r0*ctx->width, nb = (r1 - r0)*ctx->width;
-    if ((rc = LaunchTrace(ctx, false, rays + 2*i0, rays + 2*i0 + 1, 2, nb, nullptr, hits + i0, nullptr, tileW))) return rc;
+    gen.firstPixel = i0;
+    if (fused) { if ((rc = LaunchTraceGen(ctx, false, nb, hits + i0, nullptr, tileW, gen))) return rc; }
+    else if ((rc = LaunchTrace(ctx, false, rays + 2*i0, rays + 2*i0 + 1, 2, nb, nullptr, hits + i0, nullptr, tileW))) return rc;
     if (hitsOutOrNull)
     {
       HC_CUDA(cudaEventRecord(ctx->evCopy, ctx->stream));
@@ -699,13 +756,18 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
     }
   }
   HC_CUDA(cudaEventRecord(ctx->evStage[2], ctx->stream));
-  k_make_shadow_rays<<<grid, block, 0, ctx->stream>>>(rays, hits, n, make_float3(lightPos[0], lightPos[1], lightPos[2]), srays);
-  HC_CUDA(cudaGetLastError());
+  if (!fused)
+  {
+    k_make_shadow_rays<<<grid, block, 0, ctx->stream>>>(rays, hits, n, make_float3(lightPos[0], lightPos[1], lightPos[2]), srays);
+    HC_CUDA(cudaGetLastError());
+    ctx->stats.kernelLaunches++;
+  }
   HC_CUDA(cudaEventRecord(ctx->evStage[3], ctx->stream));
-  if ((rc = LaunchTrace(ctx, true, srays, srays + 1, 2, n, nullptr, nullptr, vis, tileW))) return rc;
+  gen.firstPixel = 0;
+  if (fused) { if ((rc = LaunchTraceGen(ctx, true, n, nullptr, vis, tileW, gen))) return rc; }
+  else if ((rc = LaunchTrace(ctx, true, srays, srays + 1, 2, n, nullptr, nullptr, vis, tileW))) return rc;
   if (visibleOutOrNull) HC_CUDA(cudaMemcpyAsync(visibleOutOrNull, vis, uint64_t(n), kind, ctx->stream));      // 1 byte per ray: not worth a band
   HC_CUDA(cudaEventRecord(ctx->evStage[4], ctx->stream));
-  ctx->stats.kernelLaunches += 2;
   ctx->stats.paths += (uint64_t)n;
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   if (hitsOutOrNull) HC_CUDA(cudaStreamSynchronize(ctx->copyStream));
