@@ -1,6 +1,7 @@
 """Summarise gpurun_out/<tag>_prof.ncu-rep + <tag>_launches.csv into profiles/ (tracked):
    python scripts/summarize_ncu.py r01a [round-label]"""
 import csv
+import re
 import io
 import json
 import os
@@ -32,7 +33,9 @@ for r in rows[2:]:
     for k in KEYS:
         if k in d:
             out.append(f"| {k} | {d[k]} | {units[hdr.index(k)]} |")
-    if any(t in name for t in ("k_trace<0>", "k_trace<(bool)0>", "k_trace<0, 0>", "k_trace<(bool)0, (int)0>")):
+    m_ = re.search(r"k_trace<(?:\(bool\))?(\d)(?:, (?:\(int\))?(\d))?(?:, (?:\(int\))?(\d))?>", name)      # <ANYHIT, TREE1, RAYGEN>
+    any_hit, tree1 = (int(m_.group(1)), int(m_.group(2) or 0)) if m_ else (-1, -1)
+    if any_hit == 0 and tree1 == 0:
         traffic["k_trace_closest_dram_bytes_per_launch"] = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"]))*1e6
         traffic["k_trace_closest_ms_under_ncu"] = float(d["gpu__time_duration.sum"])
         traffic["issue_active_pct"] = float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"])
@@ -42,7 +45,7 @@ for r in rows[2:]:
         traffic["l2_hit_pct"] = float(d["lts__t_sector_hit_rate.pct"])
         traffic["l2_to_l1_bytes_per_launch"] = float(d["lts__t_sectors_srcunit_tex_op_read.sum"])*32.0
         traffic["l1_load_bytes_per_launch"] = float(d["l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"])*32.0
-    if any(t in name for t in ("k_trace<1>", "k_trace<(bool)1>", "k_trace<1, 0>", "k_trace<(bool)1, (int)0>")):
+    if any_hit == 1:
         traffic["k_trace_shadow_dram_bytes_per_launch"] = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"]))*1e6
 shade = os.path.join(ROOT, "gpurun_out", f"{tag}_shade.ncu-rep")
 if os.path.exists(shade):
