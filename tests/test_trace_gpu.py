@@ -141,3 +141,32 @@ def test_raycast_pass_vs_oracle(layer, oracle):
     same = hits["primId"] == want["primId"]
     assert ((vis != vo) & same).sum() <= 1e-4*n
     assert 0.05 < vis[hits["primId"] >= 0].mean() < 0.999
+
+
+def test_raycast_pass_fused_equals_unfused_and_two_trees(layer):
+    """The eye / shadow rays generated inside the traversal kernels' fetch give exactly the records of the path through ray buffers
+    (HC_RAYCAST_UNFUSED=1); with a second (alpha-tested) BVH tree the pass walks both trees and equals hc_trace_closest on the same eye rays."""
+    import os
+    from hydracore_b200._lib import HC_HOST
+    scn = scenes.instanced_geometry(320, 240, dof=False)
+    layer.LoadScene(scn)
+    n = 320*240
+    dt = layer.TraceClosest(np.zeros((0, 8), np.float32)).dtype
+    out = {}
+    for mode in ("fused", "unfused"):
+        if mode == "unfused":
+            os.environ["HC_RAYCAST_UNFUSED"] = "1"
+        try:
+            h, v = np.empty(n, dt), np.empty(n, np.uint8)
+            layer.RaycastPass((3.0, 12.0, 5.0), h.ctypes.data, v.ctypes.data, HC_HOST)
+            out[mode] = (h, v)
+        finally:
+            os.environ.pop("HC_RAYCAST_UNFUSED", None)
+    assert out["fused"][0].tobytes() == out["unfused"][0].tobytes() and np.array_equal(out["fused"][1], out["unfused"][1])
+    cut = scenes.cornell_with_cutout(96, 96)
+    layer.LoadScene(cut)
+    h, v = np.empty(96*96, dt), np.empty(96*96, np.uint8)
+    layer.RaycastPass((0.0, 3.0, 0.0), h.ctypes.data, v.ctypes.data, HC_HOST)
+    want = layer.TraceClosest(layer.MakeEyeRays(96, 96, None))
+    assert h.tobytes() == want.tobytes()
+    assert set(np.unique(h["instId"])) >= {0, 1, 3}                 # hits in both trees (instances 1, 3, 4 live in the alpha-tested tree)
