@@ -62,7 +62,7 @@ struct hc_ctx
   int      seed = 0;
   bool     ptReady = false;
   int      tileSize = 32, rank = 0, worldSize = 1;
-  int      materialSort = 1, sortFromBounce = 1;   // K6b: sort the live-path queue by material before shading, from this bounce on
+  int      materialSort = 2 /* 0 off, 1 on, 2 auto: on for >= 3 materials and >= 384k paths per pass */, sortFromBounce = 1;   // K6b: sort the live-path queue by material before shading, from this bounce on
   HcDevBuf pixelRng;                       // uint2 per pixel: generator state carried across passes (trace.cl:6-13)
   HcDevBuf qmcTable;                       // Niederreiter table, 11 x 31 uint (qmc_sobol_niederreiter.cpp:179-186)
   unsigned passCounter = 0;

@@ -698,7 +698,10 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
     int matTab; memcpy(&matTab, ctx->globalsHead.data() + HC_EG_materialsTableSize, 4);
     // measured on B200 (scripts/gpu_sort_ab.py): C3 (6 materials) 7.66 -> 7.26 ms per 1080p pass, shade 2.02 -> 1.41 ms, sort 0.29 ms;
     // C4 (one surface material + the light's) 6.54 -> 6.59 ms.  Hence: only when there are at least three materials to tell apart.
-    if (matTab >= 3 && matTab + 1 <= HC_SORT_MAX_KEYS) sortKeys = matTab + 1;
+    // ... and, unless asked for explicitly, only when the queue is long enough for the three extra launches per bounce to pay
+    // (scripts/gpu_sort_small.py, ms per pass with / without: C1 262k paths 0.636 / 0.616, C3 130k 1.320 / 1.269, 518k 2.542 / 2.602, 2.07M 6.66 / 7.26)
+    const bool longEnough = (ctx->materialSort == 1) || n >= 384*1024;
+    if (matTab >= 3 && matTab + 1 <= HC_SORT_MAX_KEYS && longEnough) sortKeys = matTab + 1;
   }
 
   // stage timing: one {start, stop} event pair per launch, summed per kernel class after the final synchronise (feeds MRaysStat /
@@ -918,7 +921,7 @@ int hc_fb_read_ldr(hc_ctx* ctx, uint32_t* outRGBA8, int width, int height)
 int hc_pt_set_material_sort(hc_ctx* ctx, int enable, int fromBounce)
 {
   if (!ctx || fromBounce < 0) return HC_E_ARG;
-  ctx->materialSort = enable ? 1 : 0; ctx->sortFromBounce = fromBounce;
+  ctx->materialSort = (enable == 2) ? 2 : (enable ? 1 : 0); ctx->sortFromBounce = fromBounce;
   return HC_OK;
 }
 

@@ -219,7 +219,9 @@ class CudaLayer:
         check(self._L.hc_pt_set_tiles(self._c, int(tile), int(rank), int(world)), "hc_pt_set_tiles")
 
     def SetMaterialSort(self, enable=True, from_bounce=1):
-        check(self._L.hc_pt_set_material_sort(self._c, 1 if enable else 0, int(from_bounce)), "hc_pt_set_material_sort")
+        """enable: False / 0 = off, True / 1 = on, "auto" / 2 = the default (on with >= 3 materials and >= 384k paths per pass)."""
+        mode = 2 if enable in ("auto", 2) else (1 if enable else 0)
+        check(self._L.hc_pt_set_material_sort(self._c, mode, int(from_bounce)), "hc_pt_set_material_sort")
 
     def TracingPass(self, integrator=INTEGRATOR_MISPT, passes=1):
         """BeginTracingPass + EndTracingPass, `passes` times."""

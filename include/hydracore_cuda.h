@@ -113,7 +113,8 @@ int hc_measure_read_bandwidth(hc_ctx* ctx, uint64_t bytes, int repeats, float* o
 int hc_pt_init(hc_ctx* ctx, int seed);                                       /* InitPathTracing, IHWLayer.h:139 ; InitRandomGen, trace.cl:6 */
 int hc_pt_set_tiles(hc_ctx* ctx, int tileSize, int rank, int worldSize);     /* interleaved tile ownership for multi-GPU        */
 int hc_pt_set_material_sort(hc_ctx* ctx, int enable, int fromBounce);       /* material sort of the live-path queue before shading: replaces
-                                                                                 bitonic_sort_gpu (bitonic_sort_gpu.cpp:90-158); default on, from bounce 1 */
+                                                                                 bitonic_sort_gpu (bitonic_sort_gpu.cpp:90-158); enable 0 = off, 1 = on, 2 = auto (the default:
+                                                                                 on with >= 3 materials and >= 384k paths per pass), from bounce 1 */
 int hc_pt_pass(hc_ctx* ctx, int integrator, int passes);                     /* BeginTracingPass+EndTracingPass, IHWLayer.h:133-134         */
 int hc_fb_clear(hc_ctx* ctx);                                                /* ClearAccumulatedColor, IHWLayer.h:140                       */
 int hc_fb_device_ptr(hc_ctx* ctx, float** outSumRGBA, int64_t* outFloats);   /* per-pixel SUM buffer (for the NCCL reduce over NVLink)      */
