@@ -411,6 +411,9 @@ int hc_ctx_create(int device, hc_ctx** out)
   c->smCount = c->prop.multiProcessorCount;
   HC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   HC_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+  HC_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)); HC_CUDA(cudaStreamCreateWithFlags(&c->copyStream2, cudaStreamNonBlocking));
+  HC_CUDA(cudaEventCreateWithFlags(&c->evFork2, cudaEventDisableTiming)); HC_CUDA(cudaEventCreateWithFlags(&c->evJoin2, cudaEventDisableTiming));
+  HC_CUDA(cudaEventCreateWithFlags(&c->evPipeFork, cudaEventDisableTiming)); HC_CUDA(cudaEventCreateWithFlags(&c->evPipeJoin, cudaEventDisableTiming));
   HC_CUDA(cudaEventCreateWithFlags(&c->evCopy, cudaEventDisableTiming));
   HC_CUDA(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming)); HC_CUDA(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
   HC_CUDA(cudaEventCreate(&c->ev0)); HC_CUDA(cudaEventCreate(&c->ev1));
@@ -436,6 +439,7 @@ void hc_ctx_destroy(hc_ctx* c)
   for (int i = 0; i < 5; i++) cudaEventDestroy(c->evStage[i]);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->copyStream2); cudaEventDestroy(c->evFork2); cudaEventDestroy(c->evJoin2); cudaEventDestroy(c->evPipeFork); cudaEventDestroy(c->evPipeJoin);
   cudaStreamDestroy(c->copyStream); cudaEventDestroy(c->evCopy); cudaEventDestroy(c->evFork); cudaEventDestroy(c->evJoin);
   delete c;
 }

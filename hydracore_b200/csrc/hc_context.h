@@ -27,6 +27,8 @@ struct hc_ctx
   cudaStream_t stream = nullptr;
   cudaStream_t copyStream = nullptr;       // read-backs that overlap the next kernel (hc_raycast_pass)
   cudaEvent_t  evCopy = nullptr;
+  cudaStream_t stream2 = nullptr, copyStream2 = nullptr;   // second path pipeline of small frames (hc_pt_pass)
+  cudaEvent_t  evFork2 = nullptr, evJoin2 = nullptr, evPipeFork = nullptr, evPipeJoin = nullptr;
   cudaEvent_t  evFork = nullptr, evJoin = nullptr;   // closest-hit and shadow traversal of one bounce run on two streams (hc_pt_pass)
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
   cudaDeviceProp prop{};

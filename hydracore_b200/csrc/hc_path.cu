@@ -411,7 +411,7 @@ static int ReserveState(hc_ctx* ctx, int64_t n, bool qmc)
   int rc;
   if ((rc = hc_buf_reserve(ctx, p->hits, uint64_t(n)*16))) return rc;
   if ((rc = hc_buf_reserve(ctx, p->vis, uint64_t(n)))) return rc;
-  if ((rc = hc_buf_reserve(ctx, p->pathCount, 256*sizeof(int)))) return rc;
+  if ((rc = hc_buf_reserve(ctx, p->pathCount, 2*256*sizeof(int)))) return rc;      // live counts per bounce, one block per pipeline
   if ((rc = hc_buf_reserve(ctx, p->sortKeys, uint64_t(n)*2))) return rc;
   if ((rc = hc_buf_reserve(ctx, p->sortPerm, uint64_t(n)*4))) return rc;
   if (!p->sortCount.ptr)
@@ -722,68 +722,116 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   // one pass = a fixed sequence of launches (live counts stay on the device), so untimed passes of a multi-pass call are replayed from a
   // CUDA graph captured once per call: at 512x512 (C1) the ~40 launches / memsets of a pass cost more to enqueue one by one than to run.
   // Not for QMC (the pass index is a kernel argument).  The last pass of a call always runs directly, with the stage events.
+  // Small frames are latency-bound: a 262k-ray launch is 2048 warps, one 32-ray batch each, and takes as long as its slowest warp
+  // (scripts/gpu_small_launch.py: 45-50 us from 65k to 262k rays on the C1 scene).  Passes over at most 1M paths are therefore split into two
+  // independent halves of the owned-pixel list - own live counters, state slices and pair of streams - so that one half's shade / sort / launch
+  // gaps are filled by the other half's traversal.  Pixels are independent, so the image is unchanged.  Measured (scripts/gpu_graph_ab.py,
+  // HC_PT_PIPES=1 for one pipeline): C1 0.619 -> 0.591 ms per pass, C3 at 480x270 1.272 -> 1.216; no more than that, because the warps of both
+  // halves were already resident together in the single launch.  The timed last pass of a call runs as one pipeline (stage events).
+  struct Pipe { int first, n; int* counts; cudaStream_t s, side; cudaEvent_t evFork, evJoin; };
+  auto sliceOf = [&](int b, int first) -> HcPathState
+  {
+    HcPathState st = StateOf(p, b, qmc);
+    st.rpos += first; st.rdir += first; st.thr += first; st.accum += first; st.rng += first; if (st.qpos) st.qpos += first;
+    st.spos += first; st.sdir += first; st.sexp += first;
+    return st;
+  };
+  auto genPipe = [&](const Pipe& q) -> int
+  {
+    int rc = 0;
+    HC_CUDA(cudaMemsetAsync(q.counts, 0, 256*sizeof(int), q.s));
+    HcPathState st0 = sliceOf(0, q.first);
+    HC_STAGE(3, (k_pt_generate<<<(q.n + 255)/256, 256, 0, q.s>>>(cam, pp, q.n, (const int*)p->owned.ptr + q.first, (uint2*)ctx->pixelRng.ptr, rmQMC, qtab, st0, q.counts)));
+    HC_CUDA(cudaGetLastError());
+    ctx->stats.kernelLaunches++; ctx->stats.paths += (uint64_t)q.n;
+    return HC_OK;
+  };
+  auto bouncePipe = [&](const Pipe& q, int depth, int cur) -> int
+  {
+    int rc = 0;
+    HcPathState in = sliceOf(cur, q.first), out = sliceOf(1 - cur, q.first);
+    HcHit* hits = (HcHit*)p->hits.ptr + q.first;
+    unsigned char* vis = (unsigned char*)p->vis.ptr + q.first;
+    int* counts = q.counts;
+    const int n = q.n;
+    // the shadow rays of the previous bounce and the closest-hit rays of this one are independent: two streams, so that the tail of
+    // one persistent launch (last warps finishing their rays) is filled by the head of the other; joined before sort / shade
+    const bool haveShadow = (depth > 0 && integrator != HC_INTEGRATOR_PT);
+    if (haveShadow)
+    {
+      HC_CUDA(cudaEventRecord(q.evFork, q.s));
+      HC_CUDA(cudaStreamWaitEvent(q.side, q.evFork, 0));
+    }
+    HC_STAGE(0, if ((rc = hc_launch_trace_counted(ctx, false, in.rpos, in.rdir, n, counts + depth, hits, nullptr, q.s))) return rc);
+    if (haveShadow)
+    {
+      // timing: the "shadow" stage is what the any-hit launch ADDS after the closest-hit launch has finished (both measured on the
+      // main stream), so that the stage times still add up to the pass
+      if ((rc = stageBegin(1))) return rc;
+      if ((rc = hc_launch_trace_counted(ctx, true, in.spos, in.sdir, n, counts + depth, nullptr, vis, q.side))) return rc;
+      HC_CUDA(cudaEventRecord(q.evJoin, q.side));
+      HC_CUDA(cudaStreamWaitEvent(q.s, q.evJoin, 0));
+      if ((rc = stageEnd())) return rc;
+    }
+    const int* perm = nullptr;
+    if (sortKeys > 0 && depth >= ctx->sortFromBounce)        // only single-pipeline passes sort (the buffers below are not sliced)
+    {
+      // material sort of the live-path queue (skipped while the queue is still in screen order and therefore coherent)
+      const int sortGrid = std::min((n + HC_SORT_BLOCK - 1)/HC_SORT_BLOCK, ctx->smCount*8);
+      if ((rc = stageBegin(3))) return rc;
+      k_pt_sort_count<<<sortGrid, HC_SORT_BLOCK, sortKeys*sizeof(int), q.s>>>(scn, counts + depth, hits,
+                        (unsigned short*)p->sortKeys.ptr, (int*)p->sortCount.ptr, sortKeys);
+      k_pt_sort_scan<<<1, 1024, 0, q.s>>>((int*)p->sortCount.ptr, (int*)p->sortCursor.ptr, sortKeys);
+      k_pt_sort_scatter<<<(n + HC_SORT_BLOCK - 1)/HC_SORT_BLOCK, HC_SORT_BLOCK, 0, q.s>>>(counts + depth, (const unsigned short*)p->sortKeys.ptr,
+                          (int*)p->sortCursor.ptr, (int*)p->sortPerm.ptr);
+      if ((rc = stageEnd())) return rc;
+      HC_CUDA(cudaGetLastError());
+      ctx->stats.kernelLaunches += 3;
+      perm = (const int*)p->sortPerm.ptr;
+    }
+    pp.depth = depth; pp.isLast = (depth == nBounces - 1) ? 1 : 0;
+    if (p->haveNormalMaps)
+    {
+      HC_STAGE(2, (k_pt_shade<true><<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, q.s>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
+                   hits, vis, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
+    }
+    else
+    {
+      HC_STAGE(2, (k_pt_shade<false><<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, q.s>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
+                   hits, vis, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
+    }
+    HC_CUDA(cudaGetLastError());
+    ctx->stats.kernelLaunches++;
+    return HC_OK;
+  };
+  static int pipesEnv = -1; if (pipesEnv < 0) { const char* e = getenv("HC_PT_PIPES"); pipesEnv = e ? atoi(e) : 0; }
+  const bool twoPipes = !qmc && sortKeys == 0 && n >= 4096 && (pipesEnv == 2 || (pipesEnv == 0 && n <= 1024*1024));
   auto enqueuePass = [&]() -> int
   {
     int rc = 0;
-    HC_CUDA(cudaMemsetAsync(counts, 0, 256*sizeof(int), ctx->stream));
+    Pipe pipes[2]; int np = 1;
+    pipes[0] = Pipe{ 0, n, counts, ctx->stream, ctx->copyStream, ctx->evFork, ctx->evJoin };
+    if (twoPipes && !timed)
+    {
+      const int nA = ((n/2 + 31)/32)*32;
+      pipes[0].n = nA;
+      pipes[1] = Pipe{ nA, n - nA, counts + 256, ctx->stream2, ctx->copyStream2, ctx->evFork2, ctx->evJoin2 };
+      np = 2;
+      HC_CUDA(cudaEventRecord(ctx->evPipeFork, ctx->stream));
+      HC_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->evPipeFork, 0));
+    }
     if (timed) HC_CUDA(cudaEventRecord(ctx->evStage[0], ctx->stream));
-    HcPathState st0 = StateOf(p, 0, qmc);
-    HC_STAGE(3, (k_pt_generate<<<(n + 255)/256, 256, 0, ctx->stream>>>(cam, pp, n, (const int*)p->owned.ptr, (uint2*)ctx->pixelRng.ptr, rmQMC, qtab, st0, counts)));
-    HC_CUDA(cudaGetLastError());
-    ctx->stats.kernelLaunches++; ctx->stats.paths += (uint64_t)n;
+    for (int k = 0; k < np; k++) if ((rc = genPipe(pipes[k]))) return rc;
     int cur = 0;
     for (int depth = 0; depth < nBounces; depth++)
     {
-      HcPathState in = StateOf(p, cur, qmc), out = StateOf(p, 1 - cur, qmc);
-      pp.depth = depth; pp.isLast = (depth == nBounces - 1) ? 1 : 0;
-      // the shadow rays of the previous bounce and the closest-hit rays of this one are independent: two streams, so that the tail of
-      // one persistent launch (last warps finishing their rays) is filled by the head of the other; joined before sort / shade
-      const bool haveShadow = (depth > 0 && integrator != HC_INTEGRATOR_PT);
-      if (haveShadow)
-      {
-        HC_CUDA(cudaEventRecord(ctx->evFork, ctx->stream));
-        HC_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evFork, 0));
-      }
-      HC_STAGE(0, if ((rc = hc_launch_trace_counted(ctx, false, in.rpos, in.rdir, n, counts + depth, (HcHit*)p->hits.ptr, nullptr))) return rc);
-      if (haveShadow)
-      {
-        // timing: the "shadow" stage is what the any-hit launch ADDS after the closest-hit launch has finished (both measured on the
-        // main stream), so that the stage times still add up to the pass
-        if ((rc = stageBegin(1))) return rc;
-        if ((rc = hc_launch_trace_counted(ctx, true, in.spos, in.sdir, n, counts + depth, nullptr, (unsigned char*)p->vis.ptr, ctx->copyStream))) return rc;
-        HC_CUDA(cudaEventRecord(ctx->evJoin, ctx->copyStream));
-        HC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
-        if ((rc = stageEnd())) return rc;
-      }
-      const int* perm = nullptr;
-      if (sortKeys > 0 && depth >= ctx->sortFromBounce)
-      {
-        // material sort of the live-path queue (skipped while the queue is still in screen order and therefore coherent)
-        const int sortGrid = std::min((n + HC_SORT_BLOCK - 1)/HC_SORT_BLOCK, ctx->smCount*8);
-        if ((rc = stageBegin(3))) return rc;
-        k_pt_sort_count<<<sortGrid, HC_SORT_BLOCK, sortKeys*sizeof(int), ctx->stream>>>(scn, counts + depth, (const HcHit*)p->hits.ptr,
-                          (unsigned short*)p->sortKeys.ptr, (int*)p->sortCount.ptr, sortKeys);
-        k_pt_sort_scan<<<1, 1024, 0, ctx->stream>>>((int*)p->sortCount.ptr, (int*)p->sortCursor.ptr, sortKeys);
-        k_pt_sort_scatter<<<(n + HC_SORT_BLOCK - 1)/HC_SORT_BLOCK, HC_SORT_BLOCK, 0, ctx->stream>>>(counts + depth, (const unsigned short*)p->sortKeys.ptr,
-                            (int*)p->sortCursor.ptr, (int*)p->sortPerm.ptr);
-        if ((rc = stageEnd())) return rc;
-        HC_CUDA(cudaGetLastError());
-        ctx->stats.kernelLaunches += 3;
-        perm = (const int*)p->sortPerm.ptr;
-      }
-      if (p->haveNormalMaps)
-      {
-        HC_STAGE(2, (k_pt_shade<true><<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, ctx->stream>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
-                     (const HcHit*)p->hits.ptr, (const unsigned char*)p->vis.ptr, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
-      }
-      else
-      {
-        HC_STAGE(2, (k_pt_shade<false><<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, ctx->stream>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
-                     (const HcHit*)p->hits.ptr, (const unsigned char*)p->vis.ptr, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
-      }
-      HC_CUDA(cudaGetLastError());
-      ctx->stats.kernelLaunches++;
+      for (int k = 0; k < np; k++) if ((rc = bouncePipe(pipes[k], depth, cur))) return rc;
       cur = 1 - cur;
+    }
+    if (np == 2)
+    {
+      HC_CUDA(cudaEventRecord(ctx->evPipeJoin, ctx->stream2));
+      HC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evPipeJoin, 0));
     }
     if (timed) HC_CUDA(cudaEventRecord(ctx->evStage[1], ctx->stream));
     return HC_OK;
