@@ -23,7 +23,7 @@
 
 #define HC_SHADE_BLOCK 128
 #ifndef HC_SHADE_MINB
-#define HC_SHADE_MINB 4
+#define HC_SHADE_MINB 5      // CTAs per SM: 96 registers. Swept again after the code-size cut (C3 / C4 shade ms): 3 -> 1.81 / 1.19, 4 -> 1.55 / 1.04, 5 -> 1.51 / 1.03, 6 -> 1.49 / 1.06
 #endif
 
 struct HcPathState          // one half of the double buffer
