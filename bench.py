@@ -425,7 +425,8 @@ def run_ours(args):
                          "ms_per_launch": ms_closest, "peak_source": peak_src,
                          "note": "algorithmic bytes are BVH/triangle fetches that L1 (84 % hit) and the 126 MB L2 serve, so frac can exceed 1; "
                                  "the kernel is bound by instruction issue and the L1/LSU wavefront rate (fields below, from the ncu capture in profiles/)",
-                         "measured_memory_peaks": mem_peaks, "ncu": ncu_extra}}
+                         "measured_memory_peaks": mem_peaks, "ncu": ncu_extra,
+                         "frac_vs_measured_l2_read": (achieved/mem_peaks["l2_read_gbs"]) if mem_peaks else None}}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     line.update(extras)
