@@ -481,12 +481,21 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
       continue;
     }
     if (type == HC_PLAIN_LIGHT_TYPE_POINT_SPOT || type == HC_PLAIN_LIGHT_TYPE_DIRECT) continue;
+    if (type == HC_PLAIN_LIGHT_TYPE_MESH)
+    {
+      int meshTab, pdfTab, triNum, mtex; memcpy(&meshTab, L + 14, 4); memcpy(&pdfTab, L + 15, 4); memcpy(&triNum, L + 16, 4); memcpy(&mtex, L + 30, 4);   // MESH_LIGHT_* (clight.h:169-175)
+      const int nTab = gi(HC_EG_pdfTableTableSize);
+      if (!ctx->storage[HC_STORAGE_PDFS].ptr || meshTab < 0 || meshTab >= nTab || pdfTab < 0 || pdfTab >= nTab || triNum < 1) { why = "mesh light without its mesh copy / triangle table in the pdfs storage"; return HC_E_ARG; }
+      if (mtex != HC_INVALID_TEXTURE) { why = "textured mesh lights are not supported yet"; return HC_E_ARG; }
+      if (flags & HC_LIGHT_HAS_IES) { why = "IES distributions are not supported yet"; return HC_E_ARG; }
+      continue;
+    }
     if (type == HC_PLAIN_LIGHT_TYPE_SPHERE || type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI)
     {
       if (flags & HC_LIGHT_HAS_IES) { why = "IES distributions are not supported yet"; return HC_E_ARG; }
       continue;
     }
-    if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "cylinder and mesh lights are not supported yet (area, sphere, point, spot, directional, sky-dome lights are)"; return HC_E_ARG; }
+    if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "cylinder lights are not supported yet (area, sphere, mesh, point, spot, directional, sky-dome lights are)"; return HC_E_ARG; }
     if (flags & (HC_LIGHT_HAS_IES | HC_AREA_LIGHT_SKY_PORTAL | HC_LIGHT_IES_POINT_AREA)) { why = "IES / sky-portal area lights are not supported yet"; return HC_E_ARG; }
     if (tex != HC_INVALID_TEXTURE) { why = "textured area lights are not supported yet"; return HC_E_ARG; }
     if (spot != 0) { why = "area lights with a spot distribution are not supported yet"; return HC_E_ARG; }

@@ -6,7 +6,7 @@
 // reference's unqualified math calls to double (see hc_math.cuh) are kept, so that the same random numbers give the same
 // path on the GPU and in the CPU oracle.  Supported: Lambert, Oren-Nayar, translucent Lambert, Phong, Blinn (Torrance-Sparrow), GGX (Heitz VNDF sampling +
 // multiscattering table), perfect mirror, GGX glass, thin glass, blend masks (simple / fresnel / sigmoid), emissive materials, normal maps; rectangular / disk / sphere
-// area lights, omni / spot point lights, directional lights, sky domes (constant or textured); RGBA8 and float4 textures.
+// area lights, omni / spot point lights, directional lights, mesh lights, sky domes (constant or textured); RGBA8 and float4 textures.
 // Everything else is rejected with an error at hc_pt_init (no silent fallback).
 #pragma once
 #include "hc_math.cuh"
@@ -1344,6 +1344,57 @@ HC_DEV float DirectLightEvalPDF(const float* L, float3 rayDir)                  
   return (float)(HC_M_PI_D*(double)(tanAlpha*tanAlpha)*(double)(cosTheta*cosTheta*cosTheta));
 }
 
+// ---- mesh lights (clight.h:957-1029, 1513-1546): an emissive mesh sampled by area; the mesh (a PlainMesh copy) and the prefix sums of its
+// triangle areas live in the "pdfs" storage (MeshLight, PlainLightConverter.cpp:724-783; CalcTrianglePickProbTable)
+#define HC_MESH_LIGHT_MESH_OFFSET_ID  14
+#define HC_MESH_LIGHT_TABLE_OFFSET_ID 15
+#define HC_MESH_LIGHT_TRI_NUM         16
+#define HC_MESH_LIGHT_MATRIX_E00      20
+#define HC_MESH_LIGHT_TEX_ID          30
+HC_DEV float3 Mat3x3MulVec(const float* M, float3 v)                                                                          // matrix3x3f_mult_float3, cglobals.h:1091-1098
+{
+  return f3(M[0]*v.x + M[1]*v.y + M[2]*v.z, M[3]*v.x + M[4]*v.y + M[5]*v.z, M[6]*v.x + M[7]*v.y + M[8]*v.z);
+}
+HC_DEV void MeshLightSampleRev(const float* L, float3 rands, float3 illum, const HcScene& s, HcShadowSample& out)
+{
+  const int meshId = __float_as_int(L[HC_MESH_LIGHT_MESH_OFFSET_ID]), pdftId = __float_as_int(L[HC_MESH_LIGHT_TABLE_OFFSET_ID]);
+  const int triNum = __float_as_int(L[HC_MESH_LIGHT_TRI_NUM]);
+  const float4* mesh = s.pdfs + s.globals[s.pdfTableTableOffset + meshId];
+  const float* table = reinterpret_cast<const float*>(s.pdfs + s.globals[s.pdfTableTableOffset + pdftId]);
+  const int4 h0 = reinterpret_cast<const int4*>(mesh)[0];                        // vPosOffset vNormOffset vTexCoordOffset vIndicesOffset
+  const float4* vpos = mesh + h0.x; const float4* vnorm = mesh + h0.y;
+  const int* indices = reinterpret_cast<const int*>(mesh + h0.w);
+  float pickProb = 1.0f;
+  const int tri = SelectIndexPropToOpt(rands.z, table, triNum + 1, pickProb);
+  const int iA = indices[tri*3 + 0], iB = indices[tri*3 + 1], iC = indices[tri*3 + 2];
+  const float3 A = f3(vpos[iA]), B = f3(vpos[iB]), C = f3(vpos[iC]);
+  const float3 nA = f3(vnorm[iA]), nB = f3(vnorm[iB]), nC = f3(vnorm[iC]);
+  float u = rands.x, v = rands.y;
+  if (u + v > 1.0f) { u = 1.0f - u; v = 1.0f - v; }
+  const float w = 1.0f - u - v;
+  float3 samplePos = (A*u + B*v + C*w), sampleNorm = (nA*u + nB*v + nC*w);
+  const float pdfA = 1.0f/L[HC_PLIGHT_SURFACE_AREA];
+  const float* M = L + HC_MESH_LIGHT_MATRIX_E00;
+  samplePos = Mat3x3MulVec(M, samplePos);
+  sampleNorm = normalize(Mat3x3MulVec(M, sampleNorm));
+  samplePos = samplePos + Mat3(L, HC_PLIGHT_POS_X);
+  const float3 rayDir = normalize(samplePos - illum);
+  const float hitDist = length(samplePos - illum);
+  const float cosVal = fmaxf(-dot(rayDir, sampleNorm), 0.0f);
+  out.isPoint = false;
+  out.pos = samplePos + epsilonOfPos(samplePos)*sampleNorm;
+  out.color = Mat3(L, HC_PLIGHT_COLOR_X);                                        // meshLightGetIntensity without a texture (textured ones are rejected at init)
+  out.pdf = PdfAtoW(pdfA, hitDist, cosVal);
+  out.maxDist = hitDist;
+  out.cosAtLight = cosVal;
+}
+HC_DEV float MeshLightEvalPDF(const float* L, float3 rayDir, float3 lnorm, float hitDist)                                     // clight.h:1541-1546
+{
+  const float pdfA = 1.0f/fmaxf(L[HC_PLIGHT_SURFACE_AREA], HC_DEPSILON);
+  const float cosVal = fmaxf(dot(rayDir, (-1.0f)*lnorm), 0.0f);
+  return PdfAtoW(pdfA, hitDist, cosVal);
+}
+
 HC_DEV void LightSampleRev(const float* L, float3 rands, float3 illum, const HcScene& s, HcShadowSample& out)
 {
   const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
@@ -1352,6 +1403,7 @@ HC_DEV void LightSampleRev(const float* L, float3 rands, float3 illum, const HcS
   else if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI) PointLightSampleRev(L, illum, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_POINT_SPOT) SpotLightSampleRev(L, illum, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_DIRECT) DirectLightSampleRev(L, rands, illum, out);
+  else if (type == HC_PLAIN_LIGHT_TYPE_MESH) MeshLightSampleRev(L, rands, illum, s, out);
   else AreaLightSampleRev(L, rands, illum, out);
 }
 
@@ -1363,6 +1415,7 @@ HC_DEV float LightEvalPDF(const float* L, float3 illum, float3 rayDir, float3 lp
   if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI || type == HC_PLAIN_LIGHT_TYPE_POINT_SPOT)                                    // pointLightEvalPDF / spotLightEvalPDF,
     return PdfAtoW(1.0f, length(Mat3(L, HC_PLIGHT_POS_X) - illum), 1.0f);                                                  // clight.h:1387-1392, 1425-1430
   if (type == HC_PLAIN_LIGHT_TYPE_DIRECT) return DirectLightEvalPDF(L, rayDir);
+  if (type == HC_PLAIN_LIGHT_TYPE_MESH) return MeshLightEvalPDF(L, rayDir, lnorm, hitDist);
   return AreaLightEvalPDF(L, rayDir, hitDist);
 }
 

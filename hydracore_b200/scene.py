@@ -346,6 +346,49 @@ class Scene:
         self.lights.append(np.ascontiguousarray(plain_light, np.float32).reshape(128))
         return len(self.lights) - 1
 
+    def add_mesh_light(self, mesh_id, matrix, intensity):
+        """Mesh light (MeshLight + Transform, PlainLightConverter.cpp:724-830): the light samples the triangles of `mesh_id` by area.  A copy of
+        the packed mesh and the prefix sums of its triangle areas (CalcTrianglePickProbTable, RenderDriverRTE_PdfTables.cpp:650-674) go into the
+        "pdfs" storage; position, rotation sub-matrix and the transformed surface area into the light.  Returns the light id; instance the mesh
+        with the same matrix, an emissive material and light_id = this id so that paths can hit it."""
+        from . import materials as M
+        f = np.float32
+        mesh = self.meshes[mesh_id]
+        mtx = np.asarray(matrix, np.float32).reshape(4, 4)
+        P = mesh.pos.astype(np.float32)
+
+        def areas(pts):
+            A, B, Cc = pts[mesh.idx[:, 0]], pts[mesh.idx[:, 1]], pts[mesh.idx[:, 2]]
+            e1, e2 = (B - A).astype(f), (Cc - A).astype(f)
+            cx = (e1[:, 1]*e2[:, 2]).astype(f) - (e1[:, 2]*e2[:, 1]).astype(f)
+            cy = (e1[:, 2]*e2[:, 0]).astype(f) - (e1[:, 0]*e2[:, 2]).astype(f)
+            cz = (e1[:, 0]*e2[:, 1]).astype(f) - (e1[:, 1]*e2[:, 0]).astype(f)
+            ln = np.sqrt(((cx*cx).astype(f) + (cy*cy).astype(f)).astype(f) + (cz*cz).astype(f), dtype=f)
+            return (f(0.5)*ln).astype(f)
+
+        tri = areas(P)
+        table = np.zeros(tri.size + 1, f)
+        acc = f(0)
+        for i, a in enumerate(tri):
+            table[i] = acc
+            acc = f(acc + a)
+        table[tri.size] = acc
+        self.pdf_tables.append(mesh.pack())                      # the PlainMesh copy
+        self.pdf_tables.append(table)
+        # mul(a_matrix, p) of LiteMath: row-major rows dotted with (p, 1), sums left to right
+        Pw = np.stack([((mtx[r, 0]*P[:, 0]).astype(f) + (mtx[r, 1]*P[:, 1]).astype(f)).astype(f) + (mtx[r, 2]*P[:, 2]).astype(f) + mtx[r, 3] for r in range(3)], 1).astype(f)
+        total = 0.0
+        for a in areas(Pw):
+            total += float(a)
+        L = M.point_light(tuple(mtx[:3, 3]), intensity)
+        Li = L.view(np.int32)
+        Li[C["PLIGHT_TYPE"]] = C["PLAIN_LIGHT_TYPE_MESH"]
+        Li[14], Li[15], Li[16] = len(self.pdf_tables) - 2, len(self.pdf_tables) - 1, tri.size     # MESH_LIGHT_MESH_OFFSET_ID / TABLE_OFFSET_ID / TRI_NUM
+        L[20:29] = mtx[:3, :3].reshape(9)                                                              # MESH_LIGHT_MATRIX_E00, rows
+        Li[30], Li[31] = INVALID_TEXTURE, INVALID_TEXTURE                                              # MESH_LIGHT_TEX_ID / TEXMATRIX_ID
+        L[C["PLIGHT_SURFACE_AREA"]] = f(total)
+        return self.add_light(L)
+
     def add_sky_pdf_table(self, lum=None):
         """Pdf table of a sky-dome light as RenderDriverRTE::UpdatePdfTablesForLight builds it (RenderDriverRTE_PdfTables.cpp:520-566): prefix sums of
         the luminance image (2x2 of 0.25 for an untextured sky); returns the table id to put into SKY_DOME_PDF_TABLE0."""

@@ -254,6 +254,29 @@ def cornell_remap_lists(width=96, height=96):
     return scn.build()
 
 
+def cornell_mesh_light(width=96, height=96):
+    """The Cornell room lit by a MESH light: an emissive, rotated and scaled sphere sampled by triangle area (plus a small rect light)."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    ggxm = scn.add_material(M.ggx((0.8, 0.6, 0.2), 0.7))
+    emi0 = scn.add_material(M.emissive((12.0, 10.0, 6.0), 0))
+    emi1 = scn.add_material(M.emissive((17.0, 15.0, 12.0), 1))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, white, white, white), inward=True, skip_faces=(4,))))
+    sph = S.sphere_mesh(1.0, 16, 8)
+    scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, ggxm, np.int32))), S.translate(-2.0, -2.8, -1.0) @ S.scale(1.2, 1.2, 1.2))
+    lmesh = scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, emi0, np.int32)))
+    mtx = S.translate(1.5, 0.5, 0.5) @ S.rotate_y(0.7) @ S.scale(0.8, 0.5, 0.6)
+    l0 = scn.add_mesh_light(lmesh, mtx, (12.0, 10.0, 6.0))
+    scn.add_instance(lmesh, mtx, light_id=l0)
+    l1 = scn.add_light(M.area_light((0.0, 3.95, 0.0), (0.5, 0.5), (17.0, 15.0, 12.0)))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(0.5, 0.5, y=0.0, mat_id=emi1, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l1)
+    return scn.build()
+
+
 def cornell_with_cutout(width=96, height=96):
     """The Cornell room with two instances of a quad whose material has an opacity (cut-out) map - a checker of opaque and transparent
     cells, bilinear and point sampled - in front of the back wall and above the floor: the quads go into the alpha-tested tree 1, rays
