@@ -164,7 +164,7 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
           const float* L = (s.lightsNum != 0) ? LightAt(s, s.instLightIds[hit.instId]) : nullptr;
           if (L != nullptr)
           {                                                       // kernel_EvalEmission (PT_Loop.cpp:86-139)
-            const float lgtPdf = L[HC_PLIGHT_PICK_PROB_REV]*LightEvalPDF(L, rayPos, rayDir, sh.pos, sh.normal);
+            const float lgtPdf = L[HC_PLIGHT_PICK_PROB_REV]*LightEvalPDF(L, rayPos, rayDir, sh.pos, sh.normal, sh.texCoord, s);
             float w = misWeightHeuristic(prevPdf, lgtPdf);
             if (prevSpecular) w = 1.0f;
             curr = e*w;
@@ -481,6 +481,13 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
       continue;
     }
     if (type == HC_PLAIN_LIGHT_TYPE_POINT_SPOT || type == HC_PLAIN_LIGHT_TYPE_DIRECT) continue;
+    if (type == HC_PLAIN_LIGHT_TYPE_CYLINDER)
+    {
+      int ctex, ctab; memcpy(&ctex, L + 29, 4); memcpy(&ctab, L + 31, 4);                     // CYLINDER_TEX_ID, CYLINDER_PDF_TABLE_ID (clight.h:111-113)
+      if (ctex != HC_INVALID_TEXTURE) { why = "textured cylinder lights are not supported yet"; return HC_E_ARG; }
+      if (ctab < 0 || ctab >= gi(HC_EG_pdfTableTableSize) || !ctx->storage[HC_STORAGE_PDFS].ptr) { why = "cylinder light without the pdf table the driver builds for it (UpdatePdfTablesForLight)"; return HC_E_ARG; }
+      continue;
+    }
     if (type == HC_PLAIN_LIGHT_TYPE_MESH)
     {
       int meshTab, pdfTab, triNum, mtex; memcpy(&meshTab, L + 14, 4); memcpy(&pdfTab, L + 15, 4); memcpy(&triNum, L + 16, 4); memcpy(&mtex, L + 30, 4);   // MESH_LIGHT_* (clight.h:169-175)
@@ -495,7 +502,7 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
       if (flags & HC_LIGHT_HAS_IES) { why = "IES distributions are not supported yet"; return HC_E_ARG; }
       continue;
     }
-    if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "cylinder lights are not supported yet (area, sphere, mesh, point, spot, directional, sky-dome lights are)"; return HC_E_ARG; }
+    if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "unknown light type (area, sphere, cylinder, mesh, point, spot, directional, sky-dome lights are supported)"; return HC_E_ARG; }
     if (flags & (HC_LIGHT_HAS_IES | HC_AREA_LIGHT_SKY_PORTAL | HC_LIGHT_IES_POINT_AREA)) { why = "IES / sky-portal area lights are not supported yet"; return HC_E_ARG; }
     if (tex != HC_INVALID_TEXTURE) { why = "textured area lights are not supported yet"; return HC_E_ARG; }
     if (spot != 0) { why = "area lights with a spot distribution are not supported yet"; return HC_E_ARG; }

@@ -6,7 +6,7 @@
 // reference's unqualified math calls to double (see hc_math.cuh) are kept, so that the same random numbers give the same
 // path on the GPU and in the CPU oracle.  Supported: Lambert, Oren-Nayar, translucent Lambert, Phong, Blinn (Torrance-Sparrow), GGX (Heitz VNDF sampling +
 // multiscattering table), perfect mirror, GGX glass, thin glass, blend masks (simple / fresnel / sigmoid), emissive materials, normal maps; rectangular / disk / sphere
-// area lights, omni / spot point lights, directional lights, mesh lights, sky domes (constant or textured); RGBA8 and float4 textures.
+// area lights, omni / spot point lights, directional lights, mesh and cylinder lights, sky domes (constant or textured); RGBA8 and float4 textures.
 // Everything else is rejected with an error at hc_pt_init (no silent fallback).
 #pragma once
 #include "hc_math.cuh"
@@ -1395,6 +1395,73 @@ HC_DEV float MeshLightEvalPDF(const float* L, float3 rayDir, float3 lnorm, float
   return PdfAtoW(pdfA, hitDist, cosVal);
 }
 
+// ---- cylinder lights (clight.h:753-812, 1338-1380): a tube section sampled uniformly or - when its pdf table id is positive - through the 2D
+// table the driver builds for it (UpdatePdfTablesForLight: 2x2 uniform when the light has no texture).  sincos2f = double sin / cos.
+#define HC_CYLINDER_LIGHT_MATRIX_E00 16
+#define HC_CYLINDER_LIGHT_RADIUS     25
+#define HC_CYLINDER_LIGHT_ZMIN       26
+#define HC_CYLINDER_LIGHT_ZMAX       27
+#define HC_CYLINDER_LIGHT_PHIMAX     28
+#define HC_CYLINDER_TEX_ID           29
+#define HC_CYLINDER_PDF_TABLE_ID     31
+HC_DEV void CylinderLightSampleRev(const float* L, float3 rands, float3 illum, const HcScene& s, HcShadowSample& out)
+{
+  float2 tc = f2(rands.x, rands.y); float mapPdf = 1.0f;
+  const int texId = __float_as_int(L[HC_CYLINDER_PDF_TABLE_ID]);
+  if (texId > 0)
+  {
+    const float* hdr = PdfTableHeader(texId, s);
+    const float* intervals = hdr + 4;
+    const int sizeX = __float_as_int(hdr[0]), sizeY = __float_as_int(hdr[1]);
+    const float fw = (float)sizeX, fh = (float)sizeY, fN = fw*fh;
+    float pdf = 1.0f;                                                                        // sampleMap2D, clight.h:375-396
+    int pixelOffset = SelectIndexPropToOpt(rands.z, intervals, sizeX*sizeY + 1, pdf);
+    if (pixelOffset >= sizeX*sizeY) pixelOffset = sizeX*sizeY - 1;
+    const int yPos = pixelOffset/sizeX, xPos = pixelOffset - yPos*sizeX;
+    tc.x = (1.0f/fw)*(((float)(xPos) + 0.5f) + (rands.x*2.0f - 1.0f)*0.5f);
+    tc.y = (1.0f/fh)*(((float)(yPos) + 0.5f) + (rands.y*2.0f - 1.0f)*0.5f);
+    mapPdf = pdf*fN;
+  }
+  const float pdfA = mapPdf/L[HC_PLIGHT_SURFACE_AREA];
+  const float zMin = L[HC_CYLINDER_LIGHT_ZMIN], zMax = L[HC_CYLINDER_LIGHT_ZMAX], radius = L[HC_CYLINDER_LIGHT_RADIUS], phiMax = L[HC_CYLINDER_LIGHT_PHIMAX];
+  const float z = zMin + tc.x*(zMax - zMin);
+  const float phi = tc.y*phiMax;
+  const float sn = hc_sin(phi), cs = hc_cos(phi);
+  float3 pObj = f3(radius*cs, radius*sn, z);
+  float3 n = normalize(f3(pObj.x, pObj.y, 0.0f));
+  const float hitRad = sqrtf(pObj.x*pObj.x + pObj.y*pObj.y);
+  pObj.x *= radius/hitRad;
+  pObj.y *= radius/hitRad;
+  const float* M = L + HC_CYLINDER_LIGHT_MATRIX_E00;
+  n = normalize(Mat3x3MulVec(M, n));
+  const float3 center = Mat3(L, HC_PLIGHT_POS_X);
+  const float3 samplePos = center + Mat3x3MulVec(M, pObj) + epsilonOfPos(center)*n;
+  const float hitDist = length(samplePos - illum);
+  const float3 rayDir = normalize(samplePos - illum);
+  const float cosVal = fmaxf(dot(rayDir, (-1.0f)*n), 0.0f);
+  out.isPoint = false;
+  out.pos = samplePos;
+  out.color = Mat3(L, HC_PLIGHT_COLOR_X);                                                    // cylinderLightGetIntensity without a texture
+  out.pdf = PdfAtoW(pdfA, hitDist, cosVal);
+  out.maxDist = hitDist;
+  out.cosAtLight = cosVal;
+}
+HC_DEV float CylinderLightEvalPDF(const float* L, float3 illum, float3 lpos, float3 lnorm, float2 texCoord, const HcScene& s)  // clight.h:1338-1357
+{
+  float mapPdf = 1.0f;
+  const int texId = __float_as_int(L[HC_CYLINDER_PDF_TABLE_ID]);
+  if (texId)                                                                                 // sic: any non-zero id (ids < 0 are rejected at init)
+  {
+    const float* hdr = PdfTableHeader(texId, s);
+    mapPdf = EvalMap2DPdf(texCoord, hdr + 4, __float_as_int(hdr[0]), __float_as_int(hdr[1]));
+  }
+  const float hitDist = length(lpos - illum);
+  const float3 rayDir = normalize(lpos - illum);
+  const float pdfA = mapPdf/fmaxf(L[HC_PLIGHT_SURFACE_AREA], HC_DEPSILON);
+  const float cosVal = fmaxf(dot(rayDir, (-1.0f)*lnorm), 0.0f);
+  return PdfAtoW(pdfA, hitDist, cosVal);
+}
+
 HC_DEV void LightSampleRev(const float* L, float3 rands, float3 illum, const HcScene& s, HcShadowSample& out)
 {
   const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
@@ -1404,10 +1471,11 @@ HC_DEV void LightSampleRev(const float* L, float3 rands, float3 illum, const HcS
   else if (type == HC_PLAIN_LIGHT_TYPE_POINT_SPOT) SpotLightSampleRev(L, illum, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_DIRECT) DirectLightSampleRev(L, rands, illum, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_MESH) MeshLightSampleRev(L, rands, illum, s, out);
+  else if (type == HC_PLAIN_LIGHT_TYPE_CYLINDER) CylinderLightSampleRev(L, rands, illum, s, out);
   else AreaLightSampleRev(L, rands, illum, out);
 }
 
-HC_DEV float LightEvalPDF(const float* L, float3 illum, float3 rayDir, float3 lpos, float3 lnorm)
+HC_DEV float LightEvalPDF(const float* L, float3 illum, float3 rayDir, float3 lpos, float3 lnorm, float2 texCoord, const HcScene& s)
 {
   const float hitDist = length(illum - lpos);
   const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
@@ -1416,6 +1484,7 @@ HC_DEV float LightEvalPDF(const float* L, float3 illum, float3 rayDir, float3 lp
     return PdfAtoW(1.0f, length(Mat3(L, HC_PLIGHT_POS_X) - illum), 1.0f);                                                  // clight.h:1387-1392, 1425-1430
   if (type == HC_PLAIN_LIGHT_TYPE_DIRECT) return DirectLightEvalPDF(L, rayDir);
   if (type == HC_PLAIN_LIGHT_TYPE_MESH) return MeshLightEvalPDF(L, rayDir, lnorm, hitDist);
+  if (type == HC_PLAIN_LIGHT_TYPE_CYLINDER) return CylinderLightEvalPDF(L, illum, lpos, lnorm, texCoord, s);
   return AreaLightEvalPDF(L, rayDir, hitDist);
 }
 

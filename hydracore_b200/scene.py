@@ -217,6 +217,24 @@ def sphere_mesh(radius, nu, nv, mat_id=0):
     return Mesh(pos, idx, norm=n, uv=uv, mat=np.full(idx.shape[0], mat_id, np.int32))
 
 
+def cylinder_mesh(radius, height, nu, phi_max=2*math.pi, mat_id=0):
+    """Open tube section around the local Z axis (the parameterisation of CylinderLightSamplePos, clight.h:785-799): z in [-h/2, h/2],
+    phi in [0, phi_max]; outward normals, uv = (z fraction, phi fraction), 2*nu triangles."""
+    ph = np.linspace(0, phi_max, nu + 1)
+    pos, nrm, uv = [], [], []
+    for k, z in enumerate((-0.5*height, 0.5*height)):
+        for j, p in enumerate(ph):
+            pos.append([radius*math.cos(p), radius*math.sin(p), z])
+            nrm.append([math.cos(p), math.sin(p), 0.0])
+            uv.append([float(k), j/float(nu)])
+    idx = []
+    for j in range(nu):
+        a, b = j, j + nu + 1
+        idx += [[a, a + 1, b], [a + 1, b + 1, b]]
+    idx = np.array(idx, np.int32)
+    return Mesh(np.array(pos, np.float32), idx, norm=np.array(nrm, np.float32), uv=np.array(uv, np.float32), mat=np.full(idx.shape[0], mat_id, np.int32))
+
+
 # ---------------------------------------------------------------------------------------------------------------- matrices
 def translate(x, y, z):
     m = np.eye(4, dtype=np.float32)
@@ -345,6 +363,27 @@ class Scene:
     def add_light(self, plain_light):
         self.lights.append(np.ascontiguousarray(plain_light, np.float32).reshape(128))
         return len(self.lights) - 1
+
+    def add_cylinder_light(self, matrix, radius, height, angle_deg, intensity):
+        """Cylinder light (CylinderLight + CreateCylinderLightFromXmlNode + Transform, PlainLightConverter.cpp:353-413, 867-893) with the 2x2
+        uniform pdf table RenderDriverRTE::UpdatePdfTablesForLight builds for an untextured one (RenderDriverRTE.cpp:940-941)."""
+        from . import materials as M
+        f = np.float32
+        mtx = np.asarray(matrix, np.float32).reshape(4, 4)
+        z_min, z_max = f(-0.5)*f(height), f(0.5)*f(height)
+        phi_max = f(f(np.pi/180.0)*f(angle_deg))
+        L = M.point_light(tuple(mtx[:3, 3]), intensity)
+        Li = L.view(np.int32)
+        Li[C["PLIGHT_TYPE"]] = C["PLAIN_LIGHT_TYPE_CYLINDER"]
+        L[16:25] = mtx[:3, :3].reshape(9)                                  # CYLINDER_LIGHT_MATRIX_E00.., rows
+        L[25], L[26], L[27], L[28] = radius, z_min, z_max, phi_max
+        Li[29], Li[30] = INVALID_TEXTURE, INVALID_TEXTURE                  # CYLINDER_TEX_ID / TEXMATRIX_ID
+        Li[31] = self.add_sky_pdf_table()                                  # CYLINDER_PDF_TABLE_ID: the same 2x2 table of 0.25 a sky without a map gets
+        d = f(1.0)/np.sqrt(f(3.0), dtype=f)
+        vert = mtx[:3, :3] @ np.array([d, d, d], f)                        # mul(mrot, normalize(float3(1,1,1)))
+        mult = np.sqrt((vert*vert).sum(dtype=f), dtype=f)
+        L[C["PLIGHT_SURFACE_AREA"]] = f(f(f(f(z_max - z_min)*mult)*f(f(radius)*mult))*phi_max)
+        return self.add_light(L)
 
     def add_mesh_light(self, mesh_id, matrix, intensity):
         """Mesh light (MeshLight + Transform, PlainLightConverter.cpp:724-830): the light samples the triangles of `mesh_id` by area.  A copy of

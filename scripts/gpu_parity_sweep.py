@@ -19,7 +19,7 @@ P = int(os.environ.get("PASSES", "8"))
 mk_all = {"cornell": lambda: scenes.cornell(W, H, two_lights=True, dof=True), "orennayar": lambda: scenes.cornell_orennayar(W, H),
       "sphere_point": lambda: scenes.cornell_sphere_and_point_lights(W, H), "spot_direct": lambda: scenes.cornell_spot_and_direct_lights(W, H, True),
       "translucent_thin_glass": lambda: scenes.cornell_translucent(W, H), "normal_maps": lambda: scenes.cornell_normal_mapped(W, H),
-      "remap": lambda: scenes.cornell_remap_lists(W, H), "mesh_light": lambda: scenes.cornell_mesh_light(W, H), "cutout": lambda: scenes.cornell_with_cutout(W, H),
+      "remap": lambda: scenes.cornell_remap_lists(W, H), "mesh_light": lambda: scenes.cornell_mesh_light(W, H), "cylinder_light": lambda: scenes.cornell_cylinder_light(W, H, True), "cutout": lambda: scenes.cornell_with_cutout(W, H),
       "sky": lambda: scenes.open_box_under_sky(W, H, True), "sky_env": lambda: scenes.open_box_under_sky(W, H, False, env_map=True),
       "instanced": lambda: scenes.instanced_geometry(W, H, dof=True)}
 mk = {k: v for k, v in mk_all.items() if not os.environ.get("ONLY") or k in os.environ["ONLY"].split(",")}

@@ -277,6 +277,28 @@ def cornell_mesh_light(width=96, height=96):
     return scn.build()
 
 
+def cornell_cylinder_light(width=96, height=96, second_table=False):
+    """The Cornell room lit by a CYLINDER light (a tilted three-quarter tube with its emissive mesh).  second_table: another pdf table comes
+    first, so that the light's table id is positive and the 2D-table branch of CylinderLightSamplePos runs instead of the uniform one."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    ggxm = scn.add_material(M.ggx((0.8, 0.6, 0.2), 0.7))
+    emi0 = scn.add_material(M.emissive((14.0, 12.0, 9.0), 0))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, white, white, white), inward=True, skip_faces=(4,))))
+    sph = S.sphere_mesh(1.0, 16, 8)
+    scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, ggxm, np.int32))), S.translate(-2.0, -2.8, -1.0) @ S.scale(1.2, 1.2, 1.2))
+    if second_table:
+        scn.add_sky_pdf_table()
+    mtx = S.translate(0.5, 1.5, 0.0) @ S.rotate_x(1.1) @ S.rotate_y(0.4)
+    l0 = scn.add_cylinder_light(mtx, 0.4, 3.0, 270.0, (14.0, 12.0, 9.0))
+    scn.add_instance(scn.add_mesh(S.cylinder_mesh(0.4, 3.0, 24, phi_max=np.radians(270.0), mat_id=emi0)), mtx, light_id=l0)
+    return scn.build()
+
+
 def cornell_with_cutout(width=96, height=96):
     """The Cornell room with two instances of a quad whose material has an opacity (cut-out) map - a checker of opaque and transparent
     cells, bilinear and point sampled - in front of the back wall and above the floor: the quads go into the alpha-tested tree 1, rays
