@@ -21,7 +21,7 @@ mk_all = {"cornell": lambda: scenes.cornell(W, H, two_lights=True, dof=True), "o
       "translucent_thin_glass": lambda: scenes.cornell_translucent(W, H), "normal_maps": lambda: scenes.cornell_normal_mapped(W, H),
       "remap": lambda: scenes.cornell_remap_lists(W, H), "mesh_light": lambda: scenes.cornell_mesh_light(W, H), "cylinder_light": lambda: scenes.cornell_cylinder_light(W, H, True), "cutout": lambda: scenes.cornell_with_cutout(W, H),
       "sky": lambda: scenes.open_box_under_sky(W, H, True), "sky_env": lambda: scenes.open_box_under_sky(W, H, False, env_map=True),
-      "instanced": lambda: scenes.instanced_geometry(W, H, dof=True)}
+      }          # (tests/scenes.instanced_geometry is a ray-casting scene with a placeholder material: not path traced)
 mk = {k: v for k, v in mk_all.items() if not os.environ.get("ONLY") or k in os.environ["ONLY"].split(",")}
 fx = os.path.join(ROOT, "tests", "golden", "hydra_scenes.npz")
 for n in (HS.fixture_scenes(fx) if not os.environ.get("ONLY") else []):
