@@ -20,7 +20,8 @@ class hc_stats(ct.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libhydracore_b200.so")
+    # HC_LIB: another build of the same library (kernel experiments under scripts/), never a different implementation
+    return os.environ.get("HC_LIB") or os.path.join(_HERE, "libhydracore_b200.so")
 
 
 _P, _I, _I64, _U64 = ct.c_void_p, ct.c_int, ct.c_int64, ct.c_uint64

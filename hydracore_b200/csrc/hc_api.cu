@@ -2,6 +2,7 @@
 // (Path tracing entry points live in hc_path.cu.)  Reference interfaces replaced are cited in include/hydracore_cuda.h.
 #include "hc_context.h"
 #include "hc_trace.cuh"
+#include "hc_trace2.cuh"
 #include "hc_raygen.cuh"
 
 #include <cmath>
@@ -170,6 +171,156 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
   }
 }
 
+
+// K2 / K2s, second generation (hc_trace2.cuh): centre / half-extent quads fetched by 256-bit loads, one postponed leaf per lane, instance exit
+// as a stack marker, chunked ray supply with the next chunk claimed and prefetched one switch ahead.  Same template parameters as k_trace.
+//   qBias: a quad step is run while  4 * (lanes at an interior quad) >= qBias * (lanes that can only go on with a leaf step)
+#ifndef HC_TRACE2_MINB
+#define HC_TRACE2_MINB 7
+#endif
+template<bool ANYHIT, int TREE1 = 0, int RAYGEN = 0>
+__global__ void __launch_bounds__(HC_TRACE_BLOCK, HC_TRACE2_MINB)
+k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long nArg,
+         const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned* __restrict__ counter, const int refillMin, const int qBias,
+         const int tileW, const HcRayGen gen = HcRayGen())
+{
+  const unsigned n = (unsigned)(nDev ? (long long)(*nDev) : nArg);      // the path tracer keeps its live-path count on the device
+  uint2 stk[HC_STACK_CAP];                                              // {child word, entry distance}
+
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned ltMask = (1u << lane) - 1u;
+
+  // ray supply: `cur` = next unclaimed index of this warp's chunk (a chunk ends at a multiple of 32), `nxt` = base of the chunk after it,
+  // `fut` (lane 0) = atomicAdd result for the chunk after that, in flight
+  unsigned cur, nxt, fut = 0;
+  {
+    unsigned b = 0;
+    if (lane == 0) b = atomicAdd(counter, 96u);
+    b = __shfl_sync(FULL, b, 0);
+    cur = b; nxt = b + 32u; fut = b + 64u;
+  }
+  bool idle = true;
+  unsigned rayIdx = 0;
+  HcRay2 r;
+  Trav2Start(r, f3(0, 0, 0), f3(0, 0, 1), 0.0f);
+  r.node = HC_NODE_SENTINEL;
+
+  for (;;)
+  {
+    const unsigned idleMask = __ballot_sync(FULL, idle);
+    const bool exhausted = (cur >= n);
+    if (idleMask != 0u && !exhausted && (__popc(idleMask) >= refillMin || idleMask == FULL))
+    {
+      const unsigned nIdle = (unsigned)__popc(idleMask), avail = 32u - (cur & 31u);
+      const unsigned rank = (unsigned)__popc(idleMask & ltMask);
+      unsigned idx = (rank < avail) ? cur + rank : nxt + (rank - avail);
+      if (nIdle >= avail)
+      {
+        // chunk switch: the next chunk becomes current, the one claimed a switch ago becomes next, a new one is claimed (its result is
+        // not needed before the next switch), and the rays of the new `nxt` are prefetched
+        cur = nxt + (nIdle - avail);
+        nxt = __shfl_sync(FULL, fut, 0);
+        if (lane == 0) fut = atomicAdd(counter, 32u);
+        if (RAYGEN == 0 && nxt + lane < n && tileW == 0)
+        {
+          asm volatile("prefetch.global.L1 [%0];" :: "l"(rpos + size_t(nxt + lane)*stride));
+          asm volatile("prefetch.global.L1 [%0];" :: "l"(rdir + size_t(nxt + lane)*stride));
+        }
+      }
+      else cur += nIdle;
+      if (idle && idx < n)
+      {
+        if (tileW > 0)
+        {
+          // the ray stream is a W x H image in row-major order: fetch it in 8 x 4 pixel blocks, so that a warp's 32 rays cover a
+          // compact screen patch (fewer distinct BVH nodes per warp, more uniform traversal lengths) instead of a 32 x 1 strip
+          const unsigned blk = idx >> 5, w = idx & 31u, bpr = (unsigned)tileW >> 3;
+          idx = ((blk/bpr)*4u + (w >> 3))*(unsigned)tileW + (blk % bpr)*8u + (w & 7u);
+        }
+        float4 p, dd;
+        if (RAYGEN == 0) { p = __ldg(rpos + size_t(idx)*stride); dd = __ldg(rdir + size_t(idx)*stride); }
+        else
+        {
+          const long long pix = (long long)idx + gen.firstPixel;                  // launches may cover a band of the image
+          float3 eo, ed;
+          MakeRandEyeRay(int(pix % gen.width), int(pix / gen.width), gen.width, gen.height, make_float4(0.0f, 0.0f, 0.0f, 0.0f), gen.cam, eo, ed);
+          p = make_float4(eo.x, eo.y, eo.z, 0.0f); dd = make_float4(ed.x, ed.y, ed.z, HC_MAXFLOAT_RAY);
+          if (RAYGEN == 2)
+          {
+            const HcHit h = gen.hitsIn[pix];
+            p = make_float4(0, 0, 0, 0); dd = make_float4(0, 1, 0, 0);             // t_far = 0: "no shadow ray" for pixels that hit nothing
+            if (h.primId != -1)
+            {
+              const float3 pos = eo + ed*h.t;
+              const float3 sdir = normalize(gen.light - pos);
+              const float eps = fmaxf(fmaxf(fabsf(pos.x), fmaxf(fabsf(pos.y), fabsf(pos.z))), 1.0f)*1e-4f;
+              const float3 spos = pos + sdir*eps;
+              p = make_float4(spos.x, spos.y, spos.z, 0.0f);
+              dd = make_float4(sdir.x, sdir.y, sdir.z, length(spos - gen.light)*0.995f);
+            }
+          }
+        }
+        rayIdx = idx; idle = false;
+        Trav2Start(r, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
+        if (TREE1 != 0)
+        {
+          const float4 h = reinterpret_cast<const float4*>(hitsOut)[idx];      // Lite_Hit carried from tree to tree
+          r.t = h.x; r.primId = __float_as_int(h.y); r.hitInst = __float_as_int(h.z); r.geomId = __float_as_int(h.w);
+        }
+        if (ANYHIT && !(dd.w > 0.0f)) { visOut[idx] = 1; idle = true; r.node = HC_NODE_SENTINEL; }          // maxDist <= 0: lit (trace.cl:343-351)
+        else if (!RayIsFinite(r.o, r.d)) r.node = HC_NODE_SENTINEL;              // every comparison of the reference fails on NaN: no hit
+      }
+    }
+    if (__all_sync(FULL, idle)) { if (cur >= n) break; else continue; }
+
+    // Scheduling.  A lane is at an interior quad (Q), or it needs a leaf step (L: a parked triangle leaf to test, an instance to enter or to
+    // leave), or both (at a quad with a parked leaf), or it is finished.  Quad steps run while the lanes at a quad outnumber (qBias / 4 x) the
+    // lanes that can only go on with a leaf step; a leaf step serves every lane that has leaf work.
+    for (;;)
+    {
+      const bool wantQ = !(r.node & HC_LEAF_BIT);                                  // a finished / idle lane carries the sentinel (leaf bit set)
+      const bool hasL  = (r.pend != HC_PEND_EMPTY) || (!wantQ && r.node != HC_NODE_SENTINEL);
+      const unsigned mQ = __ballot_sync(FULL, wantQ), mL = __ballot_sync(FULL, hasL);
+      const int busy = __popc(mQ | mL);
+      if (busy == 0 || (cur < n && busy <= 32 - refillMin)) break;            // all done, or enough idle lanes for a refill
+      const bool inInst = (r.instId >= 0);
+      if (mQ != 0u && 4*__popc(mQ) >= qBias*__popc(mL & ~mQ))
+      {
+        if (wantQ) HC_QUAD2(r, bvh, stk, inInst)
+      }
+      else if (hasL)
+      {
+        if (r.pend == HC_PEND_EMPTY)                                               // resolve the leaf-class node word first
+        {
+          bool pop = true;
+          if (r.node == HC_EXIT_MARK) HC_EXIT2(r, stk)
+          else if (!inInst) { HC_ENTER2(r, bvh, stk) pop = false; }
+          else r.pend = r.node;
+          const bool inInst2 = (r.instId >= 0);
+          if (pop) HC_POP2(r, stk, inInst2)
+        }
+        if (r.pend != HC_PEND_EMPTY)
+        {
+          // IntersectAllPrimitivesInLeaf, ONE pair record per step; the leaf word is the cursor (index up, count down)
+          const size_t pairIndex = size_t(r.pend & HC_LEAF_INDEX_MASK);
+          const bool last = ((r.pend >> HC_LEAF_PAIRS_SHIFT) & 63u) == 0u;
+          r.pend = last ? HC_PEND_EMPTY : (r.pend - (1u << HC_LEAF_PAIRS_SHIFT) + 1u);
+          const bool found = PairTest2<TREE1 == 2>(r, bvh, pairIndex);
+          if (ANYHIT && found) { r.node = HC_NODE_SENTINEL; r.pend = HC_PEND_EMPTY; r.sp = 0; }
+        }
+      }
+    }
+
+    if (!idle && r.node == HC_NODE_SENTINEL && r.pend == HC_PEND_EMPTY)
+    {
+      if (ANYHIT) visOut[rayIdx] = (r.primId != -1) ? 0 : 1;
+      else reinterpret_cast<float4*>(hitsOut)[rayIdx] = make_float4(r.t, __int_as_float(r.primId), __int_as_float(r.hitInst), __int_as_float(r.geomId));
+      idle = true;
+    }
+  }
+}
+
 // shadow rays from closest hits toward one point light (ray-casting benchmark / debug path of the LightSample stage)
 static __global__ void k_make_shadow_rays(const float4* __restrict__ rays, const HcHit* __restrict__ hits, const long long n, const float3 L, float4* __restrict__ out)
 {
@@ -200,6 +351,26 @@ static int TraceGrid(hc_ctx* ctx)
   ctx->traceGrid = ctx->smCount*perSM;           // a whole number of waves: persistent CTAs, all resident
   return ctx->traceGrid;
 }
+static int TraceGrid2(hc_ctx* ctx)
+{
+  if (ctx->traceGrid2 > 0) return ctx->traceGrid2;
+  int perSM = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace2<false>, HC_TRACE_BLOCK, 0);
+  if (perSM < 1) perSM = 1;
+  ctx->traceGrid2 = ctx->smCount*perSM;
+  return ctx->traceGrid2;
+}
+#define HC_REFILL2_MIN 8       // k_trace2: a refill costs no memory round trip (chunk claimed and prefetched ahead)
+#define HC_QBIAS2      4       // quad steps while lanes at a quad >= lanes that can only do a leaf step
+
+// one persistent-thread ray counter per launch in flight: rotate through the counter block so that back-to-back launches never share one
+static int NextCounter(hc_ctx* ctx, cudaStream_t stream, unsigned long long** out)
+{
+  ctx->traceCounterSlot = (ctx->traceCounterSlot + 1) % 32;
+  *out = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
+  HC_CUDA(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream));
+  return HC_OK;
+}
 
 // launch K2 (closest) or K2s (any-hit) on device-resident streams; used by hc_trace_* and by the path tracer
 static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW = 0, cudaStream_t stream = nullptr);
@@ -213,15 +384,24 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   if (!stream) stream = ctx->stream;
   HC_REQUIRE(ctx->bvhNodes.ptr && ctx->bvhTris.ptr, HC_E_STATE, "hc_trace: no BVH uploaded (hc_set_bvh)");
   HC_REQUIRE(ctx->haveInst != 0, HC_E_STATE, "hc_trace: only the two-level (instanced) layout is supported");
-  HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr;
-  // one persistent-thread ray counter per launch in flight: rotate through the counter block so that back-to-back launches never share one
-  ctx->traceCounterSlot = (ctx->traceCounterSlot + 1) % 32;
-  unsigned long long* counter = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
-  HC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
-  const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
-  static int rf = 0; if (rf == 0) { const char* e = getenv("HC_TRACE_REFILL"); rf = e ? atoi(e) : HC_REFILL_MIN; if (rf < 1 || rf > 32) rf = HC_REFILL_MIN; }
-  if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf, tileW);
-  else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, tileW);
+  HC_REQUIRE(n < 0xffff0000ll, HC_E_ARG, "hc_trace: more than 2^32 rays in one launch");
+  const bool v2 = (ctx->traceImpl == 2);
+  HcBvh bvh; bvh.nodes = (const float4*)(v2 ? ctx->bvhNodesCH.ptr : ctx->bvhNodes.ptr); bvh.tris = (const float4*)ctx->bvhTris.ptr;
+  unsigned long long* counter = nullptr;
+  int rc = NextCounter(ctx, stream, &counter); if (rc) return rc;
+  const int grid = (int)std::min<long long>(v2 ? TraceGrid2(ctx) : TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
+  const int rf = ctx->traceRefill > 0 ? ctx->traceRefill : (v2 ? HC_REFILL2_MIN : HC_REFILL_MIN);
+  const int qb = ctx->traceQBias > 0 ? ctx->traceQBias : HC_QBIAS2;
+  if (v2)
+  {
+    if (anyHit) k_trace2<true><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, (unsigned*)counter, rf, qb, tileW);
+    else        k_trace2<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, (unsigned*)counter, rf, qb, tileW);
+  }
+  else
+  {
+    if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf, tileW);
+    else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, tileW);
+  }
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   if (!anyHit && ctx->haveTree1)
@@ -229,20 +409,27 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
     // IntegratorCommon::rayTrace walks the trees one after another with the hit carried along (CPUExp_Integrators_Common.cpp:131-147);
     // its shadowTrace looks at tree 0 only (:163-171), so the any-hit launch above is all a shadow ray gets - meshes with opacity maps
     // cast no shadows in the CPU integrators, and none here
-    HcBvh b1; b1.nodes = (const float4*)ctx->bvh1Nodes.ptr; b1.tris = (const float4*)ctx->bvh1Tris.ptr;
-    ctx->traceCounterSlot = (ctx->traceCounterSlot + 1) % 32;
-    unsigned long long* counter1 = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
-    HC_CUDA(cudaMemsetAsync(counter1, 0, sizeof(unsigned long long), stream));
+    HcBvh b1; b1.nodes = (const float4*)(v2 ? ctx->bvh1NodesCH.ptr : ctx->bvh1Nodes.ptr); b1.tris = (const float4*)ctx->bvh1Tris.ptr;
+    unsigned long long* counter1 = nullptr;
+    rc = NextCounter(ctx, stream, &counter1); if (rc) return rc;
+    const int alpha = ctx->haveAlpha1 ? 2 : 1;
     if (ctx->haveAlpha1)
     {
       int texTab = 0; memcpy(&texTab, ctx->globalsHead.data() + HC_EG_texturesTableOffset, 4);
       HC_REQUIRE(ctx->globals.ptr && ctx->storage[HC_STORAGE_TEXTURES].ptr, HC_E_STATE, "hc_trace: the alpha-tested tree needs the textures storage and the globals (texture table)");
       b1.alphaPairs = (const uint4*)ctx->bvh1AlphaPairs.ptr; b1.alphaTable = (const uint2*)ctx->bvh1AlphaTable.ptr;
       b1.textures = (const int4*)ctx->storage[HC_STORAGE_TEXTURES].ptr; b1.texturesTable = (const int*)ctx->globals.ptr + texTab;
-      k_trace<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, tileW);
+    }
+    if (v2)
+    {
+      if (alpha == 2) k_trace2<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, (unsigned*)counter1, rf, qb, tileW);
+      else            k_trace2<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, (unsigned*)counter1, rf, qb, tileW);
     }
     else
-      k_trace<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, tileW);
+    {
+      if (alpha == 2) k_trace<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, tileW);
+      else            k_trace<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, tileW);
+    }
     HC_CUDA(cudaGetLastError());
     ctx->stats.kernelLaunches++;
   }
@@ -256,13 +443,23 @@ static int LaunchTraceGen(hc_ctx* ctx, bool shadow, long long n, HcHit* hitsLoca
 {
   if (n <= 0) return HC_OK;
   cudaStream_t stream = ctx->stream;
-  HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr;
-  ctx->traceCounterSlot = (ctx->traceCounterSlot + 1) % 32;
-  unsigned long long* counter = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
-  HC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
-  const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
-  if (shadow) k_trace<true, 0, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, nullptr, vis, counter, HC_REFILL_MIN, tileW, gen);
-  else        k_trace<false, 0, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, hitsLocal, nullptr, counter, HC_REFILL_MIN, tileW, gen);
+  const bool v2 = (ctx->traceImpl == 2);
+  HcBvh bvh; bvh.nodes = (const float4*)(v2 ? ctx->bvhNodesCH.ptr : ctx->bvhNodes.ptr); bvh.tris = (const float4*)ctx->bvhTris.ptr;
+  unsigned long long* counter = nullptr;
+  int rc = NextCounter(ctx, stream, &counter); if (rc) return rc;
+  const int grid = (int)std::min<long long>(v2 ? TraceGrid2(ctx) : TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
+  const int rf = ctx->traceRefill > 0 ? ctx->traceRefill : (v2 ? HC_REFILL2_MIN : HC_REFILL_MIN);
+  const int qb = ctx->traceQBias > 0 ? ctx->traceQBias : HC_QBIAS2;
+  if (v2)
+  {
+    if (shadow) k_trace2<true, 0, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, nullptr, vis, (unsigned*)counter, rf, qb, tileW, gen);
+    else        k_trace2<false, 0, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, hitsLocal, nullptr, (unsigned*)counter, rf, qb, tileW, gen);
+  }
+  else
+  {
+    if (shadow) k_trace<true, 0, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, nullptr, vis, counter, rf, tileW, gen);
+    else        k_trace<false, 0, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, hitsLocal, nullptr, counter, rf, tileW, gen);
+  }
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   if (shadow) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n;
@@ -278,15 +475,32 @@ static int LaunchTraceGen(hc_ctx* ctx, bool shadow, long long n, HcHit* hitsLoca
 //                     E2z0 E2z1 prim0 prim1 | geom0 geom1 0 0} with E1 = B - A, E2 = C - A evaluated in float exactly as
 //                     IntersectAllPrimitivesInLeaf does (ctrace.h:159-160); an odd leaf is padded with a zero triangle, whose
 //                     determinant is 0 -> v = u = t = NaN -> every acceptance test fails.
+// centre / half-extent of one child slab for the second-generation quads (hc_trace2.cuh): [c - h, c + h] contains [lo, hi] in exact
+// arithmetic, h rounded up and inflated by 2^-21 (covers the rounding of h*|1/d| and of the centre distance in the kernel)
+static inline void CentreHalf(float lo, float hi, float* c, float* h)
+{
+  const double cd = 0.5*(double(lo) + double(hi));
+  float cf = float(cd);
+  if (!std::isfinite(cf)) cf = 0.0f;
+  double hd = std::max(double(hi) - double(cf), double(cf) - double(lo));
+  if (!(hd >= 0.0)) hd = 0.0;
+  hd *= (1.0 + 1.0/2097152.0);
+  float hf = float(hd);
+  if (double(hf) < hd) hf = std::nextafterf(hf, std::numeric_limits<float>::infinity());
+  *c = cf; *h = hf;
+}
+
 static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const float* trif4, int trif4Num,
                                std::vector<float>& outNodes, std::vector<float>& outPairs, int* outStackBound,
-                               const unsigned* alphaU2 = nullptr, int alphaNum = 0, std::vector<unsigned>* outAlphaPairs = nullptr)
+                               const unsigned* alphaU2 = nullptr, int alphaNum = 0, std::vector<unsigned>* outAlphaPairs = nullptr,
+                               std::vector<float>* outNodesCH = nullptr)
 {
   struct N { float bmin[3]; unsigned lo; float bmax[3]; unsigned esc; };
   const N* nd = (const N*)nodes;
   const int quads = nodesNum/4;
   if (quads < 2) return HC_E_ARG;
   outNodes.assign(size_t(quads)*32, 0.0f);
+  if (outNodesCH) outNodesCH->assign(size_t(quads)*32, 0.0f);
   outPairs.clear();
   outPairs.reserve(size_t(trif4Num)*4 + 64);
   std::vector<unsigned> leafWord(size_t(trif4Num), 0u);     // float4 offset of a leaf header -> converted child word (0 = not yet)
@@ -345,6 +559,7 @@ static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const f
     if (seen[it.quad]) continue;     // shared mesh sub-trees: depth of first visit is representative
     seen[it.quad] = 1;
     float* Q = outNodes.data() + size_t(it.quad)*32;
+    float* Q2 = outNodesCH ? outNodesCH->data() + size_t(it.quad)*32 : nullptr;       // rows {cx[4] hx[4]} {cy[4] hy[4]} {cz[4] hz[4]} {child words, spare}
     unsigned words[4];
     for (int i = 0; i < 4; i++)
     {
@@ -352,9 +567,11 @@ static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const f
       if (c.lo == 0xffffffffu && c.esc == 0xffffffffu)        // IsValidNode (cglobals.h:1321): an x slab at +inf fails for every finite ray
       {
         Q[0 + i] = INF; Q[4 + i] = INF; words[i] = HC_NODE_SENTINEL;
+        if (Q2) for (int a = 0; a < 3; a++) { Q2[8*a + i] = 0.0f; Q2[8*a + 4 + i] = -8.0e37f; }      // negative half-extent: far < near on every axis, never visited
         continue;
       }
       Q[0 + i] = c.bmin[0]; Q[4 + i] = c.bmax[0]; Q[8 + i] = c.bmin[1]; Q[12 + i] = c.bmax[1]; Q[16 + i] = c.bmin[2]; Q[20 + i] = c.bmax[2];
+      if (Q2) for (int a = 0; a < 3; a++) CentreHalf(c.bmin[a], c.bmax[a], &Q2[8*a + i], &Q2[8*a + 4 + i]);
       const unsigned off = c.lo & 0x7fffffffu;
       if (c.lo & 0x80000000u)
       {
@@ -372,14 +589,16 @@ static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const f
           else { subWord = sub; st.push_back({ sub, 1, true }); }
           memcpy(R + 16, &subWord, 4);
           memcpy(R + 17, (const float*)rec + 24, 8);           // {realInstId, meshId}: float4 8Q+6 .xy
+          if (outNodesCH) memcpy(outNodesCH->data() + size_t(off)*32, R, 128);
         }
         else { int rc = convertLeaf(off, &words[i]); if (rc) return rc; }
       }
       else { words[i] = off; st.push_back({ off, it.depth + 1, it.inst }); }
     }
     memcpy(Q + 24, words, 16);
+    if (Q2) memcpy(Q2 + 24, words, 16);
   }
-  *outStackBound = 3*(maxTop + maxMesh) + 2;
+  *outStackBound = 3*(maxTop + maxMesh) + 2 + 4;            // + the exit marker and the saved world-space ray (hc_trace2.cuh)
   return HC_OK;
 }
 
@@ -422,6 +641,9 @@ int hc_ctx_create(int device, hc_ctx** out)
   if (rc != HC_OK) { delete c; return rc; }
   HC_CUDA(cudaMemsetAsync(c->counters.ptr, 0, c->counters.bytes, c->stream));
   c->globalsHead.assign(HC_EG_HEAD_BYTES, 0);
+  if (const char* e = getenv("HC_TRACE_IMPL")) { const int v = atoi(e); if (v == 1 || v == 2) c->traceImpl = v; }
+  if (const char* e = getenv("HC_TRACE_REFILL")) { const int v = atoi(e); if (v >= 1 && v <= 32) c->traceRefill = v; }
+  if (const char* e = getenv("HC_TRACE_QBIAS")) { const int v = atoi(e); if (v >= 1 && v <= 64) c->traceQBias = v; }
   *out = c;
   return HC_OK;
 }
@@ -433,7 +655,7 @@ void hc_ctx_destroy(hc_ctx* c)
   cudaStreamSynchronize(c->stream);
   hc_path_free(c);
   for (int i = 0; i < HC_STORAGE_COUNT; i++) hc_buf_free(c->storage[i]);
-  hc_buf_free(c->globals); hc_buf_free(c->bvhNodes); hc_buf_free(c->bvhTris); hc_buf_free(c->bvh1Nodes); hc_buf_free(c->bvh1Tris); hc_buf_free(c->bvh1AlphaPairs); hc_buf_free(c->bvh1AlphaTable); hc_buf_free(c->remapLists); hc_buf_free(c->remapTable); hc_buf_free(c->remapInst); hc_buf_free(c->instMatrices); hc_buf_free(c->instLightIds);
+  hc_buf_free(c->globals); hc_buf_free(c->bvhNodes); hc_buf_free(c->bvhTris); hc_buf_free(c->bvhNodesCH); hc_buf_free(c->bvh1NodesCH); hc_buf_free(c->bvh1Nodes); hc_buf_free(c->bvh1Tris); hc_buf_free(c->bvh1AlphaPairs); hc_buf_free(c->bvh1AlphaTable); hc_buf_free(c->remapLists); hc_buf_free(c->remapTable); hc_buf_free(c->remapInst); hc_buf_free(c->instMatrices); hc_buf_free(c->instLightIds);
   hc_buf_free(c->fbSum); hc_buf_free(c->scratchRays); hc_buf_free(c->scratchOut); hc_buf_free(c->counters); hc_buf_free(c->pixelRng); hc_buf_free(c->qmcTable);
   hc_buf_free(c->rcRays); hc_buf_free(c->rcHits); hc_buf_free(c->rcSRays); hc_buf_free(c->rcVis);
   for (int i = 0; i < 5; i++) cudaEventDestroy(c->evStage[i]);
@@ -514,18 +736,21 @@ static int SetBvhTree(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, 
   HC_REQUIRE(haveInst != 0, HC_E_ARG, "hc_set_bvh: single-level trees (bvhType \"triangle4v\") are not supported, pass the two-level layout");
   HC_REQUIRE(alphaTable == nullptr || alphaNum >= trif4Num, HC_E_ARG, "hc_set_bvh_alpha: the alpha table must cover every float4 of the triangle list");
   int bound = 0;
-  std::vector<float> devNodes, devPairs;
+  std::vector<float> devNodes, devPairs, devNodesCH;
   std::vector<unsigned> devAlpha;
   int rc = ConvertBvhForDevice((const unsigned char*)nodes, nodesNum, (const float*)trif4, trif4Num, devNodes, devPairs, &bound,
-                               (const unsigned*)alphaTable, alphaNum, alphaTable ? &devAlpha : nullptr);
+                               (const unsigned*)alphaTable, alphaNum, alphaTable ? &devAlpha : nullptr, &devNodesCH);
   HC_REQUIRE(rc == HC_OK, rc, "hc_set_bvh: tree references nodes or triangles out of range (or a leaf holds more than 128 triangles)");
   HC_REQUIRE(bound <= HC_STACK_CAP, HC_E_RANGE, "hc_set_bvh: tree too deep for the traversal stack");
   HC_CUDA(cudaSetDevice(ctx->device));
   HcDevBuf& bn = treeId ? ctx->bvh1Nodes : ctx->bvhNodes;
   HcDevBuf& bt = treeId ? ctx->bvh1Tris : ctx->bvhTris;
+  HcDevBuf& bc = treeId ? ctx->bvh1NodesCH : ctx->bvhNodesCH;
   rc = hc_buf_reserve(ctx, bn, devNodes.size()*4); if (rc) return rc;
-  rc = hc_buf_reserve(ctx, bt, std::max<size_t>(devPairs.size()*4, 16)); if (rc) return rc;
+  rc = hc_buf_reserve(ctx, bc, devNodesCH.size()*4); if (rc) return rc;
+  rc = hc_buf_reserve(ctx, bt, std::max<size_t>(devPairs.size()*4, 96)); if (rc) return rc;
   HC_CUDA(cudaMemcpyAsync(bn.ptr, devNodes.data(), devNodes.size()*4, cudaMemcpyHostToDevice, ctx->stream));
+  HC_CUDA(cudaMemcpyAsync(bc.ptr, devNodesCH.data(), devNodesCH.size()*4, cudaMemcpyHostToDevice, ctx->stream));
   if (!devPairs.empty()) HC_CUDA(cudaMemcpyAsync(bt.ptr, devPairs.data(), devPairs.size()*4, cudaMemcpyHostToDevice, ctx->stream));
   if (treeId == 1)
   {

@@ -95,22 +95,39 @@ def test_bvh_builder_against_brute_force(built, oracle):
 
 def test_packed_fp32_is_not_contracted(built):
     """Bit-parity guard for the traversal kernels: ptxas contracts mul.rn.f32x2 + add/sub.rn.f32x2 into FFMA2, which rounds once
-    instead of twice.  hc_trace.cuh writes every difference of products as fma(b, -1, a); any FFMA2 in the shipped SASS whose
-    multiplier is not the immediate -1 means a packed multiply-add was fused behind our back."""
+    instead of twice.  The triangle test (hc_trace.cuh / hc_trace2.cuh) writes every difference of products as fma(b, -1, a); an FFMA2
+    whose multiplier is not the immediate -1 means a packed multiply-add was fused behind our back.  The only other FFMA2 allowed are
+    the twelve of the conservative box test of k_trace2 (near / far = tc -/+ h*|1/d|, written as fma in the source)."""
+    import re
     import shutil
     import subprocess
     from hydracore_b200 import _lib
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
-    sass = subprocess.run([cuobjdump, "-sass", "-fun", "k_trace", _lib.lib_path()], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
-    if "FMUL2" not in sass:       # older cuobjdump builds cannot filter by template name: dump everything
-        sass = subprocess.run([cuobjdump, "-sass", _lib.lib_path()], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
-    lines = [ln for ln in sass.splitlines() if " FFMA2 " in ln]
-    assert "FMUL2" in sass and "FADD2" in sass and "FMNMX3" in sass, "the traversal kernel is expected to use packed FP32 and 3-input min/max"
-    assert lines, "expected FFMA2 (a - b as fma(b, -1, a)) in the traversal kernel"
-    bad = [ln.strip() for ln in lines if ", -1, " not in ln]
-    assert not bad, "contracted packed multiply-add found:\n" + "\n".join(bad[:5])
+    sass = subprocess.run([cuobjdump, "-sass", _lib.lib_path()], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    funcs = {}
+    cur = None
+    for ln in sass.splitlines():
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+        elif cur is not None:
+            funcs[cur].append(ln)
+    trace = {k: v for k, v in funcs.items() if "k_trace" in k}
+    assert any("k_trace2" in k for k in trace), "k_trace2 instantiations expected in the library"
+    for name, lines in trace.items():
+        text = "\n".join(lines)
+        assert "FMUL2" in text and "FADD2" in text and "FMNMX3" in text, "the traversal kernel is expected to use packed FP32 and 3-input min/max: " + name
+        ffma2 = [ln.strip() for ln in lines if " FFMA2 " in ln]
+        assert ffma2, "expected FFMA2 (a - b as fma(b, -1, a)) in " + name
+        other = [ln for ln in ffma2 if ", -1, " not in ln]
+        allowed = 12 if "k_trace2" in name else 0
+        assert len(other) == allowed, "contracted packed multiply-add in %s (%d FFMA2 without the -1 multiplier, %d expected):\n%s" % (
+            name, len(other), allowed, "\n".join(other[:5]))
+        if "k_trace2" in name:
+            assert ".256" in text, "k_trace2 is expected to fetch quads and triangle pairs by 256-bit loads: " + name
 
 
 def test_cpp_layer_library_loads_and_fails_loudly_without_device(built):
