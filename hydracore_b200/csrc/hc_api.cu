@@ -172,9 +172,8 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
 }
 
 
-// K2 / K2s, second generation (hc_trace2.cuh): centre / half-extent quads fetched by 256-bit loads, one postponed leaf per lane, instance exit
-// as a stack marker, chunked ray supply with the next chunk claimed and prefetched one switch ahead.  Same template parameters as k_trace.
-//   qBias: a quad step is run while  4 * (lanes at an interior quad) >= qBias * (lanes that can only go on with a leaf step)
+// K2 / K2s, second generation (hc_trace2.cuh): centre / half-extent quads and triangle pairs fetched by 256-bit loads, stack in shared memory,
+// chunked ray supply with the next chunk claimed and prefetched one switch ahead.  Same template parameters and control flow as k_trace.
 #ifndef HC_TRACE2_MINB
 #define HC_TRACE2_MINB 7
 #endif
@@ -185,12 +184,17 @@ k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restr
          const int tileW, const HcRayGen gen = HcRayGen())
 {
   const unsigned n = (unsigned)(nDev ? (long long)(*nDev) : nArg);      // the path tracer keeps its live-path count on the device
-  uint2 stk[HC_STACK_CAP];                                              // {child word, entry distance}
+#if HC2_SSTK > 0
+  __shared__ uint2 sstk[HC2_SSTK][HC_TRACE_BLOCK];                      // {child word, entry distance}, first HC2_SSTK entries of every ray
+#endif
+  uint2 stk[HC_STACK_CAP - HC2_SSTK];                                   // deeper entries
+  uint2 saved[5];                                                       // world-space ray while inside an instance
 
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned ltMask = (1u << lane) - 1u;
 
+#if HC2_CHUNK
   // ray supply: `cur` = next unclaimed index of this warp's chunk (a chunk ends at a multiple of 32), `nxt` = base of the chunk after it,
   // `fut` (lane 0) = atomicAdd result for the chunk after that, in flight
   unsigned cur, nxt, fut = 0;
@@ -200,18 +204,21 @@ k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restr
     b = __shfl_sync(FULL, b, 0);
     cur = b; nxt = b + 32u; fut = b + 64u;
   }
+#else
+  unsigned cur = 0;              // 0 while rays are left, n once the counter has run past the end
+#endif
   bool idle = true;
   unsigned rayIdx = 0;
   HcRay2 r;
-  Trav2Start(r, f3(0, 0, 0), f3(0, 0, 1), 0.0f);
+  Trav2Start(r, bvh, f3(0, 0, 0), f3(0, 0, 1), 0.0f);
   r.node = HC_NODE_SENTINEL;
 
   for (;;)
   {
     const unsigned idleMask = __ballot_sync(FULL, idle);
-    const bool exhausted = (cur >= n);
-    if (idleMask != 0u && !exhausted && (__popc(idleMask) >= refillMin || idleMask == FULL))
+    if (idleMask != 0u && cur < n && (__popc(idleMask) >= refillMin || idleMask == FULL))
     {
+#if HC2_CHUNK
       const unsigned nIdle = (unsigned)__popc(idleMask), avail = 32u - (cur & 31u);
       const unsigned rank = (unsigned)__popc(idleMask & ltMask);
       unsigned idx = (rank < avail) ? cur + rank : nxt + (rank - avail);
@@ -229,6 +236,14 @@ k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restr
         }
       }
       else cur += nIdle;
+#else
+      const unsigned nIdle = (unsigned)__popc(idleMask); const int leader = __ffs(idleMask) - 1;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(counter, nIdle);
+      base = __shfl_sync(FULL, base, leader);
+      unsigned idx = base + (unsigned)__popc(idleMask & ltMask);
+      if (base + nIdle >= n) cur = n;
+#endif
       if (idle && idx < n)
       {
         if (tileW > 0)
@@ -262,7 +277,7 @@ k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restr
           }
         }
         rayIdx = idx; idle = false;
-        Trav2Start(r, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
+        Trav2Start(r, bvh, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
         if (TREE1 != 0)
         {
           const float4 h = reinterpret_cast<const float4*>(hitsOut)[idx];      // Lite_Hit carried from tree to tree
@@ -274,31 +289,28 @@ k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restr
     }
     if (__all_sync(FULL, idle)) { if (cur >= n) break; else continue; }
 
-    // Scheduling.  A lane is at an interior quad (Q), or it needs a leaf step (L: a parked triangle leaf to test, an instance to enter or to
-    // leave), or both (at a quad with a parked leaf), or it is finished.  Quad steps run while the lanes at a quad outnumber (qBias / 4 x) the
-    // lanes that can only go on with a leaf step; a leaf step serves every lane that has leaf work.
+#if HC2_POSTPONE
+    // Speculative scheduling.  A lane at an interior quad can take a quad step (Q) even while it holds a parked leaf.  A lane NEEDS a leaf
+    // step (N) when it cannot go on otherwise: an instance to enter, a second leaf with one already parked, the end of the instance or of
+    // the ray with a leaf still parked.  Quad steps run until qBias lanes need a leaf step (or no lane can take a quad step); a leaf step
+    // serves every lane that holds leaf work, parked or not.
     for (;;)
     {
       const bool wantQ = !(r.node & HC_LEAF_BIT);                                  // a finished / idle lane carries the sentinel (leaf bit set)
-      const bool hasL  = (r.pend != HC_PEND_EMPTY) || (!wantQ && r.node != HC_NODE_SENTINEL);
-      const unsigned mQ = __ballot_sync(FULL, wantQ), mL = __ballot_sync(FULL, hasL);
-      const int busy = __popc(mQ | mL);
-      if (busy == 0 || (cur < n && busy <= 32 - refillMin)) break;            // all done, or enough idle lanes for a refill
-      const bool inInst = (r.instId >= 0);
-      if (mQ != 0u && 4*__popc(mQ) >= qBias*__popc(mL & ~mQ))
+      const bool needL = !wantQ && (r.node != HC_NODE_SENTINEL || r.pend != HC_PEND_EMPTY);
+      const unsigned mQ = __ballot_sync(FULL, wantQ), mN = __ballot_sync(FULL, needL);
+      const int busy = __popc(mQ | mN);
+      if (busy == 0 || (cur < n && busy <= 32 - refillMin)) break;                 // all done, or enough idle lanes for a refill
+      if (mQ != 0u && __popc(mN) < qBias)
       {
-        if (wantQ) HC_QUAD2(r, bvh, stk, inInst)
+        if (wantQ) HC_QUAD2(r, bvh, saved)
       }
-      else if (hasL)
+      else if (needL || r.pend != HC_PEND_EMPTY)
       {
-        if (r.pend == HC_PEND_EMPTY)                                               // resolve the leaf-class node word first
+        if (r.pend == HC_PEND_EMPTY)
         {
-          bool pop = true;
-          if (r.node == HC_EXIT_MARK) HC_EXIT2(r, stk)
-          else if (!inInst) { HC_ENTER2(r, bvh, stk) pop = false; }
-          else r.pend = r.node;
-          const bool inInst2 = (r.instId >= 0);
-          if (pop) HC_POP2(r, stk, inInst2)
+          if (r.instId < 0) HC_ENTER2(r, bvh, saved)                               // instance leaf of the top level
+          else { r.pend = r.node; HC_POP2(r, bvh, saved) }                         // triangle leaf with nothing parked (sub-tree root)
         }
         if (r.pend != HC_PEND_EMPTY)
         {
@@ -308,11 +320,56 @@ k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restr
           r.pend = last ? HC_PEND_EMPTY : (r.pend - (1u << HC_LEAF_PAIRS_SHIFT) + 1u);
           const bool found = PairTest2<TREE1 == 2>(r, bvh, pairIndex);
           if (ANYHIT && found) { r.node = HC_NODE_SENTINEL; r.pend = HC_PEND_EMPTY; r.sp = 0; }
+          else if (last && (r.node & HC_LEAF_BIT) && r.node != HC_NODE_SENTINEL && r.instId >= 0)
+          {
+            // the lane was waiting with a second leaf (park it now) or at the end of the instance (HC_NODE_WAIT): go on
+            if (r.node != HC_NODE_WAIT) r.pend = r.node;
+            HC_POP2(r, bvh, saved)
+          }
         }
       }
     }
 
     if (!idle && r.node == HC_NODE_SENTINEL && r.pend == HC_PEND_EMPTY)
+#else
+    // Vote scheduling: every lane is at an interior quad (Q), at a leaf (L: instance leaf or triangle-pair record) or has nothing
+    // to do.  The warp runs the step the majority is waiting for, and keeps doing so until a refill pays off.
+    for (;;)
+    {
+      bool wantQ = !(r.node & HC_LEAF_BIT);                                        // a finished / idle lane carries the sentinel (leaf bit set)
+      bool wantL = !wantQ && r.node != HC_NODE_SENTINEL;
+      unsigned mQ = __ballot_sync(FULL, wantQ), mL = __ballot_sync(FULL, wantL);
+      while (mQ != 0u && qBias*__popc(mQ) >= 2*__popc(mL))      // quad steps keep going until the leaf lanes outnumber them (qBias 4: 2 to 1)
+      {
+        if (wantQ) HC_QUAD2(r, bvh, saved)
+        wantQ = !(r.node & HC_LEAF_BIT); wantL = !wantQ && r.node != HC_NODE_SENTINEL;
+        mQ = __ballot_sync(FULL, wantQ); mL = __ballot_sync(FULL, wantL);
+      }
+      while (mL != 0u && __popc(mL) > __popc(mQ))
+      {
+        if (wantL)
+        {
+          if (r.instId < 0) HC_ENTER2(r, bvh, saved)
+          else
+          {
+            // IntersectAllPrimitivesInLeaf, ONE pair record per step; the leaf word is the cursor (index up, count down)
+            const size_t pairIndex = size_t(r.node & HC_LEAF_INDEX_MASK);
+            const bool done = ((r.node >> HC_LEAF_PAIRS_SHIFT) & 63u) == 0u;
+            r.node = r.node - (1u << HC_LEAF_PAIRS_SHIFT) + 1u;
+            const bool found = PairTest2<TREE1 == 2>(r, bvh, pairIndex);
+            if (ANYHIT && found) r.node = HC_NODE_SENTINEL;
+            else if (done) HC_POP2(r, bvh, saved)
+          }
+        }
+        wantQ = !(r.node & HC_LEAF_BIT); wantL = !wantQ && r.node != HC_NODE_SENTINEL;
+        mQ = __ballot_sync(FULL, wantQ); mL = __ballot_sync(FULL, wantL);
+      }
+      const int busy = __popc(mQ | mL);
+      if (busy == 0 || (cur < n && busy <= 32 - refillMin)) break;         // all done, or enough idle lanes for a refill
+    }
+
+    if (!idle && r.node == HC_NODE_SENTINEL)
+#endif
     {
       if (ANYHIT) visOut[rayIdx] = (r.primId != -1) ? 0 : 1;
       else reinterpret_cast<float4*>(hitsOut)[rayIdx] = make_float4(r.t, __int_as_float(r.primId), __int_as_float(r.hitInst), __int_as_float(r.geomId));
@@ -357,6 +414,7 @@ static int TraceGrid2(hc_ctx* ctx)
   int perSM = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace2<false>, HC_TRACE_BLOCK, 0);
   if (perSM < 1) perSM = 1;
+  if (const char* e = getenv("HC_TRACE_CTAS")) { const int v = atoi(e); if (v >= 1 && v < perSM) perSM = v; }      // experiments: fewer resident CTAs per SM
   ctx->traceGrid2 = ctx->smCount*perSM;
   return ctx->traceGrid2;
 }
@@ -386,7 +444,7 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   HC_REQUIRE(ctx->haveInst != 0, HC_E_STATE, "hc_trace: only the two-level (instanced) layout is supported");
   HC_REQUIRE(n < 0xffff0000ll, HC_E_ARG, "hc_trace: more than 2^32 rays in one launch");
   const bool v2 = (ctx->traceImpl == 2);
-  HcBvh bvh; bvh.nodes = (const float4*)(v2 ? ctx->bvhNodesCH.ptr : ctx->bvhNodes.ptr); bvh.tris = (const float4*)ctx->bvhTris.ptr;
+  HcBvh bvh; bvh.nodes = (const float4*)((v2 && HC2_CH) ? ctx->bvhNodesCH.ptr : ctx->bvhNodes.ptr); bvh.tris = (const float4*)ctx->bvhTris.ptr;
   unsigned long long* counter = nullptr;
   int rc = NextCounter(ctx, stream, &counter); if (rc) return rc;
   const int grid = (int)std::min<long long>(v2 ? TraceGrid2(ctx) : TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
@@ -409,7 +467,7 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
     // IntegratorCommon::rayTrace walks the trees one after another with the hit carried along (CPUExp_Integrators_Common.cpp:131-147);
     // its shadowTrace looks at tree 0 only (:163-171), so the any-hit launch above is all a shadow ray gets - meshes with opacity maps
     // cast no shadows in the CPU integrators, and none here
-    HcBvh b1; b1.nodes = (const float4*)(v2 ? ctx->bvh1NodesCH.ptr : ctx->bvh1Nodes.ptr); b1.tris = (const float4*)ctx->bvh1Tris.ptr;
+    HcBvh b1; b1.nodes = (const float4*)((v2 && HC2_CH) ? ctx->bvh1NodesCH.ptr : ctx->bvh1Nodes.ptr); b1.tris = (const float4*)ctx->bvh1Tris.ptr;
     unsigned long long* counter1 = nullptr;
     rc = NextCounter(ctx, stream, &counter1); if (rc) return rc;
     const int alpha = ctx->haveAlpha1 ? 2 : 1;
@@ -444,7 +502,7 @@ static int LaunchTraceGen(hc_ctx* ctx, bool shadow, long long n, HcHit* hitsLoca
   if (n <= 0) return HC_OK;
   cudaStream_t stream = ctx->stream;
   const bool v2 = (ctx->traceImpl == 2);
-  HcBvh bvh; bvh.nodes = (const float4*)(v2 ? ctx->bvhNodesCH.ptr : ctx->bvhNodes.ptr); bvh.tris = (const float4*)ctx->bvhTris.ptr;
+  HcBvh bvh; bvh.nodes = (const float4*)((v2 && HC2_CH) ? ctx->bvhNodesCH.ptr : ctx->bvhNodes.ptr); bvh.tris = (const float4*)ctx->bvhTris.ptr;
   unsigned long long* counter = nullptr;
   int rc = NextCounter(ctx, stream, &counter); if (rc) return rc;
   const int grid = (int)std::min<long long>(v2 ? TraceGrid2(ctx) : TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
@@ -598,7 +656,7 @@ static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const f
     memcpy(Q + 24, words, 16);
     if (Q2) memcpy(Q2 + 24, words, 16);
   }
-  *outStackBound = 3*(maxTop + maxMesh) + 2 + 4;            // + the exit marker and the saved world-space ray (hc_trace2.cuh)
+  *outStackBound = 3*(maxTop + maxMesh) + 2;
   return HC_OK;
 }
 
