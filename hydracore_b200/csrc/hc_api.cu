@@ -2,7 +2,6 @@
 // (Path tracing entry points live in hc_path.cu.)  Reference interfaces replaced are cited in include/hydracore_cuda.h.
 #include "hc_context.h"
 #include "hc_trace.cuh"
-#include "hc_trace2.cuh"
 #include "hc_raygen.cuh"
 
 #include <cmath>
@@ -38,7 +37,11 @@ void hc_buf_free(HcDevBuf& b) { if (b.ptr) cudaFree(b.ptr); b.ptr = nullptr; b.b
 
 // ------------------------------------------------------------------------------------------------------------------ kernels
 #define HC_TRACE_BLOCK 128
-#define HC_REFILL_MIN  24      // refill a warp from the global ray counter once this many lanes are idle (swept 4..32 on B200: 20-24 is best)
+#define HC_TRACE_MINB  7       // 72 registers -> 7 CTAs (28 warps) per SM.  Measured on B200 (profiles/r02_k2_variants.md): 6 / 7 / 8 CTAs per SM give
+                               // 4332 / 4278 / 4164 Mrays/s incoherent and 6676 / 6782 / 6638 shadow; throughput follows N/(N + N0) in the resident CTAs (r2g rows)
+#define HC_REFILL_MIN  24      // refill a warp from the global ray counter once this many lanes are idle (swept 4..32 on B200 in both rounds: 20-24 is best:
+                               // rays started together stay in phase, a warp refilled early runs its quad steps with fewer lanes: 16.8 instead of 19.6)
+#define HC_QBIAS       2       // quad steps while  HC_QBIAS x (lanes at a quad) >= 2 x (lanes at a leaf)   (swept 2, 3, 4, 6, 8: 2 is best by 1-2 %)
 
 // K2 / K2s.  Persistent warps: lanes that finished a ray are refilled together (one atomicAdd per refill, ranks by ballot/popc).
 // Between refills a lane runs the while-while loop of hc_trace.cuh: descend through interior quads until a leaf is reached, then
@@ -52,22 +55,23 @@ void hc_buf_free(HcDevBuf& b) { if (b.ptr) cudaFree(b.ptr); b.ptr = nullptr; b.b
 // ray and the hit record hitsIn[idx] (k_make_shadow_rays fused into K2s).  Saves two launches and 2 x 64 B per pixel of ray traffic.
 struct HcRayGen { HcCamera cam; int width, height; long long firstPixel; float3 light; const HcHit* hitsIn; };
 template<bool ANYHIT, int TREE1 = 0, int RAYGEN = 0>      // TREE1: 0 = first tree, 1 = second tree (hit carried), 2 = second tree with the alpha table
-__global__ void __launch_bounds__(HC_TRACE_BLOCK, 6)   // 80 registers -> 6 CTAs (24 warps) per SM; capping at 72 / 64 registers for 7 / 8 CTAs measured slower
+__global__ void __launch_bounds__(HC_TRACE_BLOCK, HC_TRACE_MINB)
 k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long nArg,
-        const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned long long* __restrict__ counter, const int refillMin, const int tileW,
-        const HcRayGen gen = HcRayGen())
+        const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned* __restrict__ counter, const int refillMin, const int qBias,
+        const int tileW, const HcRayGen gen = HcRayGen())
 {
-  const long long n = nDev ? (long long)(*nDev) : nArg;      // the path tracer keeps its live-path count on the device
-  uint2 stk[HC_STACK_CAP];                                    // {child word, entry distance}
+  const unsigned n = (unsigned)(nDev ? (long long)(*nDev) : nArg);      // the path tracer keeps its live-path count on the device
+  uint2 stk[HC_STACK_CAP];                                              // {child word, entry distance}
+  uint2 saved[5];                                                       // world-space ray while inside an instance
 
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned ltMask = (1u << lane) - 1u;
 
-  bool  idle = true, exhausted = false;
-  long long rayIdx = -1;
+  bool idle = true, exhausted = false;
+  unsigned rayIdx = 0;
   HcRayTrav r;
-  TravStart(r, bvh, f3(0, 0, 0), f3(0, 0, 1), 0.0f);
+  TravStart(r, f3(0, 0, 0), f3(0, 0, 1), 0.0f);
   r.node = HC_NODE_SENTINEL;
 
   for (;;)
@@ -75,175 +79,12 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
     const unsigned idleMask = __ballot_sync(FULL, idle);
     if (idleMask != 0u && !exhausted && (__popc(idleMask) >= refillMin || idleMask == FULL))
     {
-      const int nIdle = __popc(idleMask), leader = __ffs(idleMask) - 1;
-      unsigned long long base = 0;
-      if (lane == leader) base = atomicAdd(counter, (unsigned long long)nIdle);
-      base = __shfl_sync(FULL, base, leader);
-      if (idle)
-      {
-        long long idx = (long long)base + __popc(idleMask & ltMask);
-        if (idx < n)
-        {
-          if (tileW > 0)
-          {
-            // the ray stream is a W x H image in row-major order: fetch it in 8 x 4 pixel blocks, so that a warp's 32 rays cover a
-            // compact screen patch (fewer distinct BVH nodes per warp, more uniform traversal lengths) instead of a 32 x 1 strip
-            const long long blk = idx >> 5; const int w = int(idx) & 31, bpr = tileW >> 3;
-            idx = ((blk/bpr)*4 + (w >> 3))*(long long)tileW + (blk % bpr)*8 + (w & 7);
-          }
-          float4 p, dd;
-          if (RAYGEN == 0) { p = __ldg(rpos + idx*stride); dd = __ldg(rdir + idx*stride); }
-          else
-          {
-            const long long pix = idx + gen.firstPixel;                  // launches may cover a band of the image
-            float3 eo, ed;
-            MakeRandEyeRay(int(pix % gen.width), int(pix / gen.width), gen.width, gen.height, make_float4(0.0f, 0.0f, 0.0f, 0.0f), gen.cam, eo, ed);
-            p = make_float4(eo.x, eo.y, eo.z, 0.0f); dd = make_float4(ed.x, ed.y, ed.z, HC_MAXFLOAT_RAY);
-            if (RAYGEN == 2)
-            {
-              const HcHit h = gen.hitsIn[pix];
-              p = make_float4(0, 0, 0, 0); dd = make_float4(0, 1, 0, 0);             // t_far = 0: "no shadow ray" for pixels that hit nothing
-              if (h.primId != -1)
-              {
-                const float3 pos = eo + ed*h.t;
-                const float3 sdir = normalize(gen.light - pos);
-                const float eps = fmaxf(fmaxf(fabsf(pos.x), fmaxf(fabsf(pos.y), fabsf(pos.z))), 1.0f)*1e-4f;
-                const float3 spos = pos + sdir*eps;
-                p = make_float4(spos.x, spos.y, spos.z, 0.0f);
-                dd = make_float4(sdir.x, sdir.y, sdir.z, length(spos - gen.light)*0.995f);
-              }
-            }
-          }
-          rayIdx = idx; idle = false;
-          TravStart(r, bvh, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
-          if (TREE1 != 0)
-          {
-            const float4 h = reinterpret_cast<const float4*>(hitsOut)[idx];      // Lite_Hit carried from tree to tree
-            r.t = h.x; r.primId = __float_as_int(h.y); r.hitInst = __float_as_int(h.z); r.geomId = __float_as_int(h.w);
-          }
-          if (ANYHIT && !(dd.w > 0.0f)) { visOut[idx] = 1; idle = true; r.node = HC_NODE_SENTINEL; }          // maxDist <= 0: lit (trace.cl:343-351)
-          else if (!RayIsFinite(r.o, r.d)) r.node = HC_NODE_SENTINEL;              // every comparison of the reference fails on NaN: no hit
-        }
-      }
-      if ((long long)base + nIdle >= n) exhausted = true;
-    }
-    if (__all_sync(FULL, idle)) { if (exhausted) break; else continue; }
-
-    // Vote scheduling: every lane is at an interior quad (Q), at a leaf (L: instance leaf or triangle-pair record) or has nothing
-    // to do.  The warp runs the step the majority is waiting for, and keeps doing so until a refill pays off.
-    for (;;)
-    {
-      bool wantQ = !(r.node & HC_LEAF_BIT);                                        // a finished / idle lane carries the sentinel (leaf bit set)
-      bool wantL = !wantQ && r.node != HC_NODE_SENTINEL;
-      unsigned mQ = __ballot_sync(FULL, wantQ), mL = __ballot_sync(FULL, wantL);
-      while (mQ != 0u && 2*__popc(mQ) >= __popc(mL))      // quad steps keep going until the leaf lanes outnumber them 2:1 (swept on B200: +3 %)
-      {
-        if (wantQ) TravQuad(r, bvh, stk);
-        wantQ = !(r.node & HC_LEAF_BIT); wantL = !wantQ && r.node != HC_NODE_SENTINEL;
-        mQ = __ballot_sync(FULL, wantQ); mL = __ballot_sync(FULL, wantL);
-      }
-      while (mL != 0u && __popc(mL) > __popc(mQ))
-      {
-        if (wantL)
-        {
-          if (!r.inInst) TravEnterInstance(r, bvh);
-          else
-          {
-            bool done;
-            const bool found = TravLeafPair<TREE1 == 2>(r, bvh, &done);
-            if (ANYHIT && found) r.node = HC_NODE_SENTINEL;
-            else if (done) HC_POP(r, bvh, stk)
-          }
-        }
-        wantQ = !(r.node & HC_LEAF_BIT); wantL = !wantQ && r.node != HC_NODE_SENTINEL;
-        mQ = __ballot_sync(FULL, wantQ); mL = __ballot_sync(FULL, wantL);
-      }
-      const int busy = __popc(mQ | mL);
-      if (busy == 0 || (!exhausted && busy <= 32 - refillMin)) break;         // all done, or enough idle lanes for a refill
-    }
-
-    if (!idle && r.node == HC_NODE_SENTINEL)
-    {
-      if (ANYHIT) visOut[rayIdx] = (r.primId != -1) ? 0 : 1;
-      else reinterpret_cast<float4*>(hitsOut)[rayIdx] = make_float4(r.t, __int_as_float(r.primId), __int_as_float(r.hitInst), __int_as_float(r.geomId));
-      idle = true;
-    }
-  }
-}
-
-
-// K2 / K2s, second generation (hc_trace2.cuh): centre / half-extent quads and triangle pairs fetched by 256-bit loads, stack in shared memory,
-// chunked ray supply with the next chunk claimed and prefetched one switch ahead.  Same template parameters and control flow as k_trace.
-#ifndef HC_TRACE2_MINB
-#define HC_TRACE2_MINB 7
-#endif
-template<bool ANYHIT, int TREE1 = 0, int RAYGEN = 0>
-__global__ void __launch_bounds__(HC_TRACE_BLOCK, HC_TRACE2_MINB)
-k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long nArg,
-         const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned* __restrict__ counter, const int refillMin, const int qBias,
-         const int tileW, const HcRayGen gen = HcRayGen())
-{
-  const unsigned n = (unsigned)(nDev ? (long long)(*nDev) : nArg);      // the path tracer keeps its live-path count on the device
-#if HC2_SSTK > 0
-  __shared__ uint2 sstk[HC2_SSTK][HC_TRACE_BLOCK];                      // {child word, entry distance}, first HC2_SSTK entries of every ray
-#endif
-  uint2 stk[HC_STACK_CAP - HC2_SSTK];                                   // deeper entries
-  uint2 saved[5];                                                       // world-space ray while inside an instance
-
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const unsigned ltMask = (1u << lane) - 1u;
-
-#if HC2_CHUNK
-  // ray supply: `cur` = next unclaimed index of this warp's chunk (a chunk ends at a multiple of 32), `nxt` = base of the chunk after it,
-  // `fut` (lane 0) = atomicAdd result for the chunk after that, in flight
-  unsigned cur, nxt, fut = 0;
-  {
-    unsigned b = 0;
-    if (lane == 0) b = atomicAdd(counter, 96u);
-    b = __shfl_sync(FULL, b, 0);
-    cur = b; nxt = b + 32u; fut = b + 64u;
-  }
-#else
-  unsigned cur = 0;              // 0 while rays are left, n once the counter has run past the end
-#endif
-  bool idle = true;
-  unsigned rayIdx = 0;
-  HcRay2 r;
-  Trav2Start(r, bvh, f3(0, 0, 0), f3(0, 0, 1), 0.0f);
-  r.node = HC_NODE_SENTINEL;
-
-  for (;;)
-  {
-    const unsigned idleMask = __ballot_sync(FULL, idle);
-    if (idleMask != 0u && cur < n && (__popc(idleMask) >= refillMin || idleMask == FULL))
-    {
-#if HC2_CHUNK
-      const unsigned nIdle = (unsigned)__popc(idleMask), avail = 32u - (cur & 31u);
-      const unsigned rank = (unsigned)__popc(idleMask & ltMask);
-      unsigned idx = (rank < avail) ? cur + rank : nxt + (rank - avail);
-      if (nIdle >= avail)
-      {
-        // chunk switch: the next chunk becomes current, the one claimed a switch ago becomes next, a new one is claimed (its result is
-        // not needed before the next switch), and the rays of the new `nxt` are prefetched
-        cur = nxt + (nIdle - avail);
-        nxt = __shfl_sync(FULL, fut, 0);
-        if (lane == 0) fut = atomicAdd(counter, 32u);
-        if (RAYGEN == 0 && nxt + lane < n && tileW == 0)
-        {
-          asm volatile("prefetch.global.L1 [%0];" :: "l"(rpos + size_t(nxt + lane)*stride));
-          asm volatile("prefetch.global.L1 [%0];" :: "l"(rdir + size_t(nxt + lane)*stride));
-        }
-      }
-      else cur += nIdle;
-#else
       const unsigned nIdle = (unsigned)__popc(idleMask); const int leader = __ffs(idleMask) - 1;
       unsigned base = 0;
       if (lane == leader) base = atomicAdd(counter, nIdle);
       base = __shfl_sync(FULL, base, leader);
       unsigned idx = base + (unsigned)__popc(idleMask & ltMask);
-      if (base + nIdle >= n) cur = n;
-#endif
+      if (base + nIdle >= n) exhausted = true;
       if (idle && idx < n)
       {
         if (tileW > 0)
@@ -277,7 +118,7 @@ k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restr
           }
         }
         rayIdx = idx; idle = false;
-        Trav2Start(r, bvh, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
+        TravStart(r, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
         if (TREE1 != 0)
         {
           const float4 h = reinterpret_cast<const float4*>(hitsOut)[idx];      // Lite_Hit carried from tree to tree
@@ -287,51 +128,8 @@ k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restr
         else if (!RayIsFinite(r.o, r.d)) r.node = HC_NODE_SENTINEL;              // every comparison of the reference fails on NaN: no hit
       }
     }
-    if (__all_sync(FULL, idle)) { if (cur >= n) break; else continue; }
+    if (__all_sync(FULL, idle)) { if (exhausted) break; else continue; }
 
-#if HC2_POSTPONE
-    // Speculative scheduling.  A lane at an interior quad can take a quad step (Q) even while it holds a parked leaf.  A lane NEEDS a leaf
-    // step (N) when it cannot go on otherwise: an instance to enter, a second leaf with one already parked, the end of the instance or of
-    // the ray with a leaf still parked.  Quad steps run until qBias lanes need a leaf step (or no lane can take a quad step); a leaf step
-    // serves every lane that holds leaf work, parked or not.
-    for (;;)
-    {
-      const bool wantQ = !(r.node & HC_LEAF_BIT);                                  // a finished / idle lane carries the sentinel (leaf bit set)
-      const bool needL = !wantQ && (r.node != HC_NODE_SENTINEL || r.pend != HC_PEND_EMPTY);
-      const unsigned mQ = __ballot_sync(FULL, wantQ), mN = __ballot_sync(FULL, needL);
-      const int busy = __popc(mQ | mN);
-      if (busy == 0 || (cur < n && busy <= 32 - refillMin)) break;                 // all done, or enough idle lanes for a refill
-      if (mQ != 0u && __popc(mN) < qBias)
-      {
-        if (wantQ) HC_QUAD2(r, bvh, saved)
-      }
-      else if (needL || r.pend != HC_PEND_EMPTY)
-      {
-        if (r.pend == HC_PEND_EMPTY)
-        {
-          if (r.instId < 0) HC_ENTER2(r, bvh, saved)                               // instance leaf of the top level
-          else { r.pend = r.node; HC_POP2(r, bvh, saved) }                         // triangle leaf with nothing parked (sub-tree root)
-        }
-        if (r.pend != HC_PEND_EMPTY)
-        {
-          // IntersectAllPrimitivesInLeaf, ONE pair record per step; the leaf word is the cursor (index up, count down)
-          const size_t pairIndex = size_t(r.pend & HC_LEAF_INDEX_MASK);
-          const bool last = ((r.pend >> HC_LEAF_PAIRS_SHIFT) & 63u) == 0u;
-          r.pend = last ? HC_PEND_EMPTY : (r.pend - (1u << HC_LEAF_PAIRS_SHIFT) + 1u);
-          const bool found = PairTest2<TREE1 == 2>(r, bvh, pairIndex);
-          if (ANYHIT && found) { r.node = HC_NODE_SENTINEL; r.pend = HC_PEND_EMPTY; r.sp = 0; }
-          else if (last && (r.node & HC_LEAF_BIT) && r.node != HC_NODE_SENTINEL && r.instId >= 0)
-          {
-            // the lane was waiting with a second leaf (park it now) or at the end of the instance (HC_NODE_WAIT): go on
-            if (r.node != HC_NODE_WAIT) r.pend = r.node;
-            HC_POP2(r, bvh, saved)
-          }
-        }
-      }
-    }
-
-    if (!idle && r.node == HC_NODE_SENTINEL && r.pend == HC_PEND_EMPTY)
-#else
     // Vote scheduling: every lane is at an interior quad (Q), at a leaf (L: instance leaf or triangle-pair record) or has nothing
     // to do.  The warp runs the step the majority is waiting for, and keeps doing so until a refill pays off.
     for (;;)
@@ -339,9 +137,9 @@ k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restr
       bool wantQ = !(r.node & HC_LEAF_BIT);                                        // a finished / idle lane carries the sentinel (leaf bit set)
       bool wantL = !wantQ && r.node != HC_NODE_SENTINEL;
       unsigned mQ = __ballot_sync(FULL, wantQ), mL = __ballot_sync(FULL, wantL);
-      while (mQ != 0u && qBias*__popc(mQ) >= 2*__popc(mL))      // quad steps keep going until the leaf lanes outnumber them (qBias 4: 2 to 1)
+      while (mQ != 0u && qBias*__popc(mQ) >= 2*__popc(mL))
       {
-        if (wantQ) HC_QUAD2(r, bvh, saved)
+        if (wantQ) HC_QUAD(r, bvh, stk, saved)
         wantQ = !(r.node & HC_LEAF_BIT); wantL = !wantQ && r.node != HC_NODE_SENTINEL;
         mQ = __ballot_sync(FULL, wantQ); mL = __ballot_sync(FULL, wantL);
       }
@@ -349,27 +147,26 @@ k_trace2(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restr
       {
         if (wantL)
         {
-          if (r.instId < 0) HC_ENTER2(r, bvh, saved)
+          if (r.instId < 0) HC_ENTER(r, bvh, saved)
           else
           {
             // IntersectAllPrimitivesInLeaf, ONE pair record per step; the leaf word is the cursor (index up, count down)
             const size_t pairIndex = size_t(r.node & HC_LEAF_INDEX_MASK);
             const bool done = ((r.node >> HC_LEAF_PAIRS_SHIFT) & 63u) == 0u;
             r.node = r.node - (1u << HC_LEAF_PAIRS_SHIFT) + 1u;
-            const bool found = PairTest2<TREE1 == 2>(r, bvh, pairIndex);
+            const bool found = PairTest<TREE1 == 2>(r, bvh, pairIndex);
             if (ANYHIT && found) r.node = HC_NODE_SENTINEL;
-            else if (done) HC_POP2(r, bvh, saved)
+            else if (done) HC_POP(r, stk, saved)
           }
         }
         wantQ = !(r.node & HC_LEAF_BIT); wantL = !wantQ && r.node != HC_NODE_SENTINEL;
         mQ = __ballot_sync(FULL, wantQ); mL = __ballot_sync(FULL, wantL);
       }
       const int busy = __popc(mQ | mL);
-      if (busy == 0 || (cur < n && busy <= 32 - refillMin)) break;         // all done, or enough idle lanes for a refill
+      if (busy == 0 || (!exhausted && busy <= 32 - refillMin)) break;         // all done, or enough idle lanes for a refill
     }
 
     if (!idle && r.node == HC_NODE_SENTINEL)
-#endif
     {
       if (ANYHIT) visOut[rayIdx] = (r.primId != -1) ? 0 : 1;
       else reinterpret_cast<float4*>(hitsOut)[rayIdx] = make_float4(r.t, __int_as_float(r.primId), __int_as_float(r.hitInst), __int_as_float(r.geomId));
@@ -405,27 +202,16 @@ static int TraceGrid(hc_ctx* ctx)
   int perSM = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace<false>, HC_TRACE_BLOCK, 0);
   if (perSM < 1) perSM = 1;
+  if (const char* e = getenv("HC_TRACE_CTAS")) { const int v = atoi(e); if (v >= 1 && v < perSM) perSM = v; }      // experiments: fewer resident CTAs per SM
   ctx->traceGrid = ctx->smCount*perSM;           // a whole number of waves: persistent CTAs, all resident
   return ctx->traceGrid;
 }
-static int TraceGrid2(hc_ctx* ctx)
-{
-  if (ctx->traceGrid2 > 0) return ctx->traceGrid2;
-  int perSM = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_trace2<false>, HC_TRACE_BLOCK, 0);
-  if (perSM < 1) perSM = 1;
-  if (const char* e = getenv("HC_TRACE_CTAS")) { const int v = atoi(e); if (v >= 1 && v < perSM) perSM = v; }      // experiments: fewer resident CTAs per SM
-  ctx->traceGrid2 = ctx->smCount*perSM;
-  return ctx->traceGrid2;
-}
-#define HC_REFILL2_MIN 8       // k_trace2: a refill costs no memory round trip (chunk claimed and prefetched ahead)
-#define HC_QBIAS2      4       // quad steps while lanes at a quad >= lanes that can only do a leaf step
 
 // one persistent-thread ray counter per launch in flight: rotate through the counter block so that back-to-back launches never share one
-static int NextCounter(hc_ctx* ctx, cudaStream_t stream, unsigned long long** out)
+static int NextCounter(hc_ctx* ctx, cudaStream_t stream, unsigned** out)
 {
   ctx->traceCounterSlot = (ctx->traceCounterSlot + 1) % 32;
-  *out = (unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot;
+  *out = (unsigned*)((unsigned long long*)ctx->counters.ptr + ctx->traceCounterSlot);
   HC_CUDA(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream));
   return HC_OK;
 }
@@ -443,23 +229,13 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   HC_REQUIRE(ctx->bvhNodes.ptr && ctx->bvhTris.ptr, HC_E_STATE, "hc_trace: no BVH uploaded (hc_set_bvh)");
   HC_REQUIRE(ctx->haveInst != 0, HC_E_STATE, "hc_trace: only the two-level (instanced) layout is supported");
   HC_REQUIRE(n < 0xffff0000ll, HC_E_ARG, "hc_trace: more than 2^32 rays in one launch");
-  const bool v2 = (ctx->traceImpl == 2);
-  HcBvh bvh; bvh.nodes = (const float4*)((v2 && HC2_CH) ? ctx->bvhNodesCH.ptr : ctx->bvhNodes.ptr); bvh.tris = (const float4*)ctx->bvhTris.ptr;
-  unsigned long long* counter = nullptr;
+  HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr;
+  unsigned* counter = nullptr;
   int rc = NextCounter(ctx, stream, &counter); if (rc) return rc;
-  const int grid = (int)std::min<long long>(v2 ? TraceGrid2(ctx) : TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
-  const int rf = ctx->traceRefill > 0 ? ctx->traceRefill : (v2 ? HC_REFILL2_MIN : HC_REFILL_MIN);
-  const int qb = ctx->traceQBias > 0 ? ctx->traceQBias : HC_QBIAS2;
-  if (v2)
-  {
-    if (anyHit) k_trace2<true><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, (unsigned*)counter, rf, qb, tileW);
-    else        k_trace2<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, (unsigned*)counter, rf, qb, tileW);
-  }
-  else
-  {
-    if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf, tileW);
-    else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, tileW);
-  }
+  const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
+  const int rf = ctx->traceRefill > 0 ? ctx->traceRefill : HC_REFILL_MIN, qb = ctx->traceQBias > 0 ? ctx->traceQBias : HC_QBIAS;
+  if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf, qb, tileW);
+  else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, qb, tileW);
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   if (!anyHit && ctx->haveTree1)
@@ -467,27 +243,19 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
     // IntegratorCommon::rayTrace walks the trees one after another with the hit carried along (CPUExp_Integrators_Common.cpp:131-147);
     // its shadowTrace looks at tree 0 only (:163-171), so the any-hit launch above is all a shadow ray gets - meshes with opacity maps
     // cast no shadows in the CPU integrators, and none here
-    HcBvh b1; b1.nodes = (const float4*)((v2 && HC2_CH) ? ctx->bvh1NodesCH.ptr : ctx->bvh1Nodes.ptr); b1.tris = (const float4*)ctx->bvh1Tris.ptr;
-    unsigned long long* counter1 = nullptr;
+    HcBvh b1; b1.nodes = (const float4*)ctx->bvh1Nodes.ptr; b1.tris = (const float4*)ctx->bvh1Tris.ptr;
+    unsigned* counter1 = nullptr;
     rc = NextCounter(ctx, stream, &counter1); if (rc) return rc;
-    const int alpha = ctx->haveAlpha1 ? 2 : 1;
     if (ctx->haveAlpha1)
     {
       int texTab = 0; memcpy(&texTab, ctx->globalsHead.data() + HC_EG_texturesTableOffset, 4);
       HC_REQUIRE(ctx->globals.ptr && ctx->storage[HC_STORAGE_TEXTURES].ptr, HC_E_STATE, "hc_trace: the alpha-tested tree needs the textures storage and the globals (texture table)");
       b1.alphaPairs = (const uint4*)ctx->bvh1AlphaPairs.ptr; b1.alphaTable = (const uint2*)ctx->bvh1AlphaTable.ptr;
       b1.textures = (const int4*)ctx->storage[HC_STORAGE_TEXTURES].ptr; b1.texturesTable = (const int*)ctx->globals.ptr + texTab;
-    }
-    if (v2)
-    {
-      if (alpha == 2) k_trace2<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, (unsigned*)counter1, rf, qb, tileW);
-      else            k_trace2<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, (unsigned*)counter1, rf, qb, tileW);
+      k_trace<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, qb, tileW);
     }
     else
-    {
-      if (alpha == 2) k_trace<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, tileW);
-      else            k_trace<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, tileW);
-    }
+      k_trace<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, qb, tileW);
     HC_CUDA(cudaGetLastError());
     ctx->stats.kernelLaunches++;
   }
@@ -501,23 +269,13 @@ static int LaunchTraceGen(hc_ctx* ctx, bool shadow, long long n, HcHit* hitsLoca
 {
   if (n <= 0) return HC_OK;
   cudaStream_t stream = ctx->stream;
-  const bool v2 = (ctx->traceImpl == 2);
-  HcBvh bvh; bvh.nodes = (const float4*)((v2 && HC2_CH) ? ctx->bvhNodesCH.ptr : ctx->bvhNodes.ptr); bvh.tris = (const float4*)ctx->bvhTris.ptr;
-  unsigned long long* counter = nullptr;
+  HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr;
+  unsigned* counter = nullptr;
   int rc = NextCounter(ctx, stream, &counter); if (rc) return rc;
-  const int grid = (int)std::min<long long>(v2 ? TraceGrid2(ctx) : TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
-  const int rf = ctx->traceRefill > 0 ? ctx->traceRefill : (v2 ? HC_REFILL2_MIN : HC_REFILL_MIN);
-  const int qb = ctx->traceQBias > 0 ? ctx->traceQBias : HC_QBIAS2;
-  if (v2)
-  {
-    if (shadow) k_trace2<true, 0, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, nullptr, vis, (unsigned*)counter, rf, qb, tileW, gen);
-    else        k_trace2<false, 0, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, hitsLocal, nullptr, (unsigned*)counter, rf, qb, tileW, gen);
-  }
-  else
-  {
-    if (shadow) k_trace<true, 0, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, nullptr, vis, counter, rf, tileW, gen);
-    else        k_trace<false, 0, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, hitsLocal, nullptr, counter, rf, tileW, gen);
-  }
+  const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
+  const int rf = ctx->traceRefill > 0 ? ctx->traceRefill : HC_REFILL_MIN, qb = ctx->traceQBias > 0 ? ctx->traceQBias : HC_QBIAS;
+  if (shadow) k_trace<true, 0, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, nullptr, vis, counter, rf, qb, tileW, gen);
+  else        k_trace<false, 0, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, hitsLocal, nullptr, counter, rf, qb, tileW, gen);
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   if (shadow) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n;
@@ -527,14 +285,16 @@ static int LaunchTraceGen(hc_ctx* ctx, bool shadow, long long n, HcHit* hitsLoca
 // Walk the uploaded reference-layout tree (producer bvh_access_dll2.cpp:199-717) on the host: validate every
 // offset, bound the traversal stack, and re-lay it out for the device (formats in hc_trace.cuh).  Quads and instance records keep
 // their quad index, so child words of interior nodes are unchanged.
-//   interior quad q : float4[8q+0..5] = minx[4] maxx[4] miny[4] maxy[4] minz[4] maxz[4], uint4[8q+6] = child words
+//   interior quad q : float4[8q+0..5] = cx[4] hx[4] cy[4] hy[4] cz[4] hz[4] (centre / half-extent of the children's boxes, see CentreHalf),
+//                     uint4[8q+6] = child words; an empty slot has half-extent HC_EMPTY_HALF_EXTENT < 0 and the sentinel word
 //   instance record : float4[8q+0..3] = inverse matrix columns, [8q+4] = {sub-tree word, realInstId, meshId, 0}
 //   triangle leaf   : pair records of 6 float4 {Ax0 Ax1 Ay0 Ay1 | Az0 Az1 E1x0 E1x1 | E1y0 E1y1 E1z0 E1z1 | E2x0 E2x1 E2y0 E2y1 |
 //                     E2z0 E2z1 prim0 prim1 | geom0 geom1 0 0} with E1 = B - A, E2 = C - A evaluated in float exactly as
 //                     IntersectAllPrimitivesInLeaf does (ctrace.h:159-160); an odd leaf is padded with a zero triangle, whose
 //                     determinant is 0 -> v = u = t = NaN -> every acceptance test fails.
-// centre / half-extent of one child slab for the second-generation quads (hc_trace2.cuh): [c - h, c + h] contains [lo, hi] in exact
-// arithmetic, h rounded up and inflated by 2^-21 (covers the rounding of h*|1/d| and of the centre distance in the kernel)
+// centre / half-extent of one child slab (hc_trace.cuh, QuadKeys): [c - h, c + h] contains [lo, hi] in exact arithmetic, h rounded up and
+// inflated by 2^-21 (covers the rounding of h*|1/d| and of the centre distance in the kernel)
+#define HC_EMPTY_HALF_EXTENT (-8.0e37f)
 static inline void CentreHalf(float lo, float hi, float* c, float* h)
 {
   const double cd = 0.5*(double(lo) + double(hi));
@@ -550,15 +310,13 @@ static inline void CentreHalf(float lo, float hi, float* c, float* h)
 
 static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const float* trif4, int trif4Num,
                                std::vector<float>& outNodes, std::vector<float>& outPairs, int* outStackBound,
-                               const unsigned* alphaU2 = nullptr, int alphaNum = 0, std::vector<unsigned>* outAlphaPairs = nullptr,
-                               std::vector<float>* outNodesCH = nullptr)
+                               const unsigned* alphaU2 = nullptr, int alphaNum = 0, std::vector<unsigned>* outAlphaPairs = nullptr)
 {
   struct N { float bmin[3]; unsigned lo; float bmax[3]; unsigned esc; };
   const N* nd = (const N*)nodes;
   const int quads = nodesNum/4;
   if (quads < 2) return HC_E_ARG;
   outNodes.assign(size_t(quads)*32, 0.0f);
-  if (outNodesCH) outNodesCH->assign(size_t(quads)*32, 0.0f);
   outPairs.clear();
   outPairs.reserve(size_t(trif4Num)*4 + 64);
   std::vector<unsigned> leafWord(size_t(trif4Num), 0u);     // float4 offset of a leaf header -> converted child word (0 = not yet)
@@ -616,20 +374,18 @@ static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const f
     if (it.inst) maxMesh = std::max(maxMesh, it.depth); else maxTop = std::max(maxTop, it.depth);
     if (seen[it.quad]) continue;     // shared mesh sub-trees: depth of first visit is representative
     seen[it.quad] = 1;
-    float* Q = outNodes.data() + size_t(it.quad)*32;
-    float* Q2 = outNodesCH ? outNodesCH->data() + size_t(it.quad)*32 : nullptr;       // rows {cx[4] hx[4]} {cy[4] hy[4]} {cz[4] hz[4]} {child words, spare}
+    float* Q = outNodes.data() + size_t(it.quad)*32;       // rows {cx[4] hx[4]} {cy[4] hy[4]} {cz[4] hz[4]} {child words, spare}
     unsigned words[4];
     for (int i = 0; i < 4; i++)
     {
       const N& c = nd[size_t(it.quad)*4 + i];
       if (c.lo == 0xffffffffu && c.esc == 0xffffffffu)        // IsValidNode (cglobals.h:1321): an x slab at +inf fails for every finite ray
       {
-        Q[0 + i] = INF; Q[4 + i] = INF; words[i] = HC_NODE_SENTINEL;
-        if (Q2) for (int a = 0; a < 3; a++) { Q2[8*a + i] = 0.0f; Q2[8*a + 4 + i] = -8.0e37f; }      // negative half-extent: far < near on every axis, never visited
+        for (int a = 0; a < 3; a++) { Q[8*a + i] = 0.0f; Q[8*a + 4 + i] = HC_EMPTY_HALF_EXTENT; }      // negative half-extent: far < near on every axis, never visited
+        words[i] = HC_NODE_SENTINEL;
         continue;
       }
-      Q[0 + i] = c.bmin[0]; Q[4 + i] = c.bmax[0]; Q[8 + i] = c.bmin[1]; Q[12 + i] = c.bmax[1]; Q[16 + i] = c.bmin[2]; Q[20 + i] = c.bmax[2];
-      if (Q2) for (int a = 0; a < 3; a++) CentreHalf(c.bmin[a], c.bmax[a], &Q2[8*a + i], &Q2[8*a + 4 + i]);
+      for (int a = 0; a < 3; a++) CentreHalf(c.bmin[a], c.bmax[a], &Q[8*a + i], &Q[8*a + 4 + i]);
       const unsigned off = c.lo & 0x7fffffffu;
       if (c.lo & 0x80000000u)
       {
@@ -647,14 +403,12 @@ static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const f
           else { subWord = sub; st.push_back({ sub, 1, true }); }
           memcpy(R + 16, &subWord, 4);
           memcpy(R + 17, (const float*)rec + 24, 8);           // {realInstId, meshId}: float4 8Q+6 .xy
-          if (outNodesCH) memcpy(outNodesCH->data() + size_t(off)*32, R, 128);
         }
         else { int rc = convertLeaf(off, &words[i]); if (rc) return rc; }
       }
       else { words[i] = off; st.push_back({ off, it.depth + 1, it.inst }); }
     }
     memcpy(Q + 24, words, 16);
-    if (Q2) memcpy(Q2 + 24, words, 16);
   }
   *outStackBound = 3*(maxTop + maxMesh) + 2;
   return HC_OK;
@@ -699,7 +453,6 @@ int hc_ctx_create(int device, hc_ctx** out)
   if (rc != HC_OK) { delete c; return rc; }
   HC_CUDA(cudaMemsetAsync(c->counters.ptr, 0, c->counters.bytes, c->stream));
   c->globalsHead.assign(HC_EG_HEAD_BYTES, 0);
-  if (const char* e = getenv("HC_TRACE_IMPL")) { const int v = atoi(e); if (v == 1 || v == 2) c->traceImpl = v; }
   if (const char* e = getenv("HC_TRACE_REFILL")) { const int v = atoi(e); if (v >= 1 && v <= 32) c->traceRefill = v; }
   if (const char* e = getenv("HC_TRACE_QBIAS")) { const int v = atoi(e); if (v >= 1 && v <= 64) c->traceQBias = v; }
   *out = c;
@@ -713,7 +466,7 @@ void hc_ctx_destroy(hc_ctx* c)
   cudaStreamSynchronize(c->stream);
   hc_path_free(c);
   for (int i = 0; i < HC_STORAGE_COUNT; i++) hc_buf_free(c->storage[i]);
-  hc_buf_free(c->globals); hc_buf_free(c->bvhNodes); hc_buf_free(c->bvhTris); hc_buf_free(c->bvhNodesCH); hc_buf_free(c->bvh1NodesCH); hc_buf_free(c->bvh1Nodes); hc_buf_free(c->bvh1Tris); hc_buf_free(c->bvh1AlphaPairs); hc_buf_free(c->bvh1AlphaTable); hc_buf_free(c->remapLists); hc_buf_free(c->remapTable); hc_buf_free(c->remapInst); hc_buf_free(c->instMatrices); hc_buf_free(c->instLightIds);
+  hc_buf_free(c->globals); hc_buf_free(c->bvhNodes); hc_buf_free(c->bvhTris); hc_buf_free(c->bvh1Nodes); hc_buf_free(c->bvh1Tris); hc_buf_free(c->bvh1AlphaPairs); hc_buf_free(c->bvh1AlphaTable); hc_buf_free(c->remapLists); hc_buf_free(c->remapTable); hc_buf_free(c->remapInst); hc_buf_free(c->instMatrices); hc_buf_free(c->instLightIds);
   hc_buf_free(c->fbSum); hc_buf_free(c->scratchRays); hc_buf_free(c->scratchOut); hc_buf_free(c->counters); hc_buf_free(c->pixelRng); hc_buf_free(c->qmcTable);
   hc_buf_free(c->rcRays); hc_buf_free(c->rcHits); hc_buf_free(c->rcSRays); hc_buf_free(c->rcVis);
   for (int i = 0; i < 5; i++) cudaEventDestroy(c->evStage[i]);
@@ -794,21 +547,18 @@ static int SetBvhTree(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, 
   HC_REQUIRE(haveInst != 0, HC_E_ARG, "hc_set_bvh: single-level trees (bvhType \"triangle4v\") are not supported, pass the two-level layout");
   HC_REQUIRE(alphaTable == nullptr || alphaNum >= trif4Num, HC_E_ARG, "hc_set_bvh_alpha: the alpha table must cover every float4 of the triangle list");
   int bound = 0;
-  std::vector<float> devNodes, devPairs, devNodesCH;
+  std::vector<float> devNodes, devPairs;
   std::vector<unsigned> devAlpha;
   int rc = ConvertBvhForDevice((const unsigned char*)nodes, nodesNum, (const float*)trif4, trif4Num, devNodes, devPairs, &bound,
-                               (const unsigned*)alphaTable, alphaNum, alphaTable ? &devAlpha : nullptr, &devNodesCH);
+                               (const unsigned*)alphaTable, alphaNum, alphaTable ? &devAlpha : nullptr);
   HC_REQUIRE(rc == HC_OK, rc, "hc_set_bvh: tree references nodes or triangles out of range (or a leaf holds more than 128 triangles)");
   HC_REQUIRE(bound <= HC_STACK_CAP, HC_E_RANGE, "hc_set_bvh: tree too deep for the traversal stack");
   HC_CUDA(cudaSetDevice(ctx->device));
   HcDevBuf& bn = treeId ? ctx->bvh1Nodes : ctx->bvhNodes;
   HcDevBuf& bt = treeId ? ctx->bvh1Tris : ctx->bvhTris;
-  HcDevBuf& bc = treeId ? ctx->bvh1NodesCH : ctx->bvhNodesCH;
   rc = hc_buf_reserve(ctx, bn, devNodes.size()*4); if (rc) return rc;
-  rc = hc_buf_reserve(ctx, bc, devNodesCH.size()*4); if (rc) return rc;
   rc = hc_buf_reserve(ctx, bt, std::max<size_t>(devPairs.size()*4, 96)); if (rc) return rc;
   HC_CUDA(cudaMemcpyAsync(bn.ptr, devNodes.data(), devNodes.size()*4, cudaMemcpyHostToDevice, ctx->stream));
-  HC_CUDA(cudaMemcpyAsync(bc.ptr, devNodesCH.data(), devNodesCH.size()*4, cudaMemcpyHostToDevice, ctx->stream));
   if (!devPairs.empty()) HC_CUDA(cudaMemcpyAsync(bt.ptr, devPairs.data(), devPairs.size()*4, cudaMemcpyHostToDevice, ctx->stream));
   if (treeId == 1)
   {

@@ -38,7 +38,6 @@ struct hc_ctx
   HcDevBuf globals;                        // EngineGlobals + tables blob
   std::vector<unsigned char> globalsHead;  // host copy of the first HC_EG_HEAD_BYTES bytes
   HcDevBuf bvhNodes, bvhTris;              // tree 0 (opaque geometry)
-  HcDevBuf bvhNodesCH, bvh1NodesCH;        // the same quads in centre / half-extent form (hc_trace2.cuh)
   HcDevBuf bvh1Nodes, bvh1Tris, bvh1AlphaPairs, bvh1AlphaTable;   // tree 1 (meshes with opacity maps), its per-pair alpha words and the reference's alpha table
   bool     haveTree1 = false, haveAlpha1 = false;
   HcDevBuf remapLists, remapTable, remapInst;   // material remap lists (SetAllRemapLists / SetAllInstIdToRemapId)
@@ -71,9 +70,8 @@ struct hc_ctx
   unsigned passCounter = 0;
 
   hc_stats stats{};
-  int traceGrid = 0, traceGrid2 = 0;
+  int traceGrid = 0;
   int traceCounterSlot = 0;
-  int traceImpl = 2;                       // 1 = first-generation kernel (k_trace), 2 = k_trace2; HC_TRACE_IMPL overrides
   int traceRefill = 0, traceQBias = 0;     // 0 = built-in defaults; HC_TRACE_REFILL / HC_TRACE_QBIAS override
 };
 

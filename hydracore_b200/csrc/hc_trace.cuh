@@ -3,22 +3,28 @@
 // Replaces BVH4TraversalInstKernel / BVH4TraversalInstShadowKenrel (reference hydra_drv/shaders/trace.cl:50, 309), i.e. the
 // device functions BVH4InstTraverse / BVH4InstTraverseShadow (hydra_drv/ctrace.h:841-1062, 1065-1294) with the triangle test
 // IntersectAllPrimitivesInLeaf (ctrace.h:124-182), the slab test RayBoxIntersectionLite2 (ctrace.h:32-53) and SafeInverse
-// (cglobals.h:726-735).  Same predicates, the same IEEE float operations in the same order (no FMA contraction), the same
-// near-to-far sorting network, so the closest hit is the same hit.  What differs is HOW the tree is stored and walked:
+// (cglobals.h:726-735).  The triangle test uses the same IEEE float operations in the same order (no FMA contraction) and the same
+// strict comparisons, children are visited near to far through the reference's sorting network, so the closest hit is the same hit.
+// What differs is HOW the tree is stored and walked:
 //
-//   * hc_set_bvh re-lays the reference blobs out for the device (ConvertBvhForDevice, hc_api.cu).  A quad stays 128 bytes and keeps its
-//     index, but becomes SoA: six float4 rows {minx[4], maxx[4], miny[4], maxy[4], minz[4], maxz[4]}, one uint4 row of child words.
-//     Two children share a 64-bit register pair, so one Blackwell packed-FP32 instruction (FADD2 / FMUL2: sub.rn.f32x2, mul.rn.f32x2,
-//     each half rounded exactly like the scalar op) slab-tests two children; the near/far row of an axis is picked by the sign of
-//     the ray direction (bit-identical to min(lo,hi) / max(lo,hi) for a finite ray) and the three axes are merged with the
-//     three-input FMNMX3.  Invalid children carry an infinite box that can never pass, so IsValidNode costs nothing.
-//   * triangles are stored two to a record with precomputed edges {A, B-A, C-A}, SoA over the pair, so the whole
-//     Moeller-Trumbore test runs in packed FP32 on two triangles at once; the leaf's triangle count lives in the child word,
+//   * hc_set_bvh re-lays the reference blobs out for the device (ConvertBvhForDevice, hc_api.cu).  A quad stays 128 bytes (one L1 line) and
+//     keeps its index, but becomes CENTRE / HALF-EXTENT, SoA: three 32-byte rows {c[4], h[4]} (x, y, z) + one row of child words.  Three
+//     256-bit loads (LDG.E.256) at FIXED offsets + one 128-bit load fetch it (round 1 used seven 128-bit loads through sign-selected row
+//     pointers: 7 L1 wavefronts per lane and quad instead of 4, and six registers of row pointers).  near / far = tc -/+ h*|1/d| with
+//     tc = (c - o)*(1/d): no near/far selection, 24 Blackwell packed-FP32 instructions (FADD2 / FMUL2 / FFMA2, two children each), the three
+//     axes merged by the three-input FMNMX3.  The box is CONSERVATIVE with respect to RayBoxIntersectionLite2: h is rounded up and inflated
+//     by 2^-21 at upload and the overlap test carries a relative margin of 2^-19, so every child the reference visits is visited; triangle
+//     acceptance is untouched.  Invalid children carry a negative half-extent (far < near on every axis), so IsValidNode costs nothing.
+//   * triangles are stored two to a record (96 B, three 256-bit loads) with precomputed edges {A, B-A, C-A}, SoA over the pair, so the
+//     whole Moeller-Trumbore test runs in packed FP32 on two triangles at once; the leaf's triangle count lives in the child word,
 //     which removes the dependent header fetch.
 //   * stack entries carry the child's entry distance, and an entry whose distance exceeds the current hit is dropped at pop time
 //     without fetching its quad (the reference re-fetches and re-tests all four children);
+//   * the world-space ray is parked in local memory while the ray is inside an instance;
 //   * "while-while" control flow (all lanes descend, then all lanes intersect) inside persistent warps that pull rays from a
 //     global counter with ballot/popc aggregation (one atomic per refill).
+// Variants measured and rejected in round 2 (postponed leaves, stack in shared memory, chunked ray supply, more resident warps) are in
+// DESIGN.md section 3 with their numbers (profiles/r02_k2_variants.md, profiles/r02_k2_ncu_compare.md).
 #pragma once
 #include "hc_math.cuh"
 #include "hc_texture.cuh"
@@ -97,119 +103,113 @@ HC_DEV hc_f2 dot2_xnynz(const HcVec2& a, const HcVec2& bn) { return dif2(dif2(mu
 #define HC_CSWAP(ta, ca, tb, cb) { const bool s_ = (tb < ta); const float tt_ = s_ ? tb : ta; const float tu_ = s_ ? ta : tb; \
                                    const unsigned ct_ = s_ ? cb : ca; const unsigned cu_ = s_ ? ca : cb; ta = tt_; tb = tu_; ca = ct_; cb = cu_; }
 
-// entry key of one child: tmin when (tmin <= tmax) && (tmax >= 0) && (tmin <= tHit), else MAXFLOAT.
-// With tHit >= 0 that condition equals max(tmin, 0) <= min(tmax, tHit).  n* / f* are the per-axis near / far plane distances.
-HC_DEV float ChildKey(float nx, float ny, float nz, float fx, float fy, float fz, float tHit)
-{
-  const float tmin = max3f(nx, ny, nz), tmax = min3f(fx, fy, fz);
-  return (fmaxf(tmin, 0.0f) <= fminf(tmax, tHit)) ? tmin : HC_MAXFLOAT;
-}
+#define HC_BOX_MARGIN  1.0000019073486328125f   // 1 + 2^-19
 
-// ------------------------------------------------------------------------------------------------ the traversal state of one ray
+struct HcF8 { float4 a, b; };
+HC_DEV HcF8 ldg256(const void* p)
+{
+  HcF8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+  return r;
+}
+HC_DEV hc_f2 fma2(hc_f2 a, hc_f2 b, hc_f2 c) { hc_f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+
 struct HcRayTrav
 {
   float3 o, d, inv;          // current space (world, or the instance's object space)
-  float3 wo, wd;             // world-space ray while inside an instance
   float  t; int primId, geomId, hitInst;
-  int    instId;             // instance being traversed
+  int    instId;             // instance being traversed (-1 outside)
   int    sp, instTop;
   unsigned node;
-  const char* nearX; const char* nearY; const char* nearZ;   // address of the near row of each axis in quad 0 (far row = near ^ 16)
-  bool   inInst;
 };
 
-// row order in a quad: minx 0, maxx 16, miny 32, maxy 48, minz 64, maxz 80 (bytes).  inv < 0 -> the max plane is the near one.
-// The quad array is 128-byte aligned, so `near ^ 16` addresses the far row of the same axis.
-HC_DEV void SetNearRows(HcRayTrav& r, const HcBvh& bvh)
+HC_DEV void TravStart(HcRayTrav& r, float3 o, float3 d, float tFar)
 {
-  const char* base = reinterpret_cast<const char*>(bvh.nodes);
-  r.nearX = base + (r.inv.x < 0.0f ? 16 : 0);
-  r.nearY = base + (r.inv.y < 0.0f ? 48 : 32);
-  r.nearZ = base + (r.inv.z < 0.0f ? 80 : 64);
-}
-
-HC_DEV void TravStart(HcRayTrav& r, const HcBvh& bvh, float3 o, float3 d, float tFar)
-{
-  r.o = o; r.d = d; r.inv = SafeInverse(d); r.wo = o; r.wd = d;
+  r.o = o; r.d = d; r.inv = SafeInverse(d);
   r.t = tFar; r.primId = -1; r.hitInst = -1; r.geomId = int(0xC0000000u);      // Make_Lite_Hit(t, -1), cglobals.h:1258-1266
-  r.instId = -1; r.sp = 0; r.instTop = 0; r.node = 1u; r.inInst = false;
-  SetNearRows(r, bvh);
+  r.instId = -1; r.sp = 0; r.instTop = 0; r.node = 1u;
 }
 
-// pop until an entry that can still matter (entry distance <= current hit; t is the same quantity in world and object space because the
-// direction is not renormalised); leave the instance when the stack has dropped below its entry level
-#define HC_POP(r, bvh, stk)                                                                                \
+// slab test of the four children of quad `node` for this lane's ray: entry keys (MAXFLOAT = not to be visited) and child words.
+// RayBoxIntersectionLite2 (ctrace.h:32-53) visits a child when (tmin <= tmax) && (tmax >= 0) && (tmin <= tHit); with tHit >= 0 that is
+// max(tmin, 0) <= min(tmax, tHit), here with the relative margin on the right-hand side.
+HC_DEV void QuadKeys(const HcRayTrav& r, const HcBvh& bvh, const unsigned node, float& t0, float& t1, float& t2, float& t3,
+                     unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3)
+{
+  const char* q = reinterpret_cast<const char*>(bvh.nodes) + size_t(node)*128u;
+  const HcF8 X = ldg256(q), Y = ldg256(q + 32), Z = ldg256(q + 64);
+  const uint4 ch = __ldg(reinterpret_cast<const uint4*>(q + 96));
+  const float ax = fabsf(r.inv.x), ay = fabsf(r.inv.y), az = fabsf(r.inv.z);
+  const hc_f2 oX = bc2(r.o.x), oY = bc2(r.o.y), oZ = bc2(r.o.z), iX = bc2(r.inv.x), iY = bc2(r.inv.y), iZ = bc2(r.inv.z);
+  const hc_f2 pX = bc2(ax), pY = bc2(ay), pZ = bc2(az), mX = bc2(-ax), mY = bc2(-ay), mZ = bc2(-az);
+  const hc_f2 tx01 = mul2(sub2(lo2(X.a), oX), iX), tx23 = mul2(sub2(hi2(X.a), oX), iX);
+  const hc_f2 ty01 = mul2(sub2(lo2(Y.a), oY), iY), ty23 = mul2(sub2(hi2(Y.a), oY), iY);
+  const hc_f2 tz01 = mul2(sub2(lo2(Z.a), oZ), iZ), tz23 = mul2(sub2(hi2(Z.a), oZ), iZ);
+  float nx0, nx1, nx2, nx3, ny0, ny1, ny2, ny3, nz0, nz1, nz2, nz3, fx0, fx1, fx2, fx3, fy0, fy1, fy2, fy3, fz0, fz1, fz2, fz3;
+  upk2(fma2(lo2(X.b), mX, tx01), nx0, nx1); upk2(fma2(hi2(X.b), mX, tx23), nx2, nx3);
+  upk2(fma2(lo2(X.b), pX, tx01), fx0, fx1); upk2(fma2(hi2(X.b), pX, tx23), fx2, fx3);
+  upk2(fma2(lo2(Y.b), mY, ty01), ny0, ny1); upk2(fma2(hi2(Y.b), mY, ty23), ny2, ny3);
+  upk2(fma2(lo2(Y.b), pY, ty01), fy0, fy1); upk2(fma2(hi2(Y.b), pY, ty23), fy2, fy3);
+  upk2(fma2(lo2(Z.b), mZ, tz01), nz0, nz1); upk2(fma2(hi2(Z.b), mZ, tz23), nz2, nz3);
+  upk2(fma2(lo2(Z.b), pZ, tz01), fz0, fz1); upk2(fma2(hi2(Z.b), pZ, tz23), fz2, fz3);
+  const float tHitK = r.t*HC_BOX_MARGIN;
+  float m0, m1, m2, m3;
+  upk2(mul2(pk2(min3f(fx0, fy0, fz0), min3f(fx1, fy1, fz1)), bc2(HC_BOX_MARGIN)), m0, m1);
+  upk2(mul2(pk2(min3f(fx2, fy2, fz2), min3f(fx3, fy3, fz3)), bc2(HC_BOX_MARGIN)), m2, m3);
+  const float n0 = max3f(nx0, ny0, nz0), n1 = max3f(nx1, ny1, nz1), n2 = max3f(nx2, ny2, nz2), n3 = max3f(nx3, ny3, nz3);
+  t0 = (fmaxf(n0, 0.0f) <= fminf(m0, tHitK)) ? n0 : HC_MAXFLOAT;
+  t1 = (fmaxf(n1, 0.0f) <= fminf(m1, tHitK)) ? n1 : HC_MAXFLOAT;
+  t2 = (fmaxf(n2, 0.0f) <= fminf(m2, tHitK)) ? n2 : HC_MAXFLOAT;
+  t3 = (fmaxf(n3, 0.0f) <= fminf(m3, tHitK)) ? n3 : HC_MAXFLOAT;
+  c0 = ch.x; c1 = ch.y; c2 = ch.z; c3 = ch.w;
+}
+
+// leave the instance: the world-space ray (origin, direction, reciprocal direction) was parked in local memory at fixed slots by HC_ENTER
+#define HC_LEAVE(r, saved)                                                                                  \
   {                                                                                                        \
+    const uint2 a_ = saved[0], b_ = saved[1], c_ = saved[2], d_ = saved[3], e_ = saved[4];                 \
+    r.o = f3(__uint_as_float(a_.x), __uint_as_float(a_.y), __uint_as_float(b_.x));                         \
+    r.d = f3(__uint_as_float(b_.y), __uint_as_float(c_.x), __uint_as_float(c_.y));                         \
+    r.inv = f3(__uint_as_float(d_.x), __uint_as_float(d_.y), __uint_as_float(e_.x));                       \
+    r.instId = -1;                                                                                         \
+  }
+
+// pop until an entry that can still matter: entry distance <= current hit (with the box margin: the stored distance is ours, up to
+// 2 ulp above the reference's; t is the same quantity in world and object space because the direction is not renormalised); leave the
+// instance when the stack has dropped below its entry level
+#define HC_POP(r, stk, saved)                                                                               \
+  {                                                                                                        \
+    const float tK_ = r.t*HC_BOX_MARGIN;                                                                   \
     for (;;)                                                                                               \
     {                                                                                                      \
       if (r.sp == 0) { r.node = HC_NODE_SENTINEL; break; }                                                 \
       r.sp--;                                                                                              \
       const uint2 e_ = stk[r.sp];                                                                          \
-      if (__uint_as_float(e_.y) <= r.t) { r.node = e_.x; break; }                                          \
+      if (!(__uint_as_float(e_.y) <= tK_)) continue;                                                       \
+      r.node = e_.x; break;                                                                                \
     }                                                                                                      \
-    if (r.inInst && r.sp < r.instTop)                                                                      \
-    {                                                                                                      \
-      asm volatile("" : "+f"(r.wd.x), "+f"(r.wd.y), "+f"(r.wd.z));   /* keeps SafeInverse(wd) out of the loop preheaders */ \
-      r.o = r.wo; r.d = r.wd; r.inv = SafeInverse(r.d); SetNearRows(r, bvh); r.inInst = false;             \
-    }                                                                                                      \
+    if (r.instId >= 0 && r.sp < r.instTop) HC_LEAVE(r, saved)                                              \
   }
 
-// one interior quad: slab-test four children (two per packed instruction), sort near to far, push three, descend into the nearest.
-// No capacity test on the pushes: hc_set_bvh rejects a tree whose worst-case stack exceeds HC_STACK_CAP (the reference instead
-// silently drops children once its 80-entry stack is full, ctrace.h:959-979 — a tree that deep is refused here).
-// slab test of the four children of quad `node` for this lane's ray: entry keys (MAXFLOAT = not to be visited) and child words
-HC_DEV void QuadKeys(const HcRayTrav& r, const HcBvh& bvh, const unsigned node, float& t0, float& t1, float& t2, float& t3,
-                     unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3)
-{
-  const size_t qo = size_t(node)*128u;
-  const char* ax = r.nearX + qo; const char* ay = r.nearY + qo; const char* az = r.nearZ + qo;
-  const float4 NX = __ldg(reinterpret_cast<const float4*>(ax)), FX = __ldg(reinterpret_cast<const float4*>(size_t(ax) ^ 16u));
-  const float4 NY = __ldg(reinterpret_cast<const float4*>(ay)), FY = __ldg(reinterpret_cast<const float4*>(size_t(ay) ^ 16u));
-  const float4 NZ = __ldg(reinterpret_cast<const float4*>(az)), FZ = __ldg(reinterpret_cast<const float4*>(size_t(az) ^ 16u));
-  const uint4  ch = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(bvh.nodes) + qo + 96));
-  const hc_f2 oX = bc2(r.o.x), oY = bc2(r.o.y), oZ = bc2(r.o.z), iX = bc2(r.inv.x), iY = bc2(r.inv.y), iZ = bc2(r.inv.z);
-  // RayBoxIntersectionLite2 (ctrace.h:32-53): t = invDir*(plane - pos)
-  float nx0, nx1, nx2, nx3, ny0, ny1, ny2, ny3, nz0, nz1, nz2, nz3, fx0, fx1, fx2, fx3, fy0, fy1, fy2, fy3, fz0, fz1, fz2, fz3;
-  upk2(mul2(iX, sub2(lo2(NX), oX)), nx0, nx1); upk2(mul2(iX, sub2(hi2(NX), oX)), nx2, nx3);
-  upk2(mul2(iX, sub2(lo2(FX), oX)), fx0, fx1); upk2(mul2(iX, sub2(hi2(FX), oX)), fx2, fx3);
-  upk2(mul2(iY, sub2(lo2(NY), oY)), ny0, ny1); upk2(mul2(iY, sub2(hi2(NY), oY)), ny2, ny3);
-  upk2(mul2(iY, sub2(lo2(FY), oY)), fy0, fy1); upk2(mul2(iY, sub2(hi2(FY), oY)), fy2, fy3);
-  upk2(mul2(iZ, sub2(lo2(NZ), oZ)), nz0, nz1); upk2(mul2(iZ, sub2(hi2(NZ), oZ)), nz2, nz3);
-  upk2(mul2(iZ, sub2(lo2(FZ), oZ)), fz0, fz1); upk2(mul2(iZ, sub2(hi2(FZ), oZ)), fz2, fz3);
-  t0 = ChildKey(nx0, ny0, nz0, fx0, fy0, fz0, r.t); t1 = ChildKey(nx1, ny1, nz1, fx1, fy1, fz1, r.t);
-  t2 = ChildKey(nx2, ny2, nz2, fx2, fy2, fz2, r.t); t3 = ChildKey(nx3, ny3, nz3, fx3, fy3, fz3, r.t);
-  c0 = ch.x; c1 = ch.y; c2 = ch.z; c3 = ch.w;
-}
+// one interior quad: slab-test four children, sort near to far (the reference's network (0,1)(2,3) (0,2)(1,3) (1,2), ctrace.h:896-957), push
+// three, descend into the nearest.  No capacity test on the pushes: hc_set_bvh rejects a tree whose worst-case stack exceeds HC_STACK_CAP
+// (the reference instead silently drops children once its 80-entry stack is full, ctrace.h:959-979 - a tree that deep is refused here).
+#define HC_QUAD(r, bvh, stk, saved)                                                                         \
+  {                                                                                                        \
+    float t0, t1, t2, t3; unsigned c0, c1, c2, c3;                                                         \
+    QuadKeys(r, bvh, r.node, t0, t1, t2, t3, c0, c1, c2, c3);                                              \
+    HC_CSWAP(t0, c0, t1, c1); HC_CSWAP(t2, c2, t3, c3);                                                    \
+    HC_CSWAP(t0, c0, t2, c2); HC_CSWAP(t1, c1, t3, c3);                                                    \
+    HC_CSWAP(t1, c1, t2, c2);                                                                              \
+    if (t3 < HC_MAXFLOAT) { stk[r.sp] = make_uint2(c3, __float_as_uint(t3)); r.sp++; }                     \
+    if (t2 < HC_MAXFLOAT) { stk[r.sp] = make_uint2(c2, __float_as_uint(t2)); r.sp++; }                     \
+    if (t1 < HC_MAXFLOAT) { stk[r.sp] = make_uint2(c1, __float_as_uint(t1)); r.sp++; }                     \
+    if (t0 < HC_MAXFLOAT) r.node = c0;                                                                     \
+    else HC_POP(r, stk, saved)                                                                             \
+  }
 
-HC_DEV void TravQuad(HcRayTrav& r, const HcBvh& bvh, uint2* stk)
-{
-  float t0, t1, t2, t3; unsigned c0, c1, c2, c3;
-  QuadKeys(r, bvh, r.node, t0, t1, t2, t3, c0, c1, c2, c3);
-  HC_CSWAP(t0, c0, t1, c1); HC_CSWAP(t2, c2, t3, c3);        // the reference's network: (0,1)(2,3) (0,2)(1,3) (1,2), ctrace.h:896-957
-  HC_CSWAP(t0, c0, t2, c2); HC_CSWAP(t1, c1, t3, c3);
-  HC_CSWAP(t1, c1, t2, c2);
-  if (t3 < HC_MAXFLOAT) { stk[r.sp] = make_uint2(c3, __float_as_uint(t3)); r.sp++; }
-  if (t2 < HC_MAXFLOAT) { stk[r.sp] = make_uint2(c2, __float_as_uint(t2)); r.sp++; }
-  if (t1 < HC_MAXFLOAT) { stk[r.sp] = make_uint2(c1, __float_as_uint(t1)); r.sp++; }
-  if (t0 < HC_MAXFLOAT) r.node = c0;
-  else HC_POP(r, bvh, stk)
-}
-
-// instance leaf of the top level: move the ray into the instance's object space (ctrace.h:1020-1046; DON'T normalise the direction)
-HC_DEV void TravEnterInstance(HcRayTrav& r, const HcBvh& bvh)
-{
-  const float4* rec = bvh.nodes + size_t(r.node & 0x7fffffffu)*8;
-  HcMat4 m; m.c0 = __ldg(rec + 0); m.c1 = __ldg(rec + 1); m.c2 = __ldg(rec + 2); m.c3 = __ldg(rec + 3);
-  const float4 w = __ldg(rec + 4);
-  r.instId = __float_as_int(w.y);
-  r.wo = r.o; r.wd = r.d;
-  r.o = mul4x3(m, r.o); r.d = mul3x3(m, r.d); r.inv = SafeInverse(r.d); SetNearRows(r, bvh);
-  r.inInst = true; r.instTop = r.sp;
-  r.node = __float_as_uint(w.x);
-}
-
-// triangle leaf: IntersectAllPrimitivesInLeaf (ctrace.h:124-182), ONE pair record (two triangles) per call; the leaf word itself is the
-// cursor (index up, count down).  Returns true when a hit was accepted; sets *done when the leaf is exhausted.
 // decompressTexCoord16 (ctrace.h:316-326) and the opacity lookup of IntersectAllPrimitivesInLeafAlpha (ctrace.h:384-398) through
 // sample2DLite (cfetch.h:738-760): a hit counts when max(rgb) of the opacity texel exceeds 0.5
 HC_DEV float2 DecompressTexCoord16(unsigned packed)
@@ -234,19 +234,20 @@ HC_DEV bool AlphaPass(const HcBvh& bvh, const uint4 a, float u, float v)
   return fmaxf(c.x, fmaxf(c.y, c.z)) > 0.5f;
 }
 
+// triangle leaf: IntersectAllPrimitivesInLeaf (ctrace.h:124-182), ONE pair record (two triangles, three 256-bit loads) per call
 template<bool ALPHA>
 HC_DEV bool PairTest(HcRayTrav& r, const HcBvh& bvh, const size_t pairIndex)
 {
-  const float4* __restrict__ p = bvh.tris + pairIndex*HC_PAIR_F4;
+  const char* p = reinterpret_cast<const char*>(bvh.tris) + pairIndex*(HC_PAIR_F4*16);
   HcVec2 O, D;
   O.x = bc2(r.o.x); O.y = bc2(r.o.y); O.z = bc2(r.o.z);
   D.x = bc2(r.d.x); D.y = bc2(r.d.y); D.z = bc2(r.d.z);
   bool found = false;
-  const float4 r0 = __ldg(p + 0), r1 = __ldg(p + 1), r2 = __ldg(p + 2), r3 = __ldg(p + 3), r4 = __ldg(p + 4);
+  const HcF8 R0 = ldg256(p), R1 = ldg256(p + 32), R2 = ldg256(p + 64);
   HcVec2 A, E1, E2;
-  A.x  = lo2(r0); A.y  = hi2(r0); A.z  = lo2(r1);
-  E1.x = hi2(r1); E1.y = lo2(r2); E1.z = hi2(r2);
-  E2.x = lo2(r3); E2.y = hi2(r3); E2.z = lo2(r4);
+  A.x  = lo2(R0.a); A.y  = hi2(R0.a); A.z  = lo2(R0.b);
+  E1.x = hi2(R0.b); E1.y = lo2(R1.a); E1.z = hi2(R1.a);
+  E2.x = lo2(R1.b); E2.y = hi2(R1.b); E2.z = lo2(R2.a);
   const HcVec2 pvecN = cross2_xnynz(D, E2);                                   // (p.x, -p.y, -p.z)
   HcVec2 tvec; tvec.x = sub2(O.x, A.x); tvec.y = sub2(O.y, A.y); tvec.z = sub2(O.z, A.z);
   const HcVec2 qvecN = cross2_xnynz(tvec, E1);                                // (q.x, -q.y, -q.z)
@@ -254,28 +255,36 @@ HC_DEV bool PairTest(HcRayTrav& r, const HcBvh& bvh, const size_t pairIndex)
   const hc_f2 invDet = pk2(1.0f/det0, 1.0f/det1);
   float v0, v1, u0, u1, t0, t1;
   upk2(mul2(dot2_xnynz(tvec, pvecN), invDet), v0, v1);
-  upk2(mul2(dot2_xnynz(D, qvecN), invDet), u0, u1);                           // dot(qvec, ray_dir): products commute
+  upk2(mul2(dot2_xnynz(D, qvecN), invDet), u0, u1);
   upk2(mul2(dot2_xnynz(E2, qvecN), invDet), t0, t1);
   if (v0 > -HC_TRI_EPS && u0 > -HC_TRI_EPS && (u0 + v0 < 1.0f + HC_TRI_EPS) && t0 > 0.0f && t0 < r.t && (!ALPHA || AlphaPass(bvh, __ldg(bvh.alphaPairs + 2*pairIndex), u0, v0)))
   {
-    r.t = t0; r.primId = __float_as_int(r4.z); r.geomId = __float_as_int(__ldg(p + 5).x); r.hitInst = r.instId; found = true;
+    r.t = t0; r.primId = __float_as_int(R2.a.z); r.geomId = __float_as_int(R2.b.x); r.hitInst = r.instId; found = true;
   }
   if (v1 > -HC_TRI_EPS && u1 > -HC_TRI_EPS && (u1 + v1 < 1.0f + HC_TRI_EPS) && t1 > 0.0f && t1 < r.t     // sequential, like the reference loop
       && (!ALPHA || AlphaPass(bvh, __ldg(bvh.alphaPairs + 2*pairIndex + 1), u1, v1)))
   {
-    r.t = t1; r.primId = __float_as_int(r4.w); r.geomId = __float_as_int(__ldg(p + 5).y); r.hitInst = r.instId; found = true;
+    r.t = t1; r.primId = __float_as_int(R2.a.w); r.geomId = __float_as_int(R2.b.y); r.hitInst = r.instId; found = true;
   }
   return found;
 }
 
-template<bool ALPHA>
-HC_DEV bool TravLeafPair(HcRayTrav& r, const HcBvh& bvh, bool* done)
-{
-  const size_t pairIndex = size_t(r.node & HC_LEAF_INDEX_MASK);
-  *done = ((r.node >> HC_LEAF_PAIRS_SHIFT) & 63u) == 0u;
-  r.node = r.node - (1u << HC_LEAF_PAIRS_SHIFT) + 1u;
-  return PairTest<ALPHA>(r, bvh, pairIndex);
-}
+// instance leaf of the top level: park the world-space ray in local memory, then move the ray into the instance's object space
+// (ctrace.h:1020-1046; DON'T normalise the direction)
+#define HC_ENTER(r, bvh, saved)                                                                             \
+  {                                                                                                        \
+    const float4* rec_ = bvh.nodes + size_t(r.node & 0x7fffffffu)*8;                                       \
+    HcMat4 m_; m_.c0 = __ldg(rec_ + 0); m_.c1 = __ldg(rec_ + 1); m_.c2 = __ldg(rec_ + 2); m_.c3 = __ldg(rec_ + 3); \
+    const float4 w_ = __ldg(rec_ + 4);                                                                     \
+    saved[0] = make_uint2(__float_as_uint(r.o.x), __float_as_uint(r.o.y));                                 \
+    saved[1] = make_uint2(__float_as_uint(r.o.z), __float_as_uint(r.d.x));                                 \
+    saved[2] = make_uint2(__float_as_uint(r.d.y), __float_as_uint(r.d.z));                                 \
+    saved[3] = make_uint2(__float_as_uint(r.inv.x), __float_as_uint(r.inv.y));                             \
+    saved[4] = make_uint2(__float_as_uint(r.inv.z), 0u);                                                   \
+    r.instId = __float_as_int(w_.y); r.instTop = r.sp;                                                     \
+    r.o = mul4x3(m_, r.o); r.d = mul3x3(m_, r.d); r.inv = SafeInverse(r.d);                                \
+    r.node = __float_as_uint(w_.x);                                                                        \
+  }
 
 HC_DEV bool RayIsFinite(float3 o, float3 d)
 {
