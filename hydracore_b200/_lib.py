@@ -60,12 +60,17 @@ SIGNATURES = {
     "hc_pt_init": (_I, [_P, _I]),
     "hc_pt_set_tiles": (_I, [_P, _I, _I, _I]),
     "hc_pt_set_material_sort": (_I, [_P, _I, _I]),
+    "hc_pt_set_shadow_trees": (_I, [_P, _I]),
     "hc_pt_pass": (_I, [_P, _I, _I]),
     "hc_fb_clear": (_I, [_P]),
     "hc_fb_device_ptr": (_I, [_P, _PP, ct.POINTER(_I64)]),
     "hc_fb_read_hdr": (_I, [_P, _P, _I, _I]),
     "hc_fb_read_sum": (_I, [_P, _P, _I, _I]),
     "hc_fb_read_ldr": (_I, [_P, _P, _I, _I]),
+    "hc_comm_unique_id": (_I, [_P]),
+    "hc_comm_init": (_I, [_P, _P, _I, _I]),
+    "hc_comm_version": (_I, [ct.POINTER(_I)]),
+    "hc_fb_reduce": (_I, [_P, _I, _I, ct.POINTER(ct.c_float)]),
     "hc_get_spp": (_I, [_P, ct.POINTER(ct.c_float)]),
     "hc_get_stats": (_I, [_P, ct.POINTER(hc_stats)]),
     "hc_reset_stats": (_I, [_P]),

@@ -1,4 +1,5 @@
 #include "GPUCUDALayer.h"
+#include <cstring>
 
 #include <cstdio>
 #include <cstdlib>
@@ -250,6 +251,40 @@ void GPUCUDALayer::CallNamedFunc(const char* a_name, const char* a_args)
     if (sscanf(args.c_str(), "%d %d %d", &tile, &rank, &world) != 3) Check(HC_E_ARG, "CallNamedFunc(tiles): expected \"<tileSize> <rank> <worldSize>\"");
     Check(hc_pt_set_tiles(m_ctx, tile, rank, world), "CallNamedFunc(tiles)");
     m_ptInitialised = false;
+  }
+  else if (name == "shadow_trees")
+  {
+    int mode = 1;
+    if (sscanf(args.c_str(), "%d", &mode) != 1) Check(HC_E_ARG, "CallNamedFunc(shadow_trees): expected 0 | 1");
+    Check(hc_pt_set_shadow_trees(m_ctx, mode), "CallNamedFunc(shadow_trees)");
+  }
+  else if (name == "comm_id")
+  {
+    // rank 0 of a multi-process render creates the NCCL unique id; the host hands its 256 hex digits to every process ("comm" below)
+    unsigned char id[128];
+    Check(hc_comm_unique_id(id), "CallNamedFunc(comm_id)");
+    static const char* hex = "0123456789abcdef";
+    m_commIdHex.assign(256, '0');
+    for (int i = 0; i < 128; i++) { m_commIdHex[2*i] = hex[id[i] >> 4]; m_commIdHex[2*i + 1] = hex[id[i] & 15]; }
+  }
+  else if (name == "comm")
+  {
+    // "<rank> <nranks> <256 hex digits>": join the communicator of the one-process-per-GPU render (what the shared-memory image is in the
+    // reference, GPUOCLLayerOther.cpp:365-430)
+    int rank = 0, world = 1; char hexId[260] = { 0 };
+    if (sscanf(args.c_str(), "%d %d %256s", &rank, &world, hexId) != 3 || strlen(hexId) != 256) Check(HC_E_ARG, "CallNamedFunc(comm): expected \"<rank> <nranks> <256 hex digits>\"");
+    unsigned char id[128];
+    auto nib = [](char c) -> int { return (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? c - 'a' + 10 : (c >= 'A' && c <= 'F') ? c - 'A' + 10 : 0; };
+    for (int i = 0; i < 128; i++) id[i] = (unsigned char)((nib(hexId[2*i]) << 4) | nib(hexId[2*i + 1]));
+    Check(hc_comm_init(m_ctx, id, rank, world), "CallNamedFunc(comm)");
+  }
+  else if (name == "reduce")
+  {
+    // "<dstRank> <mode>": combine the framebuffers of all processes on dstRank (mode 0 tile partition, 1 full-size sum); GetHDRImage /
+    // GetLDRImage on dstRank then return the whole frame
+    int dst = 0, mode = 0;
+    if (sscanf(args.c_str(), "%d %d", &dst, &mode) != 2) Check(HC_E_ARG, "CallNamedFunc(reduce): expected \"<dstRank> <mode>\"");
+    Check(hc_fb_reduce(m_ctx, dst, mode, nullptr), "CallNamedFunc(reduce)");
   }
 }
 

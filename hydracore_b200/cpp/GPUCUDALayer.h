@@ -55,6 +55,10 @@ public:
   // custom pipeline hooks of the interface, used for what the reference API has no slot for:
   //   CallNamedFunc("integrator", "pt" | "mispt" | "qmc")        which CPUExpLayer integrator to reproduce (default: by flags)
   //   CallNamedFunc("tiles", "<tileSize> <rank> <worldSize>")    interleaved tile ownership of this process (one process per GPU)
+  //   CallNamedFunc("shadow_trees", "0" | "1")                    shadow rays through the alpha-tested tree (1, default: as GPUOCLLayer) or not (0: as CPUExpLayer)
+  //   CallNamedFunc("comm_id", "") -> CommIdHex()                 rank 0: create the NCCL unique id of a multi-process render
+  //   CallNamedFunc("comm", "<rank> <nranks> <256 hex digits>")   join the communicator
+  //   CallNamedFunc("reduce", "<dstRank> <mode>")                 combine the framebuffers on dstRank (0 = tile partition, 1 = full-size sum)
   void CallNamedFunc(const char* a_name, const char* a_args) override;
 
   bool StoreCPUData() const override { return false; }          // no CPU integrator behind this layer (IHWLayerDataAssembler.cpp:574)
@@ -64,7 +68,8 @@ public:
   float GetSPP() const override { return m_spp; }
   float GetSPPContrib() const override { return m_sppContributed; }
 
-  hc_ctx* Context() const { return m_ctx; }                     // for the NCCL reduce of the caller (hc_fb_device_ptr)
+  hc_ctx* Context() const { return m_ctx; }
+  const std::string& CommIdHex() const { return m_commIdHex; }
 
 protected:
   void Check(int rc, const char* what) const;
@@ -80,6 +85,7 @@ protected:
   float   m_spp;
   float   m_sppContributed;
   MRaysStat m_stat;
+  std::string m_commIdHex;
   mutable std::string m_deviceName;
   mutable std::vector<HRRenderDeviceInfoListElem> m_deviceList;
 };

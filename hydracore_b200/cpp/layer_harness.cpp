@@ -169,6 +169,11 @@ int hl_globals_blob(void* p, int* out, int maxInts, int* outInts)
     if (out && maxInts >= n) memcpy(out, g, size_t(n)*4);
   });
 }
+int hl_comm_id_hex(void* p, char* out257)
+{
+  Session* s = static_cast<Session*>(p);
+  return Guard([&] { s->layer->CallNamedFunc("comm_id", ""); const std::string& h = static_cast<GPUCUDALayer*>(s->layer)->CommIdHex(); memcpy(out257, h.c_str(), 257); });
+}
 int hl_call(void* p, const char* name, const char* args) { Session* s = static_cast<Session*>(p); return Guard([&] { s->layer->CallNamedFunc(name, args); }); }
 int hl_init_path_tracing(void* p, int seed) { Session* s = static_cast<Session*>(p); return Guard([&] { s->layer->InitPathTracing(seed, nullptr); }); }
 int hl_passes(void* p, int n) { Session* s = static_cast<Session*>(p); return Guard([&] { for (int i = 0; i < n; i++) { s->layer->BeginTracingPass(); s->layer->EndTracingPass(); } }); }

@@ -119,12 +119,13 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
         }
         rayIdx = idx; idle = false;
         TravStart(r, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
-        if (TREE1 != 0)
+        if (TREE1 != 0 && !ANYHIT)
         {
           const float4 h = reinterpret_cast<const float4*>(hitsOut)[idx];      // Lite_Hit carried from tree to tree
           r.t = h.x; r.primId = __float_as_int(h.y); r.hitInst = __float_as_int(h.z); r.geomId = __float_as_int(h.w);
         }
-        if (ANYHIT && !(dd.w > 0.0f)) { visOut[idx] = 1; idle = true; r.node = HC_NODE_SENTINEL; }          // maxDist <= 0: lit (trace.cl:343-351)
+        if (ANYHIT && TREE1 != 0 && visOut[idx] == 0) { idle = true; r.node = HC_NODE_SENTINEL; }          // already occluded in the first tree
+        else if (ANYHIT && !(dd.w > 0.0f)) { visOut[idx] = 1; idle = true; r.node = HC_NODE_SENTINEL; }     // maxDist <= 0: lit (trace.cl:343-351)
         else if (!RayIsFinite(r.o, r.d)) r.node = HC_NODE_SENTINEL;              // every comparison of the reference fails on NaN: no hit
       }
     }
@@ -238,11 +239,13 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, qb, tileW);
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
-  if (!anyHit && ctx->haveTree1)
+  if (ctx->haveTree1 && (!anyHit || ctx->shadowTrees == 1))
   {
-    // IntegratorCommon::rayTrace walks the trees one after another with the hit carried along (CPUExp_Integrators_Common.cpp:131-147);
-    // its shadowTrace looks at tree 0 only (:163-171), so the any-hit launch above is all a shadow ray gets - meshes with opacity maps
-    // cast no shadows in the CPU integrators, and none here
+    // IntegratorCommon::rayTrace walks the trees one after another with the hit carried along (CPUExp_Integrators_Common.cpp:131-147).
+    // Shadow rays: the CPU integrators' shadowTrace looks at tree 0 only (:163-171: meshes with opacity maps cast no shadows there), the
+    // OpenCL layer walks every tree with the opacity test (GPUOCLKernels.cpp:959-1000, BVH4InstTraverseShadowAlphaS ctrace.h:1748).
+    // hc_pt_set_shadow_trees chooses: 1 (default) = every tree, a cut-out occludes where its opacity texel passes the closest-hit test
+    // (binary; the smooth-opacity and skip-shadow flags of the OpenCL path are not in the alpha words); 0 = first tree only (oracle parity)
     HcBvh b1; b1.nodes = (const float4*)ctx->bvh1Nodes.ptr; b1.tris = (const float4*)ctx->bvh1Tris.ptr;
     unsigned* counter1 = nullptr;
     rc = NextCounter(ctx, stream, &counter1); if (rc) return rc;
@@ -252,10 +255,11 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
       HC_REQUIRE(ctx->globals.ptr && ctx->storage[HC_STORAGE_TEXTURES].ptr, HC_E_STATE, "hc_trace: the alpha-tested tree needs the textures storage and the globals (texture table)");
       b1.alphaPairs = (const uint4*)ctx->bvh1AlphaPairs.ptr; b1.alphaTable = (const uint2*)ctx->bvh1AlphaTable.ptr;
       b1.textures = (const int4*)ctx->storage[HC_STORAGE_TEXTURES].ptr; b1.texturesTable = (const int*)ctx->globals.ptr + texTab;
-      k_trace<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, qb, tileW);
+      if (anyHit) k_trace<true, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, nullptr, vis, counter1, rf, qb, tileW);
+      else        k_trace<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, qb, tileW);
     }
-    else
-      k_trace<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, qb, tileW);
+    else if (anyHit) k_trace<true, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, nullptr, vis, counter1, rf, qb, tileW);
+    else             k_trace<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, qb, tileW);
     HC_CUDA(cudaGetLastError());
     ctx->stats.kernelLaunches++;
   }
@@ -465,6 +469,8 @@ void hc_ctx_destroy(hc_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   hc_path_free(c);
+  hc_comm_free(c);
+  hc_buf_free(c->fbOut);
   for (int i = 0; i < HC_STORAGE_COUNT; i++) hc_buf_free(c->storage[i]);
   hc_buf_free(c->globals); hc_buf_free(c->bvhNodes); hc_buf_free(c->bvhTris); hc_buf_free(c->bvh1Nodes); hc_buf_free(c->bvh1Tris); hc_buf_free(c->bvh1AlphaPairs); hc_buf_free(c->bvh1AlphaTable); hc_buf_free(c->remapLists); hc_buf_free(c->remapTable); hc_buf_free(c->remapInst); hc_buf_free(c->instMatrices); hc_buf_free(c->instLightIds);
   hc_buf_free(c->fbSum); hc_buf_free(c->scratchRays); hc_buf_free(c->scratchOut); hc_buf_free(c->counters); hc_buf_free(c->pixelRng); hc_buf_free(c->qmcTable);
@@ -503,6 +509,9 @@ int hc_storage_reserve(hc_ctx* ctx, int slot, uint64_t bytes)
   HC_CUDA(cudaSetDevice(ctx->device));
   HcDevBuf& b = ctx->storage[slot];
   if (b.bytes == bytes && b.ptr) return HC_OK;              // MemoryStorageOCL::Reserve keeps an equal-size buffer (MemoryStorageOCL.cpp:12-13)
+  ctx->sceneDirty = true;
+  if (slot == HC_STORAGE_TEXTURES || slot == HC_STORAGE_TEXTURES_AUX) ctx->texturesDirty = true;
+  if (slot == HC_STORAGE_MATERIALS) ctx->materialsMirror.clear();       // a re-allocated storage starts empty
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   hc_buf_free(b);
   return hc_buf_reserve(ctx, b, std::max<uint64_t>(bytes, 16));
@@ -514,6 +523,13 @@ int hc_storage_write(hc_ctx* ctx, int slot, uint64_t offsetBytes, const void* da
   HcDevBuf& b = ctx->storage[slot];
   HC_REQUIRE(offsetBytes + bytes <= b.bytes, HC_E_RANGE, "hc_storage_write: beyond reserved capacity");
   if (bytes == 0) return HC_OK;
+  ctx->sceneDirty = true;
+  if (slot == HC_STORAGE_TEXTURES || slot == HC_STORAGE_TEXTURES_AUX) ctx->texturesDirty = true;
+  if (slot == HC_STORAGE_MATERIALS)
+  {
+    if (ctx->materialsMirror.size() < b.bytes) ctx->materialsMirror.resize(b.bytes, 0);
+    memcpy(ctx->materialsMirror.data() + offsetBytes, data, bytes);
+  }
   HC_CUDA(cudaSetDevice(ctx->device));
   HC_CUDA(cudaMemcpyAsync((char*)b.ptr + offsetBytes, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));              // blocking write, as clEnqueueWriteBuffer(CL_TRUE) (MemoryStorageOCL.cpp:55)
@@ -536,6 +552,8 @@ int hc_set_globals(hc_ctx* ctx, const void* blob, uint64_t bytes)
   HC_CUDA(cudaMemcpyAsync(ctx->globals.ptr, blob, bytes, cudaMemcpyHostToDevice, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   memcpy(ctx->globalsHead.data(), blob, HC_EG_HEAD_BYTES);
+  ctx->globalsMirror.assign((const unsigned char*)blob, (const unsigned char*)blob + bytes);
+  ctx->sceneDirty = true; ctx->texturesDirty = true;        // the texture tables live in the globals blob
   return HC_OK;
 }
 
@@ -547,6 +565,7 @@ static int SetBvhTree(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, 
   HC_REQUIRE(haveInst != 0, HC_E_ARG, "hc_set_bvh: single-level trees (bvhType \"triangle4v\") are not supported, pass the two-level layout");
   HC_REQUIRE(alphaTable == nullptr || alphaNum >= trif4Num, HC_E_ARG, "hc_set_bvh_alpha: the alpha table must cover every float4 of the triangle list");
   int bound = 0;
+  ctx->sceneDirty = true;
   std::vector<float> devNodes, devPairs;
   std::vector<unsigned> devAlpha;
   int rc = ConvertBvhForDevice((const unsigned char*)nodes, nodesNum, (const float*)trif4, trif4Num, devNodes, devPairs, &bound,
@@ -600,6 +619,7 @@ int hc_set_bvh_alpha(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, c
 int hc_set_remap_lists(hc_ctx* ctx, const int32_t* allLists, const int32_t* tableOffsetAndSize, int allSize, int tableSize)
 {
   if (!ctx) return HC_E_ARG;
+  ctx->sceneDirty = true;
   if (!allLists || !tableOffsetAndSize || allSize <= 0 || tableSize <= 0) { ctx->remapListsSize = 0; ctx->remapTableSize = 0; ctx->remapListsHost.clear(); return HC_OK; }   // GPUOCLData.cpp:203-210
   for (int i = 0; i < tableSize; i++)
     HC_REQUIRE(tableOffsetAndSize[2*i] >= 0 && tableOffsetAndSize[2*i + 1] >= 0 && (long long)tableOffsetAndSize[2*i] + tableOffsetAndSize[2*i + 1] <= allSize, HC_E_RANGE,
@@ -617,6 +637,7 @@ int hc_set_remap_lists(hc_ctx* ctx, const int32_t* allLists, const int32_t* tabl
 int hc_set_inst_remap_ids(hc_ctx* ctx, const int32_t* instRemapListId, int n)
 {
   if (!ctx) return HC_E_ARG;
+  ctx->sceneDirty = true;
   if (!instRemapListId || n <= 0) { ctx->remapInstSize = 0; return HC_OK; }
   HC_CUDA(cudaSetDevice(ctx->device));
   int rc = hc_buf_reserve(ctx, ctx->remapInst, size_t(n)*4); if (rc) return rc;

@@ -1,0 +1,214 @@
+// hc_comm.cu — multi-GPU exchange of the HDR framebuffer inside the product library (C ABI: hc_comm_*, hc_fb_reduce).
+//
+// Replaces the reference's way of combining the partial images of its one-process-per-GPU mode: every process adds its buffer into an OS
+// shared-memory image under a mutex (GPUOCLLayer::ContribToExternalImageAccumulator, hydra_drv/GPUOCLLayerOther.cpp:365-430).  Here the
+// processes (still one per GPU, scene replicated) exchange over NVLink with NCCL:
+//   * PT / MISPT: the image plane is partitioned in interleaved tiles (hc_pt_set_tiles), so the per-rank buffers are DISJOINT.  Only the
+//     pixels a rank owns travel: they are packed densely (owned-pixel order), sent point to point to the destination rank and scattered
+//     into its SUM buffer - 1/G of the volume of a full-buffer reduce per rank, and assignment instead of addition, so the call can be
+//     repeated during progressive rendering without counting anything twice.
+//   * MISPT-QMC: samples land on arbitrary pixels, every rank holds a full-size buffer: ncclReduce(sum) into a SEPARATE buffer of the
+//     destination rank (the local sums stay untouched), which the read-back entry points then use.
+// NCCL is bound at run time (dlopen of libnccl.so.2): a host process that already carries an NCCL (e.g. a PyTorch process) shares it,
+// a plain C++ host gets the system library; without NCCL the single-GPU paths are unaffected and hc_comm_* fail loudly.
+#include "hc_context.h"
+#include <dlfcn.h>
+#include <cstring>
+#include <algorithm>
+
+namespace
+{
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat32 = 7 };           // ncclDataType_t (nccl.h): ncclInt8 0, ncclUint8 1, ncclInt32 2, ncclUint32 3, ncclInt64 4, ncclUint64 5, ncclFloat16 6, ncclFloat32 7
+enum { ncclSum = 0 };
+
+struct NcclApi
+{
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  int (*GetVersion)(int*) = nullptr;
+};
+NcclApi g_nccl;
+
+int LoadNccl()
+{
+  if (g_nccl.lib) return HC_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { hc_set_error("hc_comm: libnccl.so.2 not found (multi-GPU exchange needs NCCL)"); return HC_E_STATE; }
+#define HC_SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { hc_set_error("hc_comm: NCCL symbol missing: " name); dlclose(h); return HC_E_STATE; }
+  HC_SYM(GetUniqueId, "ncclGetUniqueId") HC_SYM(CommInitRank, "ncclCommInitRank") HC_SYM(CommDestroy, "ncclCommDestroy")
+  HC_SYM(GroupStart, "ncclGroupStart") HC_SYM(GroupEnd, "ncclGroupEnd") HC_SYM(Send, "ncclSend") HC_SYM(Recv, "ncclRecv")
+  HC_SYM(Reduce, "ncclReduce") HC_SYM(GetErrorString, "ncclGetErrorString") HC_SYM(GetVersion, "ncclGetVersion")
+#undef HC_SYM
+  g_nccl.lib = h;
+  return HC_OK;
+}
+
+int NcclFail(int e, const char* what)
+{
+  std::string m = std::string("NCCL error in ") + what + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+  hc_set_error(m.c_str());
+  return HC_E_STATE;
+}
+#define HC_NCCL(call, what) do { const int e_ = (call); if (e_ != ncclSuccess) return NcclFail(e_, what); } while (0)
+
+// dense <-> framebuffer by a pixel list (the owned pixels of one rank, in the order BuildOwnedPixels / OwnedPixelsOf produce)
+__global__ void k_fb_pack(const float4* __restrict__ fb, const int* __restrict__ pixels, const int n, float4* __restrict__ out)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fb[pixels[i]];
+}
+__global__ void k_fb_unpack(float4* __restrict__ fb, const int* __restrict__ pixels, const int n, const float4* __restrict__ in)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) fb[pixels[i]] = in[i];
+}
+}
+
+void hc_owned_pixels_of(int W, int H, int T, int rank, int world, std::vector<int>& owned);      // hc_path.cu
+
+void hc_comm_free(hc_ctx* ctx)
+{
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+  ctx->comm = nullptr;
+  hc_buf_free(ctx->commStage); hc_buf_free(ctx->commPixels); hc_buf_free(ctx->fbCombined);
+  ctx->combinedValid = false;
+}
+
+extern "C"
+{
+int hc_comm_unique_id(void* out128)
+{
+  if (!out128) return HC_E_ARG;
+  int rc = LoadNccl(); if (rc) return rc;
+  ncclUniqueId id;
+  HC_NCCL(g_nccl.GetUniqueId(&id), "ncclGetUniqueId");
+  memcpy(out128, &id, 128);
+  return HC_OK;
+}
+
+int hc_comm_init(hc_ctx* ctx, const void* uniqueId128, int rank, int nranks)
+{
+  if (!ctx || !uniqueId128 || nranks < 1 || rank < 0 || rank >= nranks) return HC_E_ARG;
+  int rc = LoadNccl(); if (rc) return rc;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->comm) { g_nccl.CommDestroy((ncclComm_t)ctx->comm); ctx->comm = nullptr; }
+  ncclUniqueId id; memcpy(&id, uniqueId128, 128);
+  ncclComm_t c = nullptr;
+  HC_NCCL(g_nccl.CommInitRank(&c, nranks, id, rank), "ncclCommInitRank");
+  ctx->comm = c; ctx->commRank = rank; ctx->commSize = nranks;
+  return HC_OK;
+}
+
+int hc_comm_version(int* outVersion)
+{
+  if (!outVersion) return HC_E_ARG;
+  int rc = LoadNccl(); if (rc) return rc;
+  HC_NCCL(g_nccl.GetVersion(outVersion), "ncclGetVersion");
+  return HC_OK;
+}
+
+// Combine the per-rank SUM buffers on `dstRank` (see the header comment).  mode 0 = tile partition (gather of owned tiles), 1 = full-size sum.
+// Asynchronous on the context's stream up to the final synchronise; *outMs (optional) = device time of the exchange on this rank.
+int hc_fb_reduce(hc_ctx* ctx, int dstRank, int mode, float* outMs)
+{
+  if (!ctx || (mode != 0 && mode != 1)) return HC_E_ARG;
+  HC_REQUIRE(ctx->fbSum.ptr && ctx->width > 0 && ctx->height > 0, HC_E_STATE, "hc_fb_reduce: no framebuffer (hc_resize)");
+  if (outMs) *outMs = 0.0f;
+  const int G = ctx->comm ? ctx->commSize : 1;
+  if (G == 1) return HC_OK;
+  HC_REQUIRE(dstRank >= 0 && dstRank < G, HC_E_ARG, "hc_fb_reduce: bad destination rank");
+  HC_REQUIRE(mode == 1 || (ctx->worldSize == G && ctx->rank == ctx->commRank), HC_E_STATE,
+             "hc_fb_reduce: the tile partition (hc_pt_set_tiles) must use the communicator's rank and size");
+  HC_CUDA(cudaSetDevice(ctx->device));
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  cudaStream_t s = ctx->stream;
+  const int W = ctx->width, H = ctx->height;
+  const size_t nPix = size_t(W)*H;
+  HC_CUDA(cudaEventRecord(ctx->ev0, s));
+  if (mode == 1)
+  {
+    if (ctx->commRank == dstRank) { int rc = hc_buf_reserve(ctx, ctx->fbCombined, nPix*16); if (rc) return rc; }
+    HC_NCCL(g_nccl.Reduce(ctx->fbSum.ptr, ctx->commRank == dstRank ? ctx->fbCombined.ptr : nullptr, nPix*4, ncclFloat32, ncclSum, dstRank, comm, s), "ncclReduce");
+    if (ctx->commRank == dstRank) ctx->combinedValid = true;
+  }
+  else
+  {
+    const int T = std::max(1, ctx->tileSize);
+    if (ctx->commRank != dstRank)
+    {
+      // pack my pixels densely and send them
+      if (ctx->commPixelsKey != (long long)W*100000000ll + (long long)H*10000ll + T*100 + G)
+      {
+        std::vector<int> mine; hc_owned_pixels_of(W, H, T, ctx->commRank, G, mine);
+        int rc = hc_buf_reserve(ctx, ctx->commPixels, std::max<size_t>(mine.size(), 1)*4); if (rc) return rc;
+        HC_CUDA(cudaMemcpyAsync(ctx->commPixels.ptr, mine.data(), mine.size()*4, cudaMemcpyHostToDevice, s));
+        HC_CUDA(cudaStreamSynchronize(s));
+        ctx->commCount.assign(1, (int)mine.size());
+        ctx->commPixelsKey = (long long)W*100000000ll + (long long)H*10000ll + T*100 + G;
+      }
+      const int n = ctx->commCount[0];
+      int rc = hc_buf_reserve(ctx, ctx->commStage, std::max<size_t>(n, 1)*16); if (rc) return rc;
+      if (n > 0)
+      {
+        k_fb_pack<<<(n + 255)/256, 256, 0, s>>>((const float4*)ctx->fbSum.ptr, (const int*)ctx->commPixels.ptr, n, (float4*)ctx->commStage.ptr);
+        HC_CUDA(cudaGetLastError());
+        ctx->stats.kernelLaunches++;
+        HC_NCCL(g_nccl.Send(ctx->commStage.ptr, size_t(n)*4, ncclFloat32, dstRank, comm, s), "ncclSend");
+      }
+    }
+    else
+    {
+      // destination: one dense segment per source rank, received in one group, scattered into the SUM buffer
+      if (ctx->commPixelsKey != (long long)W*100000000ll + (long long)H*10000ll + T*100 + G)
+      {
+        std::vector<int> all; ctx->commCount.assign(G, 0);
+        for (int g = 0; g < G; g++)
+        {
+          std::vector<int> px; if (g != dstRank) hc_owned_pixels_of(W, H, T, g, G, px);
+          ctx->commCount[g] = (int)px.size();
+          all.insert(all.end(), px.begin(), px.end());
+        }
+        int rc = hc_buf_reserve(ctx, ctx->commPixels, std::max<size_t>(all.size(), 1)*4); if (rc) return rc;
+        HC_CUDA(cudaMemcpyAsync(ctx->commPixels.ptr, all.data(), all.size()*4, cudaMemcpyHostToDevice, s));
+        HC_CUDA(cudaStreamSynchronize(s));
+        ctx->commPixelsKey = (long long)W*100000000ll + (long long)H*10000ll + T*100 + G;
+      }
+      size_t total = 0; for (int g = 0; g < G; g++) total += size_t(ctx->commCount[g]);
+      int rc = hc_buf_reserve(ctx, ctx->commStage, std::max<size_t>(total, 1)*16); if (rc) return rc;
+      HC_NCCL(g_nccl.GroupStart(), "ncclGroupStart");
+      size_t off = 0;
+      for (int g = 0; g < G; g++)
+      {
+        const int n = ctx->commCount[g];
+        if (g == dstRank || n == 0) continue;
+        const int e = g_nccl.Recv((float4*)ctx->commStage.ptr + off, size_t(n)*4, ncclFloat32, g, comm, s);
+        if (e != ncclSuccess) { g_nccl.GroupEnd(); return NcclFail(e, "ncclRecv"); }
+        off += size_t(n);
+      }
+      HC_NCCL(g_nccl.GroupEnd(), "ncclGroupEnd");
+      if (total > 0)
+      {
+        k_fb_unpack<<<(int)((total + 255)/256), 256, 0, s>>>((float4*)ctx->fbSum.ptr, (const int*)ctx->commPixels.ptr, (int)total, (const float4*)ctx->commStage.ptr);
+        HC_CUDA(cudaGetLastError());
+        ctx->stats.kernelLaunches++;
+      }
+    }
+  }
+  HC_CUDA(cudaEventRecord(ctx->ev1, s));
+  HC_CUDA(cudaStreamSynchronize(s));
+  if (outMs) HC_CUDA(cudaEventElapsedTime(outMs, ctx->ev0, ctx->ev1));
+  return HC_OK;
+}
+} // extern "C"

@@ -37,9 +37,12 @@ struct hc_ctx
   HcDevBuf storage[HC_STORAGE_COUNT];
   HcDevBuf globals;                        // EngineGlobals + tables blob
   std::vector<unsigned char> globalsHead;  // host copy of the first HC_EG_HEAD_BYTES bytes
+  std::vector<unsigned char> globalsMirror, materialsMirror;   // host copies of the globals blob and of the materials storage, kept by the upload entry points (scene validation reads them)
+  bool     texturesDirty = true;           // a texture storage was written since the image headers were last validated
   HcDevBuf bvhNodes, bvhTris;              // tree 0 (opaque geometry)
   HcDevBuf bvh1Nodes, bvh1Tris, bvh1AlphaPairs, bvh1AlphaTable;   // tree 1 (meshes with opacity maps), its per-pair alpha words and the reference's alpha table
   bool     haveTree1 = false, haveAlpha1 = false;
+  int      shadowTrees = 1;                // 1: shadow rays walk every tree (GPUOCLLayer), 0: the first tree only (CPU integrators); hc_pt_set_shadow_trees
   HcDevBuf remapLists, remapTable, remapInst;   // material remap lists (SetAllRemapLists / SetAllInstIdToRemapId)
   int      remapListsSize = 0, remapTableSize = 0, remapInstSize = 0;
   std::vector<int> remapListsHost;              // host copy for validation at hc_pt_init (every 'to' id must exist in the materials table)
@@ -63,11 +66,22 @@ struct hc_ctx
   void*    pathHost = nullptr;             // HcPathHost (hc_path.cu): double-buffered SoA path state, hit / visibility buffers, tile ownership
   int      seed = 0;
   bool     ptReady = false;
+  bool     sceneDirty = true;              // set by every scene upload entry point: hc_pt_pass re-validates the scene (and re-selects the shade kernel variant) before the next pass
   int      tileSize = 32, rank = 0, worldSize = 1;
   int      materialSort = 2 /* 0 off, 1 on, 2 auto: on for >= 3 materials and >= 384k paths per pass */, sortFromBounce = 1;   // K6b: sort the live-path queue by material before shading, from this bounce on
   HcDevBuf pixelRng;                       // uint2 per pixel: generator state carried across passes (trace.cl:6-13)
   HcDevBuf qmcTable;                       // Niederreiter table, 11 x 31 uint (qmc_sobol_niederreiter.cpp:179-186)
   unsigned passCounter = 0;
+
+  // multi-GPU exchange (hc_comm.cu)
+  void*    comm = nullptr;                 // ncclComm_t
+  int      commRank = 0, commSize = 1;
+  HcDevBuf commStage, commPixels;          // dense staging of owned pixels; pixel lists (mine, or every source rank's on the destination)
+  std::vector<int> commCount;              // pixels per source rank
+  long long commPixelsKey = -1;            // (W, H, tile, G) the lists were built for
+  HcDevBuf fbCombined;                     // destination rank, full-size sums (sample partition): sum over ranks, separate from fbSum
+  bool     combinedValid = false;
+  HcDevBuf fbOut;                          // read-back staging: normalised float4 image
 
   hc_stats stats{};
   int traceGrid = 0;
@@ -79,5 +93,6 @@ int hc_buf_reserve(hc_ctx* ctx, HcDevBuf& b, uint64_t bytes);   // grow-only
 void hc_buf_free(HcDevBuf& b);
 
 void hc_path_free(hc_ctx* ctx);   // hc_path.cu
+void hc_comm_free(hc_ctx* ctx);   // hc_comm.cu
 int  hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis, cudaStream_t stream = nullptr);
 int  hc_launch_trace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, HcHit* hits, unsigned char* vis);   // hc_api.cu

@@ -365,6 +365,14 @@ __global__ void k_hdr_to_ldr(const float4* __restrict__ fb, unsigned* __restrict
   out[i] = r | (g << 8) | (b << 16) | (a << 24);
 }
 
+// GetHDRImage: the image keeps SUMS, the read-back divides by the sample count (GPUOCLLayer.cpp:1184-1215) - on the device, into a staging
+// buffer that is then copied out, instead of a scalar loop over 8.3 M (1080p) / 33 M (4K) floats on the host
+__global__ void k_fb_normalize(const float4* __restrict__ fb, float4* __restrict__ out, int n, float invSpp)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fb[i]*invSpp;
+}
+
 // ------------------------------------------------------------------------------------------------------------------ host side
 struct HcPathHost
 {
@@ -433,23 +441,30 @@ static HcPathState StateOf(HcPathHost* p, int b, bool qmc)
   return s;
 }
 
-static int BuildOwnedPixels(hc_ctx* ctx)
+// pixels of `rank` under the interleaved tile ownership: tile t -> GPU t mod G.  Inside a tile: 8 x 4 pixel blocks, so that the
+// 32 paths of a warp start from a compact screen patch (coherent traversal); the image does not depend on this order (per-pixel generators,
+// per-pixel accumulation).  Also the order in which hc_fb_reduce (hc_comm.cu) packs a rank's pixels.
+void hc_owned_pixels_of(int W, int H, int T, int rank, int world, std::vector<int>& owned)
 {
-  HcPathHost* p = EnsureHost(ctx);
-  const int W = ctx->width, H = ctx->height, T = std::max(1, ctx->tileSize);
+  T = std::max(1, T);
   const int tx = (W + T - 1)/T, ty = (H + T - 1)/T;
-  std::vector<int> owned; owned.reserve(size_t(W)*H/std::max(1, ctx->worldSize) + 1024);
+  owned.clear(); owned.reserve(size_t(W)*H/std::max(1, world) + 1024);
   for (int t = 0; t < tx*ty; t++)
   {
-    if (t % ctx->worldSize != ctx->rank) continue;          // interleaved tile ownership: tile t -> GPU t mod G
+    if (t % world != rank) continue;
     const int x0 = (t % tx)*T, y0 = (t / tx)*T;
-    // inside a tile: 8 x 4 pixel blocks, so that the 32 paths of a warp start from a compact screen patch (coherent traversal);
-    // the image does not depend on this order (per-pixel generators, per-pixel accumulation)
     for (int by = y0; by < std::min(H, y0 + T); by += 4)
       for (int bx = x0; bx < std::min(W, x0 + T); bx += 8)
         for (int y = by; y < std::min(std::min(H, y0 + T), by + 4); y++)
           for (int x = bx; x < std::min(std::min(W, x0 + T), bx + 8); x++) owned.push_back(y*W + x);
   }
+}
+
+static int BuildOwnedPixels(hc_ctx* ctx)
+{
+  HcPathHost* p = EnsureHost(ctx);
+  std::vector<int> owned;
+  hc_owned_pixels_of(ctx->width, ctx->height, ctx->tileSize, ctx->rank, ctx->worldSize, owned);
   p->nOwned = int(owned.size());
   int rc = hc_buf_reserve(ctx, p->owned, std::max<size_t>(owned.size(), 1)*sizeof(int)); if (rc) return rc;
   if (!owned.empty()) HC_CUDA(cudaMemcpyAsync(p->owned.ptr, owned.data(), owned.size()*sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -522,6 +537,35 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
         int off = -1;
         if (texId > 0 && texId < texTabSize) memcpy(&off, gl.data() + 4*size_t(texTabOff + texId), 4);
         if (off < 0) { why = "an opacity sampler of the alpha-tested tree uses texture id " + std::to_string(texId) + ", which has no image in the textures storage"; return HC_E_RANGE; }
+      }
+    }
+  }
+  // every image reachable through the texture tables: RGBA8 / float4, or single-channel (depth 1) float / 8-bit - what ReadImageSw4 / ReadImageSw1
+  // (hc_texture.cuh) implement - and wholly inside its storage
+  {
+    struct Tab { int offOff, sizeOff, slot; const char* name; };
+    const Tab tabs[2] = { { HC_EG_texturesTableOffset, HC_EG_texturesTableSize, HC_STORAGE_TEXTURES, "textures" },
+                          { HC_EG_texturesAuxTableOffset, HC_EG_texturesAuxTableSize, HC_STORAGE_TEXTURES_AUX, "textures_aux" } };
+    for (const Tab& tb : tabs)
+    {
+      if (!ctx->texturesDirty) break;                        // headers unchanged since the last validation
+      const int tOff = gi(tb.offOff), tSize = gi(tb.sizeOff);
+      const HcDevBuf& st = ctx->storage[tb.slot];
+      if (tSize <= 0 || !st.ptr) continue;
+      if (tOff < 0 || size_t(tOff) + size_t(tSize) > gl.size()/4) { why = std::string(tb.name) + " table lies outside the globals blob"; return HC_E_RANGE; }
+      for (int t = 0; t < tSize; t++)
+      {
+        int off4; memcpy(&off4, gl.data() + 4*(size_t(tOff) + size_t(t)), 4);
+        if (off4 < 0) continue;
+        if ((uint64_t(off4) + 1)*16 > st.bytes) { why = std::string(tb.name) + " table entry " + std::to_string(t) + " points outside the storage"; return HC_E_RANGE; }
+        int hdr[4];
+        if (cudaMemcpy(hdr, (const char*)st.ptr + size_t(off4)*16, 16, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); why = "reading a texture header back failed"; return HC_E_STATE; }
+        const int w = hdr[0], h = hdr[1], d = hdr[2], bpp = hdr[3];
+        const bool okFmt = (d == 1) ? (bpp == 1 || bpp == 4) : (bpp == 4 || bpp == 16);
+        if (w <= 0 || h <= 0 || !okFmt)
+        { why = std::string(tb.name) + " image " + std::to_string(t) + ": " + std::to_string(w) + "x" + std::to_string(h) + ", depth " + std::to_string(d) + ", " + std::to_string(bpp) +
+                " bytes per pixel is not a supported format (RGBA8, float4, single-channel float or 8-bit)"; return HC_E_ARG; }
+        if ((uint64_t(off4) + 1)*16 + uint64_t(w)*uint64_t(h)*uint64_t(bpp) > st.bytes) { why = std::string(tb.name) + " image " + std::to_string(t) + " does not fit into the storage"; return HC_E_RANGE; }
       }
     }
   }
@@ -628,13 +672,32 @@ static void BuildQmcTable(unsigned table[HC_QRNG_DIMENSIONS_K][HC_QRNG_RESOLUTIO
   }
 }
 
+// host mirrors for validation (materials are small; the globals blob carries the lights), validation, choice of the shade-kernel variant.
+// Runs at hc_pt_init and again before the next pass whenever a scene upload entry point was called in between (ctx->sceneDirty): the reference
+// driver calls InitPathTracing once but re-uploads lights, materials and globals on later frames.
+static int RefreshScene(hc_ctx* ctx, const char* who)
+{
+  HC_REQUIRE(ctx->globals.ptr && ctx->bvhNodes.ptr && ctx->instMatrices.ptr && ctx->instLightIds.ptr, HC_E_STATE,
+             "scene incomplete (globals, BVH, instance matrices and instance light ids are required)");
+  HC_REQUIRE(ctx->storage[HC_STORAGE_GEOM].ptr && ctx->storage[HC_STORAGE_MATERIALS].ptr, HC_E_STATE, "geom / materials storage missing");
+  HcPathHost* p = EnsureHost(ctx);
+  p->materialsHost = ctx->materialsMirror;                    // kept up to date by hc_storage_write / hc_set_globals: no read-back
+  p->materialsHost.resize(ctx->storage[HC_STORAGE_MATERIALS].bytes, 0);
+  p->globalsHost = ctx->globalsMirror;
+  std::string why;
+  const int rc = ValidateScene(ctx, why);
+  if (rc) { hc_set_error((std::string(who) + ": " + why).c_str()); return rc; }
+  ctx->sceneDirty = false; ctx->texturesDirty = false;
+  return HC_OK;
+}
+
 extern "C"
 {
 int hc_resize(hc_ctx* ctx, int width, int height)
 {
   if (!ctx || width <= 0 || height <= 0) return HC_E_ARG;
   HC_CUDA(cudaSetDevice(ctx->device));
-  ctx->width = width; ctx->height = height; ctx->ptReady = false;
+  ctx->width = width; ctx->height = height; ctx->ptReady = false; ctx->combinedValid = false;
   int rc = hc_buf_reserve(ctx, ctx->fbSum, uint64_t(width)*height*16); if (rc) return rc;
   HC_CUDA(cudaMemsetAsync(ctx->fbSum.ptr, 0, uint64_t(width)*height*16, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -653,19 +716,8 @@ int hc_pt_init(hc_ctx* ctx, int seed)
 {
   if (!ctx) return HC_E_ARG;
   HC_REQUIRE(ctx->width > 0 && ctx->height > 0, HC_E_STATE, "hc_pt_init: call hc_resize first");
-  HC_REQUIRE(ctx->globals.ptr && ctx->bvhNodes.ptr && ctx->instMatrices.ptr && ctx->instLightIds.ptr, HC_E_STATE,
-             "hc_pt_init: scene incomplete (globals, BVH, instance matrices and instance light ids are required)");
-  HC_REQUIRE(ctx->storage[HC_STORAGE_GEOM].ptr && ctx->storage[HC_STORAGE_MATERIALS].ptr, HC_E_STATE, "hc_pt_init: geom / materials storage missing");
   HC_CUDA(cudaSetDevice(ctx->device));
-  HcPathHost* p = EnsureHost(ctx);
-  // host mirrors for validation (materials are small; the globals blob carries the lights)
-  p->materialsHost.resize(ctx->storage[HC_STORAGE_MATERIALS].bytes);
-  HC_CUDA(cudaMemcpy(p->materialsHost.data(), ctx->storage[HC_STORAGE_MATERIALS].ptr, p->materialsHost.size(), cudaMemcpyDeviceToHost));
-  p->globalsHost.resize(ctx->globals.bytes);
-  HC_CUDA(cudaMemcpy(p->globalsHost.data(), ctx->globals.ptr, p->globalsHost.size(), cudaMemcpyDeviceToHost));
-  std::string why;
-  int rc = ValidateScene(ctx, why);
-  if (rc) { hc_set_error(("hc_pt_init: " + why).c_str()); return rc; }
+  int rc = RefreshScene(ctx, "hc_pt_init"); if (rc) return rc;
 
   const int n = ctx->width*ctx->height;
   if ((rc = hc_buf_reserve(ctx, ctx->pixelRng, uint64_t(n)*8))) return rc;
@@ -678,7 +730,7 @@ int hc_pt_init(hc_ctx* ctx, int seed)
   if ((rc = BuildOwnedPixels(ctx))) return rc;
   HC_CUDA(cudaMemsetAsync(ctx->fbSum.ptr, 0, uint64_t(n)*16, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->seed = seed; ctx->spp = 0.0; ctx->passCounter = 0; ctx->ptReady = true;
+  ctx->seed = seed; ctx->spp = 0.0; ctx->passCounter = 0; ctx->ptReady = true; ctx->combinedValid = false;
   ctx->stats.kernelLaunches++;
   return HC_OK;
 }
@@ -689,7 +741,9 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   HC_REQUIRE(integrator == HC_INTEGRATOR_PT || integrator == HC_INTEGRATOR_MISPT || integrator == HC_INTEGRATOR_MISPT_QMC, HC_E_ARG, "hc_pt_pass: unknown integrator");
   HC_REQUIRE(ctx->ptReady, HC_E_STATE, "hc_pt_pass: call hc_pt_init first (after the scene, the screen size and the tiles are set)");
   HC_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->sceneDirty) { const int rcv = RefreshScene(ctx, "hc_pt_pass"); if (rcv) return rcv; }      // lights / materials / globals re-uploaded since hc_pt_init
   HcPathHost* p = PH(ctx);
+  ctx->combinedValid = false;                                  // new samples: an earlier cross-rank sum (hc_fb_reduce) is stale
   const bool qmc = (integrator == HC_INTEGRATOR_MISPT_QMC);
   const int W = ctx->width, H = ctx->height;
   const int n = qmc ? ((W*H - ctx->rank + ctx->worldSize - 1)/ctx->worldSize) : p->nOwned;
@@ -930,7 +984,7 @@ int hc_fb_clear(hc_ctx* ctx)
   HC_CUDA(cudaSetDevice(ctx->device));
   HC_CUDA(cudaMemsetAsync(ctx->fbSum.ptr, 0, uint64_t(ctx->width)*ctx->height*16, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->spp = 0.0;
+  ctx->spp = 0.0; ctx->combinedValid = false;
   return HC_OK;
 }
 
@@ -942,15 +996,27 @@ int hc_fb_device_ptr(hc_ctx* ctx, float** outSumRGBA, int64_t* outFloats)
   return HC_OK;
 }
 
+// the image the read-back entry points see: this rank's sums, or - on the destination rank after hc_fb_reduce of full-size buffers - the sum over ranks
+static const float4* ReadSource(hc_ctx* ctx) { return (const float4*)((ctx->combinedValid && ctx->fbCombined.ptr) ? ctx->fbCombined.ptr : ctx->fbSum.ptr); }
+
 int hc_fb_read_hdr(hc_ctx* ctx, float* outRGBA, int width, int height)
 {
   if (!ctx || !outRGBA) return HC_E_ARG;
   HC_REQUIRE(width == ctx->width && height == ctx->height && ctx->fbSum.ptr, HC_E_ARG, "hc_fb_read_hdr: bad input resolution");
   HC_CUDA(cudaSetDevice(ctx->device));
-  const size_t n = size_t(width)*height*4;
-  HC_CUDA(cudaMemcpyAsync(outRGBA, ctx->fbSum.ptr, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+  const int n = width*height;
+  const float4* src = ReadSource(ctx);
+  if (ctx->spp > 0.0)
+  {
+    // normalisation on read-back (GPUOCLLayer.cpp:1184-1215), on the device
+    int rc = hc_buf_reserve(ctx, ctx->fbOut, uint64_t(n)*16); if (rc) return rc;
+    k_fb_normalize<<<(n + 255)/256, 256, 0, ctx->stream>>>(src, (float4*)ctx->fbOut.ptr, n, float(1.0/ctx->spp));
+    HC_CUDA(cudaGetLastError());
+    ctx->stats.kernelLaunches++;
+    src = (const float4*)ctx->fbOut.ptr;
+  }
+  HC_CUDA(cudaMemcpyAsync(outRGBA, src, size_t(n)*16, cudaMemcpyDeviceToHost, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (ctx->spp > 0.0) { const float inv = float(1.0/ctx->spp); for (size_t i = 0; i < n; i++) outRGBA[i] *= inv; }   // normalisation on read-back, GPUOCLLayer.cpp:1184-1215
   return HC_OK;
 }
 
@@ -959,7 +1025,7 @@ int hc_fb_read_sum(hc_ctx* ctx, float* outRGBA, int width, int height)
   if (!ctx || !outRGBA) return HC_E_ARG;
   HC_REQUIRE(width == ctx->width && height == ctx->height && ctx->fbSum.ptr, HC_E_ARG, "hc_fb_read_sum: bad input resolution");
   HC_CUDA(cudaSetDevice(ctx->device));
-  HC_CUDA(cudaMemcpyAsync(outRGBA, ctx->fbSum.ptr, size_t(width)*height*16, cudaMemcpyDeviceToHost, ctx->stream));
+  HC_CUDA(cudaMemcpyAsync(outRGBA, ReadSource(ctx), size_t(width)*height*16, cudaMemcpyDeviceToHost, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   return HC_OK;
 }
@@ -974,7 +1040,7 @@ int hc_fb_read_ldr(hc_ctx* ctx, uint32_t* outRGBA8, int width, int height)
   int rc = hc_buf_reserve(ctx, p->ldr, uint64_t(n)*4); if (rc) return rc;
   const float* varsF = (const float*)(ctx->globalsHead.data() + HC_EG_varsF);
   const float gamma = varsF[HC_HRT_IMAGE_GAMMA] > 0.0f ? varsF[HC_HRT_IMAGE_GAMMA] : 2.2f;
-  k_hdr_to_ldr<<<(n + 255)/256, 256, 0, ctx->stream>>>((const float4*)ctx->fbSum.ptr, (unsigned*)p->ldr.ptr, n, ctx->spp > 0.0 ? float(1.0/ctx->spp) : 1.0f, 1.0f/gamma);
+  k_hdr_to_ldr<<<(n + 255)/256, 256, 0, ctx->stream>>>(ReadSource(ctx), (unsigned*)p->ldr.ptr, n, ctx->spp > 0.0 ? float(1.0/ctx->spp) : 1.0f, 1.0f/gamma);
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   HC_CUDA(cudaMemcpyAsync(outRGBA8, p->ldr.ptr, uint64_t(n)*4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -986,6 +1052,13 @@ int hc_pt_set_material_sort(hc_ctx* ctx, int enable, int fromBounce)
 {
   if (!ctx || fromBounce < 0) return HC_E_ARG;
   ctx->materialSort = (enable == 2) ? 2 : (enable ? 1 : 0); ctx->sortFromBounce = fromBounce;
+  return HC_OK;
+}
+
+int hc_pt_set_shadow_trees(hc_ctx* ctx, int mode)
+{
+  if (!ctx || (mode != 0 && mode != 1)) return HC_E_ARG;
+  ctx->shadowTrees = mode;
   return HC_OK;
 }
 

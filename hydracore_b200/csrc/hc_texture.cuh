@@ -43,11 +43,49 @@ HC_DEV int4 BilinearOffsets(float ffx, float ffy, int flags, int w, int h)     /
   return make_int4(py0*w + px0, py0*w + px1, py1*w + px0, py1*w + px1);
 }
 
-// read_imagef_sw4 (cfetch.h:461-584) for RGBA8 (bpp 4) and float4 (bpp 16) images; single-channel images are rejected at init
+// read_imagef_sw1 (cfetch.h:364-459): single-channel images, float (bpp 4) or 8-bit sRGB (bpp 1).  Other formats are rejected when
+// the scene is validated (ValidateScene, hc_path.cu), so `res` is always written.
+HC_DEV float ReadImageSw1(const int4* tex, float2 tc, int flags)
+{
+  const int4 header = *tex;
+  const int w = header.x, h = header.y, bpp = header.w;
+  float ffx = tc.x*(float)w - 0.5f, ffy = tc.y*(float)h - 0.5f;
+  if ((flags & HC_TEX_CLAMP_U) != 0 && ffx < 0) ffx = 0.0f;
+  if ((flags & HC_TEX_CLAMP_V) != 0 && ffy < 0) ffy = 0.0f;
+  const float* fdata = reinterpret_cast<const float*>(tex + 1);
+  const unsigned char* bdata = reinterpret_cast<const unsigned char*>(tex + 1);
+  const float mult = 0.003921568f;                                       // read_array_uchar, cfetch.h:305-310
+  float res = 0.0f;
+  if (flags & HC_TEX_POINT_SAM)
+  {
+    int px = (int)(ffx + 0.5f), py = (int)(ffy + 0.5f);
+    if (flags & HC_TEX_CLAMP_U) { px = (px >= w) ? w - 1 : px; px = (px < 0) ? 0 : px; } else { px = px % w; px = (px < 0) ? px + w : px; }
+    if (flags & HC_TEX_CLAMP_V) { py = (py >= h) ? h - 1 : py; py = (py < 0) ? 0 : py; } else { py = py % h; py = (py < 0) ? py + h : py; }
+    const int offset = py*w + px;
+    if (bpp == 4) res = fdata[offset];
+    else if (bpp == 1) res = sRGBToLinear(mult*(float)bdata[offset]);
+  }
+  else
+  {
+    const int px = (int)ffx, py = (int)ffy;
+    const float fx = fabsf(ffx - (float)px), fy = fabsf(ffy - (float)py);
+    const float fx1 = 1.0f - fx, fy1 = 1.0f - fy;
+    const float w1 = fx1*fy1, w2 = fx*fy1, w3 = fx1*fy, w4 = fx*fy;
+    const int4 o = BilinearOffsets(ffx, ffy, flags, w, h);
+    if (bpp == 4) res = fdata[o.x]*w1 + fdata[o.y]*w2 + fdata[o.z]*w3 + fdata[o.w]*w4;
+    else if (bpp == 1)
+      res = sRGBToLinear(mult*(float)bdata[o.x])*w1 + sRGBToLinear(mult*(float)bdata[o.y])*w2 + sRGBToLinear(mult*(float)bdata[o.z])*w3 + sRGBToLinear(mult*(float)bdata[o.w])*w4;
+  }
+  return res;
+}
+
+// read_imagef_sw4 (cfetch.h:461-584): RGBA8 (bpp 4) and float4 (bpp 16) images; single-channel images (header.z == 1, what
+// RenderDriverRTE::UpdateImage writes for grey-scale textures) go through read_imagef_sw1 and come back as (v, v, v, 1)
 HC_DEV float4 ReadImageSw4(const int4* tex, float2 tc, int flags, bool srgb)
 {
   const int4 header = *tex;
   const int w = header.x, h = header.y, bpp = header.w;
+  if (header.z == 1) { const float v = ReadImageSw1(tex, tc, flags); return make_float4(v, v, v, 1.0f); }
   float ffx = tc.x*(float)w - 0.5f, ffy = tc.y*(float)h - 0.5f;
   if ((flags & HC_TEX_CLAMP_U) != 0 && ffx < 0) ffx = 0.0f;
   if ((flags & HC_TEX_CLAMP_V) != 0 && ffy < 0) ffy = 0.0f;

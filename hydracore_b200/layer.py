@@ -218,6 +218,10 @@ class CudaLayer:
     def SetTiles(self, tile, rank, world):
         check(self._L.hc_pt_set_tiles(self._c, int(tile), int(rank), int(world)), "hc_pt_set_tiles")
 
+    def SetShadowTrees(self, mode):
+        """1 (library default): shadow rays walk every BVH tree, cut-outs occlude (GPUOCLLayer); 0: first tree only (the CPU integrators' shadowTrace)."""
+        check(self._L.hc_pt_set_shadow_trees(self._c, int(mode)), "hc_pt_set_shadow_trees")
+
     def SetMaterialSort(self, enable=True, from_bounce=1):
         """enable: False / 0 = off, True / 1 = on, "auto" / 2 = the default (on with >= 3 materials and >= 384k paths per pass)."""
         mode = 2 if enable in ("auto", 2) else (1 if enable else 0)
@@ -238,6 +242,29 @@ class CudaLayer:
     def GetLDRImage(self):
         out = np.empty((self.height, self.width), np.uint32)
         check(self._L.hc_fb_read_ldr(self._c, _ptr(out), self.width, self.height), "hc_fb_read_ldr")
+        return out
+
+    # ---- multi-GPU exchange inside the library (hc_comm.cu): one process per GPU, NCCL over NVLink
+    @staticmethod
+    def CommUniqueId():
+        """rank 0: 128 bytes of ncclGetUniqueId; the host distributes them (bench.py broadcasts them with torch.distributed)."""
+        buf = (ct.c_ubyte*128)()
+        check(load().hc_comm_unique_id(buf), "hc_comm_unique_id")
+        return bytes(buf)
+
+    def CommInit(self, unique_id, rank, world):
+        buf = (ct.c_ubyte*128).from_buffer_copy(bytes(unique_id))
+        check(self._L.hc_comm_init(self._c, buf, int(rank), int(world)), "hc_comm_init")
+
+    def ReduceFramebuffer(self, dst=0, mode=0):
+        """Combine the per-rank SUM buffers on `dst` (mode 0: owned tiles travel; mode 1: full-size sum).  Returns the device time in ms."""
+        ms = ct.c_float()
+        check(self._L.hc_fb_reduce(self._c, int(dst), int(mode), ct.byref(ms)), "hc_fb_reduce")
+        return ms.value
+
+    def GetSumImage(self):
+        out = np.empty((self.height, self.width, 4), np.float32)
+        check(self._L.hc_fb_read_sum(self._c, _ptr(out), self.width, self.height), "hc_fb_read_sum")
         return out
 
     def fb_device_ptr(self):

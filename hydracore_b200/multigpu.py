@@ -1,9 +1,11 @@
 """Multi-GPU plumbing: one process per GPU (torch.distributed), replicated scene, image plane partitioned in interleaved tiles
-(PT / MISPT) or sample indices partitioned modulo the world size (MISPT-QMC), HDR SUM buffers combined by one reduce over NVLink.
+(PT / MISPT) or sample indices partitioned modulo the world size (MISPT-QMC), HDR SUM buffers combined over NVLink.
 
 The reference's multi-GPU mode is one OS process per GPU adding partial framebuffers into a shared-memory image under a mutex
-(GPUOCLLayerOther.cpp:365-430, README.md:99-103); here the same sum is one NCCL reduce(SUM) of 4*W*H floats.  There is no per-bounce
-exchange, hence no collective inside any kernel.  The host logic below is backend-agnostic: the CPU tests run it over gloo."""
+(GPUOCLLayerOther.cpp:365-430, README.md:99-103).  Here the exchange lives in the product library (hc_comm.cu: hc_comm_init / hc_fb_reduce,
+NCCL send/recv of the owned tiles or ncclReduce of full-size buffers); this module only carries the NCCL unique id from rank 0 to the
+other ranks through torch.distributed (join_communicator) and mirrors the ownership rules for the CPU tests (gloo).  There is no
+per-bounce exchange, hence no collective inside any kernel."""
 import numpy as np
 
 
@@ -34,6 +36,21 @@ def owned_pixels(width, height, tile, rank, world):
 def qmc_sample_range(width, height, rank, world):
     """Sample slots of one QMC pass owned by `rank`: i = k*world + rank < W*H  (k_pt_generate, hc_path.cu)."""
     return np.arange(rank, width*height, world, dtype=np.int64)
+
+
+def join_communicator(layer, dist, device=None):
+    """Create the library's NCCL communicator across the ranks of `dist`: rank 0 makes the unique id (hc_comm_unique_id), torch.distributed
+    broadcasts its 128 bytes (plumbing only), every rank calls hc_comm_init."""
+    import torch
+    from .layer import CudaLayer
+    if dist is None or dist.get_world_size() == 1:
+        return
+    rank, world = dist.get_rank(), dist.get_world_size()
+    t = torch.zeros(128, dtype=torch.uint8, device=device if device is not None else "cpu")
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(CudaLayer.CommUniqueId()), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    layer.CommInit(bytes(t.cpu().numpy().tobytes()), rank, world)
 
 
 def reduce_sums(dist, tensor, dst=0):

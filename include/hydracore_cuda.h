@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define HC_ABI_VERSION 1
+#define HC_ABI_VERSION 2
 
 enum { HC_OK = 0, HC_E_ARG = -1, HC_E_STATE = -2, HC_E_NOMEM = -3, HC_E_NODEVICE = -4, HC_E_RANGE = -5 };
 
@@ -76,8 +76,8 @@ int hc_set_bvh_alpha(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, c
                                                                               /* tree 1 of the ConvertionResult: meshes with opacity maps + pTriangleAlpha / triAfNum
                                                                                  (RenderDriverRTE_AlphaTestTable.cpp:66-221; consumer BVH4InstTraverseAlpha, ctrace.h:1297).
                                                                                  Send tree 0 first (hc_set_bvh forgets an earlier tree 1).  Closest-hit launches then walk
-                                                                                 tree 0 and tree 1 with the hit carried along; shadow rays see tree 0 only, exactly like
-                                                                                 IntegratorCommon::rayTrace / shadowTrace (CPUExp_Integrators_Common.cpp:122-171)          */
+                                                                                 tree 0 and tree 1 with the hit carried along (IntegratorCommon::rayTrace,
+                                                                                 CPUExp_Integrators_Common.cpp:122-150); shadow rays: see hc_pt_set_shadow_trees             */
 int hc_bvh_device_layout(const void* nodes, int nodesNum, const void* trif4, int trif4Num, float* outNodesOrNull, float* outPairsOrNull,
                          int64_t outPairsCapacityFloats, int64_t* outPairsFloats, int* outStackBound);
                                                                               /* host only, no device needed: the re-layout hc_set_bvh applies before the upload (SoA quads, triangle
@@ -115,6 +115,10 @@ int hc_pt_set_tiles(hc_ctx* ctx, int tileSize, int rank, int worldSize);     /* 
 int hc_pt_set_material_sort(hc_ctx* ctx, int enable, int fromBounce);       /* material sort of the live-path queue before shading: replaces
                                                                                  bitonic_sort_gpu (bitonic_sort_gpu.cpp:90-158); enable 0 = off, 1 = on, 2 = auto (the default:
                                                                                  on with >= 3 materials and >= 384k paths per pass), from bounce 1 */
+int hc_pt_set_shadow_trees(hc_ctx* ctx, int mode);                            /* shadow rays and the second (alpha-tested) BVH tree: 1 (default) = every tree is walked and a
+                                                                                 cut-out occludes where its opacity texel passes, as GPUOCLLayer does (GPUOCLKernels.cpp:959-1000,
+                                                                                 BVH4InstTraverseShadowAlphaS ctrace.h:1748; binary opacity only); 0 = first tree only, as the CPU
+                                                                                 integrators do (IntegratorCommon::shadowTrace, CPUExp_Integrators_Common.cpp:163-171)        */
 int hc_pt_pass(hc_ctx* ctx, int integrator, int passes);                     /* BeginTracingPass+EndTracingPass, IHWLayer.h:133-134         */
 int hc_fb_clear(hc_ctx* ctx);                                                /* ClearAccumulatedColor, IHWLayer.h:140                       */
 int hc_fb_device_ptr(hc_ctx* ctx, float** outSumRGBA, int64_t* outFloats);   /* per-pixel SUM buffer (for the NCCL reduce over NVLink)      */
@@ -122,6 +126,17 @@ int hc_fb_read_hdr(hc_ctx* ctx, float* outRGBA, int width, int height);      /* 
 int hc_fb_read_sum(hc_ctx* ctx, float* outRGBA, int width, int height);      /* the raw per-pixel SUMS (what the OpenCL layer adds into the shared image,
                                                                                  GPUOCLLayerOther.cpp:365-430)                               */
 int hc_fb_read_ldr(hc_ctx* ctx, uint32_t* outRGBA8, int width, int height);  /* GetLDRImage, IHWLayer.h:149                                 */
+/* multi-GPU: one process (or host thread) per GPU, scene replicated, framebuffers combined over NVLink by NCCL inside the library.
+ * Replaces the shared-memory image + mutex of the reference's process-per-GPU mode (GPUOCLLayerOther.cpp:365-430). */
+int hc_comm_unique_id(void* out128);                                         /* ncclGetUniqueId: rank 0 creates it, the host distributes the 128 bytes */
+int hc_comm_init(hc_ctx* ctx, const void* uniqueId128, int rank, int nranks); /* ncclCommInitRank on the context's device                              */
+int hc_comm_version(int* outVersion);                                        /* version of the NCCL bound at run time (dlopen libnccl.so.2)            */
+int hc_fb_reduce(hc_ctx* ctx, int dstRank, int mode, float* outMsOrNull);    /* combine the per-rank SUM buffers on dstRank.  mode 0: interleaved tile partition
+                                                                                 (hc_pt_set_tiles with the communicator's rank / size): every rank sends only the pixels
+                                                                                 it owns (1/G of the image), the destination scatters them into its own SUM buffer -
+                                                                                 repeatable, nothing is counted twice.  mode 1: full-size buffers (sample partition of
+                                                                                 MISPT-QMC): ncclReduce(sum) into a separate buffer that hc_fb_read_* then read.  Without a
+                                                                                 communicator (one GPU) it is a no-op.  outMs = device time of the exchange on this rank */
 int hc_get_spp(hc_ctx* ctx, float* outSpp);                                  /* GetSPP, IHWLayer.h:207                                      */
 int hc_get_stats(hc_ctx* ctx, hc_stats* out);                                /* GetRaysStat, IHWLayer.h:155                                 */
 int hc_reset_stats(hc_ctx* ctx);                                             /* ResetPerfCounters, IHWLayer.h:145                           */

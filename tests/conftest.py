@@ -39,5 +39,6 @@ def ref(built):
 def layer(built):
     import hydracore_b200 as hc
     lay = hc.CudaLayer()
+    lay.SetShadowTrees(0)       # the parity tests compare with the CPU integrators, whose shadow rays see the first BVH tree only (IntegratorCommon::shadowTrace)
     yield lay
     lay.close()

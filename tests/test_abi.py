@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported_and_bound(built):
         assert hasattr(lib, n), f"{n} declared in include/hydracore_cuda.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.hc_abi_version() == 1
+    assert lib.hc_abi_version() == 2
 
 
 def test_no_device_means_loud_failure(built):
