@@ -482,6 +482,7 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
   p->haveNormalMaps = false;
   const std::vector<unsigned char>& gl = p->globalsHost;
   const int lightsNum = gi(HC_EG_lightsNum), lightsOffset = gi(HC_EG_lightsOffset);
+  std::vector<int> usedTex(ctx->alphaTexIdsHost.begin(), ctx->alphaTexIdsHost.end()), usedAux;      // texture ids the kernels can sample
   for (int l = 0; l < lightsNum; l++)
   {
     const float* L = reinterpret_cast<const float*>(gl.data()) + lightsOffset + l*HC_LIGHT_DATA_SIZE;
@@ -493,6 +494,9 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
       if (flags & 1) { why = "Perez sky model (SKY_LIGHT_USE_PEREZ_ENVIRONMENT) is not supported yet"; return HC_E_ARG; }
       if (l != gi(HC_EG_skyLightId)) { why = "more than one sky-dome light"; return HC_E_ARG; }
       if (!ctx->storage[HC_STORAGE_PDFS].ptr || tab < 0 || tab >= gi(HC_EG_pdfTableTableSize)) { why = "sky-dome light without a pdf table in the pdfs storage"; return HC_E_ARG; }
+      int so; memcpy(&so, L + HC_PLIGHT_COLOR_TEX_MATRIX, 4);                           // environment map: sampler at L + HC_SKY_DOME_SAMPLER0 (hc_shade.cuh)
+      if (so != HC_INVALID_TEXTURE && so >= 0 && HC_SKY_DOME_SAMPLER0 + so*4 + 12 <= HC_LIGHT_DATA_SIZE)
+      { int texId; memcpy(&texId, L + HC_SKY_DOME_SAMPLER0 + so*4 + 2, 4); if (texId > 0) usedTex.push_back(texId); }
       continue;
     }
     if (type == HC_PLAIN_LIGHT_TYPE_POINT_SPOT || type == HC_PLAIN_LIGHT_TYPE_DIRECT) continue;
@@ -540,35 +544,6 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
       }
     }
   }
-  // every image reachable through the texture tables: RGBA8 / float4, or single-channel (depth 1) float / 8-bit - what ReadImageSw4 / ReadImageSw1
-  // (hc_texture.cuh) implement - and wholly inside its storage
-  {
-    struct Tab { int offOff, sizeOff, slot; const char* name; };
-    const Tab tabs[2] = { { HC_EG_texturesTableOffset, HC_EG_texturesTableSize, HC_STORAGE_TEXTURES, "textures" },
-                          { HC_EG_texturesAuxTableOffset, HC_EG_texturesAuxTableSize, HC_STORAGE_TEXTURES_AUX, "textures_aux" } };
-    for (const Tab& tb : tabs)
-    {
-      if (!ctx->texturesDirty) break;                        // headers unchanged since the last validation
-      const int tOff = gi(tb.offOff), tSize = gi(tb.sizeOff);
-      const HcDevBuf& st = ctx->storage[tb.slot];
-      if (tSize <= 0 || !st.ptr) continue;
-      if (tOff < 0 || size_t(tOff) + size_t(tSize) > gl.size()/4) { why = std::string(tb.name) + " table lies outside the globals blob"; return HC_E_RANGE; }
-      for (int t = 0; t < tSize; t++)
-      {
-        int off4; memcpy(&off4, gl.data() + 4*(size_t(tOff) + size_t(t)), 4);
-        if (off4 < 0) continue;
-        if ((uint64_t(off4) + 1)*16 > st.bytes) { why = std::string(tb.name) + " table entry " + std::to_string(t) + " points outside the storage"; return HC_E_RANGE; }
-        int hdr[4];
-        if (cudaMemcpy(hdr, (const char*)st.ptr + size_t(off4)*16, 16, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); why = "reading a texture header back failed"; return HC_E_STATE; }
-        const int w = hdr[0], h = hdr[1], d = hdr[2], bpp = hdr[3];
-        const bool okFmt = (d == 1) ? (bpp == 1 || bpp == 4) : (bpp == 4 || bpp == 16);
-        if (w <= 0 || h <= 0 || !okFmt)
-        { why = std::string(tb.name) + " image " + std::to_string(t) + ": " + std::to_string(w) + "x" + std::to_string(h) + ", depth " + std::to_string(d) + ", " + std::to_string(bpp) +
-                " bytes per pixel is not a supported format (RGBA8, float4, single-channel float or 8-bit)"; return HC_E_ARG; }
-        if ((uint64_t(off4) + 1)*16 + uint64_t(w)*uint64_t(h)*uint64_t(bpp) > st.bytes) { why = std::string(tb.name) + " image " + std::to_string(t) + " does not fit into the storage"; return HC_E_RANGE; }
-      }
-    }
-  }
   // walk the material nodes REACHABLE from the materials table (the storage may hold stale or unused chunks after in-place updates)
   const size_t nNodes = p->materialsHost.size()/(HC_PLAIN_MATERIAL_DATA_SIZE*4);
   const int matTabOff = gi(HC_EG_materialsTableOffset), matTabSize = gi(HC_EG_materialsTableSize);
@@ -593,9 +568,24 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
                     type == HC_PLAIN_MAT_CLASS_PERFECT_MIRROR || type == HC_PLAIN_MAT_CLASS_GLASS || type == HC_PLAIN_MAT_CLASS_BLEND_MASK ||
                     type == HC_PLAIN_MAT_CLASS_EMISSIVE || type == HC_PLAIN_MAT_CLASS_OREN_NAYAR || type == HC_PLAIN_MAT_CLASS_TRANSLUCENT || type == HC_PLAIN_MAT_CLASS_THIN_GLASS;
     if (!ok) { why = "material class " + std::to_string(type) + " is not supported yet (Lambert, Oren-Nayar, translucent, Phong, Blinn, GGX, mirror, glass, thin glass, blend mask are)"; return HC_E_ARG; }
+    {
+      // texture ids behind the samplers this material class reads (Sample2D call sites of hc_shade.cuh): sampler offset in float4 from the node start
+      int slots[3] = { HC_EMISSIVE_TEXMATRIXID_OFFSET, HC_LAMBERT_TEXMATRIXID_OFFSET, -1 };
+      if (type == HC_PLAIN_MAT_CLASS_PHONG_SPECULAR || type == HC_PLAIN_MAT_CLASS_BLINN_SPECULAR || type == HC_PLAIN_MAT_CLASS_THIN_GLASS || type == HC_PLAIN_MAT_CLASS_GGX) slots[2] = HC_PHONG_GLOSINESS_TEXMATRIXID_OFFSET;
+      if (type == HC_PLAIN_MAT_CLASS_GLASS) slots[2] = HC_GLASS_GLOSINESS_TEXMATRIXID_OFFSET;
+      if (type == HC_PLAIN_MAT_CLASS_EMISSIVE) slots[1] = -1;
+      for (int sl : slots)
+      {
+        if (sl < 0) continue;
+        int so; memcpy(&so, m + sl, 4);
+        if (so == HC_INVALID_TEXTURE || so < 0 || so*4 + 12 > HC_PLAIN_MATERIAL_DATA_SIZE) continue;
+        int texId; memcpy(&texId, m + so*4 + 2, 4);
+        if (texId > 0) usedTex.push_back(texId);
+      }
+    }
     if (ntex != HC_INVALID_TEXTURE)            // normal map: image in the "textures_aux" storage, found through the aux texture table
     {
-      p->haveNormalMaps = true;
+      p->haveNormalMaps = true; usedAux.push_back(ntex);
       if (!ctx->storage[HC_STORAGE_TEXTURES_AUX].ptr || ntex < 0 || ntex >= gi(HC_EG_texturesAuxTableSize)) { why = "normal map without an image in the textures_aux storage"; return HC_E_ARG; }
       int auxOff; memcpy(&auxOff, gl.data() + 4*size_t(gi(HC_EG_texturesAuxTableOffset) + ntex), 4);
       if (auxOff < 0) { why = "normal map texture id has no entry in the aux texture table"; return HC_E_ARG; }
@@ -610,6 +600,35 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
       if (o1 == 0 || o2 == 0) { why = "blend mask node references itself"; return HC_E_ARG; }
       todo.push_back(f0 + (long long)o1*HC_PLAIN_MATERIAL_DATA_SIZE);               // children by RELATIVE node offset (cmaterial.h:1994-1995)
       todo.push_back(f0 + (long long)o2*HC_PLAIN_MATERIAL_DATA_SIZE);
+    }
+  }
+  // every image the kernels can sample: RGBA8 / float4, or single-channel (depth 1) float / 8-bit - what ReadImageSw4 / ReadImageSw1
+  // (hc_texture.cuh) implement - and wholly inside its storage.  (Unreferenced slots of a storage may hold anything.)
+  if (ctx->texturesDirty)
+  {
+    struct Tab { int offOff, sizeOff, slot; const char* name; const std::vector<int>* ids; };
+    const Tab tabs[2] = { { HC_EG_texturesTableOffset, HC_EG_texturesTableSize, HC_STORAGE_TEXTURES, "textures", &usedTex },
+                          { HC_EG_texturesAuxTableOffset, HC_EG_texturesAuxTableSize, HC_STORAGE_TEXTURES_AUX, "textures_aux", &usedAux } };
+    for (const Tab& tb : tabs)
+    {
+      const int tOff = gi(tb.offOff), tSize = gi(tb.sizeOff);
+      const HcDevBuf& st = ctx->storage[tb.slot];
+      std::vector<int> ids(*tb.ids); std::sort(ids.begin(), ids.end()); ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+      for (int t : ids)
+      {
+        if (t <= 0 || t >= tSize || tOff < 0 || size_t(tOff) + size_t(tSize) > gl.size()/4) continue;      // the fetch treats these as "no image"
+        int off4; memcpy(&off4, gl.data() + 4*(size_t(tOff) + size_t(t)), 4);
+        if (off4 < 0) continue;
+        if (!st.ptr || (uint64_t(off4) + 1)*16 > st.bytes) { why = std::string(tb.name) + " table entry " + std::to_string(t) + " points outside the storage"; return HC_E_RANGE; }
+        int hdr[4];
+        if (cudaMemcpy(hdr, (const char*)st.ptr + size_t(off4)*16, 16, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); why = "reading a texture header back failed"; return HC_E_STATE; }
+        const int w = hdr[0], h = hdr[1], d = hdr[2], bpp = hdr[3];
+        const bool okFmt = (d == 1) ? (bpp == 1 || bpp == 4) : (bpp == 4 || bpp == 16);
+        if (w <= 0 || h <= 0 || !okFmt)
+        { why = std::string(tb.name) + " image " + std::to_string(t) + ": " + std::to_string(w) + "x" + std::to_string(h) + ", depth " + std::to_string(d) + ", " + std::to_string(bpp) +
+                " bytes per pixel is not a supported format (RGBA8, float4, single-channel float or 8-bit)"; return HC_E_ARG; }
+        if ((uint64_t(off4) + 1)*16 + uint64_t(w)*uint64_t(h)*uint64_t(bpp) > st.bytes) { why = std::string(tb.name) + " image " + std::to_string(t) + " does not fit into the storage"; return HC_E_RANGE; }
+      }
     }
   }
   return HC_OK;

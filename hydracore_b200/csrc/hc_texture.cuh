@@ -85,6 +85,7 @@ HC_DEV float4 ReadImageSw4(const int4* tex, float2 tc, int flags, bool srgb)
 {
   const int4 header = *tex;
   const int w = header.x, h = header.y, bpp = header.w;
+  if (w <= 0 || h <= 0) return make_float4(1.0f, 1.0f, 1.0f, 1.0f);      // empty slot: nothing to read (the reference would divide by zero)
   if (header.z == 1) { const float v = ReadImageSw1(tex, tc, flags); return make_float4(v, v, v, 1.0f); }
   float ffx = tc.x*(float)w - 0.5f, ffy = tc.y*(float)h - 0.5f;
   if ((flags & HC_TEX_CLAMP_U) != 0 && ffx < 0) ffx = 0.0f;

@@ -23,7 +23,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 out = {"world": world}
-scn = scenes.cornell_box(200, 152)
+scn = scenes.cornell(200, 152)
 lay = hc.CudaLayer(device=local)
 lay.LoadScene(scn)
 MG.join_communicator(lay, dist, dev)

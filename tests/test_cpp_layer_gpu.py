@@ -171,6 +171,7 @@ def test_ihwlayer_two_trees_with_alpha_table_equals_c_abi_path(consts, layer):
     """SetAllBVH4 with a two-tree ConvertionResult (tree 1 = meshes with opacity maps + pTriangleAlpha, GPUOCLData.cpp:103-116) through IHWLayer."""
     scn = scenes.cornell_with_cutout(64, 64)
     lay = _make(scn, consts)
+    lay.CallNamedFunc("shadow_trees", "0")        # like the session's C-ABI layer: shadow rays as the CPU integrators trace them
     lay.InitPathTracing(9)
     lay.TracingPasses(2)
     a = lay.GetHDRImage()
