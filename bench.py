@@ -2,16 +2,17 @@
 """bench.py — headline benchmark of the hot path (BASELINE.json configs[1], "C2"):
 synthetic 1,001,112-triangle mesh, 1920x1080 primary + shadow ray casting through the CUDA layer.
 
-    python bench.py --gpus 1 --steps 20 --warmup 3                   # our arm (sm_100a kernels behind the C ABI)
+    python bench.py --gpus 1 --steps 20 --warmup 3                   # our arm (sm_100a kernels behind the C ABI / the C++ IHWLayer)
     python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # the reference's own CPU code on the host cores
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one ray-casting pass over the whole screen: K1 eye rays -> K2 closest hit -> shadow rays to a point light ->
-K2s any hit (hc_raycast_pass).  value = (primary + shadow rays) / device time, inputs resident in HBM; e2e = the same pass
-through the reference-facing call sequence with HOST buffers: upload of the EngineGlobals blob (what RenderDriverRTE::Draw
-does before every pass, RenderDriverRTE.cpp:1723-1725) + pass + read-back of the hit and visibility buffers to pinned host
-memory.  At N > 1 every rank casts its own full frame (one process per GPU, replicated scene, no data-path collective:
-the reference's process-per-GPU mode, README.md:99-103) — weak scaling.
+K2s any hit (hc_raycast_pass).  value = (primary + shadow rays of the frame) / device time, inputs resident in HBM; e2e = the same pass
+driven through the reference's plugin interface - the C++ GPUCUDALayer : IHWLayer (PrepareEngineGlobals / Tables as RenderDriverRTE::Draw
+does before every pass, RenderDriverRTE.cpp:1723-1725, then BeginTracingPass / EndTracingPass) - with HOST result buffers.
+At N > 1 the SAME frame is split over the GPUs in interleaved 32x32 tiles (one process per GPU, scene replicated): every rank casts the
+rays of its tiles and the hit / visibility records are gathered on rank 0 over NVLink by the library (NCCL send / recv of the owned
+pixels, hc_comm.cu) inside the timed step - strong scaling of one frame.
 """
 import argparse
 import json
@@ -19,7 +20,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 WIDTH, HEIGHT = 1920, 1080
 METRIC, UNIT = "Mrays/s", "Mrays/s"
 WORKLOAD = "C2: synthetic 1,001,112-triangle mesh, 1920x1080 primary + shadow ray casting"
+TILE = 32
 
 
 def _peaks():
@@ -97,6 +98,12 @@ def _dist():
 
 
 # ------------------------------------------------------------------------------------------------------------ reference arm
+def _ref_threads(ref):
+    """All host threads the reference code can use: the affinity mask, capped at the reference's own INTEGRATOR_MAX_THREADS_NUM = 32
+    (CPUExp_Integrators.h:267).  Set explicitly: torchrun exports OMP_NUM_THREADS=1, which libgomp would otherwise obey."""
+    return ref.omp_threads(min(len(os.sched_getaffinity(0)), 32))
+
+
 def reference_rays(scn, ref):
     """Primary rays of the frame (zero jitter) from the reference's own MakeRandEyeRay."""
     from tests import refapi, scenes
@@ -106,25 +113,12 @@ def reference_rays(scn, ref):
 
 
 def reference_step(scn, ref, rays):
-    """One pass of the reference CPU path over `rays`: closest hit (BVH4InstTraverse via IntegratorCommon::rayTrace semantics),
-    shadow rays to the point light, shadow query (IntegratorCommon::shadowTrace semantics).  Returns rays traced."""
+    """One pass of the reference CPU path over `rays`, entirely inside the reference library (oracle/ref_driver.cpp ref_raycast_step): closest
+    hit (BVH4InstTraverse, IntegratorCommon::rayTrace semantics), one shadow ray per hit to the point light, shadow query
+    (IntegratorCommon::shadowTrace semantics).  Returns rays traced."""
     from hydracore_b200.scene import C2_LIGHT_POS
-    nodes, tris = scn.bvh["nodes"], scn.bvh["tris"]
-    hits = ref.trace_closest(nodes, tris, rays)
-    hit = hits["primId"] >= 0
-    pos = rays[:, 0:3] + rays[:, 4:7]*hits["t"][:, None]
-    L = np.array(C2_LIGHT_POS, np.float32)
-    d = L - pos[hit]
-    dist = np.sqrt((d*d).sum(1))
-    sd = d/dist[:, None]
-    eps = np.maximum(np.abs(pos[hit]).max(1), 1.0)*np.float32(1e-4)
-    sp = pos[hit] + sd*eps[:, None]
-    sh = np.zeros((sp.shape[0], 8), np.float32)
-    sh[:, 0:3] = sp
-    sh[:, 4:7] = sd
-    sh[:, 7] = np.sqrt(((sp - L)**2).sum(1))*np.float32(0.995)
-    ref.trace_shadow(nodes, tris, sh)
-    return rays.shape[0] + sh.shape[0]
+    _h, _v, traced = ref.raycast_step(scn.bvh["nodes"], scn.bvh["tris"], rays, C2_LIGHT_POS)
+    return traced
 
 
 def cpu_baseline(scn, budget_s=12.0):
@@ -133,32 +127,60 @@ def cpu_baseline(scn, budget_s=12.0):
     which define the algorithmic bytes of the roofline."""
     from tests import refapi
     ref = refapi.Ref.try_load()
-    kind = "reference"
     if ref is None:
         raise RuntimeError("oracle/_ref/libhydra_ref.so is missing (built by __graft_entry__.build() where /root/reference exists)")
-    cores = len(os.sched_getaffinity(0))
-    cores = min(cores, 32) if False else cores
+    threads = _ref_threads(ref)
     rays = reference_rays(scn, ref)
     n = rays.shape[0]
-    # calibrate on 1/32 of the frame (strided rows keep the sample representative), then size the sample for ~budget seconds
-    probe = rays[::32]
+    # calibrate on 1/32 of the frame (strided pixels keep the sample representative), then size the sample for ~budget seconds
+    probe = np.ascontiguousarray(rays[::32])
     t0 = time.perf_counter()
     traced = reference_step(scn, ref, probe)
-    dt = time.perf_counter() - t0
-    rate = traced/dt
-    frac = min(1.0, budget_s*rate/(2.0*n))
-    stride = max(1, int(round(1.0/frac)))
-    sample = rays[::stride]
+    rate = traced/(time.perf_counter() - t0)
+    stride = max(1, int(round(2.0*n/(budget_s*rate))))
+    sample = np.ascontiguousarray(rays[::stride])
     t0 = time.perf_counter()
     traced = reference_step(scn, ref, sample)
     dt = time.perf_counter() - t0
     orc = refapi.Oracle()
-    sub = rays[::61]
+    sub = np.ascontiguousarray(rays[::61])
     _h, cnt = orc.trace_closest(scn.bvh["nodes"], scn.bvh["tris"], sub, count=True)
     qlt = [float(c)/sub.shape[0] for c in cnt]
-    return {"value": traced/dt/1e6, "unit": UNIT, "cores": cores, "kind": kind,
+    return {"value": traced/dt/1e6, "unit": UNIT, "cores": threads, "kind": "reference",
             "sample": "every %d-th pixel of the 1080p frame: %d primary + shadow rays in %.2f s; closest hit = reference BVH4InstTraverse "
-                      "(Embree unavailable), OpenMP over all host threads" % (stride, traced, dt)}, qlt
+                      "(Embree unavailable), OpenMP on %d threads (omp_get_max_threads)" % (stride, traced, dt, threads)}, qlt
+
+
+def cpu_baseline_pt(scn, kind, label, window):
+    """The reference's own CPU integrator (oracle/_ref) on a pixel window of the same scene: paths/s on the host cores."""
+    from tests import refapi
+    ref = refapi.Ref.try_load()
+    if ref is None:
+        return None
+    threads = _ref_threads(ref)
+    rs = ref.scene(scn)
+    x0, y0, x1, y1 = window
+    if kind == 3:
+        W = scn.width
+        first, count = y0*W, (y1 - y0)*W                       # QMC passes take a range of sample indices (they land on arbitrary pixels)
+        r = ref.L.ref_render_create(rs.h, 3, 777)
+        rs._renders.append(r)
+        ref.L.ref_render_pass_qmc_range(r, first, min(count, 4096))
+        t0 = time.perf_counter()
+        ref.L.ref_render_pass_qmc_range(r, first, count)
+        dt = time.perf_counter() - t0
+        paths = count
+        what = "%d consecutive sample indices of one pass" % count
+    else:
+        rs.render(kind, 777, 1, window=(x0, y0, min(x1, x0 + 64), min(y1, y0 + 16)))        # warm-up
+        t0 = time.perf_counter()
+        rs.render(kind, 777, 1, window=window)
+        dt = time.perf_counter() - t0
+        paths = (x1 - x0)*(y1 - y0)
+        what = "pixel window [%d, %d) x [%d, %d), 1 pass" % (x0, x1, y0, y1)
+    rs.close()
+    return {"paths_per_s": paths/dt, "cores": threads, "kind": "reference",
+            "sample": "%s by %s (oracle/_ref, OpenMP on %d threads, BVH4InstTraverse instead of Embree), %.2f s" % (what, label, threads, dt)}
 
 
 def run_reference(args):
@@ -172,16 +194,17 @@ def run_reference(args):
     if ref is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhydra_ref.so missing"}))
         return 0
+    threads = _ref_threads(ref)
     scn = S.scene_c2(WIDTH, HEIGHT)
     rays = reference_rays(scn, ref)
-    cores = len(os.sched_getaffinity(0))
     # bounded sample per step: calibrate so that (steps + warmup) x sample stays within ~2 minutes
+    probe = np.ascontiguousarray(rays[::64])
     t0 = time.perf_counter()
-    traced = reference_step(scn, ref, rays[::64])
+    traced = reference_step(scn, ref, probe)
     rate = traced/(time.perf_counter() - t0)
     per_step_s = min(20.0, 120.0/max(1, args.steps + args.warmup))
     stride = max(1, int(round(2.0*rays.shape[0]/(per_step_s*rate))))
-    sample = rays[::stride]
+    sample = np.ascontiguousarray(rays[::stride])
     for _ in range(args.warmup):
         reference_step(scn, ref, sample)
     t0 = time.perf_counter()
@@ -191,22 +214,44 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = traced/dt/1e6
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3*dt/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": 1e3*dt/args.steps, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "triangles": 1001112,
-                                            "sample": "every %d-th pixel per step" % stride},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
-                             "sample": "every %d-th pixel of the frame per step, %d rays per step" % (stride, traced//max(1, args.steps))},
+                                            "sample": "every %d-th pixel per step" % stride, "omp_threads": threads},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": "every %d-th pixel of the frame per step, %d rays per step, OpenMP on %d threads" % (stride, traced//max(1, args.steps), threads)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
 # ------------------------------------------------------------------------------------------------------------ our arm
+def _incoherent_rays(torch, dev, rays, hits, n):
+    """Cosine-distributed secondary rays from the primary hit points: fully incoherent directions, origins in pixel order."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    h = hits.view(-1, 4)
+    hit = h[:, 1] >= 0
+    t = h[:, 0].view(torch.float32)
+    r8 = rays.view(-1, 8)
+    pos = r8[:, 0:3] + r8[:, 4:7]*t[:, None]
+    nh = int(hit.sum().item())
+    u = torch.rand(nh, 2, device=dev, generator=g)
+    rr = torch.sqrt(u[:, 0])
+    phi = 2*np.pi*u[:, 1]
+    d = torch.stack([rr*torch.cos(phi), torch.sqrt(1 - u[:, 0]).clamp_min(1e-3), rr*torch.sin(phi)], 1)
+    inc = torch.zeros(nh, 8, device=dev)
+    inc[:, 0:3] = pos[hit] + torch.tensor([0, 1e-3, 0], device=dev)
+    inc[:, 4:7] = d/d.norm(dim=1, keepdim=True)
+    inc[:, 7] = 3.0e38
+    return inc.contiguous(), nh
+
+
 def run_ours(args):
     import torch
     import hydracore_b200 as hc
     from hydracore_b200 import scene as S
-    from hydracore_b200._lib import HC_HOST, HC_DEVICE
+    from hydracore_b200 import multigpu as MG
+    from hydracore_b200._lib import HC_DEVICE
     world, rank, local = _dist()
     dist = None
     if world > 1:
@@ -223,10 +268,13 @@ def run_ours(args):
     lay.LoadScene(scn)
     n = WIDTH*HEIGHT
     light = S.C2_LIGHT_POS
+    if world > 1:
+        lay.SetTiles(TILE, rank, world)              # this rank's interleaved 32x32 tiles of the ONE frame
+        MG.join_communicator(lay, dist, dev)         # NCCL communicator inside the library (unique id carried by torch.distributed)
 
-    # device-resident result buffers owned by torch (so that NCCL / torch can see them) and pinned host mirrors for e2e
-    hits_d = torch.empty(n*4, dtype=torch.int32, device=dev)
-    vis_d = torch.empty(n, dtype=torch.uint8, device=dev)
+    # device-resident result buffers owned by torch and pinned host mirrors for e2e (complete on rank 0)
+    hits_d = torch.zeros(n*4, dtype=torch.int32, device=dev)
+    vis_d = torch.zeros(n, dtype=torch.uint8, device=dev)
     hits_h = torch.empty(n*4, dtype=torch.int32, pin_memory=True)
     vis_h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     flush = torch.empty(256*1024*1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -237,7 +285,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_device():
-        lay.RaycastPass(light, hits_d.data_ptr(), vis_d.data_ptr(), HC_DEVICE)
+        lay.RaycastPass(light, hits_d.data_ptr(), vis_d.data_ptr(), HC_DEVICE)      # split frame: includes the gather of the records on rank 0
         return lay.last_trace_ms()
 
     sampler = ClockSampler(local)
@@ -254,126 +302,167 @@ def run_ours(args):
     ms = []
     for _ in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (outside the per-step CUDA events)
-        torch.cuda.synchronize()
-        ms.append(step_device())            # device time of the 4 kernels of this step, CUDA events on the launching stream
+        barrier()
+        ms.append(step_device())            # device time of this step's launches (+ gather), CUDA events on the launching stream
     barrier()
     clocks = sampler.stop(t_load, time.time())
     stats = lay.GetRaysStat()
-    shadow_rays = int(vis_d.numel())        # one shadow ray slot per pixel (missed pixels carry t_far = 0 and are not traced)
-    n_hit = int((hits_d.view(-1, 4)[:, 1] >= 0).sum().item())
-    rays_per_step = n + n_hit
+    n_hit = int((hits_d.view(-1, 4)[:, 1] >= 0).sum().item())       # rank 0 holds the whole frame
     t_step = float(np.sum(ms))/1e3
+    launches = float(stats["kernelLaunches"])
     if dist is not None:
         t = torch.tensor([t_step], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_step = float(t.item())
-        tot = torch.tensor([float(rays_per_step)], device=dev, dtype=torch.float64)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        rays_all = float(tot.item())
+        c = torch.tensor([float(n_hit) if rank == 0 else 0.0, launches, stats["msClosest"], stats["msShadow"], stats["msOther"]], device=dev, dtype=torch.float64)
+        mx = c.clone()
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        n_hit, launches = int(c[0].item()), float(c[1].item())
+        ms_closest_max, ms_shadow_max, ms_other_max = float(mx[2].item()), float(mx[3].item()), float(mx[4].item())
     else:
-        rays_all = float(rays_per_step)
-    value = rays_all*args.steps/t_step/1e6
+        ms_closest_max, ms_shadow_max, ms_other_max = stats["msClosest"], stats["msShadow"], stats["msOther"]
+    rays_per_step = n + n_hit                # one frame: every pixel's primary ray + one shadow ray per hit
+    value = rays_per_step*args.steps/t_step/1e6
     ms_per_step = 1e3*t_step/args.steps
+
+    # ---- incoherent secondary rays (N = 1): cosine-distributed about the up axis from the primary hit points, closest hit, L2 flushed
+    mrays_incoherent = None
+    if world == 1:
+        rays = torch.empty(n*8, dtype=torch.float32, device=dev)
+        lay.make_eye_rays_device(WIDTH, HEIGHT, rays.data_ptr())
+        inc, nh = _incoherent_rays(torch, dev, rays, hits_d, n)
+        hits2 = torch.empty(nh*4, dtype=torch.int32, device=dev)
+        tms = []
+        for k in range(3 + 10):
+            flush.zero_()
+            torch.cuda.synchronize()
+            lay.trace_closest_device(inc.data_ptr(), nh, hits2.data_ptr())
+            if k >= 3:
+                tms.append(lay.last_trace_ms())
+        mrays_incoherent = {"value": nh/float(np.median(tms))/1e3, "unit": "Mrays/s", "rays": nh, "ms": float(np.median(tms)),
+                            "hit_fraction": float((hits2.view(-1, 4)[:, 1] >= 0).float().mean().item()),
+                            "what": "closest hit of cosine-distributed secondary rays leaving the primary hit points of the C2 frame (pixel order), rays resident in HBM, L2 flushed, median of 10"}
+        del rays, inc, hits2
 
     # ---- measured denominators beside MEASURED_PEAKS.json: L2 read bandwidth (48 MiB working set, 20 sweeps) and HBM read bandwidth (2 GiB, 1 sweep)
     mem_peaks = None
     if rank == 0:
         mem_peaks = {"l2_read_gbs": lay.measure_read_bandwidth(48 << 20, 20), "hbm_read_gbs": lay.measure_read_bandwidth(2 << 30, 1),
-                     "how": "hc_measure_read_bandwidth: 128-bit ld.global.cg streaming reads, 148 x 8 CTAs, best of 5"}
+                     "how": "hc_measure_read_bandwidth: 128-bit ld.global.cg streaming reads, 148 x 8 CTAs, best of 5 (its ncu record: profiles/r02_l2_microbench_ncu.md)"}
 
-    # ---- e2e: globals upload + pass + read-back to pinned host memory, wall clock around synchronous API calls
-    blob = torch.from_numpy(scn.globals_blob.copy()).pin_memory()
-    blob_np = blob.numpy()
+    # ---- e2e through the reference's plugin interface: GPUCUDALayer : IHWLayer (C++), host result buffers
+    e2e = None
+    from tests import layerapi
+    if layerapi.CppLayer.available():
+        consts = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_consts.json")))
+        cpp = layerapi.CppLayer(WIDTH, HEIGHT, 0, local)
+        layerapi.load_scene_like_render_driver(cpp, scn, consts)
+        varsI, varsF, flags = cpp.GetAllFlagsAndVars()
+        cpp.SetAllFlagsAndVars(varsI, varsF, flags & ~consts["HRT_UNIFIED_IMAGE_SAMPLING"])      # ray-casting mode of the layer (BeginTracingPass without unified sampling)
+        cpp.CallNamedFunc("raycast_light", "%r %r %r" % tuple(float(v) for v in light))
+        if world > 1:
+            cpp.CallNamedFunc("tiles", "%d %d %d" % (TILE, rank, world))
+            idt = torch.zeros(256, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(cpp.CommIdHex().encode()), dtype=torch.uint8))
+            dist.broadcast(idt, src=0)
+            cpp.CallNamedFunc("comm", "%d %d %s" % (rank, world, bytes(idt.cpu().numpy().tobytes()).decode()))
+        cpp.CallNamedFunc("raycast_results", "%d %d" % ((hits_h.data_ptr(), vis_h.data_ptr()) if rank == 0 else (0, 0)))
 
-    def step_e2e():
-        lay.PrepareEngineGlobals(blob_np)
-        lay.RaycastPass(light, hits_h.data_ptr(), vis_h.data_ptr(), HC_HOST)
+        def step_e2e():
+            cpp.PrepareEngineGlobalsAndTables()      # RenderDriverRTE::Draw re-assembles and re-uploads the globals before every pass
+            cpp.TracingPasses(1)                     # BeginTracingPass + EndTracingPass
 
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    te = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([te], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        te = float(t.item())
-    e2e_value = rays_all*args.steps/te/1e6
-    # parity guard: the host copy must agree with the device-resident result
-    assert torch.equal(hits_h, hits_d.cpu()) and torch.equal(vis_h, vis_d.cpu())
+        for _ in range(3):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        te = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([te], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t.item())
+        if rank == 0:
+            # parity guard: the host copy from the plugin path must agree with the device-resident result of the C-ABI path
+            assert torch.equal(hits_h, hits_d.cpu()) and torch.equal(vis_h, vis_d.cpu()), "IHWLayer ray-casting results differ from the C-ABI path"
+        e2e = {"value": rays_per_step*args.steps/te/1e6, "unit": UNIT, "h2d_bytes_per_step": int(scn.globals_blob.nbytes),
+               "d2h_bytes_per_step": int(n*16 + n), "ms_per_step": 1e3*te/args.steps,
+               "path": "GPUCUDALayer : IHWLayer (libhydra_cuda_layer.so): PrepareEngineGlobals + PrepareEngineTables + BeginTracingPass + EndTracingPass, results in host memory (rank 0)"}
+        cpp.close()
+    else:
+        raise RuntimeError("hydracore_b200/cpp/_build/libhydra_cuda_layer.so is missing: the e2e leg goes through the C++ IHWLayer (build() makes it where /root/reference exists)")
 
-    # ---- C3 / C4 (reported next to the headline): MISPT on the 1M-triangle terrain with mixed materials + 2 area lights, and on the
-    # 20M-triangle instanced scene (fully incoherent diffuse secondary rays, compaction + material sort in the loop).  Image plane in
-    # interleaved 32x32 tiles across the ranks, HDR sums combined by one NCCL reduce: strong scaling of one frame.
+    # ---- C1 / C3 / C4 / C5 (reported next to the headline): path tracing.  Image plane in interleaved 32x32 tiles across the ranks (C5: sample
+    # indices modulo the world size), framebuffers combined on rank 0 by hc_fb_reduce INSIDE the timed frame: strong scaling of one frame.
     extras = {}
     if not args.no_c3:
-        from hydracore_b200 import multigpu as MG
         lay.close()
-        for key, label, build in (("c1", "C1: hydra_app/tests/test_42 (25,612 triangles, Lambert / Phong blend / emissive, rect area light, DOF), unidirectional PT, 512x512",
-                                   lambda: __import__("hydracore_b200.hydra_scene", fromlist=["x"]).build_scene(
-                                       __import__("hydracore_b200.hydra_scene", fromlist=["x"]).load_fixture(os.path.join(ROOT, "tests", "golden", "hydra_scenes.npz"), "test_42"), 512, 512)),
-                                  ("c3", "C3: MISPT trace_depth 8, Lambert/GGX/glass/blend + 2 area lights, 1,001,116 triangles, 1080p, 32x32 interleaved tiles",
-                                   lambda: S.scene_c3(WIDTH, HEIGHT)),
-                                  ("c4", "C4: MISPT trace_depth 5 on 200 instances x 100,352 triangles = 20,070,400 instanced triangles, Lambert, 1080p, 32x32 interleaved tiles",
-                                   lambda: S.scene_c4(WIDTH, HEIGHT)),
-                                  ("c5", "C5: MISPT-QMC (Sobol-Niederreiter screen + lens dimensions) on the C3 scene at 3840x2160; rank g takes the sample indices "
-                                         "i = g (mod G) of every pass into a full-size SUM buffer, one NCCL reduce of 8,294,400 x float4",
-                                   lambda: S.scene_c3(3840, 2160))):
+        HS = __import__("hydracore_b200.hydra_scene", fromlist=["x"])
+        for key, label, build, window in (
+                ("c1", "C1: hydra_app/tests/test_42 (25,612 triangles, Lambert / Phong blend / emissive, rect area light, DOF), unidirectional PT, 512x512",
+                 lambda: HS.build_scene(HS.load_fixture(os.path.join(ROOT, "tests", "golden", "hydra_scenes.npz"), "test_42"), 512, 512), (0, 0, 512, 512)),
+                ("c3", "C3: MISPT trace_depth 8, Lambert/GGX/glass/blend + 2 area lights, 1,001,116 triangles, 1080p, 32x32 interleaved tiles",
+                 lambda: S.scene_c3(WIDTH, HEIGHT), (704, 412, 1216, 668)),
+                ("c4", "C4: MISPT trace_depth 5 on 200 instances x 100,352 triangles = 20,070,400 instanced triangles, 6 materials (material sort on), 1080p, 32x32 interleaved tiles",
+                 lambda: S.scene_c4(WIDTH, HEIGHT), (704, 412, 1216, 668)),
+                ("c5", "C5: MISPT-QMC (Sobol-Niederreiter screen + lens dimensions) on the C3 scene at 3840x2160; rank g takes the sample indices "
+                       "i = g (mod G) of every pass into a full-size SUM buffer, ncclReduce of 8,294,400 x float4 inside the frame",
+                 lambda: S.scene_c3(3840, 2160), (0, 1000, 3840, 1034))):
             if args.profile and key != "c3":
                 continue                               # profiler runs: the C2 steps and the C3 passes only (keeps the ncu launch list short and stable)
             scn3 = build()
             lay = hc.CudaLayer(device=local)
             lay.LoadScene(scn3)
             integ = {"c1": 0, "c5": 3}.get(key, 2)     # C1: unidirectional PT (INTEGRATOR_PT = 0); C3 / C4: MISPT (= 2); C5: MISPT-QMC (= 3)
-            lay.SetTiles(32, rank, world)
+            mode = 1 if key == "c5" else 0
+            lay.SetTiles(TILE, rank, world)
+            if world > 1:
+                MG.join_communicator(lay, dist, dev)
             lay.InitPathTracing(777)
             lay.TracingPass(integ, 2)                  # warm-up passes
+            lay.ReduceFramebuffer(0, mode)             # warm-up of the exchange (NCCL connects lazily)
             lay.ResetPerfCounters()
             barrier()
             passes = 64 if key == "c1" else 4
             t0 = time.perf_counter()
             lay.TracingPass(integ, passes)
-            barrier()
             t_pass = time.perf_counter() - t0
+            red_ms = lay.ReduceFramebuffer(0, mode)    # the frame is not complete before rank 0 holds it
+            barrier()
+            t_frame = time.perf_counter() - t0
             st3 = lay.GetRaysStat()
             ev_ms = st3["msClosest"] + st3["msShadow"] + st3["msShade"] + st3["msOther"]
-            t0 = time.perf_counter()
-            fb = MG.reduce_framebuffer(lay, dist, dev, dst=0)
-            t_red = time.perf_counter() - t0
-            vals = torch.tensor([t_pass, ev_ms, t_red, float(st3["paths"]), float(st3["raysClosest"]), float(st3["raysShadow"]),
-                                 st3["msClosest"], st3["msShadow"], st3["msShade"], st3["msOther"]], device=dev, dtype=torch.float64)
+            vals = torch.tensor([t_frame, ev_ms, red_ms, float(st3["paths"]), float(st3["raysClosest"]), float(st3["raysShadow"]),
+                                 st3["msClosest"], st3["msShadow"], st3["msShade"], st3["msOther"], t_pass], device=dev, dtype=torch.float64)
             mx, sm = vals.clone(), vals.clone()
             if dist is not None:
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX)
                 dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             mx, sm = mx.tolist(), sm.tolist()
-            mean_img = float((fb.view(-1, 4)[:, :3].sum()/(scn3.width*scn3.height*3*(passes + 2))).item()) if rank == 0 else 0.0
-            extras[key] = {"workload": label, "passes": passes, "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": mx[1]/passes,
+            mean_img = float(lay.GetSumImage()[..., :3].sum()/(scn3.width*scn3.height*3*(passes + 2))) if rank == 0 else 0.0
+            extras[key] = {"workload": label, "passes": passes, "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": (mx[1] + mx[2])/passes,
+                           "ms_per_pass_without_reduce_wall_max": 1e3*mx[10]/passes,
                            "paths_per_s": sm[3]/mx[0], "mrays_per_s": (sm[4] + sm[5])/mx[0]/1e6,
                            "rays_closest_per_pass": sm[4]/passes, "rays_shadow_per_pass": sm[5]/passes,
                            "stage_ms_per_pass_max": {"closest": mx[6]/passes, "shadow_added": mx[7]/passes, "shade": mx[8]/passes, "raygen_sort": mx[9]/passes},
                            "stage_note": "closest-hit and any-hit launches of a bounce overlap on two streams: shadow_added = time from the end of the closest-hit launch to the join",
-                           "reduce_ms": 1e3*mx[2], "reduce_bytes": scn3.width*scn3.height*16 if world > 1 else 0, "mean_radiance": mean_img,
-                           "scaling": "strong (one frame split over the ranks)"}
+                           "reduce_ms": mx[2], "reduce": "hc_fb_reduce inside the frame: " + ("ncclReduce(sum) of the full-size buffers" if mode == 1 else "NCCL send / recv of the owned tiles only (1/G of the image per rank)"),
+                           "reduce_bytes_per_rank": (scn3.width*scn3.height*16 if mode == 1 else scn3.width*scn3.height*16//world) if world > 1 else 0,
+                           "mean_radiance": mean_img, "scaling": "strong (one frame split over the ranks, reduce included)"}
             if key == "c5":
                 extras[key]["spp_per_s"] = passes/mx[0]            # one pass of all ranks together = 1 sample per pixel of the 4K frame
                 extras[key]["partition"] = "Sobol sample index i = g (mod G); samples land on arbitrary pixels, so every rank keeps a full-size SUM buffer"
-            if key == "c1" and rank == 0 and world == 1 and not args.profile and not args.no_cpu_baseline:
-                # the reference's own CPU integrator (IntegratorStupidPT compiled in place, oracle/_ref) on the same scene, host cores
-                from tests import refapi
-                rf = refapi.Ref.try_load()
-                if rf is not None:
-                    rs = rf.scene(scn3)
-                    rs.render(0, 777, 1)
-                    t0 = time.perf_counter()
-                    _img, npass = rs.render(0, 777, 2)
-                    dtc = time.perf_counter() - t0
-                    rs.close()
-                    extras[key]["cpu_reference"] = {"paths_per_s": scn3.width*scn3.height*2/dtc, "cores": len(os.sched_getaffinity(0)), "kind": "reference",
-                                                    "sample": "2 passes of 512x512 by IntegratorStupidPT (oracle/_ref, OpenMP, BVH4InstTraverse instead of Embree)"}
+            if rank == 0 and world == 1 and not args.profile and not args.no_cpu_baseline:
+                # the reference's own CPU integrator (oracle/_ref: the reference sources compiled in place) on a pixel window of the same scene
+                names = {0: "IntegratorStupidPT", 2: "IntegratorMISPTLoop2", 3: "IntegratorMISPT_QMC"}
+                cb = cpu_baseline_pt(scn3, integ, names[integ], window)
+                if cb is not None:
+                    extras[key]["cpu_reference"] = cb
+                    extras[key]["vs_cpu_reference_paths"] = extras[key]["paths_per_s"]/cb["paths_per_s"]
             lay.close()
         lay = None
 
@@ -385,48 +474,50 @@ def run_ours(args):
         return 0
 
     # ---- roofline of the dominant kernel (K2 closest hit) + CPU baseline (N = 1 only)
-    peak, peak_src = _peaks()
+    peak_hbm, peak_src = _peaks()
     qlt_path = os.path.join(ROOT, "profiles", "c2_algorithmic_bytes.json")
     cpu = None
     if world == 1 and not args.no_cpu_baseline and not args.profile:
         cpu, qlt = cpu_baseline(scn)
-        try:
-            json.dump({"quads_per_ray": qlt[0], "leaves_per_ray": qlt[1], "tris_per_ray": qlt[2],
-                       "formula": "B_ray = 32 + 4 + 16 + 128*Q + 16*L + 48*T (SURVEY.md 8d)",
-                       "source": "oracle/hydra_oracle.cpp traversal counters on every 61st primary ray of the C2 frame (bench.py, N=1)"},
-                      open(qlt_path, "w"), indent=1)
-        except OSError:
-            pass
+        qlt_src = "oracle traversal counters on every 61st primary ray of the C2 frame, this run"
     else:
         d = json.load(open(qlt_path))
         qlt = [d["quads_per_ray"], d["leaves_per_ray"], d["tris_per_ray"]]
+        qlt_src = "profiles/c2_algorithmic_bytes.json (committed; the same counters from an N = 1 run)"
     bytes_per_ray = 52.0 + 128.0*qlt[0] + 16.0*qlt[1] + 48.0*qlt[2]
-    ms_closest = stats["msClosest"]/args.steps
-    achieved = bytes_per_ray*n/(ms_closest*1e-3)/1e9
-    traffic, ncu_extra = None, None
+    ms_closest = ms_closest_max/args.steps
+    rays_per_launch = n/world                    # this kernel's share of the frame on the slowest rank
+    achieved = bytes_per_ray*rays_per_launch/(ms_closest*1e-3)/1e9
+    ncu = None
     tp = os.path.join(ROOT, "profiles", "c2_ncu_traffic.json")
     if os.path.exists(tp):
-        tj = json.load(open(tp))
-        traffic = tj.get("k_trace_closest_dram_bytes_per_launch")
-        ncu_extra = {k: tj[k] for k in ("issue_active_pct", "lsu_wavefronts_pct_of_peak", "active_threads_per_warp_instruction", "l1_hit_pct", "l2_hit_pct",
-                                        "l2_to_l1_bytes_per_launch", "l1_load_bytes_per_launch", "source") if k in tj}
+        ncu = json.load(open(tp))
+    l2_peak = mem_peaks["l2_read_gbs"] if mem_peaks else None
+    traffic = ncu.get("k_trace_closest_dram_bytes_per_launch") if ncu else None
+    roofline = {
+        # the algorithmic bytes are BVH-node / triangle fetches that L1 and the 126 MB L2 serve; ncu shows the kernel bound by instruction issue and
+        # L1-hit latency, not by a memory ceiling.  frac is therefore taken against the measured L2 read bandwidth; HBM is reported beside it
+        "bound": "issue",
+        "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": (achieved/l2_peak) if l2_peak else None,
+        "peak_source": "L2 streaming-read bandwidth measured in this run (hc_measure_read_bandwidth); HBM peak beside it: " + peak_src,
+        "hbm_peak": peak_hbm, "frac_vs_hbm_peak": achieved/peak_hbm,
+        "traffic": traffic, "traffic_source": (ncu.get("source", "") + " - from profiles/, NOT measured in this run") if ncu else None,
+        "hbm_frac_of_dram_traffic": (traffic/(ms_closest*1e-3)/1e9/peak_hbm) if traffic else None,
+        "kernel": "k_trace<closest>", "bytes_per_ray": bytes_per_ray, "quads_leaves_tris_per_ray": qlt, "quads_leaves_tris_source": qlt_src,
+        "rays_per_launch": rays_per_launch, "ms_per_launch": ms_closest,
+        "ncu": {k: ncu[k] for k in ("issue_active_pct", "lsu_wavefronts_pct_of_peak", "active_threads_per_warp_instruction", "l1_hit_pct", "l2_hit_pct",
+                                    "l2_to_l1_bytes_per_launch", "l1_load_bytes_per_launch", "source") if ncu and k in ncu},
+        "measured_memory_peaks": mem_peaks}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "triangles": 1001112, "rays_per_step_per_gpu": rays_per_step,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "triangles": 1001112, "rays_per_step": rays_per_step,
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA events)",
-                       "parallelism": "replicated scene, one full frame per GPU, no collective" if world > 1 else "single GPU"},
-            "mrays_primary": n/(stats["msClosest"]/args.steps)/1e3, "mrays_shadow": n_hit/(stats["msShadow"]/args.steps)/1e3,
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(blob_np.nbytes), "d2h_bytes_per_step": int(n*16 + n),
-                    "ms_per_step": 1e3*te/args.steps},
-            "gpu_launches": int(stats["kernelLaunches"]),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": traffic,
-                         "kernel": "k_trace<closest>", "bytes_per_ray": bytes_per_ray, "quads_leaves_tris_per_ray": qlt,
-                         "ms_per_launch": ms_closest, "peak_source": peak_src,
-                         "note": "algorithmic bytes are BVH/triangle fetches that L1 (84 % hit) and the 126 MB L2 serve, so frac can exceed 1; "
-                                 "the kernel is bound by instruction issue and the L1/LSU wavefront rate (fields below, from the ncu capture in profiles/)",
-                         "measured_memory_peaks": mem_peaks, "ncu": ncu_extra,
-                         "frac_vs_measured_l2_read": (achieved/mem_peaks["l2_read_gbs"]) if mem_peaks else None}}
+                       "parallelism": ("one frame in interleaved %dx%d tiles over %d GPUs (replicated scene), hit / visibility records gathered on rank 0 by NCCL send / recv "
+                                       "inside the step" % (TILE, TILE, world)) if world > 1 else "single GPU"},
+            "mrays_primary": (n/world)/(ms_closest_max/args.steps)/1e3*world, "mrays_shadow": n_hit/(ms_shadow_max/args.steps)/1e3,
+            "mrays_incoherent": mrays_incoherent["value"] if mrays_incoherent else None, "incoherent": mrays_incoherent,
+            "gather_ms_per_step": (ms_other_max/args.steps) if world > 1 else 0.0,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     line.update(extras)
@@ -446,7 +537,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="profiling run (ncu): no clock pre-roll, no CPU baseline")
-    ap.add_argument("--no-c3", action="store_true", help="skip the C3 / C4 (MISPT path tracing) sections")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C1 / C3 / C4 / C5 (path tracing) sections")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

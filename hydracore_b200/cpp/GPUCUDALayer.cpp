@@ -160,7 +160,15 @@ void GPUCUDALayer::InitPathTracing(int seed, std::vector<int32_t>* pInstRemapTab
 void GPUCUDALayer::BeginTracingPass()
 {
   UploadGlobalsIfDirty();
-  if (!(m_vars.m_flags & HRT_UNIFIED_IMAGE_SAMPLING)) return;   // the OpenCL layer only draws debug normals without it (GPUOCLLayer.cpp:1455-1458)
+  if (!(m_vars.m_flags & HRT_UNIFIED_IMAGE_SAMPLING))
+  {
+    // Without unified image sampling the OpenCL layer casts the primary rays and draws debug normals (DrawNormals, GPUOCLLayer.cpp:1455-1458).
+    // Here the same branch is the ray-casting pass: primary rays + one shadow ray per hit towards the point set by
+    // CallNamedFunc("raycast_light"); hit records and visibility go to the host buffers registered by CallNamedFunc("raycast_results").
+    if (m_rcLightSet)
+      Check(hc_raycast_pass(m_ctx, m_rcLight, static_cast<hc_hit*>(m_rcHits), static_cast<uint8_t*>(m_rcVis), HC_HOST), "BeginTracingPass (ray casting)");
+    return;
+  }
   if (!m_ptInitialised) InitPathTracing(m_seed);
   Check(hc_pt_pass(m_ctx, IntegratorFromState(), 1), "BeginTracingPass");
 }
@@ -251,6 +259,18 @@ void GPUCUDALayer::CallNamedFunc(const char* a_name, const char* a_args)
     if (sscanf(args.c_str(), "%d %d %d", &tile, &rank, &world) != 3) Check(HC_E_ARG, "CallNamedFunc(tiles): expected \"<tileSize> <rank> <worldSize>\"");
     Check(hc_pt_set_tiles(m_ctx, tile, rank, world), "CallNamedFunc(tiles)");
     m_ptInitialised = false;
+  }
+  else if (name == "raycast_light")
+  {
+    if (sscanf(args.c_str(), "%f %f %f", &m_rcLight[0], &m_rcLight[1], &m_rcLight[2]) != 3) Check(HC_E_ARG, "CallNamedFunc(raycast_light): expected \"<x> <y> <z>\"");
+    m_rcLightSet = true;
+  }
+  else if (name == "raycast_results")
+  {
+    // "<hits> <visibility>": host addresses (decimal) of W*H hit records (16 B each, Lite_Hit) and W*H bytes; 0 = keep that result on the device
+    unsigned long long a = 0, b = 0;
+    if (sscanf(args.c_str(), "%llu %llu", &a, &b) != 2) Check(HC_E_ARG, "CallNamedFunc(raycast_results): expected \"<hitsAddress> <visibilityAddress>\"");
+    m_rcHits = reinterpret_cast<void*>(static_cast<uintptr_t>(a)); m_rcVis = reinterpret_cast<void*>(static_cast<uintptr_t>(b));
   }
   else if (name == "shadow_trees")
   {

@@ -55,6 +55,8 @@ public:
   // custom pipeline hooks of the interface, used for what the reference API has no slot for:
   //   CallNamedFunc("integrator", "pt" | "mispt" | "qmc")        which CPUExpLayer integrator to reproduce (default: by flags)
   //   CallNamedFunc("tiles", "<tileSize> <rank> <worldSize>")    interleaved tile ownership of this process (one process per GPU)
+  //   CallNamedFunc("raycast_light", "<x> <y> <z>")               ray-casting mode (passes without HRT_UNIFIED_IMAGE_SAMPLING): shadow rays go to this point
+  //   CallNamedFunc("raycast_results", "<hitsAddr> <visAddr>")    host buffers the ray-casting pass fills (W*H Lite_Hit records, W*H bytes)
   //   CallNamedFunc("shadow_trees", "0" | "1")                    shadow rays through the alpha-tested tree (1, default: as GPUOCLLayer) or not (0: as CPUExpLayer)
   //   CallNamedFunc("comm_id", "") -> CommIdHex()                 rank 0: create the NCCL unique id of a multi-process render
   //   CallNamedFunc("comm", "<rank> <nranks> <256 hex digits>")   join the communicator
@@ -86,6 +88,10 @@ protected:
   float   m_sppContributed;
   MRaysStat m_stat;
   std::string m_commIdHex;
+  float   m_rcLight[3] = { 0.0f, 0.0f, 0.0f };
+  bool    m_rcLightSet = false;
+  void*   m_rcHits = nullptr;
+  void*   m_rcVis = nullptr;
   mutable std::string m_deviceName;
   mutable std::vector<HRRenderDeviceInfoListElem> m_deviceList;
 };

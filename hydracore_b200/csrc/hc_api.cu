@@ -53,7 +53,7 @@ void hc_buf_free(HcDevBuf& b) { if (b.ptr) cudaFree(b.ptr); b.ptr = nullptr; b.b
 // RAYGEN (ray-casting pass only): 0 = rays come from memory; 1 = the primary eye ray of pixel idx is generated in the fetch (K1 fused into K2:
 // MakeRandEyeRay with zero offsets, the arithmetic of k_make_eye_rays); 2 = the shadow ray towards `light` is generated from the regenerated eye
 // ray and the hit record hitsIn[idx] (k_make_shadow_rays fused into K2s).  Saves two launches and 2 x 64 B per pixel of ray traffic.
-struct HcRayGen { HcCamera cam; int width, height; long long firstPixel; float3 light; const HcHit* hitsIn; };
+struct HcRayGen { HcCamera cam; int width, height; long long firstPixel; float3 light; const HcHit* hitsIn; const int* pixels = nullptr; };   // pixels: this rank's pixel list (tile partition), else pixel = index + firstPixel
 template<bool ANYHIT, int TREE1 = 0, int RAYGEN = 0>      // TREE1: 0 = first tree, 1 = second tree (hit carried), 2 = second tree with the alpha table
 __global__ void __launch_bounds__(HC_TRACE_BLOCK, HC_TRACE_MINB)
 k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long nArg,
@@ -98,7 +98,7 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
         if (RAYGEN == 0) { p = __ldg(rpos + size_t(idx)*stride); dd = __ldg(rdir + size_t(idx)*stride); }
         else
         {
-          const long long pix = (long long)idx + gen.firstPixel;                  // launches may cover a band of the image
+          const long long pix = gen.pixels ? (long long)gen.pixels[idx] : (long long)idx + gen.firstPixel;      // this rank's tiles, or a band of the image
           float3 eo, ed;
           MakeRandEyeRay(int(pix % gen.width), int(pix / gen.width), gen.width, gen.height, make_float4(0.0f, 0.0f, 0.0f, 0.0f), gen.cam, eo, ed);
           p = make_float4(eo.x, eo.y, eo.z, 0.0f); dd = make_float4(ed.x, ed.y, ed.z, HC_MAXFLOAT_RAY);
@@ -117,6 +117,7 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
             }
           }
         }
+        if (RAYGEN != 0 && gen.pixels) idx = (unsigned)gen.pixels[idx];             // results are stored per PIXEL (the gather to the destination rank packs them again)
         rayIdx = idx; idle = false;
         TravStart(r, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
         if (TREE1 != 0 && !ANYHIT)
@@ -784,6 +785,17 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
   const bool fused = !ctx->haveTree1 && ctx->bvhNodes.ptr && ctx->bvhTris.ptr && ctx->haveInst != 0 && getenv("HC_RAYCAST_UNFUSED") == nullptr;
   HcRayGen gen; gen.cam = cam; gen.width = ctx->width; gen.height = ctx->height; gen.firstPixel = 0;
   gen.light = make_float3(lightPos[0], lightPos[1], lightPos[2]); gen.hitsIn = hits;
+  // Multi-GPU: with a tile partition (hc_pt_set_tiles, world size > 1) this rank casts the rays of ITS pixels only; with a communicator
+  // (hc_comm_init) the hit records and visibility bytes of all ranks are then gathered on rank 0 - one frame, split over the GPUs.
+  const bool split = ctx->worldSize > 1;
+  long long nMine = n;
+  if (split)
+  {
+    HC_REQUIRE(fused, HC_E_STATE, "hc_raycast_pass: the tile-partitioned pass needs the fused ray generation (one BVH tree)");
+    const int* px = nullptr; int cnt = 0;
+    if ((rc = hc_path_owned_pixels(ctx, &px, &cnt))) return rc;
+    gen.pixels = px; nMine = cnt;
+  }
   HC_CUDA(cudaEventRecord(ctx->evStage[0], ctx->stream));
   if (!fused)
   {
@@ -792,21 +804,21 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
     ctx->stats.kernelLaunches++;
   }
   HC_CUDA(cudaEventRecord(ctx->evStage[1], ctx->stream));
-  const int tileW = (ctx->width % 8 == 0 && ctx->height % 4 == 0) ? ctx->width : 0;                 // rays fetched in 8 x 4 pixel blocks per warp
+  const int tileW = (!split && ctx->width % 8 == 0 && ctx->height % 4 == 0) ? ctx->width : 0;       // rays fetched in 8 x 4 pixel blocks per warp (the owned-pixel list is in that order already)
   // With HOST outputs the closest-hit pass runs in two horizontal bands, so that the read-back of the first band's hit records (16 B per ray,
   // copy stream) overlaps the traversal of the second and the read-back of the second overlaps the shadow pass.  Bands are whole groups of
   // 4 rows, which keeps the 8 x 4 block fetch order valid.
   const int rowGroups = (ctx->height + 3)/4;
-  const int bands = (space == HC_HOST && hitsOutOrNull && tileW > 0 && rowGroups >= 16) ? 2 : 1;     // measured on B200 at 1080p: 1 / 2 / 3 / 4 bands -> 1.39 / 1.18 / 1.21 / 1.30 ms
+  const int bands = (!split && space == HC_HOST && hitsOutOrNull && tileW > 0 && rowGroups >= 16) ? 2 : 1;     // measured on B200 at 1080p: 1 / 2 / 3 / 4 bands -> 1.39 / 1.18 / 1.21 / 1.30 ms
   const cudaMemcpyKind kind = (space == HC_HOST) ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   for (int b = 0; b < bands; b++)
   {
     const long long r0 = (long long)(rowGroups*b/bands)*4, r1 = std::min<long long>((long long)(rowGroups*(b + 1)/bands)*4, ctx->height);
-    const long long i0 = r0*ctx->width, nb = (r1 - r0)*ctx->width;
+    const long long i0 = split ? 0 : r0*ctx->width, nb = split ? nMine : (r1 - r0)*ctx->width;
     gen.firstPixel = i0;
-    if (fused) { if ((rc = LaunchTraceGen(ctx, false, nb, hits + i0, nullptr, tileW, gen))) return rc; }
+    if (fused) { if ((rc = LaunchTraceGen(ctx, false, nb, split ? hits : hits + i0, nullptr, tileW, gen))) return rc; }
     else if ((rc = LaunchTrace(ctx, false, rays + 2*i0, rays + 2*i0 + 1, 2, nb, nullptr, hits + i0, nullptr, tileW))) return rc;
-    if (hitsOutOrNull)
+    if (hitsOutOrNull && !split)
     {
       HC_CUDA(cudaEventRecord(ctx->evCopy, ctx->stream));
       HC_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evCopy, 0));
@@ -822,17 +834,26 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
   }
   HC_CUDA(cudaEventRecord(ctx->evStage[3], ctx->stream));
   gen.firstPixel = 0;
-  if (fused) { if ((rc = LaunchTraceGen(ctx, true, n, nullptr, vis, tileW, gen))) return rc; }
+  if (fused) { if ((rc = LaunchTraceGen(ctx, true, nMine, nullptr, vis, tileW, gen))) return rc; }
   else if ((rc = LaunchTrace(ctx, true, srays, srays + 1, 2, n, nullptr, nullptr, vis, tileW))) return rc;
-  if (visibleOutOrNull) HC_CUDA(cudaMemcpyAsync(visibleOutOrNull, vis, uint64_t(n), kind, ctx->stream));      // 1 byte per ray: not worth a band
   HC_CUDA(cudaEventRecord(ctx->evStage[4], ctx->stream));
-  ctx->stats.paths += (uint64_t)n;
+  if (split)
+  {
+    // one frame over all GPUs: the records of every rank's pixels travel to rank 0 (NCCL send / recv of the packed owned pixels)
+    if ((rc = hc_comm_gather_raycast(ctx, hits, vis, 0))) return rc;
+    if (ctx->rank == 0 && hitsOutOrNull) HC_CUDA(cudaMemcpyAsync(hitsOutOrNull, hits, uint64_t(n)*16, kind, ctx->stream));
+    if (ctx->rank == 0 && visibleOutOrNull) HC_CUDA(cudaMemcpyAsync(visibleOutOrNull, vis, uint64_t(n), kind, ctx->stream));
+  }
+  else if (visibleOutOrNull) HC_CUDA(cudaMemcpyAsync(visibleOutOrNull, vis, uint64_t(n), kind, ctx->stream));      // 1 byte per ray: not worth a band
+  HC_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->stats.paths += (uint64_t)nMine;
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (hitsOutOrNull) HC_CUDA(cudaStreamSynchronize(ctx->copyStream));
-  float ms[4];
+  if (hitsOutOrNull && !split) HC_CUDA(cudaStreamSynchronize(ctx->copyStream));
+  float ms[5];
   for (int i = 0; i < 4; i++) HC_CUDA(cudaEventElapsedTime(&ms[i], ctx->evStage[i], ctx->evStage[i + 1]));
-  ctx->stats.msOther += ms[0] + ms[2]; ctx->stats.msClosest += ms[1]; ctx->stats.msShadow += ms[3];
-  ctx->lastTraceMs = ms[0] + ms[1] + ms[2] + ms[3];
+  HC_CUDA(cudaEventElapsedTime(&ms[4], ctx->evStage[4], ctx->ev1));
+  ctx->stats.msOther += ms[0] + ms[2] + (split ? ms[4] : 0.0f); ctx->stats.msClosest += ms[1]; ctx->stats.msShadow += ms[3];
+  ctx->lastTraceMs = ms[0] + ms[1] + ms[2] + ms[3] + (split ? ms[4] : 0.0f);      // a split frame is not complete before the gather
   return HC_OK;
 }
 

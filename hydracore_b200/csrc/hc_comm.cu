@@ -16,6 +16,8 @@
 #include <cstring>
 #include <algorithm>
 
+void hc_owned_pixels_of(int W, int H, int T, int rank, int world, std::vector<int>& owned);      // hc_path.cu
+
 namespace
 {
 typedef struct ncclComm* ncclComm_t;
@@ -63,26 +65,100 @@ int NcclFail(int e, const char* what)
 }
 #define HC_NCCL(call, what) do { const int e_ = (call); if (e_ != ncclSuccess) return NcclFail(e_, what); } while (0)
 
-// dense <-> framebuffer by a pixel list (the owned pixels of one rank, in the order BuildOwnedPixels / OwnedPixelsOf produce)
-__global__ void k_fb_pack(const float4* __restrict__ fb, const int* __restrict__ pixels, const int n, float4* __restrict__ out)
+// dense <-> per-pixel buffer by a pixel list (the owned pixels of one rank, in the order hc_owned_pixels_of produces); T = float4 for the
+// framebuffer and the hit records, unsigned char for the visibility bytes
+template<class T> __global__ void k_px_pack(const T* __restrict__ buf, const int* __restrict__ pixels, const int n, T* __restrict__ out)
 {
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
-  if (i < n) out[i] = fb[pixels[i]];
+  if (i < n) out[i] = buf[pixels[i]];
 }
-__global__ void k_fb_unpack(float4* __restrict__ fb, const int* __restrict__ pixels, const int n, const float4* __restrict__ in)
+template<class T> __global__ void k_px_unpack(T* __restrict__ buf, const int* __restrict__ pixels, const int n, const T* __restrict__ in)
 {
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
-  if (i < n) fb[pixels[i]] = in[i];
+  if (i < n) buf[pixels[i]] = in[i];
+}
+
+// pixel lists of the exchange: mine on a source rank, every source rank's (back to back) on the destination
+int EnsurePixelLists(hc_ctx* ctx, int dstRank)
+{
+  const int W = ctx->width, H = ctx->height, T = std::max(1, ctx->tileSize), G = ctx->commSize;
+  const long long key = (((long long)W*65536 + H)*1024 + T)*64 + G + 1000000000000000ll*(dstRank + 1);
+  if (ctx->commPixelsKey == key) return HC_OK;
+  std::vector<int> all;
+  if (ctx->commRank != dstRank) { hc_owned_pixels_of(W, H, T, ctx->commRank, G, all); ctx->commCount.assign(1, (int)all.size()); }
+  else
+  {
+    ctx->commCount.assign(G, 0);
+    for (int g = 0; g < G; g++)
+    {
+      std::vector<int> px; if (g != dstRank) hc_owned_pixels_of(W, H, T, g, G, px);
+      ctx->commCount[g] = (int)px.size();
+      all.insert(all.end(), px.begin(), px.end());
+    }
+  }
+  int rc = hc_buf_reserve(ctx, ctx->commPixels, std::max<size_t>(all.size(), 1)*4); if (rc) return rc;
+  if (!all.empty()) HC_CUDA(cudaMemcpyAsync(ctx->commPixels.ptr, all.data(), all.size()*4, cudaMemcpyHostToDevice, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->commPixelsKey = key;
+  return HC_OK;
+}
+
+// gather the owned pixels of every rank's per-pixel buffer `buf` (elemBytes 16 or 1) into the destination rank's buffer; enqueued on the context's stream
+template<class T> int GatherOwned(hc_ctx* ctx, T* buf, int dstRank, HcDevBuf& stage)
+{
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  cudaStream_t s = ctx->stream;
+  const int G = ctx->commSize;
+  int rc = EnsurePixelLists(ctx, dstRank); if (rc) return rc;
+  if (ctx->commRank != dstRank)
+  {
+    const int n = ctx->commCount[0];
+    rc = hc_buf_reserve(ctx, stage, std::max<size_t>(n, 1)*sizeof(T)); if (rc) return rc;
+    if (n > 0)
+    {
+      k_px_pack<T><<<(n + 255)/256, 256, 0, s>>>(buf, (const int*)ctx->commPixels.ptr, n, (T*)stage.ptr);
+      HC_CUDA(cudaGetLastError());
+      ctx->stats.kernelLaunches++;
+      HC_NCCL(g_nccl.Send(stage.ptr, size_t(n)*sizeof(T), 1 /* ncclUint8 */, dstRank, comm, s), "ncclSend");
+    }
+    return HC_OK;
+  }
+  size_t total = 0; for (int g = 0; g < G; g++) total += size_t(ctx->commCount[g]);
+  rc = hc_buf_reserve(ctx, stage, std::max<size_t>(total, 1)*sizeof(T)); if (rc) return rc;
+  HC_NCCL(g_nccl.GroupStart(), "ncclGroupStart");
+  size_t off = 0;
+  for (int g = 0; g < G; g++)
+  {
+    const int n = ctx->commCount[g];
+    if (g == dstRank || n == 0) continue;
+    const int e = g_nccl.Recv((T*)stage.ptr + off, size_t(n)*sizeof(T), 1 /* ncclUint8 */, g, comm, s);
+    if (e != ncclSuccess) { g_nccl.GroupEnd(); return NcclFail(e, "ncclRecv"); }
+    off += size_t(n);
+  }
+  HC_NCCL(g_nccl.GroupEnd(), "ncclGroupEnd");
+  if (total > 0)
+  {
+    k_px_unpack<T><<<(int)((total + 255)/256), 256, 0, s>>>(buf, (const int*)ctx->commPixels.ptr, (int)total, (const T*)stage.ptr);
+    HC_CUDA(cudaGetLastError());
+    ctx->stats.kernelLaunches++;
+  }
+  return HC_OK;
 }
 }
 
-void hc_owned_pixels_of(int W, int H, int T, int rank, int world, std::vector<int>& owned);      // hc_path.cu
+// ray-casting results of a tile-partitioned pass (hc_raycast_pass): hit records and visibility bytes of the owned pixels -> destination rank
+int hc_comm_gather_raycast(hc_ctx* ctx, void* hits16, unsigned char* vis, int dstRank)
+{
+  if (!ctx->comm || ctx->commSize == 1) return HC_OK;
+  int rc = GatherOwned<float4>(ctx, (float4*)hits16, dstRank, ctx->commStage); if (rc) return rc;
+  return GatherOwned<unsigned char>(ctx, vis, dstRank, ctx->commStage2);
+}
 
 void hc_comm_free(hc_ctx* ctx)
 {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
   ctx->comm = nullptr;
-  hc_buf_free(ctx->commStage); hc_buf_free(ctx->commPixels); hc_buf_free(ctx->fbCombined);
+  hc_buf_free(ctx->commStage); hc_buf_free(ctx->commStage2); hc_buf_free(ctx->commPixels); hc_buf_free(ctx->fbCombined);
   ctx->combinedValid = false;
 }
 
@@ -145,66 +221,7 @@ int hc_fb_reduce(hc_ctx* ctx, int dstRank, int mode, float* outMs)
   }
   else
   {
-    const int T = std::max(1, ctx->tileSize);
-    if (ctx->commRank != dstRank)
-    {
-      // pack my pixels densely and send them
-      if (ctx->commPixelsKey != (long long)W*100000000ll + (long long)H*10000ll + T*100 + G)
-      {
-        std::vector<int> mine; hc_owned_pixels_of(W, H, T, ctx->commRank, G, mine);
-        int rc = hc_buf_reserve(ctx, ctx->commPixels, std::max<size_t>(mine.size(), 1)*4); if (rc) return rc;
-        HC_CUDA(cudaMemcpyAsync(ctx->commPixels.ptr, mine.data(), mine.size()*4, cudaMemcpyHostToDevice, s));
-        HC_CUDA(cudaStreamSynchronize(s));
-        ctx->commCount.assign(1, (int)mine.size());
-        ctx->commPixelsKey = (long long)W*100000000ll + (long long)H*10000ll + T*100 + G;
-      }
-      const int n = ctx->commCount[0];
-      int rc = hc_buf_reserve(ctx, ctx->commStage, std::max<size_t>(n, 1)*16); if (rc) return rc;
-      if (n > 0)
-      {
-        k_fb_pack<<<(n + 255)/256, 256, 0, s>>>((const float4*)ctx->fbSum.ptr, (const int*)ctx->commPixels.ptr, n, (float4*)ctx->commStage.ptr);
-        HC_CUDA(cudaGetLastError());
-        ctx->stats.kernelLaunches++;
-        HC_NCCL(g_nccl.Send(ctx->commStage.ptr, size_t(n)*4, ncclFloat32, dstRank, comm, s), "ncclSend");
-      }
-    }
-    else
-    {
-      // destination: one dense segment per source rank, received in one group, scattered into the SUM buffer
-      if (ctx->commPixelsKey != (long long)W*100000000ll + (long long)H*10000ll + T*100 + G)
-      {
-        std::vector<int> all; ctx->commCount.assign(G, 0);
-        for (int g = 0; g < G; g++)
-        {
-          std::vector<int> px; if (g != dstRank) hc_owned_pixels_of(W, H, T, g, G, px);
-          ctx->commCount[g] = (int)px.size();
-          all.insert(all.end(), px.begin(), px.end());
-        }
-        int rc = hc_buf_reserve(ctx, ctx->commPixels, std::max<size_t>(all.size(), 1)*4); if (rc) return rc;
-        HC_CUDA(cudaMemcpyAsync(ctx->commPixels.ptr, all.data(), all.size()*4, cudaMemcpyHostToDevice, s));
-        HC_CUDA(cudaStreamSynchronize(s));
-        ctx->commPixelsKey = (long long)W*100000000ll + (long long)H*10000ll + T*100 + G;
-      }
-      size_t total = 0; for (int g = 0; g < G; g++) total += size_t(ctx->commCount[g]);
-      int rc = hc_buf_reserve(ctx, ctx->commStage, std::max<size_t>(total, 1)*16); if (rc) return rc;
-      HC_NCCL(g_nccl.GroupStart(), "ncclGroupStart");
-      size_t off = 0;
-      for (int g = 0; g < G; g++)
-      {
-        const int n = ctx->commCount[g];
-        if (g == dstRank || n == 0) continue;
-        const int e = g_nccl.Recv((float4*)ctx->commStage.ptr + off, size_t(n)*4, ncclFloat32, g, comm, s);
-        if (e != ncclSuccess) { g_nccl.GroupEnd(); return NcclFail(e, "ncclRecv"); }
-        off += size_t(n);
-      }
-      HC_NCCL(g_nccl.GroupEnd(), "ncclGroupEnd");
-      if (total > 0)
-      {
-        k_fb_unpack<<<(int)((total + 255)/256), 256, 0, s>>>((float4*)ctx->fbSum.ptr, (const int*)ctx->commPixels.ptr, (int)total, (const float4*)ctx->commStage.ptr);
-        HC_CUDA(cudaGetLastError());
-        ctx->stats.kernelLaunches++;
-      }
-    }
+    int rc = GatherOwned<float4>(ctx, (float4*)ctx->fbSum.ptr, dstRank, ctx->commStage); if (rc) return rc;
   }
   HC_CUDA(cudaEventRecord(ctx->ev1, s));
   HC_CUDA(cudaStreamSynchronize(s));

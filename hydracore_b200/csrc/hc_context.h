@@ -76,7 +76,7 @@ struct hc_ctx
   // multi-GPU exchange (hc_comm.cu)
   void*    comm = nullptr;                 // ncclComm_t
   int      commRank = 0, commSize = 1;
-  HcDevBuf commStage, commPixels;          // dense staging of owned pixels; pixel lists (mine, or every source rank's on the destination)
+  HcDevBuf commStage, commStage2, commPixels;          // dense staging of owned pixels; pixel lists (mine, or every source rank's on the destination)
   std::vector<int> commCount;              // pixels per source rank
   long long commPixelsKey = -1;            // (W, H, tile, G) the lists were built for
   HcDevBuf fbCombined;                     // destination rank, full-size sums (sample partition): sum over ranks, separate from fbSum
@@ -94,5 +94,7 @@ void hc_buf_free(HcDevBuf& b);
 
 void hc_path_free(hc_ctx* ctx);   // hc_path.cu
 void hc_comm_free(hc_ctx* ctx);   // hc_comm.cu
+int  hc_comm_gather_raycast(hc_ctx* ctx, void* hits16, unsigned char* vis, int dstRank);
+int  hc_path_owned_pixels(hc_ctx* ctx, const int** outDevicePixels, int* outCount);   // hc_path.cu: device list of this rank's pixels (hc_pt_set_tiles)
 int  hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis, cudaStream_t stream = nullptr);
 int  hc_launch_trace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, HcHit* hits, unsigned char* vis);   // hc_api.cu

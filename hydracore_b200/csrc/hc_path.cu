@@ -382,6 +382,7 @@ struct HcPathHost
   std::vector<unsigned char> materialsHost, globalsHost;
   int64_t capacity = 0;
   int nOwned = 0;
+  long long ownedKey = -1;                    // (W, H, tile, rank, world) the owned-pixel list was built for
   bool haveNormalMaps = false;                // set by ValidateScene: selects the k_pt_shade instantiation
   std::vector<cudaEvent_t> evPool;            // per-launch stage timing of the LAST pass of a hc_pt_pass call: {start, stop} pairs
   std::vector<int> evClass;                    // 0 closest, 1 shadow, 2 shade, 3 other
@@ -469,6 +470,16 @@ static int BuildOwnedPixels(hc_ctx* ctx)
   int rc = hc_buf_reserve(ctx, p->owned, std::max<size_t>(owned.size(), 1)*sizeof(int)); if (rc) return rc;
   if (!owned.empty()) HC_CUDA(cudaMemcpyAsync(p->owned.ptr, owned.data(), owned.size()*sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HC_OK;
+}
+
+// device list of this rank's pixels for callers outside the path tracer (hc_raycast_pass): rebuilt when the screen or the partition changed
+int hc_path_owned_pixels(hc_ctx* ctx, const int** outDevicePixels, int* outCount)
+{
+  HcPathHost* p = EnsureHost(ctx);
+  const long long key = (((long long)ctx->width*65536 + ctx->height)*1024 + ctx->tileSize)*4096 + (long long)ctx->rank*64 + ctx->worldSize;
+  if (p->ownedKey != key || !p->owned.ptr) { int rc = BuildOwnedPixels(ctx); if (rc) return rc; p->ownedKey = key; }
+  *outDevicePixels = (const int*)p->owned.ptr; *outCount = p->nOwned;
   return HC_OK;
 }
 
@@ -746,7 +757,7 @@ int hc_pt_init(hc_ctx* ctx, int seed)
   BuildQmcTable(table);
   if ((rc = hc_buf_reserve(ctx, ctx->qmcTable, sizeof(table)))) return rc;
   HC_CUDA(cudaMemcpyAsync(ctx->qmcTable.ptr, table, sizeof(table), cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = BuildOwnedPixels(ctx))) return rc;
+  { const int* px; int cnt; if ((rc = hc_path_owned_pixels(ctx, &px, &cnt))) return rc; }
   HC_CUDA(cudaMemsetAsync(ctx->fbSum.ptr, 0, uint64_t(n)*16, ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->seed = seed; ctx->spp = 0.0; ctx->passCounter = 0; ctx->ptReady = true; ctx->combinedValid = false;

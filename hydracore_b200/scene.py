@@ -799,14 +799,20 @@ def scene_c3(width=1920, height=1080, trace_depth=8):
 
 def scene_c4(width=1920, height=1080, instances=200, grid=(224, 224), seed=99):
     """BASELINE config C4: 20 M instanced triangles = `instances` rigid copies (random rotation about Y + translation, seed 99) of one
-    ~100k-triangle displaced patch (224 x 224 quads = 100,352 triangles), Lambert, one large area light."""
+    ~100k-triangle displaced patch (224 x 224 quads = 100,352 triangles), five diffuse materials by triangle block (Lambert in four colours,
+    Oren-Nayar) so that the material sort of the live-path queue has something to sort, one large area light."""
     from . import materials as M
     rng = np.random.RandomState(seed)
     scn = Scene(width, height, Camera(pos=(0.0, 55.0, 95.0), look_at=(0.0, 0.0, 5.0), fov=45.0))
     scn.set_trace_depth(5, 3)
     lam = scn.add_material(M.lambert((0.7, 0.7, 0.7)))
     emi = scn.add_material(M.emissive((40.0, 40.0, 40.0), 0))
-    patch = scn.add_mesh(grid_mesh(grid[0], grid[1], size=12.0, amplitude=0.9, seed=4321, mat_blocks=[(1.0, lam)]))
+    lam2 = scn.add_material(M.lambert((0.75, 0.45, 0.35)))
+    oren = scn.add_material(M.orennayar((0.55, 0.65, 0.45), 0.6))
+    lam3 = scn.add_material(M.lambert((0.40, 0.50, 0.75)))
+    lam4 = scn.add_material(M.lambert((0.80, 0.78, 0.55)))
+    patch = scn.add_mesh(grid_mesh(grid[0], grid[1], size=12.0, amplitude=0.9, seed=4321,
+                                   mat_blocks=[(0.30, lam), (0.25, lam2), (0.20, oren), (0.15, lam3), (0.10, lam4)]))
     side = int(math.ceil(math.sqrt(instances)))
     for k in range(instances):
         gx, gz = k % side, k//side

@@ -13,6 +13,7 @@
 // available (pExternalImpl == nullptr branch of IntegratorCommon::rayTrace, CPUExp_Integrators_Common.cpp:128-151).
 #include "CPUExp_Integrators.h"
 
+#include <omp.h>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -295,6 +296,43 @@ void ref_trace_shadow_anyhit(const void* nodes, const void* tris, const float* r
     const float3 sh = BVH4InstTraverseShadow(float3(r[0], r[1], r[2]), float3(r[4], r[5], r[6]), 0.0f, h, (const float4*)nodes, (const float4*)tris, -1);
     visibleOut[i] = (sh.x > 0.5f) ? 1 : 0;
   }
+}
+
+// OpenMP control for the timed baselines: a launcher (torchrun) exports OMP_NUM_THREADS=1, which libgomp reads when it is loaded
+int ref_omp_max_threads() { return omp_get_max_threads(); }
+void ref_omp_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
+// One ray-casting step of the C2 workload entirely inside the reference code: closest hit of every ray (BVH4InstTraverse), then one shadow
+// ray per hit towards `light` (t_far = 0.995 x distance, CPUExp_Integrators_PT_Loop.cpp:176; origin pushed off the surface by 1e-4 x the
+// largest coordinate, as hc_make_shadow_rays does), answered by closest-hit-then-compare (IntegratorCommon::shadowTrace).  Returns the
+// number of rays traced (primary + shadow).
+long long ref_raycast_step(const void* nodes, const void* tris, const float* rays8, long long n, const float* light3, void* hitsOut, unsigned char* visibleOut)
+{
+  Lite_Hit* out = (Lite_Hit*)hitsOut;
+  long long traced = 0;
+  #pragma omp parallel for schedule(dynamic, 256) reduction(+:traced)
+  for (long long i = 0; i < n; i++)
+  {
+    const float* r = rays8 + 8*i;
+    const float3 ro(r[0], r[1], r[2]), rd(r[4], r[5], r[6]);
+    Lite_Hit h = BVH4InstTraverse(ro, rd, 0.0f, Make_Lite_Hit(MAXFLOAT, -1), (const float4*)nodes, (const float4*)tris);
+    out[i] = h; traced++;
+    unsigned char vis = 1;
+    if (HitSome(h))
+    {
+      const float3 pos = ro + rd*h.t;
+      const float3 L(light3[0], light3[1], light3[2]);
+      const float3 sdir = normalize(L - pos);
+      const float eps = fmaxf(fmaxf(fabsf(pos.x), fmaxf(fabsf(pos.y), fabsf(pos.z))), 1.0f)*1e-4f;
+      const float3 spos = pos + sdir*eps;
+      const float tFar = length(spos - L)*0.995f;
+      const Lite_Hit sh = BVH4InstTraverse(spos, sdir, 0.0f, Make_Lite_Hit(MAXFLOAT, -1), (const float4*)nodes, (const float4*)tris);
+      vis = (HitSome(sh) && sh.t > 0.0f && sh.t < tFar) ? 0 : 1;
+      traced++;
+    }
+    visibleOut[i] = vis;
+  }
+  return traced;
 }
 
 // ---------------------------------------------------------------------------------------------- scene + integrators

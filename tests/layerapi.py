@@ -139,6 +139,13 @@ class CppLayer:
     def CallNamedFunc(self, name, args):
         self._ck(self._L.hl_call(self._s, name.encode(), args.encode()), "CallNamedFunc")
 
+    def CommIdHex(self):
+        """rank 0 of a multi-process render: the NCCL unique id as 256 hex digits (CallNamedFunc("comm_id"))."""
+        buf = ct.create_string_buffer(257)
+        self._L.hl_comm_id_hex.restype = ct.c_int
+        self._ck(self._L.hl_comm_id_hex(self._s, buf), "CallNamedFunc(comm_id)")
+        return buf.value.decode()
+
     def InitPathTracing(self, seed):
         self._ck(self._L.hl_init_path_tracing(self._s, int(seed)), "InitPathTracing")
 

@@ -163,6 +163,21 @@ class Ref:
         self.L.ref_trace_shadow(P(nodes), P(tris), 1, P(rays8), ct.c_longlong(n), P(vis))
         return vis
 
+    def omp_threads(self, n=None):
+        """Set (n > 0) and return the number of OpenMP threads the reference code runs on."""
+        if n:
+            self.L.ref_omp_set_threads(int(n))
+        return int(self.L.ref_omp_max_threads())
+
+    def raycast_step(self, nodes, tris, rays8, light):
+        """closest hit + one shadow ray per hit towards `light`, all inside the reference library; returns (hits, visible, rays traced)."""
+        n = rays8.shape[0]
+        hits, vis = np.zeros(n, HIT_DTYPE), np.zeros(n, np.uint8)
+        self.L.ref_raycast_step.restype = ct.c_longlong
+        lt = np.asarray(light, np.float32)
+        traced = self.L.ref_raycast_step(P(nodes), P(tris), P(rays8), ct.c_longlong(n), P(lt), P(hits), P(vis))
+        return hits, vis, int(traced)
+
     def trace_shadow_anyhit(self, nodes, tris, rays8):
         n = rays8.shape[0]
         vis = np.zeros(n, np.uint8)
@@ -204,13 +219,15 @@ class RefScene:
             self.ref.L.ref_scene_destroy(self.h)
             self.h = None
 
-    def render(self, kind, seed, passes):
-        """kind: 0 PT (IntegratorStupidPT), 1 MISPT recursive, 2 MISPTLoop2, 3 MISPT+QMC.  Returns per-pixel SUM image and pass count."""
+    def render(self, kind, seed, passes, window=None):
+        """kind: 0 PT (IntegratorStupidPT), 1 MISPT recursive, 2 MISPTLoop2, 3 MISPT+QMC.  Returns per-pixel SUM image and pass count.
+        window = (x0, y0, x1, y1): only these pixels are rendered (per-pixel generators make them equal to the same pixels of a full frame)."""
         r = self.ref.L.ref_render_create(self.h, kind, seed)
         self._renders.append(r)
         W, H = self.scn.width, self.scn.height
+        x0, y0, x1, y1 = window if window is not None else (0, 0, W, H)
         for _ in range(passes):
-            self.ref.L.ref_render_pass(r, 0, 0, W, H)
+            self.ref.L.ref_render_pass(r, int(x0), int(y0), int(x1), int(y1))
         out = np.zeros((H, W, 4), np.float32)
         n = self.ref.L.ref_render_get_sum(r, P(out))
         return out, n
