@@ -196,7 +196,7 @@ def run_reference(args):
     from tests import refapi
     ref = refapi.Ref.try_load()
     if ref is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhydra_ref.so missing"}))
+        _emit({"impl": "reference", "unavailable": "oracle/_ref/libhydra_ref.so missing"})
         return 0
     threads = _ref_threads(ref)
     scn = S.scene_c2(WIDTH, HEIGHT)
@@ -224,7 +224,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
                              "sample": "every %d-th pixel of the frame per step, %d rays per step, OpenMP on %d threads" % (stride, traced//max(1, args.steps), threads)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -442,11 +442,12 @@ def run_ours(args):
             ev_ms = st3["msClosest"] + st3["msShadow"] + st3["msShade"] + st3["msOther"]
             vals = torch.tensor([t_frame, ev_ms, red_ms, float(st3["paths"]), float(st3["raysClosest"]), float(st3["raysShadow"]),
                                  st3["msClosest"], st3["msShadow"], st3["msShade"], st3["msOther"], t_pass], device=dev, dtype=torch.float64)
-            mx, sm = vals.clone(), vals.clone()
+            mx, sm, mn = vals.clone(), vals.clone(), vals.clone()
             if dist is not None:
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX)
                 dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-            mx, sm = mx.tolist(), sm.tolist()
+                dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            mx, sm, mn = mx.tolist(), sm.tolist(), mn.tolist()
             mean_img = float(lay.GetSumImage()[..., :3].sum()/(scn3.width*scn3.height*3*(passes + 2))) if rank == 0 else 0.0
             extras[key] = {"workload": label, "passes": passes, "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": (mx[1] + mx[2])/passes,
                            "ms_per_pass_without_reduce_wall_max": 1e3*mx[10]/passes,
@@ -454,7 +455,9 @@ def run_ours(args):
                            "rays_closest_per_pass": sm[4]/passes, "rays_shadow_per_pass": sm[5]/passes,
                            "stage_ms_per_pass_max": {"closest": mx[6]/passes, "shadow_added": mx[7]/passes, "shade": mx[8]/passes, "raygen_sort": mx[9]/passes},
                            "stage_note": "closest-hit and any-hit launches of a bounce overlap on two streams: shadow_added = time from the end of the closest-hit launch to the join",
-                           "reduce_ms": mx[2], "reduce": "hc_fb_reduce inside the frame: " + ("ncclReduce(sum) of the full-size buffers" if mode == 1 else "NCCL send / recv of the owned tiles only (1/G of the image per rank)"),
+                           "reduce_ms": mn[2], "reduce_ms_incl_wait_for_slowest_rank": mx[2],
+                           "reduce_note": "device time of hc_fb_reduce per rank: the minimum over ranks is the exchange itself (the last rank to arrive does not wait), the maximum includes the load imbalance of the frame",
+                           "reduce": "hc_fb_reduce inside the frame: " + ("ncclReduce(sum) of the full-size buffers" if mode == 1 else "NCCL send / recv of the owned tiles only (1/G of the image per rank)"),
                            "reduce_bytes_per_rank": (scn3.width*scn3.height*16 if mode == 1 else scn3.width*scn3.height*16//world) if world > 1 else 0,
                            "mean_radiance": mean_img, "scaling": "strong (one frame split over the ranks, reduce included)"}
             if key == "c5":
@@ -525,7 +528,7 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     line.update(extras)
-    print(json.dumps(line))
+    _emit(line)
     if lay is not None:
         lay.close()
     if dist is not None:
@@ -533,7 +536,25 @@ def run_ours(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else written to fd 1 meanwhile (NCCL prints its version line there from C)
+    was redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

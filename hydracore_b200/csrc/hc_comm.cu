@@ -215,6 +215,8 @@ int hc_fb_reduce(hc_ctx* ctx, int dstRank, int mode, float* outMs)
   HC_CUDA(cudaEventRecord(ctx->ev0, s));
   if (mode == 1)
   {
+    // out of place on the destination: the local sums stay untouched, so the call can be repeated during progressive rendering
+    // (4K, 133 MB, two B200s: 0.26 ms, the same as torch.distributed.reduce in place - scripts/gpu_reduce_probe.py)
     if (ctx->commRank == dstRank) { int rc = hc_buf_reserve(ctx, ctx->fbCombined, nPix*16); if (rc) return rc; }
     HC_NCCL(g_nccl.Reduce(ctx->fbSum.ptr, ctx->commRank == dstRank ? ctx->fbCombined.ptr : nullptr, nPix*4, ncclFloat32, ncclSum, dstRank, comm, s), "ncclReduce");
     if (ctx->commRank == dstRank) ctx->combinedValid = true;
