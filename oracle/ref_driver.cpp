@@ -5,7 +5,7 @@
 //   hydra_drv/CPUExp_Integrators_{Common,PT,PT_Loop,PT_QMC}.cpp, qmc_sobol_niederreiter.cpp
 //   bakeBrdfEnergy/MSTables{GGX2017,Transp}.cpp
 // compiled IN PLACE from /root/reference (see oracle/Makefile) against the small LiteMath stand-in
-// under oracle/ref_shim/, plus this driver which only (a) feeds them scene blobs through a C ABI and
+// under hydracore_b200/cpp/compat/ref_shim/, plus this driver which only (a) feeds them scene blobs through a C ABI and
 // (b) replaces the non-deterministic GetTickCount() seeding by the per-pixel rule of SURVEY.md 8c:
 //      gen[p] = RandomGenInit(seed + p), state carried across passes      (cf. reference shaders/trace.cl:6-13)
 // and drops the debug red pixel of reference CPUExp_Integrators_Common.cpp:295-301.
