@@ -290,29 +290,12 @@ static int LaunchTraceGen(hc_ctx* ctx, bool shadow, long long n, HcHit* hitsLoca
 // Walk the uploaded reference-layout tree (producer bvh_access_dll2.cpp:199-717) on the host: validate every
 // offset, bound the traversal stack, and re-lay it out for the device (formats in hc_trace.cuh).  Quads and instance records keep
 // their quad index, so child words of interior nodes are unchanged.
-//   interior quad q : float4[8q+0..5] = cx[4] hx[4] cy[4] hy[4] cz[4] hz[4] (centre / half-extent of the children's boxes, see CentreHalf),
-//                     uint4[8q+6] = child words; an empty slot has half-extent HC_EMPTY_HALF_EXTENT < 0 and the sentinel word
+//   interior quad q : float4[8q+0..5] = minx[4] maxx[4] miny[4] maxy[4] minz[4] maxz[4], uint4[8q+6] = child words
 //   instance record : float4[8q+0..3] = inverse matrix columns, [8q+4] = {sub-tree word, realInstId, meshId, 0}
 //   triangle leaf   : pair records of 6 float4 {Ax0 Ax1 Ay0 Ay1 | Az0 Az1 E1x0 E1x1 | E1y0 E1y1 E1z0 E1z1 | E2x0 E2x1 E2y0 E2y1 |
 //                     E2z0 E2z1 prim0 prim1 | geom0 geom1 0 0} with E1 = B - A, E2 = C - A evaluated in float exactly as
 //                     IntersectAllPrimitivesInLeaf does (ctrace.h:159-160); an odd leaf is padded with a zero triangle, whose
 //                     determinant is 0 -> v = u = t = NaN -> every acceptance test fails.
-// centre / half-extent of one child slab (hc_trace.cuh, QuadKeys): [c - h, c + h] contains [lo, hi] in exact arithmetic, h rounded up and
-// inflated by 2^-21 (covers the rounding of h*|1/d| and of the centre distance in the kernel)
-#define HC_EMPTY_HALF_EXTENT (-8.0e37f)
-static inline void CentreHalf(float lo, float hi, float* c, float* h)
-{
-  const double cd = 0.5*(double(lo) + double(hi));
-  float cf = float(cd);
-  if (!std::isfinite(cf)) cf = 0.0f;
-  double hd = std::max(double(hi) - double(cf), double(cf) - double(lo));
-  if (!(hd >= 0.0)) hd = 0.0;
-  hd *= (1.0 + 1.0/2097152.0);
-  float hf = float(hd);
-  if (double(hf) < hd) hf = std::nextafterf(hf, std::numeric_limits<float>::infinity());
-  *c = cf; *h = hf;
-}
-
 static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const float* trif4, int trif4Num,
                                std::vector<float>& outNodes, std::vector<float>& outPairs, int* outStackBound,
                                const unsigned* alphaU2 = nullptr, int alphaNum = 0, std::vector<unsigned>* outAlphaPairs = nullptr)
@@ -379,18 +362,17 @@ static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const f
     if (it.inst) maxMesh = std::max(maxMesh, it.depth); else maxTop = std::max(maxTop, it.depth);
     if (seen[it.quad]) continue;     // shared mesh sub-trees: depth of first visit is representative
     seen[it.quad] = 1;
-    float* Q = outNodes.data() + size_t(it.quad)*32;       // rows {cx[4] hx[4]} {cy[4] hy[4]} {cz[4] hz[4]} {child words, spare}
+    float* Q = outNodes.data() + size_t(it.quad)*32;
     unsigned words[4];
     for (int i = 0; i < 4; i++)
     {
       const N& c = nd[size_t(it.quad)*4 + i];
       if (c.lo == 0xffffffffu && c.esc == 0xffffffffu)        // IsValidNode (cglobals.h:1321): an x slab at +inf fails for every finite ray
       {
-        for (int a = 0; a < 3; a++) { Q[8*a + i] = 0.0f; Q[8*a + 4 + i] = HC_EMPTY_HALF_EXTENT; }      // negative half-extent: far < near on every axis, never visited
-        words[i] = HC_NODE_SENTINEL;
+        Q[0 + i] = INF; Q[4 + i] = INF; words[i] = HC_NODE_SENTINEL;
         continue;
       }
-      for (int a = 0; a < 3; a++) CentreHalf(c.bmin[a], c.bmax[a], &Q[8*a + i], &Q[8*a + 4 + i]);
+      Q[0 + i] = c.bmin[0]; Q[4 + i] = c.bmax[0]; Q[8 + i] = c.bmin[1]; Q[12 + i] = c.bmax[1]; Q[16 + i] = c.bmin[2]; Q[20 + i] = c.bmax[2];
       const unsigned off = c.lo & 0x7fffffffu;
       if (c.lo & 0x80000000u)
       {

@@ -8,13 +8,16 @@
 // What differs is HOW the tree is stored and walked:
 //
 //   * hc_set_bvh re-lays the reference blobs out for the device (ConvertBvhForDevice, hc_api.cu).  A quad stays 128 bytes (one L1 line) and
-//     keeps its index, but becomes CENTRE / HALF-EXTENT, SoA: three 32-byte rows {c[4], h[4]} (x, y, z) + one row of child words.  Three
-//     256-bit loads (LDG.E.256) at FIXED offsets + one 128-bit load fetch it (round 1 used seven 128-bit loads through sign-selected row
-//     pointers: 7 L1 wavefronts per lane and quad instead of 4, and six registers of row pointers).  near / far = tc -/+ h*|1/d| with
-//     tc = (c - o)*(1/d): no near/far selection, 24 Blackwell packed-FP32 instructions (FADD2 / FMUL2 / FFMA2, two children each), the three
-//     axes merged by the three-input FMNMX3.  The box is CONSERVATIVE with respect to RayBoxIntersectionLite2: h is rounded up and inflated
-//     by 2^-21 at upload and the overlap test carries a relative margin of 2^-19, so every child the reference visits is visited; triangle
-//     acceptance is untouched.  Invalid children carry a negative half-extent (far < near on every axis), so IsValidNode costs nothing.
+//     keeps its index, but becomes SoA: six float4 rows {minx[4], maxx[4], miny[4], maxy[4], minz[4], maxz[4]}, one uint4 row of child words.
+//     Two children share a 64-bit register pair, so one Blackwell packed-FP32 instruction (FADD2 / FMUL2: sub.rn.f32x2, mul.rn.f32x2,
+//     each half rounded exactly like the scalar op) slab-tests two children; the near/far row of an axis is picked by the sign of
+//     the ray direction (bit-identical to min(lo,hi) / max(lo,hi) for a finite ray) and the three axes are merged with the
+//     three-input FMNMX3.  Invalid children carry an infinite box that can never pass, so IsValidNode costs nothing.
+//     The slab test is the reference's arithmetic BIT FOR BIT.  Round 2 measured a cheaper alternative - centre / half-extent rows fetched
+//     by three 256-bit loads at fixed offsets, conservative boxes with a 2^-19 margin - and rejected it: 35 % fewer L1 wavefronts bought
+//     0-5 % of speed, and in the band where a ray passes a leaf box within rounding while the triangle test's 1e-6 slack still accepts it the
+//     reference culls and a conservative box does not: 8 of the 16.8 M paths of the C1 frame (512 x 512, 64 spp) ended differently
+//     (profiles/r02_k2_variants.md, gpurun_out/c1_diff.json).
 //   * triangles are stored two to a record (96 B, three 256-bit loads) with precomputed edges {A, B-A, C-A}, SoA over the pair, so the
 //     whole Moeller-Trumbore test runs in packed FP32 on two triangles at once; the leaf's triangle count lives in the child word,
 //     which removes the dependent header fetch.
@@ -103,7 +106,6 @@ HC_DEV hc_f2 dot2_xnynz(const HcVec2& a, const HcVec2& bn) { return dif2(dif2(mu
 #define HC_CSWAP(ta, ca, tb, cb) { const bool s_ = (tb < ta); const float tt_ = s_ ? tb : ta; const float tu_ = s_ ? ta : tb; \
                                    const unsigned ct_ = s_ ? cb : ca; const unsigned cu_ = s_ ? ca : cb; ta = tt_; tb = tu_; ca = ct_; cb = cu_; }
 
-#define HC_BOX_MARGIN  1.0000019073486328125f   // 1 + 2^-19
 
 struct HcF8 { float4 a, b; };
 HC_DEV HcF8 ldg256(const void* p)
@@ -113,7 +115,6 @@ HC_DEV HcF8 ldg256(const void* p)
                : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
   return r;
 }
-HC_DEV hc_f2 fma2(hc_f2 a, hc_f2 b, hc_f2 c) { hc_f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 
 struct HcRayTrav
@@ -123,46 +124,53 @@ struct HcRayTrav
   int    instId;             // instance being traversed (-1 outside)
   int    sp, instTop;
   unsigned node;
+  unsigned nearX, nearY, nearZ;   // byte offset of the near row of each axis inside a quad (far row = near ^ 16)
 };
+
+// row order in a quad: minx 0, maxx 16, miny 32, maxy 48, minz 64, maxz 80 (bytes).  inv < 0 -> the max plane is the near one.
+HC_DEV void SetNearRows(HcRayTrav& r)
+{
+  r.nearX = (r.inv.x < 0.0f) ? 16u : 0u;
+  r.nearY = (r.inv.y < 0.0f) ? 48u : 32u;
+  r.nearZ = (r.inv.z < 0.0f) ? 80u : 64u;
+}
 
 HC_DEV void TravStart(HcRayTrav& r, float3 o, float3 d, float tFar)
 {
-  r.o = o; r.d = d; r.inv = SafeInverse(d);
+  r.o = o; r.d = d; r.inv = SafeInverse(d); SetNearRows(r);
   r.t = tFar; r.primId = -1; r.hitInst = -1; r.geomId = int(0xC0000000u);      // Make_Lite_Hit(t, -1), cglobals.h:1258-1266
   r.instId = -1; r.sp = 0; r.instTop = 0; r.node = 1u;
 }
 
-// slab test of the four children of quad `node` for this lane's ray: entry keys (MAXFLOAT = not to be visited) and child words.
-// RayBoxIntersectionLite2 (ctrace.h:32-53) visits a child when (tmin <= tmax) && (tmax >= 0) && (tmin <= tHit); with tHit >= 0 that is
-// max(tmin, 0) <= min(tmax, tHit), here with the relative margin on the right-hand side.
+// entry key of one child: tmin when (tmin <= tmax) && (tmax >= 0) && (tmin <= tHit), else MAXFLOAT (RayBoxIntersectionLite2 + the visit
+// condition of BVH4InstTraverse, ctrace.h:32-53, 880-895).  With tHit >= 0 that condition equals max(tmin, 0) <= min(tmax, tHit).
+// n* / f* are the per-axis near / far plane distances.
+HC_DEV float ChildKey(float nx, float ny, float nz, float fx, float fy, float fz, float tHit)
+{
+  const float tmin = max3f(nx, ny, nz), tmax = min3f(fx, fy, fz);
+  return (fmaxf(tmin, 0.0f) <= fminf(tmax, tHit)) ? tmin : HC_MAXFLOAT;
+}
+
+// slab test of the four children of quad `node` for this lane's ray: entry keys (MAXFLOAT = not to be visited) and child words
 HC_DEV void QuadKeys(const HcRayTrav& r, const HcBvh& bvh, const unsigned node, float& t0, float& t1, float& t2, float& t3,
                      unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3)
 {
   const char* q = reinterpret_cast<const char*>(bvh.nodes) + size_t(node)*128u;
-  const HcF8 X = ldg256(q), Y = ldg256(q + 32), Z = ldg256(q + 64);
-  const uint4 ch = __ldg(reinterpret_cast<const uint4*>(q + 96));
-  const float ax = fabsf(r.inv.x), ay = fabsf(r.inv.y), az = fabsf(r.inv.z);
+  const float4 NX = __ldg(reinterpret_cast<const float4*>(q + r.nearX)), FX = __ldg(reinterpret_cast<const float4*>(q + (r.nearX ^ 16u)));
+  const float4 NY = __ldg(reinterpret_cast<const float4*>(q + r.nearY)), FY = __ldg(reinterpret_cast<const float4*>(q + (r.nearY ^ 16u)));
+  const float4 NZ = __ldg(reinterpret_cast<const float4*>(q + r.nearZ)), FZ = __ldg(reinterpret_cast<const float4*>(q + (r.nearZ ^ 16u)));
+  const uint4  ch = __ldg(reinterpret_cast<const uint4*>(q + 96));
   const hc_f2 oX = bc2(r.o.x), oY = bc2(r.o.y), oZ = bc2(r.o.z), iX = bc2(r.inv.x), iY = bc2(r.inv.y), iZ = bc2(r.inv.z);
-  const hc_f2 pX = bc2(ax), pY = bc2(ay), pZ = bc2(az), mX = bc2(-ax), mY = bc2(-ay), mZ = bc2(-az);
-  const hc_f2 tx01 = mul2(sub2(lo2(X.a), oX), iX), tx23 = mul2(sub2(hi2(X.a), oX), iX);
-  const hc_f2 ty01 = mul2(sub2(lo2(Y.a), oY), iY), ty23 = mul2(sub2(hi2(Y.a), oY), iY);
-  const hc_f2 tz01 = mul2(sub2(lo2(Z.a), oZ), iZ), tz23 = mul2(sub2(hi2(Z.a), oZ), iZ);
+  // RayBoxIntersectionLite2 (ctrace.h:32-53): t = invDir*(plane - pos)
   float nx0, nx1, nx2, nx3, ny0, ny1, ny2, ny3, nz0, nz1, nz2, nz3, fx0, fx1, fx2, fx3, fy0, fy1, fy2, fy3, fz0, fz1, fz2, fz3;
-  upk2(fma2(lo2(X.b), mX, tx01), nx0, nx1); upk2(fma2(hi2(X.b), mX, tx23), nx2, nx3);
-  upk2(fma2(lo2(X.b), pX, tx01), fx0, fx1); upk2(fma2(hi2(X.b), pX, tx23), fx2, fx3);
-  upk2(fma2(lo2(Y.b), mY, ty01), ny0, ny1); upk2(fma2(hi2(Y.b), mY, ty23), ny2, ny3);
-  upk2(fma2(lo2(Y.b), pY, ty01), fy0, fy1); upk2(fma2(hi2(Y.b), pY, ty23), fy2, fy3);
-  upk2(fma2(lo2(Z.b), mZ, tz01), nz0, nz1); upk2(fma2(hi2(Z.b), mZ, tz23), nz2, nz3);
-  upk2(fma2(lo2(Z.b), pZ, tz01), fz0, fz1); upk2(fma2(hi2(Z.b), pZ, tz23), fz2, fz3);
-  const float tHitK = r.t*HC_BOX_MARGIN;
-  float m0, m1, m2, m3;
-  upk2(mul2(pk2(min3f(fx0, fy0, fz0), min3f(fx1, fy1, fz1)), bc2(HC_BOX_MARGIN)), m0, m1);
-  upk2(mul2(pk2(min3f(fx2, fy2, fz2), min3f(fx3, fy3, fz3)), bc2(HC_BOX_MARGIN)), m2, m3);
-  const float n0 = max3f(nx0, ny0, nz0), n1 = max3f(nx1, ny1, nz1), n2 = max3f(nx2, ny2, nz2), n3 = max3f(nx3, ny3, nz3);
-  t0 = (fmaxf(n0, 0.0f) <= fminf(m0, tHitK)) ? n0 : HC_MAXFLOAT;
-  t1 = (fmaxf(n1, 0.0f) <= fminf(m1, tHitK)) ? n1 : HC_MAXFLOAT;
-  t2 = (fmaxf(n2, 0.0f) <= fminf(m2, tHitK)) ? n2 : HC_MAXFLOAT;
-  t3 = (fmaxf(n3, 0.0f) <= fminf(m3, tHitK)) ? n3 : HC_MAXFLOAT;
+  upk2(mul2(iX, sub2(lo2(NX), oX)), nx0, nx1); upk2(mul2(iX, sub2(hi2(NX), oX)), nx2, nx3);
+  upk2(mul2(iX, sub2(lo2(FX), oX)), fx0, fx1); upk2(mul2(iX, sub2(hi2(FX), oX)), fx2, fx3);
+  upk2(mul2(iY, sub2(lo2(NY), oY)), ny0, ny1); upk2(mul2(iY, sub2(hi2(NY), oY)), ny2, ny3);
+  upk2(mul2(iY, sub2(lo2(FY), oY)), fy0, fy1); upk2(mul2(iY, sub2(hi2(FY), oY)), fy2, fy3);
+  upk2(mul2(iZ, sub2(lo2(NZ), oZ)), nz0, nz1); upk2(mul2(iZ, sub2(hi2(NZ), oZ)), nz2, nz3);
+  upk2(mul2(iZ, sub2(lo2(FZ), oZ)), fz0, fz1); upk2(mul2(iZ, sub2(hi2(FZ), oZ)), fz2, fz3);
+  t0 = ChildKey(nx0, ny0, nz0, fx0, fy0, fz0, r.t); t1 = ChildKey(nx1, ny1, nz1, fx1, fy1, fz1, r.t);
+  t2 = ChildKey(nx2, ny2, nz2, fx2, fy2, fz2, r.t); t3 = ChildKey(nx3, ny3, nz3, fx3, fy3, fz3, r.t);
   c0 = ch.x; c1 = ch.y; c2 = ch.z; c3 = ch.w;
 }
 
@@ -173,21 +181,19 @@ HC_DEV void QuadKeys(const HcRayTrav& r, const HcBvh& bvh, const unsigned node, 
     r.o = f3(__uint_as_float(a_.x), __uint_as_float(a_.y), __uint_as_float(b_.x));                         \
     r.d = f3(__uint_as_float(b_.y), __uint_as_float(c_.x), __uint_as_float(c_.y));                         \
     r.inv = f3(__uint_as_float(d_.x), __uint_as_float(d_.y), __uint_as_float(e_.x));                       \
-    r.instId = -1;                                                                                         \
+    SetNearRows(r); r.instId = -1;                                                                         \
   }
 
-// pop until an entry that can still matter: entry distance <= current hit (with the box margin: the stored distance is ours, up to
-// 2 ulp above the reference's; t is the same quantity in world and object space because the direction is not renormalised); leave the
-// instance when the stack has dropped below its entry level
+// pop until an entry that can still matter (entry distance <= current hit; t is the same quantity in world and object space because the
+// direction is not renormalised); leave the instance when the stack has dropped below its entry level
 #define HC_POP(r, stk, saved)                                                                               \
   {                                                                                                        \
-    const float tK_ = r.t*HC_BOX_MARGIN;                                                                   \
     for (;;)                                                                                               \
     {                                                                                                      \
       if (r.sp == 0) { r.node = HC_NODE_SENTINEL; break; }                                                 \
       r.sp--;                                                                                              \
       const uint2 e_ = stk[r.sp];                                                                          \
-      if (!(__uint_as_float(e_.y) <= tK_)) continue;                                                       \
+      if (!(__uint_as_float(e_.y) <= r.t)) continue;                                                       \
       r.node = e_.x; break;                                                                                \
     }                                                                                                      \
     if (r.instId >= 0 && r.sp < r.instTop) HC_LEAVE(r, saved)                                              \
@@ -282,7 +288,7 @@ HC_DEV bool PairTest(HcRayTrav& r, const HcBvh& bvh, const size_t pairIndex)
     saved[3] = make_uint2(__float_as_uint(r.inv.x), __float_as_uint(r.inv.y));                             \
     saved[4] = make_uint2(__float_as_uint(r.inv.z), 0u);                                                   \
     r.instId = __float_as_int(w_.y); r.instTop = r.sp;                                                     \
-    r.o = mul4x3(m_, r.o); r.d = mul3x3(m_, r.d); r.inv = SafeInverse(r.d);                                \
+    r.o = mul4x3(m_, r.o); r.d = mul3x3(m_, r.d); r.inv = SafeInverse(r.d); SetNearRows(r);                \
     r.node = __float_as_uint(w_.x);                                                                        \
   }
 
