@@ -441,7 +441,7 @@ int hc_ctx_create(int device, hc_ctx** out)
   HC_CUDA(cudaMemsetAsync(c->counters.ptr, 0, c->counters.bytes, c->stream));
   c->globalsHead.assign(HC_EG_HEAD_BYTES, 0);
   if (const char* e = getenv("HC_TRACE_REFILL")) { const int v = atoi(e); if (v >= 1 && v <= 32) c->traceRefill = v; }
-  if (const char* e = getenv("HC_TRACE_QBIAS")) { const int v = atoi(e); if (v >= 1 && v <= 64) c->traceQBias = v; }
+  if (const char* e = getenv("HC_TRACE_QBIAS")) { const int v = atoi(e); if (v >= 2 && v <= 64) c->traceQBias = v; }      // < 2 would leave states where neither step runs
   *out = c;
   return HC_OK;
 }
