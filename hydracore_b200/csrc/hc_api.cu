@@ -50,6 +50,9 @@ void hc_buf_free(HcDevBuf& b) { if (b.ptr) cudaFree(b.ptr); b.ptr = nullptr; b.b
 // ALPHA (closest hit only): the second, alpha-tested tree of the reference (BVH4InstTraverseAlpha after BVH4InstTraverse in
 // IntegratorCommon::rayTrace, CPUExp_Integrators_Common.cpp:122-150): starts from the hit tree 0 left in hitsOut and keeps it unless a closer
 // triangle passes the opacity lookup.
+// outStride: 1 = results go to dense arrays (hit records of 16 B, visibility bytes); > 1 = the rays live in the path tracer's queue of 32-byte
+// elements (hc_path.cu): the hit record is stored at hitsOut + ray*outStride (float4 units) and an OCCLUDED shadow ray gets its t_far zeroed
+// (visOut points at the {sdir, t_far} float4 of path 0), which is how the shade kernel reads "no light from this sample".
 // RAYGEN (ray-casting pass only): 0 = rays come from memory; 1 = the primary eye ray of pixel idx is generated in the fetch (K1 fused into K2:
 // MakeRandEyeRay with zero offsets, the arithmetic of k_make_eye_rays); 2 = the shadow ray towards `light` is generated from the regenerated eye
 // ray and the hit record hitsIn[idx] (k_make_shadow_rays fused into K2s).  Saves two launches and 2 x 64 B per pixel of ray traffic.
@@ -58,7 +61,7 @@ template<bool ANYHIT, int TREE1 = 0, int RAYGEN = 0>      // TREE1: 0 = first tr
 __global__ void __launch_bounds__(HC_TRACE_BLOCK, HC_TRACE_MINB)
 k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restrict__ rdir, const int stride, const long long nArg,
         const int* __restrict__ nDev, HcHit* __restrict__ hitsOut, unsigned char* __restrict__ visOut, unsigned* __restrict__ counter, const int refillMin, const int qBias,
-        const int tileW, const HcRayGen gen = HcRayGen())
+        const int tileW, const int outStride, const HcRayGen gen = HcRayGen())
 {
   const unsigned n = (unsigned)(nDev ? (long long)(*nDev) : nArg);      // the path tracer keeps its live-path count on the device
   uint2 stk[HC_STACK_CAP];                                              // {child word, entry distance}
@@ -122,11 +125,11 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
         TravStart(r, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
         if (TREE1 != 0 && !ANYHIT)
         {
-          const float4 h = reinterpret_cast<const float4*>(hitsOut)[idx];      // Lite_Hit carried from tree to tree
+          const float4 h = reinterpret_cast<const float4*>(hitsOut)[size_t(idx)*outStride];      // Lite_Hit carried from tree to tree
           r.t = h.x; r.primId = __float_as_int(h.y); r.hitInst = __float_as_int(h.z); r.geomId = __float_as_int(h.w);
         }
-        if (ANYHIT && TREE1 != 0 && visOut[idx] == 0) { idle = true; r.node = HC_NODE_SENTINEL; }          // already occluded in the first tree
-        else if (ANYHIT && !(dd.w > 0.0f)) { visOut[idx] = 1; idle = true; r.node = HC_NODE_SENTINEL; }     // maxDist <= 0: lit (trace.cl:343-351)
+        if (ANYHIT && TREE1 != 0 && outStride == 1 && visOut[idx] == 0) { idle = true; r.node = HC_NODE_SENTINEL; }   // already occluded in the first tree
+        else if (ANYHIT && !(dd.w > 0.0f)) { if (outStride == 1) visOut[idx] = 1; idle = true; r.node = HC_NODE_SENTINEL; }     // maxDist <= 0: lit (trace.cl:343-351); in a path record an occluded ray has t_far = 0 already
         else if (!RayIsFinite(r.o, r.d)) r.node = HC_NODE_SENTINEL;              // every comparison of the reference fails on NaN: no hit
       }
     }
@@ -170,8 +173,12 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
 
     if (!idle && r.node == HC_NODE_SENTINEL)
     {
-      if (ANYHIT) visOut[rayIdx] = (r.primId != -1) ? 0 : 1;
-      else reinterpret_cast<float4*>(hitsOut)[rayIdx] = make_float4(r.t, __int_as_float(r.primId), __int_as_float(r.hitInst), __int_as_float(r.geomId));
+      if (ANYHIT)
+      {
+        if (outStride == 1) visOut[rayIdx] = (r.primId != -1) ? 0 : 1;
+        else if (r.primId != -1) reinterpret_cast<float*>(visOut)[size_t(rayIdx)*outStride*4 + 3] = 0.0f;
+      }
+      else reinterpret_cast<float4*>(hitsOut)[size_t(rayIdx)*outStride] = make_float4(r.t, __int_as_float(r.primId), __int_as_float(r.hitInst), __int_as_float(r.geomId));
       idle = true;
     }
   }
@@ -219,12 +226,12 @@ static int NextCounter(hc_ctx* ctx, cudaStream_t stream, unsigned** out)
 }
 
 // launch K2 (closest) or K2s (any-hit) on device-resident streams; used by hc_trace_* and by the path tracer
-static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW = 0, cudaStream_t stream = nullptr);
+static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW = 0, cudaStream_t stream = nullptr, int outStride = 1);
 int hc_launch_trace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, HcHit* hits, unsigned char* vis)
 { return LaunchTrace(ctx, anyHit, rpos, rdir, stride, n, nullptr, hits, vis); }
-int hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis, cudaStream_t stream)
-{ return LaunchTrace(ctx, anyHit, rpos, rdir, 1, nUpper, nDev, hits, vis, 0, stream); }
-static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW, cudaStream_t stream)
+int hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis, int outStride, cudaStream_t stream)
+{ return LaunchTrace(ctx, anyHit, rpos, rdir, stride, nUpper, nDev, hits, vis, 0, stream, outStride); }
+static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, const int* nDev, HcHit* hits, unsigned char* vis, int tileW, cudaStream_t stream, int outStride)
 {
   if (n <= 0) return HC_OK;
   if (!stream) stream = ctx->stream;
@@ -236,8 +243,8 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   int rc = NextCounter(ctx, stream, &counter); if (rc) return rc;
   const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
   const int rf = ctx->traceRefill > 0 ? ctx->traceRefill : HC_REFILL_MIN, qb = ctx->traceQBias > 0 ? ctx->traceQBias : HC_QBIAS;
-  if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf, qb, tileW);
-  else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, qb, tileW);
+  if (anyHit) k_trace<true><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, nullptr, vis, counter, rf, qb, tileW, outStride);
+  else        k_trace<false><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, rpos, rdir, stride, n, nDev, hits, nullptr, counter, rf, qb, tileW, outStride);
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   if (ctx->haveTree1 && (!anyHit || ctx->shadowTrees == 1))
@@ -256,11 +263,11 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
       HC_REQUIRE(ctx->globals.ptr && ctx->storage[HC_STORAGE_TEXTURES].ptr, HC_E_STATE, "hc_trace: the alpha-tested tree needs the textures storage and the globals (texture table)");
       b1.alphaPairs = (const uint4*)ctx->bvh1AlphaPairs.ptr; b1.alphaTable = (const uint2*)ctx->bvh1AlphaTable.ptr;
       b1.textures = (const int4*)ctx->storage[HC_STORAGE_TEXTURES].ptr; b1.texturesTable = (const int*)ctx->globals.ptr + texTab;
-      if (anyHit) k_trace<true, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, nullptr, vis, counter1, rf, qb, tileW);
-      else        k_trace<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, qb, tileW);
+      if (anyHit) k_trace<true, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, nullptr, vis, counter1, rf, qb, tileW, outStride);
+      else        k_trace<false, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, qb, tileW, outStride);
     }
-    else if (anyHit) k_trace<true, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, nullptr, vis, counter1, rf, qb, tileW);
-    else             k_trace<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, qb, tileW);
+    else if (anyHit) k_trace<true, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, nullptr, vis, counter1, rf, qb, tileW, outStride);
+    else             k_trace<false, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(b1, rpos, rdir, stride, n, nDev, hits, nullptr, counter1, rf, qb, tileW, outStride);
     HC_CUDA(cudaGetLastError());
     ctx->stats.kernelLaunches++;
   }
@@ -279,8 +286,8 @@ static int LaunchTraceGen(hc_ctx* ctx, bool shadow, long long n, HcHit* hitsLoca
   int rc = NextCounter(ctx, stream, &counter); if (rc) return rc;
   const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
   const int rf = ctx->traceRefill > 0 ? ctx->traceRefill : HC_REFILL_MIN, qb = ctx->traceQBias > 0 ? ctx->traceQBias : HC_QBIAS;
-  if (shadow) k_trace<true, 0, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, nullptr, vis, counter, rf, qb, tileW, gen);
-  else        k_trace<false, 0, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, hitsLocal, nullptr, counter, rf, qb, tileW, gen);
+  if (shadow) k_trace<true, 0, 2><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, nullptr, vis, counter, rf, qb, tileW, 1, gen);
+  else        k_trace<false, 0, 1><<<grid, HC_TRACE_BLOCK, 0, stream>>>(bvh, nullptr, nullptr, 0, n, nullptr, hitsLocal, nullptr, counter, rf, qb, tileW, 1, gen);
   HC_CUDA(cudaGetLastError());
   ctx->stats.kernelLaunches++;
   if (shadow) ctx->stats.raysShadow += (uint64_t)n; else ctx->stats.raysClosest += (uint64_t)n;

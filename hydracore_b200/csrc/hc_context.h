@@ -96,5 +96,5 @@ void hc_path_free(hc_ctx* ctx);   // hc_path.cu
 void hc_comm_free(hc_ctx* ctx);   // hc_comm.cu
 int  hc_comm_gather_raycast(hc_ctx* ctx, void* hits16, unsigned char* vis, int dstRank);
 int  hc_path_owned_pixels(hc_ctx* ctx, const int** outDevicePixels, int* outCount);   // hc_path.cu: device list of this rank's pixels (hc_pt_set_tiles)
-int  hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis, cudaStream_t stream = nullptr);
+int  hc_launch_trace_counted(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long nUpper, const int* nDev, HcHit* hits, unsigned char* vis, int outStride, cudaStream_t stream = nullptr);
 int  hc_launch_trace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float4* rdir, int stride, long long n, HcHit* hits, unsigned char* vis);   // hc_api.cu

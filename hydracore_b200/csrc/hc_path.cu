@@ -26,11 +26,29 @@
 #define HC_SHADE_MINB 5      // CTAs per SM: 96 registers. Swept again after the code-size cut (C3 / C4 shade ms): 3 -> 1.81 / 1.19, 4 -> 1.55 / 1.04, 5 -> 1.51 / 1.03, 6 -> 1.49 / 1.06
 #endif
 
-struct HcPathState          // one half of the double buffer
+// One half of the double-buffered path queue: 128 bytes per path in FOUR arrays of 32-byte elements (one L2 / DRAM sector each):
+//   A  rpos.xyz, bsdf pdf      | rdir.xyz, flags            the ray of K2 (one 256-bit load, interleaved {pos, dir} with stride 2)
+//   B  throughput.xyz, pixel | specular bit | accum.xyz, qmc position
+//   C  spos.xyz, sexp.x        | sdir.xyz, t_far            the shadow ray of K2s (it zeroes t_far when the ray is occluded)
+//   D  sexp.y, sexp.z, rng.x, rng.y | hit record            (the hit record is written by K2)
+// Unpermuted, the 32 lanes of a warp read 1 KB contiguous per array; through the material-sort permutation every gathered element is exactly
+// one sector.  Round 1 kept nine arrays of 16-, 8- and 4-byte elements: the permuted gather pulled 32-byte sectors for 16-byte elements and
+// read 2.2 x the bytes it needed (profiles/r01_final_ncu_full_summary.md); one 128-byte record per path (tried first in round 2) reads no
+// spare byte either but turns every load instruction into 32 separate L1 wavefronts: C3 shade 1.49 -> 1.61 ms, K2 3.37 -> 3.50 ms.
+struct HcPathState { float4* a; float4* b; float4* c; float4* d; };
+struct HcF8p { float4 x, y; };
+HC_DEV HcF8p LoadPair(const float4* p)
 {
-  float4* rpos; float4* rdir; float4* thr; float4* accum; uint2* rng; unsigned* qpos;
-  float4* spos; float4* sdir; float4* sexp;
-};
+  HcF8p r;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.x.x), "=f"(r.x.y), "=f"(r.x.z), "=f"(r.x.w), "=f"(r.y.x), "=f"(r.y.y), "=f"(r.y.z), "=f"(r.y.w) : "l"(p));
+  return r;
+}
+HC_DEV void StorePair(float4* p, float4 x, float4 y)
+{
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w), "f"(y.x), "f"(y.y), "f"(y.z), "f"(y.w) : "memory");
+}
 
 struct HcPassParams
 {
@@ -84,15 +102,12 @@ k_pt_generate(const HcCamera cam, const HcPassParams pp, const int n, const int*
     const float4 offs = make_float4(-1.0f + 2.0f*r.x, -1.0f + 2.0f*r.y, -1.0f + 2.0f*r.z, -1.0f + 2.0f*r.w);   // rndUniform(gen, -1, 1), crandom.h:617-620
     MakeRandEyeRay(pixel % pp.width, pixel / pp.width, pp.width, pp.height, offs, cam, rpos, rdir);
   }
-  st.rpos[i]  = make_float4(rpos.x, rpos.y, rpos.z, 1.0f);                          // makeInitialMisData: matSamplePdf = 1
-  st.rdir[i]  = make_float4(rdir.x, rdir.y, rdir.z, __uint_as_float(0u));           // flags = 0
-  st.thr[i]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float((unsigned)pixel | 0x80000000u));   // isSpecular = 1
-  st.accum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  st.rng[i]   = make_uint2(g.x, g.y);
-  if (st.qpos) st.qpos[i] = qpos;
-  st.sdir[i]  = make_float4(0.0f, 1.0f, 0.0f, 0.0f);                                // no pending shadow ray
-  st.spos[i]  = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  st.sexp[i]  = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  StorePair(st.a + 2*size_t(i), make_float4(rpos.x, rpos.y, rpos.z, 1.0f),                                   // makeInitialMisData: matSamplePdf = 1
+                                make_float4(rdir.x, rdir.y, rdir.z, __uint_as_float(0u)));                   // flags = 0
+  StorePair(st.b + 2*size_t(i), make_float4(1.0f, 1.0f, 1.0f, __uint_as_float((unsigned)pixel | 0x80000000u)),  // isSpecular = 1
+                                make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(qpos)));
+  StorePair(st.c + 2*size_t(i), make_float4(0.0f, 0.0f, 0.0f, 0.0f), make_float4(0.0f, 1.0f, 0.0f, 0.0f));     // no pending shadow ray
+  st.d[2*size_t(i)] = make_float4(0.0f, 0.0f, __uint_as_float(g.x), __uint_as_float(g.y));
 }
 
 // ------------------------------------------------------------------------------------------------------------------ K3+K4+K5+K6+K7: shade
@@ -107,7 +122,7 @@ HC_DEV void FinishPath(float4* __restrict__ fb, uint2* __restrict__ pixelRng, in
 template<bool NMAP>
 __global__ void __launch_bounds__(HC_SHADE_BLOCK, HC_SHADE_MINB)
 k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, int* __restrict__ nOut,
-           const HcPathState in, HcPathState out, const HcHit* __restrict__ hits, const unsigned char* __restrict__ vis,
+           const HcPathState in, HcPathState out,
            const unsigned* __restrict__ qmcTable, float4* __restrict__ fb, uint2* __restrict__ pixelRng, const int* __restrict__ perm)
 {
   const int tid = blockIdx.x*blockDim.x + threadIdx.x;
@@ -123,9 +138,10 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
 
   if (tid < n)
   {
-    const float4 rp = in.rpos[i], rd = in.rdir[i], th = in.thr[i], ac = in.accum[i];
-    const uint2 r2 = in.rng[i]; g.x = r2.x; g.y = r2.y;
-    if (in.qpos) qpos = in.qpos[i];
+    const HcF8p pa = LoadPair(in.a + 2*size_t(i)), pb = LoadPair(in.b + 2*size_t(i)), pc = LoadPair(in.c + 2*size_t(i)), pd = LoadPair(in.d + 2*size_t(i));
+    const float4 rp = pa.x, rd = pa.y, th = pb.x, ac = pb.y, r4 = pc.x, r5 = pc.y, r6 = pd.x, r7 = pd.y;
+    g.x = __float_as_uint(r6.z); g.y = __float_as_uint(r6.w);
+    qpos = __float_as_uint(ac.w);
     const float3 rayPos = f3(rp), rayDir = f3(rd);
     const unsigned flags = __float_as_uint(rd.w);
     pixSpec = __float_as_uint(th.w);
@@ -136,10 +152,9 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
     thr = f3(th); accum = f3(ac);
 
     // pending direct light of the previous bounce: accumColor += accumuThoroughput*explicitColor (PT_Loop.cpp:253), shadow in {0,1}
-    const float4 se = in.sexp[i];
-    if (in.sdir[i].w > 0.0f && vis[i] != 0) accum += f3(se);
+    if (r5.w > 0.0f) accum += f3(r4.w, r6.x, r6.y);                        // K2s zeroed t_far when the shadow ray was occluded
 
-    const HcHit hit = hits[i];
+    HcHit hit; hit.t = r7.x; hit.primId = __float_as_int(r7.y); hit.instId = __float_as_int(r7.z); hit.geomId = __float_as_int(r7.w);
     const bool isPT = (pp.integrator == HC_INTEGRATOR_PT);
     float3 curr = f3(0, 0, 0);
     bool finished = false;
@@ -258,13 +273,10 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
   if (alive)
   {
     const int j = base + __popc(mask & ((1u << lane) - 1u));
-    out.rpos[j]  = make_float4(nPos.x, nPos.y, nPos.z, nPdf);
-    out.rdir[j]  = make_float4(nDir.x, nDir.y, nDir.z, __uint_as_float(nFlags));
-    out.thr[j]   = make_float4(thr.x, thr.y, thr.z, __uint_as_float(pixSpec));
-    out.accum[j] = make_float4(accum.x, accum.y, accum.z, 0.0f);
-    out.rng[j]   = make_uint2(g.x, g.y);
-    if (out.qpos) out.qpos[j] = qpos;
-    out.spos[j] = sPos; out.sdir[j] = sDir; out.sexp[j] = sExp;
+    StorePair(out.a + 2*size_t(j), make_float4(nPos.x, nPos.y, nPos.z, nPdf), make_float4(nDir.x, nDir.y, nDir.z, __uint_as_float(nFlags)));
+    StorePair(out.b + 2*size_t(j), make_float4(thr.x, thr.y, thr.z, __uint_as_float(pixSpec)), make_float4(accum.x, accum.y, accum.z, __uint_as_float(qpos)));
+    StorePair(out.c + 2*size_t(j), make_float4(sPos.x, sPos.y, sPos.z, sExp.x), sDir);
+    out.d[2*size_t(j)] = make_float4(sExp.y, sExp.z, __uint_as_float(g.x), __uint_as_float(g.y));
   }
 }
 
@@ -288,7 +300,7 @@ HC_DEV int SortKeyOf(const HcScene& s, const HcHit& h, int numKeys)
 }
 
 __global__ void __launch_bounds__(HC_SORT_BLOCK)
-k_pt_sort_count(const HcScene s, const int* __restrict__ nIn, const HcHit* __restrict__ hits, unsigned short* __restrict__ keys,
+k_pt_sort_count(const HcScene s, const int* __restrict__ nIn, const float4* __restrict__ recD, unsigned short* __restrict__ keys,
                 int* __restrict__ bucketCount, const int numKeys)
 {
   extern __shared__ int sCount[];
@@ -297,7 +309,9 @@ k_pt_sort_count(const HcScene s, const int* __restrict__ nIn, const HcHit* __res
   const int n = *nIn;
   for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x)
   {
-    const int key = SortKeyOf(s, hits[i], numKeys);
+    const float4 h4 = recD[2*size_t(i) + 1];
+    HcHit h; h.t = h4.x; h.primId = __float_as_int(h4.y); h.instId = __float_as_int(h4.z); h.geomId = __float_as_int(h4.w);
+    const int key = SortKeyOf(s, h, numKeys);
     keys[i] = (unsigned short)key;
     atomicAdd(&sCount[key], 1);
   }
@@ -376,8 +390,8 @@ __global__ void k_fb_normalize(const float4* __restrict__ fb, float4* __restrict
 // ------------------------------------------------------------------------------------------------------------------ host side
 struct HcPathHost
 {
-  HcDevBuf state[2][9];       // rpos rdir thr accum rng qpos spos sdir sexp
-  HcDevBuf hits, vis, owned, pathCount, ldr;
+  HcDevBuf state[2][4];       // the two halves of the path queue: arrays A, B, C, D of 32-byte elements
+  HcDevBuf owned, pathCount, ldr;
   HcDevBuf sortKeys, sortCount, sortCursor, sortPerm;   // material sort: u16 key per path, 2 x HC_SORT_MAX_KEYS counters, int index per path
   std::vector<unsigned char> materialsHost, globalsHost;
   int64_t capacity = 0;
@@ -393,8 +407,8 @@ void hc_path_free(hc_ctx* ctx)
 {
   HcPathHost* p = PH(ctx);
   if (!p) return;
-  for (int b = 0; b < 2; b++) for (int k = 0; k < 9; k++) hc_buf_free(p->state[b][k]);
-  hc_buf_free(p->hits); hc_buf_free(p->vis); hc_buf_free(p->owned); hc_buf_free(p->pathCount); hc_buf_free(p->ldr);
+  for (int b = 0; b < 2; b++) for (int k = 0; k < 4; k++) hc_buf_free(p->state[b][k]);
+  hc_buf_free(p->owned); hc_buf_free(p->pathCount); hc_buf_free(p->ldr);
   hc_buf_free(p->sortKeys); hc_buf_free(p->sortCount); hc_buf_free(p->sortCursor); hc_buf_free(p->sortPerm);
   for (cudaEvent_t e : p->evPool) cudaEventDestroy(e);
   delete p;
@@ -410,16 +424,9 @@ static HcPathHost* EnsureHost(hc_ctx* ctx)
 static int ReserveState(hc_ctx* ctx, int64_t n, bool qmc)
 {
   HcPathHost* p = EnsureHost(ctx);
-  static const int elem[9] = { 16, 16, 16, 16, 8, 4, 16, 16, 16 };
-  for (int b = 0; b < 2; b++)
-    for (int k = 0; k < 9; k++)
-    {
-      if (k == 5 && !qmc) continue;
-      int rc = hc_buf_reserve(ctx, p->state[b][k], uint64_t(n)*elem[k]); if (rc) return rc;
-    }
   int rc;
-  if ((rc = hc_buf_reserve(ctx, p->hits, uint64_t(n)*16))) return rc;
-  if ((rc = hc_buf_reserve(ctx, p->vis, uint64_t(n)))) return rc;
+  (void)qmc;
+  for (int b = 0; b < 2; b++) for (int k = 0; k < 4; k++) if ((rc = hc_buf_reserve(ctx, p->state[b][k], uint64_t(n)*32))) return rc;
   if ((rc = hc_buf_reserve(ctx, p->pathCount, 2*256*sizeof(int)))) return rc;      // live counts per bounce, one block per pipeline
   if ((rc = hc_buf_reserve(ctx, p->sortKeys, uint64_t(n)*2))) return rc;
   if ((rc = hc_buf_reserve(ctx, p->sortPerm, uint64_t(n)*4))) return rc;
@@ -433,12 +440,9 @@ static int ReserveState(hc_ctx* ctx, int64_t n, bool qmc)
   return HC_OK;
 }
 
-static HcPathState StateOf(HcPathHost* p, int b, bool qmc)
+static HcPathState StateOf(HcPathHost* p, int b)
 {
-  HcPathState s;
-  s.rpos = (float4*)p->state[b][0].ptr; s.rdir = (float4*)p->state[b][1].ptr; s.thr = (float4*)p->state[b][2].ptr;
-  s.accum = (float4*)p->state[b][3].ptr; s.rng = (uint2*)p->state[b][4].ptr; s.qpos = qmc ? (unsigned*)p->state[b][5].ptr : nullptr;
-  s.spos = (float4*)p->state[b][6].ptr; s.sdir = (float4*)p->state[b][7].ptr; s.sexp = (float4*)p->state[b][8].ptr;
+  HcPathState s; s.a = (float4*)p->state[b][0].ptr; s.b = (float4*)p->state[b][1].ptr; s.c = (float4*)p->state[b][2].ptr; s.d = (float4*)p->state[b][3].ptr;
   return s;
 }
 
@@ -831,9 +835,8 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   struct Pipe { int first, n; int* counts; cudaStream_t s, side; cudaEvent_t evFork, evJoin; };
   auto sliceOf = [&](int b, int first) -> HcPathState
   {
-    HcPathState st = StateOf(p, b, qmc);
-    st.rpos += first; st.rdir += first; st.thr += first; st.accum += first; st.rng += first; if (st.qpos) st.qpos += first;
-    st.spos += first; st.sdir += first; st.sexp += first;
+    HcPathState st = StateOf(p, b);
+    st.a += 2*size_t(first); st.b += 2*size_t(first); st.c += 2*size_t(first); st.d += 2*size_t(first);
     return st;
   };
   auto genPipe = [&](const Pipe& q) -> int
@@ -850,8 +853,6 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   {
     int rc = 0;
     HcPathState in = sliceOf(cur, q.first), out = sliceOf(1 - cur, q.first);
-    HcHit* hits = (HcHit*)p->hits.ptr + q.first;
-    unsigned char* vis = (unsigned char*)p->vis.ptr + q.first;
     int* counts = q.counts;
     const int n = q.n;
     // the shadow rays of the previous bounce and the closest-hit rays of this one are independent: two streams, so that the tail of
@@ -862,13 +863,15 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
       HC_CUDA(cudaEventRecord(q.evFork, q.s));
       HC_CUDA(cudaStreamWaitEvent(q.side, q.evFork, 0));
     }
-    HC_STAGE(0, if ((rc = hc_launch_trace_counted(ctx, false, in.rpos, in.rdir, n, counts + depth, hits, nullptr, q.s))) return rc);
+    // closest hit: ray = array A (interleaved {pos, dir}), hit record -> second half of the D element
+    HC_STAGE(0, if ((rc = hc_launch_trace_counted(ctx, false, in.a, in.a + 1, 2, n, counts + depth, (HcHit*)(in.d + 1), nullptr, 2, q.s))) return rc);
     if (haveShadow)
     {
       // timing: the "shadow" stage is what the any-hit launch ADDS after the closest-hit launch has finished (both measured on the
       // main stream), so that the stage times still add up to the pass
       if ((rc = stageBegin(1))) return rc;
-      if ((rc = hc_launch_trace_counted(ctx, true, in.spos, in.sdir, n, counts + depth, nullptr, vis, q.side))) return rc;
+      // any hit: shadow ray = array C (the origin's .w carries sexp.x and is ignored), an occluded ray gets its t_far zeroed
+      if ((rc = hc_launch_trace_counted(ctx, true, in.c, in.c + 1, 2, n, counts + depth, nullptr, (unsigned char*)(in.c + 1), 2, q.side))) return rc;
       HC_CUDA(cudaEventRecord(q.evJoin, q.side));
       HC_CUDA(cudaStreamWaitEvent(q.s, q.evJoin, 0));
       if ((rc = stageEnd())) return rc;
@@ -879,7 +882,7 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
       // material sort of the live-path queue (skipped while the queue is still in screen order and therefore coherent)
       const int sortGrid = std::min((n + HC_SORT_BLOCK - 1)/HC_SORT_BLOCK, ctx->smCount*8);
       if ((rc = stageBegin(3))) return rc;
-      k_pt_sort_count<<<sortGrid, HC_SORT_BLOCK, sortKeys*sizeof(int), q.s>>>(scn, counts + depth, hits,
+      k_pt_sort_count<<<sortGrid, HC_SORT_BLOCK, sortKeys*sizeof(int), q.s>>>(scn, counts + depth, in.d,
                         (unsigned short*)p->sortKeys.ptr, (int*)p->sortCount.ptr, sortKeys);
       k_pt_sort_scan<<<1, 1024, 0, q.s>>>((int*)p->sortCount.ptr, (int*)p->sortCursor.ptr, sortKeys);
       k_pt_sort_scatter<<<(n + HC_SORT_BLOCK - 1)/HC_SORT_BLOCK, HC_SORT_BLOCK, 0, q.s>>>(counts + depth, (const unsigned short*)p->sortKeys.ptr,
@@ -893,12 +896,12 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
     if (p->haveNormalMaps)
     {
       HC_STAGE(2, (k_pt_shade<true><<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, q.s>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
-                   hits, vis, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
+                   qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
     }
     else
     {
       HC_STAGE(2, (k_pt_shade<false><<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, q.s>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
-                   hits, vis, qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
+                   qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
     }
     HC_CUDA(cudaGetLastError());
     ctx->stats.kernelLaunches++;
