@@ -90,6 +90,15 @@ class ClockSampler:
         return out
 
 
+_T0 = time.time()
+
+
+def _log(msg):
+    """progress marker on stderr (all ranks), so that a stuck multi-GPU run shows where it stopped"""
+    sys.stderr.write("[bench %6.1fs rank %s] %s\n" % (time.time() - _T0, os.environ.get("RANK", "0"), msg))
+    sys.stderr.flush()
+
+
 def _dist():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -267,6 +276,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
+    _log("process group up, building the C2 scene")
     scn = S.scene_c2(WIDTH, HEIGHT)
     lay = hc.CudaLayer(device=local)
     lay.LoadScene(scn)
@@ -274,7 +284,9 @@ def run_ours(args):
     light = S.C2_LIGHT_POS
     if world > 1:
         lay.SetTiles(TILE, rank, world)              # this rank's interleaved 32x32 tiles of the ONE frame
+        _log("scene loaded, joining the library's communicator")
         MG.join_communicator(lay, dist, dev)         # NCCL communicator inside the library (unique id carried by torch.distributed)
+        _log("communicator joined")
 
     # device-resident result buffers owned by torch and pinned host mirrors for e2e (complete on rank 0)
     hits_d = torch.zeros(n*4, dtype=torch.int32, device=dev)
@@ -296,6 +308,7 @@ def run_ours(args):
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
+    _log("warm-up steps done")
     # untimed pre-roll of the same step (>= 0.4 s): nvidia-smi needs ~0.1 s to come up and a 20-step timed region lasts only tens of ms;
     # clock samples are kept from here to the end of the timed region, i.e. only while the GPU runs this workload
     t_load = time.time()
@@ -310,6 +323,7 @@ def run_ours(args):
         ms.append(step_device())            # device time of this step's launches (+ gather), CUDA events on the launching stream
     barrier()
     clocks = sampler.stop(t_load, time.time())
+    _log("timed steps done")
     stats = lay.GetRaysStat()
     n_hit = int((hits_d.view(-1, 4)[:, 1] >= 0).sum().item())       # rank 0 holds the whole frame
     t_step = float(np.sum(ms))/1e3
@@ -360,6 +374,7 @@ def run_ours(args):
     from tests import layerapi
     if layerapi.CppLayer.available():
         consts = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_consts.json")))
+        _log("e2e: loading the scene through the C++ IHWLayer")
         cpp = layerapi.CppLayer(WIDTH, HEIGHT, 0, local)
         layerapi.load_scene_like_render_driver(cpp, scn, consts)
         varsI, varsF, flags = cpp.GetAllFlagsAndVars()
@@ -378,9 +393,11 @@ def run_ours(args):
             cpp.PrepareEngineGlobalsAndTables()      # RenderDriverRTE::Draw re-assembles and re-uploads the globals before every pass
             cpp.TracingPasses(1)                     # BeginTracingPass + EndTracingPass
 
+        _log("e2e: layer ready")
         for _ in range(3):
             step_e2e()
         barrier()
+        _log("e2e: warm-up done")
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step_e2e()
@@ -418,6 +435,7 @@ def run_ours(args):
                  lambda: S.scene_c3(3840, 2160), (0, 1000, 3840, 1256))):
             if args.profile and key != "c3":
                 continue                               # profiler runs: the C2 steps and the C3 passes only (keeps the ncu launch list short and stable)
+            _log("extras: building " + key)
             scn3 = build()
             lay = hc.CudaLayer(device=local)
             lay.LoadScene(scn3)
@@ -428,7 +446,9 @@ def run_ours(args):
                 MG.join_communicator(lay, dist, dev)
             lay.InitPathTracing(777)
             lay.TracingPass(integ, 2)                  # warm-up passes
+            _log("extras: " + key + " warm-up passes done, first reduce")
             lay.ReduceFramebuffer(0, mode)             # warm-up of the exchange (NCCL connects lazily)
+            _log("extras: " + key + " reduce done")
             lay.ResetPerfCounters()
             barrier()
             passes = 64 if key == "c1" else 4
