@@ -570,6 +570,20 @@ def _emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def _watchdog(limit_s):
+    """A multi-GPU run that is stuck (a rank died, a collective never completes) must not hang the caller for ever: after limit_s seconds the
+    process prints where it was and exits with status 3.  Never triggers on a healthy run (N = 8 takes about a minute)."""
+    import threading
+
+    def fire():
+        _log("watchdog: no JSON line after %d s - giving up" % limit_s)
+        os._exit(3)
+    t = threading.Timer(limit_s, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -584,6 +598,8 @@ def main():
     ap.add_argument("--profile", action="store_true", help="profiling run (ncu): no clock pre-roll, no CPU baseline")
     ap.add_argument("--no-c3", action="store_true", help="skip the C1 / C3 / C4 / C5 (path tracing) sections")
     args = ap.parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        _watchdog(900)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -146,12 +146,85 @@ template<class T> int GatherOwned(hc_ctx* ctx, T* buf, int dstRank, HcDevBuf& st
 }
 }
 
-// ray-casting results of a tile-partitioned pass (hc_raycast_pass): hit records and visibility bytes of the owned pixels -> destination rank
+// hit records (16 B) and visibility bytes of a rank's pixels packed into ONE message: [n x 16 B][n x 1 B]
+__global__ void k_rc_pack(const float4* __restrict__ hits, const unsigned char* __restrict__ vis, const int* __restrict__ pixels, const int n,
+                          float4* __restrict__ outHits, unsigned char* __restrict__ outVis)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) { const int p = pixels[i]; outHits[i] = hits[p]; outVis[i] = vis[p]; }
+}
+// destination: segment g of the staging buffer starts at byte segOff[g] and holds cnt[g] hit records followed by cnt[g] bytes
+__global__ void k_rc_unpack(float4* __restrict__ hits, unsigned char* __restrict__ vis, const int* __restrict__ pixels, const int total,
+                            const unsigned char* __restrict__ stage, const long long* __restrict__ segOff, const int* __restrict__ segFirst, const int nSeg)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int g = 0;
+  while (g + 1 < nSeg && i >= segFirst[g + 1]) g++;
+  const int k = i - segFirst[g], cnt = ((g + 1 < nSeg) ? segFirst[g + 1] : total) - segFirst[g];
+  const unsigned char* seg = stage + segOff[g];
+  const int p = pixels[i];
+  hits[p] = reinterpret_cast<const float4*>(seg)[k];
+  vis[p] = seg[size_t(cnt)*16 + k];
+}
+
+// ray-casting results of a tile-partitioned pass (hc_raycast_pass): hit records and visibility bytes of the owned pixels -> destination rank,
+// one message per source rank (17 bytes per pixel), received in one NCCL group
 int hc_comm_gather_raycast(hc_ctx* ctx, void* hits16, unsigned char* vis, int dstRank)
 {
   if (!ctx->comm || ctx->commSize == 1) return HC_OK;
-  int rc = GatherOwned<float4>(ctx, (float4*)hits16, dstRank, ctx->commStage); if (rc) return rc;
-  return GatherOwned<unsigned char>(ctx, vis, dstRank, ctx->commStage2);
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  cudaStream_t s = ctx->stream;
+  const int G = ctx->commSize;
+  int rc = EnsurePixelLists(ctx, dstRank); if (rc) return rc;
+  if (ctx->commRank != dstRank)
+  {
+    const int n = ctx->commCount[0];
+    const size_t bytes = ((size_t(n)*17 + 15)/16)*16;
+    rc = hc_buf_reserve(ctx, ctx->commStage, std::max<size_t>(bytes, 16)); if (rc) return rc;
+    if (n > 0)
+    {
+      k_rc_pack<<<(n + 255)/256, 256, 0, s>>>((const float4*)hits16, vis, (const int*)ctx->commPixels.ptr, n, (float4*)ctx->commStage.ptr, (unsigned char*)ctx->commStage.ptr + size_t(n)*16);
+      HC_CUDA(cudaGetLastError());
+      ctx->stats.kernelLaunches++;
+      HC_NCCL(g_nccl.Send(ctx->commStage.ptr, bytes, 1 /* ncclUint8 */, dstRank, comm, s), "ncclSend");
+    }
+    return HC_OK;
+  }
+  // destination: segment table (host side is tiny: G entries), one receive per source rank
+  std::vector<long long> segOff; std::vector<int> segFirst; std::vector<int> src;
+  size_t off = 0; int first = 0;
+  for (int g = 0; g < G; g++)
+  {
+    const int n = ctx->commCount[g];
+    if (g == dstRank || n == 0) continue;
+    segOff.push_back((long long)off); segFirst.push_back(first); src.push_back(g);
+    off += ((size_t(n)*17 + 15)/16)*16; first += n;
+  }
+  if (src.empty()) return HC_OK;
+  rc = hc_buf_reserve(ctx, ctx->commStage, std::max<size_t>(off, 16)); if (rc) return rc;
+  rc = hc_buf_reserve(ctx, ctx->commStage2, 64*12 + 64); if (rc) return rc;
+  HC_REQUIRE(src.size() <= 64, HC_E_RANGE, "hc_raycast_pass: more than 64 source ranks");
+  long long* dOff = (long long*)ctx->commStage2.ptr; int* dFirst = (int*)((char*)ctx->commStage2.ptr + 64*8);
+  if (ctx->commSegKey != ctx->commPixelsKey)
+  {
+    HC_CUDA(cudaMemcpyAsync(dOff, segOff.data(), segOff.size()*8, cudaMemcpyHostToDevice, s));
+    HC_CUDA(cudaMemcpyAsync(dFirst, segFirst.data(), segFirst.size()*4, cudaMemcpyHostToDevice, s));
+    HC_CUDA(cudaStreamSynchronize(s));               // the vectors are locals
+    ctx->commSegKey = ctx->commPixelsKey;
+  }
+  HC_NCCL(g_nccl.GroupStart(), "ncclGroupStart");
+  for (size_t k = 0; k < src.size(); k++)
+  {
+    const size_t bytes = ((size_t(ctx->commCount[src[k]])*17 + 15)/16)*16;
+    const int e = g_nccl.Recv((unsigned char*)ctx->commStage.ptr + segOff[k], bytes, 1 /* ncclUint8 */, src[k], comm, s);
+    if (e != ncclSuccess) { g_nccl.GroupEnd(); return NcclFail(e, "ncclRecv"); }
+  }
+  HC_NCCL(g_nccl.GroupEnd(), "ncclGroupEnd");
+  k_rc_unpack<<<(first + 255)/256, 256, 0, s>>>((float4*)hits16, vis, (const int*)ctx->commPixels.ptr, first, (const unsigned char*)ctx->commStage.ptr, dOff, dFirst, (int)src.size());
+  HC_CUDA(cudaGetLastError());
+  ctx->stats.kernelLaunches++;
+  return HC_OK;
 }
 
 void hc_comm_free(hc_ctx* ctx)

@@ -79,6 +79,7 @@ struct hc_ctx
   HcDevBuf commStage, commStage2, commPixels;          // dense staging of owned pixels; pixel lists (mine, or every source rank's on the destination)
   std::vector<int> commCount;              // pixels per source rank
   long long commPixelsKey = -1;            // (W, H, tile, G) the lists were built for
+  long long commSegKey = -2;               // ... and the destination's segment table of the ray-casting gather
   HcDevBuf fbCombined;                     // destination rank, full-size sums (sample partition): sum over ranks, separate from fbSum
   bool     combinedValid = false;
   HcDevBuf fbOut;                          // read-back staging: normalised float4 image

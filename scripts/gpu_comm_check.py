@@ -31,6 +31,23 @@ ver = __import__("ctypes").c_int()
 hc.load().hc_comm_version(__import__("ctypes").byref(ver))
 out["nccl_version"] = ver.value
 
+# ---- ray casting: one frame split in tiles, records gathered on rank 0 (hc_raycast_pass + hc_comm_gather_raycast) == the frame of one GPU
+from hydracore_b200._lib import HC_HOST  # noqa: E402
+lay.SetTiles(32, rank, world)
+nn = scn.width*scn.height
+hits = np.zeros(nn, dtype=[("t", np.float32), ("primId", np.int32), ("instId", np.int32), ("geomId", np.int32)])
+vis = np.zeros(nn, np.uint8)
+for _ in range(2):
+    lay.RaycastPass((0.0, 3.0, 0.0), hits.ctypes.data, vis.ctypes.data, HC_HOST)
+if rank == 0:
+    solo = hc.CudaLayer(device=local)
+    solo.LoadScene(scn)
+    h1, v1 = np.zeros_like(hits), np.zeros_like(vis)
+    solo.RaycastPass((0.0, 3.0, 0.0), h1.ctypes.data, v1.ctypes.data, HC_HOST)
+    out["raycast_split_equals_single_gpu"] = bool(hits.tobytes() == h1.tobytes() and np.array_equal(vis, v1))
+    out["raycast_hit_fraction"] = float((h1["primId"] >= 0).mean())
+    solo.close()
+
 # ---- tile partition, MISPT
 lay.SetTiles(32, rank, world)
 lay.InitPathTracing(777)
@@ -77,7 +94,7 @@ if rank == 0:
     out["qmc_repeat_equal"] = bool(np.array_equal(q1, q2))
     out["qmc_reduce_ms"] = msq
     solo.close()
-    ok = out["tiles_equal_after_2_passes"] and out["tiles_equal_after_3_passes_and_repeated_reduce"] and out["hdr_equal"] and out["qmc_repeat_equal"] and out["qmc_rel_rmse_vs_single_gpu"] < 1e-3
+    ok = out["raycast_split_equals_single_gpu"] and out["tiles_equal_after_2_passes"] and out["tiles_equal_after_3_passes_and_repeated_reduce"] and out["hdr_equal"] and out["qmc_repeat_equal"] and out["qmc_rel_rmse_vs_single_gpu"] < 1e-3
     out["ok"] = bool(ok)
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
