@@ -122,7 +122,7 @@ k_trace(const HcBvh bvh, const float4* __restrict__ rpos, const float4* __restri
         }
         if (RAYGEN != 0 && gen.pixels) idx = (unsigned)gen.pixels[idx];             // results are stored per PIXEL (the gather to the destination rank packs them again)
         rayIdx = idx; idle = false;
-        TravStart(r, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT);
+        TravStart(r, f3(p), f3(dd), ANYHIT ? dd.w : HC_MAXFLOAT, bvh.singleLevel);
         if (TREE1 != 0 && !ANYHIT)
         {
           const float4 h = reinterpret_cast<const float4*>(hitsOut)[size_t(idx)*outStride];      // Lite_Hit carried from tree to tree
@@ -236,9 +236,8 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
   if (n <= 0) return HC_OK;
   if (!stream) stream = ctx->stream;
   HC_REQUIRE(ctx->bvhNodes.ptr && ctx->bvhTris.ptr, HC_E_STATE, "hc_trace: no BVH uploaded (hc_set_bvh)");
-  HC_REQUIRE(ctx->haveInst != 0, HC_E_STATE, "hc_trace: only the two-level (instanced) layout is supported");
   HC_REQUIRE(n < 0xffff0000ll, HC_E_ARG, "hc_trace: more than 2^32 rays in one launch");
-  HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr;
+  HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr; bvh.singleLevel = ctx->haveInst ? 0 : 1;
   unsigned* counter = nullptr;
   int rc = NextCounter(ctx, stream, &counter); if (rc) return rc;
   const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
@@ -254,7 +253,7 @@ static int LaunchTrace(hc_ctx* ctx, bool anyHit, const float4* rpos, const float
     // OpenCL layer walks every tree with the opacity test (GPUOCLKernels.cpp:959-1000, BVH4InstTraverseShadowAlphaS ctrace.h:1748).
     // hc_pt_set_shadow_trees chooses: 1 (default) = every tree, a cut-out occludes where its opacity texel passes the closest-hit test
     // (binary; the smooth-opacity and skip-shadow flags of the OpenCL path are not in the alpha words); 0 = first tree only (oracle parity)
-    HcBvh b1; b1.nodes = (const float4*)ctx->bvh1Nodes.ptr; b1.tris = (const float4*)ctx->bvh1Tris.ptr;
+    HcBvh b1; b1.nodes = (const float4*)ctx->bvh1Nodes.ptr; b1.tris = (const float4*)ctx->bvh1Tris.ptr; b1.singleLevel = ctx->haveInst1 ? 0 : 1;
     unsigned* counter1 = nullptr;
     rc = NextCounter(ctx, stream, &counter1); if (rc) return rc;
     if (ctx->haveAlpha1)
@@ -281,7 +280,7 @@ static int LaunchTraceGen(hc_ctx* ctx, bool shadow, long long n, HcHit* hitsLoca
 {
   if (n <= 0) return HC_OK;
   cudaStream_t stream = ctx->stream;
-  HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr;
+  HcBvh bvh; bvh.nodes = (const float4*)ctx->bvhNodes.ptr; bvh.tris = (const float4*)ctx->bvhTris.ptr; bvh.singleLevel = ctx->haveInst ? 0 : 1;
   unsigned* counter = nullptr;
   int rc = NextCounter(ctx, stream, &counter); if (rc) return rc;
   const int grid = (int)std::min<long long>(TraceGrid(ctx), (n + HC_TRACE_BLOCK - 1)/HC_TRACE_BLOCK);
@@ -305,7 +304,7 @@ static int LaunchTraceGen(hc_ctx* ctx, bool shadow, long long n, HcHit* hitsLoca
 //                     determinant is 0 -> v = u = t = NaN -> every acceptance test fails.
 static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const float* trif4, int trif4Num,
                                std::vector<float>& outNodes, std::vector<float>& outPairs, int* outStackBound,
-                               const unsigned* alphaU2 = nullptr, int alphaNum = 0, std::vector<unsigned>* outAlphaPairs = nullptr)
+                               const unsigned* alphaU2 = nullptr, int alphaNum = 0, std::vector<unsigned>* outAlphaPairs = nullptr, bool singleLevel = false)
 {
   struct N { float bmin[3]; unsigned lo; float bmax[3]; unsigned esc; };
   const N* nd = (const N*)nodes;
@@ -352,14 +351,15 @@ static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const f
       R[12 + s] = e2[0]; R[14 + s] = e2[1]; R[16 + s] = e2[2];
       memcpy(&R[18 + s], &A[3], 4);            // primId
       memcpy(&R[20 + s], &B[3], 4);            // geomId
+      memcpy(&R[22 + s], &C[3], 4);            // instId (single-level trees, IntersectAllPrimitivesInLeaf1 ctrace.h:101; -1 in the two-level layout)
     }
-    if (count & 1) { float* R = P + size_t(count/2)*HC_PAIR_F4*4; const int m1 = -1; memcpy(&R[19], &m1, 4); memcpy(&R[21], &m1, 4); }
+    if (count & 1) { float* R = P + size_t(count/2)*HC_PAIR_F4*4; const int m1 = -1; memcpy(&R[19], &m1, 4); memcpy(&R[21], &m1, 4); memcpy(&R[23], &m1, 4); }
     *word = leafWord[off] = HC_LEAF_BIT | (unsigned(pairs - 1) << HC_LEAF_PAIRS_SHIFT) | unsigned(index);
     return HC_OK;
   };
 
   struct It { unsigned quad; int depth; bool inst; };
-  std::vector<It> st; st.push_back({ 1u, 1, false });
+  std::vector<It> st; st.push_back({ 1u, 1, singleLevel });       // single-level trees (no instance records): the tree at quad 1 is a mesh tree
   std::vector<unsigned char> seen(size_t(quads), 0);
   int maxTop = 0, maxMesh = 0;
   while (!st.empty())
@@ -404,7 +404,7 @@ static int ConvertBvhForDevice(const unsigned char* nodes, int nodesNum, const f
     }
     memcpy(Q + 24, words, 16);
   }
-  *outStackBound = 3*(maxTop + maxMesh) + 2;
+  *outStackBound = 3*(maxTop + maxMesh) + 2;      // single-level trees: maxMesh only (maxTop stays 0)
   return HC_OK;
 }
 
@@ -552,14 +552,13 @@ static int SetBvhTree(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, 
   if (!ctx || !nodes || !trif4 || nodesNum < 8 || trif4Num < 4) return HC_E_ARG;
   HC_REQUIRE(treeId == 0 || treeId == 1, HC_E_ARG, "hc_set_bvh: tree 0 (opaque geometry) and tree 1 (meshes with opacity maps) are supported");
   HC_REQUIRE(treeId == 1 || alphaTable == nullptr, HC_E_ARG, "hc_set_bvh: an alpha table on tree 0 is not supported (the driver puts opacity meshes into tree 1)");
-  HC_REQUIRE(haveInst != 0, HC_E_ARG, "hc_set_bvh: single-level trees (bvhType \"triangle4v\") are not supported, pass the two-level layout");
   HC_REQUIRE(alphaTable == nullptr || alphaNum >= trif4Num, HC_E_ARG, "hc_set_bvh_alpha: the alpha table must cover every float4 of the triangle list");
   int bound = 0;
   ctx->sceneDirty = true;
   std::vector<float> devNodes, devPairs;
   std::vector<unsigned> devAlpha;
   int rc = ConvertBvhForDevice((const unsigned char*)nodes, nodesNum, (const float*)trif4, trif4Num, devNodes, devPairs, &bound,
-                               (const unsigned*)alphaTable, alphaNum, alphaTable ? &devAlpha : nullptr);
+                               (const unsigned*)alphaTable, alphaNum, alphaTable ? &devAlpha : nullptr, haveInst == 0);
   HC_REQUIRE(rc == HC_OK, rc, "hc_set_bvh: tree references nodes or triangles out of range (or a leaf holds more than 128 triangles)");
   HC_REQUIRE(bound <= HC_STACK_CAP, HC_E_RANGE, "hc_set_bvh: tree too deep for the traversal stack");
   HC_CUDA(cudaSetDevice(ctx->device));
@@ -595,7 +594,7 @@ static int SetBvhTree(hc_ctx* ctx, int treeId, const void* nodes, int nodesNum, 
   HC_CUDA(cudaStreamSynchronize(ctx->stream));                // ConvertionResult pointers die at ConvertUnmap (RenderDriverRTE.cpp:1436)
   if (treeId == 0) ctx->alphaTexIdsHost.clear();
   if (treeId == 0) { ctx->nodesNum = nodesNum; ctx->trif4Num = trif4Num; ctx->haveInst = haveInst; ctx->bvhDepthBound = bound; ctx->haveTree1 = false; ctx->haveAlpha1 = false; }
-  else ctx->haveTree1 = true;
+  else { ctx->haveTree1 = true; ctx->haveInst1 = haveInst; }
   return HC_OK;
 }
 
@@ -771,7 +770,7 @@ int hc_raycast_pass(hc_ctx* ctx, const float lightPos[3], hc_hit* hitsOutOrNull,
 
   // eye rays and shadow rays are generated inside the traversal kernels' ray fetch (no ray buffers, two launches fewer) unless a second BVH
   // tree has to be walked with the same rays
-  const bool fused = !ctx->haveTree1 && ctx->bvhNodes.ptr && ctx->bvhTris.ptr && ctx->haveInst != 0 && getenv("HC_RAYCAST_UNFUSED") == nullptr;
+  const bool fused = !ctx->haveTree1 && ctx->bvhNodes.ptr && ctx->bvhTris.ptr && getenv("HC_RAYCAST_UNFUSED") == nullptr;
   HcRayGen gen; gen.cam = cam; gen.width = ctx->width; gen.height = ctx->height; gen.firstPixel = 0;
   gen.light = make_float3(lightPos[0], lightPos[1], lightPos[2]); gen.hitsIn = hits;
   // Multi-GPU: with a tile partition (hc_pt_set_tiles, world size > 1) this rank casts the rays of ITS pixels only; with a communicator

@@ -47,7 +47,7 @@ struct hc_ctx
   int      remapListsSize = 0, remapTableSize = 0, remapInstSize = 0;
   std::vector<int> remapListsHost;              // host copy for validation at hc_pt_init (every 'to' id must exist in the materials table)
   std::vector<int> alphaTexIdsHost;             // texture ids used by the opacity samplers of tree 1, validated against the texture table
-  int      nodesNum = 0, trif4Num = 0, haveInst = 1, bvhDepthBound = 0;
+  int      nodesNum = 0, trif4Num = 0, haveInst = 1, haveInst1 = 1, bvhDepthBound = 0;     // haveInst = 0: single-level tree (bvhType "triangle4v")
   HcDevBuf instMatrices, instLightIds;
   int      numInst = 0;
 

@@ -56,7 +56,10 @@ struct HcBvh
   const uint2*  __restrict__ alphaTable    = nullptr;
   const int4*   __restrict__ textures      = nullptr;
   const int*    __restrict__ texturesTable = nullptr;   // EngineGlobals texture table: id -> float4 offset of the image header
+  int singleLevel = 0;                                   // 1: no instance level (bvhType "triangle4v", BVH4Traverse ctrace.h:669-838): the leaves of the tree that
+                                                         // starts at quad 1 hold world-space triangles, each with its own instance id
 };
+#define HC_INST_SINGLE 0x7ffffffe                        // HcRayTrav::instId of a ray in a single-level tree: "inside" from the start, never left
 
 HC_DEV float3 SafeInverse(float3 d)
 {
@@ -135,11 +138,11 @@ HC_DEV void SetNearRows(HcRayTrav& r)
   r.nearZ = (r.inv.z < 0.0f) ? 80u : 64u;
 }
 
-HC_DEV void TravStart(HcRayTrav& r, float3 o, float3 d, float tFar)
+HC_DEV void TravStart(HcRayTrav& r, float3 o, float3 d, float tFar, int singleLevel = 0)
 {
   r.o = o; r.d = d; r.inv = SafeInverse(d); SetNearRows(r);
   r.t = tFar; r.primId = -1; r.hitInst = -1; r.geomId = int(0xC0000000u);      // Make_Lite_Hit(t, -1), cglobals.h:1258-1266
-  r.instId = -1; r.sp = 0; r.instTop = 0; r.node = 1u;
+  r.instId = singleLevel ? HC_INST_SINGLE : -1; r.sp = 0; r.instTop = 0; r.node = 1u;
 }
 
 // entry key of one child: tmin when (tmin <= tmax) && (tmax >= 0) && (tmin <= tHit), else MAXFLOAT (RayBoxIntersectionLite2 + the visit
@@ -265,12 +268,12 @@ HC_DEV bool PairTest(HcRayTrav& r, const HcBvh& bvh, const size_t pairIndex)
   upk2(mul2(dot2_xnynz(E2, qvecN), invDet), t0, t1);
   if (v0 > -HC_TRI_EPS && u0 > -HC_TRI_EPS && (u0 + v0 < 1.0f + HC_TRI_EPS) && t0 > 0.0f && t0 < r.t && (!ALPHA || AlphaPass(bvh, __ldg(bvh.alphaPairs + 2*pairIndex), u0, v0)))
   {
-    r.t = t0; r.primId = __float_as_int(R2.a.z); r.geomId = __float_as_int(R2.b.x); r.hitInst = r.instId; found = true;
+    r.t = t0; r.primId = __float_as_int(R2.a.z); r.geomId = __float_as_int(R2.b.x); r.hitInst = (r.instId == HC_INST_SINGLE) ? __float_as_int(R2.b.z) : r.instId; found = true;
   }
   if (v1 > -HC_TRI_EPS && u1 > -HC_TRI_EPS && (u1 + v1 < 1.0f + HC_TRI_EPS) && t1 > 0.0f && t1 < r.t     // sequential, like the reference loop
       && (!ALPHA || AlphaPass(bvh, __ldg(bvh.alphaPairs + 2*pairIndex + 1), u1, v1)))
   {
-    r.t = t1; r.primId = __float_as_int(R2.a.w); r.geomId = __float_as_int(R2.b.y); r.hitInst = r.instId; found = true;
+    r.t = t1; r.primId = __float_as_int(R2.a.w); r.geomId = __float_as_int(R2.b.y); r.hitInst = (r.instId == HC_INST_SINGLE) ? __float_as_int(R2.b.w) : r.instId; found = true;
   }
   return found;
 }

@@ -212,3 +212,47 @@ def test_hdr_read_back_is_normalised_on_the_device(layer):
     layer.TracingPass(MISPT, 3)
     s, h = layer.GetSumImage(), layer.GetHDRImage()
     assert np.array_equal(h, s*np.float32(1.0/3.0))
+
+
+def test_single_level_tree_vs_reference(layer, ref):
+    """bvhType "triangle4v": no instance level, world-space triangles that carry their own instance id (BVH4Traverse, ctrace.h:669-838, leaf test
+    IntersectAllPrimitivesInLeaf1 :63-122).  The tree is made from the mesh sub-tree of a one-instance scene: its root quad copied to quad 1
+    (child offsets are absolute quad indices), an instance id written into every triangle's third vertex."""
+    from hydracore_b200 import scene as S
+    from tests import scenes
+    scn = S.scene_c2(320, 180)
+    nodes = np.ascontiguousarray(scn.bvh["nodes"], np.float32).copy().reshape(-1, 8)
+    tris = np.ascontiguousarray(scn.bvh["tris"], np.float32).copy().reshape(-1, 4)
+    un = nodes.view(np.uint32)
+    top = un[4:8]                                        # quad 1: the top level over the single instance
+    leaf = [c for c in range(4) if not (top[c, 3] == 0xFFFFFFFF and top[c, 7] == 0xFFFFFFFF)]
+    assert len(leaf) == 1 and (top[leaf[0], 3] & 0x80000000)
+    rec = int(top[leaf[0], 3] & 0x7FFFFFFF)              # instance record quad; its node 0 points at the mesh sub-tree
+    sub = int(un[4*rec, 3])
+    assert not (sub & 0x80000000)
+    nodes[4:8] = nodes[4*sub:4*sub + 4]
+    ti = tris.view(np.int32)
+    hdr = np.nonzero((ti[:, 2] == -1) & (ti[:, 3] == -1) & (ti[:, 1] > 0) & (ti[:, 1] < 64))[0]          # leaf headers {first, count, -1, -1}
+    for h in hdr:
+        first, count = int(ti[h, 0]), int(ti[h, 1])
+        if first == h + 1:
+            ti[first + 2:first + 3*count:3, 3] = 7       # instId in the .w of every triangle's C vertex
+    layer.SetAllBVH4(nodes, tris, have_inst=False)
+    layer.SetAllInstMatrices(scn.bvh["inv_matrices"])
+    layer.ResizeScreen(320, 180)
+    layer.PrepareEngineGlobals(scn.globals_blob)
+    rays = np.concatenate([layer.MakeEyeRays(320, 180, None), scenes.incoherent_rays(40000, 5, radius=25.0)])
+    got = layer.TraceClosest(rays)
+    want = np.zeros(rays.shape[0], got.dtype)
+    ref.L.ref_trace_closest(nodes.ctypes.data_as(__import__("ctypes").c_void_p), tris.ctypes.data_as(__import__("ctypes").c_void_p), 0,
+                            rays.ctypes.data_as(__import__("ctypes").c_void_p), __import__("ctypes").c_longlong(rays.shape[0]), want.ctypes.data_as(__import__("ctypes").c_void_p))
+    hit = want["primId"] >= 0
+    assert hit.mean() > 0.3 and np.all(want["instId"][hit] == 7)
+    exact = (got["primId"] == want["primId"]) & (got["instId"] == want["instId"]) & (got["geomId"] == want["geomId"]) & (got["t"] == want["t"])
+    ties = ~exact & (got["primId"] >= 0) & hit & (np.abs(got["t"] - want["t"]) <= 1e-5*np.abs(want["t"]))
+    assert int((~exact & ~ties).sum()) == 0 and int((~exact).sum()) <= 3
+    sh = rays.copy()
+    sh[:, 7] = 12.0
+    vis = layer.TraceShadow(sh)
+    want_vis = ~(hit & (want["t"] > 0) & (want["t"] < 12.0))
+    assert (vis.astype(bool) != want_vis).sum() <= 2
