@@ -161,8 +161,19 @@ static Box RangeBox(const std::vector<Prim>& P, int32_t first, int32_t count)
   Box b; for (int32_t i = first; i < first + count; i++) b.grow(P[i].box); return b;
 }
 
-// recursive wide build; node slots are reserved up front so that tasks can write without locking
-static void BuildRec(Tree& T, int32_t nodeIdx, int32_t first, int32_t count, int maxLeaf, int depth, std::vector<int>& depthOut)
+// quad levels a balanced (median-split) tree over `count` primitives still needs
+static int LevelsNeeded(int32_t count, int maxLeaf)
+{
+  int levels = 0; long long cap = maxLeaf;
+  while (cap < count) { cap *= 4; levels++; }
+  return levels;
+}
+
+// recursive wide build; node slots are reserved up front so that tasks can write without locking.
+// maxDepth bounds the tree: the traversal stack of the kernels (HC_STACK_CAP = 80 = 3 x (top levels + mesh levels) + 2, hc_api.cu) must hold
+// the worst case, so once the levels left are only just enough for a balanced tree the splits become median splits (an unbalanced SAH tree
+// over long thin geometry could otherwise grow deeper than the stack and the scene would be refused at upload).
+static void BuildRec(Tree& T, int32_t nodeIdx, int32_t first, int32_t count, int maxLeaf, int depth, std::vector<int>& depthOut, int maxDepth)
 {
   BNode& N = T.nodes[nodeIdx];   // NOTE: T.nodes is pre-sized; never reallocates during the build
   N.box = RangeBox(T.prims, first, count);
@@ -177,7 +188,8 @@ static void BuildRec(Tree& T, int32_t nodeIdx, int32_t first, int32_t count, int
       if (parts[i].count > maxLeaf) { const float a = kPick ? parts[i].box.area() : parts[i].box.area()*float(parts[i].count); if (a > bestA) { bestA = a; best = i; } }
     if (best < 0) break;
     const Range r = parts[best];
-    const int32_t L = SplitSAH(T.prims, r.first, r.count);
+    const bool balanced = LevelsNeeded(count, maxLeaf) + 1 >= maxDepth - depth;       // no slack left for uneven splits below this node
+    const int32_t L = balanced ? r.count/2 : SplitSAH(T.prims, r.first, r.count);
     parts[best] = { r.first, L, RangeBox(T.prims, r.first, L) };
     parts[np++] = { r.first + L, r.count - L, RangeBox(T.prims, r.first + L, r.count - L) };
   }
@@ -192,23 +204,23 @@ static void BuildRec(Tree& T, int32_t nodeIdx, int32_t first, int32_t count, int
     const int32_t ci = N.child[i]; const Range r = parts[i];
     if (r.count > 8192)
     {
-      #pragma omp task shared(T, depthOut) firstprivate(ci, r, maxLeaf, depth)
-      BuildRec(T, ci, r.first, r.count, maxLeaf, depth + 1, depthOut);
+      #pragma omp task shared(T, depthOut) firstprivate(ci, r, maxLeaf, depth, maxDepth)
+      BuildRec(T, ci, r.first, r.count, maxLeaf, depth + 1, depthOut, maxDepth);
     }
     else
-      BuildRec(T, ci, r.first, r.count, maxLeaf, depth + 1, depthOut);
+      BuildRec(T, ci, r.first, r.count, maxLeaf, depth + 1, depthOut, maxDepth);
   }
   #pragma omp taskwait
 }
 
-static void BuildTree(Tree& T, int maxLeaf)
+static void BuildTree(Tree& T, int maxLeaf, int maxDepth)
 {
   const int32_t n = int32_t(T.prims.size());
   T.nodes.assign(size_t(std::max(2*n, 2)), BNode());
   std::vector<int> depthOut(T.nodes.size(), 0);
   #pragma omp parallel
   #pragma omp single
-  BuildRec(T, 0, 0, n, maxLeaf, 0, depthOut);
+  BuildRec(T, 0, 0, n, maxLeaf, 0, depthOut, maxDepth);
   T.depth = *std::max_element(depthOut.begin(), depthOut.end());
 }
 
@@ -390,7 +402,7 @@ struct Builder
         M.tree.prims.push_back(p); M.box.grow(p.box);
       }
       if (M.tree.prims.empty()) return HC_E_ARG;
-      BuildTree(M.tree, kMaxLeafEnv);
+      BuildTree(M.tree, kMaxLeafEnv, 17);        // mesh levels 17 + top levels 9 = 26 -> 3 x 26 + 2 = the 80 entries of the traversal stack
       M.built = true;
       meshDepth = std::max(meshDepth, M.tree.depth);
     }
@@ -417,7 +429,7 @@ struct Builder
       top.prims.push_back(p); sceneBox.grow(wb);
       invMatrices.insert(invMatrices.end(), I.inv, I.inv + 16);
     }
-    BuildTree(top, 1);
+    BuildTree(top, 1, 9);
 
     // quad 0 : root record (bvh_access_dll2.cpp:637-644)
     const size_t q0 = Alloc4();

@@ -9,7 +9,11 @@ SURVEY.md 8c, seed 777).
   test_42_ggx      the same with a GGX reflection layer
   test_224_sphere  another teapot, a rect and a SPHERE area light
   test_42_beckmann, test_224_sphere_microfacet   the same two with brdf_type="torranse_sparrow" (Blinn distribution) reflection layers
-  test_42_with_mirror  mirror material (glossiness 1), a black sky-dome "environment" light beside the rect light, "30 30 30" multiplier"""
+  test_42_with_mirror  mirror material (glossiness 1), a black sky-dome "environment" light beside the rect light, "30 30 30" multiplier
+  test_224, test_223_small   eleven materials (Lambert, two Phong), textures, rect area light (test_224: two lights)
+  demo_06          two triangles under a uniform sky light (its environment texture chunk is not in the reference tree: constant colour)
+The other seven libraries of hydra_app/tests (014_Bump_height, Benchmark_Scene03, demo_05, teapot_cylinder, test_aniso, test_aniso2, test_pool) cannot be
+loaded by anybody from this tree: their mesh chunks are listed in the reference's own .MISSING_LARGE_BLOBS."""
 import os
 import sys
 
@@ -22,7 +26,8 @@ from hydracore_b200 import hydra_scene as HS  # noqa: E402
 from tests import refapi  # noqa: E402
 
 REF = os.environ.get("HYDRA_REFERENCE", "/root/reference")
-SCENES = ("test_42", "test_42_ggx", "test_224_sphere", "test_42_beckmann", "test_224_sphere_microfacet", "test_42_with_mirror")
+SCENES = ("test_42", "test_42_ggx", "test_224_sphere", "test_42_beckmann", "test_224_sphere_microfacet", "test_42_with_mirror",
+          "test_224", "test_223_small", "demo_06")
 
 
 def main():

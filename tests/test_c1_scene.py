@@ -16,7 +16,8 @@ def _scene(w, h, name="test_42"):
 
 def test_fixture_describes_test_42(built):
     from hydracore_b200 import hydra_scene as HS
-    assert HS.fixture_scenes(os.path.join(G, "hydra_scenes.npz")) == ["test_224_sphere", "test_224_sphere_microfacet", "test_42", "test_42_beckmann", "test_42_ggx", "test_42_with_mirror"]
+    assert HS.fixture_scenes(os.path.join(G, "hydra_scenes.npz")) == ["demo_06", "test_223_small", "test_224", "test_224_sphere", "test_224_sphere_microfacet", "test_42", "test_42_beckmann",
+                                                                      "test_42_ggx", "test_42_with_mirror"]
     lib = HS.load_fixture(os.path.join(G, "hydra_scenes.npz"), "test_42")
     assert lib["meshes"][0]["idx"].shape == (25600, 3) and lib["meshes"][1]["idx"].shape == (10, 3) and lib["meshes"][5]["idx"].shape == (2, 3)
     assert len(lib["instances"]) == 3 and lib["camera"]["dof"] and abs(lib["camera"]["lens_radius"] - 0.25) < 1e-6
@@ -33,7 +34,8 @@ def test_fixture_describes_test_42(built):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["test_42", "test_42_ggx", "test_224_sphere", "test_42_beckmann", "test_224_sphere_microfacet", "test_42_with_mirror"])
+@pytest.mark.parametrize("name", ["test_42", "test_42_ggx", "test_224_sphere", "test_42_beckmann", "test_224_sphere_microfacet", "test_42_with_mirror",
+                                  "test_224", "test_223_small", "demo_06"])
 def test_reference_scene_libraries_match_reference_integrators(layer, name):
     golden = np.load(os.path.join(G, "hydra_scenes_images.npz"))
     scn = _scene(128, 128, name)
