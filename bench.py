@@ -367,7 +367,7 @@ def run_ours(args):
     mem_peaks = None
     if rank == 0:
         mem_peaks = {"l2_read_gbs": lay.measure_read_bandwidth(48 << 20, 20), "hbm_read_gbs": lay.measure_read_bandwidth(2 << 30, 1),
-                     "how": "hc_measure_read_bandwidth: 128-bit ld.global.cg streaming reads, 148 x 8 CTAs, best of 5 (its ncu record: profiles/r02_l2_microbench_ncu.md)"}
+                     "how": "hc_measure_read_bandwidth: 128-bit ld.global.cg streaming reads, 148 x 8 CTAs, best of 5 (its ncu record: profiles/r02_final_l2_microbench_ncu.md)"}
 
     # ---- e2e through the reference's plugin interface: GPUCUDALayer : IHWLayer (C++), host result buffers
     e2e = None

@@ -56,7 +56,7 @@ for r in rows[2:]:
                                          "warp_instructions": float(d["smsp__inst_executed.sum"])}
     if any_hit == 0 and tree1 == 0 and raygen == 1:
         traffic["k_trace_closest_dram_bytes_per_launch"] = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"]))*1e6
-        traffic["k_trace_closest_ms_under_ncu"] = float(d["gpu__time_duration.sum"])
+        traffic["k_trace_closest_ms_under_ncu"] = float(d["gpu__time_duration.sum"])/1e3
         traffic["issue_active_pct"] = float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"])
         traffic["lsu_wavefronts_pct_of_peak"] = float(d["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"])
         traffic["active_threads_per_warp_instruction"] = float(d["smsp__thread_inst_executed_per_inst_executed.ratio"])
