@@ -423,9 +423,12 @@ def run_ours(args):
     if not args.no_c3:
         lay.close()
         HS = __import__("hydracore_b200.hydra_scene", fromlist=["x"])
+        c1_build = lambda: HS.build_scene(HS.load_fixture(os.path.join(ROOT, "tests", "golden", "hydra_scenes.npz"), "test_42"), 512, 512)
         for key, label, build, window in (
                 ("c1", "C1: hydra_app/tests/test_42 (25,612 triangles, Lambert / Phong blend / emissive, rect area light, DOF), unidirectional PT, 512x512",
-                 lambda: HS.build_scene(HS.load_fixture(os.path.join(ROOT, "tests", "golden", "hydra_scenes.npz"), "test_42"), 512, 512), (0, 0, 512, 512)),
+                 c1_build, (0, 0, 512, 512)),
+                ("c1_streams8", "C1 with 8 sample streams per pixel (hc_pt_set_sample_streams): 8 passes of the 512x512 frame share one wavefront of 2M paths",
+                 c1_build, (0, 0, 512, 512)),
                 ("c3", "C3: MISPT trace_depth 8, Lambert/GGX/glass/blend + 2 area lights, 1,001,116 triangles, 1080p, 32x32 interleaved tiles",
                  lambda: S.scene_c3(WIDTH, HEIGHT), (0, 270, 1920, 810)),
                 ("c4", "C4: MISPT trace_depth 5 on 200 instances x 100,352 triangles = 20,070,400 instanced triangles, 6 materials (material sort on), 1080p, 32x32 interleaved tiles",
@@ -438,20 +441,26 @@ def run_ours(args):
             _log("extras: building " + key)
             scn3 = build()
             lay = hc.CudaLayer(device=local)
+            # sample streams: S generators per pixel, pass p draws from stream p mod S, so a rank that owns 1/G of the tiles keeps up to S passes in
+            # flight as one wavefront.  The image depends on (seed, S) only, so S is the SAME at every N (at N=1 a 1080p pass fills the wavefront alone
+            # and the streams are simply taken in turn).  C1 keeps the single-generator rule its 64 spp parity test is stated on; c1_streams8 shows the other.
+            streams = {"c1": 1, "c5": 1}.get(key, 8)
+            lay.SetSampleStreams(streams)
             lay.LoadScene(scn3)
-            integ = {"c1": 0, "c5": 3}.get(key, 2)     # C1: unidirectional PT (INTEGRATOR_PT = 0); C3 / C4: MISPT (= 2); C5: MISPT-QMC (= 3)
+            integ = {"c1": 0, "c1_streams8": 0, "c5": 3}.get(key, 2)     # C1: unidirectional PT (INTEGRATOR_PT = 0); C3 / C4: MISPT (= 2); C5: MISPT-QMC (= 3)
             mode = 1 if key == "c5" else 0
             lay.SetTiles(TILE, rank, world)
             if world > 1:
                 MG.join_communicator(lay, dist, dev)
             lay.InitPathTracing(777)
-            lay.TracingPass(integ, 2)                  # warm-up passes
+            warm = 8 if streams > 1 else 2
+            lay.TracingPass(integ, warm)               # warm-up passes (one full cycle of the streams)
             _log("extras: " + key + " warm-up passes done, first reduce")
             lay.ReduceFramebuffer(0, mode)             # warm-up of the exchange (NCCL connects lazily)
             _log("extras: " + key + " reduce done")
             lay.ResetPerfCounters()
             barrier()
-            passes = 64 if key == "c1" else 4
+            passes = 64 if key.startswith("c1") else (8 if streams > 1 else 4)
             t0 = time.perf_counter()
             lay.TracingPass(integ, passes)
             t_pass = time.perf_counter() - t0
@@ -468,8 +477,8 @@ def run_ours(args):
                 dist.all_reduce(sm, op=dist.ReduceOp.SUM)
                 dist.all_reduce(mn, op=dist.ReduceOp.MIN)
             mx, sm, mn = mx.tolist(), sm.tolist(), mn.tolist()
-            mean_img = float(lay.GetSumImage()[..., :3].sum()/(scn3.width*scn3.height*3*(passes + 2))) if rank == 0 else 0.0
-            extras[key] = {"workload": label, "passes": passes, "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": (mx[1] + mx[2])/passes,
+            mean_img = float(lay.GetSumImage()[..., :3].sum()/(scn3.width*scn3.height*3*(passes + warm))) if rank == 0 else 0.0
+            extras[key] = {"workload": label, "passes": passes, "sample_streams": streams, "passes_per_wavefront": lay.GroupPasses(), "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": (mx[1] + mx[2])/passes,
                            "ms_per_pass_without_reduce_wall_max": 1e3*mx[10]/passes,
                            "paths_per_s": sm[3]/mx[0], "mrays_per_s": (sm[4] + sm[5])/mx[0]/1e6,
                            "rays_closest_per_pass": sm[4]/passes, "rays_shadow_per_pass": sm[5]/passes,
@@ -483,7 +492,7 @@ def run_ours(args):
             if key == "c5":
                 extras[key]["spp_per_s"] = passes/mx[0]            # one pass of all ranks together = 1 sample per pixel of the 4K frame
                 extras[key]["partition"] = "Sobol sample index i = g (mod G); samples land on arbitrary pixels, so every rank keeps a full-size SUM buffer"
-            if rank == 0 and world == 1 and not args.profile and not args.no_cpu_baseline:
+            if rank == 0 and world == 1 and not args.profile and not args.no_cpu_baseline and key != "c1_streams8":
                 # the reference's own CPU integrator (oracle/_ref: the reference sources compiled in place) on a pixel window of the same scene
                 names = {0: "IntegratorStupidPT", 2: "IntegratorMISPTLoop2", 3: "IntegratorMISPT_QMC"}
                 cb = cpu_baseline_pt(scn3, integ, names[integ], window)

@@ -61,6 +61,8 @@ SIGNATURES = {
     "hc_pt_set_tiles": (_I, [_P, _I, _I, _I]),
     "hc_pt_set_material_sort": (_I, [_P, _I, _I]),
     "hc_pt_set_shadow_trees": (_I, [_P, _I]),
+    "hc_pt_set_sample_streams": (_I, [_P, _I, ct.c_int64]),
+    "hc_pt_group_passes": (_I, [_P, ct.POINTER(ct.c_int)]),
     "hc_pt_pass": (_I, [_P, _I, _I]),
     "hc_fb_clear": (_I, [_P]),
     "hc_fb_device_ptr": (_I, [_P, _PP, ct.POINTER(_I64)]),

@@ -170,7 +170,11 @@ void GPUCUDALayer::BeginTracingPass()
     return;
   }
   if (!m_ptInitialised) InitPathTracing(m_seed);
-  Check(hc_pt_pass(m_ctx, IntegratorFromState(), 1), "BeginTracingPass");
+  // one call = one wavefront: with sample streams (CallNamedFunc("sample_streams")) it carries several passes of the owned pixels, as one
+  // ray block of the OpenCL layer carries more than one sample per pixel of a small frame (MEGABLOCKSIZE, GPUOCLLayer.cpp:103); GetSPP() tells
+  int passes = 1;
+  Check(hc_pt_group_passes(m_ctx, &passes), "BeginTracingPass (hc_pt_group_passes)");
+  Check(hc_pt_pass(m_ctx, IntegratorFromState(), passes), "BeginTracingPass");
 }
 
 void GPUCUDALayer::EndTracingPass()
@@ -277,6 +281,13 @@ void GPUCUDALayer::CallNamedFunc(const char* a_name, const char* a_args)
     int mode = 1;
     if (sscanf(args.c_str(), "%d", &mode) != 1) Check(HC_E_ARG, "CallNamedFunc(shadow_trees): expected 0 | 1");
     Check(hc_pt_set_shadow_trees(m_ctx, mode), "CallNamedFunc(shadow_trees)");
+  }
+  else if (name == "sample_streams")
+  {
+    int streams = 1; long long limit = 0;
+    if (sscanf(args.c_str(), "%d %lld", &streams, &limit) < 1) Check(HC_E_ARG, "CallNamedFunc(sample_streams): expected \"<streams> [maxPathsInFlight]\"");
+    Check(hc_pt_set_sample_streams(m_ctx, streams, limit), "CallNamedFunc(sample_streams)");
+    m_ptInitialised = false;                                  // the generator array changes: the next pass initialises it again
   }
   else if (name == "comm_id")
   {

@@ -58,6 +58,7 @@ public:
   //   CallNamedFunc("raycast_light", "<x> <y> <z>")               ray-casting mode (passes without HRT_UNIFIED_IMAGE_SAMPLING): shadow rays go to this point
   //   CallNamedFunc("raycast_results", "<hitsAddr> <visAddr>")    host buffers the ray-casting pass fills (W*H Lite_Hit records, W*H bytes)
   //   CallNamedFunc("shadow_trees", "0" | "1")                    shadow rays through the alpha-tested tree (1, default: as GPUOCLLayer) or not (0: as CPUExpLayer)
+  //   CallNamedFunc("sample_streams", "<S> [maxPathsInFlight]")  S generators per pixel: one BeginTracingPass then carries up to S passes (hc_pt_set_sample_streams)
   //   CallNamedFunc("comm_id", "") -> CommIdHex()                 rank 0: create the NCCL unique id of a multi-process render
   //   CallNamedFunc("comm", "<rank> <nranks> <256 hex digits>")   join the communicator
   //   CallNamedFunc("reduce", "<dstRank> <mode>")                 combine the framebuffers on dstRank (0 = tile partition, 1 = full-size sum)

@@ -59,19 +59,25 @@ struct HcPassParams
   int isLast;               // last bounce of the pass
   unsigned qmcPass;         // passes done so far (QMC sample index = pass*W*H + i)
   int world, rank;
+  // sample streams (hc_pt_set_sample_streams): S generators per pixel, pass p draws from stream p mod S, so that up to S consecutive passes of
+  // a pixel are independent of each other and can be in flight together as one wavefront (sub-pass = path index / owned pixels)
+  int streams, streamBase;  // S; stream of sub-pass 0 of this wavefront (= first pass index mod S)
+  int groupPasses;          // sub-passes in this wavefront (1: paths add straight into the frame buffer)
+  int nOwned;               // paths per sub-pass
+  unsigned pixMask; int subShift;   // path word = pixel | sub-pass << subShift | specular bit 31
 };
 
 // ------------------------------------------------------------------------------------------------------------------ K1: eye paths
 // PT/MISPT: IntegratorCommon::makeEyeRay (CPUExp_Integrators_Common.cpp:347-359): rndUniform(-1, 1) -> MakeRandEyeRay.
 // QMC     : rndLens with the Niederreiter table (crandom.h:369-391) -> MakeEyeRayFromF4Rnd, pixel = (int)fx, (int)fy.
 __global__ void __launch_bounds__(256)
-k_pt_generate(const HcCamera cam, const HcPassParams pp, const int n, const int* __restrict__ ownedPixels, uint2* __restrict__ pixelRng,
+k_pt_generate(const HcCamera cam, const HcPassParams pp, const int n, const int first, const int* __restrict__ ownedPixels, uint2* __restrict__ pixelRng,
               const int* __restrict__ rmQMC, const unsigned* __restrict__ qmcTable, HcPathState st, int* __restrict__ pathCount)
 {
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i == 0) pathCount[0] = n;
   if (i >= n) return;
-  float3 rpos, rdir; int pixel; unsigned qpos = 0xFFFFFFFFu;
+  float3 rpos, rdir; int pixel; unsigned qpos = 0xFFFFFFFFu, subBits = 0u;
   HcRng g;
   if (pp.integrator == HC_INTEGRATOR_MISPT_QMC)
   {
@@ -96,26 +102,34 @@ k_pt_generate(const HcCamera cam, const HcPassParams pp, const int n, const int*
   }
   else
   {
-    pixel = ownedPixels[i];
-    const uint2 s2 = pixelRng[pixel]; g.x = s2.x; g.y = s2.y;
+    const int gi = first + i;                                       // index in the wavefront (this launch may be one half of it): sub-pass major
+    const int sub = (pp.groupPasses > 1) ? gi / pp.nOwned : 0;
+    pixel = ownedPixels[gi - sub*pp.nOwned];
+    const uint2 s2 = pixelRng[size_t((pp.streamBase + sub) % pp.streams)*size_t(pp.width*pp.height) + pixel]; g.x = s2.x; g.y = s2.y;
+    subBits = (unsigned)sub << pp.subShift;
     const float4 r = rndFloat4_Pseudo(g);
     const float4 offs = make_float4(-1.0f + 2.0f*r.x, -1.0f + 2.0f*r.y, -1.0f + 2.0f*r.z, -1.0f + 2.0f*r.w);   // rndUniform(gen, -1, 1), crandom.h:617-620
     MakeRandEyeRay(pixel % pp.width, pixel / pp.width, pp.width, pp.height, offs, cam, rpos, rdir);
   }
   StorePair(st.a + 2*size_t(i), make_float4(rpos.x, rpos.y, rpos.z, 1.0f),                                   // makeInitialMisData: matSamplePdf = 1
                                 make_float4(rdir.x, rdir.y, rdir.z, __uint_as_float(0u)));                   // flags = 0
-  StorePair(st.b + 2*size_t(i), make_float4(1.0f, 1.0f, 1.0f, __uint_as_float((unsigned)pixel | 0x80000000u)),  // isSpecular = 1
+  StorePair(st.b + 2*size_t(i), make_float4(1.0f, 1.0f, 1.0f, __uint_as_float((unsigned)pixel | subBits | 0x80000000u)),  // isSpecular = 1
                                 make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(qpos)));
   StorePair(st.c + 2*size_t(i), make_float4(0.0f, 0.0f, 0.0f, 0.0f), make_float4(0.0f, 1.0f, 0.0f, 0.0f));     // no pending shadow ray
   st.d[2*size_t(i)] = make_float4(0.0f, 0.0f, __uint_as_float(g.x), __uint_as_float(g.y));
 }
 
 // ------------------------------------------------------------------------------------------------------------------ K3+K4+K5+K6+K7: shade
-HC_DEV void FinishPath(float4* __restrict__ fb, uint2* __restrict__ pixelRng, int rngSlot, int pixel, float3 accum, const HcRng& g)
+HC_DEV void FinishPath(float4* __restrict__ fb, float4* __restrict__ subSums, uint2* __restrict__ pixelRng, size_t rngSlot, size_t subSlot, int pixel, float3 accum, const HcRng& g)
 {
   // K7: per-pixel HDR SUM (the GPU layer keeps sums and divides by spp on read-back, GPUOCLLayer.cpp:1184-1215)
-  float* p = reinterpret_cast<float*>(fb + pixel);
-  atomicAdd(p + 0, accum.x); atomicAdd(p + 1, accum.y); atomicAdd(p + 2, accum.z);
+  if (subSums != nullptr)
+    subSums[subSlot] = make_float4(accum.x, accum.y, accum.z, 0.0f);     // several passes of the pixel in flight: k_fb_fold adds them in pass order
+  else
+  {
+    float* p = reinterpret_cast<float*>(fb + pixel);
+    atomicAdd(p + 0, accum.x); atomicAdd(p + 1, accum.y); atomicAdd(p + 2, accum.z);
+  }
   pixelRng[rngSlot] = make_uint2(g.x, g.y);
 }
 
@@ -123,7 +137,7 @@ template<bool NMAP>
 __global__ void __launch_bounds__(HC_SHADE_BLOCK, HC_SHADE_MINB)
 k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, int* __restrict__ nOut,
            const HcPathState in, HcPathState out,
-           const unsigned* __restrict__ qmcTable, float4* __restrict__ fb, uint2* __restrict__ pixelRng, const int* __restrict__ perm)
+           const unsigned* __restrict__ qmcTable, float4* __restrict__ fb, float4* __restrict__ subSums, uint2* __restrict__ pixelRng, const int* __restrict__ perm)
 {
   const int tid = blockIdx.x*blockDim.x + threadIdx.x;
   const int n = *nIn;
@@ -145,10 +159,13 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
     const float3 rayPos = f3(rp), rayDir = f3(rd);
     const unsigned flags = __float_as_uint(rd.w);
     pixSpec = __float_as_uint(th.w);
-    const int pixel = int(pixSpec & 0x7FFFFFFFu);
+    const int pixel = int(pixSpec & pp.pixMask);
+    const int sub = int((pixSpec & 0x7FFFFFFFu) >> pp.subShift);
     const bool prevSpecular = (pixSpec & 0x80000000u) != 0;
     const float prevPdf = rp.w;
-    const int rngSlot = (pp.integrator == HC_INTEGRATOR_MISPT_QMC) ? int(qpos - pp.qmcPass*(unsigned)(pp.width*pp.height)) : pixel;
+    const size_t frame = size_t(pp.width*pp.height);
+    const size_t rngSlot = (pp.integrator == HC_INTEGRATOR_MISPT_QMC) ? size_t(qpos - pp.qmcPass*(unsigned)(pp.width*pp.height))
+                                                                       : size_t((pp.streamBase + sub) % pp.streams)*frame + size_t(pixel);
     thr = f3(th); accum = f3(ac);
 
     // pending direct light of the previous bounce: accumColor += accumuThoroughput*explicitColor (PT_Loop.cpp:253), shadow in {0,1}
@@ -250,7 +267,7 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
         nPdf = ms.pdf;
         nFlags = FlagsNextBounceLite(flags, ms, s);
         const bool spec = (ms.flags & HC_RAY_EVENT_S) != 0 || (ms.flags & HC_RAY_EVENT_T) != 0;
-        pixSpec = (unsigned)pixel | (spec ? 0x80000000u : 0u);
+        pixSpec = (pixSpec & 0x7FFFFFFFu) | (spec ? 0x80000000u : 0u);
         if (pp.isLast) finished = true;                           // PT: the recursion returns 0 one level deeper; draws are already made
         else alive = true;
       }
@@ -259,7 +276,7 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
     if (finished)
     {
       accum += thr*curr;                                          // kernel_AddLastBouceContrib (PT_Loop.cpp:258-262)
-      FinishPath(fb, pixelRng, rngSlot, pixel, accum, g);
+      FinishPath(fb, subSums, pixelRng, rngSlot, size_t(sub)*frame + size_t(pixel), pixel, accum, g);
     }
   }
 
@@ -388,10 +405,26 @@ __global__ void k_fb_normalize(const float4* __restrict__ fb, float4* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------------ host side
+// several passes of a pixel in flight (sample streams): their path sums were stored per sub-pass; add them to the frame buffer in PASS order,
+// which is the order a pass-after-pass render adds them in (floating-point sums are order-dependent, the image must not depend on the grouping)
+__global__ void k_fb_fold(float4* __restrict__ fb, const float4* __restrict__ subSums, const int* __restrict__ owned, int nOwned, int groupPasses, size_t frame)
+{
+  const int o = blockIdx.x*blockDim.x + threadIdx.x;
+  if (o >= nOwned) return;
+  const int pixel = owned[o];
+  float4 acc = fb[pixel];
+  for (int j = 0; j < groupPasses; j++)
+  {
+    const float4 v = subSums[size_t(j)*frame + size_t(pixel)];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z;
+  }
+  fb[pixel] = acc;
+}
+
 struct HcPathHost
 {
   HcDevBuf state[2][4];       // the two halves of the path queue: arrays A, B, C, D of 32-byte elements
-  HcDevBuf owned, pathCount, ldr;
+  HcDevBuf owned, pathCount, ldr, subSums;
   HcDevBuf sortKeys, sortCount, sortCursor, sortPerm;   // material sort: u16 key per path, 2 x HC_SORT_MAX_KEYS counters, int index per path
   std::vector<unsigned char> materialsHost, globalsHost;
   int64_t capacity = 0;
@@ -408,7 +441,7 @@ void hc_path_free(hc_ctx* ctx)
   HcPathHost* p = PH(ctx);
   if (!p) return;
   for (int b = 0; b < 2; b++) for (int k = 0; k < 4; k++) hc_buf_free(p->state[b][k]);
-  hc_buf_free(p->owned); hc_buf_free(p->pathCount); hc_buf_free(p->ldr);
+  hc_buf_free(p->owned); hc_buf_free(p->pathCount); hc_buf_free(p->ldr); hc_buf_free(p->subSums);
   hc_buf_free(p->sortKeys); hc_buf_free(p->sortCount); hc_buf_free(p->sortCursor); hc_buf_free(p->sortPerm);
   for (cudaEvent_t e : p->evPool) cudaEventDestroy(e);
   delete p;
@@ -746,6 +779,27 @@ int hc_pt_set_tiles(hc_ctx* ctx, int tileSize, int rank, int worldSize)
   return HC_OK;
 }
 
+int hc_pt_set_sample_streams(hc_ctx* ctx, int streams, int64_t maxPathsInFlight)
+{
+  if (!ctx || streams < 1 || streams > 64 || maxPathsInFlight < 0) return HC_E_ARG;
+  ctx->sampleStreams = streams; ctx->maxPathsInFlight = maxPathsInFlight; ctx->ptReady = false;      // the generator array changes: hc_pt_init again
+  return HC_OK;
+}
+
+int hc_pt_group_passes(hc_ctx* ctx, int* outPasses)
+{
+  if (!ctx || !outPasses) return HC_E_ARG;
+  HcPathHost* p = PH(ctx);
+  HC_REQUIRE(ctx->ptReady && p && p->nOwned > 0, HC_E_STATE, "hc_pt_group_passes: call hc_pt_init first");
+  const int64_t frame = int64_t(ctx->width)*ctx->height;
+  // default limit: what a single GPU keeps in flight for this frame anyway, and at least 2M paths (below that a launch is latency-bound)
+  const int64_t cap = ctx->maxPathsInFlight > 0 ? ctx->maxPathsInFlight : std::max<int64_t>(frame, int64_t(1) << 21);
+  int m = int(std::min<int64_t>(ctx->sampleStreams, std::max<int64_t>(1, cap/p->nOwned)));
+  if (frame > (int64_t(1) << 24) || ctx->sampleStreams > 64) m = 1;              // the sub-pass index shares the path's pixel word (7 bits above 24)
+  *outPasses = std::max(1, m);
+  return HC_OK;
+}
+
 int hc_pt_init(hc_ctx* ctx, int seed)
 {
   if (!ctx) return HC_E_ARG;
@@ -754,8 +808,10 @@ int hc_pt_init(hc_ctx* ctx, int seed)
   int rc = RefreshScene(ctx, "hc_pt_init"); if (rc) return rc;
 
   const int n = ctx->width*ctx->height;
-  if ((rc = hc_buf_reserve(ctx, ctx->pixelRng, uint64_t(n)*8))) return rc;
-  k_init_rng<<<(n + 255)/256, 256, 0, ctx->stream>>>((uint2*)ctx->pixelRng.ptr, n, seed);
+  // generator of stream k of pixel p: index k*W*H + p, i.e. stream 0 is the single-stream rule and the further streams continue the numbering
+  const int nGen = n*std::max(1, ctx->sampleStreams);
+  if ((rc = hc_buf_reserve(ctx, ctx->pixelRng, uint64_t(nGen)*8))) return rc;
+  k_init_rng<<<(nGen + 255)/256, 256, 0, ctx->stream>>>((uint2*)ctx->pixelRng.ptr, nGen, seed);
   HC_CUDA(cudaGetLastError());
   unsigned table[HC_QRNG_DIMENSIONS_K][HC_QRNG_RESOLUTION_K];
   BuildQmcTable(table);
@@ -780,15 +836,24 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   ctx->combinedValid = false;                                  // new samples: an earlier cross-rank sum (hc_fb_reduce) is stale
   const bool qmc = (integrator == HC_INTEGRATOR_MISPT_QMC);
   const int W = ctx->width, H = ctx->height;
-  const int n = qmc ? ((W*H - ctx->rank + ctx->worldSize - 1)/ctx->worldSize) : p->nOwned;
-  if (n <= 0) return HC_OK;
+  const int nPerPass = qmc ? ((W*H - ctx->rank + ctx->worldSize - 1)/ctx->worldSize) : p->nOwned;
+  if (nPerPass <= 0) return HC_OK;
+  // sample streams: up to `groupMax` consecutive passes share one wavefront (hc_pt_group_passes)
+  const int S = qmc ? 1 : std::max(1, ctx->sampleStreams);
+  int groupMax = 1; { int rcg = hc_pt_group_passes(ctx, &groupMax); if (rcg) return rcg; }
+  if (qmc) groupMax = 1;
+  groupMax = std::max(1, std::min(groupMax, passes));
+  int n = nPerPass*groupMax;                                    // paths of the wavefront being enqueued (set per group below)
   int rc = ReserveState(ctx, n, qmc); if (rc) return rc;
   p = PH(ctx);
+  if (groupMax > 1 && (rc = hc_buf_reserve(ctx, p->subSums, uint64_t(groupMax)*uint64_t(W)*uint64_t(H)*16))) return rc;
   HcScene scn = MakeScene(ctx);
   if (integrator == HC_INTEGRATOR_PT) scn.gflags |= HC_HRT_STUPID_PT_MODE;          // IntegratorStupidPT::DoPass sets it in g_flags (CPUExp_Integrators.h:326-330)
   const HcCamera cam = hc_camera_from_globals(ctx->globalsHead.data());
   HcPassParams pp;
   pp.integrator = integrator; pp.width = W; pp.height = H; pp.world = ctx->worldSize; pp.rank = ctx->rank;
+  pp.streams = S; pp.streamBase = 0; pp.groupPasses = 1; pp.nOwned = nPerPass; pp.pixMask = 0x7FFFFFFFu; pp.subShift = 31;
+  float4* subSums = nullptr;
   pp.maxDepth = (integrator == HC_INTEGRATOR_PT) ? scn.traceDepth + 1 : scn.traceDepth;     // IntegratorStupidPT::SetMaxDepth adds one (CPUExp_Integrators.h:333)
   HC_REQUIRE(pp.maxDepth >= 1 && pp.maxDepth < 250, HC_E_ARG, "hc_pt_pass: HRT_TRACE_DEPTH out of range");
   int* counts = (int*)p->pathCount.ptr;
@@ -844,7 +909,7 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
     int rc = 0;
     HC_CUDA(cudaMemsetAsync(q.counts, 0, 256*sizeof(int), q.s));
     HcPathState st0 = sliceOf(0, q.first);
-    HC_STAGE(3, (k_pt_generate<<<(q.n + 255)/256, 256, 0, q.s>>>(cam, pp, q.n, (const int*)p->owned.ptr + q.first, (uint2*)ctx->pixelRng.ptr, rmQMC, qtab, st0, q.counts)));
+    HC_STAGE(3, (k_pt_generate<<<(q.n + 255)/256, 256, 0, q.s>>>(cam, pp, q.n, qmc ? 0 : q.first, (const int*)p->owned.ptr, (uint2*)ctx->pixelRng.ptr, rmQMC, qtab, st0, q.counts)));
     HC_CUDA(cudaGetLastError());
     ctx->stats.kernelLaunches++; ctx->stats.paths += (uint64_t)q.n;
     return HC_OK;
@@ -896,22 +961,22 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
     if (p->haveNormalMaps)
     {
       HC_STAGE(2, (k_pt_shade<true><<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, q.s>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
-                   qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
+                   qtab, (float4*)ctx->fbSum.ptr, subSums, (uint2*)ctx->pixelRng.ptr, perm)));
     }
     else
     {
       HC_STAGE(2, (k_pt_shade<false><<<(n + HC_SHADE_BLOCK - 1)/HC_SHADE_BLOCK, HC_SHADE_BLOCK, 0, q.s>>>(scn, pp, counts + depth, counts + depth + 1, in, out,
-                   qtab, (float4*)ctx->fbSum.ptr, (uint2*)ctx->pixelRng.ptr, perm)));
+                   qtab, (float4*)ctx->fbSum.ptr, subSums, (uint2*)ctx->pixelRng.ptr, perm)));
     }
     HC_CUDA(cudaGetLastError());
     ctx->stats.kernelLaunches++;
     return HC_OK;
   };
   static int pipesEnv = -1; if (pipesEnv < 0) { const char* e = getenv("HC_PT_PIPES"); pipesEnv = e ? atoi(e) : 0; }
-  const bool twoPipes = !qmc && sortKeys == 0 && n >= 4096 && (pipesEnv == 2 || (pipesEnv == 0 && n <= 1024*1024));
   auto enqueuePass = [&]() -> int
   {
     int rc = 0;
+    const bool twoPipes = !qmc && sortKeys == 0 && n >= 4096 && (pipesEnv == 2 || (pipesEnv == 0 && n <= 1024*1024));
     Pipe pipes[2]; int np = 1;
     pipes[0] = Pipe{ 0, n, counts, ctx->stream, ctx->copyStream, ctx->evFork, ctx->evJoin };
     if (twoPipes && !timed)
@@ -936,18 +1001,32 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
       HC_CUDA(cudaEventRecord(ctx->evPipeJoin, ctx->stream2));
       HC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evPipeJoin, 0));
     }
+    if (pp.groupPasses > 1)
+    {
+      HC_STAGE(3, (k_fb_fold<<<(nPerPass + 255)/256, 256, 0, ctx->stream>>>((float4*)ctx->fbSum.ptr, subSums, (const int*)p->owned.ptr, nPerPass, pp.groupPasses, size_t(W)*size_t(H))));
+      HC_CUDA(cudaGetLastError());
+      ctx->stats.kernelLaunches++;
+    }
     if (timed) HC_CUDA(cudaEventRecord(ctx->evStage[1], ctx->stream));
     return HC_OK;
   };
   // measured (scripts/gpu_graph_ab.py, ms per pass, graph / direct): C1 512x512 64 passes 0.637 / 0.681, 16 passes 0.659 / 0.690, 4 passes 0.741 / 0.729;
   // C3 1080p 64 passes 6.73 / 6.71, 4 passes 7.07 / 6.78 (capture + instantiate cost about 1 ms): worth it only for long calls
-  const bool useGraph = !qmc && passes >= 32 && getenv("HC_PT_NO_GRAPH") == nullptr;
+  const bool useGraph = !qmc && S == 1 && passes >= 32 && getenv("HC_PT_NO_GRAPH") == nullptr;        // (with streams the stream base is a kernel argument)
   cudaGraphExec_t gexec = nullptr;
   uint64_t launchesPerPass = 0;
-  for (int pass = 0; pass < passes; pass++)
+  int lastGroup = 1;
+  for (int pass = 0; pass < passes; )
   {
+    const int m = std::min(groupMax, passes - pass);
     pp.qmcPass = ctx->passCounter;
-    timed = (pass == passes - 1);
+    pp.streamBase = int(ctx->passCounter % (unsigned)S);
+    pp.groupPasses = m;
+    if (m > 1) { pp.pixMask = 0x00FFFFFFu; pp.subShift = 24; subSums = (float4*)p->subSums.ptr; }
+    else       { pp.pixMask = 0x7FFFFFFFu; pp.subShift = 31; subSums = nullptr; }
+    n = nPerPass*m;
+    lastGroup = m;
+    timed = (pass + m >= passes);
     if (useGraph && !timed)
     {
       if (gexec == nullptr)
@@ -975,14 +1054,16 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
       ctx->stats.kernelLaunches += launchesPerPass; ctx->stats.paths += (uint64_t)n;
     }
     else if ((rc = enqueuePass())) { if (gexec) cudaGraphExecDestroy(gexec); return rc; }
-    ctx->passCounter++;
-    ctx->spp += qmc ? double(n)*ctx->worldSize/double(W*H) : 1.0;
+    ctx->passCounter += (unsigned)m;
+    ctx->spp += qmc ? double(n)*ctx->worldSize/double(W*H) : double(m);
+    pass += m;
   }
   if (gexec) { HC_CUDA(cudaStreamSynchronize(ctx->stream)); cudaGraphExecDestroy(gexec); }
 #undef HC_STAGE
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0.0f; HC_CUDA(cudaEventElapsedTime(&ms, ctx->evStage[0], ctx->evStage[1]));
-  ctx->lastTraceMs = ms;              // device time of the LAST pass
+  ctx->lastTraceMs = ms;              // device time of the LAST wavefront (lastGroup passes)
+  ctx->lastGroupPasses = lastGroup;
   float cls[4] = { 0, 0, 0, 0 };
   for (size_t k = 0; k < p->evClass.size(); k++)
   {
@@ -1003,11 +1084,13 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
     int live[256]; HC_CUDA(cudaMemcpy(live, counts, sizeof(live), cudaMemcpyDeviceToHost));     // live paths per bounce of the last pass
     uint64_t closest = 0, shadow = 0;
     for (int d = 0; d < nBounces && d < 255; d++) { closest += uint64_t(live[d]); if (d > 0 && integrator != HC_INTEGRATOR_PT) shadow += uint64_t(live[d]); }
-    ctx->stats.raysClosest += closest*uint64_t(passes); ctx->stats.raysShadow += shadow*uint64_t(passes);
+    const double scale = double(passes)/double(lastGroup);               // the counts are those of the last wavefront (lastGroup passes)
+    ctx->stats.raysClosest += uint64_t(double(closest)*scale); ctx->stats.raysShadow += uint64_t(double(shadow)*scale);
   }
-  // the per-class times are those of the last pass; scale to all passes of this call
-  ctx->stats.msClosest += cls[0]*float(passes); ctx->stats.msShadow += cls[1]*float(passes);
-  ctx->stats.msShade += cls[2]*float(passes); ctx->stats.msOther += cls[3]*float(passes);
+  // the per-class times are those of the last wavefront; scale to all passes of this call
+  const float tscale = float(passes)/float(lastGroup);
+  ctx->stats.msClosest += cls[0]*tscale; ctx->stats.msShadow += cls[1]*tscale;
+  ctx->stats.msShade += cls[2]*tscale; ctx->stats.msOther += cls[3]*tscale;
   return HC_OK;
 }
 

@@ -218,6 +218,16 @@ class CudaLayer:
     def SetTiles(self, tile, rank, world):
         check(self._L.hc_pt_set_tiles(self._c, int(tile), int(rank), int(world)), "hc_pt_set_tiles")
 
+    def SetSampleStreams(self, streams, max_paths_in_flight=0):
+        """S generators per pixel: pass p draws from stream p mod S, so up to S passes share one wavefront (hc_pt_set_sample_streams).  Call before InitPathTracing."""
+        check(self._L.hc_pt_set_sample_streams(self._c, int(streams), int(max_paths_in_flight)), "hc_pt_set_sample_streams")
+
+    def GroupPasses(self):
+        """Passes one wavefront carries with the current streams / tiles / limit (after InitPathTracing)."""
+        m = ct.c_int(0)
+        check(self._L.hc_pt_group_passes(self._c, ct.byref(m)), "hc_pt_group_passes")
+        return int(m.value)
+
     def SetShadowTrees(self, mode):
         """1 (library default): shadow rays walk every BVH tree, cut-outs occlude (GPUOCLLayer); 0: first tree only (the CPU integrators' shadowTrace)."""
         check(self._L.hc_pt_set_shadow_trees(self._c, int(mode)), "hc_pt_set_shadow_trees")

@@ -119,6 +119,16 @@ int hc_pt_set_shadow_trees(hc_ctx* ctx, int mode);                            /*
                                                                                  cut-out occludes where its opacity texel passes, as GPUOCLLayer does (GPUOCLKernels.cpp:959-1000,
                                                                                  BVH4InstTraverseShadowAlphaS ctrace.h:1748; binary opacity only); 0 = first tree only, as the CPU
                                                                                  integrators do (IntegratorCommon::shadowTrace, CPUExp_Integrators_Common.cpp:163-171)        */
+int hc_pt_set_sample_streams(hc_ctx* ctx, int streams, int64_t maxPathsInFlight);
+                                                                              /* S generators per pixel (1..64, default 1): pass p of a pixel draws from stream p mod S, generator
+                                                                                 index k*W*H + pixel.  Up to S consecutive passes are then independent and hc_pt_pass keeps them in
+                                                                                 flight as ONE wavefront (small frames, or a GPU that owns 1/G of the tiles, no longer run
+                                                                                 latency-bound launches); their sums are added to the frame in pass order, so the image depends on
+                                                                                 (seed, S) only, not on how many passes shared a wavefront, the tile split or the GPU count.
+                                                                                 The OpenCL layer has the same degree of freedom: one RandomGen per slot of its ray block,
+                                                                                 randGenState[MEGABLOCKSIZE] (GPUOCLLayer.cpp:131), whatever the frame size.
+                                                                                 maxPathsInFlight: 0 = max(W*H, 2M).  Call before hc_pt_init.                                 */
+int hc_pt_group_passes(hc_ctx* ctx, int* outPasses);                         /* passes one wavefront carries with the current streams / tiles / limit (after hc_pt_init)    */
 int hc_pt_pass(hc_ctx* ctx, int integrator, int passes);                     /* BeginTracingPass+EndTracingPass, IHWLayer.h:133-134         */
 int hc_fb_clear(hc_ctx* ctx);                                                /* ClearAccumulatedColor, IHWLayer.h:140                       */
 int hc_fb_device_ptr(hc_ctx* ctx, float** outSumRGBA, int64_t* outFloats);   /* per-pixel SUM buffer (for the NCCL reduce over NVLink)      */

@@ -82,16 +82,31 @@ namespace
   struct Det : public Base
   {
     template<class... A> Det(A... a) : Base(a...) {}
-    std::vector<RandomGen> pix;
+    std::vector<RandomGen> pix;      // generators of the stream the current pass draws from
+    std::vector<std::vector<RandomGen>> parked;   // the other streams (sample streams: pass p uses stream p mod S, generator index k*W*H + pixel)
     std::vector<float4>    sum;      // per-pixel SUM of samples (the GPU layer keeps sums too, screen.cl:409-463)
-    int passes = 0;
+    int passes = 0, streams = 1, seed0 = 0;
 
-    void Seed(int seed)
+    void Seed(int seed) { seed0 = seed; SetStreams(1); }
+    void SetStreams(int S)
     {
-      pix.resize(size_t(this->m_width)*this->m_height);
-      for (size_t i = 0; i < pix.size(); i++) pix[i] = RandomGenInit(seed + int(i));
-      sum.assign(pix.size(), float4(0, 0, 0, 0));
+      const size_t n = size_t(this->m_width)*this->m_height;
+      streams = S < 1 ? 1 : S;
+      parked.assign(size_t(streams), std::vector<RandomGen>());
+      for (int k = 0; k < streams; k++)
+      {
+        parked[k].resize(n);
+        for (size_t i = 0; i < n; i++) parked[k][i] = RandomGenInit(seed0 + int(size_t(k)*n + i));
+      }
+      pix.swap(parked[0]);
+      sum.assign(n, float4(0, 0, 0, 0));
       passes = 0;
+    }
+    void NextPass()                  // park the stream of the pass just done, take the one of the next pass
+    {
+      pix.swap(parked[size_t(passes % streams)]);
+      passes++;
+      pix.swap(parked[size_t(passes % streams)]);
     }
 
     // mirrors IntegratorCommon::DoPass (CPUExp_Integrators_Common.cpp:278-316) with the per-pixel generator swapped in
@@ -111,7 +126,7 @@ namespace
           pix[size_t(y)*W + x] = pt.gen;
           sum[size_t(y)*W + x] += to_float4(c, 0.0f);
         }
-      passes++;
+      NextPass();
       (void)rayCount;
     }
 
@@ -385,6 +400,14 @@ void* ref_render_create(void* scene, int kind, int seed)
   return r;
 }
 void ref_render_destroy(void* p) { delete (RefRender*)p; }
+// S generators per pixel, pass p draws from stream p mod S (the rule of hc_pt_set_sample_streams); resets the render
+void ref_render_set_streams(void* p, int S)
+{
+  RefRender* r = (RefRender*)p;
+  if (r->kind == 0) r->pt->SetStreams(S);
+  else if (r->kind == 1) r->mis->SetStreams(S);
+  else if (r->kind == 2) r->loop->SetStreams(S);
+}
 
 void ref_render_pass(void* p, int x0, int y0, int x1, int y1)
 {

@@ -103,6 +103,7 @@ class Ref:
         L.ref_render_create.argtypes = [ct.c_void_p, ct.c_int, ct.c_int]
         L.ref_render_destroy.argtypes = [ct.c_void_p]
         L.ref_render_pass.argtypes = [ct.c_void_p] + [ct.c_int]*4
+        L.ref_render_set_streams.argtypes = [ct.c_void_p, ct.c_int]; L.ref_render_set_streams.restype = None
         L.ref_render_pass_qmc_range.argtypes = [ct.c_void_p, ct.c_int, ct.c_int]
         L.ref_render_get_sum.argtypes = [ct.c_void_p, ct.c_void_p]
         for f in (L.ref_surface_eval, L.ref_material_sample, L.ref_material_eval, L.ref_light_sample, L.ref_emission_eval):
@@ -219,11 +220,13 @@ class RefScene:
             self.ref.L.ref_scene_destroy(self.h)
             self.h = None
 
-    def render(self, kind, seed, passes, window=None):
+    def render(self, kind, seed, passes, window=None, streams=1):
         """kind: 0 PT (IntegratorStupidPT), 1 MISPT recursive, 2 MISPTLoop2, 3 MISPT+QMC.  Returns per-pixel SUM image and pass count.
         window = (x0, y0, x1, y1): only these pixels are rendered (per-pixel generators make them equal to the same pixels of a full frame)."""
         r = self.ref.L.ref_render_create(self.h, kind, seed)
         self._renders.append(r)
+        if streams != 1:
+            self.ref.L.ref_render_set_streams(r, int(streams))
         W, H = self.scn.width, self.scn.height
         x0, y0, x1, y1 = window if window is not None else (0, 0, W, H)
         for _ in range(passes):

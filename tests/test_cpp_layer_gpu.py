@@ -167,6 +167,27 @@ def test_ihwlayer_sky_dome_scene_equals_c_abi_path(consts, layer):
     lay.close()
 
 
+def test_ihwlayer_sample_streams_one_call_carries_several_passes(consts, layer):
+    """CallNamedFunc("sample_streams", "4"): one BeginTracingPass / EndTracingPass is one wavefront of four passes (GetSPP says so) and the image is
+    the C-ABI path's with the same streams."""
+    scn = scenes.cornell(64, 64)
+    lay = _make(scn, consts)
+    lay.CallNamedFunc("sample_streams", "4")
+    lay.InitPathTracing(9)
+    lay.TracingPasses(2)
+    assert abs(lay.GetSPP() - 8.0) < 1e-4
+    a = lay.GetHDRImage()
+    try:
+        layer.SetSampleStreams(4)
+        layer.LoadScene(scn)
+        layer.InitPathTracing(9)
+        layer.TracingPass(2, 8)
+        assert np.array_equal(a, layer.GetHDRImage())
+    finally:
+        layer.SetSampleStreams(1)
+    lay.close()
+
+
 def test_ihwlayer_two_trees_with_alpha_table_equals_c_abi_path(consts, layer):
     """SetAllBVH4 with a two-tree ConvertionResult (tree 1 = meshes with opacity maps + pTriangleAlpha, GPUOCLData.cpp:103-116) through IHWLayer."""
     scn = scenes.cornell_with_cutout(64, 64)

@@ -150,7 +150,7 @@ def test_shadow_rays_through_the_alpha_tested_tree(layer):
     tree1 = np.isin(both["instId"], (1, 3, 4)) & (both["primId"] >= 0)        # nearest hit on an instance of the alpha-tested tree (cornell_with_cutout)
     assert tree1.sum() > 50
     sh = rays.copy()
-    sh[:, 7] = np.where(both["primId"] >= 0, both["t"]*np.float32(1.001), np.float32(1.0e30))     # just past the nearest hit of both trees
+    sh[:, 7] = np.where(both["primId"] >= 0, np.minimum(both["t"], np.float32(1.0e30))*np.float32(1.001), np.float32(1.0e30))     # just past the nearest hit of both trees
     try:
         layer.SetShadowTrees(1)
         vis_all = layer.TraceShadow(sh)
