@@ -458,27 +458,36 @@ def run_ours(args):
             _log("extras: " + key + " warm-up passes done, first reduce")
             lay.ReduceFramebuffer(0, mode)             # warm-up of the exchange (NCCL connects lazily)
             _log("extras: " + key + " reduce done")
-            lay.ResetPerfCounters()
-            barrier()
             passes = 64 if key.startswith("c1") else (8 if streams > 1 else 4)
-            t0 = time.perf_counter()
-            lay.TracingPass(integ, passes)
-            t_pass = time.perf_counter() - t0
-            red_ms = lay.ReduceFramebuffer(0, mode)    # the frame is not complete before rank 0 holds it
-            barrier()
-            t_frame = time.perf_counter() - t0
-            st3 = lay.GetRaysStat()
-            ev_ms = st3["msClosest"] + st3["msShadow"] + st3["msShade"] + st3["msOther"]
-            vals = torch.tensor([t_frame, ev_ms, red_ms, float(st3["paths"]), float(st3["raysClosest"]), float(st3["raysShadow"]),
-                                 st3["msClosest"], st3["msShadow"], st3["msShade"], st3["msOther"], t_pass], device=dev, dtype=torch.float64)
-            mx, sm, mn = vals.clone(), vals.clone(), vals.clone()
-            if dist is not None:
-                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-                dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-                dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-            mx, sm, mn = mx.tolist(), sm.tolist(), mn.tolist()
-            mean_img = float(lay.GetSumImage()[..., :3].sum()/(scn3.width*scn3.height*3*(passes + warm))) if rank == 0 else 0.0
-            extras[key] = {"workload": label, "passes": passes, "sample_streams": streams, "passes_per_wavefront": lay.GroupPasses(), "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": (mx[1] + mx[2])/passes,
+            # several frames, the MEDIAN frame is reported (frame time = max over ranks, reduce and the closing barrier included): with 8 processes on
+            # the 32 vCPUs of the box single frames show host-side stalls of 1-5 ms on one rank or another (profiles/r02_streams_ranks_n8.log)
+            frames = 1 if args.profile else 5
+            rows = []
+            for _f in range(frames):
+                lay.ResetPerfCounters()
+                barrier()
+                t0 = time.perf_counter()
+                lay.TracingPass(integ, passes)
+                t_pass = time.perf_counter() - t0
+                red_ms = lay.ReduceFramebuffer(0, mode)    # the frame is not complete before rank 0 holds it
+                barrier()
+                t_frame = time.perf_counter() - t0
+                st3 = lay.GetRaysStat()
+                ev_ms = st3["msClosest"] + st3["msShadow"] + st3["msShade"] + st3["msOther"]
+                vals = torch.tensor([t_frame, ev_ms, red_ms, float(st3["paths"]), float(st3["raysClosest"]), float(st3["raysShadow"]),
+                                     st3["msClosest"], st3["msShadow"], st3["msShade"], st3["msOther"], t_pass], device=dev, dtype=torch.float64)
+                mx, sm, mn = vals.clone(), vals.clone(), vals.clone()
+                if dist is not None:
+                    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+                    dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+                rows.append((mx.tolist(), sm.tolist(), mn.tolist()))
+            rows.sort(key=lambda r: r[0][0])
+            frame_ms = [1e3*r[0][0] for r in rows]
+            mx, sm, mn = rows[len(rows)//2]
+            mean_img = float(lay.GetSumImage()[..., :3].sum()/(scn3.width*scn3.height*3*(passes*frames + warm))) if rank == 0 else 0.0
+            extras[key] = {"workload": label, "passes": passes, "frames_timed": frames, "frame_ms_min_median_max": [frame_ms[0], frame_ms[len(frame_ms)//2], frame_ms[-1]],
+                           "sample_streams": streams, "passes_per_wavefront": lay.GroupPasses(), "ms_per_pass_wall_max": 1e3*mx[0]/passes, "ms_per_pass_device_max": (mx[1] + mx[2])/passes,
                            "ms_per_pass_without_reduce_wall_max": 1e3*mx[10]/passes,
                            "paths_per_s": sm[3]/mx[0], "mrays_per_s": (sm[4] + sm[5])/mx[0]/1e6,
                            "rays_closest_per_pass": sm[4]/passes, "rays_shadow_per_pass": sm[5]/passes,

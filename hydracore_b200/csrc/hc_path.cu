@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <chrono>
 #include <string>
 
 #define HC_SHADE_BLOCK 128
@@ -831,6 +832,7 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   HC_REQUIRE(integrator == HC_INTEGRATOR_PT || integrator == HC_INTEGRATOR_MISPT || integrator == HC_INTEGRATOR_MISPT_QMC, HC_E_ARG, "hc_pt_pass: unknown integrator");
   HC_REQUIRE(ctx->ptReady, HC_E_STATE, "hc_pt_pass: call hc_pt_init first (after the scene, the screen size and the tiles are set)");
   HC_CUDA(cudaSetDevice(ctx->device));
+  const auto hostT0 = std::chrono::steady_clock::now();
   if (ctx->sceneDirty) { const int rcv = RefreshScene(ctx, "hc_pt_pass"); if (rcv) return rcv; }      // lights / materials / globals re-uploaded since hc_pt_init
   HcPathHost* p = PH(ctx);
   ctx->combinedValid = false;                                  // new samples: an earlier cross-rank sum (hc_fb_reduce) is stale
@@ -1060,7 +1062,9 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   }
   if (gexec) { HC_CUDA(cudaStreamSynchronize(ctx->stream)); cudaGraphExecDestroy(gexec); }
 #undef HC_STAGE
+  const auto hostT1 = std::chrono::steady_clock::now();
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const auto hostT2 = std::chrono::steady_clock::now();
   float ms = 0.0f; HC_CUDA(cudaEventElapsedTime(&ms, ctx->evStage[0], ctx->evStage[1]));
   ctx->lastTraceMs = ms;              // device time of the LAST wavefront (lastGroup passes)
   ctx->lastGroupPasses = lastGroup;
@@ -1070,7 +1074,10 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
     float t = 0.0f; HC_CUDA(cudaEventElapsedTime(&t, p->evPool[2*k], p->evPool[2*k + 1]));
     cls[p->evClass[k]] += t;
   }
-  if (getenv("HC_PT_LOG"))                    // per-launch device times of the last pass (class 0 closest, 1 shadow added, 2 shade, 3 raygen / sort)
+  if (getenv("HC_PT_LOG"))
+    fprintf(stderr, "[hc_pt_pass] rank %d: %d passes, last wavefront %d passes / %d paths: host enqueue %.3f ms, wait %.3f ms, device span of the last wavefront %.3f ms\n", ctx->rank, passes,
+            lastGroup, n, std::chrono::duration<double, std::milli>(hostT1 - hostT0).count(), std::chrono::duration<double, std::milli>(hostT2 - hostT1).count(), ms);
+  if (getenv("HC_PT_LOG") && atoi(getenv("HC_PT_LOG")) >= 2)                    // per-launch device times of the last pass (class 0 closest, 1 shadow added, 2 shade, 3 raygen / sort)
   {
     int live[256]; HC_CUDA(cudaMemcpy(live, counts, sizeof(live), cudaMemcpyDeviceToHost));
     for (int d = 0; d < nBounces && d < 255; d++) fprintf(stderr, "[hc_pt_pass] bounce %d live %d\n", d, live[d]);
