@@ -594,7 +594,12 @@ def _watchdog(limit_s):
     import threading
 
     def fire():
-        _log("watchdog: no JSON line after %d s - giving up" % limit_s)
+        _log("watchdog: no JSON line after %d s - giving up; stacks follow" % limit_s)
+        try:
+            import faulthandler
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        except Exception:
+            pass
         os._exit(3)
     t = threading.Timer(limit_s, fire)
     t.daemon = True
