@@ -431,7 +431,7 @@ struct HcPathHost
   int64_t capacity = 0;
   int nOwned = 0;
   long long ownedKey = -1;                    // (W, H, tile, rank, world) the owned-pixel list was built for
-  bool haveNormalMaps = false;                // set by ValidateScene: selects the k_pt_shade instantiation
+  bool haveNormalMaps = false;                // set by ValidateScene: normal-mapped or anisotropic (Beckmann / TRGGX) materials present - selects the extended k_pt_shade instantiation
   std::vector<cudaEvent_t> evPool;            // per-launch stage timing of the LAST pass of a hc_pt_pass call: {start, stop} pairs
   std::vector<int> evClass;                    // 0 closest, 1 shadow, 2 shade, 3 other
 };
@@ -615,11 +615,17 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
     memcpy(&ntex, m + HC_NORMAL_TEX_OFFSET, 4); memcpy(&ptex, m + HC_PROC_TEX1_F4_HEAD_OFFSET, 4);
     const bool ok = type == HC_PLAIN_MAT_CLASS_LAMBERT || type == HC_PLAIN_MAT_CLASS_PHONG_SPECULAR || type == HC_PLAIN_MAT_CLASS_BLINN_SPECULAR || type == HC_PLAIN_MAT_CLASS_GGX ||
                     type == HC_PLAIN_MAT_CLASS_PERFECT_MIRROR || type == HC_PLAIN_MAT_CLASS_GLASS || type == HC_PLAIN_MAT_CLASS_BLEND_MASK ||
-                    type == HC_PLAIN_MAT_CLASS_EMISSIVE || type == HC_PLAIN_MAT_CLASS_OREN_NAYAR || type == HC_PLAIN_MAT_CLASS_TRANSLUCENT || type == HC_PLAIN_MAT_CLASS_THIN_GLASS;
-    if (!ok) { why = "material class " + std::to_string(type) + " is not supported yet (Lambert, Oren-Nayar, translucent, Phong, Blinn, GGX, mirror, glass, thin glass, blend mask are)"; return HC_E_ARG; }
+                    type == HC_PLAIN_MAT_CLASS_EMISSIVE || type == HC_PLAIN_MAT_CLASS_OREN_NAYAR || type == HC_PLAIN_MAT_CLASS_TRANSLUCENT || type == HC_PLAIN_MAT_CLASS_THIN_GLASS ||
+                    type == HC_PLAIN_MAT_CLASS_BECKMANN || type == HC_PLAIN_MAT_CLASS_TRGGX;
+    if (!ok) { why = "material class " + std::to_string(type) + " is not supported yet (Lambert, Oren-Nayar, translucent, Phong, Blinn, GGX, Beckmann, TRGGX, mirror, glass, thin glass, blend mask are)"; return HC_E_ARG; }
     {
       // texture ids behind the samplers this material class reads (Sample2D call sites of hc_shade.cuh): sampler offset in float4 from the node start
-      int slots[3] = { HC_EMISSIVE_TEXMATRIXID_OFFSET, HC_LAMBERT_TEXMATRIXID_OFFSET, -1 };
+      int slots[5] = { HC_EMISSIVE_TEXMATRIXID_OFFSET, HC_LAMBERT_TEXMATRIXID_OFFSET, -1, -1, -1 };
+      if (type == HC_PLAIN_MAT_CLASS_BECKMANN || type == HC_PLAIN_MAT_CLASS_TRGGX)
+      {
+        slots[2] = HC_BECKMANN_GLOSINESS_TEXMATRIXID_OFFSET; slots[3] = HC_BECKMANN_ANISO_TEXMATRIXID_OFFSET; slots[4] = HC_BECKMANN_ROT_TEXMATRIXID_OFFSET;
+        p->haveNormalMaps = true;                      // the anisotropic lobes live in the extended k_pt_shade instantiation only
+      }
       if (type == HC_PLAIN_MAT_CLASS_PHONG_SPECULAR || type == HC_PLAIN_MAT_CLASS_BLINN_SPECULAR || type == HC_PLAIN_MAT_CLASS_THIN_GLASS || type == HC_PLAIN_MAT_CLASS_GGX) slots[2] = HC_PHONG_GLOSINESS_TEXMATRIXID_OFFSET;
       if (type == HC_PLAIN_MAT_CLASS_GLASS) slots[2] = HC_GLASS_GLOSINESS_TEXMATRIXID_OFFSET;
       if (type == HC_PLAIN_MAT_CLASS_EMISSIVE) slots[1] = -1;
@@ -791,7 +797,8 @@ int hc_pt_group_passes(hc_ctx* ctx, int* outPasses)
 {
   if (!ctx || !outPasses) return HC_E_ARG;
   HcPathHost* p = PH(ctx);
-  HC_REQUIRE(ctx->ptReady && p && p->nOwned > 0, HC_E_STATE, "hc_pt_group_passes: call hc_pt_init first");
+  HC_REQUIRE(ctx->ptReady && p, HC_E_STATE, "hc_pt_group_passes: call hc_pt_init first");
+  if (p->nOwned <= 0) { *outPasses = 1; return HC_OK; }                          // a rank without pixels (more ranks than tiles): its passes are empty
   const int64_t frame = int64_t(ctx->width)*ctx->height;
   // default limit: what a single GPU keeps in flight for this frame anyway, and at least 2M paths (below that a launch is latency-bound)
   const int64_t cap = ctx->maxPathsInFlight > 0 ? ctx->maxPathsInFlight : std::max<int64_t>(frame, int64_t(1) << 21);

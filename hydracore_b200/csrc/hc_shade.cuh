@@ -12,6 +12,7 @@
 #include "hc_math.cuh"
 #include "hc_layout.h"
 #include "hc_trace.cuh"
+#include "hc_microfacet.cuh"
 
 #define HC_GEPSILON   5e-6f      // cglobals.h:68-70
 #define HC_DEPSILON   1e-20f
@@ -862,9 +863,99 @@ HC_DEV float3 BumpMapping(float3 tangent, float3 bitangent, float3 normal, float
 }
 HC_DEV bool HasNormalMap(const float* m) { return MatI(m, HC_NORMAL_TEX_OFFSET) != HC_INVALID_TEXTURE; }
 
+// ---- anisotropic Beckmann / Trowbridge-Reitz materials (PLAIN_MAT_CLASS_BECKMANN, _TRGGX; cmaterial.h:1529-1830).  Both share one slot map and
+// one tangent-frame rule; the lobe itself (D, G, pdf, visible-normal sampling in the local frame) is hc_microfacet.cuh, KIND 0 / 1.
+HC_DEV HcMf3 ToMf(float3 v) { return mf3(v.x, v.y, v.z); }
+HC_DEV float AnisoGloss(const float* m, float2 tc, const HcScene& s)                        // beckmannGlosiness, cmaterial.h:1567-1580
+{
+  if (MatI(m, HC_BECKMANN_GLOSINESS_TEXID_OFFSET) != HC_INVALID_TEXTURE)
+  {
+    const float3 gc = Sample2D(MatI(m, HC_BECKMANN_GLOSINESS_TEXMATRIXID_OFFSET), tc, m, s);
+    return clampf(m[HC_BECKMANN_GLOSINESS_OFFSET]*maxcomp(gc), 0.0f, 0.99f);
+  }
+  return m[HC_BECKMANN_GLOSINESS_OFFSET];
+}
+HC_DEV float2 AnisoAlphaXY(const float* m, float2 tc, const HcScene& s)                     // beckmannAnisotropy + beckmannAlphaXY, cmaterial.h:1582-1609
+{
+  const float3 ac = Sample2D(MatI(m, HC_BECKMANN_ANISO_TEXMATRIXID_OFFSET), tc, m, s);
+  const float aniso = clampf(m[HC_BECKMANN_ANISOTROPY_OFFSET]*maxcomp(ac), 0.0f, 1.0f);
+  const float roughness = 0.5f - 0.5f*AnisoGloss(m, tc, s);
+  const float anisoMult = 1.0f - aniso;
+  return f2(mfRoughnessToAlpha(roughness*roughness), mfRoughnessToAlpha(roughness*roughness*anisoMult*anisoMult));
+}
+// BeckmanTangentSpace (cmaterial.h:1611-1636): anisotropic lobes use the surface's (bitangent, tangent) turned about the normal by the
+// rotation parameter (RotateAroundVector4x4, cglobals.h:1122-1150), isotropic ones any frame; FLIP_TANGENT swaps the two axes
+HC_DEV void AnisoFrame(const float* m, float2 alpha, float3 nz, float3 tan, float3 bitan, float2 tc, const HcScene& s, float3& nx, float3& ny)
+{
+  if (fabsf(alpha.x - alpha.y) > 1e-5f)
+  {
+    const float3 rc = Sample2D(MatI(m, HC_BECKMANN_ROT_TEXMATRIXID_OFFSET), tc, m, s);
+    const float rotVal = clampf(m[HC_BECKMANN_ANISO_ROT_OFFSET]*maxcomp(rc), 0.0f, 1.0f);
+    const float ang = rotVal*HC_M_TWOPI;
+    const float c = hc_cos(ang), sn = hc_sin(ang), omc = 1.0f - c;
+    HcMat4 r;
+    r.c0 = make_float4(omc*nz.x*nz.x + c,       omc*nz.y*nz.x + sn*nz.z, omc*nz.x*nz.z - sn*nz.y, 0.0f);
+    r.c1 = make_float4(omc*nz.x*nz.y - sn*nz.z, omc*nz.y*nz.y + c,       omc*nz.z*nz.y + sn*nz.x, 0.0f);
+    r.c2 = make_float4(omc*nz.x*nz.z + sn*nz.y, omc*nz.y*nz.z - sn*nz.x, omc*nz.z*nz.z + c,       0.0f);
+    r.c3 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    nx = mul3x3(r, bitan);
+    ny = mul3x3(r, tan);
+  }
+  else
+    CoordinateSystem(nz, nx, ny);
+  if (MatI(m, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_FLIP_TANGENT) { const float3 t = nx; nx = ny; ny = t; }
+}
+HC_DEV float3 AnisoColor(const float* m, float2 tc, const HcScene& s)
+{
+  const float3 tex = Sample2D(MatI(m, HC_BECKMANN_TEXMATRIXID_OFFSET), tc, m, s);
+  return clamp3(tex*Mat3(m, HC_BECKMANN_COLORX_OFFSET), 0.0f, 1.0f);
+}
+// beckmannEvalPDF / trggxEvalPDF (cmaterial.h:1638-1662, 1740-1765).  As in the reference, wo is the view direction's NEGATIVE in the local frame and
+// the half vector normalize(l + v) is used in world coordinates.
+template<int KIND>
+HC_DEV float AnisoEvalPDF(const float* m, float3 l, float3 v, float3 n, float3 tan, float3 bitan, float2 tc, const HcScene& s)
+{
+  if (dot(n, v) < 1e-6f || dot(n, l) < 1e-6f) return 1.0f;
+  const float2 alpha = AnisoAlphaXY(m, tc, s);
+  float3 nx, ny;
+  AnisoFrame(m, alpha, n, tan, bitan, tc, s, nx, ny);
+  const HcMf3 wo = mf3(-dot(v, nx), -dot(v, ny), -dot(v, n));
+  return mfPdf<KIND>(wo, ToMf(normalize(l + v)), alpha.x, alpha.y);
+}
+template<int KIND>
+HC_DEV float3 AnisoEvalBxDF(const float* m, float3 l, float3 v, float3 n, float3 tan, float3 bitan, float2 tc, const HcScene& s)      // cmaterial.h:1664-1690, 1767-1792
+{
+  if (dot(n, v) < 1e-6f || dot(n, l) < 1e-6f) return f3(0.0f, 0.0f, 0.0f);
+  const float3 color = AnisoColor(m, tc, s);
+  const float2 alpha = AnisoAlphaXY(m, tc, s);
+  float3 nx, ny;
+  AnisoFrame(m, alpha, n, tan, bitan, tc, s, nx, ny);
+  const HcMf3 wo = mf3(-dot(v, nx), -dot(v, ny), -dot(v, n)), wi = mf3(-dot(l, nx), -dot(l, ny), -dot(l, n));
+  return color*mfBrdf<KIND>(wo, wi, alpha.x, alpha.y);
+}
+template<int KIND>
+HC_DEV void AnisoSample(const float* m, float r1, float r2, float3 rayDir, float3 n, float2 tc, float3 tan, float3 bitan, const HcScene& s, HcMatSample& out)
+{                                                                                                    // cmaterial.h:1692-1728, 1794-1830
+  const float3 color = AnisoColor(m, tc, s);
+  const float2 alpha = AnisoAlphaXY(m, tc, s);
+  const float gloss = AnisoGloss(m, tc, s);
+  float3 nx, ny;
+  AnisoFrame(m, alpha, n, tan, bitan, tc, s, nx, ny);
+  const HcMf3 wo = mf3(-dot(rayDir, nx), -dot(rayDir, ny), -dot(rayDir, n));
+  const HcMf3 wh = mfSampleWh<KIND>(wo, r1, r2, alpha.x, alpha.y);
+  const float k = 2.0f*mfDot(wo, wh);
+  const HcMf3 wi = mf3(k*wh.x - wo.x, k*wh.y - wo.y, k*wh.z - wo.z);                                 // wo mirrored about wh
+  const float3 newDir = normalize(wi.x*nx + wi.y*ny + wi.z*n);
+  const float3 v = rayDir*(-1.0f);
+  if (dot(n, v) < 1e-6f || dot(n, newDir) < 1e-6f) { out.color = f3(0.0f, 0.0f, 0.0f); out.pdf = 1.0f; }
+  else { out.color = color*mfBrdf<KIND>(wo, wi, alpha.x, alpha.y); out.pdf = mfPdf<KIND>(wo, wh, alpha.x, alpha.y); }
+  out.direction = newDir;
+  out.flags = (gloss >= 0.99f) ? HC_RAY_EVENT_S : HC_RAY_EVENT_G;
+}
+
 // leaf dispatch: MaterialLeafSampleAndEvalBRDF (cmaterial.h:2245-2335)
-// NMAP: the scene has at least one normal-mapped material (found by ValidateScene); scenes without any run the instantiation without
-// this code, which keeps the register-limited shade kernel as it was
+// NMAP: the "extended" instantiation - the scene has at least one normal-mapped or anisotropic (Beckmann / TRGGX) material (found by
+// ValidateScene); scenes without any run the instantiation without this code, which keeps the register-limited shade kernel as it was
 template<bool NMAP>
 HC_DEV void LeafSample(const float* m, const HcSurfaceHit& shIn, float3 rayDir, float3 rands, const HcScene& s, HcMatSample& out)
 {
@@ -888,6 +979,8 @@ HC_DEV void LeafSample(const float* m, const HcSurfaceHit& shIn, float3 rayDir, 
     case HC_PLAIN_MAT_CLASS_THIN_GLASS:     ThinglassSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_TRANSLUCENT:    TranslucentSample(m, rands.x, rands.y, sh.normal, sh.texCoord, s, out); break;
     case HC_PLAIN_MAT_CLASS_OREN_NAYAR:     OrennayarSample(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, s, out); break;
+    case HC_PLAIN_MAT_CLASS_BECKMANN:       if (NMAP) AnisoSample<0>(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, shIn.tangent, shIn.biTangent, s, out); break;
+    case HC_PLAIN_MAT_CLASS_TRGGX:          if (NMAP) AnisoSample<1>(m, rands.x, rands.y, rayDir, sh.normal, sh.texCoord, shIn.tangent, shIn.biTangent, s, out); break;
     default: break;
   }
   if (hasNormalMap)                          // the caller multiplies by the cosine to the UNBUMPED normal (cmaterial.h:2320-2330)
@@ -969,6 +1062,14 @@ HC_DEV HcBxDF LeafEval(const float* m, float3 l, float3 v, const HcSurfaceHit& s
       r.brdf = OrennayarEvalBxDF(m, l, v, n, tc, s)*cosMult; r.pdfFwd = fabsf(dot(l, n))*HC_INV_PI; r.pdfRev = fabsf(dot(v, n))*HC_INV_PI; r.diffuse = true; break;
     case HC_PLAIN_MAT_CLASS_TRANSLUCENT:
       r.btdf = TranslucentEvalBxDF(m, l, v, n, tc, s)*cosMult2; r.pdfFwd = TranslucentEvalPDF(l, v, n); r.pdfRev = TranslucentEvalPDF(v, l, n); r.diffuse = true; break;
+    case HC_PLAIN_MAT_CLASS_BECKMANN:
+      if (NMAP) { r.brdf = AnisoEvalBxDF<0>(m, l, v, n, sh.tangent, sh.biTangent, tc, s)*cosMult; r.pdfFwd = AnisoEvalPDF<0>(m, l, v, n, sh.tangent, sh.biTangent, tc, s);
+                  r.pdfRev = AnisoEvalPDF<0>(m, v, l, n, sh.tangent, sh.biTangent, tc, s); }
+      break;
+    case HC_PLAIN_MAT_CLASS_TRGGX:
+      if (NMAP) { r.brdf = AnisoEvalBxDF<1>(m, l, v, n, sh.tangent, sh.biTangent, tc, s)*cosMult; r.pdfFwd = AnisoEvalPDF<1>(m, l, v, n, sh.tangent, sh.biTangent, tc, s);
+                  r.pdfRev = AnisoEvalPDF<1>(m, v, l, n, sh.tangent, sh.biTangent, tc, s); }
+      break;
     default: break;      // mirror, glass and thin glass evaluate to zero for explicit light (cmaterial.h:396-404, 620-629)
   }
   return r;

@@ -77,6 +77,10 @@ def parse_library(xml_path, mesh_fallback_dirs=()):
             col = ref.find("color")
             d["reflect"] = dict(color=_floats(_val(col, "0 0 0")), gloss=float(_val(ref.find("glossiness"), "1")),
                                 brdf=ref.get("brdf_type", "phong"), fresnel=_val(ref.find("fresnel"), "0") == "1", ior=float(_val(ref.find("fresnel_ior"), "1.5")))
+            ani = ref.find("anisotropy")                                          # ReflectiveMaterialFromHydraMtl, PlainMaterialConverter.cpp:1063-1083
+            if ani is not None:
+                d["reflect"].update(aniso=float(_val(ani, "0")), aniso_rot=float(ani.get("rot", "0")), aniso_flip=int(ani.get("flip_axis", "0")) == 1)
+            d["reflect"]["brdf"] = {"GGX": "ggx", "TRGGX": "trggx"}.get(d["reflect"]["brdf"], d["reflect"]["brdf"])
         if emi is not None:
             col = emi.find("color")
             d["emission"] = _floats(_val(col, "0 0 0"))
@@ -178,9 +182,12 @@ def build_scene(lib, width, height):
             if "reflect" in d and max(d["reflect"]["color"]) > 1e-5:
                 r = d["reflect"]
                 if r["brdf"] not in _BRDF_CODE:
-                    raise ValueError("material %d: reflectivity brdf_type '%s' is not supported yet (phong, ggx, torranse_sparrow are)" % (mid, r["brdf"]))
+                    raise ValueError("material %d: reflectivity brdf_type '%s' is not supported yet (phong, ggx, torranse_sparrow, beckmann, trggx are)" % (mid, r["brdf"]))
                 if r["gloss"] >= 0.995:                            # an untextured glossiness this high becomes a perfect mirror (PlainMaterialConverter.cpp:1128)
                     top = M.mirror(tuple(r["color"]))
+                elif r["brdf"] in ("beckmann", "trggx"):
+                    top = {"beckmann": M.beckmann, "trggx": M.trggx}[r["brdf"]](tuple(r["color"]), r["gloss"], aniso=r.get("aniso", 0.0), rot=r.get("aniso_rot", 0.0),
+                                                                                  flip=r.get("aniso_flip", False))
                 else:
                     top = {"ggx": M.ggx, "torranse_sparrow": M.blinn, "phong": M.phong}[r["brdf"]](tuple(r["color"]), r["gloss"])
                 nodes = M.blend(tuple(r["color"]), top, lam, fresnel=r["fresnel"], ior=r["ior"])
@@ -200,7 +207,7 @@ def build_scene(lib, width, height):
     return scn.build()
 
 
-_BRDF_CODE = {"phong": 0, "ggx": 1, "torranse_sparrow": 2}     # column 10 of the fixture's material rows
+_BRDF_CODE = {"phong": 0, "ggx": 1, "torranse_sparrow": 2, "beckmann": 3, "trggx": 4}     # column 10 of the fixture's material rows
 _BRDF_NAME = {v: k for k, v in _BRDF_CODE.items()}
 
 
@@ -223,7 +230,8 @@ def _fixture_arrays(lib):
         dif, ref = d.get("diffuse"), d.get("reflect")
         mats.append([mid, d.get("light_id", -1)] + (dif["color"] + [dif["tex"]] if dif else [0, 0, 0, -1]) +
                     (ref["color"] + [ref["gloss"], float(_BRDF_CODE[ref["brdf"]]), 1.0 if ref["fresnel"] else 0.0, ref["ior"]] if ref else [0, 0, 0, -1, 0, 0, 0]) +
-                    (d["emission"] if "emission" in d else [-1, -1, -1]) + [d.get("opacity_tex", -1)])
+                    (d["emission"] if "emission" in d else [-1, -1, -1]) + [d.get("opacity_tex", -1)] +
+                    ([ref.get("aniso", 0.0), ref.get("aniso_rot", 0.0), 1.0 if ref.get("aniso_flip", False) else 0.0] if ref else [0.0, 0.0, 0.0]))
     a["materials"] = np.array(mats, np.float64)
     shapes = {"rect": 0, "sphere": 1, "point": 2, "sky": 3, "spot": 4, "directional": 5}
     a["lights"] = np.array([[lid] + list(l["half"]) + l["color"] + [l["mat_id"], shapes[l["type"] if l["type"] in ("sky", "spot", "directional") else l["shape"]], l["radius"]] + list(l.get("params", [0.0, 0.0, 0.0])) for lid, l in sorted(lib["lights"].items())], np.float64)
@@ -280,6 +288,8 @@ def load_fixture(path, scene):
             d["diffuse"] = dict(color=list(r[2:5]), tex=int(r[5]))
         if r[9] >= 0:
             d["reflect"] = dict(color=list(r[6:9]), gloss=float(r[9]), brdf=_BRDF_NAME[int(round(r[10]))], fresnel=r[11] > 0.5, ior=float(r[12]))
+            if len(r) > 19:                                                       # fixtures written before the anisotropic lobes have 17 columns
+                d["reflect"].update(aniso=float(r[17]), aniso_rot=float(r[18]), aniso_flip=r[19] > 0.5)
         if r[13] >= 0:
             d["emission"] = list(r[13:16])
         if len(r) > 16 and r[16] > 0:

@@ -137,6 +137,39 @@ def ggx(color, gloss, tex_id=0, multiscatter=False, **kw):
                    C["PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER"] if multiscatter else 0, **kw)
 
 
+def _aniso(mat_type, color, gloss, aniso, rot, flip, tex_id, gloss_tex_id, aniso_tex_id, rot_tex_id, **kw):
+    m = _node(mat_type, C["PLAIN_MATERIAL_CAST_CAUSTICS"] | (C["PLAIN_MATERIAL_FLIP_TANGENT"] if flip else 0))
+    m[C["BECKMANN_COLORX_OFFSET"]:C["BECKMANN_COLORX_OFFSET"] + 3] = color
+    m[C["BECKMANN_COSPOWER_OFFSET"]] = 0.0
+    m[C["BECKMANN_GLOSINESS_OFFSET"]] = gloss
+    m[C["BECKMANN_ANISOTROPY_OFFSET"]] = aniso
+    m[C["BECKMANN_ANISO_ROT_OFFSET"]] = rot
+    for tid, id_off, mat_off, samp_off in ((tex_id, "BECKMANN_TEXID_OFFSET", "BECKMANN_TEXMATRIXID_OFFSET", "BECKMANN_SAMPLER0_OFFSET"),
+                                           (gloss_tex_id, "BECKMANN_GLOSINESS_TEXID_OFFSET", "BECKMANN_GLOSINESS_TEXMATRIXID_OFFSET", "BECKMANN_SAMPLER1_OFFSET"),
+                                           (aniso_tex_id, "BECKMANN_ANISO_TEXID_OFFSET", "BECKMANN_ANISO_TEXMATRIXID_OFFSET", "BECKMANN_SAMPLER2_OFFSET"),
+                                           (rot_tex_id, "BECKMANN_ROT_TEXID_OFFSET", "BECKMANN_ROT_TEXMATRIXID_OFFSET", "BECKMANN_SAMPLER3_OFFSET")):
+        if tid and tid > 0:
+            m[C[id_off]] = _i2f(tid)
+            m[C[mat_off]] = _i2f(_sampler(m, C[samp_off], tid, **kw))
+        else:
+            m[C[id_off]] = _i2f(INVALID_TEXTURE)
+            m[C[mat_off]] = _i2f(INVALID_TEXTURE)
+            _sampler(m, C[samp_off], INVALID_TEXTURE)                # DummySampler(): the converter always writes the four samplers
+    return m
+
+
+def beckmann(color, gloss, aniso=0.0, rot=0.0, flip=False, tex_id=0, gloss_tex_id=0, aniso_tex_id=0, rot_tex_id=0, **kw):
+    """BeckmannMaterial (PlainMaterialConverter.cpp:501-565; XML brdf_type="beckmann"): anisotropic Beckmann lobe, alpha_x from the glossiness,
+    alpha_y narrowed by `aniso` in [0, 1], tangent frame turned by `rot` (fraction of a full turn) about the normal; four samplers (colour,
+    glossiness, anisotropy, rotation); always CAST_CAUSTICS, FLIP_TANGENT swaps the frame axes."""
+    return _aniso(C["PLAIN_MAT_CLASS_BECKMANN"], color, gloss, aniso, rot, flip, tex_id, gloss_tex_id, aniso_tex_id, rot_tex_id, **kw)
+
+
+def trggx(color, gloss, aniso=0.0, rot=0.0, flip=False, tex_id=0, gloss_tex_id=0, aniso_tex_id=0, rot_tex_id=0, **kw):
+    """TRGGXMaterial (PlainMaterialConverter.cpp:568-632; XML brdf_type="trggx"): the Trowbridge-Reitz counterpart in Beckmann's slots."""
+    return _aniso(C["PLAIN_MAT_CLASS_TRGGX"], color, gloss, aniso, rot, flip, tex_id, gloss_tex_id, aniso_tex_id, rot_tex_id, **kw)
+
+
 def mirror(color):
     m = _node(C["PLAIN_MAT_CLASS_PERFECT_MIRROR"], 0)
     m[10:13] = color

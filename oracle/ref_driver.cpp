@@ -314,6 +314,39 @@ void ref_trace_shadow_anyhit(const void* nodes, const void* tris, const float* r
 }
 
 // OpenMP control for the timed baselines: a launcher (torchrun) exports OMP_NUM_THREADS=1, which libgomp reads when it is loaded
+// microfacet lobes of cmatpbrt.h in the local (PBRT) frame, kind 0 = Beckmann (:195-363), 1 = Trowbridge-Reitz (:365-524).  Per item:
+// out[0] BRDF(wo, wi), out[1] pdf(wo, wh = normalize(wo + wi)), out[2..4] the half vector sampled from (wo, u), out[5] D(that wh),
+// out[6] Lambda(wo), out[7] RoughnessToAlpha(u.x)
+void ref_pbrt_microfacet(int kind, const float* wo3, const float* wi3, const float* u2, const float* alpha2, int n, float* out8)
+{
+  for (int i = 0; i < n; i++)
+  {
+    const float3 wo = make_float3(wo3[3*i], wo3[3*i + 1], wo3[3*i + 2]), wi = make_float3(wi3[3*i], wi3[3*i + 1], wi3[3*i + 2]);
+    const float2 u = make_float2(u2[2*i], u2[2*i + 1]);
+    const float ax = alpha2[2*i], ay = alpha2[2*i + 1];
+    const float3 whe = normalize(wo + wi);
+    float* o = out8 + 8*i;
+    if (kind == 0)
+    {
+      const float3 wh = BeckmannDistributionSampleWH(wo, u, ax, ay);
+      o[0] = BeckmannBRDF_PBRT(wo, wi, ax, ay); o[1] = BeckmannDistributionPdf(wo, whe, ax, ay);
+      o[2] = wh.x; o[3] = wh.y; o[4] = wh.z; o[5] = BeckmannDistributionD(wh, ax, ay);
+      o[6] = BeckmannDistributionLambda(wo, ax, ay); o[7] = BeckmannRoughnessToAlpha(u.x);
+    }
+    else
+    {
+      const float3 wh = TrowbridgeReitzDistributionSampleWH(wo, u, ax, ay);
+      o[0] = TrowbridgeReitzBRDF_PBRT(wo, wi, ax, ay); o[1] = TrowbridgeReitzDistributionPdf(wo, whe, ax, ay);
+      o[2] = wh.x; o[3] = wh.y; o[4] = wh.z; o[5] = TrowbridgeReitzDistributionD(wh, ax, ay);
+      o[6] = TrowbridgeReitzDistributionLambda(wo, ax, ay); o[7] = TrowbridgeReitzRoughnessToAlpha(u.x);
+    }
+  }
+}
+void ref_pbrt_erf(const float* x, int n, float* erfOut, float* erfInvOut)
+{
+  for (int i = 0; i < n; i++) { erfOut[i] = ErfPBRT(x[i]); erfInvOut[i] = ErfInvPBRT(x[i]); }
+}
+
 int ref_omp_max_threads() { return omp_get_max_threads(); }
 void ref_omp_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 

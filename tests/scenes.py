@@ -127,6 +127,43 @@ def cornell_orennayar(width=96, height=96):
     return scn.build()
 
 
+def cornell_anisotropic(width=96, height=96):
+    """Cornell room with the anisotropic microfacet materials of the reference (PLAIN_MAT_CLASS_BECKMANN / _TRGGX): isotropic and anisotropic lobes,
+    rotated and axis-flipped tangent frames, textured colour / glossiness / anisotropy / rotation, a near-specular lobe (gloss 0.99: RAY_EVENT_S),
+    one of them under a fresnel blend over Lambert, lit by a rect area light (so that the eval / pdf side is used by MIS as well)."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    rng = np.random.RandomState(3)
+    img = np.zeros((16, 16, 4), np.uint8)
+    yy, xx = np.mgrid[0:16, 0:16]
+    img[..., 0] = 90 + 160*(((xx//2) + (yy//2)) % 2)
+    img[..., 1] = 120 + 8*xx
+    img[..., 2] = (rng.rand(16, 16)*255).astype(np.uint8)
+    img[..., 3] = 255
+    tex = scn.add_texture_rgba8(img)
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    floor = scn.add_material(M.trggx((0.8, 0.8, 0.8), 0.75, aniso=0.7, rot=0.35, tex_id=tex, gloss_tex_id=tex, aniso_tex_id=tex, rot_tex_id=tex))
+    back = scn.add_material(M.beckmann((0.7, 0.7, 0.75), 0.55, aniso=0.5, rot=0.1, tex_id=tex))
+    b_iso = scn.add_material(M.beckmann((0.9, 0.6, 0.3), 0.6))
+    b_ani = scn.add_material(M.beckmann((0.5, 0.8, 0.9), 0.7, aniso=0.8, rot=0.15))
+    t_ani = scn.add_material(M.trggx((0.9, 0.9, 0.5), 0.8, aniso=0.6, rot=0.4, flip=True))
+    t_bl = scn.add_material(M.blend((0.8, 0.8, 0.8), M.trggx((0.95, 0.95, 0.95), 0.85), M.lambert((0.2, 0.3, 0.8)), fresnel=True, ior=1.5))
+    b_spec = scn.add_material(M.beckmann((0.9, 0.9, 0.9), 0.99, aniso=0.3))
+    emi = scn.add_material(M.emissive((17.0, 15.0, 12.0), 0))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, floor, white, back), inward=True, skip_faces=(4,))))
+    sph = S.sphere_mesh(1.0, 32, 16)
+    for mat, mtx in ((b_iso, S.translate(-2.4, -2.9, -0.5) @ S.scale(1.1, 1.1, 1.1)), (b_ani, S.translate(0.0, -2.8, 0.8) @ S.scale(1.2, 1.2, 1.2)),
+                     (t_ani, S.translate(2.4, -2.9, -0.3) @ S.scale(1.1, 1.1, 1.1)), (t_bl, S.translate(-1.2, 0.6, -2.2) @ S.scale(0.9, 0.9, 0.9))):
+        scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, mat, np.int32))), mtx)
+    scn.add_instance(scn.add_mesh(S.box_mesh(0.8, 1.4, 0.8, mat_ids=(b_spec,)*6, inward=False)), S.translate(1.6, 0.2, -2.4) @ S.rotate_y(0.5))
+    l0 = scn.add_light(M.area_light((0.0, 3.95, 0.0), (1.0, 1.0), (17.0, 15.0, 12.0)))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l0)
+    return scn.build()
+
+
 def cornell_sphere_and_point_lights(width=96, height=96):
     """The Cornell room lit by a sphere area light (with its emissive mesh, so that paths can hit it) and an omni point light."""
     from hydracore_b200 import materials as M
