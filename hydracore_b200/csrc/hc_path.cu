@@ -552,7 +552,12 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
     if (type == HC_PLAIN_LIGHT_TYPE_CYLINDER)
     {
       int ctex, ctab; memcpy(&ctex, L + 29, 4); memcpy(&ctab, L + 31, 4);                     // CYLINDER_TEX_ID, CYLINDER_PDF_TABLE_ID (clight.h:111-113)
-      if (ctex != HC_INVALID_TEXTURE) { why = "textured cylinder lights are not supported yet"; return HC_E_ARG; }
+      if (ctex != HC_INVALID_TEXTURE)                                                         // colour texture: sampler inside the light record (CYLINDER_TEXMATRIX_ID, float4 index)
+      {
+        int so; memcpy(&so, L + 30, 4);
+        if (so < 0 || so*4 + 12 > HC_LIGHT_DATA_SIZE) { why = "cylinder light: colour sampler outside the light record"; return HC_E_RANGE; }
+        int texId; memcpy(&texId, L + so*4 + 2, 4); if (texId > 0) usedTex.push_back(texId);
+      }
       if (ctab < 0 || ctab >= gi(HC_EG_pdfTableTableSize) || !ctx->storage[HC_STORAGE_PDFS].ptr) { why = "cylinder light without the pdf table the driver builds for it (UpdatePdfTablesForLight)"; return HC_E_ARG; }
       continue;
     }
@@ -561,7 +566,12 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
       int meshTab, pdfTab, triNum, mtex; memcpy(&meshTab, L + 14, 4); memcpy(&pdfTab, L + 15, 4); memcpy(&triNum, L + 16, 4); memcpy(&mtex, L + 30, 4);   // MESH_LIGHT_* (clight.h:169-175)
       const int nTab = gi(HC_EG_pdfTableTableSize);
       if (!ctx->storage[HC_STORAGE_PDFS].ptr || meshTab < 0 || meshTab >= nTab || pdfTab < 0 || pdfTab >= nTab || triNum < 1) { why = "mesh light without its mesh copy / triangle table in the pdfs storage"; return HC_E_ARG; }
-      if (mtex != HC_INVALID_TEXTURE) { why = "textured mesh lights are not supported yet"; return HC_E_ARG; }
+      if (mtex != HC_INVALID_TEXTURE)                                                         // MESH_LIGHT_TEXMATRIX_ID
+      {
+        int so; memcpy(&so, L + 31, 4);
+        if (so < 0 || so*4 + 12 > HC_LIGHT_DATA_SIZE) { why = "mesh light: colour sampler outside the light record"; return HC_E_RANGE; }
+        int texId; memcpy(&texId, L + so*4 + 2, 4); if (texId > 0) usedTex.push_back(texId);
+      }
       if (flags & HC_LIGHT_HAS_IES) { why = "IES distributions are not supported yet"; return HC_E_ARG; }
       continue;
     }
@@ -573,7 +583,6 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
     if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "unknown light type (area, sphere, cylinder, mesh, point, spot, directional, sky-dome lights are supported)"; return HC_E_ARG; }
     if (flags & (HC_LIGHT_HAS_IES | HC_AREA_LIGHT_SKY_PORTAL | HC_LIGHT_IES_POINT_AREA)) { why = "IES / sky-portal area lights are not supported yet"; return HC_E_ARG; }
     if (tex != HC_INVALID_TEXTURE) { why = "textured area lights are not supported yet"; return HC_E_ARG; }
-    if (spot != 0) { why = "area lights with a spot distribution are not supported yet"; return HC_E_ARG; }
   }
   {
     // remap lists: every target material id must exist; opacity samplers of the alpha-tested tree: every texture id must have an image
@@ -646,7 +655,6 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
       if (auxOff < 0) { why = "normal map texture id has no entry in the aux texture table"; return HC_E_ARG; }
     }
     if (ptex != HC_INVALID_TEXTURE) { why = "procedural textures are not supported yet"; return HC_E_ARG; }
-    if (type == HC_PLAIN_MAT_CLASS_GLASS && (flags & HC_PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER)) { why = "glass multiscattering table is not supported yet"; return HC_E_ARG; }
     if (type == HC_PLAIN_MAT_CLASS_BLEND_MASK)
     {
       int bf, o1, o2; memcpy(&bf, m + HC_BLEND_MASK_FLAGS_OFFSET, 4);

@@ -662,6 +662,32 @@ HC_DEV float3 GgxMultiscatter(const HcScene& s, float roughness, float dotNV, fl
   const float3 t = color*(1.0f - Ess)/fmaxf(Ess, 1e-6f);
   return f3(1.0f + t.x, 1.0f + t.y, 1.0f + t.z);
 }
+// GetMultiscatteringFrom3dTable + BilinearFrom3dTable (cmaterial.h:96-149, 161-196) over EngineGlobals::m_essTranspTable (64 x 64 x 64: cosine, roughness,
+// relative IOR in [0.4166, 2.4]); the X / Y range test and the 1/65536 scale are the reference's
+HC_DEV float3 GlassMultiscatter(const HcScene& s, float roughness, float dotNV, float ior, float3 color)
+{
+  if (!(ior >= 0.4166f && ior <= 2.4f)) return f3(1.0f, 1.0f, 1.0f);
+  const unsigned short* tab = reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(s.globals) + HC_EG_m_essTranspTable);
+  const int W = 64, H = 64, Dp = 64, plane = W*H;
+  const float iorNormal = (ior - 0.4166f)/(2.4f - 0.4166f);
+  const float x = clampf(dotNV*(float)W, 0.0f, W - 1.0001f), y = clampf(roughness*(float)H, 0.0f, H - 1.0001f), z = clampf(iorNormal*(float)Dp, 0.0f, Dp - 1.0001f);
+  const int fx = (int)floorf(x), fy = (int)floorf(y), fz = (int)floorf(z);
+  const int z0 = fz*plane, z1 = (fz + 1)*plane;
+  const int d1 = z0 + fy*W + fx, d3 = z0 + (fy + 1)*W + fx, d2 = d1 + 1, d4 = d3 + 1;
+  const int d5 = z1 + fy*W + fx, d7 = z1 + (fy + 1)*W + fx, d6 = d5 + 1, d8 = d7 + 1;
+  const float dx = x - fx, dy = y - fy, dz = z - fz;
+  const float m1 = (1.0f - dx)*(1.0f - dy), m2 = dx*(1.0f - dy), m3 = dy*(1.0f - dx), m4 = dx*dy;
+  float val = 1.0f;
+  if (fy >= 0 && fx >= 0 && fy <= H - 2 && fx <= W - 2)
+  {
+    const float p1 = tab[d1]*m1 + tab[d2]*m2 + tab[d3]*m3 + tab[d4]*m4;
+    const float p2 = tab[d5]*m1 + tab[d6]*m2 + tab[d7]*m3 + tab[d8]*m4;
+    val = p1 + dz*(p2 - p1);
+  }
+  const float Ess = val*(1.0f/65536.0f);
+  const float3 t = color*(1.0f - Ess)/fmaxf(Ess, 1e-6f);
+  return f3(1.0f + t.x, 1.0f + t.y, 1.0f + t.z);
+}
 HC_DEV float3 GgxColor(const float* m, float2 tc, const HcScene& s)
 {
   const float3 tex = Sample2D(MatI(m, HC_GGX_TEXMATRIXID_OFFSET), tc, m, s);
@@ -740,7 +766,7 @@ HC_DEV void GlassGgxSample(const float* m, float3 rands, float3 rayDir, float3 n
   const float roughness = clampf(1.0f - gloss, 0.0f, 1.0f), roughSqr = roughness*roughness;
   const float IOR = m[HC_GLASS_IOR_OFFSET];
   const float3 normal2 = hfi ? (-1.0f)*nrm : nrm;
-  bool spec = true; float Pss = 1.0f; const float3 Pms = f3(1.0f, 1.0f, 1.0f);
+  bool spec = true; float Pss = 1.0f; float3 Pms = f3(1.0f, 1.0f, 1.0f);
   out.pdf = 1.0f;
 
   // myRefractGgx(ray_dir, normal2, IOR, 1.0f, rands.z)
@@ -776,6 +802,7 @@ HC_DEV void GlassGgxSample(const float* m, float3 rands, float3 rayDir, float3 n
     const float G1 = SmithGGXMasking(dotNV, roughSqr);
     const float G2 = SmithGGXMaskingShadowing(dotNL, dotNV, roughSqr);
     Pss = G2/fmaxf(G1, 1e-6f);
+    if (MatI(m, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER) Pms = GlassMultiscatter(s, roughness, dotNV, 1.0f/eta, color);
   }
 
   const float cosOut = dot(rdir, nrm);
@@ -1173,7 +1200,28 @@ HC_DEV float AreaLightEvalPDF(const float* L, float3 rayDir, float hitDist)     
   return (pdfA*hitDist*hitDist)/fmaxf(cosVal, HC_DEPSILON2);
 }
 
-// AreaLightSampleRev (clight.h:1180-1229), untextured, no spot distribution / IES / sky portal (rejected at init)
+// areaSpotLightAttenuation (clight.h:7-12, 532-539): smoothstep between the two cone cosines about the light's normal
+HC_DEV float AreaSpotAttenuation(const float* L, float3 shadowRayDir)
+{
+  const float cos1 = L[HC_AREA_LIGHT_SPOT_COS1], cos2 = L[HC_AREA_LIGHT_SPOT_COS2];
+  const float cosTheta = fmaxf(dot(shadowRayDir, Mat3(L, HC_PLIGHT_NORM_X)), 0.0f);
+  const float tVal = (cosTheta - cos2)/(cos1 - cos2);
+  const float t = fminf(fmaxf(tVal, 0.0f), 1.0f);
+  return t*t*(3.0f - 2.0f*t);
+}
+// areaDiffuseLightGetIntensity (clight.h:542-611) for untextured lights without IES / sky portal: base colour, cut by the spot cone for light
+// samples and GI hits; an EYE ray that hits a spot-distributed light sees it white (colour / its largest component), as the reference draws it
+HC_DEV float3 AreaLightIntensity(const float* L, float3 rayDir, bool eyeRay)
+{
+  float3 color = Mat3(L, HC_PLIGHT_COLOR_X);
+  if (__float_as_int(L[HC_AREA_LIGHT_SPOT_DISTR]) != 0)
+  {
+    if (!eyeRay) color *= clampf(AreaSpotAttenuation(L, (-1.0f)*rayDir), 0.0f, 1.0f);
+    else color *= (1.0f/fmaxf(color.x, fmaxf(color.y, color.z)));
+  }
+  return color;
+}
+// AreaLightSampleRev (clight.h:1180-1229), untextured, no IES / sky portal (rejected at init)
 HC_DEV void AreaLightSampleRev(const float* L, float3 rands, float3 illum, HcShadowSample& out)
 {
   const float ox = rands.x*2.0f - 1.0f, oy = rands.y*2.0f - 1.0f;
@@ -1197,7 +1245,7 @@ HC_DEV void AreaLightSampleRev(const float* L, float3 rands, float3 illum, HcSha
   const float3 ln = Mat3(L, HC_PLIGHT_NORM_X);
   out.isPoint = false;
   out.pos = sp + epsilonOfPos(sp)*ln;
-  out.color = Mat3(L, HC_PLIGHT_COLOR_X);                                                // areaDiffuseLightGetIntensity, clight.h:542-611 (plain branch)
+  out.color = AreaLightIntensity(L, rayDir, false);
   out.pdf = AreaLightEvalPDF(L, rayDir, hitDist);
   out.maxDist = hitDist;
   out.cosAtLight = -dot(rayDir, ln);
@@ -1452,6 +1500,7 @@ HC_DEV float DirectLightEvalPDF(const float* L, float3 rayDir)                  
 #define HC_MESH_LIGHT_TRI_NUM         16
 #define HC_MESH_LIGHT_MATRIX_E00      20
 #define HC_MESH_LIGHT_TEX_ID          30
+#define HC_MESH_LIGHT_TEXMATRIX_ID    31      // float4 index of the SWTexSampler inside the light record (MESH_LIGHT_TEX_SAMPLER / 4), clight.h:174-176
 HC_DEV float3 Mat3x3MulVec(const float* M, float3 v)                                                                          // matrix3x3f_mult_float3, cglobals.h:1091-1098
 {
   return f3(M[0]*v.x + M[1]*v.y + M[2]*v.z, M[3]*v.x + M[4]*v.y + M[5]*v.z, M[6]*v.x + M[7]*v.y + M[8]*v.z);
@@ -1468,12 +1517,14 @@ HC_DEV void MeshLightSampleRev(const float* L, float3 rands, float3 illum, const
   float pickProb = 1.0f;
   const int tri = SelectIndexPropToOpt(rands.z, table, triNum + 1, pickProb);
   const int iA = indices[tri*3 + 0], iB = indices[tri*3 + 1], iC = indices[tri*3 + 2];
-  const float3 A = f3(vpos[iA]), B = f3(vpos[iB]), C = f3(vpos[iC]);
-  const float3 nA = f3(vnorm[iA]), nB = f3(vnorm[iB]), nC = f3(vnorm[iC]);
+  const float4 dA = vpos[iA], dB = vpos[iB], dC = vpos[iC], eA = vnorm[iA], eB = vnorm[iB], eC = vnorm[iC];
+  const float3 A = f3(dA), B = f3(dB), C = f3(dC);
+  const float3 nA = f3(eA), nB = f3(eB), nC = f3(eC);
   float u = rands.x, v = rands.y;
   if (u + v > 1.0f) { u = 1.0f - u; v = 1.0f - v; }
   const float w = 1.0f - u - v;
   float3 samplePos = (A*u + B*v + C*w), sampleNorm = (nA*u + nB*v + nC*w);
+  const float2 sampleTc = f2(dA.w, eA.w)*u + f2(dB.w, eB.w)*v + f2(dC.w, eC.w)*w;           // texture coordinates ride in pos.w / norm.w (clight.h:1007-1024)
   const float pdfA = 1.0f/L[HC_PLIGHT_SURFACE_AREA];
   const float* M = L + HC_MESH_LIGHT_MATRIX_E00;
   samplePos = Mat3x3MulVec(M, samplePos);
@@ -1484,7 +1535,7 @@ HC_DEV void MeshLightSampleRev(const float* L, float3 rands, float3 illum, const
   const float cosVal = fmaxf(-dot(rayDir, sampleNorm), 0.0f);
   out.isPoint = false;
   out.pos = samplePos + epsilonOfPos(samplePos)*sampleNorm;
-  out.color = Mat3(L, HC_PLIGHT_COLOR_X);                                        // meshLightGetIntensity without a texture (textured ones are rejected at init)
+  out.color = Sample2D(__float_as_int(L[HC_MESH_LIGHT_TEXMATRIX_ID]), sampleTc, L, s)*Mat3(L, HC_PLIGHT_COLOR_X);   // meshLightGetIntensity, clight.h:957-963
   out.pdf = PdfAtoW(pdfA, hitDist, cosVal);
   out.maxDist = hitDist;
   out.cosAtLight = cosVal;
@@ -1504,6 +1555,7 @@ HC_DEV float MeshLightEvalPDF(const float* L, float3 rayDir, float3 lnorm, float
 #define HC_CYLINDER_LIGHT_ZMAX       27
 #define HC_CYLINDER_LIGHT_PHIMAX     28
 #define HC_CYLINDER_TEX_ID           29
+#define HC_CYLINDER_TEXMATRIX_ID     30      // float4 index of the sampler inside the light record (CYLINDER_TEX_SAMPLER / 4), clight.h:111-114
 #define HC_CYLINDER_PDF_TABLE_ID     31
 HC_DEV void CylinderLightSampleRev(const float* L, float3 rands, float3 illum, const HcScene& s, HcShadowSample& out)
 {
@@ -1542,7 +1594,7 @@ HC_DEV void CylinderLightSampleRev(const float* L, float3 rands, float3 illum, c
   const float cosVal = fmaxf(dot(rayDir, (-1.0f)*n), 0.0f);
   out.isPoint = false;
   out.pos = samplePos;
-  out.color = Mat3(L, HC_PLIGHT_COLOR_X);                                                    // cylinderLightGetIntensity without a texture
+  out.color = Sample2D(__float_as_int(L[HC_CYLINDER_TEXMATRIX_ID]), tc, L, s)*Mat3(L, HC_PLIGHT_COLOR_X);      // cylinderLightGetIntensity, clight.h:753-759
   out.pdf = PdfAtoW(pdfA, hitDist, cosVal);
   out.maxDist = hitDist;
   out.cosAtLight = cosVal;
@@ -1598,7 +1650,14 @@ HC_DEV float3 EmissionEval(const HcScene& s, float3 rayPos, float3 rayDir, const
   if (dot(rayDir, normal) >= 0.0f) return f3(0, 0, 0);
   float3 outColor = MaterialEvalEmission(mat, rayDir, normal, sh.texCoord, s);
   if ((MatI(mat, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_FORBID_EMISSIVE_GI) && (flags & 0xFFu) > 0) outColor = f3(0, 0, 0);
-  if (s.lightsNum > 0 && L != nullptr) outColor = Mat3(L, HC_PLIGHT_COLOR_X);           // lightGetIntensity -> area light base colour (clight.h:1661-1706)
+  if (s.lightsNum > 0 && L != nullptr)                                                  // lightGetIntensity (clight.h:1661-1706): base colour, times the light's texture
+  {                                                                                     // at the hit's texture coordinates for cylinder and mesh lights
+    outColor = Mat3(L, HC_PLIGHT_COLOR_X);
+    const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
+    if (type == HC_PLAIN_LIGHT_TYPE_AREA) outColor = AreaLightIntensity(L, rayDir, (flags & 0xFFu) == 0);       // eyeRay: no diffuse bounce so far
+    else if (type == HC_PLAIN_LIGHT_TYPE_CYLINDER) outColor = Sample2D(__float_as_int(L[HC_CYLINDER_TEXMATRIX_ID]), sh.texCoord, L, s)*outColor;
+    else if (type == HC_PLAIN_LIGHT_TYPE_MESH) outColor = Sample2D(__float_as_int(L[HC_MESH_LIGHT_TEXMATRIX_ID]), sh.texCoord, L, s)*outColor;
+  }
   return outColor;
 }
 

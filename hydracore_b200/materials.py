@@ -178,8 +178,11 @@ def mirror(color):
     return m
 
 
-def glass(color, ior=1.5, gloss=1.0):
-    m = _node(C["PLAIN_MAT_CLASS_GLASS"], C["PLAIN_MATERIAL_HAS_TRANSPARENCY"] | C["PLAIN_MATERIAL_HAVE_BTDF"])
+def glass(color, ior=1.5, gloss=1.0, multiscatter=False):
+    """multiscatter: PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER - rough glass takes its energy compensation from the baked 64^3 table
+    EngineGlobals::m_essTranspTable (Scene.ms_tables must hold the tables then)."""
+    m = _node(C["PLAIN_MAT_CLASS_GLASS"], C["PLAIN_MATERIAL_HAS_TRANSPARENCY"] | C["PLAIN_MATERIAL_HAVE_BTDF"] |
+              (C["PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER"] if multiscatter else 0))
     m[10:13] = color
     m[C["GLASS_TEXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
     m[C["GLASS_TEXMATRIXID_OFFSET"]] = _i2f(INVALID_TEXTURE)
@@ -223,7 +226,7 @@ def blend(mask_color, top, bottom, fresnel=True, ior=1.5, sigmoid_exp=None):
     return [m] + top + bottom
 
 
-def area_light(pos, half_size, intensity, rotation=None, disk=False, pick_prob=1.0):
+def area_light(pos, half_size, intensity, rotation=None, disk=False, pick_prob=1.0, spot_angles_deg=None):
     """Rectangular / disk area light (AreaDiffuseLight, PlainLightConverter.cpp:130-300): local normal (0,-1,0), sample position
     R*(+-sx, 0, +-sy) + pos, surface area 4*sx*sy (pi*r^2 for disks); field map hydra_drv/clight.h:15-64, 493-521."""
     L = np.zeros(128, np.float32)
@@ -243,6 +246,11 @@ def area_light(pos, half_size, intensity, rotation=None, disk=False, pick_prob=1
     L[C["AREA_LIGHT_MATRIX_E00"]:C["AREA_LIGHT_MATRIX_E00"] + 9] = R.reshape(9)
     L[C["AREA_LIGHT_IS_DISK"]] = _i2f(1 if disk else 0)
     L[C["AREA_LIGHT_SPOT_DISTR"]] = _i2f(0)
+    if spot_angles_deg is not None:                                   # distribution="spot": cosines of the half angles of the inner and outer cone (PlainLightConverter.cpp:241-245)
+        a1, a2 = spot_angles_deg
+        L[C["AREA_LIGHT_SPOT_DISTR"]] = _i2f(1)
+        L[C["AREA_LIGHT_SPOT_COS1"]] = np.float32(math.cos(math.radians(0.5*a1)))
+        L[C["AREA_LIGHT_SPOT_COS2"]] = np.float32(math.cos(math.radians(0.5*a2)))
     L[C["PLIGHT_PROB_MULT"]] = 1.0
     L[C["PLIGHT_PICK_PROB_FWD"]] = pick_prob
     L[C["PLIGHT_PICK_PROB_REV"]] = pick_prob

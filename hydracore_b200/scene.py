@@ -364,7 +364,7 @@ class Scene:
         self.lights.append(np.ascontiguousarray(plain_light, np.float32).reshape(128))
         return len(self.lights) - 1
 
-    def add_cylinder_light(self, matrix, radius, height, angle_deg, intensity):
+    def add_cylinder_light(self, matrix, radius, height, angle_deg, intensity, tex_id=0, tex_lum=None, **sampler_kw):
         """Cylinder light (CylinderLight + CreateCylinderLightFromXmlNode + Transform, PlainLightConverter.cpp:353-413, 867-893) with the 2x2
         uniform pdf table RenderDriverRTE::UpdatePdfTablesForLight builds for an untextured one (RenderDriverRTE.cpp:940-941)."""
         from . import materials as M
@@ -378,14 +378,19 @@ class Scene:
         L[16:25] = mtx[:3, :3].reshape(9)                                  # CYLINDER_LIGHT_MATRIX_E00.., rows
         L[25], L[26], L[27], L[28] = radius, z_min, z_max, phi_max
         Li[29], Li[30] = INVALID_TEXTURE, INVALID_TEXTURE                  # CYLINDER_TEX_ID / TEXMATRIX_ID
-        Li[31] = self.add_sky_pdf_table()                                  # CYLINDER_PDF_TABLE_ID: the same 2x2 table of 0.25 a sky without a map gets
+        if tex_id and tex_id > 0:                                          # PutSamplerAt(..., CYLINDER_TEX_ID, CYLINDER_TEXMATRIX_ID, CYLINDER_TEX_SAMPLER = 32), PlainLightConverter.cpp:374
+            Li[29] = tex_id
+            Li[30] = M._sampler(L, 32, tex_id, **sampler_kw)
+        # CYLINDER_PDF_TABLE_ID: the 2x2 table of 0.25 an untextured light gets, or the table of the texture's luminance image (tex_lum) the
+        # driver builds for a textured one (UpdatePdfTablesForLight, RenderDriverRTE_PdfTables.cpp)
+        Li[31] = self.add_sky_pdf_table(tex_lum)
         d = f(1.0)/np.sqrt(f(3.0), dtype=f)
         vert = mtx[:3, :3] @ np.array([d, d, d], f)                        # mul(mrot, normalize(float3(1,1,1)))
         mult = np.sqrt((vert*vert).sum(dtype=f), dtype=f)
         L[C["PLIGHT_SURFACE_AREA"]] = f(f(f(f(z_max - z_min)*mult)*f(f(radius)*mult))*phi_max)
         return self.add_light(L)
 
-    def add_mesh_light(self, mesh_id, matrix, intensity):
+    def add_mesh_light(self, mesh_id, matrix, intensity, tex_id=0, **sampler_kw):
         """Mesh light (MeshLight + Transform, PlainLightConverter.cpp:724-830): the light samples the triangles of `mesh_id` by area.  A copy of
         the packed mesh and the prefix sums of its triangle areas (CalcTrianglePickProbTable, RenderDriverRTE_PdfTables.cpp:650-674) go into the
         "pdfs" storage; position, rotation sub-matrix and the transformed surface area into the light.  Returns the light id; instance the mesh
@@ -425,6 +430,9 @@ class Scene:
         Li[14], Li[15], Li[16] = len(self.pdf_tables) - 2, len(self.pdf_tables) - 1, tri.size     # MESH_LIGHT_MESH_OFFSET_ID / TABLE_OFFSET_ID / TRI_NUM
         L[20:29] = mtx[:3, :3].reshape(9)                                                              # MESH_LIGHT_MATRIX_E00, rows
         Li[30], Li[31] = INVALID_TEXTURE, INVALID_TEXTURE                                              # MESH_LIGHT_TEX_ID / TEXMATRIX_ID
+        if tex_id and tex_id > 0:                                                                      # PutSamplerAt(..., MESH_LIGHT_TEX_SAMPLER = 32), PlainLightConverter.cpp:782
+            Li[30] = tex_id
+            Li[31] = M._sampler(L, 32, tex_id, **sampler_kw)
         L[C["PLIGHT_SURFACE_AREA"]] = f(total)
         return self.add_light(L)
 

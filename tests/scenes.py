@@ -164,6 +164,57 @@ def cornell_anisotropic(width=96, height=96):
     return scn.build()
 
 
+def cornell_multiscatter(ms_tables, width=96, height=96):
+    """Cornell room with energy-compensated microfacet materials (PLAIN_MATERIAL_ENERGY_FIX_OR_MULTISCATTER): rough GGX reflectors read the baked
+    64 x 64 table EngineGlobals::m_essGgx2017Table, rough glass the 64^3 table m_essTranspTable (ms_tables = both, as InitEngineGlobals copies them)."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(6, 3)
+    scn.ms_tables = ms_tables
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    g1 = scn.add_material(M.ggx((0.9, 0.7, 0.3), 0.4, multiscatter=True))
+    g2 = scn.add_material(M.ggx((0.8, 0.8, 0.9), 0.75, multiscatter=True))
+    gl1 = scn.add_material(M.glass((0.9, 0.95, 0.9), ior=1.5, gloss=0.6, multiscatter=True))
+    gl2 = scn.add_material(M.glass((0.95, 0.9, 1.0), ior=1.8, gloss=0.85, multiscatter=True))
+    gl3 = scn.add_material(M.glass((1.0, 1.0, 1.0), ior=2.6, gloss=0.7, multiscatter=True))       # relative IOR outside the table: no compensation
+    emi = scn.add_material(M.emissive((17.0, 15.0, 12.0), 0))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, g2, white, white), inward=True, skip_faces=(4,))))
+    sph = S.sphere_mesh(1.0, 32, 16)
+    for mat, mtx in ((g1, S.translate(-2.4, -2.9, -0.8) @ S.scale(1.1, 1.1, 1.1)), (gl1, S.translate(0.0, -2.8, 1.0) @ S.scale(1.2, 1.2, 1.2)),
+                     (gl2, S.translate(2.4, -2.9, -0.3) @ S.scale(1.1, 1.1, 1.1)), (gl3, S.translate(-0.8, 0.4, -2.0) @ S.scale(0.9, 0.9, 0.9))):
+        scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, mat, np.int32))), mtx)
+    l0 = scn.add_light(M.area_light((0.0, 3.95, 0.0), (1.0, 1.0), (17.0, 15.0, 12.0)))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l0)
+    return scn.build()
+
+
+def cornell_area_spot(width=96, height=96):
+    """The Cornell room under a rect area light with a SPOT distribution (distribution="spot": smoothstep between two cone cosines about the light's
+    normal, clight.h:532-539, 576-590) and a tilted disk light with another cone; both have emissive meshes, so that eye rays and GI rays hit them."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    ggxm = scn.add_material(M.ggx((0.8, 0.6, 0.2), 0.7))
+    mir = scn.add_material(M.mirror((0.9, 0.9, 0.9)))
+    emi0 = scn.add_material(M.emissive((30.0, 26.0, 20.0), 0))
+    emi1 = scn.add_material(M.emissive((9.0, 12.0, 20.0), 1))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, white, white, white), inward=True, skip_faces=(4,))))
+    sph = S.sphere_mesh(1.0, 32, 16)
+    scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, ggxm, np.int32))), S.translate(-2.0, -2.8, -1.0) @ S.scale(1.2, 1.2, 1.2))
+    scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, mir, np.int32))), S.translate(1.8, -2.9, 0.8) @ S.scale(1.1, 1.1, 1.1))
+    l0 = scn.add_light(M.area_light((0.0, 3.95, 0.0), (1.0, 1.0), (30.0, 26.0, 20.0), spot_angles_deg=(40.0, 90.0)))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi0, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l0)
+    R = S.rotate_x(0.6)[:3, :3]
+    l1 = scn.add_light(M.area_light((-3.0, 2.0, 1.0), (0.6, 0.6), (9.0, 12.0, 20.0), rotation=R, disk=True, spot_angles_deg=(60.0, 120.0)))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(0.6, 0.6, y=0.0, mat_id=emi1, flip=True)), S.translate(-3.0, 2.0, 1.0) @ S.rotate_x(0.6), light_id=l1)
+    return scn.build()
+
+
 def cornell_sphere_and_point_lights(width=96, height=96):
     """The Cornell room lit by a sphere area light (with its emissive mesh, so that paths can hit it) and an omni point light."""
     from hydracore_b200 import materials as M
@@ -291,11 +342,25 @@ def cornell_remap_lists(width=96, height=96):
     return scn.build()
 
 
-def cornell_mesh_light(width=96, height=96):
-    """The Cornell room lit by a MESH light: an emissive, rotated and scaled sphere sampled by triangle area (plus a small rect light)."""
+def _light_texture(scn):
+    """16 x 8 RGBA8 stripes-and-gradient image for textured lights; returns (texture id, luminance image for the light's pdf table)."""
+    yy, xx = np.mgrid[0:8, 0:16]
+    img = np.zeros((8, 16, 4), np.uint8)
+    img[..., 0] = 40 + 200*((xx//2) % 2)
+    img[..., 1] = 60 + 20*yy
+    img[..., 2] = 250 - 12*xx
+    img[..., 3] = 255
+    lum = (0.2126*img[..., 0] + 0.7152*img[..., 1] + 0.0722*img[..., 2]).astype(np.float32)/np.float32(255.0)
+    return scn.add_texture_rgba8(img), lum
+
+
+def cornell_mesh_light(width=96, height=96, textured=False):
+    """The Cornell room lit by a MESH light: an emissive, rotated and scaled sphere sampled by triangle area (plus a small rect light).
+    textured: the light's colour is modulated by a texture looked up at the mesh's texture coordinates (meshLightGetIntensity)."""
     from hydracore_b200 import materials as M
     scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
     scn.set_trace_depth(5, 3)
+    ltex = _light_texture(scn)[0] if textured else 0
     white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
     red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
     green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
@@ -307,19 +372,21 @@ def cornell_mesh_light(width=96, height=96):
     scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, ggxm, np.int32))), S.translate(-2.0, -2.8, -1.0) @ S.scale(1.2, 1.2, 1.2))
     lmesh = scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, emi0, np.int32)))
     mtx = S.translate(1.5, 0.5, 0.5) @ S.rotate_y(0.7) @ S.scale(0.8, 0.5, 0.6)
-    l0 = scn.add_mesh_light(lmesh, mtx, (12.0, 10.0, 6.0))
+    l0 = scn.add_mesh_light(lmesh, mtx, (12.0, 10.0, 6.0), tex_id=ltex)
     scn.add_instance(lmesh, mtx, light_id=l0)
     l1 = scn.add_light(M.area_light((0.0, 3.95, 0.0), (0.5, 0.5), (17.0, 15.0, 12.0)))
     scn.add_instance(scn.add_mesh(S.quad_mesh(0.5, 0.5, y=0.0, mat_id=emi1, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l1)
     return scn.build()
 
 
-def cornell_cylinder_light(width=96, height=96, second_table=False):
+def cornell_cylinder_light(width=96, height=96, second_table=False, textured=False):
     """The Cornell room lit by a CYLINDER light (a tilted three-quarter tube with its emissive mesh).  second_table: another pdf table comes
-    first, so that the light's table id is positive and the 2D-table branch of CylinderLightSamplePos runs instead of the uniform one."""
+    first, so that the light's table id is positive and the 2D-table branch of CylinderLightSamplePos runs instead of the uniform one.
+    textured: colour texture on the light (cylinderLightGetIntensity) and the pdf table of its luminance image, as the driver builds it."""
     from hydracore_b200 import materials as M
     scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
     scn.set_trace_depth(5, 3)
+    ltex, llum = _light_texture(scn) if textured else (0, None)
     white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
     red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
     green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
@@ -331,7 +398,7 @@ def cornell_cylinder_light(width=96, height=96, second_table=False):
     if second_table:
         scn.add_sky_pdf_table()
     mtx = S.translate(0.5, 1.5, 0.0) @ S.rotate_x(1.1) @ S.rotate_y(0.4)
-    l0 = scn.add_cylinder_light(mtx, 0.4, 3.0, 270.0, (14.0, 12.0, 9.0))
+    l0 = scn.add_cylinder_light(mtx, 0.4, 3.0, 270.0, (14.0, 12.0, 9.0), tex_id=ltex, tex_lum=llum)
     scn.add_instance(scn.add_mesh(S.cylinder_mesh(0.4, 3.0, 24, phi_max=np.radians(270.0), mat_id=emi0)), mtx, light_id=l0)
     return scn.build()
 
