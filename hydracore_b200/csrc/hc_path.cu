@@ -540,7 +540,6 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
     if (type == HC_PLAIN_LIGHT_TYPE_SKY_DOME)
     {
       int tab, aux; memcpy(&tab, L + 30, 4); memcpy(&aux, L + 20, 4);                  // SKY_DOME_PDF_TABLE0, SKY_DOME_COLOR_TEX_AUX (clight.h:138, 153)
-      if (flags & 1) { why = "Perez sky model (SKY_LIGHT_USE_PEREZ_ENVIRONMENT) is not supported yet"; return HC_E_ARG; }
       if (l != gi(HC_EG_skyLightId)) { why = "more than one sky-dome light"; return HC_E_ARG; }
       if (!ctx->storage[HC_STORAGE_PDFS].ptr || tab < 0 || tab >= gi(HC_EG_pdfTableTableSize)) { why = "sky-dome light without a pdf table in the pdfs storage"; return HC_E_ARG; }
       int so; memcpy(&so, L + HC_PLIGHT_COLOR_TEX_MATRIX, 4);                           // environment map: sampler at L + HC_SKY_DOME_SAMPLER0 (hc_shade.cuh)

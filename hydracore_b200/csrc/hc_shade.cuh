@@ -13,6 +13,7 @@
 #include "hc_layout.h"
 #include "hc_trace.cuh"
 #include "hc_microfacet.cuh"
+#include "hc_perez.cuh"
 
 #define HC_GEPSILON   5e-6f      // cglobals.h:68-70
 #define HC_DEPSILON   1e-20f
@@ -1339,6 +1340,11 @@ HC_DEV float3 SkyLightIntensityTexturedEnv(const float* L, float3 dir, const HcS
   float sintheta = 0.0f;
   const float2 tc = SphereMapTo2DTexCoord(dir, sintheta);
   const float3 texColor = Sample2D(__float_as_int(L[HC_PLIGHT_COLOR_TEX_MATRIX]), tc, L + HC_SKY_DOME_SAMPLER0, s);
+  if (__float_as_int(L[HC_PLIGHT_FLAGS]) & HC_SKY_LIGHT_USE_PEREZ_ENVIRONMENT)              // analytic sky + sun disk instead of the map (skyLightPerezColor, hc_perez.cuh)
+  {
+    const HcMf3 c = mfPerezSkyColor(ToMf(Mat3(L, HC_SKY_DOME_SUN_DIR_X)), L[HC_SKY_DOME_TURBIDITY], ToMf(Mat3(L, HC_SKY_SUN_COLOR_X)), ToMf(dir));
+    return Mat3(L, HC_PLIGHT_COLOR_X)*f3(c.x, c.y, c.z);
+  }
   return Mat3(L, HC_PLIGHT_COLOR_X)*texColor;
 }
 HC_DEV float EvalMap2DPdf(float2 t, const float* __restrict__ intervals, int sizeX, int sizeY)                                 // clight.h:309-337 (quirks included)

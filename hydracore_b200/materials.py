@@ -319,7 +319,7 @@ def direct_light(pos, direction, intensity, radius1, radius2, soft_angle_deg=0.0
     return L
 
 
-def sky_light(color, pdf_table_id, pick_prob=1.0, tex_id=None, gamma=1.0):
+def sky_light(color, pdf_table_id, pick_prob=1.0, tex_id=None, gamma=1.0, perez=None):
     """Sky-dome light, optionally textured (environment map), without the Perez model (SkyDomeLight, PlainLightConverter.cpp:909-1060):
     identity sampler matrices, the pdf table built by Scene.add_sky_pdf_table (from the map's luminance when textured)."""
     L = np.zeros(128, np.float32)
@@ -345,6 +345,12 @@ def sky_light(color, pdf_table_id, pick_prob=1.0, tex_id=None, gamma=1.0):
     for base in (56, 72):                             # SKY_DOME_INV_MATRIX0 / 1: identity float4x4 (columns)
         L[base:base + 16] = np.eye(4, dtype=np.float32).reshape(16)
     Li[88] = -1                                       # SKY_DOME_SUN_DIR_ID
+    if perez is not None:                             # <perez turbidity=...>: analytic sky, dict(sun_dir=(x, y, z) pointing AWAY from the sun, turbidity=t, sun_color=(r, g, b))
+        Li[C["PLIGHT_FLAGS"]] |= C["SKY_LIGHT_USE_PEREZ_ENVIRONMENT"]          # PlainLightConverter.cpp:920-923; sun direction / colour are filled by the driver from the sun light
+        d = np.asarray(perez["sun_dir"], np.float32)
+        L[C["SKY_DOME_SUN_DIR_X"]:C["SKY_DOME_SUN_DIR_X"] + 3] = d/np.linalg.norm(d)
+        L[C["SKY_DOME_TURBIDITY"]] = perez["turbidity"]
+        L[C["SKY_SUN_COLOR_X"]:C["SKY_SUN_COLOR_X"] + 3] = perez.get("sun_color", (1.0, 1.0, 1.0))
     if tex_id is not None:                            # PlainLightConverter.cpp:969-978: texture id for the pdf table builder, sampler at offset 0
         Li[C["PLIGHT_COLOR_TEX"]] = tex_id
         Li[C["PLIGHT_COLOR_TEX_MATRIX"]] = 0

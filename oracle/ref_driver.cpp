@@ -342,6 +342,19 @@ void ref_pbrt_microfacet(int kind, const float* wo3, const float* wi3, const flo
     }
   }
 }
+// skyLightPerezColor (clight.h:255-283) of a sky-dome light with the given sun direction, turbidity and sun colour, for n ray directions
+void ref_perez_sky(const float* sunDir3, float turbidity, const float* sunColor3, const float* dirs3, int n, float* out3)
+{
+  PlainLight L; memset(&L, 0, sizeof(L));
+  L.data[SKY_DOME_SUN_DIR_X] = sunDir3[0]; L.data[SKY_DOME_SUN_DIR_Y] = sunDir3[1]; L.data[SKY_DOME_SUN_DIR_Z] = sunDir3[2];
+  L.data[SKY_DOME_TURBIDITY] = turbidity;
+  L.data[SKY_SUN_COLOR_X] = sunColor3[0]; L.data[SKY_SUN_COLOR_Y] = sunColor3[1]; L.data[SKY_SUN_COLOR_Z] = sunColor3[2];
+  for (int i = 0; i < n; i++)
+  {
+    const float3 c = skyLightPerezColor(&L, make_float3(dirs3[3*i], dirs3[3*i + 1], dirs3[3*i + 2]));
+    out3[3*i] = c.x; out3[3*i + 1] = c.y; out3[3*i + 2] = c.z;
+  }
+}
 void ref_pbrt_erf(const float* x, int n, float* erfOut, float* erfInvOut)
 {
   for (int i = 0; i < n; i++) { erfOut[i] = ErfPBRT(x[i]); erfInvOut[i] = ErfInvPBRT(x[i]); }

@@ -8,7 +8,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from tests.test_microfacet import inputs, P          # noqa: E402
+from tests.test_microfacet import inputs, perez_inputs, _perez, P          # noqa: E402
 
 R = ct.CDLL(os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "libhydra_ref.so"))
 wo, wi, u, al, x = inputs(8192, 11)
@@ -20,5 +20,6 @@ for kind in (0, 1):
 e, ie = np.zeros_like(x), np.zeros_like(x)
 R.ref_pbrt_erf(P(x), x.size, P(e), P(ie))
 out["erf"], out["erfinv"] = e, ie
+out["perez"] = _perez(R, "ref", perez_inputs(2048, 3))
 np.savez_compressed(os.path.join(HERE, "microfacet.npz"), **out)
 print({k: v.shape for k, v in out.items()})

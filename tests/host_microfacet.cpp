@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE: the product header hydracore_b200/csrc/hc_microfacet.cuh compiled as plain C++ (it is pure arithmetic), behind the
 // same signatures as oracle/ref_driver.cpp's ref_pbrt_* so that tests/test_microfacet.py can compare the two on the CPU, bit for bit.
 #include "../hydracore_b200/csrc/hc_microfacet.cuh"
+#include "../hydracore_b200/csrc/hc_perez.cuh"
 
 template<int KIND>
 static void Run(const float* wo3, const float* wi3, const float* u2, const float* alpha2, int n, float* out8)
@@ -25,4 +26,12 @@ extern "C" void host_pbrt_microfacet(int kind, const float* wo3, const float* wi
 extern "C" void host_pbrt_erf(const float* x, int n, float* erfOut, float* erfInvOut)
 {
   for (int i = 0; i < n; i++) { erfOut[i] = mfErf(x[i]); erfInvOut[i] = mfErfInv(x[i]); }
+}
+extern "C" void host_perez_sky(const float* sunDir3, float turbidity, const float* sunColor3, const float* dirs3, int n, float* out3)
+{
+  for (int i = 0; i < n; i++)
+  {
+    const HcMf3 c = mfPerezSkyColor(mf3(sunDir3[0], sunDir3[1], sunDir3[2]), turbidity, mf3(sunColor3[0], sunColor3[1], sunColor3[2]), mf3(dirs3[3*i], dirs3[3*i + 1], dirs3[3*i + 2]));
+    out3[3*i] = c.x; out3[3*i + 1] = c.y; out3[3*i + 2] = c.z;
+  }
 }

@@ -439,7 +439,7 @@ def C_TEX_POINT_SAM():
     return C["TEX_POINT_SAM"]
 
 
-def open_box_under_sky(width=96, height=96, with_area_light=True, env_map=False):
+def open_box_under_sky(width=96, height=96, with_area_light=True, env_map=False, perez=False):
     """Objects on a floor under a uniform sky-dome light (plus, optionally, a rect area light): rays that leave the scene pick up the
     environment colour with MIS, the sky is sampled through its pdf table."""
     from hydracore_b200 import materials as M
@@ -471,7 +471,8 @@ def open_box_under_sky(width=96, height=96, with_area_light=True, env_map=False)
         scn.add_light(M.sky_light((1.0, 1.0, 1.0), tab, tex_id=tex))
     else:
         tab = scn.add_sky_pdf_table()
-        scn.add_light(M.sky_light((0.9, 1.0, 1.3), tab))
+        # perez: the analytic all-weather sky with a sun disk (SKY_LIGHT_USE_PEREZ_ENVIRONMENT) instead of a constant colour; uniform pdf table
+        scn.add_light(M.sky_light((0.9, 1.0, 1.3), tab, perez=dict(sun_dir=(0.35, -0.75, -0.55), turbidity=2.8, sun_color=(6.0, 5.5, 4.5)) if perez else None))
     if with_area_light:
         l1 = scn.add_light(M.area_light((0.0, 3.5, 0.0), (1.0, 1.0), (12.0, 11.0, 9.0)))
         scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi, flip=True)), S.translate(0.0, 3.5, 0.0), light_id=l1)

@@ -69,6 +69,33 @@ def _run(lib, prefix, wo, wi, u, al, x):
     return out
 
 
+def perez_inputs(n, seed):
+    rs = np.random.RandomState(seed)
+    d = rs.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    cases = []
+    for sun, turb in (((0.3, -0.8, 0.52), 2.5), ((0.0, -1.0, 0.0), 2.0), ((0.7, -0.1, 0.7), 6.0), ((0.5, 0.2, 0.84), 3.0)):
+        s = np.array(sun, np.float64)
+        s = (s/np.linalg.norm(s)).astype(np.float32)
+        dd = d.copy()
+        k = n//20
+        dd[:k] = -s + rs.normal(size=(k, 3))*0.02                          # directions into the sun disk
+        dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+        cases.append((s, np.float32(turb), np.array([1.0, 0.9, 0.7], np.float32), np.ascontiguousarray(dd.astype(np.float32))))
+    return cases
+
+
+def _perez(lib, prefix, cases):
+    f = getattr(lib, prefix + "_perez_sky")
+    f.argtypes = [ct.c_void_p, ct.c_float, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_void_p]
+    out = []
+    for s, turb, col, dd in cases:
+        a = np.zeros_like(dd)
+        f(P(s), float(turb), P(col), P(dd), dd.shape[0], P(a))
+        out.append(a)
+    return np.concatenate(out)
+
+
 def _same(a, b):
     return bool(((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all())
 
@@ -78,6 +105,8 @@ def test_microfacet_header_matches_golden_vectors(host):
     got = _run(host, "host", *inputs(8192, 11))
     for k in ("lobe0", "lobe1", "erf", "erfinv"):
         assert _same(got[k], want[k]), k
+    got_sky = _perez(host, "host", perez_inputs(2048, 3))
+    assert _same(got_sky, want["perez"]) and (want["perez"].max(1) > 1.5).sum() > 50 and want["perez"].mean() > 0.02      # sky colours, some inside the sun disk
     for k in ("lobe0", "lobe1"):                          # the vectors are not trivial: most BRDF / pdf values are positive, half vectors are unit
         assert (want[k][:, 0] > 0).mean() > 0.4 and (want[k][:, 1] > 0).mean() > 0.4
         assert np.allclose(np.linalg.norm(want[k][:, 2:5], axis=1), 1.0, atol=1e-5)
@@ -88,3 +117,5 @@ def test_microfacet_header_matches_live_reference(host, ref):
     got, want = _run(host, "host", *args), _run(ref.L, "ref", *args)
     for k in ("lobe0", "lobe1", "erf", "erfinv"):
         assert _same(got[k], want[k]), k
+    cases = perez_inputs(100000, 2)
+    assert _same(_perez(host, "host", cases), _perez(ref.L, "ref", cases))
