@@ -574,13 +574,32 @@ static int ValidateScene(hc_ctx* ctx, std::string& why)
       if (flags & HC_LIGHT_HAS_IES) { why = "IES distributions are not supported yet"; return HC_E_ARG; }
       continue;
     }
-    if (type == HC_PLAIN_LIGHT_TYPE_SPHERE || type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI)
+    // IES web: a single-channel float image in the pdfs storage, looked up by point and area lights (lightDistributionMask)
+    auto iesOk = [&]() -> bool
     {
-      if (flags & HC_LIGHT_HAS_IES) { why = "IES distributions are not supported yet"; return HC_E_ARG; }
+      int iesTex; memcpy(&iesTex, L + HC_IES_SPHERE_TEX_ID, 4);
+      if (!ctx->storage[HC_STORAGE_PDFS].ptr || iesTex < 0 || iesTex >= gi(HC_EG_pdfTableTableSize)) { why = "light with LIGHT_HAS_IES but no IES table in the pdfs storage"; return false; }
+      int off; memcpy(&off, gl.data() + (size_t(gi(HC_EG_pdfTableTableOffset)) + size_t(iesTex))*4, 4);
+      const size_t pdfBytes = ctx->storage[HC_STORAGE_PDFS].bytes;
+      if (off < 0 || size_t(off)*16 + 16 > pdfBytes) { why = "IES table outside the pdfs storage"; return false; }
+      int hdr[4] = { 0, 0, 0, 0 };                                          // the storage has no host mirror: read the 16-byte image header back (init time only)
+      if (cudaMemcpy(hdr, (const char*)ctx->storage[HC_STORAGE_PDFS].ptr + size_t(off)*16, 16, cudaMemcpyDeviceToHost) != cudaSuccess) { why = "IES table: header read-back failed"; return false; }
+      if (hdr[0] <= 0 || hdr[1] <= 0 || hdr[3] != 4 || size_t(off)*16 + 16 + size_t(hdr[0])*size_t(hdr[1])*4 > pdfBytes) { why = "IES table: expected a w x h single-channel float image"; return false; }
+      return true;
+    };
+    if (type == HC_PLAIN_LIGHT_TYPE_SPHERE)
+    {
+      if (flags & HC_LIGHT_HAS_IES) { why = "IES distributions on sphere lights are not supported yet (point and area lights are)"; return HC_E_ARG; }
+      continue;
+    }
+    if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI)
+    {
+      if ((flags & HC_LIGHT_HAS_IES) && !iesOk()) return HC_E_ARG;
       continue;
     }
     if (type != HC_PLAIN_LIGHT_TYPE_AREA) { why = "unknown light type (area, sphere, cylinder, mesh, point, spot, directional, sky-dome lights are supported)"; return HC_E_ARG; }
-    if (flags & (HC_LIGHT_HAS_IES | HC_AREA_LIGHT_SKY_PORTAL | HC_LIGHT_IES_POINT_AREA)) { why = "IES / sky-portal area lights are not supported yet"; return HC_E_ARG; }
+    if (flags & HC_AREA_LIGHT_SKY_PORTAL) { why = "sky-portal area lights are not supported yet"; return HC_E_ARG; }
+    if ((flags & HC_LIGHT_HAS_IES) && !iesOk()) return HC_E_ARG;
     if (tex != HC_INVALID_TEXTURE) { why = "textured area lights are not supported yet"; return HC_E_ARG; }
   }
   {

@@ -1197,8 +1197,23 @@ HC_DEV float AreaLightEvalPDF(const float* L, float3 rayDir, float hitDist)     
 {
   const float3 ln = Mat3(L, HC_PLIGHT_NORM_X);
   const float pdfA = 1.0f/fmaxf(L[HC_PLIGHT_SURFACE_AREA], HC_DEPSILON);
-  const float cosVal = fmaxf(dot(rayDir, -1.0f*ln), 0.0f);
+  const float cosVal = (__float_as_int(L[HC_PLIGHT_FLAGS]) & HC_LIGHT_HAS_IES) ? fabsf(dot(rayDir, -1.0f*ln)) : fmaxf(dot(rayDir, -1.0f*ln), 0.0f);   // an IES light shines to both sides
   return (pdfA*hitDist*hitDist)/fmaxf(cosVal, HC_DEPSILON2);
+}
+
+// ---- IES distributions (LIGHT_HAS_IES): the photometric web as a single-channel float image over the sphere, kept in the "pdfs" storage
+// (AddIesTexTableToStorage, RenderDriverRTE_PdfTables.cpp:385-475); lightDistributionMask (clight.h:465-483) looks it up along the light's own axes
+HC_DEV float2 SphereMapTo2DTexCoord(float3 rayDir, float& sinTheta);
+HC_DEV float3 Mat3x3MulVec(const float* M, float3 v);
+HC_DEV float3 LightDistributionMask(const float* L, float3 rayDir, const HcScene& s)
+{
+  if (!(__float_as_int(L[HC_PLIGHT_FLAGS]) & HC_LIGHT_HAS_IES)) return f3(1.0f, 1.0f, 1.0f);
+  rayDir = normalize(Mat3x3MulVec(L + HC_IES_LIGHT_MATRIX_E00, rayDir));
+  float sintheta = 0.0f;
+  const float2 tc = SphereMapTo2DTexCoord((-1.0f)*rayDir, sintheta);
+  const int offset = s.globals[s.pdfTableTableOffset + __float_as_int(L[HC_IES_SPHERE_TEX_ID])];
+  const float val = ReadImageSw1(reinterpret_cast<const int4*>(s.pdfs + offset), tc, HC_TEX_CLAMP_U | HC_TEX_CLAMP_V);
+  return f3(val, val, val);
 }
 
 // areaSpotLightAttenuation (clight.h:7-12, 532-539): smoothstep between the two cone cosines about the light's normal
@@ -1210,12 +1225,17 @@ HC_DEV float AreaSpotAttenuation(const float* L, float3 shadowRayDir)
   const float t = fminf(fmaxf(tVal, 0.0f), 1.0f);
   return t*t*(3.0f - 2.0f*t);
 }
-// areaDiffuseLightGetIntensity (clight.h:542-611) for untextured lights without IES / sky portal: base colour, cut by the spot cone for light
+// areaDiffuseLightGetIntensity (clight.h:542-611) for untextured lights that are no sky portals: base colour, cut by the spot cone for light
 // samples and GI hits; an EYE ray that hits a spot-distributed light sees it white (colour / its largest component), as the reference draws it
-HC_DEV float3 AreaLightIntensity(const float* L, float3 rayDir, bool eyeRay)
+HC_DEV float3 AreaLightIntensity(const float* L, float3 rayDir, bool eyeRay, const HcScene& s)
 {
   float3 color = Mat3(L, HC_PLIGHT_COLOR_X);
-  if (__float_as_int(L[HC_AREA_LIGHT_SPOT_DISTR]) != 0)
+  if (__float_as_int(L[HC_PLIGHT_FLAGS]) & HC_LIGHT_HAS_IES)                              // takes precedence over the spot cone (clight.h:560-574)
+  {
+    if (!eyeRay) color *= LightDistributionMask(L, rayDir, s);
+    else color *= (1.0f/fmaxf(color.x, fmaxf(color.y, color.z)));
+  }
+  else if (__float_as_int(L[HC_AREA_LIGHT_SPOT_DISTR]) != 0)
   {
     if (!eyeRay) color *= clampf(AreaSpotAttenuation(L, (-1.0f)*rayDir), 0.0f, 1.0f);
     else color *= (1.0f/fmaxf(color.x, fmaxf(color.y, color.z)));
@@ -1223,7 +1243,7 @@ HC_DEV float3 AreaLightIntensity(const float* L, float3 rayDir, bool eyeRay)
   return color;
 }
 // AreaLightSampleRev (clight.h:1180-1229), untextured, no IES / sky portal (rejected at init)
-HC_DEV void AreaLightSampleRev(const float* L, float3 rands, float3 illum, HcShadowSample& out)
+HC_DEV void AreaLightSampleRev(const float* L, float3 rands, float3 illum, const HcScene& s, HcShadowSample& out)
 {
   const float ox = rands.x*2.0f - 1.0f, oy = rands.y*2.0f - 1.0f;
   float3 sp = f3(ox*L[HC_AREA_LIGHT_SIZE_X], 0.0f, oy*L[HC_AREA_LIGHT_SIZE_Y]);
@@ -1246,7 +1266,9 @@ HC_DEV void AreaLightSampleRev(const float* L, float3 rands, float3 illum, HcSha
   const float3 ln = Mat3(L, HC_PLIGHT_NORM_X);
   out.isPoint = false;
   out.pos = sp + epsilonOfPos(sp)*ln;
-  out.color = AreaLightIntensity(L, rayDir, false);
+  float3 customRayDir = rayDir;                                                          // LIGHT_IES_POINT_AREA: the web is looked up from the light's centre
+  if (__float_as_int(L[HC_PLIGHT_FLAGS]) & HC_LIGHT_IES_POINT_AREA) customRayDir = normalize(Mat3(L, HC_PLIGHT_POS_X) - illum);
+  out.color = AreaLightIntensity(L, customRayDir, false, s);
   out.pdf = AreaLightEvalPDF(L, rayDir, hitDist);
   out.maxDist = hitDist;
   out.cosAtLight = -dot(rayDir, ln);
@@ -1290,13 +1312,13 @@ HC_DEV void SphereLightSampleRev(const float* L, float3 rands, float3 illum, HcS
   out.cosAtLight = fabsf(dot(lightNorm, dirToV));
 }
 
-HC_DEV void PointLightSampleRev(const float* L, float3 illum, HcShadowSample& out)                                         // clight.h:1394-1407, no IES
+HC_DEV void PointLightSampleRev(const float* L, float3 illum, const HcScene& s, HcShadowSample& out)                      // clight.h:1394-1407
 {
   const float3 samplePos = Mat3(L, HC_PLIGHT_POS_X);
   const float hitDist = length(samplePos - illum);
   out.isPoint = true;
   out.pos = samplePos;
-  out.color = f3(1.0f, 1.0f, 1.0f)*Mat3(L, HC_PLIGHT_COLOR_X);                           // lightDistributionMask = (1,1,1) without LIGHT_HAS_IES
+  out.color = LightDistributionMask(L, normalize(samplePos - illum), s)*Mat3(L, HC_PLIGHT_COLOR_X);      // pointLightGetIntensity: (1,1,1) without LIGHT_HAS_IES
   out.pdf = PdfAtoW(1.0f, hitDist, 1.0f);
   out.maxDist = hitDist;
   out.cosAtLight = 1.0f;
@@ -1626,12 +1648,12 @@ HC_DEV void LightSampleRev(const float* L, float3 rands, float3 illum, const HcS
   const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
   if (type == HC_PLAIN_LIGHT_TYPE_SKY_DOME) SkyLightSampleRev(L, rands, illum, s, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_SPHERE) SphereLightSampleRev(L, rands, illum, out);
-  else if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI) PointLightSampleRev(L, illum, out);
+  else if (type == HC_PLAIN_LIGHT_TYPE_POINT_OMNI) PointLightSampleRev(L, illum, s, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_POINT_SPOT) SpotLightSampleRev(L, illum, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_DIRECT) DirectLightSampleRev(L, rands, illum, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_MESH) MeshLightSampleRev(L, rands, illum, s, out);
   else if (type == HC_PLAIN_LIGHT_TYPE_CYLINDER) CylinderLightSampleRev(L, rands, illum, s, out);
-  else AreaLightSampleRev(L, rands, illum, out);
+  else AreaLightSampleRev(L, rands, illum, s, out);
 }
 
 HC_DEV float LightEvalPDF(const float* L, float3 illum, float3 rayDir, float3 lpos, float3 lnorm, float2 texCoord, const HcScene& s)
@@ -1653,14 +1675,20 @@ HC_DEV float3 EmissionEval(const HcScene& s, float3 rayPos, float3 rayDir, const
   const float* L = (s.lightsNum > 0) ? LightAt(s, s.instLightIds[instId]) : nullptr;
   const float* mat = MaterialAt(s, sh.matId);
   const float3 normal = sh.hfi ? (-1.0f)*sh.normal : sh.normal;
-  if (dot(rayDir, normal) >= 0.0f) return f3(0, 0, 0);
+  const bool hasIES = (L != nullptr) && (__float_as_int(L[HC_PLIGHT_FLAGS]) & HC_LIGHT_HAS_IES) != 0;     // a light with a photometric web emits from its back side too
+  if (dot(rayDir, normal) >= 0.0f && !hasIES) return f3(0, 0, 0);
   float3 outColor = MaterialEvalEmission(mat, rayDir, normal, sh.texCoord, s);
   if ((MatI(mat, HC_PLAIN_MAT_FLAGS_OFFSET) & HC_PLAIN_MATERIAL_FORBID_EMISSIVE_GI) && (flags & 0xFFu) > 0) outColor = f3(0, 0, 0);
   if (s.lightsNum > 0 && L != nullptr)                                                  // lightGetIntensity (clight.h:1661-1706): base colour, times the light's texture
   {                                                                                     // at the hit's texture coordinates for cylinder and mesh lights
     outColor = Mat3(L, HC_PLIGHT_COLOR_X);
     const int type = __float_as_int(L[HC_PLIGHT_TYPE]);
-    if (type == HC_PLAIN_LIGHT_TYPE_AREA) outColor = AreaLightIntensity(L, rayDir, (flags & 0xFFu) == 0);       // eyeRay: no diffuse bounce so far
+    if (type == HC_PLAIN_LIGHT_TYPE_AREA)
+    {
+      float3 customDir = rayDir;
+      if (__float_as_int(L[HC_PLIGHT_FLAGS]) & HC_LIGHT_IES_POINT_AREA) customDir = normalize(Mat3(L, HC_PLIGHT_POS_X) - rayPos);
+      outColor = AreaLightIntensity(L, customDir, (flags & 0xFFu) == 0, s);                 // eyeRay: no diffuse bounce so far
+    }
     else if (type == HC_PLAIN_LIGHT_TYPE_CYLINDER) outColor = Sample2D(__float_as_int(L[HC_CYLINDER_TEXMATRIX_ID]), sh.texCoord, L, s)*outColor;
     else if (type == HC_PLAIN_LIGHT_TYPE_MESH) outColor = Sample2D(__float_as_int(L[HC_MESH_LIGHT_TEXMATRIX_ID]), sh.texCoord, L, s)*outColor;
   }

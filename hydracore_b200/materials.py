@@ -291,6 +291,20 @@ def point_light(pos, intensity, pick_prob=1.0):
     return L
 
 
+def with_ies(L, tex_table_id, pdf_table_id=None, matrix=None, point_area=False):
+    """IES photometric web on a point or area light (LIGHT_HAS_IES; PlainLightConverter.cpp:255-270, 676-694): ids of the web image and of its pdf
+    table in the "pdfs" storage (Scene.add_ies_table), the light's rotation for the look-up (IES_LIGHT_MATRIX, rows) and its inverse;
+    point_area: LIGHT_IES_POINT_AREA - an area light looks the web up from its centre."""
+    Li = L.view(np.int32)
+    Li[C["PLIGHT_FLAGS"]] |= C["LIGHT_HAS_IES"] | (C["LIGHT_IES_POINT_AREA"] if point_area else 0)
+    Li[C["IES_SPHERE_TEX_ID"]] = tex_table_id
+    Li[C["IES_SPHERE_PDF_ID"]] = tex_table_id if pdf_table_id is None else pdf_table_id
+    R = np.eye(3, dtype=np.float32) if matrix is None else np.asarray(matrix, np.float32).reshape(3, 3)
+    L[C["IES_LIGHT_MATRIX_E00"]:C["IES_LIGHT_MATRIX_E00"] + 9] = R.reshape(9)
+    L[C["IES_INV_MATRIX_E00"]:C["IES_INV_MATRIX_E00"] + 9] = np.linalg.inv(R.astype(np.float64)).astype(np.float32).reshape(9)
+    return L
+
+
 def spot_light(pos, direction, intensity, falloff_angle, falloff_angle2):
     """Spot light (SpotLight + CreatePointSpotLightFromXmlNode, PlainLightConverter.cpp:568-626, 895-906): cone angles in degrees, full
     intensity inside falloff_angle2 (cos1), smooth fall-off to zero at falloff_angle (cos2).  `direction` is the light's axis."""

@@ -454,6 +454,18 @@ class Scene:
         self.pdf_tables.append(data)
         return len(self.pdf_tables) - 1
 
+    def add_ies_table(self, web):
+        """IES photometric web as AddIesTexTableToStorage stores it (RenderDriverRTE_PdfTables.cpp:385-443): single-channel float image over the
+        sphere, normalised to its maximum, behind an image header {w, h, 1, 4}; returns its table id in the "pdfs" storage."""
+        web = np.ascontiguousarray(web, np.float32)
+        h, w = web.shape
+        web = (web*(np.float32(1.0)/web.max())).astype(np.float32)
+        data = np.zeros(web.size + 5, np.float32)
+        data[0:4] = np.array([w, h, 1, 4], np.int32).view(np.float32)
+        data[4:4 + web.size] = web.reshape(-1)
+        self.pdf_tables.append(data)
+        return len(self.pdf_tables) - 1
+
     def add_texture_rgba8(self, rgba):
         """Texture ids start at 1; id 0 means "white" (sample2D, cfetch.h:654-655)."""
         rgba = np.ascontiguousarray(rgba, np.uint8)

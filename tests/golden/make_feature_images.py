@@ -19,7 +19,8 @@ FEATURES = {"orennayar": lambda: scenes.cornell_orennayar(W, H), "sphere_point":
             "cylinder_light": lambda: scenes.cornell_cylinder_light(W, H, True), "sky": lambda: scenes.open_box_under_sky(W, H, True),
             "sky_env": lambda: scenes.open_box_under_sky(W, H, False, env_map=True), "anisotropic": lambda: scenes.cornell_anisotropic(W, H),
             "mesh_light_tex": lambda: scenes.cornell_mesh_light(W, H, True), "cylinder_light_tex": lambda: scenes.cornell_cylinder_light(W, H, True, True),
-            "area_spot": lambda: scenes.cornell_area_spot(W, H), "perez_sky": lambda: scenes.open_box_under_sky(W, H, False, perez=True)}
+            "area_spot": lambda: scenes.cornell_area_spot(W, H), "perez_sky": lambda: scenes.open_box_under_sky(W, H, False, perez=True),
+            "ies": lambda: scenes.cornell_ies(W, H)}
 
 
 def main():

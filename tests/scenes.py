@@ -215,6 +215,34 @@ def cornell_area_spot(width=96, height=96):
     return scn.build()
 
 
+def cornell_ies(width=96, height=96):
+    """The Cornell room lit through IES photometric webs (LIGHT_HAS_IES): an omni point light, a rect area light that looks the web up per sample
+    and a tilted disk light that looks it up from its centre (LIGHT_IES_POINT_AREA); the area lights have emissive meshes (eye rays see them white)."""
+    from hydracore_b200 import materials as M
+    scn = S.Scene(width, height, S.Camera(pos=(0, 0, 14.0), look_at=(0, 0, 0), fov=45))
+    scn.set_trace_depth(5, 3)
+    yy, xx = np.mgrid[0:16, 0:32]
+    web = (0.15 + np.cos(np.pi*yy/15.0)**2*(0.6 + 0.4*np.cos(2.0*np.pi*xx/32.0*3))).astype(np.float32)      # three lobes around the axis
+    ies = scn.add_ies_table(web)
+    ies2 = scn.add_ies_table(web[::-1, :]*np.float32(0.5) + np.float32(0.1))
+    white = scn.add_material(M.lambert((0.73, 0.73, 0.73)))
+    red = scn.add_material(M.lambert((0.65, 0.05, 0.05)))
+    green = scn.add_material(M.lambert((0.12, 0.45, 0.15)))
+    ggxm = scn.add_material(M.ggx((0.8, 0.6, 0.2), 0.7))
+    emi0 = scn.add_material(M.emissive((20.0, 18.0, 14.0), 1))
+    emi1 = scn.add_material(M.emissive((8.0, 11.0, 18.0), 2))
+    scn.add_instance(scn.add_mesh(S.box_mesh(4.0, 4.0, 4.0, mat_ids=(green, red, white, white, white, white), inward=True, skip_faces=(4,))))
+    sph = S.sphere_mesh(1.0, 32, 16)
+    scn.add_instance(scn.add_mesh(S.Mesh(sph.pos, sph.idx, norm=sph.norm, uv=sph.uv, mat=np.full(sph.tri_count, ggxm, np.int32))), S.translate(-2.0, -2.8, -1.0) @ S.scale(1.2, 1.2, 1.2))
+    scn.add_light(M.with_ies(M.point_light((2.0, 1.0, 1.5), (60.0, 50.0, 40.0)), ies, matrix=S.rotate_x(0.5)[:3, :3]))
+    l1 = scn.add_light(M.with_ies(M.area_light((0.0, 3.95, 0.0), (1.0, 1.0), (20.0, 18.0, 14.0)), ies2))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(1.0, 1.0, y=0.0, mat_id=emi0, flip=True)), S.translate(0.0, 3.95, 0.0), light_id=l1)
+    R = S.rotate_x(0.6)[:3, :3]
+    l2 = scn.add_light(M.with_ies(M.area_light((-3.0, 2.0, 1.0), (0.6, 0.6), (8.0, 11.0, 18.0), rotation=R, disk=True), ies, matrix=R, point_area=True))
+    scn.add_instance(scn.add_mesh(S.quad_mesh(0.6, 0.6, y=0.0, mat_id=emi1, flip=True)), S.translate(-3.0, 2.0, 1.0) @ S.rotate_x(0.6), light_id=l2)
+    return scn.build()
+
+
 def cornell_sphere_and_point_lights(width=96, height=96):
     """The Cornell room lit by a sphere area light (with its emissive mesh, so that paths can hit it) and an omni point light."""
     from hydracore_b200 import materials as M
