@@ -442,8 +442,8 @@ def run_ours(args):
             scn3 = build()
             lay = hc.CudaLayer(device=local)
             # sample streams: S generators per pixel, pass p draws from stream p mod S, so a rank that owns 1/G of the tiles keeps up to S passes in
-            # flight as one wavefront.  The image depends on (seed, S) only, so S is the SAME at every N (at N=1 a 1080p pass fills the wavefront alone
-            # and the streams are simply taken in turn).  C1 keeps the single-generator rule its 64 spp parity test is stated on; c1_streams8 shows the other.
+            # flight as one wavefront (up to 8M paths by default: four 1080p passes on one GPU, all eight from two GPUs on).  The image depends on
+            # (seed, S) only, so S is the SAME at every N.  C1 keeps the single-generator rule its 64 spp parity test is stated on; c1_streams8 shows the other.
             streams = {"c1": 1, "c5": 1}.get(key, 8)
             lay.SetSampleStreams(streams)
             lay.LoadScene(scn3)

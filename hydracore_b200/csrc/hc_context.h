@@ -63,7 +63,7 @@ struct hc_ctx
   float    lastTraceMs = 0.0f;
   int      lastGroupPasses = 1;            // passes the last wavefront of hc_pt_pass carried (sample streams)
   int      sampleStreams = 1;              // generators per pixel (hc_pt_set_sample_streams)
-  int64_t  maxPathsInFlight = 0;           // 0: max(W*H, 2M)
+  int64_t  maxPathsInFlight = 0;           // 0: max(W*H, 8M)
 
   // path tracing
   void*    pathHost = nullptr;             // HcPathHost (hc_path.cu): double-buffered SoA path state, hit / visibility buffers, tile ownership

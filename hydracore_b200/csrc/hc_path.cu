@@ -826,8 +826,10 @@ int hc_pt_group_passes(hc_ctx* ctx, int* outPasses)
   HC_REQUIRE(ctx->ptReady && p, HC_E_STATE, "hc_pt_group_passes: call hc_pt_init first");
   if (p->nOwned <= 0) { *outPasses = 1; return HC_OK; }                          // a rank without pixels (more ranks than tiles): its passes are empty
   const int64_t frame = int64_t(ctx->width)*ctx->height;
-  // default limit: what a single GPU keeps in flight for this frame anyway, and at least 2M paths (below that a launch is latency-bound)
-  const int64_t cap = ctx->maxPathsInFlight > 0 ? ctx->maxPathsInFlight : std::max<int64_t>(frame, int64_t(1) << 21);
+  // default limit: 8M paths (4 GB of path queue), or one pass of the frame if that is more.  Below 2M paths a launch is latency-bound;
+  // beyond that the late bounces still gain from launching over more live paths (scripts/gpu_streams_cap.py, 1080p, 1 / 2 / 4 / 8 passes in
+  // flight: C3 6.81 / 6.20 / 5.92 / 5.78 ms per pass, C4 6.33 / 6.03 / 5.86 / 5.78)
+  const int64_t cap = ctx->maxPathsInFlight > 0 ? ctx->maxPathsInFlight : std::max<int64_t>(frame, int64_t(1) << 23);
   int m = int(std::min<int64_t>(ctx->sampleStreams, std::max<int64_t>(1, cap/p->nOwned)));
   if (frame > (int64_t(1) << 24) || ctx->sampleStreams > 64) m = 1;              // the sub-pass index shares the path's pixel word (7 bits above 24)
   *outPasses = std::max(1, m);

@@ -127,7 +127,7 @@ int hc_pt_set_sample_streams(hc_ctx* ctx, int streams, int64_t maxPathsInFlight)
                                                                                  (seed, S) only, not on how many passes shared a wavefront, the tile split or the GPU count.
                                                                                  The OpenCL layer has the same degree of freedom: one RandomGen per slot of its ray block,
                                                                                  randGenState[MEGABLOCKSIZE] (GPUOCLLayer.cpp:131), whatever the frame size.
-                                                                                 maxPathsInFlight: 0 = max(W*H, 2M).  Call before hc_pt_init.                                 */
+                                                                                 maxPathsInFlight: 0 = max(W*H, 8M).  Call before hc_pt_init.                                 */
 int hc_pt_group_passes(hc_ctx* ctx, int* outPasses);                         /* passes one wavefront carries with the current streams / tiles / limit (after hc_pt_init)    */
 int hc_pt_pass(hc_ctx* ctx, int integrator, int passes);                     /* BeginTracingPass+EndTracingPass, IHWLayer.h:133-134         */
 int hc_fb_clear(hc_ctx* ctx);                                                /* ClearAccumulatedColor, IHWLayer.h:140                       */
