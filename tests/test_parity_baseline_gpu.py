@@ -28,16 +28,20 @@ def _tiles(width, height, count, seed, size=32):
     return out
 
 
-def _compare_tiles(layer, ref, scn, integrator, ref_kind, passes, tiles, seed=777):
-    layer.LoadScene(scn)
-    layer.InitPathTracing(seed)
-    layer.TracingPass(integrator, passes)
-    got = layer.GetHDRImage()[..., :3]*np.float32(passes)
+def _compare_tiles(layer, ref, scn, integrator, ref_kind, passes, tiles, seed=777, streams=1):
+    layer.SetSampleStreams(streams)
+    try:
+        layer.LoadScene(scn)
+        layer.InitPathTracing(seed)
+        layer.TracingPass(integrator, passes)
+        got = layer.GetHDRImage()[..., :3]*np.float32(passes)
+    finally:
+        layer.SetSampleStreams(1)
     rs = ref.scene(scn)
     worst, close_frac, lit = 0.0, 1.0, 0
     try:
         for (x0, y0, x1, y1) in tiles:
-            want, npass = rs.render(ref_kind, seed, passes, window=(x0, y0, x1, y1))
+            want, npass = rs.render(ref_kind, seed, passes, window=(x0, y0, x1, y1), streams=streams)
             assert npass == passes
             w, g = want[y0:y1, x0:x1, :3], got[y0:y1, x0:x1]
             assert np.isfinite(g).all()
@@ -76,6 +80,15 @@ def test_c3_full_size_tiles_vs_reference(layer, ref):
     scn = S.scene_c3(1920, 1080)
     worst, close, lit = _compare_tiles(layer, ref, scn, MISPT, 2, 2, _tiles(1920, 1080, 8, 5))
     assert lit >= 6 and close >= 0.999 and worst <= 1e-4, (worst, close, lit)
+
+
+def test_c3_full_size_with_sample_streams_vs_reference(layer, ref):
+    """C3 at 1080p with 8 sample streams, 8 passes: two wavefronts of four passes each (8.3 M paths in flight, material sort on) against the reference
+    integrator driven with the same stream rule, on six scattered tiles - the configuration bench.py times."""
+    from hydracore_b200 import scene as S
+    scn = S.scene_c3(1920, 1080)
+    worst, close, lit = _compare_tiles(layer, ref, scn, MISPT, 2, 8, _tiles(1920, 1080, 6, 21), streams=8)
+    assert lit >= 4 and close >= 0.999 and worst <= 1e-4, (worst, close, lit)
 
 
 def test_c4_full_size_tiles_vs_reference(layer, ref):
