@@ -444,7 +444,7 @@ def run_ours(args):
             # sample streams: S generators per pixel, pass p draws from stream p mod S, so a rank that owns 1/G of the tiles keeps up to S passes in
             # flight as one wavefront (up to 8M paths by default: four 1080p passes on one GPU, all eight from two GPUs on).  The image depends on
             # (seed, S) only, so S is the SAME at every N.  C1 keeps the single-generator rule its 64 spp parity test is stated on; c1_streams8 shows the other.
-            streams = {"c1": 1, "c5": 1}.get(key, 8)
+            streams = {"c1": 1}.get(key, 8)
             lay.SetSampleStreams(streams)
             lay.LoadScene(scn3)
             integ = {"c1": 0, "c1_streams8": 0, "c5": 3}.get(key, 2)     # C1: unidirectional PT (INTEGRATOR_PT = 0); C3 / C4: MISPT (= 2); C5: MISPT-QMC (= 3)

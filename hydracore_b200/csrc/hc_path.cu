@@ -82,9 +82,11 @@ k_pt_generate(const HcCamera cam, const HcPassParams pp, const int n, const int 
   HcRng g;
   if (pp.integrator == HC_INTEGRATOR_MISPT_QMC)
   {
-    const int sample = i*pp.world + pp.rank;                      // this GPU's share of the sample indices of the pass
-    const uint2 s2 = pixelRng[sample]; g.x = s2.x; g.y = s2.y;
-    qpos = pp.qmcPass*(unsigned)(pp.width*pp.height) + (unsigned)sample;
+    const int sub = (pp.groupPasses > 1) ? i / pp.nOwned : 0;     // sample streams: sub-pass major, as for PT / MISPT
+    const int sample = (i - sub*pp.nOwned)*pp.world + pp.rank;    // this GPU's share of the sample indices of the pass
+    const uint2 s2 = pixelRng[size_t((pp.streamBase + sub) % pp.streams)*size_t(pp.width*pp.height) + sample]; g.x = s2.x; g.y = s2.y;
+    qpos = (pp.qmcPass + (unsigned)sub)*(unsigned)(pp.width*pp.height) + (unsigned)sample;
+    subBits = (unsigned)sub << pp.subShift;
     float4 lens;
     lens.y = rndQmcTab(g, rmQMC, qpos, HC_QMC_VAR_SCR_Y, qmcTable);
     lens.z = rndQmcTab(g, rmQMC, qpos, HC_QMC_VAR_DOF_X, qmcTable);
@@ -165,8 +167,8 @@ k_pt_shade(const HcScene s, const HcPassParams pp, const int* __restrict__ nIn, 
     const bool prevSpecular = (pixSpec & 0x80000000u) != 0;
     const float prevPdf = rp.w;
     const size_t frame = size_t(pp.width*pp.height);
-    const size_t rngSlot = (pp.integrator == HC_INTEGRATOR_MISPT_QMC) ? size_t(qpos - pp.qmcPass*(unsigned)(pp.width*pp.height))
-                                                                       : size_t((pp.streamBase + sub) % pp.streams)*frame + size_t(pixel);
+    const size_t rngSlot = size_t((pp.streamBase + sub) % pp.streams)*frame +                                 // QMC: one generator per SAMPLE index of the stream
+                           ((pp.integrator == HC_INTEGRATOR_MISPT_QMC) ? size_t(qpos - (pp.qmcPass + (unsigned)sub)*(unsigned)(pp.width*pp.height)) : size_t(pixel));
     thr = f3(th); accum = f3(ac);
 
     // pending direct light of the previous bounce: accumColor += accumuThoroughput*explicitColor (PT_Loop.cpp:253), shadow in {0,1}
@@ -876,14 +878,21 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
   const int nPerPass = qmc ? ((W*H - ctx->rank + ctx->worldSize - 1)/ctx->worldSize) : p->nOwned;
   if (nPerPass <= 0) return HC_OK;
   // sample streams: up to `groupMax` consecutive passes share one wavefront (hc_pt_group_passes)
-  const int S = qmc ? 1 : std::max(1, ctx->sampleStreams);
+  const int S = std::max(1, ctx->sampleStreams);
   int groupMax = 1; { int rcg = hc_pt_group_passes(ctx, &groupMax); if (rcg) return rcg; }
-  if (qmc) groupMax = 1;
+  if (qmc)                                                       // QMC splits SAMPLE indices over the ranks, not tiles: its own pass size
+  {
+    const int64_t frame = int64_t(W)*H;
+    const int64_t cap = ctx->maxPathsInFlight > 0 ? ctx->maxPathsInFlight : std::max<int64_t>(frame, int64_t(1) << 23);
+    groupMax = (frame > (int64_t(1) << 24)) ? 1 : int(std::min<int64_t>(S, std::max<int64_t>(1, cap/nPerPass)));
+  }
   groupMax = std::max(1, std::min(groupMax, passes));
   int n = nPerPass*groupMax;                                    // paths of the wavefront being enqueued (set per group below)
   int rc = ReserveState(ctx, n, qmc); if (rc) return rc;
   p = PH(ctx);
-  if (groupMax > 1 && (rc = hc_buf_reserve(ctx, p->subSums, uint64_t(groupMax)*uint64_t(W)*uint64_t(H)*16))) return rc;
+  // per-sub-pass sums (PT / MISPT: one path per pixel and sub-pass, folded in pass order).  QMC paths land on arbitrary pixels and add with float
+  // atomics in any case, so they go straight into the frame
+  if (groupMax > 1 && !qmc && (rc = hc_buf_reserve(ctx, p->subSums, uint64_t(groupMax)*uint64_t(W)*uint64_t(H)*16))) return rc;
   HcScene scn = MakeScene(ctx);
   if (integrator == HC_INTEGRATOR_PT) scn.gflags |= HC_HRT_STUPID_PT_MODE;          // IntegratorStupidPT::DoPass sets it in g_flags (CPUExp_Integrators.h:326-330)
   const HcCamera cam = hc_camera_from_globals(ctx->globalsHead.data());
@@ -1038,7 +1047,7 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
       HC_CUDA(cudaEventRecord(ctx->evPipeJoin, ctx->stream2));
       HC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evPipeJoin, 0));
     }
-    if (pp.groupPasses > 1)
+    if (pp.groupPasses > 1 && !qmc)
     {
       HC_STAGE(3, (k_fb_fold<<<(nPerPass + 255)/256, 256, 0, ctx->stream>>>((float4*)ctx->fbSum.ptr, subSums, (const int*)p->owned.ptr, nPerPass, pp.groupPasses, size_t(W)*size_t(H))));
       HC_CUDA(cudaGetLastError());
@@ -1059,7 +1068,7 @@ int hc_pt_pass(hc_ctx* ctx, int integrator, int passes)
     pp.qmcPass = ctx->passCounter;
     pp.streamBase = int(ctx->passCounter % (unsigned)S);
     pp.groupPasses = m;
-    if (m > 1) { pp.pixMask = 0x00FFFFFFu; pp.subShift = 24; subSums = (float4*)p->subSums.ptr; }
+    if (m > 1) { pp.pixMask = 0x00FFFFFFu; pp.subShift = 24; subSums = qmc ? nullptr : (float4*)p->subSums.ptr; }
     else       { pp.pixMask = 0x7FFFFFFFu; pp.subShift = 31; subSums = nullptr; }
     n = nPerPass*m;
     lastGroup = m;

@@ -125,6 +125,8 @@ int hc_pt_set_sample_streams(hc_ctx* ctx, int streams, int64_t maxPathsInFlight)
                                                                                  flight as ONE wavefront (small frames, or a GPU that owns 1/G of the tiles, no longer run
                                                                                  latency-bound launches); their sums are added to the frame in pass order, so the image depends on
                                                                                  (seed, S) only, not on how many passes shared a wavefront, the tile split or the GPU count.
+                                                                                 MISPT-QMC: one generator per SAMPLE index and stream, the Sobol index keeps running over
+                                                                                 pass*W*H + sample; its samples add with float atomics, so groupings agree to rounding only.
                                                                                  The OpenCL layer has the same degree of freedom: one RandomGen per slot of its ray block,
                                                                                  randGenState[MEGABLOCKSIZE] (GPUOCLLayer.cpp:131), whatever the frame size.
                                                                                  maxPathsInFlight: 0 = max(W*H, 8M).  Call before hc_pt_init.                                 */

@@ -160,7 +160,7 @@ namespace
         #pragma omp atomic
         d.z += c.z;
       }
-      passes++;
+      NextPass();
     }
     const unsigned int* QmcTable() const { return (const unsigned int*)this->m_tableQMC; }
   };
@@ -453,6 +453,7 @@ void ref_render_set_streams(void* p, int S)
   if (r->kind == 0) r->pt->SetStreams(S);
   else if (r->kind == 1) r->mis->SetStreams(S);
   else if (r->kind == 2) r->loop->SetStreams(S);
+  else r->qmc->SetStreams(S);
 }
 
 void ref_render_pass(void* p, int x0, int y0, int x1, int y1)

@@ -10,7 +10,7 @@ import pytest
 from tests import scenes
 
 pytestmark = pytest.mark.gpu
-MISPT, PT = 2, 0
+MISPT, PT, QMC = 2, 0, 3
 
 
 def _rel_rmse(a, b):
@@ -77,6 +77,40 @@ def test_first_pass_of_any_stream_count_is_the_single_generator_rule(layer):
         assert np.array_equal(a, b)
     finally:
         layer.SetSampleStreams(1)
+
+
+def test_qmc_streams_match_the_reference_and_do_not_depend_on_the_grouping(layer, ref):
+    """MISPT-QMC with sample streams: one generator per SAMPLE index and stream, the Sobol index still runs over pass * W * H + sample, so passes of a
+    stream cycle are independent here as well.  Samples land on arbitrary pixels and add with float atomics (order-dependent rounding), hence tolerances:
+    1e-3 against the reference integrator with the same stream rule (as for one stream), 1e-5 between groupings and the emulated sample partition."""
+    scn = scenes.cornell(96, 64, two_lights=True, dof=True)
+    n = 96*64
+    try:
+        a = _sum(layer, scn, QMC, 6, 11, 4)                               # wavefronts of 4 and 2 passes
+        b = _sum(layer, scn, QMC, 6, 11, 4, limit=n)                      # one pass per wavefront
+        c = _sum(layer, scn, QMC, 6, 11, 4, calls=[1, 3, 2])
+        assert _rel_rmse(b, a) <= 1e-5 and _rel_rmse(c, a) <= 1e-5
+        total = np.zeros_like(a)
+        for r in range(3):                                                # sample indices i = r (mod 3)
+            layer.SetTiles(32, r, 3)
+            layer.SetSampleStreams(4)
+            layer.LoadScene(scn)
+            layer.InitPathTracing(11)
+            layer.TracingPass(QMC, 6)
+            total += layer.GetSumImage()[..., :3]
+        layer.SetTiles(32, 0, 1)
+        assert _rel_rmse(total, a) <= 1e-5
+        one = _sum(layer, scn, QMC, 6, 11, 1)
+    finally:
+        layer.SetTiles(32, 0, 1)
+        layer.SetSampleStreams(1)
+    rs = ref.scene(scn)
+    try:
+        want, npass = rs.render(3, 11, 6, streams=4)
+    finally:
+        rs.close()
+    assert npass == 6 and _rel_rmse(a, want[..., :3]) <= 1e-3, _rel_rmse(a, want[..., :3])
+    assert _rel_rmse(a, one) > 1e-2                                        # a different sample set from the single-stream one
 
 
 def test_bad_arguments(layer):
