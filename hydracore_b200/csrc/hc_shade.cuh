@@ -5,8 +5,9 @@
 // file:line cited per function).  Formulas, operation order and — where it changes rounding — the C++ promotion of the
 // reference's unqualified math calls to double (see hc_math.cuh) are kept, so that the same random numbers give the same
 // path on the GPU and in the CPU oracle.  Supported: Lambert, Oren-Nayar, translucent Lambert, Phong, Blinn (Torrance-Sparrow), GGX (Heitz VNDF sampling +
-// multiscattering table), perfect mirror, GGX glass, thin glass, blend masks (simple / fresnel / sigmoid), emissive materials, normal maps; rectangular / disk / sphere
-// area lights, omni / spot point lights, directional lights, mesh and cylinder lights, sky domes (constant or textured); RGBA8 and float4 textures.
+// multiscattering table), anisotropic Beckmann / TRGGX (hc_microfacet.cuh), perfect mirror, GGX glass (+ multiscattering table), thin glass, blend masks
+// (simple / fresnel / sigmoid), emissive materials, normal maps; rectangular / disk area lights (spot cone, IES web), sphere lights, omni (IES web) / spot point
+// lights, directional lights, mesh and cylinder lights (also textured), sky domes (constant, textured, Perez: hc_perez.cuh); RGBA8, float4 and single-channel textures.
 // Everything else is rejected with an error at hc_pt_init (no silent fallback).
 #pragma once
 #include "hc_math.cuh"
@@ -1242,7 +1243,7 @@ HC_DEV float3 AreaLightIntensity(const float* L, float3 rayDir, bool eyeRay, con
   }
   return color;
 }
-// AreaLightSampleRev (clight.h:1180-1229), untextured, no IES / sky portal (rejected at init)
+// AreaLightSampleRev (clight.h:1180-1229), untextured, no sky portal (rejected at init)
 HC_DEV void AreaLightSampleRev(const float* L, float3 rands, float3 illum, const HcScene& s, HcShadowSample& out)
 {
   const float ox = rands.x*2.0f - 1.0f, oy = rands.y*2.0f - 1.0f;
@@ -1324,7 +1325,7 @@ HC_DEV void PointLightSampleRev(const float* L, float3 illum, const HcScene& s, 
   out.cosAtLight = 1.0f;
 }
 
-// ---- sky dome (clight.h:286-463, cfetch.h:258-296, cbidir.h:492-533), without the Perez model and without a secondary (AUX) sky.
+// ---- sky dome (clight.h:286-463, cfetch.h:258-296, cbidir.h:492-533): constant, textured or Perez (hc_perez.cuh); without a secondary (AUX) sky.
 // M_PI is the <cmath> double in the reference's host build; sin / cos / acos / atan2 resolve to the double functions (hc_math.cuh).
 #define HC_SKY_DOME_PDF_TABLE0  30
 #define HC_SKY_DOME_SAMPLER0    32
